@@ -1,0 +1,10 @@
+"""hunter_bipedal_control_b200 -- B200-native batched NMPC + WBC solve path for the Hunter biped (one hot path, not a port).
+
+Only what the path needs: ``csrc/`` (sm_100a CUDA kernels + the C ABI of include/hunter_b200.h) and ``api`` (ctypes binding and
+host-side mirrors of the reference's WbcBase / MPC_MRT_Interface calls). No CPU fallback exists.
+"""
+from .api import (Context, WeightedWbc, SqpMpc, HbReference, HbSolveInfo, HbConfig, HunterB200Error, load_library, EXPORTED_SYMBOLS,
+                  NX, NU, NQ, NJ, NWBC, INFO_DTYPE)
+
+__all__ = ["Context", "WeightedWbc", "SqpMpc", "HbReference", "HbSolveInfo", "HbConfig", "HunterB200Error", "load_library",
+           "EXPORTED_SYMBOLS", "NX", "NU", "NQ", "NJ", "NWBC", "INFO_DTYPE"]

@@ -1,0 +1,276 @@
+"""ctypes binding of libhunter_b200.so (C ABI in include/hunter_b200.h) and host-side mirrors of the reference operators.
+
+The product path has no CPU fallback: if the CUDA library is missing or no B200 is visible, every entry point raises.
+
+Mirrors of the reference interface for this path (same names / argument meaning / error behaviour):
+  * ``WeightedWbc.update(stateDesired, inputDesired, rbdStateMeasured, mode, period)``  -- legged_wbc/include/legged_wbc/WbcBase.h:43-44,
+    legged_wbc/src/WeightedWbc.cpp:18-66 (returns the 38-vector [qdd, F, tau]; on solver failure prints and re-uses the last solution).
+  * ``SqpMpc.advance / evaluatePolicy``  -- the calls legged_controllers/src/LeggedController.cpp:144-156,406 makes through MPC_MRT_Interface.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libhunter_b200.so")
+_lib = None
+
+NX, NU, NQ, NJ, NWBC = 22, 22, 16, 10, 38
+HB_MAX_EVENTS, HB_MAX_TARGETS, HB_MAX_SEGMENTS = 32, 8, 24
+
+EXPORTED_SYMBOLS = [
+    "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_launch_count", "hb_stream",
+    "hb_wbc_qp_batch_dev", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
+    "hb_policy_eval_batch_dev", "hb_control_step_batch_dev", "hb_rbd_to_centroidal_batch_dev", "hb_reference_expand_batch_dev",
+    "hb_probe_flow_map_dev",
+    "hb_wbc_qp_batch", "hb_wbc_solve_batch", "hb_mpc_cold_start_batch", "hb_mpc_solve_batch", "hb_control_step_batch",
+    "hb_rbd_to_centroidal_batch", "hb_reference_expand_batch", "hb_probe_flow_map",
+]
+
+
+class HbConfig(C.Structure):
+    _fields_ = [("horizon_N", C.c_int32), ("dt", C.c_double), ("max_batch", C.c_int32), ("wbc_rho", C.c_double),
+                ("qp_max_iter", C.c_int32), ("line_search_max_trials", C.c_int32)]
+
+
+class HbSolveInfo(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("merit0", C.c_double), ("merit1", C.c_double), ("viol0", C.c_double), ("viol1", C.c_double),
+                ("armijo", C.c_double), ("status", C.c_int32), ("n_trials", C.c_int32)]
+
+
+class HbReference(C.Structure):
+    _fields_ = [("n_events", C.c_int32), ("event_times", C.c_double * HB_MAX_EVENTS), ("modes", C.c_int32 * (HB_MAX_EVENTS + 1)),
+                ("n_targets", C.c_int32), ("target_times", C.c_double * HB_MAX_TARGETS), ("target_states", (C.c_double * 22) * HB_MAX_TARGETS),
+                ("n_segments", (C.c_int32 * 3) * 4), ("segments", (((C.c_double * 6) * HB_MAX_SEGMENTS) * 3) * 4)]
+
+
+INFO_DTYPE = np.dtype([("alpha", "f8"), ("merit0", "f8"), ("merit1", "f8"), ("viol0", "f8"), ("viol1", "f8"), ("armijo", "f8"),
+                       ("status", "i4"), ("n_trials", "i4")], align=True)
+assert INFO_DTYPE.itemsize == C.sizeof(HbSolveInfo)
+
+
+class HunterB200Error(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load libhunter_b200.so. Raises if the CUDA extension has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise HunterB200Error("libhunter_b200.so is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                  "(the product path has no CPU fallback)")
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.hb_strerror.restype = C.c_char_p
+        _lib.hb_launch_count.restype = C.c_int64
+        _lib.hb_stream.restype = C.c_void_p
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise HunterB200Error("%s failed: %s (%d)" % (what, load_library().hb_strerror(rc).decode(), rc))
+
+
+def _ptr(a):
+    """Pointer of a numpy array (host) or of a torch tensor (host or cuda)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """Owner of one hb_ctx (one GPU, one stream). Single-owner: use it from one thread at a time."""
+
+    def __init__(self, horizon_N=100, dt=0.01, max_batch=1024, device=0, wbc_rho=1e-8, qp_max_iter=40, line_search_max_trials=14):
+        lib = load_library()
+        cfg = HbConfig()
+        _check(lib.hb_default_config(C.byref(cfg)), "hb_default_config")
+        cfg.horizon_N, cfg.dt, cfg.max_batch, cfg.wbc_rho = horizon_N, dt, max_batch, wbc_rho
+        cfg.qp_max_iter, cfg.line_search_max_trials = qp_max_iter, line_search_max_trials
+        self.cfg = cfg
+        self.N, self.dt, self.max_batch, self.device = horizon_N, dt, max_batch, device
+        self._h = C.c_void_p()
+        _check(lib.hb_create(C.byref(cfg), C.c_int(device), C.byref(self._h)), "hb_create")
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.hb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _check(self._lib.hb_sync(self._h), "hb_sync")
+
+    @property
+    def launch_count(self):
+        return int(self._lib.hb_launch_count(self._h))
+
+    @property
+    def stream_handle(self):
+        return int(self._lib.hb_stream(self._h) or 0)
+
+    # ------------------------------------------------------------------ host-pointer calls (numpy in / numpy out)
+    def wbc_qp(self, H, g, A, lbA, ubA):
+        H, g, A, lbA, ubA = map(_f64, (H, g, A, lbA, ubA))
+        B, n = g.shape
+        m = lbA.shape[1]
+        x = np.zeros((B, n)); st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_wbc_qp_batch(self._h, B, n, m, _ptr(H), _ptr(g), _ptr(A), _ptr(lbA), _ptr(ubA), _ptr(x), _ptr(st), _ptr(it)), "hb_wbc_qp_batch")
+        return x, st, it
+
+    def wbc_solve(self, x_des, u_des, rbd, mode, stance_mode=None):
+        x_des, u_des, rbd = map(_f64, (x_des, u_des, rbd))
+        B = x_des.shape[0]
+        mode = np.ascontiguousarray(mode, dtype=np.int32)
+        sm = None if stance_mode is None else np.ascontiguousarray(stance_mode, dtype=np.uint8)
+        sol = np.zeros((B, NWBC)); st = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_wbc_solve_batch(self._h, B, _ptr(x_des), _ptr(u_des), _ptr(rbd), _ptr(mode), _ptr(sm), _ptr(sol), _ptr(st)), "hb_wbc_solve_batch")
+        return sol, st
+
+    def mpc_cold_start(self, x0, mode):
+        x0 = _f64(x0); B = x0.shape[0]
+        mode = np.ascontiguousarray(mode, dtype=np.int32)
+        xt = np.zeros((B, self.N + 1, NX)); ut = np.zeros((B, self.N, NU))
+        _check(self._lib.hb_mpc_cold_start_batch(self._h, B, _ptr(x0), _ptr(mode), _ptr(xt), _ptr(ut)), "hb_mpc_cold_start_batch")
+        return xt, ut
+
+    def mpc_solve(self, x0, x_ref, swing, mode, xt, ut):
+        x0, x_ref, swing = map(_f64, (x0, x_ref, swing))
+        B = x0.shape[0]
+        mode = np.ascontiguousarray(mode, dtype=np.int32)
+        xt = _f64(xt).copy(); ut = _f64(ut).copy()
+        info = np.zeros(B, dtype=INFO_DTYPE)
+        _check(self._lib.hb_mpc_solve_batch(self._h, B, _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(xt), _ptr(ut), _ptr(info)), "hb_mpc_solve_batch")
+        return xt, ut, info
+
+    def control_step(self, t_rel, x0, x_ref, swing, mode, rbd, xt, ut):
+        x0, x_ref, swing, rbd = map(_f64, (x0, x_ref, swing, rbd))
+        B = x0.shape[0]
+        mode = np.ascontiguousarray(mode, dtype=np.int32)
+        xt = _f64(xt).copy(); ut = _f64(ut).copy()
+        info = np.zeros(B, dtype=INFO_DTYPE)
+        sol = np.zeros((B, NWBC)); tau = np.zeros((B, NJ)); st = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_control_step_batch(self._h, B, C.c_double(t_rel), _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(rbd), _ptr(xt), _ptr(ut),
+                                               _ptr(info), _ptr(sol), _ptr(tau), _ptr(st)), "hb_control_step_batch")
+        return xt, ut, info, sol, tau, st
+
+    def rbd_to_centroidal(self, rbd):
+        rbd = _f64(rbd); B = rbd.shape[0]
+        x = np.zeros((B, NX))
+        _check(self._lib.hb_rbd_to_centroidal_batch(self._h, B, _ptr(rbd), _ptr(x)), "hb_rbd_to_centroidal_batch")
+        return x
+
+    def reference_expand(self, t0, refs):
+        """refs: ctypes array of HbReference (len B)."""
+        t0 = _f64(t0); B = t0.shape[0]
+        x_ref = np.zeros((B, self.N + 1, NX)); swing = np.zeros((B, self.N + 1, 24)); mode = np.zeros((B, self.N + 1), dtype=np.int32)
+        _check(self._lib.hb_reference_expand_batch(self._h, B, _ptr(t0), C.cast(refs, C.c_void_p), _ptr(x_ref), _ptr(swing), _ptr(mode)), "hb_reference_expand_batch")
+        return x_ref, swing, mode
+
+    def probe_flow_map(self, x, u):
+        x, u = _f64(x), _f64(u); B = x.shape[0]
+        f = np.zeros((B, NX)); A = np.zeros((B, NX, NX)); Bm = np.zeros((B, NX, NU)); ee = np.zeros((B, 24 + 36 * NX))
+        _check(self._lib.hb_probe_flow_map(self._h, B, _ptr(x), _ptr(u), _ptr(f), _ptr(A), _ptr(Bm), _ptr(ee)), "hb_probe_flow_map")
+        out = dict(f=f, A=A, B=Bm, epos=ee[:, :12], evel=ee[:, 12:24], dpos_dx=ee[:, 24:24 + 264].reshape(B, 12, NX),
+                   dvel_dx=ee[:, 24 + 264:24 + 528].reshape(B, 12, NX), dvel_du=ee[:, 24 + 528:].reshape(B, 12, NX))
+        return out
+
+    # ------------------------------------------------------------------ device-pointer calls (torch cuda tensors, asynchronous)
+    def mpc_solve_dev(self, x0, x_ref, swing, mode, xt, ut, info=None):
+        B = x0.shape[0]
+        _check(self._lib.hb_mpc_solve_batch_dev(self._h, B, _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(xt), _ptr(ut), _ptr(info)), "hb_mpc_solve_batch_dev")
+
+    def mpc_cold_start_dev(self, x0, mode, xt, ut):
+        _check(self._lib.hb_mpc_cold_start_batch_dev(self._h, x0.shape[0], _ptr(x0), _ptr(mode), _ptr(xt), _ptr(ut)), "hb_mpc_cold_start_batch_dev")
+
+    def wbc_solve_dev(self, x_des, u_des, rbd, mode, stance_mode, sol, status=None):
+        _check(self._lib.hb_wbc_solve_batch_dev(self._h, x_des.shape[0], _ptr(x_des), _ptr(u_des), _ptr(rbd), _ptr(mode), _ptr(stance_mode), _ptr(sol), _ptr(status)),
+               "hb_wbc_solve_batch_dev")
+
+    def wbc_qp_dev(self, n, m, H, g, A, lbA, ubA, x, status=None, iters=None):
+        _check(self._lib.hb_wbc_qp_batch_dev(self._h, g.shape[0], n, m, _ptr(H), _ptr(g), _ptr(A), _ptr(lbA), _ptr(ubA), _ptr(x), _ptr(status), _ptr(iters)),
+               "hb_wbc_qp_batch_dev")
+
+    def control_step_dev(self, t_rel, x0, x_ref, swing, mode, rbd, xt, ut, info, sol, tau, status=None):
+        _check(self._lib.hb_control_step_batch_dev(self._h, x0.shape[0], C.c_double(t_rel), _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(rbd), _ptr(xt),
+                                                   _ptr(ut), _ptr(info), _ptr(sol), _ptr(tau), _ptr(status)), "hb_control_step_batch_dev")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Host-side mirrors of the reference operators (single-robot use, B = 1), for drop-in style tests.
+class WeightedWbc:
+    """Mirror of legged::WeightedWbc (legged_wbc/include/legged_wbc/WeightedWbc.h, WbcBase.h:41-76)."""
+
+    def __init__(self, ctx=None):
+        self._ctx = ctx or Context(max_batch=1)
+        self._stance_mode = True      # WbcBase default until setStanceMode(false) (LeggedController.cpp:161-173)
+        self._last = None
+
+    def loadTasksSetting(self, taskFile=None, verbose=False):
+        """Gains are compiled in from task.info through include/hunter_model_constants.h (WbcBase.cpp:352-411)."""
+        return None
+
+    def setStanceMode(self, flag):
+        self._stance_mode = bool(flag)
+
+    def getContactForceSize(self):
+        return 12
+
+    def update(self, stateDesired, inputDesired, rbdStateMeasured, mode, period):
+        sol, st = self._ctx.wbc_solve(np.asarray(stateDesired)[None], np.asarray(inputDesired)[None], np.asarray(rbdStateMeasured)[None],
+                                      [int(mode)], [1 if self._stance_mode else 0])
+        x = sol[0]
+        if st[0] != 0:
+            print("ERROR: WeightWBC Not Solved!!!")          # WeightedWbc.cpp:57-62
+            if self._last is not None:
+                x = self._last
+        self._last = x.copy()
+        return x
+
+
+class SqpMpc:
+    """Mirror of the MPC_MRT_Interface calls the controller makes (LeggedController.cpp:144-156,406) on a batch of 1."""
+
+    def __init__(self, ctx=None, horizon_N=100, dt=0.01):
+        self._ctx = ctx or Context(horizon_N=horizon_N, dt=dt, max_batch=1)
+        self._xt = None
+        self._ut = None
+        self._mode = None
+
+    def reset(self):
+        self._xt = self._ut = None
+
+    def advance(self, x0, x_ref, swing, mode):
+        """One SQP iteration warm-started from the previous solution (mpc.coldStart false, task.info:146)."""
+        x0 = np.asarray(x0, dtype=np.float64)[None]
+        mode = np.asarray(mode, dtype=np.int32)[None]
+        if self._xt is None:
+            self._xt, self._ut = self._ctx.mpc_cold_start(x0, mode)
+        self._xt, self._ut, info = self._ctx.mpc_solve(x0, np.asarray(x_ref)[None], np.asarray(swing)[None], mode, self._xt, self._ut)
+        self._mode = mode
+        if info["status"][0] != 0:
+            raise HunterB200Error("[SqpMpc] numerical failure in the SQP iteration")   # the reference's MPC thread stops the controller (LeggedController.cpp:413-418)
+        return info[0]
+
+    def evaluatePolicy(self, t_rel):
+        s = min(max(t_rel / self._ctx.dt, 0.0), float(self._ctx.N))
+        k = min(int(np.floor(s)), self._ctx.N - 1)
+        al = s - k
+        x = (1 - al) * self._xt[0, k] + al * self._xt[0, k + 1]
+        k1 = min(k + 1, self._ctx.N - 1)
+        u = (1 - al) * self._ut[0, k] + al * self._ut[0, k1]
+        return x, u, int(self._mode[0, k])

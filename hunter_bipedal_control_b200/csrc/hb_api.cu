@@ -1,0 +1,620 @@
+// libhunter_b200.so -- C ABI (include/hunter_b200.h) over the sm_100a kernels. Host side: context, scratch, launches.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/hunter_b200.h"
+#include "hb_common.cuh"
+#include "hb_mpc.cuh"
+#include "hb_qp.cuh"
+#include "hb_rbd.cuh"
+#include "hb_wbc.cuh"
+
+using namespace hb;
+
+// ---------------------------------------------------------------------------------------------- kernels
+namespace {
+
+constexpr int QP_STRIDE_H = NWBC * NWBC, QP_STRIDE_A = WBC_ROWS * NWBC;
+
+// input cost R = blkdiag(R_f, J0' R_v J0) with J0 the contact Jacobian at initialState (LeggedInterface.cpp:263-288)
+__global__ void init_input_cost_kernel(double* Rout) {
+  __shared__ double J0[12 * 16];
+  const int lane = threadIdx.x;
+  if (lane < 16) {
+    double q[NQ], e[NQ];
+    const double q0[NQ] = {HB_INITIAL_STATE[6], HB_INITIAL_STATE[7], HB_INITIAL_STATE[8], HB_INITIAL_STATE[9], HB_INITIAL_STATE[10], HB_INITIAL_STATE[11],
+                           HB_INITIAL_STATE[12], HB_INITIAL_STATE[13], HB_INITIAL_STATE[14], HB_INITIAL_STATE[15], HB_INITIAL_STATE[16], HB_INITIAL_STATE[17],
+                           HB_INITIAL_STATE[18], HB_INITIAL_STATE[19], HB_INITIAL_STATE[20], HB_INITIAL_STATE[21]};
+    for (int i = 0; i < NQ; ++i) { q[i] = q0[i]; e[i] = (i == lane) ? 1.0 : 0.0; }
+    KinOut<double> o;
+    kin_pass<double>(q, e, o);
+    for (int r = 0; r < 12; ++r) J0[r * 16 + lane] = o.cvel[r];
+  }
+  __syncthreads();
+  const double rts[24] = {HB_R_TASKSPACE_DIAG[0], HB_R_TASKSPACE_DIAG[1], HB_R_TASKSPACE_DIAG[2], HB_R_TASKSPACE_DIAG[3], HB_R_TASKSPACE_DIAG[4], HB_R_TASKSPACE_DIAG[5],
+                          HB_R_TASKSPACE_DIAG[6], HB_R_TASKSPACE_DIAG[7], HB_R_TASKSPACE_DIAG[8], HB_R_TASKSPACE_DIAG[9], HB_R_TASKSPACE_DIAG[10], HB_R_TASKSPACE_DIAG[11],
+                          HB_R_TASKSPACE_DIAG[12], HB_R_TASKSPACE_DIAG[13], HB_R_TASKSPACE_DIAG[14], HB_R_TASKSPACE_DIAG[15], HB_R_TASKSPACE_DIAG[16], HB_R_TASKSPACE_DIAG[17],
+                          HB_R_TASKSPACE_DIAG[18], HB_R_TASKSPACE_DIAG[19], HB_R_TASKSPACE_DIAG[20], HB_R_TASKSPACE_DIAG[21], HB_R_TASKSPACE_DIAG[22], HB_R_TASKSPACE_DIAG[23]};
+  for (int idx = lane; idx < NU * NU; idx += 32) {
+    const int i = idx / NU, j = idx - i * NU;
+    double v = 0.0;
+    if (i < 12 && i == j) v = rts[i];
+    if (i >= 12 && j >= 12) for (int r = 0; r < 12; ++r) v += J0[r * 16 + 6 + i - 12] * rts[12 + r] * J0[r * 16 + 6 + j - 12];
+    Rout[idx] = v;
+  }
+}
+
+__global__ void qp_batch_kernel(int B, int n, int m, const double* H, const double* g, const double* A, const double* lbA, const double* ubA,
+                                size_t strideH, size_t strideA, size_t strideB, const int32_t* m_per, double rho, int max_iter, double* x,
+                                int32_t* status, int32_t* iters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int inst = blockIdx.x * wpb + warp;
+  if (inst >= B) return;
+  double* base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * qp_workspace_doubles(n);
+  QpWorkspace w;
+  qp_carve(base, n, w);
+  const int mi = m_per ? m_per[inst] : m;
+  QpResult r = qp_solve_warp(n, mi, H + inst * strideH, g + (size_t)inst * n, A + inst * strideA, lbA + inst * strideB, ubA + inst * strideB,
+                             rho, max_iter, x + (size_t)inst * n, w);
+  if (lane_id() == 0) { if (status) status[inst] = r.status; if (iters) iters[inst] = r.iters; }
+}
+
+__global__ void wbc_assemble_kernel(int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                                    const uint8_t* stance_mode, double* H, double* g, double* A, double* lbA, double* ubA, int32_t* m_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int inst = blockIdx.x * wpb + warp;
+  if (inst >= B) return;
+  WbcShared& sh = reinterpret_cast<WbcShared*>(smem_raw)[warp];
+  const int m = wbc_assemble_warp(x_des + (size_t)inst * NX, u_des + (size_t)inst * NU, rbd + (size_t)inst * 32, mode[inst],
+                                  stance_mode ? stance_mode[inst] != 0 : false, sh, H + (size_t)inst * QP_STRIDE_H, g + (size_t)inst * NWBC,
+                                  A + (size_t)inst * QP_STRIDE_A, lbA + (size_t)inst * WBC_ROWS, ubA + (size_t)inst * WBC_ROWS);
+  if (lane_id() == 0) m_out[inst] = m;
+}
+
+// LeggedRobotInitializer::compute (initialization/LeggedRobotInitializer.cpp:67-77)
+__global__ void cold_start_kernel(int B, int N, const double* x0, const int32_t* mode, double* xt, double* ut) {
+  const int inst = blockIdx.x;
+  const double* x = x0 + (size_t)inst * NX;
+  for (int idx = threadIdx.x; idx < (N + 1) * NX; idx += blockDim.x) xt[(size_t)inst * (N + 1) * NX + idx] = x[idx % NX];
+  for (int idx = threadIdx.x; idx < N * NU; idx += blockDim.x) {
+    const int k = idx / NU, j = idx - k * NU;
+    const int md = mode[(size_t)inst * (N + 1) + k];
+    int ns = 0;
+    for (int c = 0; c < 4; ++c) ns += contact_flag(md, c);
+    double v = 0.0;
+    if (j < 12 && (j % 3) == 2 && contact_flag(md, j / 3)) v = c_model.total_mass * HB_GRAVITY / ns;
+    ut[(size_t)inst * N * NU + idx] = v;
+  }
+}
+
+// MPC_MRT_Interface::evaluatePolicy with the feed-forward policy (LeggedController.cpp:154-156, task.info:93):
+// linear interpolation of the state / input trajectories at t0 + t_rel; mode = mode in force at that time.
+__global__ void policy_eval_kernel(int B, int N, double dt, double t_rel, const double* xt, const double* ut, const int32_t* mode, double* x_des,
+                                   double* u_des, int32_t* mode_out) {
+  const int inst = blockIdx.x * blockDim.x / 32 + (threadIdx.x >> 5);
+  if (inst >= B) return;
+  const int lane = threadIdx.x & 31;
+  double s = t_rel / dt;
+  if (s < 0.0) s = 0.0;
+  if (s > (double)N) s = (double)N;
+  int k = (int)floor(s);
+  if (k >= N) k = N - 1;
+  const double al = s - k;
+  const double* x = xt + (size_t)inst * (N + 1) * NX;
+  const double* u = ut + (size_t)inst * N * NU;
+  if (lane < NX) {
+    x_des[(size_t)inst * NX + lane] = (1.0 - al) * x[k * NX + lane] + al * x[(k + 1) * NX + lane];
+    const int k1 = (k + 1 < N) ? k + 1 : N - 1;   // the input trajectory repeats its last sample at the final node
+    u_des[(size_t)inst * NU + lane] = (1.0 - al) * u[k * NU + lane] + al * u[k1 * NU + lane];
+  }
+  if (lane == 0 && mode_out) mode_out[inst] = mode[(size_t)inst * (N + 1) + k];
+}
+
+// torque law (LeggedController.cpp:181-184): feed-forward joint torques = tail(10) of the WBC solution
+__global__ void torque_kernel(int B, const double* sol, double* torque) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < B * NJ) { const int i = idx / NJ, j = idx - i * NJ; torque[idx] = sol[(size_t)i * NWBC + 28 + j]; }
+}
+
+// computeCentroidalStateFromRbdModel (LeggedController.cpp:336)
+__global__ void rbd_to_centroidal_kernel(int B, const double* rbd, double* x) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= B) return;
+  const double* r = rbd + (size_t)inst * 32;
+  double q[NQ], v[NQ];
+  for (int i = 0; i < 3; ++i) { q[i] = r[3 + i]; q[3 + i] = r[i]; v[i] = r[NQ + 3 + i]; }
+  for (int j = 0; j < NJ; ++j) { q[6 + j] = r[6 + j]; v[6 + j] = r[NQ + 6 + j]; }
+  double sz, cz, sy, cy;
+  sincos(q[3], &sz, &cz); sincos(q[4], &sy, &cy);
+  const double dxr = (cz * r[NQ] + sz * r[NQ + 1]) / cy;
+  v[5] = dxr; v[4] = -sz * r[NQ] + cz * r[NQ + 1]; v[3] = r[NQ + 2] + sy * dxr;
+  KinOut<double> o;
+  kin_pass<double>(q, v, o);
+  for (int i = 0; i < 6; ++i) x[(size_t)inst * NX + i] = o.h[i] / c_model.total_mass;
+  for (int i = 0; i < NQ; ++i) x[(size_t)inst * NX + 6 + i] = q[i];
+}
+
+// Expansion of the compact reference description onto the node grid (SwitchedModelReferenceManager::modifyReferences
+// products evaluated where the solver needs them: TargetTrajectories::getDesiredState, ModeSchedule::modeAtTime,
+// SwingTrajectoryPlanner::get{X,Y,Z}{position,velocity}Constraint; CubicSpline.cpp:46-124).
+__global__ void reference_expand_kernel(int B, int N, double dt, const double* t0, const hb_reference* refs, double* x_ref, double* swing,
+                                        int32_t* mode) {
+  const int inst = blockIdx.x;
+  const hb_reference& rf = refs[inst];
+  for (int k = threadIdx.x; k <= N; k += blockDim.x) {
+    const double t = t0[inst] + k * dt;
+    // mode in force on the interval starting at t (post-event mode when t coincides with an event)
+    int idx = 0;
+    while (idx < rf.n_events && rf.event_times[idx] <= t + 1e-9) ++idx;
+    mode[(size_t)inst * (N + 1) + k] = rf.modes[idx];
+    // target state: linear interpolation, clamped
+    double* xr = x_ref + ((size_t)inst * (N + 1) + k) * NX;
+    if (rf.n_targets <= 1 || t <= rf.target_times[0]) { for (int i = 0; i < NX; ++i) xr[i] = rf.target_states[0][i]; }
+    else if (t >= rf.target_times[rf.n_targets - 1]) { for (int i = 0; i < NX; ++i) xr[i] = rf.target_states[rf.n_targets - 1][i]; }
+    else {
+      int s = 0;
+      while (s + 2 < rf.n_targets && rf.target_times[s + 1] <= t) ++s;
+      const double al = (t - rf.target_times[s]) / (rf.target_times[s + 1] - rf.target_times[s]);
+      for (int i = 0; i < NX; ++i) xr[i] = (1.0 - al) * rf.target_states[s][i] + al * rf.target_states[s + 1][i];
+    }
+    // swing references: cubic Hermite segments
+    double* sw = swing + ((size_t)inst * (N + 1) + k) * 24;
+    for (int c = 0; c < 4; ++c)
+      for (int a = 0; a < 3; ++a) {
+        const int ns = rf.n_segments[c][a];
+        double pos = 0.0, vel = 0.0;
+        if (ns > 0) {
+          int s = 0;
+          while (s + 1 < ns && t >= rf.segments[c][a][s][1]) ++s;
+          const double* sg = rf.segments[c][a][s];
+          const double T = sg[1] - sg[0], tn = (t - sg[0]) / T;
+          const double dp = sg[4] - sg[2], dvv = sg[5] - sg[3];
+          const double c0 = sg[2], c1 = sg[3] * T, c2 = -(3.0 * sg[3] + dvv) * T + 3.0 * dp, c3 = (2.0 * sg[3] + dvv) * T - 2.0 * dp;
+          pos = ((c3 * tn + c2) * tn + c1) * tn + c0;
+          vel = ((3.0 * c3 * tn + 2.0 * c2) * tn + c1) / T;
+        }
+        sw[6 * c + a] = pos; sw[6 * c + 3 + a] = vel;
+      }
+  }
+}
+
+// parity probe: flow map value, Jacobians and contact kinematics from the warp-cooperative linearisation
+__global__ void __launch_bounds__(32) probe_flow_map_kernel(int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MpcShared& sh = *reinterpret_cast<MpcShared*>(smem_raw);
+  const int inst = blockIdx.x, lane = threadIdx.x;
+  if (lane < NX) { sh.x[lane] = x[(size_t)inst * NX + lane]; sh.u[lane] = u[(size_t)inst * NU + lane]; }
+  __syncwarp();
+  flow_lin_warp(sh, sh.x, sh.f1, sh.A1, sh.B1, true);
+  if (lane < NX) f[(size_t)inst * NX + lane] = sh.f1[lane];
+  for (int idx = lane; idx < TS; idx += 32) { A[(size_t)inst * TS + idx] = sh.A1[idx]; Bm[(size_t)inst * TS + idx] = sh.B1[idx]; }
+  if (ee) {
+    double* o = ee + (size_t)inst * (24 + 3 * 12 * NX);
+    if (lane < 12) { o[lane] = sh.epos[lane]; o[12 + lane] = sh.evel[lane]; }
+    for (int idx = lane; idx < 3 * 12 * NX; idx += 32) o[24 + idx] = sh.EJ[idx];
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- context
+struct hb_ctx {
+  hb_config cfg;
+  int device;
+  cudaStream_t stream;
+  int64_t launches;
+  // MPC scratch
+  double *gains, *dxt, *dut, *perf;
+  int32_t* flags;
+  // WBC scratch
+  double *qH, *qg, *qA, *qlb, *qub, *xdes, *udes, *wsol;
+  int32_t *qm, *wstatus, *witers, *wmode;
+  // staging for host-pointer calls
+  double *s_x0, *s_xref, *s_swing, *s_xt, *s_ut, *s_rbd, *s_xd, *s_ud, *s_sol, *s_tau, *s_t0, *s_misc;
+  int32_t *s_mode, *s_imode, *s_status, *s_iters;
+  uint8_t* s_stance;
+  hb_solve_info* s_info;
+  hb_reference* s_refs;
+  double *s_qpH, *s_qpA;   // generic QP staging (sized on demand)
+  size_t s_qp_cap;
+  int last_cuda;
+};
+
+namespace {
+
+enum { HB_OK = 0, HB_EINVAL = -1, HB_ECUDA = -2, HB_ENOMEM = -3, HB_ECAP = -4 };
+
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t e__ = (call);                      \
+    if (e__ != cudaSuccess) { if (ctx) ctx->last_cuda = (int)e__; return HB_ECUDA; } \
+  } while (0)
+
+template <class T> cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
+
+int set_device(hb_ctx* ctx) { return cudaSetDevice(ctx->device) == cudaSuccess ? HB_OK : HB_ECUDA; }
+
+}  // namespace
+
+extern "C" {
+
+int hb_default_config(hb_config* cfg) {
+  if (!cfg) return HB_EINVAL;
+  cfg->horizon_N = 100;
+  cfg->dt = 0.01;
+  cfg->max_batch = 1024;
+  cfg->wbc_rho = 1e-8;
+  cfg->qp_max_iter = 40;
+  cfg->line_search_max_trials = 14;
+  return HB_OK;
+}
+
+const char* hb_strerror(int code) {
+  switch (code) {
+    case HB_OK: return "ok";
+    case HB_EINVAL: return "invalid argument";
+    case HB_ECUDA: return "CUDA error";
+    case HB_ENOMEM: return "out of memory";
+    case HB_ECAP: return "batch exceeds context capacity";
+    default: return "unknown error";
+  }
+}
+
+int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
+  if (!cfg || !out || cfg->horizon_N < 1 || cfg->horizon_N > 4096 || cfg->max_batch < 1 || !(cfg->dt > 0.0)) return HB_EINVAL;
+  hb_ctx* ctx = new (std::nothrow) hb_ctx();
+  if (!ctx) return HB_ENOMEM;
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->cfg = *cfg;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return HB_ECUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HB_ECUDA; }
+  // model constants
+  Model* m = new Model();
+  memset(m, 0, sizeof(Model));
+  for (int b = 0; b < NBODY; ++b) {
+    for (int i = 0; i < 3; ++i) { m->joint_xyz[3 * b + i] = HB_JOINT_XYZ[3 * b + i]; m->com[3 * b + i] = HB_BODY_COM[3 * b + i]; }
+    for (int i = 0; i < 9; ++i) m->inertia[9 * b + i] = HB_BODY_INERTIA[9 * b + i];
+    m->mass[b] = HB_BODY_MASS[b];
+    int code = 0;
+    for (int i = 0; i < 3; ++i) if (HB_JOINT_AXIS[3 * b + i] != 0.0) code = (HB_JOINT_AXIS[3 * b + i] > 0 ? 1 : -1) * (i + 1);
+    m->joint_axis[b] = code;
+  }
+  m->total_mass = HB_TOTAL_MASS;
+  for (int i = 0; i < 12; ++i) m->contact_offset[i] = HB_CONTACT_OFFSET[i];
+  for (int j = 0; j < NJ; ++j) { m->joint_lower[j] = HB_JOINT_LOWER[j]; m->joint_upper[j] = HB_JOINT_UPPER[j]; m->joint_vel_limit[j] = HB_JOINT_VEL_LIMIT[j]; m->torque_limit[j] = HB_WBC_TORQUE_LIMITS[j % 5]; }
+  for (int i = 0; i < NX; ++i) m->Q[i] = HB_Q_DIAG[i];
+  cudaError_t e = cudaMemcpyToSymbol(c_model, m, sizeof(Model));
+  if (e == cudaSuccess) {
+    double* dR = nullptr;
+    e = dalloc(&dR, NU * NU);
+    if (e == cudaSuccess) {
+      init_input_cost_kernel<<<1, 32, 0, ctx->stream>>>(dR);
+      e = cudaStreamSynchronize(ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpy(m->R, dR, sizeof(double) * NU * NU, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_model, m, sizeof(Model));
+      cudaFree(dR);
+    }
+  }
+  delete m;
+  if (e != cudaSuccess) { ctx->last_cuda = (int)e; hb_destroy(ctx); return HB_ECUDA; }
+  const size_t B = cfg->max_batch, N = cfg->horizon_N;
+  bool ok = true;
+  ok = ok && dalloc(&ctx->gains, B * N * GAIN_STRIDE) == cudaSuccess;
+  ok = ok && dalloc(&ctx->dxt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->dut, B * N * NU) == cudaSuccess;
+  ok = ok && dalloc(&ctx->perf, B * 4) == cudaSuccess && dalloc(&ctx->flags, B) == cudaSuccess;
+  ok = ok && dalloc(&ctx->qH, B * QP_STRIDE_H) == cudaSuccess && dalloc(&ctx->qg, B * NWBC) == cudaSuccess && dalloc(&ctx->qA, B * QP_STRIDE_A) == cudaSuccess;
+  ok = ok && dalloc(&ctx->qlb, B * WBC_ROWS) == cudaSuccess && dalloc(&ctx->qub, B * WBC_ROWS) == cudaSuccess && dalloc(&ctx->qm, B) == cudaSuccess;
+  ok = ok && dalloc(&ctx->xdes, B * NX) == cudaSuccess && dalloc(&ctx->udes, B * NU) == cudaSuccess && dalloc(&ctx->wsol, B * NWBC) == cudaSuccess;
+  ok = ok && dalloc(&ctx->wstatus, B) == cudaSuccess && dalloc(&ctx->witers, B) == cudaSuccess && dalloc(&ctx->wmode, B) == cudaSuccess;
+  ok = ok && dalloc(&ctx->s_x0, B * NX) == cudaSuccess && dalloc(&ctx->s_xref, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_swing, B * (N + 1) * 24) == cudaSuccess;
+  ok = ok && dalloc(&ctx->s_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->s_rbd, B * 32) == cudaSuccess;
+  ok = ok && dalloc(&ctx->s_xd, B * NX) == cudaSuccess && dalloc(&ctx->s_ud, B * NU) == cudaSuccess && dalloc(&ctx->s_sol, B * NWBC) == cudaSuccess;
+  ok = ok && dalloc(&ctx->s_tau, B * NJ) == cudaSuccess && dalloc(&ctx->s_t0, B) == cudaSuccess && dalloc(&ctx->s_misc, B * (size_t)(NX + 2 * TS + 24 + 36 * NX)) == cudaSuccess;
+  ok = ok && dalloc(&ctx->s_mode, B * (N + 1)) == cudaSuccess && dalloc(&ctx->s_imode, B) == cudaSuccess && dalloc(&ctx->s_status, B) == cudaSuccess && dalloc(&ctx->s_iters, B) == cudaSuccess;
+  ok = ok && dalloc(&ctx->s_stance, B) == cudaSuccess && dalloc(&ctx->s_info, B) == cudaSuccess && dalloc(&ctx->s_refs, B) == cudaSuccess;
+  if (!ok) { hb_destroy(ctx); return HB_ENOMEM; }
+  cudaFuncSetAttribute(mpc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MpcShared));
+  cudaFuncSetAttribute(probe_flow_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MpcShared));
+  cudaFuncSetAttribute(mpc_forward_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsShared));
+  cudaFuncSetAttribute(qp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  *out = ctx;
+  return HB_OK;
+}
+
+int hb_destroy(hb_ctx* ctx) {
+  if (!ctx) return HB_EINVAL;
+  cudaSetDevice(ctx->device);
+  void* ptrs[] = {ctx->gains, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->qH, ctx->qg, ctx->qA, ctx->qlb, ctx->qub, ctx->qm, ctx->xdes, ctx->udes,
+                  ctx->wsol, ctx->wstatus, ctx->witers, ctx->wmode, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_xt, ctx->s_ut, ctx->s_rbd, ctx->s_xd,
+                  ctx->s_ud, ctx->s_sol, ctx->s_tau, ctx->s_t0, ctx->s_misc, ctx->s_mode, ctx->s_imode, ctx->s_status, ctx->s_iters, ctx->s_stance,
+                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return HB_OK;
+}
+
+int hb_sync(hb_ctx* ctx) {
+  if (!ctx) return HB_EINVAL;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HB_OK;
+}
+int64_t hb_launch_count(const hb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* hb_stream(hb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------ device-pointer entry points
+static int launch_qp(hb_ctx* ctx, int B, int n, int m, const double* H, const double* g, const double* A, const double* lbA, const double* ubA,
+                     size_t sH, size_t sA, size_t sB, const int32_t* m_per, double* x, int32_t* status, int32_t* iters) {
+  if (n < 1 || n > QP_MAX_N || m < 0 || m > QP_MAX_M) return HB_EINVAL;
+  const size_t per_warp = qp_workspace_doubles(n) * sizeof(double);
+  int wpb = (int)((200 * 1024) / per_warp);
+  if (wpb < 1) return HB_EINVAL;
+  if (wpb > 1) wpb = 1;   // one warp per CTA: the shared-memory footprint, not the thread count, bounds residency
+  const int blocks = (B + wpb - 1) / wpb;
+  qp_batch_kernel<<<blocks, 32 * wpb, per_warp * wpb, ctx->stream>>>(B, n, m, H, g, A, lbA, ubA, sH, sA, sB, m_per, ctx->cfg.wbc_rho,
+                                                                     ctx->cfg.qp_max_iter, x, status, iters);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_wbc_qp_batch_dev(hb_ctx* ctx, int B, int n, int m, const double* H, const double* g, const double* A, const double* lbA,
+                        const double* ubA, double* x, int32_t* status, int32_t* iters) {
+  if (!ctx || B < 0 || !H || !g || !A || !lbA || !ubA || !x) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  return launch_qp(ctx, B, n, m, H, g, A, lbA, ubA, (size_t)n * n, (size_t)m * n, (size_t)m, nullptr, x, status, iters);
+}
+
+int hb_wbc_solve_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                           const uint8_t* stance_mode, double* sol, int32_t* status) {
+  if (!ctx || B < 0 || !x_des || !u_des || !rbd || !mode || !sol) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  const int wpb = 4;
+  wbc_assemble_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, sizeof(WbcShared) * wpb, ctx->stream>>>(B, x_des, u_des, rbd, mode, stance_mode, ctx->qH, ctx->qg,
+                                                                                               ctx->qA, ctx->qlb, ctx->qub, ctx->qm);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return launch_qp(ctx, B, NWBC, WBC_ROWS, ctx->qH, ctx->qg, ctx->qA, ctx->qlb, ctx->qub, QP_STRIDE_H, QP_STRIDE_A, WBC_ROWS, ctx->qm, sol,
+                   status ? status : ctx->wstatus, ctx->witers);
+}
+
+int hb_mpc_cold_start_batch_dev(hb_ctx* ctx, int B, const double* x0, const int32_t* mode, double* x_traj, double* u_traj) {
+  if (!ctx || B < 0 || !x0 || !mode || !x_traj || !u_traj) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  cold_start_kernel<<<B, 128, 0, ctx->stream>>>(B, ctx->cfg.horizon_N, x0, mode, x_traj, u_traj);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
+                           double* x_traj, double* u_traj, hb_solve_info* info) {
+  if (!ctx || B < 0 || !x0 || !x_ref || !swing_ref || !mode || !x_traj || !u_traj) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  MpcArgs a;
+  a.B = B; a.N = ctx->cfg.horizon_N; a.dt = ctx->cfg.dt; a.x_ref = x_ref; a.swing = swing_ref; a.mode = mode; a.xt = x_traj; a.ut = u_traj;
+  a.gains = ctx->gains; a.dxt = ctx->dxt; a.dut = ctx->dut; a.perf = ctx->perf; a.flags = ctx->flags; a.x0 = x0;
+  mpc_backward_kernel<<<B, 32, sizeof(MpcShared), ctx->stream>>>(a);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  mpc_forward_linesearch_kernel<<<B, 32, sizeof(LsShared), ctx->stream>>>(a, ctx->cfg.line_search_max_trials, info);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_policy_eval_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x_traj, const double* u_traj, const int32_t* mode, double* x_des,
+                             double* u_des, int32_t* mode_out) {
+  if (!ctx || B < 0 || !x_traj || !u_traj || !mode || !x_des || !u_des) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  const int wpb = 4;
+  policy_eval_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, 0, ctx->stream>>>(B, ctx->cfg.horizon_N, ctx->cfg.dt, t_rel, x_traj, u_traj, mode, x_des, u_des, mode_out);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
+                              const double* rbd, double* x_traj, double* u_traj, hb_solve_info* info, double* wbc_sol, double* torque,
+                              int32_t* wbc_status) {
+  if (!ctx || !rbd || !wbc_sol) return HB_EINVAL;
+  int rc = hb_mpc_solve_batch_dev(ctx, B, x0, x_ref, swing_ref, mode, x_traj, u_traj, info);
+  if (rc) return rc;
+  if (B == 0) return HB_OK;
+  rc = hb_policy_eval_batch_dev(ctx, B, t_rel, x_traj, u_traj, mode, ctx->xdes, ctx->udes, ctx->wmode);
+  if (rc) return rc;
+  rc = hb_wbc_solve_batch_dev(ctx, B, ctx->xdes, ctx->udes, rbd, ctx->wmode, nullptr, wbc_sol, wbc_status);
+  if (rc) return rc;
+  if (torque) {
+    torque_kernel<<<(B * NJ + 127) / 128, 128, 0, ctx->stream>>>(B, wbc_sol, torque);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  return HB_OK;
+}
+
+int hb_rbd_to_centroidal_batch_dev(hb_ctx* ctx, int B, const double* rbd, double* x) {
+  if (!ctx || B < 0 || !rbd || !x) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  rbd_to_centroidal_kernel<<<(B + 63) / 64, 64, 0, ctx->stream>>>(B, rbd, x);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_reference_expand_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref, int32_t* mode) {
+  if (!ctx || B < 0 || !t0 || !refs || !x_ref || !swing_ref || !mode) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  reference_expand_kernel<<<B, 128, 0, ctx->stream>>>(B, ctx->cfg.horizon_N, ctx->cfg.dt, t0, refs, x_ref, swing_ref, mode);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_probe_flow_map_dev(hb_ctx* ctx, int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee) {
+  if (!ctx || B < 0 || !x || !u || !f || !A || !Bm) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  probe_flow_map_kernel<<<B, 32, sizeof(MpcShared), ctx->stream>>>(B, x, u, f, A, Bm, ee);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ host-pointer entry points
+#define H2D(dst, src, n) CK(cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, ctx->stream))
+#define D2H(dst, src, n) CK(cudaMemcpyAsync(dst, src, (n), cudaMemcpyDeviceToHost, ctx->stream))
+
+int hb_wbc_qp_batch(hb_ctx* ctx, int B, int n, int m, const double* H, const double* g, const double* A, const double* lbA, const double* ubA,
+                    double* x, int32_t* status, int32_t* iters) {
+  if (!ctx || B < 0 || !H || !g || !A || !lbA || !ubA || !x) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (n < 1 || n > QP_MAX_N || m < 0 || m > QP_MAX_M) return HB_EINVAL;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t need = (size_t)B * ((size_t)n * n + (size_t)m * n + 3 * (size_t)n + 2 * (size_t)m + 2);
+  if (need > ctx->s_qp_cap) {
+    if (ctx->s_qpH) cudaFree(ctx->s_qpH);
+    ctx->s_qpH = nullptr; ctx->s_qp_cap = 0;
+    CK(dalloc(&ctx->s_qpH, need));
+    ctx->s_qp_cap = need;
+  }
+  double* dH = ctx->s_qpH; double* dA = dH + (size_t)B * n * n; double* dg = dA + (size_t)B * m * n; double* dlb = dg + (size_t)B * n;
+  double* dub = dlb + (size_t)B * m; double* dx = dub + (size_t)B * m; int32_t* dst = reinterpret_cast<int32_t*>(dx + (size_t)B * n); int32_t* dit = dst + B;
+  H2D(dH, H, sizeof(double) * B * n * n); H2D(dA, A, sizeof(double) * B * m * n); H2D(dg, g, sizeof(double) * B * n);
+  H2D(dlb, lbA, sizeof(double) * B * m); H2D(dub, ubA, sizeof(double) * B * m);
+  int rc = hb_wbc_qp_batch_dev(ctx, B, n, m, dH, dg, dA, dlb, dub, dx, dst, dit);
+  if (rc) return rc;
+  D2H(x, dx, sizeof(double) * B * n);
+  if (status) D2H(status, dst, sizeof(int32_t) * B);
+  if (iters) D2H(iters, dit, sizeof(int32_t) * B);
+  return hb_sync(ctx);
+}
+
+int hb_wbc_solve_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                       const uint8_t* stance_mode, double* sol, int32_t* status) {
+  if (!ctx || B < 0 || !x_des || !u_des || !rbd || !mode || !sol) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  H2D(ctx->s_xd, x_des, sizeof(double) * B * NX); H2D(ctx->s_ud, u_des, sizeof(double) * B * NU); H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32);
+  H2D(ctx->s_imode, mode, sizeof(int32_t) * B);
+  if (stance_mode) H2D(ctx->s_stance, stance_mode, B);
+  int rc = hb_wbc_solve_batch_dev(ctx, B, ctx->s_xd, ctx->s_ud, ctx->s_rbd, ctx->s_imode, stance_mode ? ctx->s_stance : nullptr, ctx->s_sol, ctx->s_status);
+  if (rc) return rc;
+  D2H(sol, ctx->s_sol, sizeof(double) * B * NWBC);
+  if (status) D2H(status, ctx->s_status, sizeof(int32_t) * B);
+  return hb_sync(ctx);
+}
+
+int hb_mpc_cold_start_batch(hb_ctx* ctx, int B, const double* x0, const int32_t* mode, double* x_traj, double* u_traj) {
+  if (!ctx || B < 0 || !x0 || !mode || !x_traj || !u_traj) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t N = ctx->cfg.horizon_N;
+  H2D(ctx->s_x0, x0, sizeof(double) * B * NX); H2D(ctx->s_mode, mode, sizeof(int32_t) * B * (N + 1));
+  int rc = hb_mpc_cold_start_batch_dev(ctx, B, ctx->s_x0, ctx->s_mode, ctx->s_xt, ctx->s_ut);
+  if (rc) return rc;
+  D2H(x_traj, ctx->s_xt, sizeof(double) * B * (N + 1) * NX); D2H(u_traj, ctx->s_ut, sizeof(double) * B * N * NU);
+  return hb_sync(ctx);
+}
+
+int hb_mpc_solve_batch(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode, double* x_traj,
+                       double* u_traj, hb_solve_info* info) {
+  if (!ctx || B < 0 || !x0 || !x_ref || !swing_ref || !mode || !x_traj || !u_traj) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t N = ctx->cfg.horizon_N;
+  H2D(ctx->s_x0, x0, sizeof(double) * B * NX); H2D(ctx->s_xref, x_ref, sizeof(double) * B * (N + 1) * NX);
+  H2D(ctx->s_swing, swing_ref, sizeof(double) * B * (N + 1) * 24); H2D(ctx->s_mode, mode, sizeof(int32_t) * B * (N + 1));
+  H2D(ctx->s_xt, x_traj, sizeof(double) * B * (N + 1) * NX); H2D(ctx->s_ut, u_traj, sizeof(double) * B * N * NU);
+  int rc = hb_mpc_solve_batch_dev(ctx, B, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_mode, ctx->s_xt, ctx->s_ut, ctx->s_info);
+  if (rc) return rc;
+  D2H(x_traj, ctx->s_xt, sizeof(double) * B * (N + 1) * NX); D2H(u_traj, ctx->s_ut, sizeof(double) * B * N * NU);
+  if (info) D2H(info, ctx->s_info, sizeof(hb_solve_info) * B);
+  return hb_sync(ctx);
+}
+
+int hb_control_step_batch(hb_ctx* ctx, int B, double t_rel, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
+                          const double* rbd, double* x_traj, double* u_traj, hb_solve_info* info, double* wbc_sol, double* torque,
+                          int32_t* wbc_status) {
+  if (!ctx || B < 0 || !x0 || !x_ref || !swing_ref || !mode || !rbd || !x_traj || !u_traj) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t N = ctx->cfg.horizon_N;
+  H2D(ctx->s_x0, x0, sizeof(double) * B * NX); H2D(ctx->s_xref, x_ref, sizeof(double) * B * (N + 1) * NX);
+  H2D(ctx->s_swing, swing_ref, sizeof(double) * B * (N + 1) * 24); H2D(ctx->s_mode, mode, sizeof(int32_t) * B * (N + 1));
+  H2D(ctx->s_xt, x_traj, sizeof(double) * B * (N + 1) * NX); H2D(ctx->s_ut, u_traj, sizeof(double) * B * N * NU);
+  H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32);
+  int rc = hb_control_step_batch_dev(ctx, B, t_rel, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_mode, ctx->s_rbd, ctx->s_xt, ctx->s_ut, ctx->s_info,
+                                     ctx->s_sol, ctx->s_tau, ctx->s_status);
+  if (rc) return rc;
+  D2H(x_traj, ctx->s_xt, sizeof(double) * B * (N + 1) * NX); D2H(u_traj, ctx->s_ut, sizeof(double) * B * N * NU);
+  if (info) D2H(info, ctx->s_info, sizeof(hb_solve_info) * B);
+  if (wbc_sol) D2H(wbc_sol, ctx->s_sol, sizeof(double) * B * NWBC);
+  if (torque) D2H(torque, ctx->s_tau, sizeof(double) * B * NJ);
+  if (wbc_status) D2H(wbc_status, ctx->s_status, sizeof(int32_t) * B);
+  return hb_sync(ctx);
+}
+
+int hb_rbd_to_centroidal_batch(hb_ctx* ctx, int B, const double* rbd, double* x) {
+  if (!ctx || B < 0 || !rbd || !x) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32);
+  int rc = hb_rbd_to_centroidal_batch_dev(ctx, B, ctx->s_rbd, ctx->s_xd);
+  if (rc) return rc;
+  D2H(x, ctx->s_xd, sizeof(double) * B * NX);
+  return hb_sync(ctx);
+}
+
+int hb_reference_expand_batch(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref, int32_t* mode) {
+  if (!ctx || B < 0 || !t0 || !refs || !x_ref || !swing_ref || !mode) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t N = ctx->cfg.horizon_N;
+  H2D(ctx->s_t0, t0, sizeof(double) * B); H2D(ctx->s_refs, refs, sizeof(hb_reference) * B);
+  int rc = hb_reference_expand_batch_dev(ctx, B, ctx->s_t0, ctx->s_refs, ctx->s_xref, ctx->s_swing, ctx->s_mode);
+  if (rc) return rc;
+  D2H(x_ref, ctx->s_xref, sizeof(double) * B * (N + 1) * NX); D2H(swing_ref, ctx->s_swing, sizeof(double) * B * (N + 1) * 24);
+  D2H(mode, ctx->s_mode, sizeof(int32_t) * B * (N + 1));
+  return hb_sync(ctx);
+}
+
+int hb_probe_flow_map(hb_ctx* ctx, int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee) {
+  if (!ctx || B < 0 || !x || !u || !f || !A || !Bm) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t per = NX + 2 * TS + 24 + 36 * NX;
+  H2D(ctx->s_xd, x, sizeof(double) * B * NX); H2D(ctx->s_ud, u, sizeof(double) * B * NU);
+  double* df = ctx->s_misc; double* dA = df + (size_t)B * NX; double* dB = dA + (size_t)B * TS; double* dee = dB + (size_t)B * TS;
+  (void)per;
+  int rc = hb_probe_flow_map_dev(ctx, B, ctx->s_xd, ctx->s_ud, df, dA, dB, dee);
+  if (rc) return rc;
+  D2H(f, df, sizeof(double) * B * NX); D2H(A, dA, sizeof(double) * B * TS); D2H(Bm, dB, sizeof(double) * B * TS);
+  if (ee) D2H(ee, dee, sizeof(double) * B * (24 + 36 * NX));
+  return hb_sync(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,350 @@
+// Batched dense QP: primal-dual interior point (Mehrotra predictor-corrector), one warp per problem.
+// Replaces the qpOASES active-set call of legged::WeightedWbc::update (legged_wbc/src/WeightedWbc.cpp:44-55):
+//     min 1/2 x'(H + rho I)x + g'x   s.t.  lbA <= A x <= ubA
+// rows with lbA == ubA are equalities, |bound| >= 1e19 means "no bound" (qpOASES::INFTY = 1e20), all-zero rows are
+// dropped (the reference appends 3 zero rows per swing contact, WbcBase.cpp:212). rho is the Tikhonov weight that
+// selects the least-norm point of the optimal face, as qpOASES' setToMPC() regularisation does.
+//
+// Linear algebra per iteration, all in shared memory, float64:
+//   K = H + rho I + D' diag(z/s) D      (span-aware rank-1 updates; WBC inequality rows touch 1..3 columns)
+//   K = L L' (left-looking Cholesky, lanes over rows), Li = L^-1 (lane per column), V = Li Aeq', S = V'V = Ls Ls', Si = Ls^-1
+//   every Newton solve is then a chain of mat-vecs (no sequential triangular solve on the critical path).
+#pragma once
+#include "hb_common.cuh"
+
+namespace hb {
+
+constexpr int QP_MAX_N = 40;    // variables
+constexpr int QP_MAX_EQ = 32;   // equality rows
+constexpr int QP_MAX_IN = 96;   // one-sided inequality entries (two-sided rows count twice)
+constexpr int QP_MAX_M = 64;    // rows of A
+
+struct QpWorkspace {
+  double *H, *Aeq, *K, *V, *S;
+  double *kdi, *sdi;
+  double *g, *x, *rd, *dx, *t1, *t2;
+  double *beq, *y, *rp, *dy, *t3;
+  double *f, *s, *z, *rs, *ds, *dz, *rc, *sgn;
+  int *in_row, *in_c0, *in_c1, *eq_row;
+  int ldn, ldv, lds;
+};
+
+__host__ __device__ inline int qp_ld(int n) { return n | 1; }
+
+// doubles needed by one warp
+__host__ __device__ inline size_t qp_workspace_doubles(int n) {
+  const int ldn = qp_ld(n);
+  size_t d = 0;
+  d += (size_t)n * ldn;            // H
+  d += (size_t)QP_MAX_EQ * ldn;    // Aeq
+  d += (size_t)n * ldn;            // K
+  d += (size_t)n * 33;             // V
+  d += (size_t)32 * 33;            // S
+  d += n + 32;                     // kdi, sdi
+  d += 6 * (size_t)n;              // g x rd dx t1 t2
+  d += 5 * 32;                     // beq y rp dy t3
+  d += 8 * (size_t)QP_MAX_IN;      // f s z rs ds dz rc sgn
+  d += (3 * QP_MAX_IN + QP_MAX_EQ + 1) / 2 + 1;  // int arrays
+  return d;
+}
+
+__device__ inline void qp_carve(double* base, int n, QpWorkspace& w) {
+  const int ldn = qp_ld(n);
+  w.ldn = ldn; w.ldv = 33; w.lds = 33;
+  double* p = base;
+  w.H = p; p += n * ldn;
+  w.Aeq = p; p += QP_MAX_EQ * ldn;
+  w.K = p; p += n * ldn;
+  w.V = p; p += n * 33;
+  w.S = p; p += 32 * 33;
+  w.kdi = p; p += n;
+  w.sdi = p; p += 32;
+  w.g = p; p += n; w.x = p; p += n; w.rd = p; p += n; w.dx = p; p += n; w.t1 = p; p += n; w.t2 = p; p += n;
+  w.beq = p; p += 32; w.y = p; p += 32; w.rp = p; p += 32; w.dy = p; p += 32; w.t3 = p; p += 32;
+  w.f = p; p += QP_MAX_IN; w.s = p; p += QP_MAX_IN; w.z = p; p += QP_MAX_IN; w.rs = p; p += QP_MAX_IN;
+  w.ds = p; p += QP_MAX_IN; w.dz = p; p += QP_MAX_IN; w.rc = p; p += QP_MAX_IN; w.sgn = p; p += QP_MAX_IN;
+  int* ip = reinterpret_cast<int*>(p);
+  w.in_row = ip; ip += QP_MAX_IN; w.in_c0 = ip; ip += QP_MAX_IN; w.in_c1 = ip; ip += QP_MAX_IN; w.eq_row = ip;
+}
+
+// In-place Cholesky M = L L' (lower triangle) followed by Li = L^-1, stored transposed in the strict upper triangle
+// (Li[i][k] at M[k*ld + i], i > k) with diag(Li) = invdiag. Returns false when a pivot is not positive.
+__device__ inline bool warp_chol_inv(double* M, int n, int ld, double* invdiag, int lane) {
+  bool ok = true;
+  for (int j = 0; j < n; ++j) {
+    for (int i = j + lane; i < n; i += 32) {
+      const double* ri = M + i * ld;
+      const double* rj = M + j * ld;
+      double a0 = ri[j], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int k = 0;
+      for (; k + 3 < j; k += 4) {
+        a0 -= ri[k] * rj[k]; a1 -= ri[k + 1] * rj[k + 1]; a2 -= ri[k + 2] * rj[k + 2]; a3 -= ri[k + 3] * rj[k + 3];
+      }
+      for (; k < j; ++k) a0 -= ri[k] * rj[k];
+      M[i * ld + j] = (a0 + a1) + (a2 + a3);
+    }
+    __syncwarp();
+    double d = M[j * ld + j];
+    if (!(d > 0.0)) { ok = false; d = 1.0; }
+    const double r = 1.0 / sqrt(d);
+    __syncwarp();
+    for (int i = j + lane; i < n; i += 32) M[i * ld + j] *= r;
+    if (lane == 0) invdiag[j] = r;
+    __syncwarp();
+  }
+  // Li by forward substitution on the identity, lane c owns column c (rows are swept uniformly so L reads broadcast)
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int c = c0 + lane;
+    const bool act = c < n;
+    for (int i = c0 + 1; i < n; ++i) {
+      if (act && i > c) {
+        const double* Li_row = M + i * ld;   // L[i][k], k < i  (lower)
+        double* col = M + c * ld;            // Li[k][c] at M[c*ld + k], k > c (upper)
+        double a0 = Li_row[c] * invdiag[c], a1 = 0.0;
+        int k = c + 1;
+        for (; k + 1 < i; k += 2) { a0 += Li_row[k] * col[k]; a1 += Li_row[k + 1] * col[k + 1]; }
+        if (k < i) a0 += Li_row[k] * col[k];
+        col[i] = -(a0 + a1) * invdiag[i];
+      }
+    }
+  }
+  __syncwarp();
+  return ok;
+}
+
+// y = Li v  (lower-triangular inverse stored as described above); lanes over rows
+__device__ inline void warp_li_mv(const double* M, int n, int ld, const double* invdiag, const double* v, double* y, int lane) {
+  for (int i = lane; i < n; i += 32) {
+    double a0 = invdiag[i] * v[i], a1 = 0.0;
+    int k = 0;
+    for (; k + 1 < i; k += 2) { a0 += M[k * ld + i] * v[k]; a1 += M[(k + 1) * ld + i] * v[k + 1]; }
+    if (k < i) a0 += M[k * ld + i] * v[k];
+    y[i] = a0 + a1;
+  }
+  __syncwarp();
+}
+// y = Li' v
+__device__ inline void warp_lit_mv(const double* M, int n, int ld, const double* invdiag, const double* v, double* y, int lane) {
+  for (int i = lane; i < n; i += 32) {
+    const double* row = M + i * ld;
+    double a0 = invdiag[i] * v[i], a1 = 0.0;
+    int k = i + 1;
+    for (; k + 1 < n; k += 2) { a0 += row[k] * v[k]; a1 += row[k + 1] * v[k + 1]; }
+    if (k < n) a0 += row[k] * v[k];
+    y[i] = a0 + a1;
+  }
+  __syncwarp();
+}
+
+struct QpResult { int status; int iters; };
+
+// A, lbA, ubA, H, g may live in global or shared memory (generic pointers). x_out: n doubles (generic).
+__device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict__ H, const double* __restrict__ g,
+                                         const double* __restrict__ A, const double* __restrict__ lbA,
+                                         const double* __restrict__ ubA, double rho, int max_iter, double* x_out,
+                                         QpWorkspace& w) {
+  const int lane = lane_id();
+  const int ldn = w.ldn, ldv = w.ldv, lds = w.lds;
+  // ---------------- classify rows
+  int me = 0, mi = 0;
+  bool infeasible = false;
+  for (int r0 = 0; r0 < m; r0 += 32) {
+    const int r = r0 + lane;
+    int c0 = n, c1 = 0;
+    double lo = 0.0, hi = 0.0;
+    if (r < m) {
+      const double* a = A + (size_t)r * n;
+      for (int c = 0; c < n; ++c) if (a[c] != 0.0) { if (c < c0) c0 = c; c1 = c + 1; }
+      lo = lbA[r]; hi = ubA[r];
+    }
+    const bool valid = r < m;
+    const bool zero_row = valid && c1 == 0;
+    const bool has_lo = valid && lo > -1e19, has_hi = valid && hi < 1e19;
+    if (zero_row && ((has_lo && lo > 1e-12) || (has_hi && hi < -1e-12))) infeasible = true;
+    const bool is_eq = valid && !zero_row && has_lo && has_hi && lo == hi;
+    const bool up = valid && !zero_row && !is_eq && has_hi;
+    const bool dn = valid && !zero_row && !is_eq && has_lo;
+    const unsigned beq = __ballot_sync(HB_FULL_MASK, is_eq);
+    const unsigned bup = __ballot_sync(HB_FULL_MASK, up);
+    const unsigned bdn = __ballot_sync(HB_FULL_MASK, dn);
+    const unsigned below = (1u << lane) - 1u;
+    if (is_eq) { const int e = me + __popc(beq & below); if (e < QP_MAX_EQ) { w.eq_row[e] = r; w.beq[e] = hi; } }
+    if (up) { const int e = mi + __popc(bup & below); if (e < QP_MAX_IN) { w.in_row[e] = r; w.in_c0[e] = c0; w.in_c1[e] = c1; w.sgn[e] = 1.0; w.f[e] = hi; } }
+    const int mi2 = mi + __popc(bup);
+    if (dn) { const int e = mi2 + __popc(bdn & below); if (e < QP_MAX_IN) { w.in_row[e] = r; w.in_c0[e] = c0; w.in_c1[e] = c1; w.sgn[e] = -1.0; w.f[e] = -lo; } }
+    me += __popc(beq);
+    mi = mi2 + __popc(bdn);
+  }
+  infeasible = __any_sync(HB_FULL_MASK, infeasible);
+  QpResult res{1, 0};
+  if (infeasible || me > QP_MAX_EQ || mi > QP_MAX_IN || n > QP_MAX_N) {
+    for (int i = lane; i < n; i += 32) x_out[i] = 0.0;
+    res.status = 2;
+    return res;
+  }
+  __syncwarp();
+  // ---------------- stage H, Aeq, g; initial point
+  for (int idx = lane; idx < n * n; idx += 32) { const int i = idx / n, c = idx - i * n; w.H[i * ldn + c] = H[idx]; }
+  for (int e = 0; e < me; ++e) {
+    const double* a = A + (size_t)w.eq_row[e] * n;
+    for (int c = lane; c < n; c += 32) w.Aeq[e * ldn + c] = a[c];
+  }
+  double gs = 1.0, bs = 1.0;
+  for (int i = lane; i < n; i += 32) { const double gi = g[i]; w.g[i] = gi; w.x[i] = 0.0; gs = fmax(gs, 1.0 + fabs(gi)); }
+  for (int e = lane; e < me; e += 32) { w.y[e] = 0.0; bs = fmax(bs, 1.0 + fabs(w.beq[e])); }
+  for (int j = lane; j < mi; j += 32) { w.s[j] = fmax(1.0, w.f[j]); w.z[j] = 1.0; bs = fmax(bs, 1.0 + fabs(w.f[j])); }
+  gs = warp_max(gs); bs = warp_max(bs);
+  __syncwarp();
+
+  int it = 0;
+  for (; it < max_iter; ++it) {
+    // ---------------- residuals
+    for (int i = lane; i < n; i += 32) {
+      double a = w.g[i] + rho * w.x[i];
+      const double* hr = w.H + i * ldn;
+      for (int c = 0; c < n; ++c) a += hr[c] * w.x[c];
+      for (int e = 0; e < me; ++e) a += w.Aeq[e * ldn + i] * w.y[e];
+      for (int j = 0; j < mi; ++j) if (i >= w.in_c0[j] && i < w.in_c1[j]) a += w.sgn[j] * w.z[j] * A[(size_t)w.in_row[j] * n + i];
+      w.rd[i] = a;
+    }
+    for (int e = lane; e < me; e += 32) {
+      double a = -w.beq[e];
+      for (int c = 0; c < n; ++c) a += w.Aeq[e * ldn + c] * w.x[c];
+      w.rp[e] = a;
+    }
+    double sz = 0.0;
+    for (int j = lane; j < mi; j += 32) {
+      const double* a = A + (size_t)w.in_row[j] * n;
+      double d = 0.0;
+      for (int c = w.in_c0[j]; c < w.in_c1[j]; ++c) d += a[c] * w.x[c];
+      w.rs[j] = w.sgn[j] * d + w.s[j] - w.f[j];
+      sz += w.s[j] * w.z[j];
+    }
+    __syncwarp();
+    double rdn = 0.0, rpn = 0.0;
+    for (int i = lane; i < n; i += 32) rdn = fmax(rdn, fabs(w.rd[i]));
+    for (int e = lane; e < me; e += 32) rpn = fmax(rpn, fabs(w.rp[e]));
+    for (int j = lane; j < mi; j += 32) rpn = fmax(rpn, fabs(w.rs[j]));
+    rdn = warp_max(rdn); rpn = warp_max(rpn);
+    const double mu = mi > 0 ? warp_sum(sz) / mi : 0.0;
+    if (!(rdn == rdn) || !(rpn == rpn) || !(mu == mu) || rdn > 1e300 || rpn > 1e300) { res.status = 3; break; }
+    if (rdn < 1e-10 * gs && rpn < 1e-10 * bs && mu < 1e-12) { res.status = 0; break; }
+    // ---------------- K = H + rho I + D' W D
+    for (int idx = lane; idx < n * ldn; idx += 32) { const int i = idx / ldn, c = idx - i * ldn; w.K[idx] = w.H[idx] + ((i == c) ? rho : 0.0); }
+    __syncwarp();
+    for (int j = 0; j < mi; ++j) {
+      const int c0 = w.in_c0[j], L = w.in_c1[j] - c0;
+      const double wj = w.z[j] / w.s[j];
+      const double* a = A + (size_t)w.in_row[j] * n + c0;
+      for (int idx = lane; idx < L * L; idx += 32) {
+        const int i = idx / L, c = idx - i * L;
+        w.K[(c0 + i) * ldn + c0 + c] += wj * a[i] * a[c];
+      }
+      __syncwarp();
+    }
+    bool ok = warp_chol_inv(w.K, n, ldn, w.kdi, lane);
+    // ---------------- V = Li Aeq'  (n x me), lane per equality row
+    if (me > 0) {
+      if (lane < me) {
+        const double* ar = w.Aeq + lane * ldn;
+        for (int i = 0; i < n; ++i) {
+          double a0 = w.kdi[i] * ar[i], a1 = 0.0;
+          int k = 0;
+          for (; k + 1 < i; k += 2) { a0 += w.K[k * ldn + i] * ar[k]; a1 += w.K[(k + 1) * ldn + i] * ar[k + 1]; }
+          if (k < i) a0 += w.K[k * ldn + i] * ar[k];
+          w.V[i * ldv + lane] = a0 + a1;
+        }
+      }
+      __syncwarp();
+      // S = V'V (lower), then Cholesky + inverse
+      for (int idx = lane; idx < me * me; idx += 32) {
+        const int a = idx / me, b = idx - a * me;
+        if (b <= a) {
+          double s0 = 0.0, s1 = 0.0;
+          int i = 0;
+          for (; i + 1 < n; i += 2) { s0 += w.V[i * ldv + a] * w.V[i * ldv + b]; s1 += w.V[(i + 1) * ldv + a] * w.V[(i + 1) * ldv + b]; }
+          if (i < n) s0 += w.V[i * ldv + a] * w.V[i * ldv + b];
+          w.S[a * lds + b] = s0 + s1;
+        }
+      }
+      __syncwarp();
+      ok = warp_chol_inv(w.S, me, lds, w.sdi, lane) && ok;
+    }
+    if (!ok) { res.status = 2; break; }
+
+    // Newton solve for the complementarity target in w.rc; results in dx, dy, ds, dz
+    auto newton = [&]() {
+      for (int i = lane; i < n; i += 32) {
+        double a = -w.rd[i];
+        for (int j = 0; j < mi; ++j)
+          if (i >= w.in_c0[j] && i < w.in_c1[j]) a += w.sgn[j] * A[(size_t)w.in_row[j] * n + i] * ((w.rc[j] - w.z[j] * w.rs[j]) / w.s[j]);
+        w.t2[i] = a;
+      }
+      __syncwarp();
+      warp_li_mv(w.K, n, ldn, w.kdi, w.t2, w.t1, lane);  // t1 = Li r1
+      if (me > 0) {
+        for (int e = lane; e < me; e += 32) {
+          double a = w.rp[e];
+          for (int i = 0; i < n; ++i) a += w.V[i * ldv + e] * w.t1[i];
+          w.t3[e] = a;
+        }
+        __syncwarp();
+        warp_li_mv(w.S, me, lds, w.sdi, w.t3, w.dy, lane);
+        for (int e = lane; e < me; e += 32) w.t3[e] = w.dy[e];
+        __syncwarp();
+        warp_lit_mv(w.S, me, lds, w.sdi, w.t3, w.dy, lane);
+        for (int i = lane; i < n; i += 32) {
+          double a = w.t1[i];
+          for (int e = 0; e < me; ++e) a -= w.V[i * ldv + e] * w.dy[e];
+          w.t2[i] = a;
+        }
+        __syncwarp();
+      } else {
+        for (int i = lane; i < n; i += 32) w.t2[i] = w.t1[i];
+        __syncwarp();
+      }
+      warp_lit_mv(w.K, n, ldn, w.kdi, w.t2, w.dx, lane);
+      for (int j = lane; j < mi; j += 32) {
+        const double* a = A + (size_t)w.in_row[j] * n;
+        double d = 0.0;
+        for (int c = w.in_c0[j]; c < w.in_c1[j]; ++c) d += a[c] * w.dx[c];
+        const double dsj = -w.rs[j] - w.sgn[j] * d;
+        w.ds[j] = dsj;
+        w.dz[j] = -(w.rc[j] + w.z[j] * dsj) / w.s[j];
+      }
+      __syncwarp();
+    };
+    auto max_step = [&]() {
+      double a = 1.0;
+      for (int j = lane; j < mi; j += 32) {
+        if (w.ds[j] < 0.0) a = fmin(a, -w.s[j] / w.ds[j]);
+        if (w.dz[j] < 0.0) a = fmin(a, -w.z[j] / w.dz[j]);
+      }
+      return warp_min(a);
+    };
+    for (int j = lane; j < mi; j += 32) w.rc[j] = w.s[j] * w.z[j];
+    __syncwarp();
+    newton();
+    if (mi > 0) {
+      const double a_aff = max_step();
+      double ma = 0.0;
+      for (int j = lane; j < mi; j += 32) ma += (w.s[j] + a_aff * w.ds[j]) * (w.z[j] + a_aff * w.dz[j]);
+      ma = warp_sum(ma) / mi;
+      const double r = ma / mu;
+      const double sigma = r * r * r;
+      for (int j = lane; j < mi; j += 32) w.rc[j] = w.s[j] * w.z[j] + w.ds[j] * w.dz[j] - sigma * mu;
+      __syncwarp();
+      newton();
+    }
+    const double alpha = fmin(1.0, 0.995 * max_step());
+    for (int i = lane; i < n; i += 32) w.x[i] += alpha * w.dx[i];
+    for (int e = lane; e < me; e += 32) w.y[e] += alpha * w.dy[e];
+    for (int j = lane; j < mi; j += 32) { w.s[j] += alpha * w.ds[j]; w.z[j] += alpha * w.dz[j]; }
+    __syncwarp();
+  }
+  for (int i = lane; i < n; i += 32) x_out[i] = w.x[i];
+  res.iters = it;
+  return res;
+}
+
+}  // namespace hb

@@ -1,0 +1,239 @@
+// K5: WeightedWbc problem assembly on the device (legged_wbc/src/WbcBase.cpp:54-338, WeightedWbc.cpp:18-94),
+// one warp per instance. Lane-level parallelism (see hb_rbd.cuh):
+//   pass A  lanes 0-15: unit velocities at the measured q -> contact Jacobian columns J_c (12x16)
+//           lanes 16-31: unit velocities at the planned q -> centroidal momentum matrix columns A(q_des) (6x16)
+//   pass B  lane 0: dual pass at (q_meas; direction v_meas)  -> p_c, v_c, dJ_c/dt v   (WbcBase.cpp:91-109)
+//           lane 1: dual pass at (q_des;  direction v_des)   -> p_c, v_c, dA/dt v      (WbcBase.cpp:119-136)
+//   pass C  lanes 0-15: RNEA with unit accelerations -> M(q) columns (CRBA, WbcBase.cpp:88-89); lane 16: nle (WbcBase.cpp:90)
+// The QP (H, g, A, lbA, ubA) is written in the reference's own layout (qpOASES row-major, WeightedWbc.cpp:27-41).
+#pragma once
+#include "hb_common.cuh"
+#include "hb_rbd.cuh"
+
+namespace hb {
+
+constexpr int WBC_ROWS = 60;     // allocated rows of A per instance
+constexpr double QP_INFTY = 1e20;  // qpOASES::INFTY
+
+struct WbcShared {
+  double J[12 * 16];
+  double Ad[6 * 16];
+  double M[16 * 16];
+  double nle[16];
+  double q[16], v[16], qd[16], vd[16];
+  double pos_m[12], vel_m[12], dJv[12], pos_d[12], vel_d[12];
+  double Adv[6], com_d[3];
+  double Aw[12 * 16];   // weighted task rows acting on qdd (swing: <=6, base: 6)
+  double bw[12];
+  double misc[32];
+};
+
+// rotationMatrixToRotationVector(R_ref R_meas^T)  (rotationErrorInWorld, WbcBase.cpp:281)
+__device__ inline void rotation_error_world(const double* Rref, const double* Rmeas, double* err) {
+  double E[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) E[3 * i + j] = Rref[3 * i] * Rmeas[3 * j] + Rref[3 * i + 1] * Rmeas[3 * j + 1] + Rref[3 * i + 2] * Rmeas[3 * j + 2];
+  const double sk[3] = {E[7] - E[5], E[2] - E[6], E[3] - E[1]};
+  double c = 0.5 * (E[0] + E[4] + E[8] - 1.0);
+  c = fmin(1.0, fmax(-1.0, c));
+  const double ang = acos(c);
+  const double sn = sqrt(sk[0] * sk[0] + sk[1] * sk[1] + sk[2] * sk[2]);
+  double f = 0.5;
+  if (ang > 1e-8 && sn > 1e-12) f = ang / sn;
+  for (int i = 0; i < 3; ++i) err[i] = f * sk[i];
+}
+
+// Assemble one instance. Outputs may be global or shared. Returns the number of constraint rows m.
+__device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const double* __restrict__ u_des,
+                                        const double* __restrict__ rbd, int mode, bool stance_mode, WbcShared& sh,
+                                        double* H, double* g, double* A, double* lbA, double* ubA) {
+  const int lane = lane_id();
+  const Model& md = c_model;
+  // ---- measured q, v (WbcBase.cpp:72-79)
+  if (lane == 0) {
+    for (int i = 0; i < 3; ++i) { sh.q[i] = rbd[3 + i]; sh.q[3 + i] = rbd[i]; sh.v[i] = rbd[NQ + 3 + i]; }
+    for (int j = 0; j < NJ; ++j) { sh.q[6 + j] = rbd[6 + j]; sh.v[6 + j] = rbd[NQ + 6 + j]; }
+    double sz, cz, sy, cy;
+    sincos(sh.q[3], &sz, &cz); sincos(sh.q[4], &sy, &cy);
+    const double w0 = rbd[NQ], w1 = rbd[NQ + 1], w2 = rbd[NQ + 2];
+    const double dxr = (cz * w0 + sz * w1) / cy;
+    sh.v[5] = dxr; sh.v[4] = -sz * w0 + cz * w1; sh.v[3] = w2 + sy * dxr;
+    for (int i = 0; i < NQ; ++i) sh.qd[i] = x_des[6 + i];
+  }
+  __syncwarp();
+  // ---- pass A
+  {
+    double q[NQ], e[NQ];
+    const bool meas = lane < 16;
+    const int k = lane & 15;
+    for (int i = 0; i < NQ; ++i) { q[i] = meas ? sh.q[i] : sh.qd[i]; e[i] = (i == k) ? 1.0 : 0.0; }
+    KinOut<double> o;
+    kin_pass<double>(q, e, o);
+    if (meas) { for (int r = 0; r < 12; ++r) sh.J[r * 16 + k] = o.cvel[r]; }
+    else { for (int r = 0; r < 6; ++r) sh.Ad[r * 16 + k] = o.h[r]; }
+  }
+  __syncwarp();
+  // ---- planned generalised velocity: v_b = A_b^-1 (m hbar - A_j qj_dot)  (mapping_.getPinocchioJointVelocity, WbcBase.cpp:130)
+  if (lane == 0) {
+    double Ab[36], rhs[6], vb[6];
+    for (int r = 0; r < 6; ++r) {
+      for (int c = 0; c < 6; ++c) Ab[6 * r + c] = sh.Ad[r * 16 + c];
+      double s = md.total_mass * x_des[r];
+      for (int j = 0; j < NJ; ++j) s -= sh.Ad[r * 16 + 6 + j] * u_des[12 + j];
+      rhs[r] = s;
+    }
+    solve6(Ab, rhs, vb);
+    for (int i = 0; i < 6; ++i) sh.vd[i] = vb[i];
+    for (int j = 0; j < NJ; ++j) sh.vd[6 + j] = u_des[12 + j];
+  }
+  __syncwarp();
+  // ---- pass B (dual pass along q_dot = v)
+  if (lane < 2) {
+    D1 q[NQ], v[NQ];
+    for (int i = 0; i < NQ; ++i) {
+      const double qi = lane == 0 ? sh.q[i] : sh.qd[i], vi = lane == 0 ? sh.v[i] : sh.vd[i];
+      q[i] = D1(qi, vi); v[i] = D1(vi, 0.0);
+    }
+    KinOut<D1> o;
+    kin_pass<D1>(q, v, o);
+    if (lane == 0) { for (int r = 0; r < 12; ++r) { sh.pos_m[r] = o.cpos[r].v; sh.vel_m[r] = o.cvel[r].v; sh.dJv[r] = o.cvel[r].d; } }
+    else {
+      for (int r = 0; r < 12; ++r) { sh.pos_d[r] = o.cpos[r].v; sh.vel_d[r] = o.cvel[r].v; }
+      for (int r = 0; r < 6; ++r) sh.Adv[r] = o.h[r].d;
+      for (int r = 0; r < 3; ++r) sh.com_d[r] = o.com[r].v;
+    }
+  }
+  // ---- pass C (RNEA columns)
+  if (lane < 17) {
+    double q[NQ], v[NQ], a[NQ], tau[NQ];
+    for (int i = 0; i < NQ; ++i) { q[i] = sh.q[i]; v[i] = lane == 16 ? sh.v[i] : 0.0; a[i] = (i == lane) ? 1.0 : 0.0; }
+    rnea_pass(q, v, a, lane == 16, tau, nullptr);
+    if (lane < 16) { for (int r = 0; r < NQ; ++r) sh.M[r * 16 + lane] = tau[r]; }
+    else { for (int r = 0; r < NQ; ++r) sh.nle[r] = tau[r]; }
+  }
+  __syncwarp();
+  // symmetrise M (WbcBase.cpp:88-89 copies the upper triangle; numerically the same matrix)
+  for (int idx = lane; idx < 256; idx += 32) {
+    const int i = idx >> 4, j = idx & 15;
+    if (j < i) { const double a = 0.5 * (sh.M[i * 16 + j] + sh.M[j * 16 + i]); sh.M[i * 16 + j] = a; }
+  }
+  __syncwarp();
+  for (int idx = lane; idx < 256; idx += 32) { const int i = idx >> 4, j = idx & 15; if (j > i) sh.M[i * 16 + j] = sh.M[j * 16 + i]; }
+  __syncwarp();
+  // ---- desired base kinematics (computeBaseKinematicsFromCentroidalModel, WbcBase.cpp:134-135) and task rows
+  int nw = 0;  // number of weighted rows (uniform)
+  bool fl[4];
+  int nc = 0;
+  for (int c = 0; c < 4; ++c) { fl[c] = contact_flag(mode, c); nc += fl[c]; }
+  if (stance_mode) nw = 6;
+  else nw = 3 * (4 - nc) + 6;
+  if (lane == 0) {
+    for (int i = 0; i < 12 * 16; ++i) sh.Aw[i] = 0.0;
+    if (stance_mode) {
+      for (int i = 0; i < 6; ++i) { sh.Aw[i * 16 + i] = HB_WBC_WEIGHT_BASE; sh.bw[i] = 0.0; }
+    } else {
+      // normalised centroidal momentum rate at the plan (getNormalizedCentroidalMomentumRate)
+      double hd[6] = {0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < 4; ++c) {
+        const double* F = u_des + 3 * c;
+        const double r0 = sh.pos_d[3 * c] - sh.com_d[0], r1 = sh.pos_d[3 * c + 1] - sh.com_d[1], r2 = sh.pos_d[3 * c + 2] - sh.com_d[2];
+        hd[0] += F[0]; hd[1] += F[1]; hd[2] += F[2];
+        hd[3] += r1 * F[2] - r2 * F[1]; hd[4] += r2 * F[0] - r0 * F[2]; hd[5] += r0 * F[1] - r1 * F[0];
+      }
+      hd[2] -= md.total_mass * HB_GRAVITY;
+      double Ab[36], rhs[6], qbdd[6];
+      for (int r = 0; r < 6; ++r) { for (int c = 0; c < 6; ++c) Ab[6 * r + c] = sh.Ad[r * 16 + c]; rhs[r] = hd[r] - sh.Adv[r]; }
+      solve6(Ab, rhs, qbdd);
+      // euler axes at the plan and at the measurement
+      double Rd[9], axd[9], Rm[9], axm[9];
+      base_frame<double>(sh.qd, Rd, axd);
+      base_frame<double>(sh.q, Rm, axm);
+      double baseVelW[3], baseAccW[3], wm[3], dJw_v[3];
+      {
+        const double* vd = sh.vd;
+        double w1[3], w2[3], t1[3], t2[3];
+        for (int i = 0; i < 3; ++i) { w1[i] = axd[i] * vd[3]; w2[i] = w1[i] + axd[3 + i] * vd[4]; }
+        cross(w1, &axd[3], t1); cross(w2, &axd[6], t2);
+        for (int i = 0; i < 3; ++i) {
+          baseVelW[i] = w2[i] + axd[6 + i] * vd[5];
+          baseAccW[i] = axd[i] * qbdd[3] + axd[3 + i] * qbdd[4] + axd[6 + i] * qbdd[5] + t1[i] * vd[4] + t2[i] * vd[5];
+        }
+      }
+      {
+        const double* vm = sh.v;
+        double w1[3], w2[3], t1[3], t2[3];
+        for (int i = 0; i < 3; ++i) { w1[i] = axm[i] * vm[3]; w2[i] = w1[i] + axm[3 + i] * vm[4]; }
+        cross(w1, &axm[3], t1); cross(w2, &axm[6], t2);
+        for (int i = 0; i < 3; ++i) { wm[i] = w2[i] + axm[6 + i] * vm[5]; dJw_v[i] = t1[i] * vm[4] + t2[i] * vm[5]; }
+      }
+      int r = 0;
+      // swing leg task (WbcBase.cpp:297-323), weight 100
+      for (int c = 0; c < 4; ++c) if (!fl[c]) for (int a = 0; a < 3; ++a) {
+        const double acc = HB_WBC_SWING_KP * (sh.pos_d[3 * c + a] - sh.pos_m[3 * c + a]) + HB_WBC_SWING_KD * (sh.vel_d[3 * c + a] - sh.vel_m[3 * c + a]);
+        for (int j = 0; j < NQ; ++j) sh.Aw[r * 16 + j] = HB_WBC_WEIGHT_SWING * sh.J[(3 * c + a) * 16 + j];
+        sh.bw[r] = HB_WBC_WEIGHT_SWING * (acc - sh.dJv[3 * c + a]);
+        ++r;
+      }
+      // base xy acceleration (WbcBase.cpp:228-240)
+      for (int a = 0; a < 2; ++a) { sh.Aw[r * 16 + a] = HB_WBC_WEIGHT_BASE; sh.bw[r] = HB_WBC_WEIGHT_BASE * qbdd[a]; ++r; }
+      // base height (WbcBase.cpp:243-256)
+      sh.Aw[r * 16 + 2] = HB_WBC_WEIGHT_BASE;
+      sh.bw[r] = HB_WBC_WEIGHT_BASE * (qbdd[2] + HB_WBC_BASE_HEIGHT_KP * (sh.qd[2] - sh.q[2]) + HB_WBC_BASE_HEIGHT_KD * (sh.vd[2] - sh.v[2]));
+      ++r;
+      // base angular motion (WbcBase.cpp:259-290)
+      double err[3];
+      rotation_error_world(Rd, Rm, err);
+      for (int a = 0; a < 3; ++a) {
+        for (int i = 0; i < 3; ++i) sh.Aw[r * 16 + 3 + i] = HB_WBC_WEIGHT_BASE * axm[3 * i + a];
+        sh.bw[r] = HB_WBC_WEIGHT_BASE * (baseAccW[a] + HB_WBC_BASE_ANGULAR_KP * err[a] + HB_WBC_BASE_ANGULAR_KD * (baseVelW[a] - wm[a]) - dJw_v[a]);
+        ++r;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- H = Aw'Aw, g = -Aw'bw (WeightedWbc.cpp:38-41); only the qdd block is non-zero
+  for (int idx = lane; idx < NWBC * NWBC; idx += 32) {
+    const int i = idx / NWBC, j = idx - i * NWBC;
+    double s = 0.0;
+    if (i < NQ && j < NQ) for (int r = 0; r < nw; ++r) s += sh.Aw[r * 16 + i] * sh.Aw[r * 16 + j];
+    H[idx] = s;
+  }
+  for (int i = lane; i < NWBC; i += 32) {
+    double s = 0.0;
+    if (i < NQ) for (int r = 0; r < nw; ++r) s += sh.Aw[r * 16 + i] * sh.bw[r];
+    g[i] = -s;
+  }
+  // ---- constraints (WeightedWbc.cpp:68-71): EoM (16 eq) + swing force = 0 (3 per swing contact) + torque limits (20)
+  //      + friction pyramid (5 per stance contact) + 3 zero rows per swing contact
+  const int n_sw = 4 - nc;
+  const int r_sw = 16, r_tq = 16 + 3 * n_sw, r_fr = r_tq + 20, r_zero = r_fr + 5 * nc, m = r_zero + 3 * n_sw;
+  for (int idx = lane; idx < m * NWBC; idx += 32) A[idx] = 0.0;
+  __syncwarp();
+  for (int idx = lane; idx < 16 * NWBC; idx += 32) {
+    const int i = idx / NWBC, j = idx - i * NWBC;
+    double a;
+    if (j < NQ) a = sh.M[i * 16 + j];
+    else if (j < NQ + 12) a = -sh.J[(j - NQ) * 16 + i];
+    else a = (i >= 6 && j - NQ - 12 == i - 6) ? -1.0 : 0.0;
+    A[idx] = a;
+  }
+  for (int i = lane; i < 16; i += 32) { lbA[i] = -sh.nle[i]; ubA[i] = -sh.nle[i]; }
+  if (lane == 0) {
+    int r = r_sw;
+    for (int c = 0; c < 4; ++c) if (!fl[c]) for (int a = 0; a < 3; ++a) { A[r * NWBC + NQ + 3 * c + a] = 1.0; lbA[r] = 0.0; ubA[r] = 0.0; ++r; }
+    for (int sgn = 0; sgn < 2; ++sgn) for (int j = 0; j < NJ; ++j) {
+      A[r * NWBC + NQ + 12 + j] = sgn == 0 ? 1.0 : -1.0; lbA[r] = -QP_INFTY; ubA[r] = md.torque_limit[j]; ++r;
+    }
+    const double mu = HB_WBC_FRICTION_MU;
+    const double pyr[5][3] = {{0, 0, -1}, {1, 0, -mu}, {-1, 0, -mu}, {0, 1, -mu}, {0, -1, -mu}};
+    for (int c = 0; c < 4; ++c) if (fl[c]) for (int k = 0; k < 5; ++k) {
+      for (int a = 0; a < 3; ++a) A[r * NWBC + NQ + 3 * c + a] = pyr[k][a];
+      lbA[r] = -QP_INFTY; ubA[r] = 0.0; ++r;
+    }
+    for (int k = 0; k < 3 * n_sw; ++k) { lbA[r] = -QP_INFTY; ubA[r] = 0.0; ++r; }
+  }
+  __syncwarp();
+  return m;
+}
+
+}  // namespace hb

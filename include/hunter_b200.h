@@ -1,0 +1,118 @@
+/* hunter_b200.h -- C ABI of libhunter_b200.so: batched NMPC iteration + WeightedWbc QP for the Hunter biped on B200.
+ *
+ * Every entry point replaces one operator of the reference's per-control-step path; the reference-side
+ * bindings (C++ adapters deriving from ocs2::MPC_BASE / legged::WbcBase) are shown in INTEGRATION.md.
+ *
+ *   hb_wbc_solve_batch      <-> legged::WeightedWbc::update            legged_wbc/src/WeightedWbc.cpp:18-66,
+ *                               legged::WbcBase::update               legged_wbc/include/legged_wbc/WbcBase.h:43-44
+ *   hb_wbc_qp_batch         <-> qpOASES::QProblem::init + getPrimalSolution   legged_wbc/src/WeightedWbc.cpp:44-55
+ *   hb_mpc_solve_batch      <-> ocs2::MPC_MRT_Interface::advanceMpc -> SqpMpc/SqpSolver::run (one SQP iteration)
+ *                               legged_controllers/src/LeggedController.cpp:378-379,406
+ *   hb_mpc_cold_start_batch <-> LeggedRobotInitializer::compute       legged_interface/src/initialization/LeggedRobotInitializer.cpp:67-77
+ *   hb_policy_eval_batch    <-> MPC_MRT_Interface::evaluatePolicy     legged_controllers/src/LeggedController.cpp:154-156
+ *   hb_control_step_batch   <-> LeggedController::update MPC->policy->WBC->torque law   LeggedController.cpp:137-257
+ *   hb_rbd_to_centroidal_batch <-> CentroidalModelRbdConversions::computeCentroidalStateFromRbdModel  LeggedController.cpp:336
+ *   hb_reference_expand_batch  <-> SwitchedModelReferenceManager::modifyReferences (gait tiling, swing planner, target
+ *                               interpolation, evaluated on the node grid)   legged_interface/src/SwitchedModelReferenceManager.cpp:136-171
+ *
+ * Conventions: plain pointers and sizes only; no exceptions cross the ABI. Return 0 on success, <0 on misuse / CUDA error
+ * (hb_strerror). Per-instance status words: 0 converged, 1 iteration cap, 2 infeasible / ill-posed, 3 NaN.
+ * All arithmetic is IEEE float64 (the reference is all-double: ocs2::scalar_t).
+ * Layouts (row-major, instance-major): state x[22] = [h_lin/m, h_ang/m, p, zyx, q_j]; input u[22] = [F0..F3, qj_dot];
+ * rbd[32] = [zyx, p, q_j, omega_world, v, qj_dot]; WBC solution sol[38] = [qdd(16), F(12), tau(10)].
+ * The *_host entry points take host pointers (pinned or pageable) and copy through the context's staging buffers;
+ * the *_dev entry points take device pointers and run asynchronously on the context's stream (hb_sync to wait).
+ */
+#ifndef HUNTER_B200_H
+#define HUNTER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb_ctx hb_ctx;
+
+typedef struct {
+  int32_t horizon_N;     /* shooting intervals (BASELINE: 100; shipped task.info: ~54)            */
+  double dt;             /* node spacing [s] (BASELINE: 0.01; task.info:82 0.015)                 */
+  int32_t max_batch;     /* capacity of the context's scratch buffers                             */
+  double wbc_rho;        /* Tikhonov weight that defines the least-norm WBC optimum (qpOASES setToMPC regularisation) */
+  int32_t qp_max_iter;   /* interior-point iteration cap                                          */
+  int32_t line_search_max_trials; /* alpha = 1, 1/2, ... >= 1e-4 -> 14                            */
+} hb_config;
+
+typedef struct {
+  double alpha;          /* accepted step length (0 = step rejected, iterate kept)                */
+  double merit0, merit1; /* merit before / after                                                  */
+  double viol0, viol1;   /* sqrt(dynamics SSE + equality SSE) before / after                      */
+  double armijo;         /* descent metric of the projected subproblem                            */
+  int32_t status;        /* 0 ok, 3 NaN                                                           */
+  int32_t n_trials;      /* line-search trials evaluated                                          */
+} hb_solve_info;
+
+/* compact per-instance reference description consumed by hb_reference_expand_batch */
+#define HB_MAX_EVENTS 32
+#define HB_MAX_TARGETS 8
+#define HB_MAX_SEGMENTS 24
+typedef struct {
+  int32_t n_events;                       /* mode schedule: modes[i] holds on (event_times[i-1], event_times[i]] */
+  double event_times[HB_MAX_EVENTS];
+  int32_t modes[HB_MAX_EVENTS + 1];
+  int32_t n_targets;                      /* target trajectory samples (time, state)                              */
+  double target_times[HB_MAX_TARGETS];
+  double target_states[HB_MAX_TARGETS][22];
+  int32_t n_segments[4][3];               /* per contact, per axis: cubic Hermite segments [t0,t1,p0,v0,p1,v1]    */
+  double segments[4][3][HB_MAX_SEGMENTS][6];
+} hb_reference;
+
+int hb_default_config(hb_config* cfg);
+int hb_create(const hb_config* cfg, int device, hb_ctx** out);
+int hb_destroy(hb_ctx* ctx);
+int hb_sync(hb_ctx* ctx);
+const char* hb_strerror(int code);
+/* number of kernel launches issued through this context since creation (bench.py reports it as gpu_launches) */
+int64_t hb_launch_count(const hb_ctx* ctx);
+/* the context's CUDA stream as a cudaStream_t cast to void* (for event timing on the launching stream) */
+void* hb_stream(hb_ctx* ctx);
+
+/* ---- device-pointer (asynchronous) entry points ---- */
+int hb_wbc_qp_batch_dev(hb_ctx* ctx, int B, int n, int m, const double* H, const double* g, const double* A, const double* lbA,
+                        const double* ubA, double* x, int32_t* status, int32_t* iters);
+int hb_wbc_solve_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                           const uint8_t* stance_mode, double* sol, int32_t* status);
+int hb_mpc_cold_start_batch_dev(hb_ctx* ctx, int B, const double* x0, const int32_t* mode, double* x_traj, double* u_traj);
+int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
+                           double* x_traj, double* u_traj, hb_solve_info* info);
+int hb_policy_eval_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x_traj, const double* u_traj, const int32_t* mode,
+                             double* x_des, double* u_des, int32_t* mode_out);
+int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0, const double* x_ref, const double* swing_ref,
+                              const int32_t* mode, const double* rbd, double* x_traj, double* u_traj, hb_solve_info* info,
+                              double* wbc_sol, double* torque, int32_t* wbc_status);
+int hb_rbd_to_centroidal_batch_dev(hb_ctx* ctx, int B, const double* rbd, double* x);
+int hb_reference_expand_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
+                                  int32_t* mode);
+/* probes used by the parity tests: rigid-body quantities and the node LQ model computed by the device code */
+int hb_probe_flow_map_dev(hb_ctx* ctx, int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee);
+
+/* ---- host-pointer (synchronous) entry points: H2D copy, device call, D2H copy ---- */
+int hb_wbc_qp_batch(hb_ctx* ctx, int B, int n, int m, const double* H, const double* g, const double* A, const double* lbA,
+                    const double* ubA, double* x, int32_t* status, int32_t* iters);
+int hb_wbc_solve_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                       const uint8_t* stance_mode, double* sol, int32_t* status);
+int hb_mpc_cold_start_batch(hb_ctx* ctx, int B, const double* x0, const int32_t* mode, double* x_traj, double* u_traj);
+int hb_mpc_solve_batch(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
+                       double* x_traj, double* u_traj, hb_solve_info* info);
+int hb_control_step_batch(hb_ctx* ctx, int B, double t_rel, const double* x0, const double* x_ref, const double* swing_ref,
+                          const int32_t* mode, const double* rbd, double* x_traj, double* u_traj, hb_solve_info* info,
+                          double* wbc_sol, double* torque, int32_t* wbc_status);
+int hb_rbd_to_centroidal_batch(hb_ctx* ctx, int B, const double* rbd, double* x);
+int hb_reference_expand_batch(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
+                              int32_t* mode);
+int hb_probe_flow_map(hb_ctx* ctx, int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -770,7 +770,17 @@ int qp_solve(int n, int m, const double* H, const double* g, const double* A, co
     for (double v : rp) rn = std::max(rn, std::fabs(v));
     for (double v : rs) rn = std::max(rn, std::fabs(v));
     if (!std::isfinite(rn)) { status = 3; break; }
-    if (rn < 1e-9 && mu < 1e-10) { status = 0; break; }
+    {
+      // termination: relative residuals 1e-11, complementarity 1e-13 (tighter than the CUDA solver's 1e-10 / 1e-12)
+      double gs = 1.0, bs = 1.0, rdn = 0.0, rpn = 0.0;
+      for (int i = 0; i < n; ++i) gs = std::max(gs, 1.0 + std::fabs(g[i]));
+      for (double v : beq) bs = std::max(bs, 1.0 + std::fabs(v));
+      for (double v : fin) bs = std::max(bs, 1.0 + std::fabs(v));
+      for (double v : rd) rdn = std::max(rdn, std::fabs(v));
+      for (double v : rp) rpn = std::max(rpn, std::fabs(v));
+      for (double v : rs) rpn = std::max(rpn, std::fabs(v));
+      if (rdn < 1e-11 * gs && rpn < 1e-11 * bs && mu < 1e-13) { status = 0; break; }
+    }
     // KKT matrix
     std::vector<double> K0(nk * nk, 0.0);
     for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) K0[i * nk + j] = H[i * n + j] + (i == j ? rho : 0.0);
