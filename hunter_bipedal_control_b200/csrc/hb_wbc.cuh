@@ -23,8 +23,8 @@ struct WbcShared {
   double q[16], v[16], qd[16], vd[16];
   double pos_m[12], vel_m[12], dJv[12], pos_d[12], vel_d[12];
   double Adv[6], com_d[3];
-  double Aw[12 * 16];   // weighted task rows acting on qdd (swing: <=6, base: 6)
-  double bw[12];
+  double Aw[18 * 16];   // weighted task rows acting on qdd (swing: <=12, base: 6)
+  double bw[18];
   double misc[32];
 };
 
@@ -128,7 +128,7 @@ __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const 
   if (stance_mode) nw = 6;
   else nw = 3 * (4 - nc) + 6;
   if (lane == 0) {
-    for (int i = 0; i < 12 * 16; ++i) sh.Aw[i] = 0.0;
+    for (int i = 0; i < 18 * 16; ++i) sh.Aw[i] = 0.0;
     if (stance_mode) {
       for (int i = 0; i < 6; ++i) { sh.Aw[i * 16 + i] = HB_WBC_WEIGHT_BASE; sh.bw[i] = 0.0; }
     } else {

@@ -1,0 +1,177 @@
+"""Pins the oracle's solver layer: the dense QP by an optimality certificate (KKT conditions on the recovered active set),
+the WBC assembly by physical facts, and the projected Riccati step by one dense KKT solve of the same equality-constrained
+LQ problem."""
+import numpy as np
+import pytest
+
+X0 = np.array([0, 0, 0, 0, 0, 0, 0, 0, 0.63, 0, 0, 0, .1, 0, .4, .93, .53, -.1, 0, -.4, .93, -.53])
+M = 12.586944
+
+
+def wbc_case(oracle, rng, mode):
+    xd = X0 + rng.uniform(-.05, .05, 22)
+    ud = np.zeros(22)
+    fl = [mode in (2, 3), mode in (1, 3), mode in (2, 3), mode in (1, 3)]
+    for c in range(4):
+        if fl[c]:
+            ud[3 * c + 2] = M * 9.81 / sum(fl)
+    ud[12:] = rng.uniform(-.5, .5, 10)
+    q = xd[6:] + rng.uniform(-.02, .02, 16)
+    rbd = np.r_[q[3:6], q[0:3], q[6:], rng.uniform(-.3, .3, 16)]
+    return xd, ud, rbd
+
+
+def kkt_certificate(H, g, A, lb, ub, rho, x, tol=1e-6):
+    n = len(g)
+    Hr = H + rho * np.eye(n)
+    Ax = A @ x
+    assert (Ax <= ub + 1e-7 * (1 + np.abs(ub))).all() and (Ax >= lb - 1e-7 * (1 + np.abs(lb))).all()
+    eq = np.isclose(lb, ub) & (np.abs(A).max(axis=1) > 0)
+    act_u = (~eq) & (ub < 1e19) & (np.abs(Ax - ub) < 1e-6) & (np.abs(A).max(axis=1) > 0)
+    act_l = (~eq) & (lb > -1e19) & (np.abs(Ax - lb) < 1e-6) & (np.abs(A).max(axis=1) > 0)
+    rows = np.vstack([A[eq], A[act_u], -A[act_l]])
+    grad = Hr @ x + g
+    lam, *_ = np.linalg.lstsq(rows.T, -grad, rcond=None)
+    res = np.abs(rows.T @ lam + grad).max()
+    assert res < tol * (1 + np.abs(g).max()), res
+    lam_in = lam[eq.sum():]
+    assert (lam_in > -1e-6 * (1 + np.abs(lam).max())).all()
+
+
+@pytest.mark.parametrize("mode,stance", [(3, True), (3, False), (2, False), (1, False), (0, False)])
+def test_wbc_qp_optimality(oracle, mode, stance):
+    rng = np.random.default_rng(10 + mode)
+    for _ in range(3):
+        xd, ud, rbd = wbc_case(oracle, rng, mode)
+        H, g, A, lb, ub = oracle.wbc_assemble(xd, ud, rbd, mode, stance)
+        nsw = 4 - sum([mode in (2, 3), mode in (1, 3)]) * 2
+        assert A.shape == (16 + 3 * nsw + 20 + 5 * (4 - nsw) + 3 * nsw, 38)      # 56 / 58 / 60 rows
+        assert np.linalg.matrix_rank(H) <= min(16, 6 + 3 * nsw if not stance else 6)
+        for rho in (1e-6, 1e-8):
+            x, st, it = oracle.qp_solve(H, g, A, lb, ub, rho)
+            assert st == 0 and it < 40
+            kkt_certificate(H, g, A, lb, ub, rho, x)
+            # EoM rows hold to 1e-9
+            assert np.abs(A[:16] @ x - ub[:16]).max() < 1e-8
+            # friction pyramid and torque limits
+            for c in range(4):
+                F = x[16 + 3 * c:19 + 3 * c]
+                assert F[2] > -1e-7 and abs(F[0]) <= 0.7 * F[2] + 1e-6 and abs(F[1]) <= 0.7 * F[2] + 1e-6
+            assert (np.abs(x[28:]) <= np.tile([28, 60, 60, 60, 28], 2) + 1e-6).all()
+
+
+def test_wbc_stance_mode_at_rest(oracle):
+    """Before /set_walk the task is qdd_base = 0 (WeightedWbc.cpp:83-94): at rest the base acceleration vanishes and
+    the contact forces carry the weight."""
+    u = np.zeros(22); u[[2, 5, 8, 11]] = M * 9.81 / 4
+    rbd = np.r_[X0[9:12], X0[6:9], X0[12:], np.zeros(16)]
+    x, st = oracle.wbc_solve(X0, u, rbd, 3, True, 1e-8)
+    assert st == 0
+    assert np.abs(x[:6]).max() < 1e-4
+    assert abs(x[[18, 21, 24, 27]].sum() - M * 9.81) < 0.05   # joint accelerations of the least-norm point carry a little momentum
+
+
+def test_least_norm_limit(oracle):
+    """The Tikhonov weight selects (to O(rho)) the least-norm point of the optimal face: ||x|| is non-increasing in rho and the
+    torques converge as rho -> 0 (qpOASES setToMPC regularisation)."""
+    rng = np.random.default_rng(5)
+    xd, ud, rbd = wbc_case(oracle, rng, 2)
+    H, g, A, lb, ub = oracle.wbc_assemble(xd, ud, rbd, 2, False)
+    xs = [oracle.qp_solve(H, g, A, lb, ub, r)[0] for r in (1e-7, 1e-8, 1e-9)]
+    assert np.abs(xs[1][28:] - xs[2][28:]).max() < 1e-4 * np.abs(xs[2][28:]).max()
+    assert np.abs(xs[0][28:] - xs[1][28:]).max() < 1e-3 * np.abs(xs[2][28:]).max()
+
+
+def test_random_qp_against_enumeration(oracle):
+    """Small strictly convex QPs: the IPM optimum equals the best vertex of the active-set enumeration."""
+    import itertools
+    rng = np.random.default_rng(7)
+    for _ in range(5):
+        n, m = 4, 5
+        Mx = rng.normal(size=(n, n)); H = Mx @ Mx.T + 0.1 * np.eye(n); g = rng.normal(size=n)
+        A = rng.normal(size=(m, n)); ub = rng.uniform(0.1, 1, m); lb = -1e20 * np.ones(m)
+        x, st, _ = oracle.qp_solve(H, g, A, lb, ub, 0.0)
+        assert st == 0
+        best = None
+        for k in range(m + 1):
+            for S in itertools.combinations(range(m), k):
+                S = list(S)
+                K = np.block([[H, A[S].T], [A[S], np.zeros((k, k))]])
+                try:
+                    sol = np.linalg.solve(K, np.r_[-g, ub[S]])
+                except np.linalg.LinAlgError:
+                    continue
+                xx, lam = sol[:n], sol[n:]
+                if (A @ xx <= ub + 1e-9).all() and (lam >= -1e-9).all():
+                    f = 0.5 * xx @ H @ xx + g @ xx
+                    if best is None or f < best[0]:
+                        best = (f, xx)
+        assert best is not None and np.abs(best[1] - x).max() < 1e-6
+
+
+def test_riccati_against_dense_kkt(oracle):
+    """One SQP iteration (projection + Riccati + forward pass) equals the solution of the same LQ subproblem assembled
+    as one dense KKT system, on a short horizon with a mode switch."""
+    N, dt = 6, 0.01
+    rng = np.random.default_rng(11)
+    mode = np.array([3, 3, 2, 2, 1, 1, 1], dtype=np.int32)
+    x0 = X0 + rng.uniform(-.02, .02, 22)
+    xref = np.tile(X0, (N + 1, 1)); swing = np.zeros((N + 1, 4, 6)); swing[:, :, 2] = 0.02
+    pos, *_ = oracle.ee_kinematics(x0, np.zeros(22))
+    swing[:, :, 0:2] = pos.reshape(4, 3)[None, :, 0:2]
+    swing = swing.reshape(N + 1, 24)
+    xt, ut = oracle.mpc_cold_start(N, dt, x0, mode)
+    xt = xt + rng.uniform(-.01, .01, xt.shape); xt[0] = x0
+    ut = ut + rng.uniform(-.5, .5, ut.shape)
+    # dense problem: variables [dx_1..dx_N, du_0..du_{N-1}], dx_0 = 0
+    nx, nu = 22, 22
+    nv = N * nx + N * nu
+    Hh = np.zeros((nv, nv)); gg = np.zeros(nv)
+    rows = []; rhs = []
+    ix = lambda k: slice((k - 1) * nx, k * nx)
+    iu = lambda k: slice(N * nx + k * nu, N * nx + (k + 1) * nu)
+    for k in range(N):
+        lq = oracle.node_lq(dt, xt[k], ut[k], xt[k + 1], xref[k], swing[k], int(mode[k]))
+        m = lq["m"]
+        Hh[iu(k), iu(k)] += dt * lq["R"]; gg[iu(k)] += dt * lq["r"]
+        if k > 0:
+            Hh[ix(k), ix(k)] += dt * lq["Q"]; gg[ix(k)] += dt * lq["q"]
+            Hh[iu(k), ix(k)] += dt * lq["P"]; Hh[ix(k), iu(k)] += dt * lq["P"].T
+        row = np.zeros((nx, nv)); row[:, ix(k + 1)] = -np.eye(nx); row[:, iu(k)] = lq["Bd"]
+        if k > 0:
+            row[:, ix(k)] = lq["Ad"]
+        rows.append(row); rhs.append(-lq["b"])
+        D, Cm, e = lq["D"][:m], lq["C"][:m], lq["e"][:m]
+        row = np.zeros((nu, nv)); row[:, iu(k)] = D.T @ D
+        if k > 0:
+            row[:, ix(k)] = D.T @ Cm
+        rows.append(row); rhs.append(-D.T @ e)
+    Aeq = np.vstack(rows); beq = np.concatenate(rhs)
+    # null-space method on the (rank-deficient but consistent) constraints
+    U, s, Vt = np.linalg.svd(Aeq)
+    r = (s > 1e-9 * s[0]).sum()
+    xp = Vt[:r].T @ ((U[:, :r].T @ beq) / s[:r])
+    Z = Vt[r:].T
+    z = np.linalg.solve(Z.T @ Hh @ Z, -Z.T @ (gg + Hh @ xp))
+    sol = xp + Z @ z
+    xt1, ut1, info = oracle.mpc_iteration(N, dt, x0, xref, swing, mode, xt, ut)
+    assert info["alpha"] > 0
+    dx = (xt1 - xt) / info["alpha"]; du = (ut1 - ut) / info["alpha"]
+    dx[0] = 0
+    for k in range(1, N + 1):
+        assert np.abs(dx[k] - sol[ix(k)]).max() < 1e-6 * max(1, np.abs(sol).max()), k
+    for k in range(N):
+        assert np.abs(du[k] - sol[iu(k)]).max() < 1e-6 * max(1, np.abs(sol).max()), k
+
+
+def test_sqp_converges_on_stance(oracle):
+    N, dt = 40, 0.01
+    mode = np.full(N + 1, 3, dtype=np.int32)
+    xref = np.tile(X0, (N + 1, 1)); swing = np.zeros((N + 1, 24))
+    xt, ut = oracle.mpc_cold_start(N, dt, X0, mode)
+    viol = []
+    for _ in range(4):
+        xt, ut, info = oracle.mpc_iteration(N, dt, X0, xref, swing, mode, xt, ut)
+        assert info["status"] == 0 and info["alpha"] == 1.0
+        viol.append(info["viol1"])
+    assert viol[-1] < 1e-6 and viol[1] < 0.1 * viol[0]
