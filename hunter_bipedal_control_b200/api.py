@@ -20,7 +20,7 @@ NX, NU, NQ, NJ, NWBC = 22, 22, 16, 10, 38
 HB_MAX_EVENTS, HB_MAX_TARGETS, HB_MAX_SEGMENTS = 32, 8, 24
 
 EXPORTED_SYMBOLS = [
-    "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_launch_count", "hb_stream",
+    "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_launch_count", "hb_stream", "hb_profile_enable", "hb_profile_read",
     "hb_wbc_qp_batch_dev", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
     "hb_policy_eval_batch_dev", "hb_control_step_batch_dev", "hb_rbd_to_centroidal_batch_dev", "hb_reference_expand_batch_dev",
     "hb_probe_flow_map_dev",
@@ -118,6 +118,15 @@ class Context:
     @property
     def launch_count(self):
         return int(self._lib.hb_launch_count(self._h))
+
+    def profile_enable(self, on=True):
+        _check(self._lib.hb_profile_enable(self._h, int(on)), "hb_profile_enable")
+
+    def profile_read(self):
+        ms = np.zeros(5); cnt = np.zeros(5, dtype=np.int64)
+        _check(self._lib.hb_profile_read(self._h, _ptr(ms), _ptr(cnt)), "hb_profile_read")
+        names = ["mpc_backward", "mpc_forward_linesearch", "wbc_assemble", "qp_ipm", "other"]
+        return {n: dict(ms=float(m), launches=int(c)) for n, m, c in zip(names, ms, cnt)}
 
     @property
     def stream_handle(self):

@@ -224,6 +224,10 @@ struct hb_ctx {
   double *s_qpH, *s_qpA;   // generic QP staging (sized on demand)
   size_t s_qp_cap;
   int last_cuda;
+  // optional per-kernel event timing (hb_profile_enable / hb_profile_read)
+  int prof_on, prof_n;
+  cudaEvent_t* prof_ev;   // 2 * PROF_MAX events
+  int* prof_kind;
 };
 
 namespace {
@@ -236,7 +240,19 @@ enum { HB_OK = 0, HB_EINVAL = -1, HB_ECUDA = -2, HB_ENOMEM = -3, HB_ECAP = -4 };
     if (e__ != cudaSuccess) { if (ctx) ctx->last_cuda = (int)e__; return HB_ECUDA; } \
   } while (0)
 
+constexpr int PROF_MAX = 4096;
+enum { K_BACKWARD = 0, K_FORWARD_LS = 1, K_WBC_ASSEMBLE = 2, K_QP = 3, K_OTHER = 4, K_NKINDS = 5 };
+inline void prof_begin(hb_ctx* ctx, int kind);
+inline void prof_end(hb_ctx* ctx);
+
 template <class T> cudaError_t dalloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
+
+inline void prof_begin(hb_ctx* ctx, int kind) {
+  if (ctx->prof_on && ctx->prof_n < PROF_MAX) { ctx->prof_kind[ctx->prof_n] = kind; cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream); }
+}
+inline void prof_end(hb_ctx* ctx) {
+  if (ctx->prof_on && ctx->prof_n < PROF_MAX) { cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n + 1], ctx->stream); ctx->prof_n++; }
+}
 
 int set_device(hb_ctx* ctx) { return cudaSetDevice(ctx->device) == cudaSuccess ? HB_OK : HB_ECUDA; }
 
@@ -336,6 +352,7 @@ int hb_destroy(hb_ctx* ctx) {
                   ctx->s_ud, ctx->s_sol, ctx->s_tau, ctx->s_t0, ctx->s_misc, ctx->s_mode, ctx->s_imode, ctx->s_status, ctx->s_iters, ctx->s_stance,
                   ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return HB_OK;
@@ -346,6 +363,35 @@ int hb_sync(hb_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->stream));
   return HB_OK;
 }
+int hb_profile_enable(hb_ctx* ctx, int on) {
+  if (!ctx) return HB_EINVAL;
+  if (set_device(ctx)) return HB_ECUDA;
+  if (on && !ctx->prof_ev) {
+    ctx->prof_ev = new (std::nothrow) cudaEvent_t[2 * PROF_MAX];
+    ctx->prof_kind = new (std::nothrow) int[PROF_MAX];
+    if (!ctx->prof_ev || !ctx->prof_kind) return HB_ENOMEM;
+    for (int i = 0; i < 2 * PROF_MAX; ++i) CK(cudaEventCreate(&ctx->prof_ev[i]));
+  }
+  ctx->prof_on = on ? 1 : 0;
+  ctx->prof_n = 0;
+  return HB_OK;
+}
+
+int hb_profile_read(hb_ctx* ctx, double* ms_per_kind, int64_t* count_per_kind) {
+  if (!ctx || !ms_per_kind || !count_per_kind) return HB_EINVAL;
+  if (set_device(ctx)) return HB_ECUDA;
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < K_NKINDS; ++k) { ms_per_kind[k] = 0.0; count_per_kind[k] = 0; }
+  for (int i = 0; i < ctx->prof_n; ++i) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+    ms_per_kind[ctx->prof_kind[i]] += ms;
+    count_per_kind[ctx->prof_kind[i]]++;
+  }
+  ctx->prof_n = 0;
+  return HB_OK;
+}
+
 int64_t hb_launch_count(const hb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* hb_stream(hb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
@@ -358,8 +404,10 @@ static int launch_qp(hb_ctx* ctx, int B, int n, int m, const double* H, const do
   if (wpb < 1) return HB_EINVAL;
   if (wpb > 1) wpb = 1;   // one warp per CTA: the shared-memory footprint, not the thread count, bounds residency
   const int blocks = (B + wpb - 1) / wpb;
+  prof_begin(ctx, K_QP);
   qp_batch_kernel<<<blocks, 32 * wpb, per_warp * wpb, ctx->stream>>>(B, n, m, H, g, A, lbA, ubA, sH, sA, sB, m_per, ctx->cfg.wbc_rho,
                                                                      ctx->cfg.qp_max_iter, x, status, iters);
+  prof_end(ctx);
   ctx->launches++;
   CK(cudaGetLastError());
   return HB_OK;
@@ -380,8 +428,10 @@ int hb_wbc_solve_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (set_device(ctx)) return HB_ECUDA;
   const int wpb = 4;
+  prof_begin(ctx, K_WBC_ASSEMBLE);
   wbc_assemble_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, sizeof(WbcShared) * wpb, ctx->stream>>>(B, x_des, u_des, rbd, mode, stance_mode, ctx->qH, ctx->qg,
                                                                                                ctx->qA, ctx->qlb, ctx->qub, ctx->qm);
+  prof_end(ctx);
   ctx->launches++;
   CK(cudaGetLastError());
   return launch_qp(ctx, B, NWBC, WBC_ROWS, ctx->qH, ctx->qg, ctx->qA, ctx->qlb, ctx->qub, QP_STRIDE_H, QP_STRIDE_A, WBC_ROWS, ctx->qm, sol,
@@ -407,10 +457,14 @@ int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x
   MpcArgs a;
   a.B = B; a.N = ctx->cfg.horizon_N; a.dt = ctx->cfg.dt; a.x_ref = x_ref; a.swing = swing_ref; a.mode = mode; a.xt = x_traj; a.ut = u_traj;
   a.gains = ctx->gains; a.dxt = ctx->dxt; a.dut = ctx->dut; a.perf = ctx->perf; a.flags = ctx->flags; a.x0 = x0;
+  prof_begin(ctx, K_BACKWARD);
   mpc_backward_kernel<<<B, 32, sizeof(MpcShared), ctx->stream>>>(a);
+  prof_end(ctx);
   ctx->launches++;
   CK(cudaGetLastError());
+  prof_begin(ctx, K_FORWARD_LS);
   mpc_forward_linesearch_kernel<<<B, 32, sizeof(LsShared), ctx->stream>>>(a, ctx->cfg.line_search_max_trials, info);
+  prof_end(ctx);
   ctx->launches++;
   CK(cudaGetLastError());
   return HB_OK;
