@@ -20,7 +20,7 @@ NX, NU, NQ, NJ, NWBC = 22, 22, 16, 10, 38
 HB_MAX_EVENTS, HB_MAX_TARGETS, HB_MAX_SEGMENTS = 32, 8, 24
 
 EXPORTED_SYMBOLS = [
-    "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_launch_count", "hb_stream", "hb_profile_enable", "hb_profile_read",
+    "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_last_cuda_error", "hb_launch_count", "hb_stream", "hb_profile_enable", "hb_profile_read",
     "hb_wbc_qp_batch_dev", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
     "hb_policy_eval_batch_dev", "hb_control_step_batch_dev", "hb_rbd_to_centroidal_batch_dev", "hb_reference_expand_batch_dev",
     "hb_probe_flow_map_dev",
@@ -63,14 +63,18 @@ def load_library():
                                   "(the product path has no CPU fallback)")
         _lib = C.CDLL(_LIB_PATH)
         _lib.hb_strerror.restype = C.c_char_p
+        _lib.hb_last_cuda_error.restype = C.c_char_p
         _lib.hb_launch_count.restype = C.c_int64
         _lib.hb_stream.restype = C.c_void_p
     return _lib
 
 
-def _check(rc, what):
+def _check(rc, what, ctx=None):
     if rc != 0:
-        raise HunterB200Error("%s failed: %s (%d)" % (what, load_library().hb_strerror(rc).decode(), rc))
+        extra = ""
+        if rc == -2 and ctx is not None:
+            extra = ": " + load_library().hb_last_cuda_error(ctx).decode()
+        raise HunterB200Error("%s failed: %s (%d)%s" % (what, load_library().hb_strerror(rc).decode(), rc, extra))
 
 
 def _ptr(a):
@@ -120,11 +124,11 @@ class Context:
         return int(self._lib.hb_launch_count(self._h))
 
     def profile_enable(self, on=True):
-        _check(self._lib.hb_profile_enable(self._h, int(on)), "hb_profile_enable")
+        _check(self._lib.hb_profile_enable(self._h, int(on)), "hb_profile_enable", self._h)
 
     def profile_read(self):
         ms = np.zeros(5); cnt = np.zeros(5, dtype=np.int64)
-        _check(self._lib.hb_profile_read(self._h, _ptr(ms), _ptr(cnt)), "hb_profile_read")
+        _check(self._lib.hb_profile_read(self._h, _ptr(ms), _ptr(cnt)), "hb_profile_read", self._h)
         names = ["mpc_backward", "mpc_forward_linesearch", "wbc_assemble", "qp_ipm", "other"]
         return {n: dict(ms=float(m), launches=int(c)) for n, m, c in zip(names, ms, cnt)}
 
@@ -138,7 +142,7 @@ class Context:
         B, n = g.shape
         m = lbA.shape[1]
         x = np.zeros((B, n)); st = np.zeros(B, dtype=np.int32); it = np.zeros(B, dtype=np.int32)
-        _check(self._lib.hb_wbc_qp_batch(self._h, B, n, m, _ptr(H), _ptr(g), _ptr(A), _ptr(lbA), _ptr(ubA), _ptr(x), _ptr(st), _ptr(it)), "hb_wbc_qp_batch")
+        _check(self._lib.hb_wbc_qp_batch(self._h, B, n, m, _ptr(H), _ptr(g), _ptr(A), _ptr(lbA), _ptr(ubA), _ptr(x), _ptr(st), _ptr(it)), "hb_wbc_qp_batch", self._h)
         return x, st, it
 
     def wbc_solve(self, x_des, u_des, rbd, mode, stance_mode=None):
@@ -147,14 +151,14 @@ class Context:
         mode = np.ascontiguousarray(mode, dtype=np.int32)
         sm = None if stance_mode is None else np.ascontiguousarray(stance_mode, dtype=np.uint8)
         sol = np.zeros((B, NWBC)); st = np.zeros(B, dtype=np.int32)
-        _check(self._lib.hb_wbc_solve_batch(self._h, B, _ptr(x_des), _ptr(u_des), _ptr(rbd), _ptr(mode), _ptr(sm), _ptr(sol), _ptr(st)), "hb_wbc_solve_batch")
+        _check(self._lib.hb_wbc_solve_batch(self._h, B, _ptr(x_des), _ptr(u_des), _ptr(rbd), _ptr(mode), _ptr(sm), _ptr(sol), _ptr(st)), "hb_wbc_solve_batch", self._h)
         return sol, st
 
     def mpc_cold_start(self, x0, mode):
         x0 = _f64(x0); B = x0.shape[0]
         mode = np.ascontiguousarray(mode, dtype=np.int32)
         xt = np.zeros((B, self.N + 1, NX)); ut = np.zeros((B, self.N, NU))
-        _check(self._lib.hb_mpc_cold_start_batch(self._h, B, _ptr(x0), _ptr(mode), _ptr(xt), _ptr(ut)), "hb_mpc_cold_start_batch")
+        _check(self._lib.hb_mpc_cold_start_batch(self._h, B, _ptr(x0), _ptr(mode), _ptr(xt), _ptr(ut)), "hb_mpc_cold_start_batch", self._h)
         return xt, ut
 
     def mpc_solve(self, x0, x_ref, swing, mode, xt, ut):
@@ -163,7 +167,7 @@ class Context:
         mode = np.ascontiguousarray(mode, dtype=np.int32)
         xt = _f64(xt).copy(); ut = _f64(ut).copy()
         info = np.zeros(B, dtype=INFO_DTYPE)
-        _check(self._lib.hb_mpc_solve_batch(self._h, B, _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(xt), _ptr(ut), _ptr(info)), "hb_mpc_solve_batch")
+        _check(self._lib.hb_mpc_solve_batch(self._h, B, _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(xt), _ptr(ut), _ptr(info)), "hb_mpc_solve_batch", self._h)
         return xt, ut, info
 
     def control_step(self, t_rel, x0, x_ref, swing, mode, rbd, xt, ut):
@@ -174,26 +178,26 @@ class Context:
         info = np.zeros(B, dtype=INFO_DTYPE)
         sol = np.zeros((B, NWBC)); tau = np.zeros((B, NJ)); st = np.zeros(B, dtype=np.int32)
         _check(self._lib.hb_control_step_batch(self._h, B, C.c_double(t_rel), _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(rbd), _ptr(xt), _ptr(ut),
-                                               _ptr(info), _ptr(sol), _ptr(tau), _ptr(st)), "hb_control_step_batch")
+                                               _ptr(info), _ptr(sol), _ptr(tau), _ptr(st)), "hb_control_step_batch", self._h)
         return xt, ut, info, sol, tau, st
 
     def rbd_to_centroidal(self, rbd):
         rbd = _f64(rbd); B = rbd.shape[0]
         x = np.zeros((B, NX))
-        _check(self._lib.hb_rbd_to_centroidal_batch(self._h, B, _ptr(rbd), _ptr(x)), "hb_rbd_to_centroidal_batch")
+        _check(self._lib.hb_rbd_to_centroidal_batch(self._h, B, _ptr(rbd), _ptr(x)), "hb_rbd_to_centroidal_batch", self._h)
         return x
 
     def reference_expand(self, t0, refs):
         """refs: ctypes array of HbReference (len B)."""
         t0 = _f64(t0); B = t0.shape[0]
         x_ref = np.zeros((B, self.N + 1, NX)); swing = np.zeros((B, self.N + 1, 24)); mode = np.zeros((B, self.N + 1), dtype=np.int32)
-        _check(self._lib.hb_reference_expand_batch(self._h, B, _ptr(t0), C.cast(refs, C.c_void_p), _ptr(x_ref), _ptr(swing), _ptr(mode)), "hb_reference_expand_batch")
+        _check(self._lib.hb_reference_expand_batch(self._h, B, _ptr(t0), C.cast(refs, C.c_void_p), _ptr(x_ref), _ptr(swing), _ptr(mode)), "hb_reference_expand_batch", self._h)
         return x_ref, swing, mode
 
     def probe_flow_map(self, x, u):
         x, u = _f64(x), _f64(u); B = x.shape[0]
         f = np.zeros((B, NX)); A = np.zeros((B, NX, NX)); Bm = np.zeros((B, NX, NU)); ee = np.zeros((B, 24 + 36 * NX))
-        _check(self._lib.hb_probe_flow_map(self._h, B, _ptr(x), _ptr(u), _ptr(f), _ptr(A), _ptr(Bm), _ptr(ee)), "hb_probe_flow_map")
+        _check(self._lib.hb_probe_flow_map(self._h, B, _ptr(x), _ptr(u), _ptr(f), _ptr(A), _ptr(Bm), _ptr(ee)), "hb_probe_flow_map", self._h)
         out = dict(f=f, A=A, B=Bm, epos=ee[:, :12], evel=ee[:, 12:24], dpos_dx=ee[:, 24:24 + 264].reshape(B, 12, NX),
                    dvel_dx=ee[:, 24 + 264:24 + 528].reshape(B, 12, NX), dvel_du=ee[:, 24 + 528:].reshape(B, 12, NX))
         return out
@@ -201,10 +205,10 @@ class Context:
     # ------------------------------------------------------------------ device-pointer calls (torch cuda tensors, asynchronous)
     def mpc_solve_dev(self, x0, x_ref, swing, mode, xt, ut, info=None):
         B = x0.shape[0]
-        _check(self._lib.hb_mpc_solve_batch_dev(self._h, B, _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(xt), _ptr(ut), _ptr(info)), "hb_mpc_solve_batch_dev")
+        _check(self._lib.hb_mpc_solve_batch_dev(self._h, B, _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(xt), _ptr(ut), _ptr(info)), "hb_mpc_solve_batch_dev", self._h)
 
     def mpc_cold_start_dev(self, x0, mode, xt, ut):
-        _check(self._lib.hb_mpc_cold_start_batch_dev(self._h, x0.shape[0], _ptr(x0), _ptr(mode), _ptr(xt), _ptr(ut)), "hb_mpc_cold_start_batch_dev")
+        _check(self._lib.hb_mpc_cold_start_batch_dev(self._h, x0.shape[0], _ptr(x0), _ptr(mode), _ptr(xt), _ptr(ut)), "hb_mpc_cold_start_batch_dev", self._h)
 
     def wbc_solve_dev(self, x_des, u_des, rbd, mode, stance_mode, sol, status=None):
         _check(self._lib.hb_wbc_solve_batch_dev(self._h, x_des.shape[0], _ptr(x_des), _ptr(u_des), _ptr(rbd), _ptr(mode), _ptr(stance_mode), _ptr(sol), _ptr(status)),
@@ -216,7 +220,7 @@ class Context:
 
     def control_step_dev(self, t_rel, x0, x_ref, swing, mode, rbd, xt, ut, info, sol, tau, status=None):
         _check(self._lib.hb_control_step_batch_dev(self._h, x0.shape[0], C.c_double(t_rel), _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(rbd), _ptr(xt),
-                                                   _ptr(ut), _ptr(info), _ptr(sol), _ptr(tau), _ptr(status)), "hb_control_step_batch_dev")
+                                                   _ptr(ut), _ptr(info), _ptr(sol), _ptr(tau), _ptr(status)), "hb_control_step_batch_dev", self._h)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

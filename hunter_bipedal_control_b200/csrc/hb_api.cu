@@ -392,6 +392,8 @@ int hb_profile_read(hb_ctx* ctx, double* ms_per_kind, int64_t* count_per_kind) {
   return HB_OK;
 }
 
+const char* hb_last_cuda_error(const hb_ctx* ctx) { return ctx ? cudaGetErrorString((cudaError_t)ctx->last_cuda) : "no context"; }
+
 int64_t hb_launch_count(const hb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* hb_stream(hb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 

@@ -52,7 +52,7 @@ struct MpcShared {
   // vectors
   double x[NX], u[NX], xn[NX], x2[NX], f1[NX], f2[NX], b[NX], xref[NX], swing[24];
   double q[NX], r[NX], e[16], pe[NX], sv[NX], bt[NX], sb[NX], qt[NX], rt[NX], rRpe[NX], hu[NX], kff[NX], idg[NX];
-  double epos[12], evel[12], com[3], vgen[16], gxy[4 * 2 * NX + 8];
+  double epos[12], evel[12], com[3], vgen[16], gxy[8 * 2 * NX + 8];
   int freeidx[NX], pivflag[NX], rowc[16], rowa[16], rowt[16];
 };
 
@@ -384,7 +384,7 @@ __device__ inline int node_cost_constraints_warp(MpcShared& sh, int mode, double
       const int row = 3 * c + a;
       double* gx = sh.gxy + npair * 2 * NX; double* gu = gx + NX;
       if (lane < NX) { gx[lane] = dvel_dx[row * NX + lane] + HB_XY_POSITION_GAIN * dpos_dx[row * NX + lane]; gu[lane] = dvel_du[row * NX + lane]; }
-      if (lane == 0) sh.gxy[8 * NX + npair] = sh.evel[row] - sh.swing[6 * c + 3 + a] + HB_XY_POSITION_GAIN * (sh.epos[row] - sh.swing[6 * c + a]);
+      if (lane == 0) sh.gxy[16 * NX + npair] = sh.evel[row] - sh.swing[6 * c + 3 + a] + HB_XY_POSITION_GAIN * (sh.epos[row] - sh.swing[6 * c + a]);
       ++npair;
     }
   }
@@ -393,7 +393,7 @@ __device__ inline int node_cost_constraints_warp(MpcShared& sh, int mode, double
     const double w = HB_SOFT_SWING_WEIGHT;
     for (int pidx = 0; pidx < npair; ++pidx) {
       const double* gx = sh.gxy + pidx * 2 * NX; const double* gu = gx + NX;
-      const double h = sh.gxy[8 * NX + pidx];
+      const double h = sh.gxy[16 * NX + pidx];
       if (lane == 0) cost += 0.5 * w * h * h;
       if (lane < NX) {
         const int j = lane;

@@ -72,6 +72,8 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out);
 int hb_destroy(hb_ctx* ctx);
 int hb_sync(hb_ctx* ctx);
 const char* hb_strerror(int code);
+/* text of the last CUDA runtime error seen by this context (diagnostics for return code -2) */
+const char* hb_last_cuda_error(const hb_ctx* ctx);
 /* number of kernel launches issued through this context since creation (bench.py reports it as gpu_launches) */
 int64_t hb_launch_count(const hb_ctx* ctx);
 /* per-kernel device timing with CUDA events on the context's stream (used by bench.py for the roofline line):

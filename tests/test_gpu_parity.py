@@ -150,12 +150,21 @@ def test_mpc_backtracking_line_search_vs_oracle(oracle):
     """A poor warm start forces alpha < 1 on some instances: the filter line search must take the same decisions."""
     import hunter_bipedal_control_b200 as hb
     sc = S()
-    N, dt, B = 16, 0.02, 8
+    N, dt = 16, 0.02
+    seeds = [9, 21, 1, 5, 13, 17, 25, 29]     # 9 and 21 back-track (alpha 0.5 / 0.25) with the recipe below
+    B = len(seeds)
     ctx = hb.Context(horizon_N=N, dt=dt, max_batch=B)
-    x0, x_ref, swing, mode = sc.make_batch(B, N, dt, gait="trot", seed=31)
-    rng = np.random.default_rng(31)
-    xt, ut = ctx.mpc_cold_start(x0, mode)
-    xt = xt + rng.uniform(-.15, .15, xt.shape); ut = ut + rng.uniform(-40, 40, ut.shape)
+    x0 = np.zeros((B, 22)); x_ref = np.zeros((B, N + 1, 22)); swing = np.zeros((B, N + 1, 24)); mode = np.zeros((B, N + 1), dtype=np.int32)
+    xt = np.zeros((B, N + 1, 22)); ut = np.zeros((B, N, 22))
+    for i, seed in enumerate(seeds):
+        rng = np.random.default_rng(seed)
+        a, b, c, d = sc.make_batch(1, N, dt, gait=["trot", "flying_trot", "standing_trot"][seed % 3], seed=1000 + seed)
+        x0[i], x_ref[i], swing[i], mode[i] = a[0], b[0], c[0], d[0]
+        xi, ui = oracle.mpc_cold_start(N, dt, x0[i], mode[i])
+        for _ in range(3):                                     # converge, then push the joint trajectory far off
+            xi, ui, _ = oracle.mpc_iteration(N, dt, x0[i], x_ref[i], swing[i], mode[i], xi, ui)
+        xi[1:, 12:] += rng.uniform(-0.6, 0.6, (N, 10))
+        xt[i], ut[i] = xi, ui
     xt1, ut1, info = ctx.mpc_solve(x0, x_ref, swing, mode, xt, ut)
     n_bt = 0
     for i in range(B):
@@ -245,7 +254,8 @@ def test_reference_expand_matches_host_generator(gpu_ctx):
                 r.target_states[k][j] = c["target_states"][k][j]
         for cc in range(4):
             for a in range(3):
-                segs = c["segments"][cc][a]
+                segs = [sg for sg in c["segments"][cc][a] if sg[0] <= N * dt + 1e-9]   # only what the horizon can see
+                assert len(segs) <= 24
                 r.n_segments[cc][a] = len(segs)
                 for s, sg in enumerate(segs):
                     for j in range(6):
