@@ -241,7 +241,9 @@ def main():
         peaks, src = load_peaks()
         value = total_B * args.steps / (ms * 1e-3)
         e2e_val = total_B * args.steps / (e2e_ms * 1e-3)
-        bk = prof["mpc_backward"]
+        mpc_names = [n for n in prof if n.startswith("mpc_")]
+        top = max(mpc_names, key=lambda n: prof[n]["ms"])     # dominant kernel of the step
+        bk = prof[top]
         bk_ms = bk["ms"] / max(1, bk["launches"])
         ach = B * BYTES_PER_MPC_SOLVE / (bk_ms * 1e-3) / 1e9 if bk_ms > 0 else None
         step_ms = ms / args.steps
@@ -254,7 +256,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches),
                 "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
-                "roofline": {"bound": "hbm", "kernel": "mpc_backward_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": (ach / peaks["hbm_gbs"]) if ach else None, "peak_source": src, "traffic": None,
                              "share_of_step": bk_ms / step_ms if step_ms > 0 else None,
                              "note": "latency/FP64-bound path: the HBM fraction is small by construction (SURVEY 8d); see roofline_fp64"},

@@ -127,9 +127,9 @@ class Context:
         _check(self._lib.hb_profile_enable(self._h, int(on)), "hb_profile_enable", self._h)
 
     def profile_read(self):
-        ms = np.zeros(5); cnt = np.zeros(5, dtype=np.int64)
+        ms = np.zeros(7); cnt = np.zeros(7, dtype=np.int64)
         _check(self._lib.hb_profile_read(self._h, _ptr(ms), _ptr(cnt)), "hb_profile_read", self._h)
-        names = ["mpc_backward", "mpc_forward_linesearch", "wbc_assemble", "qp_ipm", "other"]
+        names = ["mpc_riccati", "mpc_forward_linesearch", "wbc_assemble", "qp_ipm", "other", "mpc_linearise", "mpc_lq_project"]
         return {n: dict(ms=float(m), launches=int(c)) for n, m, c in zip(names, ms, cnt)}
 
     @property

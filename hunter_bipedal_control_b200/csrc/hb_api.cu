@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -11,6 +12,7 @@
 #include "hb_mpc.cuh"
 #include "hb_qp.cuh"
 #include "hb_rbd.cuh"
+#include "hb_sqp.cuh"
 #include "hb_wbc.cuh"
 
 using namespace hb;
@@ -211,6 +213,8 @@ struct hb_ctx {
   int64_t launches;
   // MPC scratch
   double *gains, *dxt, *dut, *perf;
+  double *lin, *proj, *rk;   // version-2 pipeline records
+  int sqp_version;           // 2 (default) or 1 (HB_SQP_VERSION=1: fused backward sweep, kept for A/B comparison)
   int32_t* flags;
   // WBC scratch
   double *qH, *qg, *qA, *qlb, *qub, *xdes, *udes, *wsol;
@@ -241,7 +245,7 @@ enum { HB_OK = 0, HB_EINVAL = -1, HB_ECUDA = -2, HB_ENOMEM = -3, HB_ECAP = -4 };
   } while (0)
 
 constexpr int PROF_MAX = 4096;
-enum { K_BACKWARD = 0, K_FORWARD_LS = 1, K_WBC_ASSEMBLE = 2, K_QP = 3, K_OTHER = 4, K_NKINDS = 5 };
+enum { K_BACKWARD = 0, K_FORWARD_LS = 1, K_WBC_ASSEMBLE = 2, K_QP = 3, K_OTHER = 4, K_LIN = 5, K_LQ = 6, K_NKINDS = 7 };
 inline void prof_begin(hb_ctx* ctx, int kind);
 inline void prof_end(hb_ctx* ctx);
 
@@ -322,7 +326,12 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   if (e != cudaSuccess) { ctx->last_cuda = (int)e; hb_destroy(ctx); return HB_ECUDA; }
   const size_t B = cfg->max_batch, N = cfg->horizon_N;
   bool ok = true;
-  ok = ok && dalloc(&ctx->gains, B * N * GAIN_STRIDE) == cudaSuccess;
+  {
+    const char* v = getenv("HB_SQP_VERSION");
+    ctx->sqp_version = (v && v[0] == '1') ? 1 : 2;
+  }
+  if (ctx->sqp_version == 1) ok = ok && dalloc(&ctx->gains, B * N * GAIN_STRIDE) == cudaSuccess;
+  else ok = ok && dalloc(&ctx->lin, B * N * LIN_STRIDE) == cudaSuccess && dalloc(&ctx->proj, B * N * PJ_STRIDE) == cudaSuccess && dalloc(&ctx->rk, B * N * RK_STRIDE) == cudaSuccess;
   ok = ok && dalloc(&ctx->dxt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->dut, B * N * NU) == cudaSuccess;
   ok = ok && dalloc(&ctx->perf, B * 4) == cudaSuccess && dalloc(&ctx->flags, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->qH, B * QP_STRIDE_H) == cudaSuccess && dalloc(&ctx->qg, B * NWBC) == cudaSuccess && dalloc(&ctx->qA, B * QP_STRIDE_A) == cudaSuccess;
@@ -340,6 +349,10 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   cudaFuncSetAttribute(probe_flow_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MpcShared));
   cudaFuncSetAttribute(mpc_forward_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsShared));
   cudaFuncSetAttribute(qp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(LinHalf)));
+  cudaFuncSetAttribute(lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqShared));
+  cudaFuncSetAttribute(riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicShared));
+  cudaFuncSetAttribute(forward_linesearch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fw2Shared));
   *out = ctx;
   return HB_OK;
 }
@@ -347,7 +360,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
 int hb_destroy(hb_ctx* ctx) {
   if (!ctx) return HB_EINVAL;
   cudaSetDevice(ctx->device);
-  void* ptrs[] = {ctx->gains, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->qH, ctx->qg, ctx->qA, ctx->qlb, ctx->qub, ctx->qm, ctx->xdes, ctx->udes,
+  void* ptrs[] = {ctx->lin, ctx->proj, ctx->rk, ctx->gains, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->qH, ctx->qg, ctx->qA, ctx->qlb, ctx->qub, ctx->qm, ctx->xdes, ctx->udes,
                   ctx->wsol, ctx->wstatus, ctx->witers, ctx->wmode, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_xt, ctx->s_ut, ctx->s_rbd, ctx->s_xd,
                   ctx->s_ud, ctx->s_sol, ctx->s_tau, ctx->s_t0, ctx->s_misc, ctx->s_mode, ctx->s_imode, ctx->s_status, ctx->s_iters, ctx->s_stance,
                   ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA};
@@ -456,16 +469,44 @@ int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x
   if (B == 0) return HB_OK;
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (set_device(ctx)) return HB_ECUDA;
-  MpcArgs a;
+  if (ctx->sqp_version == 1) {
+    MpcArgs a;
+    a.B = B; a.N = ctx->cfg.horizon_N; a.dt = ctx->cfg.dt; a.x_ref = x_ref; a.swing = swing_ref; a.mode = mode; a.xt = x_traj; a.ut = u_traj;
+    a.gains = ctx->gains; a.dxt = ctx->dxt; a.dut = ctx->dut; a.perf = ctx->perf; a.flags = ctx->flags; a.x0 = x0;
+    prof_begin(ctx, K_BACKWARD);
+    mpc_backward_kernel<<<B, 32, sizeof(MpcShared), ctx->stream>>>(a);
+    prof_end(ctx);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    prof_begin(ctx, K_FORWARD_LS);
+    mpc_forward_linesearch_kernel<<<B, 32, sizeof(LsShared), ctx->stream>>>(a, ctx->cfg.line_search_max_trials, info);
+    prof_end(ctx);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return HB_OK;
+  }
+  SqpArgs a;
   a.B = B; a.N = ctx->cfg.horizon_N; a.dt = ctx->cfg.dt; a.x_ref = x_ref; a.swing = swing_ref; a.mode = mode; a.xt = x_traj; a.ut = u_traj;
-  a.gains = ctx->gains; a.dxt = ctx->dxt; a.dut = ctx->dut; a.perf = ctx->perf; a.flags = ctx->flags; a.x0 = x0;
+  a.lin = ctx->lin; a.proj = ctx->proj; a.rk = ctx->rk; a.dxt = ctx->dxt; a.dut = ctx->dut; a.perf = ctx->perf; a.flags = ctx->flags; a.x0 = x0;
+  const int N = a.N, NP = (N + 1) / 2;
+  const long long nw = (long long)B * NP;
+  prof_begin(ctx, K_LIN);
+  lin_kernel<<<(unsigned)((nw + 1) / 2), 64, 4 * sizeof(LinHalf), ctx->stream>>>(a);
+  prof_end(ctx);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  prof_begin(ctx, K_LQ);
+  lq_kernel<<<(unsigned)((long long)B * N), 32, sizeof(LqShared), ctx->stream>>>(a);
+  prof_end(ctx);
+  ctx->launches++;
+  CK(cudaGetLastError());
   prof_begin(ctx, K_BACKWARD);
-  mpc_backward_kernel<<<B, 32, sizeof(MpcShared), ctx->stream>>>(a);
+  riccati_kernel<<<B, 32, sizeof(RicShared), ctx->stream>>>(a);
   prof_end(ctx);
   ctx->launches++;
   CK(cudaGetLastError());
   prof_begin(ctx, K_FORWARD_LS);
-  mpc_forward_linesearch_kernel<<<B, 32, sizeof(LsShared), ctx->stream>>>(a, ctx->cfg.line_search_max_trials, info);
+  forward_linesearch2_kernel<<<B, 32, sizeof(Fw2Shared), ctx->stream>>>(a, ctx->cfg.line_search_max_trials, info);
   prof_end(ctx);
   ctx->launches++;
   CK(cudaGetLastError());

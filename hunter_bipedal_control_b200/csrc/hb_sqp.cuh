@@ -1,0 +1,828 @@
+// SQP iteration, version 2: the per-node work is split from the sequential recursion so that every SM runs many warps.
+//
+//   K0 lin_kernel      one warp = TWO horizon nodes (half-warp each). Lane-parallel unit / dual sweeps of the kinematic tree
+//                      give, per node and RK2 stage, the non-trivial rows of d f/dx, d f/du and the contact kinematics with
+//                      their Jacobians. Output: a compact "linearisation record" per node (LIN_STRIDE doubles).
+//   K1 lq_kernel       one warp = one node. RK2 sensitivities using the row sparsity of the flow-map Jacobian, cost and soft
+//                      constraints, equality constraints, least-squares projection of the contact-velocity rows (10x10 normal
+//                      equations), projected LQ model. Output: "projected record" (PROJ_STRIDE doubles).
+//   K2 riccati_kernel  one warp = one instance, sequential in k, only the value-function recursion: S, s, K, k.
+//   K3 forward_ls      one warp = one instance: forward pass through the projected model, then the filter line search with
+//                      lanes = nodes (shared with version 1: flow_map_lane / node_values_lane in hb_mpc.cuh).
+//
+// Block structure used throughout (x = [hbar(6) | p(3) | theta(3) | qj(10)], u = [F(12) | vj(10)]):
+//   d f/dx has non-zero rows 3..11 only; d f/dF is (1/m) I in rows 0..2, (r_c - com)x / m in rows 3..5;
+//   d f/dvj is -A_b^-1 A_j in rows 6..11 and I in rows 12..21;
+//   the state-input equalities split into "swing force = 0" (selector rows) and contact-velocity rows that involve vj only,
+//   so the projection is a 10-dimensional problem; free inputs are the stance forces and the null space of the velocity rows.
+#pragma once
+#include "hb_common.cuh"
+#include "hb_mpc.cuh"
+#include "hb_rbd.cuh"
+
+namespace hb {
+
+// ---------------------------------------------------------------- record layouts (doubles)
+constexpr int LIN_F1 = 0, LIN_F2 = 22, LIN_A1 = 44, LIN_A2 = 242, LIN_BF1 = 440, LIN_BF2 = 476, LIN_BV1 = 512, LIN_BV2 = 572,
+              LIN_EPOS = 632, LIN_EVEL = 644, LIN_DPQ = 656, LIN_DVX = 812, LIN_DVV = 1076, LIN_STRIDE = 1200;
+constexpr int NTMAX = 16;   // free inputs after projection: 3 n_stance + (10 - rank of the velocity rows); 12 / 9 / 6 in regular poses
+constexpr int NVMAX = 8;    // null-space columns kept for the velocity rows
+constexpr int PJ_AT = 0, PJ_BT = 484, PJ_BTV = 836, PJ_QT = 858, PJ_PT = 1342, PJ_RT = 1694, PJ_QV = 1950, PJ_RV = 1972,
+              PJ_PXV = 1988, PJ_NV = 2208, PJ_PEV = 2288, PJ_META = 2298, PJ_STRIDE = 2320;
+// META: [0] nt, [1] n_stance_force_dims, [2] nv, [3] cost, [4] defect^2, [5] eq^2, [6] overflow flag
+constexpr int RK_STRIDE = NTMAX * NX + NTMAX;  // K (nt x 22, ld 22) + kff
+
+// ---------------------------------------------------------------- K0
+struct LinHalf {
+  double x[NX], u[NU], x2[NX], f[NX];
+  double Acm[6 * 16], Jc[12 * 16], dh[6 * NDIR], dcom[3 * NDIR], dp[12 * NDIR], dv[12 * NDIR];
+  double Abinv[36], AbinvAj[6 * NJ], dvb[6 * NDIR], vgen[16], epos[12], evel[12], com[3];
+};
+
+// Linearise the flow map of one node at state xs (half-warp cooperative; `hl` = lane within the half, `act` = node exists).
+// Writes f, compact A rows 3..11 (9x22), Bf rows 3..5 (3x12), Bv rows 6..11 (6x10); with want_ee the contact kinematics record.
+__device__ __noinline__ void lin_half(LinHalf& sh, const double* xs, int hl, bool act, double* rec_f, double* rec_A, double* rec_Bf,
+                                      double* rec_Bv, bool want_ee, double* rec) {
+  const double m = c_model.total_mass;
+  {
+    double q[NQ], e[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) { q[i] = xs[6 + i]; e[i] = (i == hl) ? 1.0 : 0.0; }
+    KinOut<double> o;
+    kin_pass<double>(q, e, o);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) sh.Acm[r * 16 + hl] = o.h[r];
+#pragma unroll
+    for (int r = 0; r < 12; ++r) sh.Jc[r * 16 + hl] = o.cvel[r];
+    if (hl == 0) {
+#pragma unroll
+      for (int r = 0; r < 12; ++r) sh.epos[r] = o.cpos[r];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) sh.com[r] = o.com[r];
+    }
+  }
+  __syncwarp();
+  if (hl < 7) {
+    double Ab[36], rhs[6], y[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) Ab[6 * r + c] = sh.Acm[r * 16 + c];
+    if (hl < 6) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) rhs[r] = (r == hl) ? 1.0 : 0.0;
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { double s = m * xs[r]; for (int j = 0; j < NJ; ++j) s -= sh.Acm[r * 16 + 6 + j] * sh.u[12 + j]; rhs[r] = s; }
+    }
+    solve6(Ab, rhs, y);
+    if (hl < 6) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) sh.Abinv[6 * r + hl] = y[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) sh.vgen[r] = y[r];
+    }
+  }
+  if (hl >= 6) sh.vgen[hl] = sh.u[6 + hl];   // vgen[6..15] = joint velocities u[12..21]
+  __syncwarp();
+  if (hl < NJ) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { double s = 0.0; for (int c = 0; c < 6; ++c) s += sh.Abinv[6 * r + c] * sh.Acm[c * 16 + 6 + hl]; sh.AbinvAj[r * NJ + hl] = s; }
+  }
+  if (hl < NDIR) {
+    D1 q[NQ], v[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) { q[i] = D1(xs[6 + i], (i == 3 + hl) ? 1.0 : 0.0); v[i] = D1(sh.vgen[i], 0.0); }
+    KinOut<D1> o;
+    kin_pass<D1>(q, v, o);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) sh.dh[r * NDIR + hl] = o.h[r].d;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) sh.dcom[r * NDIR + hl] = o.com[r].d;
+#pragma unroll
+    for (int r = 0; r < 12; ++r) { sh.dp[r * NDIR + hl] = o.cpos[r].d; sh.dv[r * NDIR + hl] = o.cvel[r].d; }
+    if (hl == 0) {
+#pragma unroll
+      for (int r = 0; r < 12; ++r) sh.evel[r] = o.cvel[r].v;
+    }
+  }
+  __syncwarp();
+  if (hl < NDIR) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { double s = 0.0; for (int c = 0; c < 6; ++c) s += sh.Abinv[6 * r + c] * sh.dh[c * NDIR + hl]; sh.dvb[r * NDIR + hl] = -s; }
+  }
+  // flow map value (all 16 lanes of the half take part; entries 16..21 by lanes 0..5 in a second round)
+  for (int i = hl; i < NX; i += 16) {
+    double val;
+    if (i < 3) {
+      double s = 0.0;
+      for (int c = 0; c < NC; ++c) s += sh.u[3 * c + i];
+      val = s / m - (i == 2 ? HB_GRAVITY : 0.0);
+    } else if (i < 6) {
+      const int a = i - 3, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+      double s = 0.0;
+      for (int c = 0; c < NC; ++c) s += (sh.epos[3 * c + a1] - sh.com[a1]) * sh.u[3 * c + a2] - (sh.epos[3 * c + a2] - sh.com[a2]) * sh.u[3 * c + a1];
+      val = s / m;
+    } else if (i < 12) val = sh.vgen[i - 6];
+    else val = sh.u[i];
+    sh.f[i] = val;
+    if (act) rec_f[i] = val;
+  }
+  __syncwarp();
+  if (!act) return;
+  // compact Jacobian blocks; column j of the 9x22 block by lane (two rounds for 22 columns)
+  for (int j = hl; j < NX; j += 16) {
+    double ca[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ca[i] = 0.0;
+    if (j < 6) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) ca[3 + r] = m * sh.Abinv[6 * r + j];
+    } else if (j >= 9) {
+      const int k = j - 9;
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+      for (int c = 0; c < NC; ++c) {
+        const double d0 = sh.dp[(3 * c) * NDIR + k] - sh.dcom[k], d1 = sh.dp[(3 * c + 1) * NDIR + k] - sh.dcom[NDIR + k], d2 = sh.dp[(3 * c + 2) * NDIR + k] - sh.dcom[2 * NDIR + k];
+        const double* F = sh.u + 3 * c;
+        t0 += d1 * F[2] - d2 * F[1]; t1 += d2 * F[0] - d0 * F[2]; t2 += d0 * F[1] - d1 * F[0];
+      }
+      ca[0] = t0 / m; ca[1] = t1 / m; ca[2] = t2 / m;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) ca[3 + r] = sh.dvb[r * NDIR + k];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rec_A[i * NX + j] = ca[i];
+  }
+  if (hl < 12) {
+    const int c = hl / 3, a = hl - 3 * c;
+    const double r0 = (sh.epos[3 * c] - sh.com[0]) / m, r1 = (sh.epos[3 * c + 1] - sh.com[1]) / m, r2 = (sh.epos[3 * c + 2] - sh.com[2]) / m;
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0;   // (r - com) x e_a / m
+    if (a == 0) { b1 = r2; b2 = -r1; } else if (a == 1) { b0 = -r2; b2 = r0; } else { b0 = r1; b1 = -r0; }
+    rec_Bf[0 * 12 + hl] = b0; rec_Bf[1 * 12 + hl] = b1; rec_Bf[2 * 12 + hl] = b2;
+  }
+  if (hl < NJ) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) rec_Bv[r * NJ + hl] = -sh.AbinvAj[r * NJ + hl];
+  }
+  if (want_ee) {
+    if (hl < 12) { rec[LIN_EPOS + hl] = sh.epos[hl]; rec[LIN_EVEL + hl] = sh.evel[hl]; }
+    for (int j = hl; j < NX; j += 16) {
+      for (int r = 0; r < 12; ++r) {
+        double vx = 0.0;
+        if (j < 6) { for (int c = 0; c < 6; ++c) vx += sh.Jc[r * 16 + c] * sh.Abinv[6 * c + j]; vx *= m; }
+        else if (j >= 9) { const int k = j - 9; vx = sh.dv[r * NDIR + k]; for (int c = 0; c < 6; ++c) vx += sh.Jc[r * 16 + c] * sh.dvb[c * NDIR + k]; rec[LIN_DPQ + r * NDIR + k] = sh.dp[r * NDIR + k]; }
+        rec[LIN_DVX + r * NX + j] = vx;
+        if (j >= 12) { const int jj = j - 12; double vu = sh.Jc[r * 16 + 6 + jj]; for (int c = 0; c < 6; ++c) vu -= sh.Jc[r * 16 + c] * sh.AbinvAj[c * NJ + jj]; rec[LIN_DVV + r * NJ + jj] = vu; }
+      }
+    }
+  }
+}
+
+struct SqpArgs {
+  int B, N;
+  double dt;
+  const double* x_ref; const double* swing; const int32_t* mode;
+  double* xt; double* ut;
+  double* lin;     // B x N x LIN_STRIDE
+  double* proj;    // B x N x PROJ_STRIDE
+  double* rk;      // B x N x RK_STRIDE
+  double* dxt; double* dut; double* perf; int32_t* flags;
+  const double* x0;
+};
+
+__global__ void __launch_bounds__(64) lin_kernel(SqpArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp_in_block = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+  LinHalf& sh = reinterpret_cast<LinHalf*>(smem_raw)[warp_in_block * 2 + half];
+  const int N = a.N, NP = (N + 1) >> 1;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+  if (w >= (long long)a.B * NP) return;
+  const int inst = (int)(w / NP), pr = (int)(w - (long long)inst * NP);
+  const int k = 2 * pr + half;
+  const bool act = k < N;
+  const int kk = act ? k : N - 1;
+  const double* xk = (kk == 0) ? a.x0 + (size_t)inst * NX : a.xt + ((size_t)inst * (N + 1) + kk) * NX;   // node 0 is pinned to the measured state
+  const double* uk = a.ut + ((size_t)inst * N + kk) * NU;
+  for (int i = hl; i < NX; i += 16) { sh.x[i] = xk[i]; sh.u[i] = uk[i]; }
+  __syncwarp();
+  double* rec = a.lin + ((size_t)inst * N + kk) * LIN_STRIDE;
+  lin_half(sh, sh.x, hl, act, rec + LIN_F1, rec + LIN_A1, rec + LIN_BF1, rec + LIN_BV1, true, rec);
+  for (int i = hl; i < NX; i += 16) sh.x2[i] = sh.x[i] + a.dt * sh.f[i];
+  __syncwarp();
+  lin_half(sh, sh.x2, hl, act, rec + LIN_F2, rec + LIN_A2, rec + LIN_BF2, rec + LIN_BV2, false, rec);
+}
+
+// ---------------------------------------------------------------- K1
+struct LqShared {
+  double Ad[TS];                 // discrete A, then At
+  double Q[TS];                  // Q, then Qt
+  double A1c[9 * NX], A2c[9 * NX];
+  double BdF[9 * 12], Bdv[9 * NJ];     // rows 3..11 of Bd
+  double Bf1[36], Bf2[36], Bv1[60], Bv2[60];
+  double dpq[12 * NDIR], dvx[12 * NX], dvv[12 * NJ];
+  double Cv[12 * NX], Dv[12 * NJ], ev[12];
+  double G[NJ * 36];             // 10 x (10 + 22 + 1) normal equations (ld 36)
+  double Pxv[NJ * NX], Nv[NJ * 8], pev[NJ];
+  double Rvv[NJ * NJ], Pv[NJ * NX], RFF[12 * 12];
+  double T1[NJ * NX];            // PRPx_v
+  double Bt[NX * NTMAX];
+  double gx[8 * NX], gv[8 * NJ], gh[8];
+  double x[NX], u[NU], xn[NX], xref[NX], swing[24], f1[NX], f2[NX], b[NX], q[NX], r[NU], bt[NX], qt[NX], rRpe[NJ], rt[NTMAX];
+  double epos[12], evel[12];
+  int rowc[12], rowa[12], rowt[12], piv[NJ], freev[NJ], stidx[12];
+};
+
+__global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LqShared& sh = *reinterpret_cast<LqShared*>(smem_raw);
+  const int lane = threadIdx.x;
+  const int N = a.N;
+  const long long w = blockIdx.x;
+  const int inst = (int)(w / N), k = (int)(w - (long long)inst * N);
+  const double dt = a.dt;
+  const Model& md = c_model;
+  const double* rec = a.lin + ((size_t)inst * N + k) * LIN_STRIDE;
+  double* out = a.proj + ((size_t)inst * N + k) * PJ_STRIDE;
+  const double* xk = (k == 0) ? a.x0 + (size_t)inst * NX : a.xt + ((size_t)inst * (N + 1) + k) * NX;
+  // ---- load
+  if (lane < NX) {
+    sh.x[lane] = xk[lane]; sh.u[lane] = a.ut[((size_t)inst * N + k) * NU + lane]; sh.xn[lane] = a.xt[((size_t)inst * (N + 1) + k + 1) * NX + lane];
+    sh.xref[lane] = a.x_ref[((size_t)inst * (N + 1) + k) * NX + lane]; sh.f1[lane] = rec[LIN_F1 + lane]; sh.f2[lane] = rec[LIN_F2 + lane];
+  }
+  if (lane < 24) sh.swing[lane] = a.swing[((size_t)inst * (N + 1) + k) * 24 + lane];
+  if (lane < 12) { sh.epos[lane] = rec[LIN_EPOS + lane]; sh.evel[lane] = rec[LIN_EVEL + lane]; }
+  for (int i = lane; i < 9 * NX; i += 32) { sh.A1c[i] = rec[LIN_A1 + i]; sh.A2c[i] = rec[LIN_A2 + i]; }
+  for (int i = lane; i < 36; i += 32) { sh.Bf1[i] = rec[LIN_BF1 + i]; sh.Bf2[i] = rec[LIN_BF2 + i]; }
+  for (int i = lane; i < 60; i += 32) { sh.Bv1[i] = rec[LIN_BV1 + i]; sh.Bv2[i] = rec[LIN_BV2 + i]; }
+  for (int i = lane; i < 12 * NDIR; i += 32) sh.dpq[i] = rec[LIN_DPQ + i];
+  for (int i = lane; i < 12 * NX; i += 32) sh.dvx[i] = rec[LIN_DVX + i];
+  for (int i = lane; i < 12 * NJ; i += 32) sh.dvv[i] = rec[LIN_DVV + i];
+  const int mode = a.mode[(size_t)inst * (N + 1) + k];
+  bool fl[4]; int ns = 0;
+  for (int c = 0; c < 4; ++c) { fl[c] = contact_flag(mode, c); ns += fl[c]; }
+  __syncwarp();
+  // ---- RK2 sensitivities (S2) on the non-trivial rows 3..11
+  // Ad = I + dt/2 (A1 + A2 + dt A2 A1);  (A2 A1)[i][j] = sum_{k=3..11} A2c[i][k] A1c[k-3][j]
+  if (lane < NX) {
+    const int j = lane;
+    double c1[9];
+#pragma unroll
+    for (int kk = 0; kk < 9; ++kk) c1[kk] = sh.A1c[kk * NX + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 9; ++kk) s = fma(sh.A2c[i * NX + 3 + kk], c1[kk], s);
+      sh.Ad[(3 + i) * NX + j] = 0.5 * dt * (c1[i] + sh.A2c[i * NX + j] + dt * s);
+    }
+    for (int i = 0; i < 3; ++i) sh.Ad[i * NX + j] = 0.0;
+    for (int i = 12; i < NX; ++i) sh.Ad[i * NX + j] = 0.0;
+  }
+  __syncwarp();
+  if (lane < NX) sh.Ad[lane * NX + lane] += 1.0;
+  // Bd force columns (rows 3..11): B1 rows 3..5 = Bf1; A2 B1 = A2c[:, 3:6] Bf1.  vj columns: B1 rows 6..11 = Bv1, rows 12..21 = I;
+  // A2 B1 = A2c[:, 6:12] Bv1 + A2c[:, 12:22]
+  if (lane < 12) {
+    const int j = lane;
+    const double b0 = sh.Bf1[j], b1 = sh.Bf1[12 + j], b2 = sh.Bf1[24 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      // B1 force column j = [e_a / m ; Bf1[:, j] ; 0]: (A2 B1)[i][j] = A2c[i][a] / m + A2c[i][3:6] Bf1[:, j]
+      const double s = sh.A2c[i * NX + 3] * b0 + sh.A2c[i * NX + 4] * b1 + sh.A2c[i * NX + 5] * b2 + sh.A2c[i * NX + (j % 3)] / md.total_mass;
+      const double base = (i < 3) ? (sh.Bf1[i * 12 + j] + sh.Bf2[i * 12 + j]) : 0.0;
+      sh.BdF[i * 12 + j] = 0.5 * dt * (base + dt * s);
+    }
+  } else if (lane >= 16 && lane < 16 + NJ) {
+    const int j = lane - 16;
+    double c1[6];
+#pragma unroll
+    for (int kk = 0; kk < 6; ++kk) c1[kk] = sh.Bv1[kk * NJ + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      double s = sh.A2c[i * NX + 12 + j];
+#pragma unroll
+      for (int kk = 0; kk < 6; ++kk) s = fma(sh.A2c[i * NX + 6 + kk], c1[kk], s);
+      const double base = (i >= 3) ? (sh.Bv1[(i - 3) * NJ + j] + sh.Bv2[(i - 3) * NJ + j]) : 0.0;
+      sh.Bdv[i * NJ + j] = 0.5 * dt * (base + dt * s);
+    }
+  }
+  double d2 = 0.0;
+  if (lane < NX) { const double bb = sh.x[lane] + 0.5 * dt * (sh.f1[lane] + sh.f2[lane]) - sh.xn[lane]; sh.b[lane] = bb; d2 = bb * bb; }
+  d2 = warp_sum(d2);
+  __syncwarp();
+  // ---- cost (M2, M6, M7, M8), scaled by dt at the end
+  const double fz = ns > 0 ? md.total_mass * HB_GRAVITY / ns : 0.0;
+  double cost = 0.0;
+  for (int idx = lane; idx < TS; idx += 32) sh.Q[idx] = 0.0;
+  for (int idx = lane; idx < NJ * NJ; idx += 32) { const int i = idx / NJ, j = idx - i * NJ; sh.Rvv[idx] = md.R[(12 + i) * NU + 12 + j]; }
+  for (int idx = lane; idx < 144; idx += 32) { const int i = idx / 12, j = idx - i * 12; sh.RFF[idx] = (i == j) ? md.R[i * NU + i] : 0.0; }
+  for (int idx = lane; idx < NJ * NX; idx += 32) sh.Pv[idx] = 0.0;
+  __syncwarp();
+  if (lane < NX) {
+    const double d = sh.x[lane] - sh.xref[lane];
+    sh.q[lane] = md.Q[lane] * d;
+    sh.Q[lane * NX + lane] = md.Q[lane];
+    cost += 0.5 * md.Q[lane] * d * d;
+    double s = 0.0;
+    if (lane < 12) { double dul = sh.u[lane]; if ((lane % 3) == 2 && fl[lane / 3]) dul -= fz; s = md.R[lane * NU + lane] * dul; cost += 0.5 * dul * s; }
+    else { for (int j = 12; j < NU; ++j) s += md.R[lane * NU + j] * sh.u[j]; cost += 0.5 * sh.u[lane] * s; }
+    sh.r[lane] = s;
+  }
+  __syncwarp();
+  double shiftsum = 0.0;
+  if (lane < 10) {
+    const Pen p = double_sided(sh.x[12 + lane], md.joint_lower[lane], md.joint_upper[lane], HB_LIMIT_POS_MU, HB_LIMIT_POS_DELTA);
+    cost += p.v; sh.q[12 + lane] += p.d1; sh.Q[(12 + lane) * NX + 12 + lane] += p.d2;
+  } else if (lane < 20) {
+    const int j = lane - 10;
+    const Pen p = double_sided(sh.u[12 + j], -md.joint_vel_limit[j], md.joint_vel_limit[j], HB_LIMIT_VEL_MU, HB_LIMIT_VEL_DELTA);
+    cost += p.v; sh.r[12 + j] += p.d1; sh.Rvv[j * NJ + j] += p.d2;
+  } else if (lane < 24) {
+    const int c = lane - 20;
+    const Pen p = double_sided(sh.u[3 * c + 2], 0.0, HB_LIMIT_FORCE_MAX, HB_LIMIT_FORCE_MU, HB_LIMIT_FORCE_DELTA);
+    cost += p.v; sh.r[3 * c + 2] += p.d1; sh.RFF[(3 * c + 2) * 12 + 3 * c + 2] += p.d2;
+  }
+  __syncwarp();
+  if (lane >= 24 && lane < 28) {
+    const int c = lane - 24;
+    if (fl[c]) {
+      const double Fx = sh.u[3 * c], Fy = sh.u[3 * c + 1], Fz = sh.u[3 * c + 2];
+      const double t2 = Fx * Fx + Fy * Fy + HB_FRICTION_REGULARIZATION, tn = sqrt(t2), t32 = tn * t2;
+      const double h = HB_FRICTION_MU * Fz - tn;
+      const Pen p = relaxed_barrier(h, HB_FRICTION_BARRIER_MU, HB_FRICTION_BARRIER_DELTA);
+      cost += p.v;
+      const double gr[3] = {-Fx / tn, -Fy / tn, HB_FRICTION_MU};
+      const double Hh[9] = {-(Fy * Fy + HB_FRICTION_REGULARIZATION) / t32, Fx * Fy / t32, 0.0, Fx * Fy / t32,
+                            -(Fx * Fx + HB_FRICTION_REGULARIZATION) / t32, 0.0, 0.0, 0.0, 0.0};
+      for (int i = 0; i < 3; ++i) {
+        sh.r[3 * c + i] += p.d1 * gr[i];
+        for (int j = 0; j < 3; ++j) sh.RFF[(3 * c + i) * 12 + 3 * c + j] += p.d2 * gr[i] * gr[j] + p.d1 * Hh[3 * i + j];
+      }
+      shiftsum = -p.d1 * HB_FRICTION_HESSIAN_SHIFT;
+    }
+  }
+  shiftsum = warp_sum(shiftsum);
+  __syncwarp();
+  if (lane < NX) sh.Q[lane * NX + lane] += shiftsum;
+  if (lane < 12) sh.RFF[lane * 12 + lane] += shiftsum;
+  else if (lane >= 16 && lane < 16 + NJ) sh.Rvv[(lane - 16) * NJ + lane - 16] += shiftsum;
+  __syncwarp();
+  // xy swing soft constraint: gradients gx (22) / gv (10, vj columns only)
+  int npair = 0;
+  for (int c = 0; c < 4; ++c) {
+    if (fl[c]) continue;
+    for (int ax = 0; ax < 2; ++ax) {
+      const int row = 3 * c + ax;
+      if (lane < NX) {
+        double px = 0.0;
+        if (lane >= 6 && lane < 9) px = (lane - 6 == ax) ? 1.0 : 0.0;
+        else if (lane >= 9) px = sh.dpq[row * NDIR + lane - 9];
+        sh.gx[npair * NX + lane] = sh.dvx[row * NX + lane] + HB_XY_POSITION_GAIN * px;
+        if (lane < NJ) sh.gv[npair * NJ + lane] = sh.dvv[row * NJ + lane];
+      }
+      if (lane == 0) sh.gh[npair] = sh.evel[row] - sh.swing[6 * c + 3 + ax] + HB_XY_POSITION_GAIN * (sh.epos[row] - sh.swing[6 * c + ax]);
+      ++npair;
+    }
+  }
+  __syncwarp();
+  for (int p = 0; p < npair; ++p) {
+    const double w = HB_SOFT_SWING_WEIGHT, h = sh.gh[p];
+    const double* gx = sh.gx + p * NX; const double* gv = sh.gv + p * NJ;
+    if (lane == 0) cost += 0.5 * w * h * h;
+    if (lane < NX) {
+      const double gxj = gx[lane];
+      sh.q[lane] += w * h * gxj;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) sh.Q[i * NX + lane] += w * gx[i] * gxj;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) sh.Pv[i * NX + lane] += w * gv[i] * gxj;
+      if (lane < NJ) {
+        sh.r[12 + lane] += w * h * gv[lane];
+#pragma unroll
+        for (int i = 0; i < NJ; ++i) sh.Rvv[i * NJ + lane] += w * gv[i] * gv[lane];
+      }
+    }
+    __syncwarp();
+  }
+  cost = warp_sum(cost);
+  // ---- contact-velocity equality rows (M4, M5); swing forces handled separately (M3)
+  int mr = 0;
+  for (int c = 0; c < 4; ++c) {
+    if (fl[c]) { for (int ax = 0; ax < 3; ++ax) { if (lane == 0) { sh.rowc[mr] = c; sh.rowa[mr] = ax; sh.rowt[mr] = 0; } ++mr; } }
+    else { if (lane == 0) { sh.rowc[mr] = c; sh.rowa[mr] = 2; sh.rowt[mr] = 2; } ++mr; }
+  }
+  __syncwarp();
+  double e2 = 0.0;
+  if (lane < NX) {
+    for (int rr = 0; rr < mr; ++rr) {
+      const int row = 3 * sh.rowc[rr] + sh.rowa[rr], t = sh.rowt[rr];
+      const double gain = (t == 0) ? ((sh.rowa[rr] == 2) ? HB_ZEROVEL_Z_GAIN : 0.0) : HB_POSITION_ERROR_GAIN;
+      double px = 0.0;
+      if (lane >= 6 && lane < 9) px = (lane - 6 == sh.rowa[rr]) ? 1.0 : 0.0;
+      else if (lane >= 9) px = sh.dpq[row * NDIR + lane - 9];
+      sh.Cv[rr * NX + lane] = sh.dvx[row * NX + lane] + gain * px;
+      if (lane < NJ) sh.Dv[rr * NJ + lane] = sh.dvv[row * NJ + lane];
+    }
+  }
+  if (lane < mr) {
+    const int c = sh.rowc[lane], ax = sh.rowa[lane], row = 3 * c + ax;
+    double evv;
+    if (sh.rowt[lane] == 0) evv = sh.evel[row] + (ax == 2 ? HB_ZEROVEL_Z_GAIN * sh.epos[row] + HB_ZEROVEL_Z_OFFSET : 0.0);
+    else evv = sh.evel[row] - sh.swing[6 * c + 5] + HB_POSITION_ERROR_GAIN * (sh.epos[row] - sh.swing[6 * c + 2]);
+    sh.ev[lane] = evv;
+    e2 = evv * evv;
+  }
+  if (lane >= 16 && lane < 28) { const int j = lane - 16; if (!fl[j / 3]) e2 += sh.u[j] * sh.u[j]; }
+  e2 = warp_sum(e2);
+  __syncwarp();
+  // ---- least-squares projection on vj: G = Dv'Dv, rhs = -Dv'[Cv | ev]  (10 x 33, ld 36)
+  constexpr int GW = NJ + NX + 1, GL = 36;
+  for (int j = lane; j < GW; j += 32) {
+    for (int i = 0; i < NJ; ++i) {
+      double s = 0.0;
+      if (j < NJ) { for (int r = 0; r < mr; ++r) s += sh.Dv[r * NJ + i] * sh.Dv[r * NJ + j]; }
+      else if (j < NJ + NX) { for (int r = 0; r < mr; ++r) s -= sh.Dv[r * NJ + i] * sh.Cv[r * NX + j - NJ]; }
+      else { for (int r = 0; r < mr; ++r) s -= sh.Dv[r * NJ + i] * sh.ev[r]; }
+      sh.G[i * GL + j] = s;
+    }
+  }
+  if (lane < NJ) sh.piv[lane] = 0;
+  __syncwarp();
+  double dmax = lane < NJ ? sh.G[lane * GL + lane] : 0.0;
+  if (ns < 4) dmax = fmax(dmax, 1.0);     // the swing-force selector rows of D have unit diagonal in D'D
+  dmax = warp_max(dmax);
+  const double tol = 1e-9 * fmax(dmax, 1e-300);
+  for (int step = 0; step < NJ; ++step) {
+    double dv = (lane < NJ && !sh.piv[lane]) ? sh.G[lane * GL + lane] : -1.0;
+    int pi = lane;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(HB_FULL_MASK, dv, o);
+      const int oi = __shfl_xor_sync(HB_FULL_MASK, pi, o);
+      if (ov > dv || (ov == dv && oi < pi)) { dv = ov; pi = oi; }
+    }
+    if (!(dv > tol)) break;
+    const int p = pi;
+    const double inv = 1.0 / dv;
+    __syncwarp();
+    for (int j = lane; j < GW; j += 32) sh.G[p * GL + j] *= inv;
+    if (lane == 0) sh.piv[p] = 1;
+    __syncwarp();
+    for (int j = lane; j < GW; j += 32) {
+      if (j == p) continue;
+      const double gp = sh.G[p * GL + j];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) if (i != p) sh.G[i * GL + j] -= sh.G[i * GL + p] * gp;
+    }
+    __syncwarp();
+    if (lane < NJ && lane != p) sh.G[lane * GL + p] = 0.0;
+    __syncwarp();
+  }
+  int nv = 0;
+  for (int i = 0; i < NJ; ++i) if (!sh.piv[i]) { if (lane == 0) sh.freev[nv] = i; ++nv; }
+  int nf = 0;
+  for (int j = 0; j < 12; ++j) if (fl[j / 3]) { if (lane == 0) sh.stidx[nf] = j; ++nf; }
+  bool overflow = false;
+  if (nv > NVMAX) { nv = NVMAX; overflow = true; }       // degenerate pose (velocity rows lost rank): flagged, instance reported as failed
+  if (nf + nv > NTMAX) { nv = NTMAX - nf; overflow = true; }
+  const int nt = nf + nv;
+  __syncwarp();
+  if (lane < NX) {
+    for (int i = 0; i < NJ; ++i) sh.Pxv[i * NX + lane] = sh.piv[i] ? sh.G[i * GL + NJ + lane] : 0.0;
+    if (lane < NJ) sh.pev[lane] = sh.piv[lane] ? sh.G[lane * GL + NJ + NX] : 0.0;
+    if (lane < nv) { const int fc = sh.freev[lane]; for (int i = 0; i < NJ; ++i) sh.Nv[i * 8 + lane] = sh.piv[i] ? -sh.G[i * GL + fc] : ((i == fc) ? 1.0 : 0.0); }
+  }
+  __syncwarp();
+  // ---- projected model (cost scaled by dt)
+  // At = Ad + Bd_v Pxv : rows 3..11 += Bdv Pxv ; rows 12..21 += dt Pxv
+  if (lane < NX) {
+    const int j = lane;
+    double pc[NJ];
+#pragma unroll
+    for (int kk = 0; kk < NJ; ++kk) pc[kk] = sh.Pxv[kk * NX + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Bdv[i * NJ + kk], pc[kk], s);
+      sh.Ad[(3 + i) * NX + j] += s;
+    }
+#pragma unroll
+    for (int kk = 0; kk < NJ; ++kk) sh.Ad[(12 + kk) * NX + j] += dt * pc[kk];
+    // PRPx_v = Pv + Rvv Pxv (10 x 22)
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      double s = sh.Pv[i * NX + j];
+#pragma unroll
+      for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Rvv[i * NJ + kk], pc[kk], s);
+      sh.T1[i * NX + j] = s;
+    }
+  }
+  if (lane < NJ) {
+    double s = sh.r[12 + lane];
+    for (int kk = 0; kk < NJ; ++kk) s += sh.Rvv[lane * NJ + kk] * sh.pev[kk];
+    sh.rRpe[lane] = s;
+  }
+  __syncwarp();
+  // Qt = Q + Pxv' PRPx_v + Pv' Pxv ; qt = q + Pxv' rRpe + Pv' pev
+  if (lane < NX) {
+    const int j = lane;
+    double tc[NJ], pc[NJ];
+#pragma unroll
+    for (int kk = 0; kk < NJ; ++kk) { tc[kk] = sh.T1[kk * NX + j]; pc[kk] = sh.Pxv[kk * NX + j]; }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double s = sh.Q[i * NX + j];
+#pragma unroll
+      for (int kk = 0; kk < NJ; ++kk) { s = fma(sh.Pxv[kk * NX + i], tc[kk], s); s = fma(sh.Pv[kk * NX + i], pc[kk], s); }
+      out[PJ_QT + i * NX + j] = dt * s;
+    }
+    double s = sh.q[j];
+#pragma unroll
+    for (int kk = 0; kk < NJ; ++kk) s += pc[kk] * sh.rRpe[kk] + sh.Pv[kk * NX + j] * sh.pev[kk];
+    out[PJ_QV + j] = dt * s;
+  }
+  // Bt (22 x nt, ld NTMAX): stance-force columns then null-space columns
+  if (lane < nt) {
+    const int c = lane;
+    if (c < nf) {
+      const int j = sh.stidx[c];
+      for (int i = 0; i < NX; ++i) {
+        double v = 0.0;
+        if (i < 3) v = (i == (j % 3)) ? dt / md.total_mass : 0.0;
+        else if (i < 12) v = sh.BdF[(i - 3) * 12 + j];
+        sh.Bt[i * NTMAX + c] = v;
+      }
+    } else {
+      const int cc = c - nf;
+      for (int i = 0; i < 3; ++i) sh.Bt[i * NTMAX + c] = 0.0;
+      for (int i = 0; i < 9; ++i) { double s = 0.0; for (int kk = 0; kk < NJ; ++kk) s += sh.Bdv[i * NJ + kk] * sh.Nv[kk * 8 + cc]; sh.Bt[(3 + i) * NTMAX + c] = s; }
+      for (int kk = 0; kk < NJ; ++kk) sh.Bt[(12 + kk) * NTMAX + c] = dt * sh.Nv[kk * 8 + cc];
+    }
+  }
+  // bt = b + Bd_v pev - Bd_F[:, swing] F_swing
+  if (lane < NX) {
+    const int i = lane;
+    double s = sh.b[i];
+    if (i >= 3 && i < 12) {
+      for (int kk = 0; kk < NJ; ++kk) s += sh.Bdv[(i - 3) * NJ + kk] * sh.pev[kk];
+      for (int j = 0; j < 12; ++j) if (!fl[j / 3]) s -= sh.BdF[(i - 3) * 12 + j] * sh.u[j];
+    } else if (i >= 12) s += dt * sh.pev[i - 12];
+    else { for (int c = 0; c < 4; ++c) if (!fl[c]) s -= dt / md.total_mass * sh.u[3 * c + i]; }
+    sh.bt[i] = s;
+  }
+  __syncwarp();
+  // Rt (nt x nt), Pt (nt x 22), rt (nt)
+  for (int idx = lane; idx < nt * nt; idx += 32) {
+    const int i = idx / nt, j = idx - i * nt;
+    double s = 0.0;
+    if (i < nf && j < nf) s = sh.RFF[sh.stidx[i] * 12 + sh.stidx[j]];
+    else if (i >= nf && j >= nf) {
+      const int ci = i - nf, cj = j - nf;
+      for (int p = 0; p < NJ; ++p) { double t = 0.0; for (int qq = 0; qq < NJ; ++qq) t += sh.Rvv[p * NJ + qq] * sh.Nv[qq * 8 + cj]; s += sh.Nv[p * 8 + ci] * t; }
+    }
+    out[PJ_RT + i * NTMAX + j] = dt * s;
+  }
+  if (lane < NX) {
+    for (int c = 0; c < nt; ++c) {
+      double s = 0.0;
+      if (c >= nf) { const int cc = c - nf; for (int kk = 0; kk < NJ; ++kk) s += sh.Nv[kk * 8 + cc] * sh.T1[kk * NX + lane]; }
+      out[PJ_PT + c * NX + lane] = dt * s;
+    }
+  }
+  if (lane < nt) {
+    double s;
+    if (lane < nf) s = sh.r[sh.stidx[lane]];
+    else { s = 0.0; const int cc = lane - nf; for (int kk = 0; kk < NJ; ++kk) s += sh.Nv[kk * 8 + cc] * sh.rRpe[kk]; }
+    out[PJ_RV + lane] = dt * s;
+  }
+  // ---- write the rest of the record
+  for (int idx = lane; idx < TS; idx += 32) out[PJ_AT + idx] = sh.Ad[idx];
+  for (int idx = lane; idx < NX * NTMAX; idx += 32) out[PJ_BT + idx] = sh.Bt[idx];
+  if (lane < NX) out[PJ_BTV + lane] = sh.bt[lane];
+  for (int idx = lane; idx < NJ * NX; idx += 32) out[PJ_PXV + idx] = sh.Pxv[idx];
+  for (int idx = lane; idx < NJ * NVMAX; idx += 32) { const int c = idx % NVMAX; out[PJ_NV + idx] = (c < nv) ? sh.Nv[idx] : 0.0; }
+  if (lane < NJ) out[PJ_PEV + lane] = sh.pev[lane];
+  if (lane == 0) { out[PJ_META] = nt; out[PJ_META + 1] = nf; out[PJ_META + 2] = nv; out[PJ_META + 3] = cost; out[PJ_META + 4] = d2; out[PJ_META + 5] = e2; out[PJ_META + 6] = overflow ? 1.0 : 0.0; }
+}
+
+// ---------------------------------------------------------------- K2: value-function recursion
+struct RicShared {
+  double S[TS], At[TS], SA[TS];
+  double Bt[NX * NTMAX], SB[NX * NTMAX], Hux[NTMAX * NX], K[NTMAX * NX], Huu[NTMAX * 17];
+  double sv[NX], bt[NX], sb[NX], qt[NX], rt[NTMAX], hu[NTMAX], kff[NTMAX], idg[NTMAX];
+};
+
+__global__ void __launch_bounds__(32) riccati_kernel(SqpArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RicShared& sh = *reinterpret_cast<RicShared*>(smem_raw);
+  const int inst = blockIdx.x, lane = threadIdx.x, N = a.N;
+  for (int idx = lane; idx < TS; idx += 32) sh.S[idx] = 0.0;   // no terminal cost
+  if (lane < NX) sh.sv[lane] = 0.0;
+  __syncwarp();
+  bool fail = false;
+  double merit = 0.0, dyn = 0.0, eqs = 0.0;
+  for (int k = N - 1; k >= 0; --k) {
+    const double* rec = a.proj + ((size_t)inst * N + k) * PJ_STRIDE;
+    const int nt = (int)rec[PJ_META];
+    merit += a.dt * rec[PJ_META + 3]; dyn += a.dt * rec[PJ_META + 4]; eqs += a.dt * rec[PJ_META + 5];
+    if (rec[PJ_META + 6] != 0.0) fail = true;
+    for (int idx = lane; idx < TS; idx += 32) sh.At[idx] = rec[PJ_AT + idx];
+    for (int idx = lane; idx < NX * NTMAX; idx += 32) sh.Bt[idx] = rec[PJ_BT + idx];
+    if (lane < NX) { sh.bt[lane] = rec[PJ_BTV + lane]; sh.qt[lane] = rec[PJ_QV + lane]; }
+    if (lane < NTMAX) sh.rt[lane] = rec[PJ_RV + lane];
+    __syncwarp();
+    // SA = S At ; SB = S Bt ; sb = s + S bt
+    wmm<false, 0>(sh.SA, NX, sh.S, NX, sh.At, NX, NX, NX, NX);
+    wmm<false, 0>(sh.SB, NTMAX, sh.S, NX, sh.Bt, NTMAX, NX, NX, nt);
+    wmv<false, 0>(sh.sb, sh.S, NX, sh.bt, NX, NX);
+    if (lane < NX) sh.sb[lane] += sh.sv[lane];
+    __syncwarp();
+    // Hux = Pt + Bt' SA ; Huu = Rt + Bt' SB ; hu = rt + Bt' sb
+    for (int idx = lane; idx < nt * NX; idx += 32) sh.Hux[idx] = rec[PJ_PT + idx];
+    for (int idx = lane; idx < nt * nt; idx += 32) { const int i = idx / nt, j = idx - i * nt; sh.Huu[i * 17 + j] = rec[PJ_RT + i * NTMAX + j]; }
+    __syncwarp();
+    wmm<true, 1>(sh.Hux, NX, sh.Bt, NTMAX, sh.SA, NX, nt, NX, NX);
+    wmm<true, 1>(sh.Huu, 17, sh.Bt, NTMAX, sh.SB, NTMAX, nt, NX, nt);
+    wmv<true, 0>(sh.hu, sh.Bt, NTMAX, sh.sb, nt, NX);
+    if (lane < nt) sh.hu[lane] += sh.rt[lane];
+    __syncwarp();
+    for (int idx = lane; idx < nt * nt; idx += 32) { const int i = idx / nt, j = idx - i * nt; if (j < i) sh.Huu[i * 17 + j] = 0.5 * (sh.Huu[i * 17 + j] + sh.Huu[j * 17 + i]); }
+    __syncwarp();
+    if (nt > 0) {
+      if (!warp_chol_inv(sh.Huu, nt, 17, sh.idg, lane)) fail = true;
+      if (lane <= NX) {
+        double col[NTMAX], y[NTMAX];
+#pragma unroll
+        for (int i = 0; i < NTMAX; ++i) col[i] = (i < nt) ? ((lane < NX) ? sh.Hux[i * NX + lane] : sh.hu[i]) : 0.0;
+#pragma unroll
+        for (int i = 0; i < NTMAX; ++i) {
+          double s = 0.0;
+          if (i < nt) { s = sh.idg[i] * col[i];
+#pragma unroll
+            for (int kk = 0; kk < NTMAX; ++kk) if (kk < i) s += sh.Huu[kk * 17 + i] * col[kk]; }
+          y[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < NTMAX; ++i) {
+          double s = 0.0;
+          if (i < nt) { s = sh.idg[i] * y[i];
+#pragma unroll
+            for (int kk = 0; kk < NTMAX; ++kk) if (kk > i && kk < nt) s += sh.Huu[i * 17 + kk] * y[kk]; }
+          col[i] = -s;
+        }
+        if (lane < NX) {
+#pragma unroll
+          for (int i = 0; i < NTMAX; ++i) if (i < nt) sh.K[i * NX + lane] = col[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < NTMAX; ++i) if (i < nt) sh.kff[i] = col[i];
+        }
+      }
+    }
+    __syncwarp();
+    // store K, kff
+    double* rk = a.rk + ((size_t)inst * N + k) * RK_STRIDE;
+    for (int idx = lane; idx < nt * NX; idx += 32) rk[idx] = sh.K[idx];
+    if (lane < nt) rk[NTMAX * NX + lane] = sh.kff[lane];
+    // S <- Qt + At' SA + Hux' K ; s <- qt + At' sb + Hux' kff   (S assembled in At's slot? no: use SB region is too small -> reuse SA after products)
+    // first s (needs At, Hux), then S into a temporary (Bt/SB are dead now -> use At after the product is done via SA)
+    wmv<true, 0>(sh.sv, sh.At, NX, sh.sb, NX, NX);
+    wmv<true, 1>(sh.sv, sh.Hux, NX, sh.kff, NX, nt);
+    if (lane < NX) sh.sv[lane] += sh.qt[lane];
+    // T = At' SA -> written over S is unsafe (S not needed any more: SA, SB, sb already formed) -> write into S directly
+    wmm<true, 0>(sh.S, NX, sh.At, NX, sh.SA, NX, NX, NX, NX);
+    wmm<true, 1>(sh.S, NX, sh.Hux, NX, sh.K, NX, NX, nt, NX);
+    for (int idx = lane; idx < TS; idx += 32) sh.S[idx] += rec[PJ_QT + idx];
+    __syncwarp();
+    // symmetrise in place (pairs handled by the lane owning the lower index)
+    for (int idx = lane; idx < TS; idx += 32) { const int i = idx / NX, j = idx - i * NX; if (j > i) { const double v = 0.5 * (sh.S[idx] + sh.S[j * NX + i]); sh.S[idx] = v; sh.S[j * NX + i] = v; } }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    double* pf = a.perf + (size_t)inst * 4;
+    pf[0] = merit; pf[1] = dyn; pf[2] = eqs; pf[3] = 0.0;
+    a.flags[inst] = fail ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------- K3: forward pass + filter line search
+struct Fw2Shared {
+  double At[TS], Bt[NX * NTMAX], K[NTMAX * NX], Pxv[NJ * NX], Nv[NJ * NVMAX];
+  double bt[NX], kff[NTMAX], pev[NJ], qt[NX], rt[NTMAX], dx[NX], dxn[NX], w[NTMAX], u[NU];
+};
+
+__global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int max_trials, void* info_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Fw2Shared& sh = *reinterpret_cast<Fw2Shared*>(smem_raw);
+  const int inst = blockIdx.x, lane = threadIdx.x, N = a.N;
+  const double dt = a.dt;
+  double* xt = a.xt + (size_t)inst * (N + 1) * NX;
+  double* ut = a.ut + (size_t)inst * N * NU;
+  double* dxt = a.dxt + (size_t)inst * (N + 1) * NX;
+  double* dut = a.dut + (size_t)inst * N * NU;
+  const double* xref = a.x_ref + (size_t)inst * (N + 1) * NX;
+  const double* swing = a.swing + (size_t)inst * (N + 1) * 24;
+  const int32_t* mode = a.mode + (size_t)inst * (N + 1);
+  if (lane < NX) { xt[lane] = a.x0[(size_t)inst * NX + lane]; sh.dx[lane] = 0.0; dxt[lane] = 0.0; }
+  __syncwarp();
+  double armijo = 0.0;
+  bool finite = (a.flags[inst] == 0);
+  for (int k = 0; k < N; ++k) {
+    const double* rec = a.proj + ((size_t)inst * N + k) * PJ_STRIDE;
+    const double* rk = a.rk + ((size_t)inst * N + k) * RK_STRIDE;
+    const int nt = (int)rec[PJ_META], nf = (int)rec[PJ_META + 1], nv = (int)rec[PJ_META + 2];
+    const int md_k = mode[k];
+    for (int idx = lane; idx < TS; idx += 32) sh.At[idx] = rec[PJ_AT + idx];
+    for (int idx = lane; idx < NX * NTMAX; idx += 32) sh.Bt[idx] = rec[PJ_BT + idx];
+    for (int idx = lane; idx < nt * NX; idx += 32) sh.K[idx] = rk[idx];
+    for (int idx = lane; idx < NJ * NX; idx += 32) sh.Pxv[idx] = rec[PJ_PXV + idx];
+    for (int idx = lane; idx < NJ * NVMAX; idx += 32) sh.Nv[idx] = rec[PJ_NV + idx];
+    if (lane < NX) { sh.bt[lane] = rec[PJ_BTV + lane]; sh.qt[lane] = rec[PJ_QV + lane]; sh.u[lane] = ut[k * NU + lane]; }
+    if (lane < NTMAX) { sh.kff[lane] = rk[NTMAX * NX + lane]; sh.rt[lane] = rec[PJ_RV + lane]; }
+    if (lane < NJ) sh.pev[lane] = rec[PJ_PEV + lane];
+    __syncwarp();
+    double arm = 0.0;
+    if (lane < nt) {
+      double s = sh.kff[lane];
+      for (int j = 0; j < NX; ++j) s = fma(sh.K[lane * NX + j], sh.dx[j], s);
+      sh.w[lane] = s;
+      arm = sh.rt[lane] * s;
+    }
+    __syncwarp();
+    if (lane < NX) {
+      double s = sh.bt[lane];
+      for (int j = 0; j < NX; ++j) s = fma(sh.At[lane * NX + j], sh.dx[j], s);
+      for (int c = 0; c < nt; ++c) s = fma(sh.Bt[lane * NTMAX + c], sh.w[c], s);
+      sh.dxn[lane] = s;
+      dxt[(k + 1) * NX + lane] = s;
+      arm += sh.qt[lane] * sh.dx[lane];
+      // du: stance forces are free variables, swing forces go to zero, vj from the projection
+      double du;
+      if (lane < 12) {
+        if (contact_flag(md_k, lane / 3)) { int c = 0; for (int j = 0; j < lane; ++j) c += contact_flag(md_k, j / 3); du = sh.w[c]; }
+        else du = -sh.u[lane];
+      } else {
+        const int i = lane - 12;
+        du = sh.pev[i];
+        for (int j = 0; j < NX; ++j) du = fma(sh.Pxv[i * NX + j], sh.dx[j], du);
+        for (int c = 0; c < nv; ++c) du = fma(sh.Nv[i * NVMAX + c], sh.w[nf + c], du);
+      }
+      dut[k * NU + lane] = du;
+      if (!isfinite(s) || !isfinite(du)) finite = false;
+    }
+    armijo += warp_sum(arm);
+    __syncwarp();
+    if (lane < NX) sh.dx[lane] = sh.dxn[lane];
+    __syncwarp();
+  }
+  finite = __all_sync(HB_FULL_MASK, finite);
+  const double* pf = a.perf + (size_t)inst * 4;
+  const double merit0 = pf[0], v0 = sqrt(pf[1] + pf[2]);
+  const double gamma_c = 1e-6, armijoFactor = 1e-4, alpha_decay = 0.5, alpha_min = 1e-4;
+  double alpha = 1.0, merit1 = merit0, v1 = v0;
+  bool accepted = false;
+  int trials = 0;
+  if (finite) {
+    while (alpha >= alpha_min && trials < max_trials) {
+      double ms = 0.0, ds = 0.0, es = 0.0;
+      for (int k = lane; k < N; k += 32) {
+        double x[NX], u[NU], xn[NX], f1[NX], f2[NX], x2[NX], ep[12], ev[12], xr[NX], sw[24];
+        for (int i = 0; i < NX; ++i) { x[i] = xt[k * NX + i] + alpha * dxt[k * NX + i]; xn[i] = xt[(k + 1) * NX + i] + alpha * dxt[(k + 1) * NX + i]; xr[i] = xref[k * NX + i]; }
+        for (int i = 0; i < NU; ++i) u[i] = ut[k * NU + i] + alpha * dut[k * NU + i];
+        for (int i = 0; i < 24; ++i) sw[i] = swing[k * 24 + i];
+        flow_map_lane(x, u, f1, ep, ev);
+        for (int i = 0; i < NX; ++i) x2[i] = x[i] + dt * f1[i];
+        flow_map_lane(x2, u, f2, nullptr, nullptr);
+        double d2 = 0.0;
+        for (int i = 0; i < NX; ++i) { const double d = x[i] + 0.5 * dt * (f1[i] + f2[i]) - xn[i]; d2 += d * d; }
+        double cost, e2;
+        node_values_lane(x, u, xr, sw, mode[k], ep, ev, cost, e2);
+        ms += dt * cost; ds += dt * d2; es += dt * e2;
+      }
+      ms = warp_sum(ms); ds = warp_sum(ds); es = warp_sum(es);
+      ++trials;
+      const double vn = sqrt(ds + es);
+      const double am = alpha * armijo;
+      bool acc;
+      if (vn > HB_SQP_G_MAX) acc = vn < (1.0 - gamma_c) * v0;
+      else if (vn < HB_SQP_G_MIN && v0 < HB_SQP_G_MIN && am < 0.0) acc = ms < merit0 + armijoFactor * am;
+      else acc = ms < (merit0 - gamma_c * v0) || vn < (1.0 - gamma_c) * v0;
+      if (isfinite(ms) && isfinite(vn) && acc) { accepted = true; merit1 = ms; v1 = vn; break; }
+      alpha *= alpha_decay;
+    }
+  }
+  if (accepted) {
+    for (int idx = lane; idx < (N + 1) * NX; idx += 32) xt[idx] += alpha * dxt[idx];
+    for (int idx = lane; idx < N * NU; idx += 32) ut[idx] += alpha * dut[idx];
+  }
+  if (lane == 0 && info_out) {
+    struct Info { double alpha, merit0, merit1, viol0, viol1, armijo; int32_t status, n_trials; };
+    Info* io = reinterpret_cast<Info*>(info_out) + inst;
+    io->alpha = accepted ? alpha : 0.0; io->merit0 = merit0; io->merit1 = merit1; io->viol0 = v0; io->viol1 = v1;
+    io->armijo = armijo; io->status = finite ? 0 : 3; io->n_trials = trials;
+  }
+}
+
+}  // namespace hb

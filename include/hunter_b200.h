@@ -77,9 +77,10 @@ const char* hb_last_cuda_error(const hb_ctx* ctx);
 /* number of kernel launches issued through this context since creation (bench.py reports it as gpu_launches) */
 int64_t hb_launch_count(const hb_ctx* ctx);
 /* per-kernel device timing with CUDA events on the context's stream (used by bench.py for the roofline line):
- * kinds 0 = SQP backward sweep, 1 = forward pass + line search, 2 = WBC assembly, 3 = interior-point QP, 4 = other */
+ * kinds 0 = Riccati sweep, 1 = forward pass + line search, 2 = WBC assembly, 3 = interior-point QP, 4 = other,
+ *       5 = node linearisation (kinematics), 6 = node LQ model + projection */
 int hb_profile_enable(hb_ctx* ctx, int on);
-int hb_profile_read(hb_ctx* ctx, double* ms_per_kind /*5*/, int64_t* count_per_kind /*5*/);
+int hb_profile_read(hb_ctx* ctx, double* ms_per_kind /*7*/, int64_t* count_per_kind /*7*/);
 /* the context's CUDA stream as a cudaStream_t cast to void* (for event timing on the launching stream) */
 void* hb_stream(hb_ctx* ctx);
 
