@@ -79,6 +79,57 @@ __global__ void wbc_assemble_kernel(int B, const double* x_des, const double* u_
   if (lane_id() == 0) m_out[inst] = m;
 }
 
+// Fused WeightedWbc step (K5+K6): assembly terms, reduced QP (tau and swing forces eliminated), interior point, expansion to
+// the reference's 38-vector [qdd, F, tau]. Shared memory per warp: QP workspace for n<=28 (the assembly scratch aliases the
+// factorisation area, which is dead until the first Newton step) + the reduced constraint matrix.
+constexpr int WZ_N = 28, WZ_ME = 6, WZ_MI = 40, WZ_ROWS = 36;
+__host__ __device__ inline size_t wbc_fused_doubles() { return qp_workspace_doubles(WZ_N, WZ_ME, WZ_MI) + WZ_ROWS * WZ_N + 2 * WZ_ROWS + 3 * WZ_N + 16 + 8; }
+
+__global__ void wbc_fused_kernel(int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const uint8_t* stance_mode,
+                                 double rho, int max_iter, double* sol, int32_t* status, int32_t* iters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const int inst = blockIdx.x * wpb + warp;
+  if (inst >= B) return;
+  double* base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * wbc_fused_doubles();
+  QpWorkspace w;
+  qp_carve(base, WZ_N, w, WZ_ME, WZ_MI);
+  double* p = base + qp_workspace_doubles(WZ_N, WZ_ME, WZ_MI);
+  double* Az = p; p += WZ_ROWS * WZ_N;
+  double* lbz = p; p += WZ_ROWS;
+  double* ubz = p; p += WZ_ROWS;
+  double* gz = p; p += WZ_N;
+  double* xz = p; p += WZ_N;
+  double* nlej = p; p += WZ_N;
+  int* stcol = reinterpret_cast<int*>(p);
+  static_assert(sizeof(WbcShared) <= sizeof(double) * (WZ_N * 29 + WZ_N * 7 + WZ_ME * 7 + WZ_N + WZ_ME + 6 * WZ_N + 5 * WZ_ME + 8 * WZ_MI), "assembly scratch must fit in the aliased area");
+  WbcShared& sh = *reinterpret_cast<WbcShared*>(w.K);   // K, V, S, vectors: dead until the QP starts
+  const int md = mode[inst];
+  int nw = 0;
+  wbc_assemble_warp(x_des + (size_t)inst * NX, u_des + (size_t)inst * NU, rbd + (size_t)inst * 32, md, stance_mode ? stance_mode[inst] != 0 : false, sh,
+                    nullptr, nullptr, nullptr, nullptr, nullptr, &nw);
+  int m = 0;
+  const int nz = wbc_reduced_build(sh, md, nw, rho, w.H, qp_ld(WZ_N), gz, Az, lbz, ubz, stcol, m);
+  if (lane < NJ) nlej[lane] = sh.nle[6 + lane];
+  __syncwarp();
+  // the workspace is carved for n = 28 (leading dimension 29); smaller problems (nz = 22, 16) use the same leading dimension
+  QpResult r = qp_solve_warp(nz, m, nullptr, gz, Az, lbz, ubz, 0.0, max_iter, xz, w);
+  __syncwarp();
+  double* out = sol + (size_t)inst * NWBC;
+  if (lane < NQ) out[lane] = xz[lane];
+  if (lane < 12) {
+    double f = 0.0;
+    for (int c = 0; c < nz - NQ; ++c) if (stcol[c] == lane) f = xz[NQ + c];
+    out[NQ + lane] = f;
+  }
+  if (lane < NJ) {
+    double t = nlej[lane];
+    for (int c = 0; c < nz; ++c) t += Az[(6 + lane) * nz + c] * xz[c];
+    out[NQ + 12 + lane] = t;
+  }
+  if (lane == 0) { if (status) status[inst] = r.status; if (iters) iters[inst] = r.iters; }
+}
+
 // LeggedRobotInitializer::compute (initialization/LeggedRobotInitializer.cpp:67-77)
 __global__ void cold_start_kernel(int B, int N, const double* x0, const int32_t* mode, double* xt, double* ut) {
   const int inst = blockIdx.x;
@@ -214,6 +265,7 @@ struct hb_ctx {
   // MPC scratch
   double *gains, *dxt, *dut, *perf;
   double *lin, *proj, *rk;   // version-2 pipeline records
+  int wbc_generic;           // HB_WBC_GENERIC=1: assemble the reference-layout QP and run the generic solver (A/B comparison)
   int sqp_version;           // 2 (default) or 1 (HB_SQP_VERSION=1: fused backward sweep, kept for A/B comparison)
   int32_t* flags;
   // WBC scratch
@@ -329,6 +381,8 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   {
     const char* v = getenv("HB_SQP_VERSION");
     ctx->sqp_version = (v && v[0] == '1') ? 1 : 2;
+    const char* g = getenv("HB_WBC_GENERIC");
+    ctx->wbc_generic = (g && g[0] == '1') ? 1 : 0;
   }
   if (ctx->sqp_version == 1) ok = ok && dalloc(&ctx->gains, B * N * GAIN_STRIDE) == cudaSuccess;
   else ok = ok && dalloc(&ctx->lin, B * N * LIN_STRIDE) == cudaSuccess && dalloc(&ctx->proj, B * N * PJ_STRIDE) == cudaSuccess && dalloc(&ctx->rk, B * N * RK_STRIDE) == cudaSuccess;
@@ -349,6 +403,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   cudaFuncSetAttribute(probe_flow_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MpcShared));
   cudaFuncSetAttribute(mpc_forward_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsShared));
   cudaFuncSetAttribute(qp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(wbc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wbc_fused_doubles() * sizeof(double)));
   cudaFuncSetAttribute(lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(LinHalf)));
   cudaFuncSetAttribute(lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqShared));
   cudaFuncSetAttribute(riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicShared));
@@ -442,6 +497,16 @@ int hb_wbc_solve_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double
   if (B == 0) return HB_OK;
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (set_device(ctx)) return HB_ECUDA;
+  if (!ctx->wbc_generic) {
+    const size_t per_warp = wbc_fused_doubles() * sizeof(double);
+    prof_begin(ctx, K_QP);
+    wbc_fused_kernel<<<B, 32, per_warp, ctx->stream>>>(B, x_des, u_des, rbd, mode, stance_mode, ctx->cfg.wbc_rho, ctx->cfg.qp_max_iter, sol,
+                                                        status ? status : ctx->wstatus, ctx->witers);
+    prof_end(ctx);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return HB_OK;
+  }
   const int wpb = 4;
   prof_begin(ctx, K_WBC_ASSEMBLE);
   wbc_assemble_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, sizeof(WbcShared) * wpb, ctx->stream>>>(B, x_des, u_des, rbd, mode, stance_mode, ctx->qH, ctx->qg,

@@ -27,44 +27,45 @@ struct QpWorkspace {
   double *f, *s, *z, *rs, *ds, *dz, *rc, *sgn;
   int *in_row, *in_c0, *in_c1, *eq_row;
   int ldn, ldv, lds;
+  int me_cap, mi_cap;   // capacity of the equality / one-sided inequality lists
 };
 
 __host__ __device__ inline int qp_ld(int n) { return n | 1; }
 
-// doubles needed by one warp
-__host__ __device__ inline size_t qp_workspace_doubles(int n) {
-  const int ldn = qp_ld(n);
+// doubles needed by one warp for problems with n variables, <= me_cap equalities and <= mi_cap one-sided inequality entries
+__host__ __device__ inline size_t qp_workspace_doubles(int n, int me_cap = QP_MAX_EQ, int mi_cap = QP_MAX_IN) {
+  const int ldn = qp_ld(n), lde = me_cap | 1;
   size_t d = 0;
   d += (size_t)n * ldn;            // H
-  d += (size_t)QP_MAX_EQ * ldn;    // Aeq
+  d += (size_t)me_cap * ldn;       // Aeq
   d += (size_t)n * ldn;            // K
-  d += (size_t)n * 33;             // V
-  d += (size_t)32 * 33;            // S
-  d += n + 32;                     // kdi, sdi
+  d += (size_t)n * lde;            // V
+  d += (size_t)me_cap * lde;       // S
+  d += n + me_cap;                 // kdi, sdi
   d += 6 * (size_t)n;              // g x rd dx t1 t2
-  d += 5 * 32;                     // beq y rp dy t3
-  d += 8 * (size_t)QP_MAX_IN;      // f s z rs ds dz rc sgn
-  d += (3 * QP_MAX_IN + QP_MAX_EQ + 1) / 2 + 1;  // int arrays
+  d += 5 * (size_t)me_cap;         // beq y rp dy t3
+  d += 8 * (size_t)mi_cap;         // f s z rs ds dz rc sgn
+  d += (3 * (size_t)mi_cap + me_cap + 1) / 2 + 1;  // int arrays
   return d;
 }
 
-__device__ inline void qp_carve(double* base, int n, QpWorkspace& w) {
-  const int ldn = qp_ld(n);
-  w.ldn = ldn; w.ldv = 33; w.lds = 33;
+__device__ inline void qp_carve(double* base, int n, QpWorkspace& w, int me_cap = QP_MAX_EQ, int mi_cap = QP_MAX_IN) {
+  const int ldn = qp_ld(n), lde = me_cap | 1;
+  w.ldn = ldn; w.ldv = lde; w.lds = lde; w.me_cap = me_cap; w.mi_cap = mi_cap;
   double* p = base;
   w.H = p; p += n * ldn;
-  w.Aeq = p; p += QP_MAX_EQ * ldn;
+  w.Aeq = p; p += me_cap * ldn;
   w.K = p; p += n * ldn;
-  w.V = p; p += n * 33;
-  w.S = p; p += 32 * 33;
+  w.V = p; p += n * lde;
+  w.S = p; p += me_cap * lde;
   w.kdi = p; p += n;
-  w.sdi = p; p += 32;
+  w.sdi = p; p += me_cap;
   w.g = p; p += n; w.x = p; p += n; w.rd = p; p += n; w.dx = p; p += n; w.t1 = p; p += n; w.t2 = p; p += n;
-  w.beq = p; p += 32; w.y = p; p += 32; w.rp = p; p += 32; w.dy = p; p += 32; w.t3 = p; p += 32;
-  w.f = p; p += QP_MAX_IN; w.s = p; p += QP_MAX_IN; w.z = p; p += QP_MAX_IN; w.rs = p; p += QP_MAX_IN;
-  w.ds = p; p += QP_MAX_IN; w.dz = p; p += QP_MAX_IN; w.rc = p; p += QP_MAX_IN; w.sgn = p; p += QP_MAX_IN;
+  w.beq = p; p += me_cap; w.y = p; p += me_cap; w.rp = p; p += me_cap; w.dy = p; p += me_cap; w.t3 = p; p += me_cap;
+  w.f = p; p += mi_cap; w.s = p; p += mi_cap; w.z = p; p += mi_cap; w.rs = p; p += mi_cap;
+  w.ds = p; p += mi_cap; w.dz = p; p += mi_cap; w.rc = p; p += mi_cap; w.sgn = p; p += mi_cap;
   int* ip = reinterpret_cast<int*>(p);
-  w.in_row = ip; ip += QP_MAX_IN; w.in_c0 = ip; ip += QP_MAX_IN; w.in_c1 = ip; ip += QP_MAX_IN; w.eq_row = ip;
+  w.in_row = ip; ip += mi_cap; w.in_c0 = ip; ip += mi_cap; w.in_c1 = ip; ip += mi_cap; w.eq_row = ip;
 }
 
 // In-place Cholesky M = L L' (lower triangle) followed by Li = L^-1, stored transposed in the strict upper triangle
@@ -168,23 +169,24 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
     const unsigned bup = __ballot_sync(HB_FULL_MASK, up);
     const unsigned bdn = __ballot_sync(HB_FULL_MASK, dn);
     const unsigned below = (1u << lane) - 1u;
-    if (is_eq) { const int e = me + __popc(beq & below); if (e < QP_MAX_EQ) { w.eq_row[e] = r; w.beq[e] = hi; } }
-    if (up) { const int e = mi + __popc(bup & below); if (e < QP_MAX_IN) { w.in_row[e] = r; w.in_c0[e] = c0; w.in_c1[e] = c1; w.sgn[e] = 1.0; w.f[e] = hi; } }
+    if (is_eq) { const int e = me + __popc(beq & below); if (e < w.me_cap) { w.eq_row[e] = r; w.beq[e] = hi; } }
+    if (up) { const int e = mi + __popc(bup & below); if (e < w.mi_cap) { w.in_row[e] = r; w.in_c0[e] = c0; w.in_c1[e] = c1; w.sgn[e] = 1.0; w.f[e] = hi; } }
     const int mi2 = mi + __popc(bup);
-    if (dn) { const int e = mi2 + __popc(bdn & below); if (e < QP_MAX_IN) { w.in_row[e] = r; w.in_c0[e] = c0; w.in_c1[e] = c1; w.sgn[e] = -1.0; w.f[e] = -lo; } }
+    if (dn) { const int e = mi2 + __popc(bdn & below); if (e < w.mi_cap) { w.in_row[e] = r; w.in_c0[e] = c0; w.in_c1[e] = c1; w.sgn[e] = -1.0; w.f[e] = -lo; } }
     me += __popc(beq);
     mi = mi2 + __popc(bdn);
   }
   infeasible = __any_sync(HB_FULL_MASK, infeasible);
   QpResult res{1, 0};
-  if (infeasible || me > QP_MAX_EQ || mi > QP_MAX_IN || n > QP_MAX_N) {
+  if (infeasible || me > w.me_cap || mi > w.mi_cap || n > QP_MAX_N) {
     for (int i = lane; i < n; i += 32) x_out[i] = 0.0;
     res.status = 2;
     return res;
   }
   __syncwarp();
   // ---------------- stage H, Aeq, g; initial point
-  for (int idx = lane; idx < n * n; idx += 32) { const int i = idx / n, c = idx - i * n; w.H[i * ldn + c] = H[idx]; }
+  // H == nullptr: the caller assembled the Hessian directly in w.H (leading dimension ldn)
+  if (H != nullptr) for (int idx = lane; idx < n * n; idx += 32) { const int i = idx / n, c = idx - i * n; w.H[i * ldn + c] = H[idx]; }
   for (int e = 0; e < me; ++e) {
     const double* a = A + (size_t)w.eq_row[e] * n;
     for (int c = lane; c < n; c += 32) w.Aeq[e * ldn + c] = a[c];

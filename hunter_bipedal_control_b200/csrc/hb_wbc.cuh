@@ -46,7 +46,7 @@ __device__ inline void rotation_error_world(const double* Rref, const double* Rm
 // Assemble one instance. Outputs may be global or shared. Returns the number of constraint rows m.
 __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const double* __restrict__ u_des,
                                         const double* __restrict__ rbd, int mode, bool stance_mode, WbcShared& sh,
-                                        double* H, double* g, double* A, double* lbA, double* ubA) {
+                                        double* H, double* g, double* A, double* lbA, double* ubA, int* nw_out = nullptr) {
   const int lane = lane_id();
   const Model& md = c_model;
   // ---- measured q, v (WbcBase.cpp:72-79)
@@ -191,6 +191,8 @@ __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const 
     }
   }
   __syncwarp();
+  if (nw_out) *nw_out = nw;
+  if (H == nullptr) return 16 + 3 * (4 - nc) + 20 + 5 * nc + 3 * (4 - nc);   // terms only (fused path builds the reduced QP from sh)
   // ---- H = Aw'Aw, g = -Aw'bw (WeightedWbc.cpp:38-41); only the qdd block is non-zero
   for (int idx = lane; idx < NWBC * NWBC; idx += 32) {
     const int i = idx / NWBC, j = idx - i * NWBC;
@@ -234,6 +236,63 @@ __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const 
   }
   __syncwarp();
   return m;
+}
+
+// Reduced WeightedWbc QP for the fused path: tau = M_j qdd - J_j' F + nle_j and F_swing = 0 are substituted, leaving
+//   z = [qdd(16), F_stance(3 n_st)],  6 equalities (base rows of the EoM), 10 two-sided torque rows, 5 friction rows per
+// stance contact. The Tikhonov term rho ||[qdd, F, tau]||^2 of the full problem is carried over exactly (rho I + rho T'T).
+// Hz is written into `Hw` (leading dimension ldh), rows of Az have stride nz. Returns nz; m_out = number of rows.
+__device__ inline int wbc_reduced_build(const WbcShared& sh, int mode, int nw, double rho, double* Hw, int ldh, double* gz, double* Az,
+                                        double* lbz, double* ubz, int* stcol /*12*/, int& m_out) {
+  const int lane = lane_id();
+  const Model& md = c_model;
+  int nst = 0;
+  for (int j = 0; j < 12; ++j) if (contact_flag(mode, j / 3)) { if (lane == 0) stcol[nst] = j; ++nst; }
+  const int nz = NQ + nst;
+  const int nc = nst / 3;
+  const int m = 6 + NJ + 5 * nc;
+  __syncwarp();
+  // rows: 6 base EoM equalities, 10 torque rows T = [M_j, -J_j,st'], 5 friction rows per stance contact
+  for (int idx = lane; idx < m * nz; idx += 32) {
+    const int r = idx / nz, c = idx - r * nz;
+    double v = 0.0;
+    if (r < 6 + NJ) v = (c < NQ) ? sh.M[r * 16 + c] : -sh.J[stcol[c - NQ] * 16 + r];
+    else {
+      const int fr = r - 6 - NJ, ci = fr / 5, k = fr - 5 * ci;     // stance contact ci occupies columns NQ+3ci .. NQ+3ci+2
+      const int cc = c - NQ - 3 * ci;
+      if (cc >= 0 && cc < 3) {
+        const double mu = HB_WBC_FRICTION_MU;
+        const double pyr[5][3] = {{0, 0, -1}, {1, 0, -mu}, {-1, 0, -mu}, {0, 1, -mu}, {0, -1, -mu}};
+        v = pyr[k][cc];
+      }
+    }
+    Az[idx] = v;
+  }
+  for (int r = lane; r < m; r += 32) {
+    if (r < 6) { lbz[r] = -sh.nle[r]; ubz[r] = -sh.nle[r]; }
+    else if (r < 6 + NJ) { const int j = r - 6; lbz[r] = -md.torque_limit[j] - sh.nle[6 + j]; ubz[r] = md.torque_limit[j] - sh.nle[6 + j]; }
+    else { lbz[r] = -QP_INFTY; ubz[r] = 0.0; }
+  }
+  __syncwarp();
+  const double* Tm = Az + 6 * nz;   // torque rows double as the map tau = T z + nle_j
+  for (int idx = lane; idx < nz * nz; idx += 32) {
+    const int i = idx / nz, j = idx - i * nz;
+    double s = (i == j) ? rho : 0.0;
+    if (i < NQ && j < NQ) for (int r = 0; r < nw; ++r) s += sh.Aw[r * 16 + i] * sh.Aw[r * 16 + j];
+    double t = 0.0;
+    for (int r = 0; r < NJ; ++r) t += Tm[r * nz + i] * Tm[r * nz + j];
+    Hw[i * ldh + j] = s + rho * t;
+  }
+  for (int i = lane; i < nz; i += 32) {
+    double s = 0.0;
+    if (i < NQ) for (int r = 0; r < nw; ++r) s -= sh.Aw[r * 16 + i] * sh.bw[r];
+    double t = 0.0;
+    for (int r = 0; r < NJ; ++r) t += Tm[r * nz + i] * sh.nle[6 + r];
+    gz[i] = s + rho * t;
+  }
+  __syncwarp();
+  m_out = m;
+  return nz;
 }
 
 }  // namespace hb
