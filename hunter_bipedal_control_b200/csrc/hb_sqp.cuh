@@ -31,6 +31,7 @@ constexpr int PJ_AT = 0, PJ_BT = 484, PJ_BTV = 836, PJ_QT = 858, PJ_PT = 1342, P
               PJ_PXV = 1988, PJ_NV = 2208, PJ_PEV = 2288, PJ_META = 2298, PJ_STRIDE = 2320;
 // META: [0] nt, [1] n_stance_force_dims, [2] nv, [3] cost, [4] defect^2, [5] eq^2, [6] overflow flag
 constexpr int RK_STRIDE = NTMAX * NX + NTMAX;  // K (nt x 22, ld 22) + kff
+__host__ __device__ inline int ntp_of(int nt) { return nt <= 6 ? 6 : (nt <= 10 ? 10 : (nt <= 12 ? 12 : 16)); }
 
 // ---------------------------------------------------------------- K0
 struct LinHalf {
@@ -543,7 +544,10 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     for (int kk = 0; kk < NJ; ++kk) s += pc[kk] * sh.rRpe[kk] + sh.Pv[kk * NX + j] * sh.pev[kk];
     out[PJ_QV + j] = dt * s;
   }
-  // Bt (22 x nt, ld NTMAX): stance-force columns then null-space columns
+  // Bt (22 x nt, ld NTMAX): stance-force columns then null-space columns; padded columns are zero
+  const int ntp = ntp_of(nt);
+  for (int idx = lane; idx < NX * NTMAX; idx += 32) sh.Bt[idx] = 0.0;
+  __syncwarp();
   if (lane < nt) {
     const int c = lane;
     if (c < nf) {
@@ -574,10 +578,11 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
   }
   __syncwarp();
   // Rt (nt x nt), Pt (nt x 22), rt (nt)
-  for (int idx = lane; idx < nt * nt; idx += 32) {
-    const int i = idx / nt, j = idx - i * nt;
+  for (int idx = lane; idx < ntp * ntp; idx += 32) {
+    const int i = idx / ntp, j = idx - i * ntp;
     double s = 0.0;
-    if (i < nf && j < nf) s = sh.RFF[sh.stidx[i] * 12 + sh.stidx[j]];
+    if (i >= nt || j >= nt) s = (i == j) ? 1.0 / dt : 0.0;       // identity on the padded diagonal
+    else if (i < nf && j < nf) s = sh.RFF[sh.stidx[i] * 12 + sh.stidx[j]];
     else if (i >= nf && j >= nf) {
       const int ci = i - nf, cj = j - nf;
       for (int p = 0; p < NJ; ++p) { double t = 0.0; for (int qq = 0; qq < NJ; ++qq) t += sh.Rvv[p * NJ + qq] * sh.Nv[qq * 8 + cj]; s += sh.Nv[p * 8 + ci] * t; }
@@ -585,15 +590,16 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     out[PJ_RT + i * NTMAX + j] = dt * s;
   }
   if (lane < NX) {
-    for (int c = 0; c < nt; ++c) {
+    for (int c = 0; c < ntp; ++c) {
       double s = 0.0;
-      if (c >= nf) { const int cc = c - nf; for (int kk = 0; kk < NJ; ++kk) s += sh.Nv[kk * 8 + cc] * sh.T1[kk * NX + lane]; }
+      if (c >= nf && c < nt) { const int cc = c - nf; for (int kk = 0; kk < NJ; ++kk) s += sh.Nv[kk * 8 + cc] * sh.T1[kk * NX + lane]; }
       out[PJ_PT + c * NX + lane] = dt * s;
     }
   }
-  if (lane < nt) {
+  if (lane < ntp) {
     double s;
-    if (lane < nf) s = sh.r[sh.stidx[lane]];
+    if (lane >= nt) s = 0.0;
+    else if (lane < nf) s = sh.r[sh.stidx[lane]];
     else { s = 0.0; const int cc = lane - nf; for (int kk = 0; kk < NJ; ++kk) s += sh.Nv[kk * 8 + cc] * sh.rRpe[kk]; }
     out[PJ_RV + lane] = dt * s;
   }
@@ -608,11 +614,126 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
 }
 
 // ---------------------------------------------------------------- K2: value-function recursion
+// Row-owner products: lane i owns row i of the result, the right operand is streamed from shared memory with 128-bit
+// broadcast loads (two doubles per load), N accumulators stay in registers. NTP = number of free inputs padded to an even
+// compile-time size (6 flight, 10 single support, 12 stance, 16 degenerate); the padded rows/columns of the projected model
+// are zero (identity on the diagonal of R~), so the padded gains are zero.
+template <int N, bool TA, int MODE>
+__device__ __forceinline__ void rowmm(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda,
+                                      const double* __restrict__ B, int ldb, int m, int kdim) {
+  const int i = lane_id();
+  if (i < m) {
+    double c[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) c[j] = (MODE == 1) ? C[i * ldc + j] : 0.0;
+#pragma unroll 2
+    for (int k = 0; k < kdim; ++k) {
+      const double a = TA ? A[k * lda + i] : A[i * lda + k];
+      const double* br = B + k * ldb;
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        const double2 b2 = *reinterpret_cast<const double2*>(br + j);
+        c[j] = fma(a, b2.x, c[j]);
+        c[j + 1] = fma(a, b2.y, c[j + 1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) C[i * ldc + j] = c[j];
+  }
+  __syncwarp();
+}
+
+
 struct RicShared {
   double S[TS], At[TS], SA[TS];
-  double Bt[NX * NTMAX], SB[NX * NTMAX], Hux[NTMAX * NX], K[NTMAX * NX], Huu[NTMAX * 17];
+  double Bt[NX * NTMAX], SB[NX * NTMAX], HuxT[NX * NTMAX], K[NTMAX * NX], Huu[NTMAX * 18];
   double sv[NX], bt[NX], sb[NX], qt[NX], rt[NTMAX], hu[NTMAX], kff[NTMAX], idg[NTMAX];
 };
+
+template <int NTP>
+__device__ __noinline__ void riccati_node(RicShared& sh, const double* __restrict__ rec, double* __restrict__ rk, bool& fail) {
+  const int lane = lane_id();
+  // SA = S At ; SB = S Bt ; sb = s + S bt
+  rowmm<NX, false, 0>(sh.SA, NX, sh.S, NX, sh.At, NX, NX, NX);
+  rowmm<NTP, false, 0>(sh.SB, NTMAX, sh.S, NX, sh.Bt, NTMAX, NX, NX);
+  if (lane < NX) {
+    double s0 = sh.sv[lane], s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < NX; k += 2) { s0 = fma(sh.S[lane * NX + k], sh.bt[k], s0); s1 = fma(sh.S[lane * NX + k + 1], sh.bt[k + 1], s1); }
+    sh.sb[lane] = s0 + s1;
+    // Hux^T initialised with Pt^T (Pt is NTP x 22 in the record)
+#pragma unroll
+    for (int c = 0; c < NTP; ++c) sh.HuxT[lane * NTMAX + c] = rec[PJ_PT + c * NX + lane];
+  }
+  if (lane < NTP) {
+#pragma unroll
+    for (int c = 0; c < NTP; ++c) sh.Huu[lane * 18 + c] = rec[PJ_RT + lane * NTMAX + c];
+  }
+  __syncwarp();
+  // Hux^T (22 x NTP) += SA^T Bt ; Huu (NTP x NTP) += Bt^T SB ; hu = rt + Bt^T sb
+  rowmm<NTP, true, 1>(sh.HuxT, NTMAX, sh.SA, NX, sh.Bt, NTMAX, NX, NX);
+  rowmm<NTP, true, 1>(sh.Huu, 18, sh.Bt, NTMAX, sh.SB, NTMAX, NTP, NX);
+  if (lane < NTP) {
+    double s0 = sh.rt[lane];
+#pragma unroll
+    for (int k = 0; k < NX; ++k) s0 = fma(sh.Bt[k * NTMAX + lane], sh.sb[k], s0);
+    sh.hu[lane] = s0;
+  }
+  __syncwarp();
+  // symmetrise the lower triangle, factorise, K = -Huu^-1 Hux (stored NTP x 22), kff = -Huu^-1 hu
+  if (lane < NTP) {
+#pragma unroll
+    for (int c = 0; c < NTP; ++c) if (c < lane) sh.Huu[lane * 18 + c] = 0.5 * (sh.Huu[lane * 18 + c] + sh.Huu[c * 18 + lane]);
+  }
+  __syncwarp();
+  if (!warp_chol_inv(sh.Huu, NTP, 18, sh.idg, lane)) fail = true;
+  if (lane <= NX) {
+    double col[NTP], y[NTP];
+#pragma unroll
+    for (int c = 0; c < NTP; ++c) col[c] = (lane < NX) ? sh.HuxT[lane * NTMAX + c] : sh.hu[c];
+#pragma unroll
+    for (int c = 0; c < NTP; ++c) {
+      double s = sh.idg[c] * col[c];
+#pragma unroll
+      for (int kk = 0; kk < c; ++kk) s = fma(sh.Huu[kk * 18 + c], col[kk], s);
+      y[c] = s;
+    }
+#pragma unroll
+    for (int c = 0; c < NTP; ++c) {
+      double s = sh.idg[c] * y[c];
+#pragma unroll
+      for (int kk = c + 1; kk < NTP; ++kk) s = fma(sh.Huu[c * 18 + kk], y[kk], s);
+      col[c] = -s;
+    }
+    if (lane < NX) {
+#pragma unroll
+      for (int c = 0; c < NTP; ++c) { sh.K[c * NX + lane] = col[c]; rk[c * NX + lane] = col[c]; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NTP; ++c) { sh.kff[c] = col[c]; rk[NTMAX * NX + c] = col[c]; }
+    }
+  }
+  __syncwarp();
+  // s <- qt + At' sb + Hux' kff
+  if (lane < NX) {
+    double s0 = sh.qt[lane], s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < NX; k += 2) { s0 = fma(sh.At[k * NX + lane], sh.sb[k], s0); s1 = fma(sh.At[(k + 1) * NX + lane], sh.sb[k + 1], s1); }
+#pragma unroll
+    for (int c = 0; c < NTP; ++c) s0 = fma(sh.HuxT[lane * NTMAX + c], sh.kff[c], s0);
+    sh.sv[lane] = s0 + s1;
+    // S row i initialised with Qt row i
+#pragma unroll
+    for (int j = 0; j < NX; ++j) sh.S[lane * NX + j] = rec[PJ_QT + lane * NX + j];
+  }
+  __syncwarp();
+  // S += At' SA + Hux' K
+  rowmm<NX, true, 1>(sh.S, NX, sh.At, NX, sh.SA, NX, NX, NX);
+  rowmm<NX, false, 1>(sh.S, NX, sh.HuxT, NTMAX, sh.K, NX, NX, NTP);
+  // symmetrise
+  for (int idx = lane; idx < TS; idx += 32) { const int i = idx / NX, j = idx - i * NX; if (j > i) { const double v = 0.5 * (sh.S[idx] + sh.S[j * NX + i]); sh.S[idx] = v; sh.S[j * NX + i] = v; } }
+  __syncwarp();
+}
 
 __global__ void __launch_bounds__(32) riccati_kernel(SqpArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -625,6 +746,7 @@ __global__ void __launch_bounds__(32) riccati_kernel(SqpArgs a) {
   double merit = 0.0, dyn = 0.0, eqs = 0.0;
   for (int k = N - 1; k >= 0; --k) {
     const double* rec = a.proj + ((size_t)inst * N + k) * PJ_STRIDE;
+    double* rk = a.rk + ((size_t)inst * N + k) * RK_STRIDE;
     const int nt = (int)rec[PJ_META];
     merit += a.dt * rec[PJ_META + 3]; dyn += a.dt * rec[PJ_META + 4]; eqs += a.dt * rec[PJ_META + 5];
     if (rec[PJ_META + 6] != 0.0) fail = true;
@@ -633,72 +755,11 @@ __global__ void __launch_bounds__(32) riccati_kernel(SqpArgs a) {
     if (lane < NX) { sh.bt[lane] = rec[PJ_BTV + lane]; sh.qt[lane] = rec[PJ_QV + lane]; }
     if (lane < NTMAX) sh.rt[lane] = rec[PJ_RV + lane];
     __syncwarp();
-    // SA = S At ; SB = S Bt ; sb = s + S bt
-    wmm<false, 0>(sh.SA, NX, sh.S, NX, sh.At, NX, NX, NX, NX);
-    wmm<false, 0>(sh.SB, NTMAX, sh.S, NX, sh.Bt, NTMAX, NX, NX, nt);
-    wmv<false, 0>(sh.sb, sh.S, NX, sh.bt, NX, NX);
-    if (lane < NX) sh.sb[lane] += sh.sv[lane];
-    __syncwarp();
-    // Hux = Pt + Bt' SA ; Huu = Rt + Bt' SB ; hu = rt + Bt' sb
-    for (int idx = lane; idx < nt * NX; idx += 32) sh.Hux[idx] = rec[PJ_PT + idx];
-    for (int idx = lane; idx < nt * nt; idx += 32) { const int i = idx / nt, j = idx - i * nt; sh.Huu[i * 17 + j] = rec[PJ_RT + i * NTMAX + j]; }
-    __syncwarp();
-    wmm<true, 1>(sh.Hux, NX, sh.Bt, NTMAX, sh.SA, NX, nt, NX, NX);
-    wmm<true, 1>(sh.Huu, 17, sh.Bt, NTMAX, sh.SB, NTMAX, nt, NX, nt);
-    wmv<true, 0>(sh.hu, sh.Bt, NTMAX, sh.sb, nt, NX);
-    if (lane < nt) sh.hu[lane] += sh.rt[lane];
-    __syncwarp();
-    for (int idx = lane; idx < nt * nt; idx += 32) { const int i = idx / nt, j = idx - i * nt; if (j < i) sh.Huu[i * 17 + j] = 0.5 * (sh.Huu[i * 17 + j] + sh.Huu[j * 17 + i]); }
-    __syncwarp();
-    if (nt > 0) {
-      if (!warp_chol_inv(sh.Huu, nt, 17, sh.idg, lane)) fail = true;
-      if (lane <= NX) {
-        double col[NTMAX], y[NTMAX];
-#pragma unroll
-        for (int i = 0; i < NTMAX; ++i) col[i] = (i < nt) ? ((lane < NX) ? sh.Hux[i * NX + lane] : sh.hu[i]) : 0.0;
-#pragma unroll
-        for (int i = 0; i < NTMAX; ++i) {
-          double s = 0.0;
-          if (i < nt) { s = sh.idg[i] * col[i];
-#pragma unroll
-            for (int kk = 0; kk < NTMAX; ++kk) if (kk < i) s += sh.Huu[kk * 17 + i] * col[kk]; }
-          y[i] = s;
-        }
-#pragma unroll
-        for (int i = 0; i < NTMAX; ++i) {
-          double s = 0.0;
-          if (i < nt) { s = sh.idg[i] * y[i];
-#pragma unroll
-            for (int kk = 0; kk < NTMAX; ++kk) if (kk > i && kk < nt) s += sh.Huu[i * 17 + kk] * y[kk]; }
-          col[i] = -s;
-        }
-        if (lane < NX) {
-#pragma unroll
-          for (int i = 0; i < NTMAX; ++i) if (i < nt) sh.K[i * NX + lane] = col[i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < NTMAX; ++i) if (i < nt) sh.kff[i] = col[i];
-        }
-      }
-    }
-    __syncwarp();
-    // store K, kff
-    double* rk = a.rk + ((size_t)inst * N + k) * RK_STRIDE;
-    for (int idx = lane; idx < nt * NX; idx += 32) rk[idx] = sh.K[idx];
-    if (lane < nt) rk[NTMAX * NX + lane] = sh.kff[lane];
-    // S <- Qt + At' SA + Hux' K ; s <- qt + At' sb + Hux' kff   (S assembled in At's slot? no: use SB region is too small -> reuse SA after products)
-    // first s (needs At, Hux), then S into a temporary (Bt/SB are dead now -> use At after the product is done via SA)
-    wmv<true, 0>(sh.sv, sh.At, NX, sh.sb, NX, NX);
-    wmv<true, 1>(sh.sv, sh.Hux, NX, sh.kff, NX, nt);
-    if (lane < NX) sh.sv[lane] += sh.qt[lane];
-    // T = At' SA -> written over S is unsafe (S not needed any more: SA, SB, sb already formed) -> write into S directly
-    wmm<true, 0>(sh.S, NX, sh.At, NX, sh.SA, NX, NX, NX, NX);
-    wmm<true, 1>(sh.S, NX, sh.Hux, NX, sh.K, NX, NX, nt, NX);
-    for (int idx = lane; idx < TS; idx += 32) sh.S[idx] += rec[PJ_QT + idx];
-    __syncwarp();
-    // symmetrise in place (pairs handled by the lane owning the lower index)
-    for (int idx = lane; idx < TS; idx += 32) { const int i = idx / NX, j = idx - i * NX; if (j > i) { const double v = 0.5 * (sh.S[idx] + sh.S[j * NX + i]); sh.S[idx] = v; sh.S[j * NX + i] = v; } }
-    __syncwarp();
+    const int ntp = ntp_of(nt);
+    if (ntp == 12) riccati_node<12>(sh, rec, rk, fail);
+    else if (ntp == 10) riccati_node<10>(sh, rec, rk, fail);
+    else if (ntp == 6) riccati_node<6>(sh, rec, rk, fail);
+    else riccati_node<16>(sh, rec, rk, fail);
   }
   if (lane == 0) {
     double* pf = a.perf + (size_t)inst * 4;
@@ -708,10 +769,39 @@ __global__ void __launch_bounds__(32) riccati_kernel(SqpArgs a) {
 }
 
 // ---------------------------------------------------------------- K3: forward pass + filter line search
-struct Fw2Shared {
+// per-node data of the forward pass, double-buffered and filled with cp.async (16-byte LDGSTS) one node ahead
+struct FwNode {
   double At[TS], Bt[NX * NTMAX], K[NTMAX * NX], Pxv[NJ * NX], Nv[NJ * NVMAX];
-  double bt[NX], kff[NTMAX], pev[NJ], qt[NX], rt[NTMAX], dx[NX], dxn[NX], w[NTMAX], u[NU];
+  double bt[NX], qt[NX], kff[NTMAX], rt[NTMAX], pev[NJ], meta[8], u[NU];
 };
+struct Fw2Shared {
+  FwNode nd[2];
+  double dx[NX], dxn[NX], w[NTMAX];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
+
+__device__ __forceinline__ void fw_prefetch(FwNode& n, const double* __restrict__ rec, const double* __restrict__ rk, const double* __restrict__ uk, int lane) {
+  auto copy = [&](double* dst, const double* src, int ndbl) { for (int i = 2 * lane; i < ndbl; i += 64) cp_async16(dst + i, src + i); };
+  copy(n.At, rec + PJ_AT, TS);
+  copy(n.Bt, rec + PJ_BT, NX * NTMAX);
+  copy(n.K, rk, NTMAX * NX);
+  copy(n.Pxv, rec + PJ_PXV, NJ * NX);
+  copy(n.Nv, rec + PJ_NV, NJ * NVMAX);
+  copy(n.bt, rec + PJ_BTV, NX);
+  copy(n.qt, rec + PJ_QV, NX);
+  copy(n.kff, rk + NTMAX * NX, NTMAX);
+  copy(n.rt, rec + PJ_RV, NTMAX);
+  copy(n.pev, rec + PJ_PEV, NJ);
+  copy(n.meta, rec + PJ_META, 8);
+  copy(n.u, uk, NU);
+  cp_async_commit();
+}
 
 __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int max_trials, void* info_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -725,49 +815,48 @@ __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int 
   const double* xref = a.x_ref + (size_t)inst * (N + 1) * NX;
   const double* swing = a.swing + (size_t)inst * (N + 1) * 24;
   const int32_t* mode = a.mode + (size_t)inst * (N + 1);
+  const double* proj = a.proj + (size_t)inst * N * PJ_STRIDE;
+  const double* rkb = a.rk + (size_t)inst * N * RK_STRIDE;
+  fw_prefetch(sh.nd[0], proj, rkb, ut, lane);
   if (lane < NX) { xt[lane] = a.x0[(size_t)inst * NX + lane]; sh.dx[lane] = 0.0; dxt[lane] = 0.0; }
-  __syncwarp();
   double armijo = 0.0;
   bool finite = (a.flags[inst] == 0);
   for (int k = 0; k < N; ++k) {
-    const double* rec = a.proj + ((size_t)inst * N + k) * PJ_STRIDE;
-    const double* rk = a.rk + ((size_t)inst * N + k) * RK_STRIDE;
-    const int nt = (int)rec[PJ_META], nf = (int)rec[PJ_META + 1], nv = (int)rec[PJ_META + 2];
-    const int md_k = mode[k];
-    for (int idx = lane; idx < TS; idx += 32) sh.At[idx] = rec[PJ_AT + idx];
-    for (int idx = lane; idx < NX * NTMAX; idx += 32) sh.Bt[idx] = rec[PJ_BT + idx];
-    for (int idx = lane; idx < nt * NX; idx += 32) sh.K[idx] = rk[idx];
-    for (int idx = lane; idx < NJ * NX; idx += 32) sh.Pxv[idx] = rec[PJ_PXV + idx];
-    for (int idx = lane; idx < NJ * NVMAX; idx += 32) sh.Nv[idx] = rec[PJ_NV + idx];
-    if (lane < NX) { sh.bt[lane] = rec[PJ_BTV + lane]; sh.qt[lane] = rec[PJ_QV + lane]; sh.u[lane] = ut[k * NU + lane]; }
-    if (lane < NTMAX) { sh.kff[lane] = rk[NTMAX * NX + lane]; sh.rt[lane] = rec[PJ_RV + lane]; }
-    if (lane < NJ) sh.pev[lane] = rec[PJ_PEV + lane];
+    if (k + 1 < N) { fw_prefetch(sh.nd[(k + 1) & 1], proj + (size_t)(k + 1) * PJ_STRIDE, rkb + (size_t)(k + 1) * RK_STRIDE, ut + (k + 1) * NU, lane); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
     __syncwarp();
+    const FwNode& nd = sh.nd[k & 1];
+    const int nt = (int)nd.meta[0], nf = (int)nd.meta[1], nv = (int)nd.meta[2];
+    const int md_k = mode[k];
     double arm = 0.0;
     if (lane < nt) {
-      double s = sh.kff[lane];
-      for (int j = 0; j < NX; ++j) s = fma(sh.K[lane * NX + j], sh.dx[j], s);
+      double s = nd.kff[lane];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) s = fma(nd.K[lane * NX + j], sh.dx[j], s);
       sh.w[lane] = s;
-      arm = sh.rt[lane] * s;
+      arm = nd.rt[lane] * s;
     }
     __syncwarp();
     if (lane < NX) {
-      double s = sh.bt[lane];
-      for (int j = 0; j < NX; ++j) s = fma(sh.At[lane * NX + j], sh.dx[j], s);
-      for (int c = 0; c < nt; ++c) s = fma(sh.Bt[lane * NTMAX + c], sh.w[c], s);
+      double s = nd.bt[lane], s1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; j += 2) { s = fma(nd.At[lane * NX + j], sh.dx[j], s); s1 = fma(nd.At[lane * NX + j + 1], sh.dx[j + 1], s1); }
+      s += s1;
+      for (int c = 0; c < nt; ++c) s = fma(nd.Bt[lane * NTMAX + c], sh.w[c], s);
       sh.dxn[lane] = s;
       dxt[(k + 1) * NX + lane] = s;
-      arm += sh.qt[lane] * sh.dx[lane];
+      arm += nd.qt[lane] * sh.dx[lane];
       // du: stance forces are free variables, swing forces go to zero, vj from the projection
       double du;
       if (lane < 12) {
         if (contact_flag(md_k, lane / 3)) { int c = 0; for (int j = 0; j < lane; ++j) c += contact_flag(md_k, j / 3); du = sh.w[c]; }
-        else du = -sh.u[lane];
+        else du = -nd.u[lane];
       } else {
         const int i = lane - 12;
-        du = sh.pev[i];
-        for (int j = 0; j < NX; ++j) du = fma(sh.Pxv[i * NX + j], sh.dx[j], du);
-        for (int c = 0; c < nv; ++c) du = fma(sh.Nv[i * NVMAX + c], sh.w[nf + c], du);
+        du = nd.pev[i];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) du = fma(nd.Pxv[i * NX + j], sh.dx[j], du);
+        for (int c = 0; c < nv; ++c) du = fma(nd.Nv[i * NVMAX + c], sh.w[nf + c], du);
       }
       dut[k * NU + lane] = du;
       if (!isfinite(s) || !isfinite(du)) finite = false;
