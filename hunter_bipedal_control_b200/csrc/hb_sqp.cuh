@@ -216,24 +216,29 @@ __global__ void __launch_bounds__(64) lin_kernel(SqpArgs a) {
 }
 
 // ---------------------------------------------------------------- K1
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
+
+// Shared memory of the node LQ kernel. `rec` first holds the linearisation record (brought in with cp.async); once the
+// discretisation, cost and constraint rows are built it is dead and re-used for the projection workspace and the projected model.
 struct LqShared {
-  double Ad[TS];                 // discrete A, then At
-  double Q[TS];                  // Q, then Qt
-  double A1c[9 * NX], A2c[9 * NX];
+  double rec[LIN_STRIDE];
+  double Ad[TS];                       // discrete A, then At
   double BdF[9 * 12], Bdv[9 * NJ];     // rows 3..11 of Bd
-  double Bf1[36], Bf2[36], Bv1[60], Bv2[60];
-  double dpq[12 * NDIR], dvx[12 * NX], dvv[12 * NJ];
   double Cv[12 * NX], Dv[12 * NJ], ev[12];
-  double G[NJ * 36];             // 10 x (10 + 22 + 1) normal equations (ld 36)
-  double Pxv[NJ * NX], Nv[NJ * 8], pev[NJ];
+  double Nv[NJ * NVMAX], pev[NJ];
   double Rvv[NJ * NJ], Pv[NJ * NX], RFF[12 * 12];
-  double T1[NJ * NX];            // PRPx_v
-  double Bt[NX * NTMAX];
   double gx[8 * NX], gv[8 * NJ], gh[8];
-  double x[NX], u[NU], xn[NX], xref[NX], swing[24], f1[NX], f2[NX], b[NX], q[NX], r[NU], bt[NX], qt[NX], rRpe[NJ], rt[NTMAX];
-  double epos[12], evel[12];
+  double x[NX], u[NU], xn[NX], xref[NX], swing[24], b[NX], Qd[NX], q[NX], r[NU], bt[NX], rRpe[NJ];
   int rowc[12], rowa[12], rowt[12], piv[NJ], freev[NJ], stidx[12];
 };
+// aliases inside `rec` after it is dead
+constexpr int LQ_G = 0, LQ_GL = 34, LQ_T1 = 340, LQ_BT = 560, LQ_PXV = 912;   // G 10x34, T1 10x22, Bt 22x16, Pxv 10x22 (ends at 1132)
+static_assert(LQ_PXV + NJ * NX <= LIN_STRIDE, "aliased area overflow");
 
 __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -244,87 +249,86 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
   const int inst = (int)(w / N), k = (int)(w - (long long)inst * N);
   const double dt = a.dt;
   const Model& md = c_model;
-  const double* rec = a.lin + ((size_t)inst * N + k) * LIN_STRIDE;
+  const double* grec = a.lin + ((size_t)inst * N + k) * LIN_STRIDE;
   double* out = a.proj + ((size_t)inst * N + k) * PJ_STRIDE;
   const double* xk = (k == 0) ? a.x0 + (size_t)inst * NX : a.xt + ((size_t)inst * (N + 1) + k) * NX;
-  // ---- load
-  if (lane < NX) {
-    sh.x[lane] = xk[lane]; sh.u[lane] = a.ut[((size_t)inst * N + k) * NU + lane]; sh.xn[lane] = a.xt[((size_t)inst * (N + 1) + k + 1) * NX + lane];
-    sh.xref[lane] = a.x_ref[((size_t)inst * (N + 1) + k) * NX + lane]; sh.f1[lane] = rec[LIN_F1 + lane]; sh.f2[lane] = rec[LIN_F2 + lane];
+  // ---- asynchronous loads: record + node vectors
+  for (int i = 2 * lane; i < LIN_DVV + 12 * NJ; i += 64) cp_async16(sh.rec + i, grec + i);
+  if (lane < 11) {
+    cp_async16(sh.x + 2 * lane, xk + 2 * lane);
+    cp_async16(sh.u + 2 * lane, a.ut + ((size_t)inst * N + k) * NU + 2 * lane);
+    cp_async16(sh.xn + 2 * lane, a.xt + ((size_t)inst * (N + 1) + k + 1) * NX + 2 * lane);
+    cp_async16(sh.xref + 2 * lane, a.x_ref + ((size_t)inst * (N + 1) + k) * NX + 2 * lane);
+  } else if (lane >= 16 && lane < 28) {
+    cp_async16(sh.swing + 2 * (lane - 16), a.swing + ((size_t)inst * (N + 1) + k) * 24 + 2 * (lane - 16));
   }
-  if (lane < 24) sh.swing[lane] = a.swing[((size_t)inst * (N + 1) + k) * 24 + lane];
-  if (lane < 12) { sh.epos[lane] = rec[LIN_EPOS + lane]; sh.evel[lane] = rec[LIN_EVEL + lane]; }
-  for (int i = lane; i < 9 * NX; i += 32) { sh.A1c[i] = rec[LIN_A1 + i]; sh.A2c[i] = rec[LIN_A2 + i]; }
-  for (int i = lane; i < 36; i += 32) { sh.Bf1[i] = rec[LIN_BF1 + i]; sh.Bf2[i] = rec[LIN_BF2 + i]; }
-  for (int i = lane; i < 60; i += 32) { sh.Bv1[i] = rec[LIN_BV1 + i]; sh.Bv2[i] = rec[LIN_BV2 + i]; }
-  for (int i = lane; i < 12 * NDIR; i += 32) sh.dpq[i] = rec[LIN_DPQ + i];
-  for (int i = lane; i < 12 * NX; i += 32) sh.dvx[i] = rec[LIN_DVX + i];
-  for (int i = lane; i < 12 * NJ; i += 32) sh.dvv[i] = rec[LIN_DVV + i];
+  cp_async_commit();
   const int mode = a.mode[(size_t)inst * (N + 1) + k];
   bool fl[4]; int ns = 0;
   for (int c = 0; c < 4; ++c) { fl[c] = contact_flag(mode, c); ns += fl[c]; }
+  // constant parts that do not need the record
+  for (int idx = lane; idx < NJ * NJ; idx += 32) { const int i = idx / NJ, j = idx - i * NJ; sh.Rvv[idx] = md.R[(12 + i) * NU + 12 + j]; }
+  for (int idx = lane; idx < 144; idx += 32) { const int i = idx / 12, j = idx - i * 12; sh.RFF[idx] = (i == j) ? md.R[i * NU + i] : 0.0; }
+  for (int idx = lane; idx < NJ * NX; idx += 32) sh.Pv[idx] = 0.0;
+  cp_async_wait<0>();
   __syncwarp();
+  const double* A1c = sh.rec + LIN_A1; const double* A2c = sh.rec + LIN_A2;
+  const double* Bf1 = sh.rec + LIN_BF1; const double* Bf2 = sh.rec + LIN_BF2;
+  const double* Bv1 = sh.rec + LIN_BV1; const double* Bv2 = sh.rec + LIN_BV2;
+  const double* f1 = sh.rec + LIN_F1; const double* f2 = sh.rec + LIN_F2;
+  const double* epos = sh.rec + LIN_EPOS; const double* evel = sh.rec + LIN_EVEL;
+  const double* dpq = sh.rec + LIN_DPQ; const double* dvx = sh.rec + LIN_DVX; const double* dvv = sh.rec + LIN_DVV;
   // ---- RK2 sensitivities (S2) on the non-trivial rows 3..11
-  // Ad = I + dt/2 (A1 + A2 + dt A2 A1);  (A2 A1)[i][j] = sum_{k=3..11} A2c[i][k] A1c[k-3][j]
   if (lane < NX) {
     const int j = lane;
     double c1[9];
 #pragma unroll
-    for (int kk = 0; kk < 9; ++kk) c1[kk] = sh.A1c[kk * NX + j];
+    for (int kk = 0; kk < 9; ++kk) c1[kk] = A1c[kk * NX + j];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
       double s = 0.0;
 #pragma unroll
-      for (int kk = 0; kk < 9; ++kk) s = fma(sh.A2c[i * NX + 3 + kk], c1[kk], s);
-      sh.Ad[(3 + i) * NX + j] = 0.5 * dt * (c1[i] + sh.A2c[i * NX + j] + dt * s);
+      for (int kk = 0; kk < 9; ++kk) s = fma(A2c[i * NX + 3 + kk], c1[kk], s);
+      sh.Ad[(3 + i) * NX + j] = 0.5 * dt * (c1[i] + A2c[i * NX + j] + dt * s) + ((3 + i == j) ? 1.0 : 0.0);
     }
-    for (int i = 0; i < 3; ++i) sh.Ad[i * NX + j] = 0.0;
-    for (int i = 12; i < NX; ++i) sh.Ad[i * NX + j] = 0.0;
-  }
-  __syncwarp();
-  if (lane < NX) sh.Ad[lane * NX + lane] += 1.0;
-  // Bd force columns (rows 3..11): B1 rows 3..5 = Bf1; A2 B1 = A2c[:, 3:6] Bf1.  vj columns: B1 rows 6..11 = Bv1, rows 12..21 = I;
-  // A2 B1 = A2c[:, 6:12] Bv1 + A2c[:, 12:22]
-  if (lane < 12) {
-    const int j = lane;
-    const double b0 = sh.Bf1[j], b1 = sh.Bf1[12 + j], b2 = sh.Bf1[24 + j];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
+    for (int i = 0; i < 3; ++i) sh.Ad[i * NX + j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 12; i < NX; ++i) sh.Ad[i * NX + j] = (i == j) ? 1.0 : 0.0;
+    if (j < 12) {
       // B1 force column j = [e_a / m ; Bf1[:, j] ; 0]: (A2 B1)[i][j] = A2c[i][a] / m + A2c[i][3:6] Bf1[:, j]
-      const double s = sh.A2c[i * NX + 3] * b0 + sh.A2c[i * NX + 4] * b1 + sh.A2c[i * NX + 5] * b2 + sh.A2c[i * NX + (j % 3)] / md.total_mass;
-      const double base = (i < 3) ? (sh.Bf1[i * 12 + j] + sh.Bf2[i * 12 + j]) : 0.0;
-      sh.BdF[i * 12 + j] = 0.5 * dt * (base + dt * s);
-    }
-  } else if (lane >= 16 && lane < 16 + NJ) {
-    const int j = lane - 16;
-    double c1[6];
+      const double b0 = Bf1[j], b1 = Bf1[12 + j], b2 = Bf1[24 + j];
 #pragma unroll
-    for (int kk = 0; kk < 6; ++kk) c1[kk] = sh.Bv1[kk * NJ + j];
+      for (int i = 0; i < 9; ++i) {
+        const double s = A2c[i * NX + 3] * b0 + A2c[i * NX + 4] * b1 + A2c[i * NX + 5] * b2 + A2c[i * NX + (j % 3)] / md.total_mass;
+        const double base = (i < 3) ? (Bf1[i * 12 + j] + Bf2[i * 12 + j]) : 0.0;
+        sh.BdF[i * 12 + j] = 0.5 * dt * (base + dt * s);
+      }
+    } else {
+      const int jj = j - 12;
+      double cb[6];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      double s = sh.A2c[i * NX + 12 + j];
+      for (int kk = 0; kk < 6; ++kk) cb[kk] = Bv1[kk * NJ + jj];
 #pragma unroll
-      for (int kk = 0; kk < 6; ++kk) s = fma(sh.A2c[i * NX + 6 + kk], c1[kk], s);
-      const double base = (i >= 3) ? (sh.Bv1[(i - 3) * NJ + j] + sh.Bv2[(i - 3) * NJ + j]) : 0.0;
-      sh.Bdv[i * NJ + j] = 0.5 * dt * (base + dt * s);
+      for (int i = 0; i < 9; ++i) {
+        double s = A2c[i * NX + 12 + jj];
+#pragma unroll
+        for (int kk = 0; kk < 6; ++kk) s = fma(A2c[i * NX + 6 + kk], cb[kk], s);
+        const double base = (i >= 3) ? (Bv1[(i - 3) * NJ + jj] + Bv2[(i - 3) * NJ + jj]) : 0.0;
+        sh.Bdv[i * NJ + jj] = 0.5 * dt * (base + dt * s);
+      }
     }
   }
   double d2 = 0.0;
-  if (lane < NX) { const double bb = sh.x[lane] + 0.5 * dt * (sh.f1[lane] + sh.f2[lane]) - sh.xn[lane]; sh.b[lane] = bb; d2 = bb * bb; }
+  if (lane < NX) { const double bb = sh.x[lane] + 0.5 * dt * (f1[lane] + f2[lane]) - sh.xn[lane]; sh.b[lane] = bb; d2 = bb * bb; }
   d2 = warp_sum(d2);
-  __syncwarp();
   // ---- cost (M2, M6, M7, M8), scaled by dt at the end
   const double fz = ns > 0 ? md.total_mass * HB_GRAVITY / ns : 0.0;
   double cost = 0.0;
-  for (int idx = lane; idx < TS; idx += 32) sh.Q[idx] = 0.0;
-  for (int idx = lane; idx < NJ * NJ; idx += 32) { const int i = idx / NJ, j = idx - i * NJ; sh.Rvv[idx] = md.R[(12 + i) * NU + 12 + j]; }
-  for (int idx = lane; idx < 144; idx += 32) { const int i = idx / 12, j = idx - i * 12; sh.RFF[idx] = (i == j) ? md.R[i * NU + i] : 0.0; }
-  for (int idx = lane; idx < NJ * NX; idx += 32) sh.Pv[idx] = 0.0;
-  __syncwarp();
   if (lane < NX) {
     const double d = sh.x[lane] - sh.xref[lane];
     sh.q[lane] = md.Q[lane] * d;
-    sh.Q[lane * NX + lane] = md.Q[lane];
+    sh.Qd[lane] = md.Q[lane];
     cost += 0.5 * md.Q[lane] * d * d;
     double s = 0.0;
     if (lane < 12) { double dul = sh.u[lane]; if ((lane % 3) == 2 && fl[lane / 3]) dul -= fz; s = md.R[lane * NU + lane] * dul; cost += 0.5 * dul * s; }
@@ -332,44 +336,53 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     sh.r[lane] = s;
   }
   __syncwarp();
+  // all scalar penalties in ONE pass: lanes 0-9 joint position limits, 10-19 joint velocity limits, 20-23 normal-force limits
+  // (double sided), 24-27 friction cones of stance contacts (one sided)
   double shiftsum = 0.0;
-  if (lane < 10) {
-    const Pen p = double_sided(sh.x[12 + lane], md.joint_lower[lane], md.joint_upper[lane], HB_LIMIT_POS_MU, HB_LIMIT_POS_DELTA);
-    cost += p.v; sh.q[12 + lane] += p.d1; sh.Q[(12 + lane) * NX + 12 + lane] += p.d2;
-  } else if (lane < 20) {
-    const int j = lane - 10;
-    const Pen p = double_sided(sh.u[12 + j], -md.joint_vel_limit[j], md.joint_vel_limit[j], HB_LIMIT_VEL_MU, HB_LIMIT_VEL_DELTA);
-    cost += p.v; sh.r[12 + j] += p.d1; sh.Rvv[j * NJ + j] += p.d2;
-  } else if (lane < 24) {
-    const int c = lane - 20;
-    const Pen p = double_sided(sh.u[3 * c + 2], 0.0, HB_LIMIT_FORCE_MAX, HB_LIMIT_FORCE_MU, HB_LIMIT_FORCE_DELTA);
-    cost += p.v; sh.r[3 * c + 2] += p.d1; sh.RFF[(3 * c + 2) * 12 + 3 * c + 2] += p.d2;
-  }
-  __syncwarp();
-  if (lane >= 24 && lane < 28) {
-    const int c = lane - 24;
-    if (fl[c]) {
-      const double Fx = sh.u[3 * c], Fy = sh.u[3 * c + 1], Fz = sh.u[3 * c + 2];
-      const double t2 = Fx * Fx + Fy * Fy + HB_FRICTION_REGULARIZATION, tn = sqrt(t2), t32 = tn * t2;
-      const double h = HB_FRICTION_MU * Fz - tn;
-      const Pen p = relaxed_barrier(h, HB_FRICTION_BARRIER_MU, HB_FRICTION_BARRIER_DELTA);
-      cost += p.v;
+  {
+    double h = 1.0, lo = 0.0, hi = 2.0, pmu = 0.0, pdl = 1.0;
+    bool two = true, on = false;
+    double Fx = 0.0, Fy = 0.0, tn = 1.0, t2 = 1.0;
+    if (lane < 10) { h = sh.x[12 + lane]; lo = md.joint_lower[lane]; hi = md.joint_upper[lane]; pmu = HB_LIMIT_POS_MU; pdl = HB_LIMIT_POS_DELTA; on = true; }
+    else if (lane < 20) { const int j = lane - 10; h = sh.u[12 + j]; lo = -md.joint_vel_limit[j]; hi = md.joint_vel_limit[j]; pmu = HB_LIMIT_VEL_MU; pdl = HB_LIMIT_VEL_DELTA; on = true; }
+    else if (lane < 24) { const int c = lane - 20; h = sh.u[3 * c + 2]; lo = 0.0; hi = HB_LIMIT_FORCE_MAX; pmu = HB_LIMIT_FORCE_MU; pdl = HB_LIMIT_FORCE_DELTA; on = true; }
+    else if (lane < 28) {
+      const int c = lane - 24;
+      if (fl[c]) {
+        Fx = sh.u[3 * c]; Fy = sh.u[3 * c + 1];
+        t2 = Fx * Fx + Fy * Fy + HB_FRICTION_REGULARIZATION; tn = sqrt(t2);
+        h = HB_FRICTION_MU * sh.u[3 * c + 2] - tn; lo = 0.0; pmu = HB_FRICTION_BARRIER_MU; pdl = HB_FRICTION_BARRIER_DELTA; two = false; on = true;
+      }
+    }
+    const Pen pa = relaxed_barrier(h - lo, pmu, pdl);
+    const Pen pb = relaxed_barrier(two ? hi - h : 1.0, two ? pmu : 0.0, pdl);
+    const double pv = pa.v + pb.v, p1 = pa.d1 - pb.d1, p2 = pa.d2 + pb.d2;
+    __syncwarp();
+    if (on) {
+      cost += pv;
+      if (lane < 10) { sh.q[12 + lane] += p1; sh.Qd[12 + lane] += p2; }
+      else if (lane < 20) { const int j = lane - 10; sh.r[12 + j] += p1; sh.Rvv[j * NJ + j] += p2; }
+      else if (lane < 24) { const int c = lane - 20; sh.r[3 * c + 2] += p1; sh.RFF[(3 * c + 2) * 12 + 3 * c + 2] += p2; }
+    }
+    __syncwarp();
+    if (on && lane >= 24) {
+      const int c = lane - 24;
+      const double t32 = tn * t2;
       const double gr[3] = {-Fx / tn, -Fy / tn, HB_FRICTION_MU};
       const double Hh[9] = {-(Fy * Fy + HB_FRICTION_REGULARIZATION) / t32, Fx * Fy / t32, 0.0, Fx * Fy / t32,
                             -(Fx * Fx + HB_FRICTION_REGULARIZATION) / t32, 0.0, 0.0, 0.0, 0.0};
       for (int i = 0; i < 3; ++i) {
-        sh.r[3 * c + i] += p.d1 * gr[i];
-        for (int j = 0; j < 3; ++j) sh.RFF[(3 * c + i) * 12 + 3 * c + j] += p.d2 * gr[i] * gr[j] + p.d1 * Hh[3 * i + j];
+        sh.r[3 * c + i] += p1 * gr[i];
+        for (int j = 0; j < 3; ++j) sh.RFF[(3 * c + i) * 12 + 3 * c + j] += p2 * gr[i] * gr[j] + p1 * Hh[3 * i + j];
       }
-      shiftsum = -p.d1 * HB_FRICTION_HESSIAN_SHIFT;
+      shiftsum = -p1 * HB_FRICTION_HESSIAN_SHIFT;
     }
   }
   shiftsum = warp_sum(shiftsum);
   __syncwarp();
-  if (lane < NX) sh.Q[lane * NX + lane] += shiftsum;
+  if (lane < NX) sh.Qd[lane] += shiftsum;
   if (lane < 12) sh.RFF[lane * 12 + lane] += shiftsum;
   else if (lane >= 16 && lane < 16 + NJ) sh.Rvv[(lane - 16) * NJ + lane - 16] += shiftsum;
-  __syncwarp();
   // xy swing soft constraint: gradients gx (22) / gv (10, vj columns only)
   int npair = 0;
   for (int c = 0; c < 4; ++c) {
@@ -379,33 +392,44 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
       if (lane < NX) {
         double px = 0.0;
         if (lane >= 6 && lane < 9) px = (lane - 6 == ax) ? 1.0 : 0.0;
-        else if (lane >= 9) px = sh.dpq[row * NDIR + lane - 9];
-        sh.gx[npair * NX + lane] = sh.dvx[row * NX + lane] + HB_XY_POSITION_GAIN * px;
-        if (lane < NJ) sh.gv[npair * NJ + lane] = sh.dvv[row * NJ + lane];
+        else if (lane >= 9) px = dpq[row * NDIR + lane - 9];
+        sh.gx[npair * NX + lane] = dvx[row * NX + lane] + HB_XY_POSITION_GAIN * px;
+        if (lane < NJ) sh.gv[npair * NJ + lane] = dvv[row * NJ + lane];
       }
-      if (lane == 0) sh.gh[npair] = sh.evel[row] - sh.swing[6 * c + 3 + ax] + HB_XY_POSITION_GAIN * (sh.epos[row] - sh.swing[6 * c + ax]);
+      if (lane == 0) sh.gh[npair] = evel[row] - sh.swing[6 * c + 3 + ax] + HB_XY_POSITION_GAIN * (epos[row] - sh.swing[6 * c + ax]);
       ++npair;
     }
   }
+  for (int idx = npair * NX + lane; idx < 8 * NX; idx += 32) sh.gx[idx] = 0.0;   // unused pairs must be exact zeros (they enter Qt with weight 0)
   __syncwarp();
-  for (int p = 0; p < npair; ++p) {
-    const double w = HB_SOFT_SWING_WEIGHT, h = sh.gh[p];
-    const double* gx = sh.gx + p * NX; const double* gv = sh.gv + p * NJ;
-    if (lane == 0) cost += 0.5 * w * h * h;
+  if (npair > 0) {
+    const double w = HB_SOFT_SWING_WEIGHT;
     if (lane < NX) {
-      const double gxj = gx[lane];
-      sh.q[lane] += w * h * gxj;
+      double qa = 0.0;
+      double pvc[NJ];
 #pragma unroll
-      for (int i = 0; i < NX; ++i) sh.Q[i * NX + lane] += w * gx[i] * gxj;
+      for (int i = 0; i < NJ; ++i) pvc[i] = 0.0;
+      for (int p = 0; p < npair; ++p) {
+        const double h = sh.gh[p], gxj = sh.gx[p * NX + lane];
+        qa += w * h * gxj;
 #pragma unroll
-      for (int i = 0; i < NJ; ++i) sh.Pv[i * NX + lane] += w * gv[i] * gxj;
+        for (int i = 0; i < NJ; ++i) pvc[i] = fma(w * sh.gv[p * NJ + i], gxj, pvc[i]);
+      }
+      sh.q[lane] += qa;
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) sh.Pv[i * NX + lane] = pvc[i];
       if (lane < NJ) {
-        sh.r[12 + lane] += w * h * gv[lane];
+        double ra = 0.0;
+        for (int p = 0; p < npair; ++p) {
+          const double gvj = sh.gv[p * NJ + lane];
+          ra += w * sh.gh[p] * gvj;
 #pragma unroll
-        for (int i = 0; i < NJ; ++i) sh.Rvv[i * NJ + lane] += w * gv[i] * gv[lane];
+          for (int i = 0; i < NJ; ++i) sh.Rvv[i * NJ + lane] += w * sh.gv[p * NJ + i] * gvj;
+        }
+        sh.r[12 + lane] += ra;
       }
     }
-    __syncwarp();
+    if (lane < npair) cost += 0.5 * w * sh.gh[lane] * sh.gh[lane];
   }
   cost = warp_sum(cost);
   // ---- contact-velocity equality rows (M4, M5); swing forces handled separately (M3)
@@ -418,66 +442,70 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
   double e2 = 0.0;
   if (lane < NX) {
     for (int rr = 0; rr < mr; ++rr) {
-      const int row = 3 * sh.rowc[rr] + sh.rowa[rr], t = sh.rowt[rr];
-      const double gain = (t == 0) ? ((sh.rowa[rr] == 2) ? HB_ZEROVEL_Z_GAIN : 0.0) : HB_POSITION_ERROR_GAIN;
+      const int ra = sh.rowa[rr], row = 3 * sh.rowc[rr] + ra, t = sh.rowt[rr];
+      const double gain = (t == 0) ? ((ra == 2) ? HB_ZEROVEL_Z_GAIN : 0.0) : HB_POSITION_ERROR_GAIN;
       double px = 0.0;
-      if (lane >= 6 && lane < 9) px = (lane - 6 == sh.rowa[rr]) ? 1.0 : 0.0;
-      else if (lane >= 9) px = sh.dpq[row * NDIR + lane - 9];
-      sh.Cv[rr * NX + lane] = sh.dvx[row * NX + lane] + gain * px;
-      if (lane < NJ) sh.Dv[rr * NJ + lane] = sh.dvv[row * NJ + lane];
+      if (lane >= 6 && lane < 9) px = (lane - 6 == ra) ? 1.0 : 0.0;
+      else if (lane >= 9) px = dpq[row * NDIR + lane - 9];
+      sh.Cv[rr * NX + lane] = dvx[row * NX + lane] + gain * px;
+      if (lane < NJ) sh.Dv[rr * NJ + lane] = dvv[row * NJ + lane];
     }
   }
   if (lane < mr) {
     const int c = sh.rowc[lane], ax = sh.rowa[lane], row = 3 * c + ax;
     double evv;
-    if (sh.rowt[lane] == 0) evv = sh.evel[row] + (ax == 2 ? HB_ZEROVEL_Z_GAIN * sh.epos[row] + HB_ZEROVEL_Z_OFFSET : 0.0);
-    else evv = sh.evel[row] - sh.swing[6 * c + 5] + HB_POSITION_ERROR_GAIN * (sh.epos[row] - sh.swing[6 * c + 2]);
+    if (sh.rowt[lane] == 0) evv = evel[row] + (ax == 2 ? HB_ZEROVEL_Z_GAIN * epos[row] + HB_ZEROVEL_Z_OFFSET : 0.0);
+    else evv = evel[row] - sh.swing[6 * c + 5] + HB_POSITION_ERROR_GAIN * (epos[row] - sh.swing[6 * c + 2]);
     sh.ev[lane] = evv;
     e2 = evv * evv;
   }
   if (lane >= 16 && lane < 28) { const int j = lane - 16; if (!fl[j / 3]) e2 += sh.u[j] * sh.u[j]; }
   e2 = warp_sum(e2);
   __syncwarp();
-  // ---- least-squares projection on vj: G = Dv'Dv, rhs = -Dv'[Cv | ev]  (10 x 33, ld 36)
-  constexpr int GW = NJ + NX + 1, GL = 36;
-  for (int j = lane; j < GW; j += 32) {
-    for (int i = 0; i < NJ; ++i) {
-      double s = 0.0;
-      if (j < NJ) { for (int r = 0; r < mr; ++r) s += sh.Dv[r * NJ + i] * sh.Dv[r * NJ + j]; }
-      else if (j < NJ + NX) { for (int r = 0; r < mr; ++r) s -= sh.Dv[r * NJ + i] * sh.Cv[r * NX + j - NJ]; }
-      else { for (int r = 0; r < mr; ++r) s -= sh.Dv[r * NJ + i] * sh.ev[r]; }
-      sh.G[i * GL + j] = s;
-    }
+  // ================= the record is dead from here on: its storage holds G, T1, Bt, Pxv =================
+  double* G = sh.rec + LQ_G; double* T1 = sh.rec + LQ_T1; double* Bt = sh.rec + LQ_BT; double* Pxv = sh.rec + LQ_PXV;
+  // ---- least-squares projection on vj: G = Dv'Dv, rhs = -Dv'[Cv | ev]  (10 x 33, ld 34), entries spread over all lanes
+  constexpr int GW = NJ + NX + 1, GL = LQ_GL;
+  for (int idx = lane; idx < NJ * GW; idx += 32) {
+    const int i = idx / GW, j = idx - i * GW;
+    double s = 0.0;
+    if (j < NJ) { for (int r = 0; r < mr; ++r) s = fma(sh.Dv[r * NJ + i], sh.Dv[r * NJ + j], s); }
+    else if (j < NJ + NX) { for (int r = 0; r < mr; ++r) s = fma(-sh.Dv[r * NJ + i], sh.Cv[r * NX + j - NJ], s); }
+    else { for (int r = 0; r < mr; ++r) s = fma(-sh.Dv[r * NJ + i], sh.ev[r], s); }
+    G[i * GL + j] = s;
   }
   if (lane < NJ) sh.piv[lane] = 0;
   __syncwarp();
-  double dmax = lane < NJ ? sh.G[lane * GL + lane] : 0.0;
+  double dmax = lane < NJ ? G[lane * GL + lane] : 0.0;
   if (ns < 4) dmax = fmax(dmax, 1.0);     // the swing-force selector rows of D have unit diagonal in D'D
   dmax = warp_max(dmax);
   const double tol = 1e-9 * fmax(dmax, 1e-300);
   for (int step = 0; step < NJ; ++step) {
-    double dv = (lane < NJ && !sh.piv[lane]) ? sh.G[lane * GL + lane] : -1.0;
+    double dv = (lane < NJ && !sh.piv[lane]) ? G[lane * GL + lane] : -1.0;
     int pi = lane;
-    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {      // candidates live in lanes 0..9: a 16-lane butterfly suffices
       const double ov = __shfl_xor_sync(HB_FULL_MASK, dv, o);
       const int oi = __shfl_xor_sync(HB_FULL_MASK, pi, o);
       if (ov > dv || (ov == dv && oi < pi)) { dv = ov; pi = oi; }
     }
+    dv = __shfl_sync(HB_FULL_MASK, dv, 0); pi = __shfl_sync(HB_FULL_MASK, pi, 0);
     if (!(dv > tol)) break;
     const int p = pi;
     const double inv = 1.0 / dv;
-    __syncwarp();
-    for (int j = lane; j < GW; j += 32) sh.G[p * GL + j] *= inv;
+    for (int j = lane; j < GW; j += 32) G[p * GL + j] *= inv;
     if (lane == 0) sh.piv[p] = 1;
     __syncwarp();
-    for (int j = lane; j < GW; j += 32) {
-      if (j == p) continue;
-      const double gp = sh.G[p * GL + j];
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) if (i != p) sh.G[i * GL + j] -= sh.G[i * GL + p] * gp;
-    }
+    const double colv = (lane < NJ) ? G[lane * GL + p] : 0.0;   // column p before elimination, one entry per lane
     __syncwarp();
-    if (lane < NJ && lane != p) sh.G[lane * GL + p] = 0.0;
+#pragma unroll 1
+    for (int t = 0; t < (NJ * GW + 31) / 32; ++t) {
+      const int idx = lane + 32 * t;
+      const bool valid = idx < NJ * GW;
+      const int i = valid ? idx / GW : 0, j = valid ? idx - i * GW : 0;
+      const double ci = __shfl_sync(HB_FULL_MASK, colv, i);
+      if (valid && i != p) G[i * GL + j] -= ci * G[p * GL + j];
+    }
     __syncwarp();
   }
   int nv = 0;
@@ -488,26 +516,29 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
   if (nv > NVMAX) { nv = NVMAX; overflow = true; }       // degenerate pose (velocity rows lost rank): flagged, instance reported as failed
   if (nf + nv > NTMAX) { nv = NTMAX - nf; overflow = true; }
   const int nt = nf + nv;
+  const int ntp = ntp_of(nt);
   __syncwarp();
   if (lane < NX) {
-    for (int i = 0; i < NJ; ++i) sh.Pxv[i * NX + lane] = sh.piv[i] ? sh.G[i * GL + NJ + lane] : 0.0;
-    if (lane < NJ) sh.pev[lane] = sh.piv[lane] ? sh.G[lane * GL + NJ + NX] : 0.0;
-    if (lane < nv) { const int fc = sh.freev[lane]; for (int i = 0; i < NJ; ++i) sh.Nv[i * 8 + lane] = sh.piv[i] ? -sh.G[i * GL + fc] : ((i == fc) ? 1.0 : 0.0); }
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) Pxv[i * NX + lane] = sh.piv[i] ? G[i * GL + NJ + lane] : 0.0;
+    if (lane < NJ) sh.pev[lane] = sh.piv[lane] ? G[lane * GL + NJ + NX] : 0.0;
+    if (lane < nv) { const int fc = sh.freev[lane]; for (int i = 0; i < NJ; ++i) sh.Nv[i * NVMAX + lane] = sh.piv[i] ? -G[i * GL + fc] : ((i == fc) ? 1.0 : 0.0); }
   }
+  for (int idx = lane; idx < NX * NTMAX; idx += 32) Bt[idx] = 0.0;
   __syncwarp();
   // ---- projected model (cost scaled by dt)
-  // At = Ad + Bd_v Pxv : rows 3..11 += Bdv Pxv ; rows 12..21 += dt Pxv
   if (lane < NX) {
     const int j = lane;
     double pc[NJ];
 #pragma unroll
-    for (int kk = 0; kk < NJ; ++kk) pc[kk] = sh.Pxv[kk * NX + j];
+    for (int kk = 0; kk < NJ; ++kk) pc[kk] = Pxv[kk * NX + j];
+    // At = Ad + Bd_v Pxv : rows 3..11 += Bdv Pxv ; rows 12..21 += dt Pxv
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-      double s = 0.0;
+      double s = sh.Ad[(3 + i) * NX + j];
 #pragma unroll
       for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Bdv[i * NJ + kk], pc[kk], s);
-      sh.Ad[(3 + i) * NX + j] += s;
+      sh.Ad[(3 + i) * NX + j] = s;
     }
 #pragma unroll
     for (int kk = 0; kk < NJ; ++kk) sh.Ad[(12 + kk) * NX + j] += dt * pc[kk];
@@ -517,26 +548,33 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
       double s = sh.Pv[i * NX + j];
 #pragma unroll
       for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Rvv[i * NJ + kk], pc[kk], s);
-      sh.T1[i * NX + j] = s;
+      T1[i * NX + j] = s;
     }
   }
   if (lane < NJ) {
     double s = sh.r[12 + lane];
-    for (int kk = 0; kk < NJ; ++kk) s += sh.Rvv[lane * NJ + kk] * sh.pev[kk];
+#pragma unroll
+    for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Rvv[lane * NJ + kk], sh.pev[kk], s);
     sh.rRpe[lane] = s;
   }
   __syncwarp();
-  // Qt = Q + Pxv' PRPx_v + Pv' Pxv ; qt = q + Pxv' rRpe + Pv' pev
+  // Qt = diag(Qd) + sum_p w gx_p gx_p' + Pxv' PRPx_v + Pv' Pxv ; qt = q + Pxv' rRpe + Pv' pev   (column j by lane j)
   if (lane < NX) {
     const int j = lane;
-    double tc[NJ], pc[NJ];
+    double tc[NJ], pc[NJ], gj[8];
 #pragma unroll
-    for (int kk = 0; kk < NJ; ++kk) { tc[kk] = sh.T1[kk * NX + j]; pc[kk] = sh.Pxv[kk * NX + j]; }
+    for (int kk = 0; kk < NJ; ++kk) { tc[kk] = T1[kk * NX + j]; pc[kk] = Pxv[kk * NX + j]; }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) gj[p] = (p < npair) ? HB_SOFT_SWING_WEIGHT * sh.gx[p * NX + j] : 0.0;
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      double s = sh.Q[i * NX + j];
+      double s = (i == j) ? sh.Qd[i] : 0.0;
 #pragma unroll
-      for (int kk = 0; kk < NJ; ++kk) { s = fma(sh.Pxv[kk * NX + i], tc[kk], s); s = fma(sh.Pv[kk * NX + i], pc[kk], s); }
+      for (int kk = 0; kk < NJ; ++kk) { s = fma(Pxv[kk * NX + i], tc[kk], s); s = fma(sh.Pv[kk * NX + i], pc[kk], s); }
+      if (npair > 0) {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) s = fma(sh.gx[p * NX + i], gj[p], s);
+      }
       out[PJ_QT + i * NX + j] = dt * s;
     }
     double s = sh.q[j];
@@ -544,25 +582,19 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     for (int kk = 0; kk < NJ; ++kk) s += pc[kk] * sh.rRpe[kk] + sh.Pv[kk * NX + j] * sh.pev[kk];
     out[PJ_QV + j] = dt * s;
   }
-  // Bt (22 x nt, ld NTMAX): stance-force columns then null-space columns; padded columns are zero
-  const int ntp = ntp_of(nt);
-  for (int idx = lane; idx < NX * NTMAX; idx += 32) sh.Bt[idx] = 0.0;
-  __syncwarp();
+  // Bt (22 x nt, ld NTMAX): stance-force columns then null-space columns; padded columns stay zero
   if (lane < nt) {
     const int c = lane;
     if (c < nf) {
       const int j = sh.stidx[c];
-      for (int i = 0; i < NX; ++i) {
-        double v = 0.0;
-        if (i < 3) v = (i == (j % 3)) ? dt / md.total_mass : 0.0;
-        else if (i < 12) v = sh.BdF[(i - 3) * 12 + j];
-        sh.Bt[i * NTMAX + c] = v;
-      }
+      Bt[(j % 3) * NTMAX + c] = dt / md.total_mass;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Bt[(3 + i) * NTMAX + c] = sh.BdF[i * 12 + j];
     } else {
       const int cc = c - nf;
-      for (int i = 0; i < 3; ++i) sh.Bt[i * NTMAX + c] = 0.0;
-      for (int i = 0; i < 9; ++i) { double s = 0.0; for (int kk = 0; kk < NJ; ++kk) s += sh.Bdv[i * NJ + kk] * sh.Nv[kk * 8 + cc]; sh.Bt[(3 + i) * NTMAX + c] = s; }
-      for (int kk = 0; kk < NJ; ++kk) sh.Bt[(12 + kk) * NTMAX + c] = dt * sh.Nv[kk * 8 + cc];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { double s = 0.0; for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Bdv[i * NJ + kk], sh.Nv[kk * NVMAX + cc], s); Bt[(3 + i) * NTMAX + c] = s; }
+      for (int kk = 0; kk < NJ; ++kk) Bt[(12 + kk) * NTMAX + c] = dt * sh.Nv[kk * NVMAX + cc];
     }
   }
   // bt = b + Bd_v pev - Bd_F[:, swing] F_swing
@@ -570,14 +602,14 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     const int i = lane;
     double s = sh.b[i];
     if (i >= 3 && i < 12) {
-      for (int kk = 0; kk < NJ; ++kk) s += sh.Bdv[(i - 3) * NJ + kk] * sh.pev[kk];
+      for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Bdv[(i - 3) * NJ + kk], sh.pev[kk], s);
       for (int j = 0; j < 12; ++j) if (!fl[j / 3]) s -= sh.BdF[(i - 3) * 12 + j] * sh.u[j];
     } else if (i >= 12) s += dt * sh.pev[i - 12];
     else { for (int c = 0; c < 4; ++c) if (!fl[c]) s -= dt / md.total_mass * sh.u[3 * c + i]; }
     sh.bt[i] = s;
   }
   __syncwarp();
-  // Rt (nt x nt), Pt (nt x 22), rt (nt)
+  // Rt (ntp x ntp), Pt (ntp x 22), rt (ntp); RN = Rvv Nv computed on the fly per entry
   for (int idx = lane; idx < ntp * ntp; idx += 32) {
     const int i = idx / ntp, j = idx - i * ntp;
     double s = 0.0;
@@ -585,14 +617,14 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     else if (i < nf && j < nf) s = sh.RFF[sh.stidx[i] * 12 + sh.stidx[j]];
     else if (i >= nf && j >= nf) {
       const int ci = i - nf, cj = j - nf;
-      for (int p = 0; p < NJ; ++p) { double t = 0.0; for (int qq = 0; qq < NJ; ++qq) t += sh.Rvv[p * NJ + qq] * sh.Nv[qq * 8 + cj]; s += sh.Nv[p * 8 + ci] * t; }
+      for (int p = 0; p < NJ; ++p) { double t = 0.0; for (int qq = 0; qq < NJ; ++qq) t = fma(sh.Rvv[p * NJ + qq], sh.Nv[qq * NVMAX + cj], t); s = fma(sh.Nv[p * NVMAX + ci], t, s); }
     }
     out[PJ_RT + i * NTMAX + j] = dt * s;
   }
   if (lane < NX) {
     for (int c = 0; c < ntp; ++c) {
       double s = 0.0;
-      if (c >= nf && c < nt) { const int cc = c - nf; for (int kk = 0; kk < NJ; ++kk) s += sh.Nv[kk * 8 + cc] * sh.T1[kk * NX + lane]; }
+      if (c >= nf && c < nt) { const int cc = c - nf; for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Nv[kk * NVMAX + cc], T1[kk * NX + lane], s); }
       out[PJ_PT + c * NX + lane] = dt * s;
     }
   }
@@ -600,14 +632,14 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     double s;
     if (lane >= nt) s = 0.0;
     else if (lane < nf) s = sh.r[sh.stidx[lane]];
-    else { s = 0.0; const int cc = lane - nf; for (int kk = 0; kk < NJ; ++kk) s += sh.Nv[kk * 8 + cc] * sh.rRpe[kk]; }
+    else { s = 0.0; const int cc = lane - nf; for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Nv[kk * NVMAX + cc], sh.rRpe[kk], s); }
     out[PJ_RV + lane] = dt * s;
   }
   // ---- write the rest of the record
   for (int idx = lane; idx < TS; idx += 32) out[PJ_AT + idx] = sh.Ad[idx];
-  for (int idx = lane; idx < NX * NTMAX; idx += 32) out[PJ_BT + idx] = sh.Bt[idx];
+  for (int idx = lane; idx < NX * NTMAX; idx += 32) out[PJ_BT + idx] = Bt[idx];
   if (lane < NX) out[PJ_BTV + lane] = sh.bt[lane];
-  for (int idx = lane; idx < NJ * NX; idx += 32) out[PJ_PXV + idx] = sh.Pxv[idx];
+  for (int idx = lane; idx < NJ * NX; idx += 32) out[PJ_PXV + idx] = Pxv[idx];
   for (int idx = lane; idx < NJ * NVMAX; idx += 32) { const int c = idx % NVMAX; out[PJ_NV + idx] = (c < nv) ? sh.Nv[idx] : 0.0; }
   if (lane < NJ) out[PJ_PEV + lane] = sh.pev[lane];
   if (lane == 0) { out[PJ_META] = nt; out[PJ_META + 1] = nf; out[PJ_META + 2] = nv; out[PJ_META + 3] = cost; out[PJ_META + 4] = d2; out[PJ_META + 5] = e2; out[PJ_META + 6] = overflow ? 1.0 : 0.0; }
@@ -778,13 +810,6 @@ struct Fw2Shared {
   FwNode nd[2];
   double dx[NX], dxn[NX], w[NTMAX];
 };
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
 
 __device__ __forceinline__ void fw_prefetch(FwNode& n, const double* __restrict__ rec, const double* __restrict__ rk, const double* __restrict__ uk, int lane) {
   auto copy = [&](double* dst, const double* src, int ndbl) { for (int i = 2 * lane; i < ndbl; i += 64) cp_async16(dst + i, src + i); };
