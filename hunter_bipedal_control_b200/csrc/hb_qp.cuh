@@ -25,7 +25,7 @@ struct QpWorkspace {
   double *g, *x, *rd, *dx, *t1, *t2;
   double *beq, *y, *rp, *dy, *t3;
   double *f, *s, *z, *rs, *ds, *dz, *rc, *sgn;
-  int *in_row, *in_c0, *in_c1, *eq_row;
+  int *in_row, *in_c0, *in_c1, *in_pair, *eq_row;   // in_pair: partner entry of a two-sided row (-1 none, -2 merged into its partner)
   int ldn, ldv, lds;
   int me_cap, mi_cap;   // capacity of the equality / one-sided inequality lists
 };
@@ -45,7 +45,7 @@ __host__ __device__ inline size_t qp_workspace_doubles(int n, int me_cap = QP_MA
   d += 6 * (size_t)n;              // g x rd dx t1 t2
   d += 5 * (size_t)me_cap;         // beq y rp dy t3
   d += 8 * (size_t)mi_cap;         // f s z rs ds dz rc sgn
-  d += (3 * (size_t)mi_cap + me_cap + 1) / 2 + 1;  // int arrays
+  d += (4 * (size_t)mi_cap + me_cap + 1) / 2 + 1;  // int arrays
   return d;
 }
 
@@ -65,7 +65,7 @@ __device__ inline void qp_carve(double* base, int n, QpWorkspace& w, int me_cap 
   w.f = p; p += mi_cap; w.s = p; p += mi_cap; w.z = p; p += mi_cap; w.rs = p; p += mi_cap;
   w.ds = p; p += mi_cap; w.dz = p; p += mi_cap; w.rc = p; p += mi_cap; w.sgn = p; p += mi_cap;
   int* ip = reinterpret_cast<int*>(p);
-  w.in_row = ip; ip += mi_cap; w.in_c0 = ip; ip += mi_cap; w.in_c1 = ip; ip += mi_cap; w.eq_row = ip;
+  w.in_row = ip; ip += mi_cap; w.in_c0 = ip; ip += mi_cap; w.in_c1 = ip; ip += mi_cap; w.in_pair = ip; ip += mi_cap; w.eq_row = ip;
 }
 
 // In-place Cholesky M = L L' (lower triangle) followed by Li = L^-1, stored transposed in the strict upper triangle
@@ -170,9 +170,10 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
     const unsigned bdn = __ballot_sync(HB_FULL_MASK, dn);
     const unsigned below = (1u << lane) - 1u;
     if (is_eq) { const int e = me + __popc(beq & below); if (e < w.me_cap) { w.eq_row[e] = r; w.beq[e] = hi; } }
-    if (up) { const int e = mi + __popc(bup & below); if (e < w.mi_cap) { w.in_row[e] = r; w.in_c0[e] = c0; w.in_c1[e] = c1; w.sgn[e] = 1.0; w.f[e] = hi; } }
     const int mi2 = mi + __popc(bup);
-    if (dn) { const int e = mi2 + __popc(bdn & below); if (e < w.mi_cap) { w.in_row[e] = r; w.in_c0[e] = c0; w.in_c1[e] = c1; w.sgn[e] = -1.0; w.f[e] = -lo; } }
+    const int e_up = mi + __popc(bup & below), e_dn = mi2 + __popc(bdn & below);
+    if (up && e_up < w.mi_cap) { w.in_row[e_up] = r; w.in_c0[e_up] = c0; w.in_c1[e_up] = c1; w.sgn[e_up] = 1.0; w.f[e_up] = hi; w.in_pair[e_up] = (dn && e_dn < w.mi_cap) ? e_dn : -1; }
+    if (dn && e_dn < w.mi_cap) { w.in_row[e_dn] = r; w.in_c0[e_dn] = c0; w.in_c1[e_dn] = c1; w.sgn[e_dn] = -1.0; w.f[e_dn] = -lo; w.in_pair[e_dn] = up ? -2 : -1; }
     me += __popc(beq);
     mi = mi2 + __popc(bdn);
   }
@@ -234,13 +235,18 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
     // ---------------- K = H + rho I + D' W D
     for (int idx = lane; idx < n * ldn; idx += 32) { const int i = idx / ldn, c = idx - i * ldn; w.K[idx] = w.H[idx] + ((i == c) ? rho : 0.0); }
     __syncwarp();
+    // lower triangle only; a two-sided row contributes once with the sum of its two weights; rows of the span are swept
+    // uniformly and lanes own the columns c <= i (no integer division on the hot path)
     for (int j = 0; j < mi; ++j) {
-      const int c0 = w.in_c0[j], L = w.in_c1[j] - c0;
-      const double wj = w.z[j] / w.s[j];
-      const double* a = A + (size_t)w.in_row[j] * n + c0;
-      for (int idx = lane; idx < L * L; idx += 32) {
-        const int i = idx / L, c = idx - i * L;
-        w.K[(c0 + i) * ldn + c0 + c] += wj * a[i] * a[c];
+      const int pr = w.in_pair[j];
+      if (pr == -2) continue;
+      const int c0 = w.in_c0[j], c1 = w.in_c1[j];
+      double wj = w.z[j] / w.s[j];
+      if (pr >= 0) wj += w.z[pr] / w.s[pr];
+      const double* a = A + (size_t)w.in_row[j] * n;
+      for (int i = c0; i < c1; ++i) {
+        const double ai = wj * a[i];
+        for (int c = c0 + lane; c <= i; c += 32) w.K[i * ldn + c] += ai * a[c];
       }
       __syncwarp();
     }

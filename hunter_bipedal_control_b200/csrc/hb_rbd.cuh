@@ -114,57 +114,132 @@ struct KinOut {
   T cvel[12];  // contact velocities J_c(q) v
 };
 
+// R <- R * Rot(axis) given the sine / cosine of the joint angle; returns the world joint axis in a[].
+template <class T> __device__ __forceinline__ void joint_rotate_sc(T* R, int code, T s, const T& c, T* a) {
+  const int ax = code < 0 ? -code : code;
+  if (code < 0) s = -s;
+  const double sg = code < 0 ? -1.0 : 1.0;
+  if (ax == 1) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      a[r] = R[3 * r] * sg;
+      const T c1 = R[3 * r + 1], c2 = R[3 * r + 2];
+      R[3 * r + 1] = c * c1 + s * c2; R[3 * r + 2] = c * c2 - s * c1;
+    }
+  } else if (ax == 2) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      a[r] = R[3 * r + 1] * sg;
+      const T c0 = R[3 * r], c2 = R[3 * r + 2];
+      R[3 * r] = c * c0 - s * c2; R[3 * r + 2] = s * c0 + c * c2;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      a[r] = R[3 * r + 2] * sg;
+      const T c0 = R[3 * r], c1 = R[3 * r + 1];
+      R[3 * r] = c * c0 + s * c1; R[3 * r + 1] = c * c1 - s * c0;
+    }
+  }
+}
+
 // One sweep over the tree: positions, velocities, CoM and centroidal momentum for generalised (q, v).
-template <class T>
-__device__ void kin_pass(const T* q, const T* v, KinOut<T>& o) {
+// Functor form (no runtime-indexed local arrays): qf(i), vf(i) return coordinate / velocity i; scf(k, s, c) returns the sine and
+// cosine of angle k (0..2 = yaw, pitch, roll; 3..12 = joints), so that callers can share one sincos evaluation per configuration;
+// of.h(r,x), of.com(r,x), of.cpos(i,x), of.cvel(i,x) receive the results.
+template <class T, class QF, class VF, class SCF, class OF>
+__device__ __forceinline__ void kin_pass_f(QF qf, VF vf, SCF scf, OF of) {
   const Model& md = c_model;
   T R0[9], ax0[9];
-  base_frame(q, R0, ax0);
+  {
+    T sz, cz, sy, cy, sx, cx;
+    scf(0, sz, cz); scf(1, sy, cy); scf(2, sx, cx);
+    R0[0] = cz * cy; R0[1] = cz * sy * sx - sz * cx; R0[2] = cz * sy * cx + sz * sx;
+    R0[3] = sz * cy; R0[4] = sz * sy * sx + cz * cx; R0[5] = sz * sy * cx - cz * sx;
+    R0[6] = -sy;     R0[7] = cy * sx;                R0[8] = cy * cx;
+    ax0[0] = T(0.0); ax0[1] = T(0.0); ax0[2] = T(1.0);
+    ax0[3] = -sz; ax0[4] = cz; ax0[5] = T(0.0);
+    ax0[6] = cz * cy; ax0[7] = sz * cy; ax0[8] = -sy;
+  }
   T w0[3], P[3], Lo[3], mc[3];
-  for (int i = 0; i < 3; ++i) w0[i] = ax0[i] * v[3] + ax0[3 + i] * v[4] + ax0[6 + i] * v[5];
+  {
+    const T v3 = vf(3), v4 = vf(4), v5 = vf(5);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w0[i] = ax0[i] * v3 + ax0[3 + i] * v4 + ax0[6 + i] * v5;
+  }
+#pragma unroll
   for (int i = 0; i < 3; ++i) { P[i] = T(0.0); Lo[i] = T(0.0); mc[i] = T(0.0); }
   auto add_body = [&](int b, const T* R, const T* p, const T* w, const T* vl) {
     T r[3], wxr[3], vc[3], cw[3], l[3], wl[3], Iwl[3], Iw[3];
     rot_const(R, &md.com[3 * b], r);
     cross(w, r, wxr);
     const double mb = md.mass[b];
+#pragma unroll
     for (int i = 0; i < 3; ++i) { vc[i] = (vl[i] + wxr[i]) * mb; cw[i] = p[i] + r[i]; }
     cross(cw, vc, l);
     rotT(R, w, wl);
     const double* I = &md.inertia[9 * b];
+#pragma unroll
     for (int i = 0; i < 3; ++i) Iwl[i] = wl[0] * I[3 * i] + wl[1] * I[3 * i + 1] + wl[2] * I[3 * i + 2];
     rot(R, Iwl, Iw);
+#pragma unroll
     for (int i = 0; i < 3; ++i) { P[i] = P[i] + vc[i]; Lo[i] = Lo[i] + l[i] + Iw[i]; mc[i] = mc[i] + cw[i] * mb; }
   };
-  T p0[3] = {q[0], q[1], q[2]}, v0[3] = {v[0], v[1], v[2]};
+  T p0[3] = {qf(0), qf(1), qf(2)}, v0[3] = {vf(0), vf(1), vf(2)};
   add_body(0, R0, p0, w0, v0);
   for (int leg = 0; leg < 2; ++leg) {
     T R[9], p[3], w[3], vl[3];
+#pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = R0[i];
+#pragma unroll
     for (int i = 0; i < 3; ++i) { p[i] = p0[i]; w[i] = w0[i]; vl[i] = v0[i]; }
     for (int j = 0; j < 5; ++j) {
       const int b = 1 + 5 * leg + j;
-      T d[3], wxd[3], a[3];
+      T d[3], wxd[3], a[3], sj, cj;
       rot_const(R, &md.joint_xyz[3 * b], d);
       cross(w, d, wxd);
+#pragma unroll
       for (int i = 0; i < 3; ++i) { p[i] = p[i] + d[i]; vl[i] = vl[i] + wxd[i]; }
-      joint_rotate(R, md.joint_axis[b], q[5 + b], a);
-      for (int i = 0; i < 3; ++i) w[i] = w[i] + a[i] * v[5 + b];
+      scf(2 + b, sj, cj);
+      joint_rotate_sc(R, md.joint_axis[b], sj, cj, a);
+      const T vb = vf(5 + b);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) w[i] = w[i] + a[i] * vb;
       add_body(b, R, p, w, vl);
     }
+#pragma unroll
     for (int t = 0; t < 2; ++t) {  // toe (contact leg), heel (contact 2+leg)
       const int c = leg + 2 * t;
       T off[3], wxo[3];
       rot_const(R, &md.contact_offset[3 * c], off);
       cross(w, off, wxo);
-      for (int i = 0; i < 3; ++i) { o.cpos[3 * c + i] = p[i] + off[i]; o.cvel[3 * c + i] = vl[i] + wxo[i]; }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { of.cpos(3 * c + i, p[i] + off[i]); of.cvel(3 * c + i, vl[i] + wxo[i]); }
     }
   }
   const double im = 1.0 / md.total_mass;
-  for (int i = 0; i < 3; ++i) o.com[i] = mc[i] * im;
-  T cxP[3];
-  cross(o.com, P, cxP);
-  for (int i = 0; i < 3; ++i) { o.h[i] = P[i]; o.h[3 + i] = Lo[i] - cxP[i]; }
+  T com[3], cxP[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { com[i] = mc[i] * im; of.com(i, com[i]); }
+  cross(com, P, cxP);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { of.h(i, P[i]); of.h(3 + i, Lo[i] - cxP[i]); }
+}
+
+template <class T> struct KinOutSink {
+  KinOut<T>& o;
+  __device__ __forceinline__ void h(int i, const T& x) { o.h[i] = x; }
+  __device__ __forceinline__ void com(int i, const T& x) { o.com[i] = x; }
+  __device__ __forceinline__ void cpos(int i, const T& x) { o.cpos[i] = x; }
+  __device__ __forceinline__ void cvel(int i, const T& x) { o.cvel[i] = x; }
+};
+
+// Array form (used where the lane-private copy of q, v is needed anyway)
+template <class T>
+__device__ void kin_pass(const T* q, const T* v, KinOut<T>& o) {
+  KinOutSink<T> sink{o};
+  kin_pass_f<T>([&](int i) { return q[i]; }, [&](int i) { return v[i]; },
+                [&](int k, T& s, T& c) { sincos_t(q[3 + k], s, c); }, sink);
 }
 
 // Recursive Newton-Euler in the coordinates above: tau = M(q) a + C(q,v) v + g(q)   (float64, per lane).

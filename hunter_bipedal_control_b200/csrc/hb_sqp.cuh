@@ -38,6 +38,7 @@ struct LinHalf {
   double x[NX], u[NU], x2[NX], f[NX];
   double Acm[6 * 16], Jc[12 * 16], dh[6 * NDIR], dcom[3 * NDIR], dp[12 * NDIR], dv[12 * NDIR];
   double Abinv[36], AbinvAj[6 * NJ], dvb[6 * NDIR], vgen[16], epos[12], evel[12], com[3];
+  double sn[NDIR], cs[NDIR];   // sines / cosines of yaw, pitch, roll and the ten joint angles, shared by all sweeps of a stage
 };
 
 // Linearise the flow map of one node at state xs (half-warp cooperative; `hl` = lane within the half, `act` = node exists).
@@ -45,22 +46,19 @@ struct LinHalf {
 __device__ __noinline__ void lin_half(LinHalf& sh, const double* xs, int hl, bool act, double* rec_f, double* rec_A, double* rec_Bf,
                                       double* rec_Bv, bool want_ee, double* rec) {
   const double m = c_model.total_mass;
+  if (hl < NDIR) { double s, c; sincos(xs[9 + hl], &s, &c); sh.sn[hl] = s; sh.cs[hl] = c; }
+  __syncwarp();
   {
-    double q[NQ], e[NQ];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) { q[i] = xs[6 + i]; e[i] = (i == hl) ? 1.0 : 0.0; }
-    KinOut<double> o;
-    kin_pass<double>(q, e, o);
-#pragma unroll
-    for (int r = 0; r < 6; ++r) sh.Acm[r * 16 + hl] = o.h[r];
-#pragma unroll
-    for (int r = 0; r < 12; ++r) sh.Jc[r * 16 + hl] = o.cvel[r];
-    if (hl == 0) {
-#pragma unroll
-      for (int r = 0; r < 12; ++r) sh.epos[r] = o.cpos[r];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) sh.com[r] = o.com[r];
-    }
+    // sweep 1: unit generalised velocity e_hl -> column hl of the centroidal momentum matrix and of the contact Jacobians
+    struct Sink1 {
+      LinHalf& sh; int hl;
+      __device__ __forceinline__ void h(int i, double x) { sh.Acm[i * 16 + hl] = x; }
+      __device__ __forceinline__ void com(int i, double x) { if (hl == 0) sh.com[i] = x; }
+      __device__ __forceinline__ void cpos(int i, double x) { if (hl == 0) sh.epos[i] = x; }
+      __device__ __forceinline__ void cvel(int i, double x) { sh.Jc[i * 16 + hl] = x; }
+    } sink{sh, hl};
+    kin_pass_f<double>([&](int i) { return xs[6 + i]; }, [&](int i) { return (i == hl) ? 1.0 : 0.0; },
+                       [&](int k, double& s, double& c) { s = sh.sn[k]; c = sh.cs[k]; }, sink);
   }
   __syncwarp();
   if (hl < 7) {
@@ -92,21 +90,17 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const double* xs, int hl, boo
     for (int r = 0; r < 6; ++r) { double s = 0.0; for (int c = 0; c < 6; ++c) s += sh.Abinv[6 * r + c] * sh.Acm[c * 16 + 6 + hl]; sh.AbinvAj[r * NJ + hl] = s; }
   }
   if (hl < NDIR) {
-    D1 q[NQ], v[NQ];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) { q[i] = D1(xs[6 + i], (i == 3 + hl) ? 1.0 : 0.0); v[i] = D1(sh.vgen[i], 0.0); }
-    KinOut<D1> o;
-    kin_pass<D1>(q, v, o);
-#pragma unroll
-    for (int r = 0; r < 6; ++r) sh.dh[r * NDIR + hl] = o.h[r].d;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) sh.dcom[r * NDIR + hl] = o.com[r].d;
-#pragma unroll
-    for (int r = 0; r < 12; ++r) { sh.dp[r * NDIR + hl] = o.cpos[r].d; sh.dv[r * NDIR + hl] = o.cvel[r].d; }
-    if (hl == 0) {
-#pragma unroll
-      for (int r = 0; r < 12; ++r) sh.evel[r] = o.cvel[r].v;
-    }
+    // sweep 2: dual numbers seeded along configuration direction 3+hl, generalised velocity held fixed
+    struct Sink2 {
+      LinHalf& sh; int hl;
+      __device__ __forceinline__ void h(int i, D1 x) { sh.dh[i * NDIR + hl] = x.d; }
+      __device__ __forceinline__ void com(int i, D1 x) { sh.dcom[i * NDIR + hl] = x.d; }
+      __device__ __forceinline__ void cpos(int i, D1 x) { sh.dp[i * NDIR + hl] = x.d; }
+      __device__ __forceinline__ void cvel(int i, D1 x) { sh.dv[i * NDIR + hl] = x.d; if (hl == 0) sh.evel[i] = x.v; }
+    } sink{sh, hl};
+    kin_pass_f<D1>([&](int i) { return D1(xs[6 + i], (i == 3 + hl) ? 1.0 : 0.0); }, [&](int i) { return D1(sh.vgen[i], 0.0); },
+                   [&](int k, D1& s, D1& c) { const double sv = sh.sn[k], cv = sh.cs[k]; const double on = (k == hl) ? 1.0 : 0.0; s = D1(sv, cv * on); c = D1(cv, -sv * on); },
+                   sink);
   }
   __syncwarp();
   if (hl < NDIR) {
@@ -610,8 +604,8 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
   }
   __syncwarp();
   // Rt (ntp x ntp), Pt (ntp x 22), rt (ntp); RN = Rvv Nv computed on the fly per entry
-  for (int idx = lane; idx < ntp * ntp; idx += 32) {
-    const int i = idx / ntp, j = idx - i * ntp;
+  for (int idx = lane; idx < NTMAX * NTMAX; idx += 32) {
+    const int i = idx / NTMAX, j = idx - i * NTMAX;
     double s = 0.0;
     if (i >= nt || j >= nt) s = (i == j) ? 1.0 / dt : 0.0;       // identity on the padded diagonal
     else if (i < nf && j < nf) s = sh.RFF[sh.stidx[i] * 12 + sh.stidx[j]];
@@ -622,10 +616,11 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     out[PJ_RT + i * NTMAX + j] = dt * s;
   }
   if (lane < NX) {
-    for (int c = 0; c < ntp; ++c) {
+    // Pt is stored transposed (22 x NTMAX) so that the Riccati kernel can stage it with 16-byte async copies
+    for (int c = 0; c < NTMAX; ++c) {
       double s = 0.0;
       if (c >= nf && c < nt) { const int cc = c - nf; for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Nv[kk * NVMAX + cc], T1[kk * NX + lane], s); }
-      out[PJ_PT + c * NX + lane] = dt * s;
+      out[PJ_PT + lane * NTMAX + c] = dt * s;
     }
   }
   if (lane < ntp) {
@@ -676,43 +671,51 @@ __device__ __forceinline__ void rowmm(double* __restrict__ C, int ldc, const dou
 }
 
 
+struct RicNodeIn { double At[TS], Bt[NX * NTMAX], bt[NX], qt[NX], rt[NTMAX], meta[8]; };
 struct RicShared {
-  double S[TS], At[TS], SA[TS];
-  double Bt[NX * NTMAX], SB[NX * NTMAX], HuxT[NX * NTMAX], K[NTMAX * NX], Huu[NTMAX * 18];
-  double sv[NX], bt[NX], sb[NX], qt[NX], rt[NTMAX], hu[NTMAX], kff[NTMAX], idg[NTMAX];
+  double S[TS], SA[TS];
+  RicNodeIn in[2];                                   // node data, staged one node ahead with cp.async
+  double SBK[NX * NTMAX];                            // SB (22 x NTMAX), later K (NTMAX x 22)
+  double HuxT[NX * NTMAX], Huu[NTMAX * 18];
+  double sv[NX], sb[NX], hu[NTMAX], kff[NTMAX], idg[NTMAX];
 };
 
+__device__ __forceinline__ void ric_prefetch(RicNodeIn& n, const double* __restrict__ rec, int lane) {
+  for (int i = 2 * lane; i < TS; i += 64) cp_async16(n.At + i, rec + PJ_AT + i);
+  for (int i = 2 * lane; i < NX * NTMAX; i += 64) cp_async16(n.Bt + i, rec + PJ_BT + i);
+  if (lane < 11) { cp_async16(n.bt + 2 * lane, rec + PJ_BTV + 2 * lane); cp_async16(n.qt + 2 * lane, rec + PJ_QV + 2 * lane); }
+  else if (lane < 19) cp_async16(n.rt + 2 * (lane - 11), rec + PJ_RV + 2 * (lane - 11));
+  else if (lane < 23) cp_async16(n.meta + 2 * (lane - 19), rec + PJ_META + 2 * (lane - 19));
+  cp_async_commit();
+}
+
 template <int NTP>
-__device__ __noinline__ void riccati_node(RicShared& sh, const double* __restrict__ rec, double* __restrict__ rk, bool& fail) {
+__device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, const double* __restrict__ rec, double* __restrict__ rk, bool& fail) {
   const int lane = lane_id();
+  double* SB = sh.SBK; double* K = sh.SBK;
   // SA = S At ; SB = S Bt ; sb = s + S bt
-  rowmm<NX, false, 0>(sh.SA, NX, sh.S, NX, sh.At, NX, NX, NX);
-  rowmm<NTP, false, 0>(sh.SB, NTMAX, sh.S, NX, sh.Bt, NTMAX, NX, NX);
+  rowmm<NX, false, 0>(sh.SA, NX, sh.S, NX, in.At, NX, NX, NX);
+  rowmm<NTP, false, 0>(SB, NTMAX, sh.S, NX, in.Bt, NTMAX, NX, NX);
   if (lane < NX) {
     double s0 = sh.sv[lane], s1 = 0.0;
 #pragma unroll
-    for (int k = 0; k < NX; k += 2) { s0 = fma(sh.S[lane * NX + k], sh.bt[k], s0); s1 = fma(sh.S[lane * NX + k + 1], sh.bt[k + 1], s1); }
+    for (int k = 0; k < NX; k += 2) { s0 = fma(sh.S[lane * NX + k], in.bt[k], s0); s1 = fma(sh.S[lane * NX + k + 1], in.bt[k + 1], s1); }
     sh.sb[lane] = s0 + s1;
-    // Hux^T initialised with Pt^T (Pt is NTP x 22 in the record)
-#pragma unroll
-    for (int c = 0; c < NTP; ++c) sh.HuxT[lane * NTMAX + c] = rec[PJ_PT + c * NX + lane];
-  }
-  if (lane < NTP) {
-#pragma unroll
-    for (int c = 0; c < NTP; ++c) sh.Huu[lane * 18 + c] = rec[PJ_RT + lane * NTMAX + c];
   }
   __syncwarp();
-  // Hux^T (22 x NTP) += SA^T Bt ; Huu (NTP x NTP) += Bt^T SB ; hu = rt + Bt^T sb
-  rowmm<NTP, true, 1>(sh.HuxT, NTMAX, sh.SA, NX, sh.Bt, NTMAX, NX, NX);
-  rowmm<NTP, true, 1>(sh.Huu, 18, sh.Bt, NTMAX, sh.SB, NTMAX, NTP, NX);
+  // S is dead until the end of the node: stage Qt into it now (arrives while the gains are computed)
+  for (int i = 2 * lane; i < TS; i += 64) cp_async16(sh.S + i, rec + PJ_QT + i);
+  cp_async_commit();
+  // Hux^T (22 x NTP) = Pt^T + SA^T Bt ; Huu (NTP x NTP) = Rt + Bt^T SB ; hu = rt + Bt^T sb   (Pt^T, Rt were staged at node start)
+  rowmm<NTP, true, 1>(sh.HuxT, NTMAX, sh.SA, NX, in.Bt, NTMAX, NX, NX);
+  rowmm<NTP, true, 1>(sh.Huu, 18, in.Bt, NTMAX, SB, NTMAX, NTP, NX);
   if (lane < NTP) {
-    double s0 = sh.rt[lane];
+    double s0 = in.rt[lane];
 #pragma unroll
-    for (int k = 0; k < NX; ++k) s0 = fma(sh.Bt[k * NTMAX + lane], sh.sb[k], s0);
+    for (int k = 0; k < NX; ++k) s0 = fma(in.Bt[k * NTMAX + lane], sh.sb[k], s0);
     sh.hu[lane] = s0;
   }
   __syncwarp();
-  // symmetrise the lower triangle, factorise, K = -Huu^-1 Hux (stored NTP x 22), kff = -Huu^-1 hu
   if (lane < NTP) {
 #pragma unroll
     for (int c = 0; c < NTP; ++c) if (c < lane) sh.Huu[lane * 18 + c] = 0.5 * (sh.Huu[lane * 18 + c] + sh.Huu[c * 18 + lane]);
@@ -739,7 +742,7 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const double* __restric
     }
     if (lane < NX) {
 #pragma unroll
-      for (int c = 0; c < NTP; ++c) { sh.K[c * NX + lane] = col[c]; rk[c * NX + lane] = col[c]; }
+      for (int c = 0; c < NTP; ++c) { K[c * NX + lane] = col[c]; rk[c * NX + lane] = col[c]; }     // SB is dead: K takes its place
     } else {
 #pragma unroll
       for (int c = 0; c < NTP; ++c) { sh.kff[c] = col[c]; rk[NTMAX * NX + c] = col[c]; }
@@ -748,21 +751,18 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const double* __restric
   __syncwarp();
   // s <- qt + At' sb + Hux' kff
   if (lane < NX) {
-    double s0 = sh.qt[lane], s1 = 0.0;
+    double s0 = in.qt[lane], s1 = 0.0;
 #pragma unroll
-    for (int k = 0; k < NX; k += 2) { s0 = fma(sh.At[k * NX + lane], sh.sb[k], s0); s1 = fma(sh.At[(k + 1) * NX + lane], sh.sb[k + 1], s1); }
+    for (int k = 0; k < NX; k += 2) { s0 = fma(in.At[k * NX + lane], sh.sb[k], s0); s1 = fma(in.At[(k + 1) * NX + lane], sh.sb[k + 1], s1); }
 #pragma unroll
     for (int c = 0; c < NTP; ++c) s0 = fma(sh.HuxT[lane * NTMAX + c], sh.kff[c], s0);
     sh.sv[lane] = s0 + s1;
-    // S row i initialised with Qt row i
-#pragma unroll
-    for (int j = 0; j < NX; ++j) sh.S[lane * NX + j] = rec[PJ_QT + lane * NX + j];
   }
+  cp_async_wait<0>();   // Qt has landed in S
   __syncwarp();
-  // S += At' SA + Hux' K
-  rowmm<NX, true, 1>(sh.S, NX, sh.At, NX, sh.SA, NX, NX, NX);
-  rowmm<NX, false, 1>(sh.S, NX, sh.HuxT, NTMAX, sh.K, NX, NX, NTP);
-  // symmetrise
+  // S = Qt + At' SA + Hux' K
+  rowmm<NX, true, 1>(sh.S, NX, in.At, NX, sh.SA, NX, NX, NX);
+  rowmm<NX, false, 1>(sh.S, NX, sh.HuxT, NTMAX, K, NX, NX, NTP);
   for (int idx = lane; idx < TS; idx += 32) { const int i = idx / NX, j = idx - i * NX; if (j > i) { const double v = 0.5 * (sh.S[idx] + sh.S[j * NX + i]); sh.S[idx] = v; sh.S[j * NX + i] = v; } }
   __syncwarp();
 }
@@ -771,27 +771,32 @@ __global__ void __launch_bounds__(32) riccati_kernel(SqpArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RicShared& sh = *reinterpret_cast<RicShared*>(smem_raw);
   const int inst = blockIdx.x, lane = threadIdx.x, N = a.N;
+  const double* proj = a.proj + (size_t)inst * N * PJ_STRIDE;
+  ric_prefetch(sh.in[(N - 1) & 1], proj + (size_t)(N - 1) * PJ_STRIDE, lane);
   for (int idx = lane; idx < TS; idx += 32) sh.S[idx] = 0.0;   // no terminal cost
   if (lane < NX) sh.sv[lane] = 0.0;
   __syncwarp();
   bool fail = false;
   double merit = 0.0, dyn = 0.0, eqs = 0.0;
   for (int k = N - 1; k >= 0; --k) {
-    const double* rec = a.proj + ((size_t)inst * N + k) * PJ_STRIDE;
+    const double* rec = proj + (size_t)k * PJ_STRIDE;
     double* rk = a.rk + ((size_t)inst * N + k) * RK_STRIDE;
-    const int nt = (int)rec[PJ_META];
-    merit += a.dt * rec[PJ_META + 3]; dyn += a.dt * rec[PJ_META + 4]; eqs += a.dt * rec[PJ_META + 5];
-    if (rec[PJ_META + 6] != 0.0) fail = true;
-    for (int idx = lane; idx < TS; idx += 32) sh.At[idx] = rec[PJ_AT + idx];
-    for (int idx = lane; idx < NX * NTMAX; idx += 32) sh.Bt[idx] = rec[PJ_BT + idx];
-    if (lane < NX) { sh.bt[lane] = rec[PJ_BTV + lane]; sh.qt[lane] = rec[PJ_QV + lane]; }
-    if (lane < NTMAX) sh.rt[lane] = rec[PJ_RV + lane];
+    // stage Pt^T -> HuxT (22 x 16) and Rt -> Huu (16 rows of 16, leading dimension 18) for this node, then the next node's inputs
+    for (int i = 2 * lane; i < NX * NTMAX; i += 64) cp_async16(sh.HuxT + i, rec + PJ_PT + i);
+    for (int c = lane; c < NTMAX * 8; c += 32) { const int r = c >> 3, q = c & 7; cp_async16(sh.Huu + r * 18 + 2 * q, rec + PJ_RT + r * NTMAX + 2 * q); }
+    cp_async_commit();
+    if (k > 0) { ric_prefetch(sh.in[(k - 1) & 1], proj + (size_t)(k - 1) * PJ_STRIDE, lane); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
     __syncwarp();
+    const RicNodeIn& in = sh.in[k & 1];
+    const int nt = (int)in.meta[0];
+    merit += a.dt * in.meta[3]; dyn += a.dt * in.meta[4]; eqs += a.dt * in.meta[5];
+    if (in.meta[6] != 0.0) fail = true;
     const int ntp = ntp_of(nt);
-    if (ntp == 12) riccati_node<12>(sh, rec, rk, fail);
-    else if (ntp == 10) riccati_node<10>(sh, rec, rk, fail);
-    else if (ntp == 6) riccati_node<6>(sh, rec, rk, fail);
-    else riccati_node<16>(sh, rec, rk, fail);
+    if (ntp == 12) riccati_node<12>(sh, in, rec, rk, fail);
+    else if (ntp == 10) riccati_node<10>(sh, in, rec, rk, fail);
+    else if (ntp == 6) riccati_node<6>(sh, in, rec, rk, fail);
+    else riccati_node<16>(sh, in, rec, rk, fail);
   }
   if (lane == 0) {
     double* pf = a.perf + (size_t)inst * 4;
