@@ -261,6 +261,8 @@ struct hb_ctx {
   hb_config cfg;
   int device;
   cudaStream_t stream;
+  cudaStream_t stream_main, stream_aux;   // the host-pointer control step pipelines two half-batches over these
+  int base;                               // instance offset into the per-instance scratch (chunked calls)
   int64_t launches;
   // MPC scratch
   double *gains, *dxt, *dut, *perf;
@@ -347,6 +349,8 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return HB_ECUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HB_ECUDA; }
+  ctx->stream_main = ctx->stream;
+  if (cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HB_ECUDA; }
   // model constants
   Model* m = new Model();
   memset(m, 0, sizeof(Model));
@@ -421,7 +425,8 @@ int hb_destroy(hb_ctx* ctx) {
                   ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
+  if (ctx->stream_main) cudaStreamDestroy(ctx->stream_main);
   delete ctx;
   return HB_OK;
 }
@@ -501,7 +506,7 @@ int hb_wbc_solve_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double
     const size_t per_warp = wbc_fused_doubles() * sizeof(double);
     prof_begin(ctx, K_QP);
     wbc_fused_kernel<<<B, 32, per_warp, ctx->stream>>>(B, x_des, u_des, rbd, mode, stance_mode, ctx->cfg.wbc_rho, ctx->cfg.qp_max_iter, sol,
-                                                        status ? status : ctx->wstatus, ctx->witers);
+                                                        status ? status : ctx->wstatus + ctx->base, ctx->witers + ctx->base);
     prof_end(ctx);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -552,7 +557,11 @@ int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x
   }
   SqpArgs a;
   a.B = B; a.N = ctx->cfg.horizon_N; a.dt = ctx->cfg.dt; a.x_ref = x_ref; a.swing = swing_ref; a.mode = mode; a.xt = x_traj; a.ut = u_traj;
-  a.lin = ctx->lin; a.proj = ctx->proj; a.rk = ctx->rk; a.dxt = ctx->dxt; a.dut = ctx->dut; a.perf = ctx->perf; a.flags = ctx->flags; a.x0 = x0;
+  {
+    const size_t o = (size_t)ctx->base, Nn = (size_t)ctx->cfg.horizon_N;
+    a.lin = ctx->lin + o * Nn * LIN_STRIDE; a.proj = ctx->proj + o * Nn * PJ_STRIDE; a.rk = ctx->rk + o * Nn * RK_STRIDE;
+    a.dxt = ctx->dxt + o * (Nn + 1) * NX; a.dut = ctx->dut + o * Nn * NU; a.perf = ctx->perf + o * 4; a.flags = ctx->flags + o; a.x0 = x0;
+  }
   const int N = a.N, NP = (N + 1) / 2;
   const long long nw = (long long)B * NP;
   prof_begin(ctx, K_LIN);
@@ -597,9 +606,10 @@ int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0
   int rc = hb_mpc_solve_batch_dev(ctx, B, x0, x_ref, swing_ref, mode, x_traj, u_traj, info);
   if (rc) return rc;
   if (B == 0) return HB_OK;
-  rc = hb_policy_eval_batch_dev(ctx, B, t_rel, x_traj, u_traj, mode, ctx->xdes, ctx->udes, ctx->wmode);
+  double* xdes = ctx->xdes + (size_t)ctx->base * NX; double* udes = ctx->udes + (size_t)ctx->base * NU; int32_t* wmode = ctx->wmode + ctx->base;
+  rc = hb_policy_eval_batch_dev(ctx, B, t_rel, x_traj, u_traj, mode, xdes, udes, wmode);
   if (rc) return rc;
-  rc = hb_wbc_solve_batch_dev(ctx, B, ctx->xdes, ctx->udes, rbd, ctx->wmode, nullptr, wbc_sol, wbc_status);
+  rc = hb_wbc_solve_batch_dev(ctx, B, xdes, udes, rbd, wmode, nullptr, wbc_sol, wbc_status);
   if (rc) return rc;
   if (torque) {
     torque_kernel<<<(B * NJ + 127) / 128, 128, 0, ctx->stream>>>(B, wbc_sol, torque);
@@ -722,19 +732,42 @@ int hb_control_step_batch(hb_ctx* ctx, int B, double t_rel, const double* x0, co
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (set_device(ctx)) return HB_ECUDA;
   const size_t N = ctx->cfg.horizon_N;
-  H2D(ctx->s_x0, x0, sizeof(double) * B * NX); H2D(ctx->s_xref, x_ref, sizeof(double) * B * (N + 1) * NX);
-  H2D(ctx->s_swing, swing_ref, sizeof(double) * B * (N + 1) * 24); H2D(ctx->s_mode, mode, sizeof(int32_t) * B * (N + 1));
-  H2D(ctx->s_xt, x_traj, sizeof(double) * B * (N + 1) * NX); H2D(ctx->s_ut, u_traj, sizeof(double) * B * N * NU);
-  H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32);
-  int rc = hb_control_step_batch_dev(ctx, B, t_rel, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_mode, ctx->s_rbd, ctx->s_xt, ctx->s_ut, ctx->s_info,
-                                     ctx->s_sol, ctx->s_tau, ctx->s_status);
+  // Two half-batches on two streams: the copies of one half overlap the kernels of the other (pinned host memory assumed).
+  const int nchunk = (B >= 256 && ctx->sqp_version == 2) ? 2 : 1;
+  int rc = HB_OK;
+  for (int c = 0; c < nchunk && rc == HB_OK; ++c) {
+    const size_t lo = (size_t)B * c / nchunk, hi = (size_t)B * (c + 1) / nchunk, n = hi - lo;
+    ctx->stream = (c == 0) ? ctx->stream_main : ctx->stream_aux;
+    ctx->base = (int)lo;
+    cudaError_t e = cudaSuccess;
+    auto h2d = [&](void* d, const void* h, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream); };
+    auto d2h = [&](void* h, const void* d, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream); };
+    h2d(ctx->s_x0 + lo * NX, x0 + lo * NX, sizeof(double) * n * NX);
+    h2d(ctx->s_xref + lo * (N + 1) * NX, x_ref + lo * (N + 1) * NX, sizeof(double) * n * (N + 1) * NX);
+    h2d(ctx->s_swing + lo * (N + 1) * 24, swing_ref + lo * (N + 1) * 24, sizeof(double) * n * (N + 1) * 24);
+    h2d(ctx->s_mode + lo * (N + 1), mode + lo * (N + 1), sizeof(int32_t) * n * (N + 1));
+    h2d(ctx->s_xt + lo * (N + 1) * NX, x_traj + lo * (N + 1) * NX, sizeof(double) * n * (N + 1) * NX);
+    h2d(ctx->s_ut + lo * N * NU, u_traj + lo * N * NU, sizeof(double) * n * N * NU);
+    h2d(ctx->s_rbd + lo * 32, rbd + lo * 32, sizeof(double) * n * 32);
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = HB_ECUDA; break; }
+    rc = hb_control_step_batch_dev(ctx, (int)n, t_rel, ctx->s_x0 + lo * NX, ctx->s_xref + lo * (N + 1) * NX, ctx->s_swing + lo * (N + 1) * 24,
+                                   ctx->s_mode + lo * (N + 1), ctx->s_rbd + lo * 32, ctx->s_xt + lo * (N + 1) * NX, ctx->s_ut + lo * N * NU,
+                                   ctx->s_info + lo, ctx->s_sol + lo * NWBC, ctx->s_tau + lo * NJ, ctx->s_status + lo);
+    if (rc) break;
+    d2h(x_traj + lo * (N + 1) * NX, ctx->s_xt + lo * (N + 1) * NX, sizeof(double) * n * (N + 1) * NX);
+    d2h(u_traj + lo * N * NU, ctx->s_ut + lo * N * NU, sizeof(double) * n * N * NU);
+    if (info) d2h(info + lo, ctx->s_info + lo, sizeof(hb_solve_info) * n);
+    if (wbc_sol) d2h(wbc_sol + lo * NWBC, ctx->s_sol + lo * NWBC, sizeof(double) * n * NWBC);
+    if (torque) d2h(torque + lo * NJ, ctx->s_tau + lo * NJ, sizeof(double) * n * NJ);
+    if (wbc_status) d2h(wbc_status + lo, ctx->s_status + lo, sizeof(int32_t) * n);
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = HB_ECUDA; }
+  }
+  ctx->stream = ctx->stream_main;
+  ctx->base = 0;
+  cudaError_t e1 = cudaStreamSynchronize(ctx->stream_aux), e0 = cudaStreamSynchronize(ctx->stream_main);
   if (rc) return rc;
-  D2H(x_traj, ctx->s_xt, sizeof(double) * B * (N + 1) * NX); D2H(u_traj, ctx->s_ut, sizeof(double) * B * N * NU);
-  if (info) D2H(info, ctx->s_info, sizeof(hb_solve_info) * B);
-  if (wbc_sol) D2H(wbc_sol, ctx->s_sol, sizeof(double) * B * NWBC);
-  if (torque) D2H(torque, ctx->s_tau, sizeof(double) * B * NJ);
-  if (wbc_status) D2H(wbc_status, ctx->s_status, sizeof(int32_t) * B);
-  return hb_sync(ctx);
+  if (e0 != cudaSuccess || e1 != cudaSuccess) { ctx->last_cuda = (int)(e0 != cudaSuccess ? e0 : e1); return HB_ECUDA; }
+  return HB_OK;
 }
 
 int hb_rbd_to_centroidal_batch(hb_ctx* ctx, int B, const double* rbd, double* x) {
