@@ -251,6 +251,13 @@ def main():
         bk_ms = bk["ms"] / max(1, bk["launches"])
         ach = B * BYTES_PER_MPC_SOLVE / (bk_ms * 1e-3) / 1e9 if bk_ms > 0 else None
         step_ms = ms / args.steps
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (same workload, 1024 instances)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            kname = {"mpc_lq_project": "lq_kernel", "mpc_linearise": "lin_kernel", "mpc_riccati": "riccati_kernel", "mpc_forward_linesearch": "forward_linesearch2_kernel"}[top]
+            traffic = tj[kname]["dram_bytes"] * B / tj[kname]["instances"]
+        except Exception:
+            pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "configs[1]: %d Hunter instances per GPU, trot gait, N=100 dt=10 ms, randomised initial base pose (seed 20240901+i), "
@@ -261,7 +268,7 @@ def main():
                 "gpu_launches": int(launches),
                 "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
                 "roofline": {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": (ach / peaks["hbm_gbs"]) if ach else None, "peak_source": src, "traffic": None,
+                             "frac": (ach / peaks["hbm_gbs"]) if ach else None, "peak_source": src, "traffic": traffic,
                              "share_of_step": bk_ms / step_ms if step_ms > 0 else None,
                              "note": "latency/FP64-bound path: the HBM fraction is small by construction (SURVEY 8d); see roofline_fp64"},
                 "roofline_fp64": {"achieved_tflops": value / world * FLOPS_PER_SOLVE / 1e12, "peak_tflops_nominal": FP64_NOMINAL_TFLOPS,
