@@ -70,7 +70,7 @@ __device__ inline void qp_carve(double* base, int n, QpWorkspace& w, int me_cap 
 
 // In-place Cholesky M = L L' (lower triangle) followed by Li = L^-1, stored transposed in the strict upper triangle
 // (Li[i][k] at M[k*ld + i], i > k) with diag(Li) = invdiag. Returns false when a pivot is not positive.
-__device__ inline bool warp_chol_inv(double* M, int n, int ld, double* invdiag, int lane) {
+__device__ inline bool warp_chol_inv(double* M, int n, int ld, double* invdiag, int lane, double piv_floor = 0.0) {
   bool ok = true;
   for (int j = 0; j < n; ++j) {
     for (int i = j + lane; i < n; i += 32) {
@@ -86,7 +86,11 @@ __device__ inline bool warp_chol_inv(double* M, int n, int ld, double* invdiag, 
     }
     __syncwarp();
     double d = M[j * ld + j];
-    if (!(d > 0.0)) { ok = false; d = 1.0; }
+    if (!(d > piv_floor)) {
+      // piv_floor > 0: regularised factorisation (the interior-point residuals are exact, so a floored pivot only perturbs the
+      // search direction); piv_floor == 0: strict, report failure
+      if (piv_floor > 0.0 && d == d) d = piv_floor; else { ok = false; d = 1.0; }
+    }
     const double r = 1.0 / sqrt(d);
     __syncwarp();
     for (int i = j + lane; i < n; i += 32) M[i * ld + j] *= r;
@@ -256,7 +260,9 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
       }
       __syncwarp();
     }
-    bool ok = warp_chol_inv(w.K, n, ldn, w.kdi, lane);
+    // directions that only the Tikhonov term rho controls have pivots ~1e-8 next to barrier weights ~1e10 late in the solve:
+    // floor the pivots instead of failing
+    bool ok = warp_chol_inv(w.K, n, ldn, w.kdi, lane, 1e-10);
     // ---------------- V = Li Aeq'  (n x me), lane per equality row
     if (me > 0) {
       if (lane < me) {
@@ -282,7 +288,7 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
         }
       }
       __syncwarp();
-      ok = warp_chol_inv(w.S, me, lds, w.sdi, lane) && ok;
+      ok = warp_chol_inv(w.S, me, lds, w.sdi, lane, 1e-14) && ok;
     }
     if (!ok) { res.status = 2; break; }
 
