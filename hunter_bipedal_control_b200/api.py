@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_last_cuda_error", "hb_launch_count", "hb_stream", "hb_profile_enable", "hb_profile_read",
     "hb_wbc_qp_batch_dev", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
     "hb_policy_eval_batch_dev", "hb_control_step_batch_dev", "hb_rbd_to_centroidal_batch_dev", "hb_reference_expand_batch_dev",
-    "hb_probe_flow_map_dev",
+    "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references",
     "hb_wbc_qp_batch", "hb_wbc_solve_batch", "hb_mpc_cold_start_batch", "hb_mpc_solve_batch", "hb_control_step_batch",
     "hb_rbd_to_centroidal_batch", "hb_reference_expand_batch", "hb_probe_flow_map",
 ]
@@ -43,6 +43,35 @@ class HbReference(C.Structure):
     _fields_ = [("n_events", C.c_int32), ("event_times", C.c_double * HB_MAX_EVENTS), ("modes", C.c_int32 * (HB_MAX_EVENTS + 1)),
                 ("n_targets", C.c_int32), ("target_times", C.c_double * HB_MAX_TARGETS), ("target_states", (C.c_double * 22) * HB_MAX_TARGETS),
                 ("n_segments", (C.c_int32 * 3) * 4), ("segments", (((C.c_double * 6) * HB_MAX_SEGMENTS) * 3) * 4)]
+
+
+class HbPlanInput(C.Structure):
+    _fields_ = [("t0", C.c_double), ("horizon", C.c_double), ("time_to_target", C.c_double), ("gait_start", C.c_double), ("prev_event", C.c_double),
+                ("x0", C.c_double * 22), ("cmd_vel", C.c_double * 4), ("feet_pos", C.c_double * 12), ("gait", C.c_int32), ("reserved", C.c_int32)]
+
+
+GAIT_IDS = {"stance": 0, "trot": 1, "standing_trot": 2, "flying_trot": 3}
+
+
+def plan_references(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event=None, time_to_target=None, latest_stance=None):
+    """Host-side reference planner (hb_plan_references): returns (ctypes array of HbReference, latest_stance[B,12])."""
+    lib = load_library()
+    x0 = _f64(x0); B = x0.shape[0]
+    cmd_vel = np.broadcast_to(_f64(cmd_vel), (B, 4)); feet_pos = _f64(feet_pos).reshape(B, 12)
+    t0 = np.broadcast_to(_f64(t0), (B,)); gait_start = np.broadcast_to(_f64(gait_start), (B,))
+    ins = (HbPlanInput * B)()
+    for i in range(B):
+        p = ins[i]
+        p.t0 = t0[i]; p.horizon = horizon; p.time_to_target = horizon if time_to_target is None else time_to_target
+        p.gait_start = gait_start[i]; p.prev_event = (min(t0[i], gait_start[i]) - 0.5) if prev_event is None else prev_event
+        p.gait = GAIT_IDS[gait[i]] if isinstance(gait, (list, tuple)) else GAIT_IDS[gait]
+        for j in range(22): p.x0[j] = x0[i, j]
+        for j in range(4): p.cmd_vel[j] = cmd_vel[i, j]
+        for j in range(12): p.feet_pos[j] = feet_pos[i, j]
+    ls = np.zeros((B, 12)) if latest_stance is None else _f64(latest_stance).copy()
+    refs = (HbReference * B)()
+    _check(lib.hb_plan_references(B, ins, _ptr(ls), refs), "hb_plan_references")
+    return refs, ls
 
 
 INFO_DTYPE = np.dtype([("alpha", "f8"), ("merit0", "f8"), ("merit1", "f8"), ("viol0", "f8"), ("viol1", "f8"), ("armijo", "f8"),
@@ -193,6 +222,12 @@ class Context:
         x_ref = np.zeros((B, self.N + 1, NX)); swing = np.zeros((B, self.N + 1, 24)); mode = np.zeros((B, self.N + 1), dtype=np.int32)
         _check(self._lib.hb_reference_expand_batch(self._h, B, _ptr(t0), C.cast(refs, C.c_void_p), _ptr(x_ref), _ptr(swing), _ptr(mode)), "hb_reference_expand_batch", self._h)
         return x_ref, swing, mode
+
+    def contact_positions(self, x):
+        x = _f64(x); B = x.shape[0]
+        pos = np.zeros((B, 12))
+        _check(self._lib.hb_contact_positions_batch(self._h, B, _ptr(x), _ptr(pos)), "hb_contact_positions_batch", self._h)
+        return pos
 
     def probe_flow_map(self, x, u):
         x, u = _f64(x), _f64(u); B = x.shape[0]

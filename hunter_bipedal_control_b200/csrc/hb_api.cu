@@ -10,6 +10,7 @@
 #include "../../include/hunter_b200.h"
 #include "hb_common.cuh"
 #include "hb_mpc.cuh"
+#include "hb_planner.h"
 #include "hb_qp.cuh"
 #include "hb_rbd.cuh"
 #include "hb_sqp.cuh"
@@ -237,6 +238,17 @@ __global__ void reference_expand_kernel(int B, int N, double dt, const double* t
   }
 }
 
+// InverseKinematics::computeFootPos: contact frame positions at the configuration of x (one thread per instance)
+__global__ void contact_positions_kernel(int B, const double* x, double* pos) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= B) return;
+  double q[NQ], v[NQ];
+  for (int i = 0; i < NQ; ++i) { q[i] = x[(size_t)inst * NX + 6 + i]; v[i] = 0.0; }
+  KinOut<double> o;
+  kin_pass<double>(q, v, o);
+  for (int i = 0; i < 12; ++i) pos[(size_t)inst * 12 + i] = o.cpos[i];
+}
+
 // parity probe: flow map value, Jacobians and contact kinematics from the warp-cooperative linearisation
 __global__ void __launch_bounds__(32) probe_flow_map_kernel(int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -290,7 +302,7 @@ struct hb_ctx {
 
 namespace {
 
-enum { HB_OK = 0, HB_EINVAL = -1, HB_ECUDA = -2, HB_ENOMEM = -3, HB_ECAP = -4 };
+enum { HB_OK = 0, HB_EINVAL = -1, HB_ECUDA = -2, HB_ENOMEM = -3, HB_ECAP = -4, HB_EPLAN = -5 };
 
 #define CK(call)                                   \
   do {                                             \
@@ -336,6 +348,7 @@ const char* hb_strerror(int code) {
     case HB_ECUDA: return "CUDA error";
     case HB_ENOMEM: return "out of memory";
     case HB_ECAP: return "batch exceeds context capacity";
+    case HB_EPLAN: return "reference planner: swing phase without take-off / touch-down time, or reference capacity exceeded";
     default: return "unknown error";
   }
 }
@@ -639,6 +652,16 @@ int hb_reference_expand_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb
   return HB_OK;
 }
 
+int hb_contact_positions_batch_dev(hb_ctx* ctx, int B, const double* x, double* pos) {
+  if (!ctx || B < 0 || !x || !pos) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  contact_positions_kernel<<<(B + 63) / 64, 64, 0, ctx->stream>>>(B, x, pos);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
 int hb_probe_flow_map_dev(hb_ctx* ctx, int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee) {
   if (!ctx || B < 0 || !x || !u || !f || !A || !Bm) return HB_EINVAL;
   if (B == 0) return HB_OK;
@@ -794,6 +817,35 @@ int hb_reference_expand_batch(hb_ctx* ctx, int B, const double* t0, const hb_ref
   D2H(x_ref, ctx->s_xref, sizeof(double) * B * (N + 1) * NX); D2H(swing_ref, ctx->s_swing, sizeof(double) * B * (N + 1) * 24);
   D2H(mode, ctx->s_mode, sizeof(int32_t) * B * (N + 1));
   return hb_sync(ctx);
+}
+
+int hb_contact_positions_batch(hb_ctx* ctx, int B, const double* x, double* pos) {
+  if (!ctx || B < 0 || !x || !pos) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  H2D(ctx->s_xd, x, sizeof(double) * B * NX);
+  int rc = hb_contact_positions_batch_dev(ctx, B, ctx->s_xd, ctx->s_misc);
+  if (rc) return rc;
+  D2H(pos, ctx->s_misc, sizeof(double) * B * 12);
+  return hb_sync(ctx);
+}
+
+int hb_plan_references(int B, const hb_plan_input* in, double* latest_stance, hb_reference* out) {
+  if (B < 0 || !in || !latest_stance || !out) return HB_EINVAL;
+  for (int i = 0; i < B; ++i) {
+    const hb_plan_input& p = in[i];
+    if (!(p.horizon > 0.0) || !(p.prev_event < p.gait_start) || p.gait < 0 || p.gait > 3) return HB_EINVAL;
+    const double tf = p.t0 + p.horizon;
+    // the reference tiles over [t0 - T, tf + T] (SwitchedModelReferenceManager.cpp:147)
+    hbplan::ModeSchedule ms = hbplan::tile_gait(p.gait, p.prev_event, p.gait_start, tf + p.horizon);
+    hbplan::Target tg = hbplan::cmd_vel_to_target(p.cmd_vel, p.t0, p.x0, p.time_to_target);
+    const double body_vel_cmd[6] = {p.cmd_vel[0], p.cmd_vel[1], p.cmd_vel[2], p.cmd_vel[3], 0.0, 0.0};
+    hbplan::SwingPlan sp;
+    if (!hbplan::plan_swing(ms, tg, p.t0, p.feet_pos, body_vel_cmd, latest_stance + (size_t)i * 12, sp)) return HB_EPLAN;
+    if (hbplan::fill_reference(ms, tg, sp, p.t0 - 1e-9, tf + 1e-9, out + i) != 0) return HB_EPLAN;
+  }
+  return HB_OK;
 }
 
 int hb_probe_flow_map(hb_ctx* ctx, int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee) {

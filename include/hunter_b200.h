@@ -67,6 +67,20 @@ typedef struct {
   double segments[4][3][HB_MAX_SEGMENTS][6];
 } hb_reference;
 
+/* inputs of the host-side reference planner (one MPC solve of one instance) */
+typedef struct {
+  double t0;              /* solver init time                                                             */
+  double horizon;         /* final time = t0 + horizon                                                    */
+  double time_to_target;  /* TIME_TO_TARGET of the cmd_vel target (TargetTrajectoriesPublisher.cpp:107)   */
+  double gait_start;      /* time at which the gait template starts (STANCE before)                       */
+  double prev_event;      /* an event time inside the initial stance (< gait_start)                       */
+  double x0[22];          /* current observation state                                                    */
+  double cmd_vel[4];      /* filtered command: vx, vy, vz, yaw rate (body frame)                          */
+  double feet_pos[12];    /* current contact positions in world (hb_contact_positions_batch)              */
+  int32_t gait;           /* 0 stance, 1 trot, 2 standing_trot, 3 flying_trot (reference.info:54-118)     */
+  int32_t reserved;
+} hb_plan_input;
+
 int hb_default_config(hb_config* cfg);
 int hb_create(const hb_config* cfg, int device, hb_ctx** out);
 int hb_destroy(hb_ctx* ctx);
@@ -100,6 +114,9 @@ int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0
 int hb_rbd_to_centroidal_batch_dev(hb_ctx* ctx, int B, const double* rbd, double* x);
 int hb_reference_expand_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                                   int32_t* mode);
+/* world positions of the four contact frames at the configuration of x (InverseKinematics::computeFootPos,
+ * legged_interface/src/foot_planner/InverseKinematics.cpp:253-267) */
+int hb_contact_positions_batch_dev(hb_ctx* ctx, int B, const double* x, double* pos /*B x 12*/);
 /* probes used by the parity tests: rigid-body quantities and the node LQ model computed by the device code */
 int hb_probe_flow_map_dev(hb_ctx* ctx, int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee);
 
@@ -118,6 +135,15 @@ int hb_rbd_to_centroidal_batch(hb_ctx* ctx, int B, const double* rbd, double* x)
 int hb_reference_expand_batch(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                               int32_t* mode);
 int hb_probe_flow_map(hb_ctx* ctx, int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee);
+int hb_contact_positions_batch(hb_ctx* ctx, int B, const double* x, double* pos /*B x 12*/);
+
+/* ---- host-only reference preprocessing (no GPU work): gait tiling, swing-foot planner, cmd_vel target ----
+ * replaces GaitSchedule::{insert,tile}ModeSequenceTemplate (legged_interface/src/gait/GaitSchedule.cpp:57-161),
+ * SwingTrajectoryPlanner::update (src/foot_planner/SwingTrajectoryPlanner.cpp:164-286) and cmdVelToTargetTrajectories
+ * (legged_controllers/src/TargetTrajectoriesPublisher.cpp:102-130). latest_stance (B x 12) is the planner's state, in/out.
+ * Returns 0, or -1 on misuse, or -5 when a schedule does not define the take-off / touch-down of a swing phase (the reference
+ * throws there, SwingTrajectoryPlanner.cpp:421-458) or exceeds the capacity of hb_reference. */
+int hb_plan_references(int B, const hb_plan_input* in, double* latest_stance, hb_reference* out);
 
 #ifdef __cplusplus
 }
