@@ -17,13 +17,13 @@ _LIB_PATH = os.path.join(_HERE, "libhunter_b200.so")
 _lib = None
 
 NX, NU, NQ, NJ, NWBC = 22, 22, 16, 10, 38
-HB_MAX_EVENTS, HB_MAX_TARGETS, HB_MAX_SEGMENTS = 32, 8, 24
+HB_MAX_EVENTS, HB_MAX_TARGETS, HB_MAX_SEGMENTS = 32, 16, 24
 
 EXPORTED_SYMBOLS = [
     "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_last_cuda_error", "hb_launch_count", "hb_stream", "hb_profile_enable", "hb_profile_read",
     "hb_wbc_qp_batch_dev", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
     "hb_policy_eval_batch_dev", "hb_control_step_batch_dev", "hb_rbd_to_centroidal_batch_dev", "hb_reference_expand_batch_dev",
-    "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references",
+    "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references", "hb_gait_select", "hb_default_pd_gains", "hb_joint_command_batch_dev", "hb_joint_command_batch",
     "hb_wbc_qp_batch", "hb_wbc_solve_batch", "hb_mpc_cold_start_batch", "hb_mpc_solve_batch", "hb_control_step_batch",
     "hb_rbd_to_centroidal_batch", "hb_reference_expand_batch", "hb_probe_flow_map",
 ]
@@ -47,13 +47,51 @@ class HbReference(C.Structure):
 
 class HbPlanInput(C.Structure):
     _fields_ = [("t0", C.c_double), ("horizon", C.c_double), ("time_to_target", C.c_double), ("gait_start", C.c_double), ("prev_event", C.c_double),
-                ("x0", C.c_double * 22), ("cmd_vel", C.c_double * 4), ("feet_pos", C.c_double * 12), ("gait", C.c_int32), ("reserved", C.c_int32)]
+                ("x0", C.c_double * 22), ("cmd_vel", C.c_double * 4), ("feet_pos", C.c_double * 12), ("gait", C.c_int32), ("joint_ik", C.c_int32)]
+
+
+class HbPdGains(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("kp_position", "kd_position", "kp_big_stance", "kp_big_swing", "kd_big", "kp_small_stance",
+                                          "kp_small_swing", "kd_small", "kd_feet")]
+
+
+def default_pd_gains():
+    g = HbPdGains()
+    _check(load_library().hb_default_pd_gains(C.byref(g)), "hb_default_pd_gains")
+    return g
+
+
+class HbGaitSelector(C.Structure):
+    _fields_ = [("history", C.c_double * 50), ("vel_avg", C.c_double), ("head", C.c_int32), ("count", C.c_int32), ("gait_level", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class GaitSelector:
+    """Batch of speed-based gait selectors (SwitchedModelReferenceManager::calculateVelAbs + walkGait / trotGait)."""
+
+    def __init__(self, B, gait_level=-1):
+        self.B = B
+        self.state = (HbGaitSelector * B)()
+        for i in range(B):
+            self.state[i].gait_level = gait_level
+
+    def update(self, cmd_vel, target_state0, gait_type=0):
+        lib = load_library()
+        cmd_vel = _f64(np.broadcast_to(_f64(cmd_vel), (self.B, 4))); ts = _f64(target_state0).reshape(self.B, 22)
+        gt = np.ascontiguousarray(np.broadcast_to(np.asarray(gait_type, dtype=np.int32), (self.B,)))
+        level = np.zeros(self.B, dtype=np.int32); insert = np.zeros(self.B, dtype=np.int32)
+        _check(lib.hb_gait_select(self.B, self.state, _ptr(gt), _ptr(cmd_vel), _ptr(ts), _ptr(level), _ptr(insert)), "hb_gait_select")
+        return level, insert
+
+    @property
+    def vel_avg(self):
+        return np.array([self.state[i].vel_avg for i in range(self.B)])
 
 
 GAIT_IDS = {"stance": 0, "trot": 1, "standing_trot": 2, "flying_trot": 3}
 
 
-def plan_references(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event=None, time_to_target=None, latest_stance=None):
+def plan_references(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event=None, time_to_target=None, latest_stance=None, joint_ik=True):
     """Host-side reference planner (hb_plan_references): returns (ctypes array of HbReference, latest_stance[B,12])."""
     lib = load_library()
     x0 = _f64(x0); B = x0.shape[0]
@@ -65,6 +103,7 @@ def plan_references(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_e
         p.t0 = t0[i]; p.horizon = horizon; p.time_to_target = horizon if time_to_target is None else time_to_target
         p.gait_start = gait_start[i]; p.prev_event = (min(t0[i], gait_start[i]) - 0.5) if prev_event is None else prev_event
         p.gait = GAIT_IDS[gait[i]] if isinstance(gait, (list, tuple)) else GAIT_IDS[gait]
+        p.joint_ik = 1 if joint_ik else 0
         for j in range(22): p.x0[j] = x0[i, j]
         for j in range(4): p.cmd_vel[j] = cmd_vel[i, j]
         for j in range(12): p.feet_pos[j] = feet_pos[i, j]
@@ -209,6 +248,19 @@ class Context:
         _check(self._lib.hb_control_step_batch(self._h, B, C.c_double(t_rel), _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(rbd), _ptr(xt), _ptr(ut),
                                                _ptr(info), _ptr(sol), _ptr(tau), _ptr(st)), "hb_control_step_batch", self._h)
         return xt, ut, info, sol, tau, st
+
+    def joint_command(self, period, x_des, u_des, wbc_sol, mode_cmd, rbd, loaded=None, estop=None, gains=None):
+        """Joint command law (LeggedController.cpp:186-257): returns (command [B,10,5], output_torque [B,10], estop [B])."""
+        x_des, u_des, wbc_sol, rbd = _f64(x_des), _f64(u_des), _f64(wbc_sol), _f64(rbd); B = x_des.shape[0]
+        mode_cmd = np.ascontiguousarray(mode_cmd, dtype=np.int32)
+        gains = gains or default_pd_gains()
+        ld = None if loaded is None else np.ascontiguousarray(loaded, dtype=np.uint8)
+        es = np.zeros(B, dtype=np.uint8) if estop is None else np.ascontiguousarray(estop, dtype=np.uint8).copy()
+        cmd = np.zeros((B, NJ, 5)); tau = np.zeros((B, NJ))
+        _check(self._lib.hb_joint_command_batch(self._h, B, C.byref(gains), C.c_double(period), _ptr(x_des), _ptr(u_des), _ptr(wbc_sol), _ptr(mode_cmd),
+                                                _ptr(rbd), None if ld is None else _ptr(ld), _ptr(es), _ptr(cmd), _ptr(tau)),
+               "hb_joint_command_batch", self._h)
+        return cmd, tau, es
 
     def rbd_to_centroidal(self, rbd):
         rbd = _f64(rbd); B = rbd.shape[0]

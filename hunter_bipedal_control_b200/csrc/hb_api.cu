@@ -11,6 +11,7 @@
 #include "hb_common.cuh"
 #include "hb_mpc.cuh"
 #include "hb_planner.h"
+#include <thread>
 #include "hb_qp.cuh"
 #include "hb_rbd.cuh"
 #include "hb_sqp.cuh"
@@ -174,6 +175,40 @@ __global__ void policy_eval_kernel(int B, int N, double dt, double t_rel, const 
 __global__ void torque_kernel(int B, const double* sol, double* torque) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < B * NJ) { const int i = idx / NJ, j = idx - i * NJ; torque[idx] = sol[(size_t)i * NWBC + 28 + j]; }
+}
+
+// joint command law (LeggedController.cpp:186-257), one thread per instance; joints are visited in order because the limit
+// protection of joint j only affects the commands of joints >= j within the same cycle
+__global__ void joint_command_kernel(int B, hb_pd_gains g, double dt, const double* x_des, const double* u_des, const double* sol,
+                                     const int32_t* mode_cmd, const double* rbd, const uint8_t* loaded, uint8_t* estop, double* command,
+                                     double* out_tau) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= B) return;
+  const double* xd = x_des + (size_t)inst * NX; const double* ud = u_des + (size_t)inst * NU;
+  const double* ws = sol + (size_t)inst * NWBC; const double* r = rbd + (size_t)inst * 32;
+  const bool is_loaded = loaded ? loaded[inst] != 0 : true;
+  bool stop = estop ? estop[inst] != 0 : false;
+  const int mode = mode_cmd[inst];
+  for (int j = 0; j < NJ; ++j) {
+    const double q = r[6 + j], qd = r[NQ + 6 + j];
+    if (!stop && is_loaded && (q > c_model.joint_upper[j] + 0.02 || q < c_model.joint_lower[j] - 0.02)) stop = true;
+    double pd, vd, kp, kd, ff;
+    if (!is_loaded) {
+      pd = xd[12 + j]; vd = ud[12 + j]; kp = g.kp_position; kd = (j == 4 || j == 9) ? g.kd_feet : g.kd_position; ff = 0.0;
+    } else {
+      const double qdd = ws[6 + j];
+      pd = xd[12 + j] + 0.5 * qdd * dt * dt; vd = ud[12 + j] + qdd * dt; ff = ws[28 + j];
+      const bool contact = contact_flag(mode, j / 5);
+      if (j == 0 || j == 1 || j == 5 || j == 6) { kp = contact ? g.kp_small_stance : g.kp_small_swing; kd = g.kd_small; }
+      else if (j == 4 || j == 9) { kp = contact ? g.kp_small_stance : g.kp_small_swing; kd = g.kd_feet; }
+      else { kp = contact ? g.kp_big_stance : g.kp_big_swing; kd = g.kd_big; }
+    }
+    if (stop) { pd = 0.0; vd = 0.0; kp = 0.0; kd = 1.0; ff = 0.0; }
+    double* c = command + ((size_t)inst * NJ + j) * 5;
+    c[0] = pd; c[1] = vd; c[2] = kp; c[3] = kd; c[4] = ff;
+    out_tau[(size_t)inst * NJ + j] = ff + kp * (pd - q) + kd * (vd - qd);
+  }
+  if (estop) estop[inst] = stop ? 1 : 0;
 }
 
 // computeCentroidalStateFromRbdModel (LeggedController.cpp:336)
@@ -632,6 +667,28 @@ int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0
   return HB_OK;
 }
 
+int hb_default_pd_gains(hb_pd_gains* g) {
+  if (!g) return HB_EINVAL;
+  g->kp_position = 10.0; g->kd_position = 3.0;
+  g->kp_big_stance = 40.0; g->kp_big_swing = 30.0; g->kd_big = 2.0;
+  g->kp_small_stance = 30.0; g->kp_small_swing = 20.0; g->kd_small = 2.0;
+  g->kd_feet = 0.01;
+  return HB_OK;
+}
+
+int hb_joint_command_batch_dev(hb_ctx* ctx, int B, const hb_pd_gains* gains, double period, const double* x_des, const double* u_des,
+                               const double* wbc_sol, const int32_t* mode_cmd, const double* rbd, const uint8_t* loaded, uint8_t* estop,
+                               double* command, double* output_torque) {
+  if (!ctx || B < 0 || !gains || !x_des || !u_des || !wbc_sol || !mode_cmd || !rbd || !command || !output_torque) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  joint_command_kernel<<<(B + 63) / 64, 64, 0, ctx->stream>>>(B, *gains, period, x_des, u_des, wbc_sol, mode_cmd, rbd, loaded, estop, command,
+                                                             output_torque);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
 int hb_rbd_to_centroidal_batch_dev(hb_ctx* ctx, int B, const double* rbd, double* x) {
   if (!ctx || B < 0 || !rbd || !x) return HB_EINVAL;
   if (B == 0) return HB_OK;
@@ -793,6 +850,27 @@ int hb_control_step_batch(hb_ctx* ctx, int B, double t_rel, const double* x0, co
   return HB_OK;
 }
 
+int hb_joint_command_batch(hb_ctx* ctx, int B, const hb_pd_gains* gains, double period, const double* x_des, const double* u_des,
+                           const double* wbc_sol, const int32_t* mode_cmd, const double* rbd, const uint8_t* loaded, uint8_t* estop,
+                           double* command, double* output_torque) {
+  if (!ctx || B < 0 || !gains || !x_des || !u_des || !wbc_sol || !mode_cmd || !rbd || !command || !output_torque) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  H2D(ctx->s_xd, x_des, sizeof(double) * B * NX); H2D(ctx->s_ud, u_des, sizeof(double) * B * NU); H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32);
+  H2D(ctx->s_sol, wbc_sol, sizeof(double) * B * NWBC); H2D(ctx->s_imode, mode_cmd, sizeof(int32_t) * B);
+  uint8_t* d_loaded = (uint8_t*)ctx->s_status;      // B int32 words: room for two B-byte flag arrays
+  uint8_t* d_estop = d_loaded + B;
+  if (loaded) H2D(d_loaded, loaded, B);
+  if (estop) H2D(d_estop, estop, B);
+  int rc = hb_joint_command_batch_dev(ctx, B, gains, period, ctx->s_xd, ctx->s_ud, ctx->s_sol, ctx->s_imode, ctx->s_rbd, loaded ? d_loaded : nullptr,
+                                      estop ? d_estop : nullptr, ctx->s_misc, ctx->s_tau);
+  if (rc) return rc;
+  D2H(command, ctx->s_misc, sizeof(double) * B * NJ * 5); D2H(output_torque, ctx->s_tau, sizeof(double) * B * NJ);
+  if (estop) D2H(estop, d_estop, B);
+  return hb_sync(ctx);
+}
+
 int hb_rbd_to_centroidal_batch(hb_ctx* ctx, int B, const double* rbd, double* x) {
   if (!ctx || B < 0 || !rbd || !x) return HB_EINVAL;
   if (B == 0) return HB_OK;
@@ -831,9 +909,8 @@ int hb_contact_positions_batch(hb_ctx* ctx, int B, const double* x, double* pos)
   return hb_sync(ctx);
 }
 
-int hb_plan_references(int B, const hb_plan_input* in, double* latest_stance, hb_reference* out) {
-  if (B < 0 || !in || !latest_stance || !out) return HB_EINVAL;
-  for (int i = 0; i < B; ++i) {
+static int plan_range(int lo, int hi, const hb_plan_input* in, double* latest_stance, hb_reference* out) {
+  for (int i = lo; i < hi; ++i) {
     const hb_plan_input& p = in[i];
     if (!(p.horizon > 0.0) || !(p.prev_event < p.gait_start) || p.gait < 0 || p.gait > 3) return HB_EINVAL;
     const double tf = p.t0 + p.horizon;
@@ -843,7 +920,38 @@ int hb_plan_references(int B, const hb_plan_input* in, double* latest_stance, hb
     const double body_vel_cmd[6] = {p.cmd_vel[0], p.cmd_vel[1], p.cmd_vel[2], p.cmd_vel[3], 0.0, 0.0};
     hbplan::SwingPlan sp;
     if (!hbplan::plan_swing(ms, tg, p.t0, p.feet_pos, body_vel_cmd, latest_stance + (size_t)i * 12, sp)) return HB_EPLAN;
+    if (p.joint_ik && !hbplan::joint_references(sp, p.t0, tf, p.x0, tg)) return HB_EPLAN;
     if (hbplan::fill_reference(ms, tg, sp, p.t0 - 1e-9, tf + 1e-9, out + i) != 0) return HB_EPLAN;
+  }
+  return HB_OK;
+}
+
+int hb_plan_references(int B, const hb_plan_input* in, double* latest_stance, hb_reference* out) {
+  if (B < 0 || !in || !latest_stance || !out) return HB_EINVAL;
+  // instances are independent: spread them over the host cores (the planner feeds ~1e5 solves/s per GPU; one core plans ~2e4/s)
+  unsigned hw = std::thread::hardware_concurrency();
+  if (const char* e = getenv("HB_PLAN_THREADS")) hw = (unsigned)atoi(e);
+  int nt = (int)std::min<unsigned>(hw ? hw : 1u, (unsigned)((B + 63) / 64));
+  if (nt <= 1) return plan_range(0, B, in, latest_stance, out);
+  std::vector<std::thread> pool;
+  std::vector<int> rcs(nt, HB_OK);
+  for (int t = 0; t < nt; ++t) {
+    const int lo = (int)((long long)B * t / nt), hi = (int)((long long)B * (t + 1) / nt);
+    pool.emplace_back([=, &rcs]() { rcs[t] = plan_range(lo, hi, in, latest_stance, out); });
+  }
+  for (auto& th : pool) th.join();
+  for (int t = 0; t < nt; ++t) if (rcs[t]) return rcs[t];
+  return HB_OK;
+}
+
+int hb_gait_select(int B, hb_gait_selector* state, const int32_t* gait_type, const double* cmd_vel, const double* target_state0, int32_t* level,
+                   int32_t* insert) {
+  if (B < 0 || !state || !gait_type || !cmd_vel || !target_state0 || !level || !insert) return HB_EINVAL;
+  for (int i = 0; i < B; ++i) {
+    if (state[i].head < 0 || state[i].head >= 50 || state[i].count < 0 || state[i].count > 50) return HB_EINVAL;
+    int ins = 0;
+    level[i] = hbplan::gait_select(state + i, gait_type[i], cmd_vel + (size_t)i * 4, target_state0 + (size_t)i * 22, &ins);
+    insert[i] = ins;
   }
   return HB_OK;
 }

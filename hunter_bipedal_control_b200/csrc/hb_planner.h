@@ -5,7 +5,9 @@
 //       CubicSpline nodes (time, position, velocity)                              legged_interface/src/foot_planner/CubicSpline.cpp:46-70
 //   P5  cmdVelToTargetTrajectories / targetPoseToTargetTrajectories               legged_controllers/src/TargetTrajectoriesPublisher.cpp:41-130
 // The output is the compact hb_reference consumed by hb_reference_expand_batch (device). P2 (speed-based gait switching) is a
-// caller decision (the gait id is an input) and P4 (IK joint references) is "next" (targets carry the default joint angles).
+//   P4  calculateJointRef + InverseKinematics::computeIK                        legged_interface/src/SwitchedModelReferenceManager.cpp:251-300,
+//                                                                                 src/foot_planner/InverseKinematics.cpp:20-231
+//   P2  calculateVelAbs / walkGait (speed-based gait selection)                   legged_interface/src/SwitchedModelReferenceManager.cpp:185-249
 #pragma once
 #include <math.h>
 #include <string.h>
@@ -73,7 +75,7 @@ inline int mode_at(const ModeSchedule& ms, double t) {
   return ms.modes[idx];
 }
 
-struct Target { double t[2]; double x[2][22]; };
+struct Target { int n; double t[HB_MAX_TARGETS]; double x[HB_MAX_TARGETS][22]; };
 
 // cmdVelToTargetTrajectories (TargetTrajectoriesPublisher.cpp:102-130) with targetPoseToTargetTrajectories (:41-62)
 inline Target cmd_vel_to_target(const double* cmd /*vx,vy,vz,wz*/, double time, const double* state, double time_to_target) {
@@ -87,6 +89,7 @@ inline Target cmd_vel_to_target(const double* cmd /*vx,vy,vz,wz*/, double time, 
   dz = dz > 0 ? fmin(dz, 0.04) : fmax(dz, -0.04);      // changeLimit_[2] (TargetTrajectoriesPublisher.h:97)
   cur[2] = pose[2] + dz;
   Target tg;
+  tg.n = 2;
   tg.t[0] = time; tg.t[1] = time + time_to_target;
   for (int k = 0; k < 2; ++k) {
     for (int i = 0; i < 22; ++i) tg.x[k][i] = 0.0;
@@ -97,11 +100,14 @@ inline Target cmd_vel_to_target(const double* cmd /*vx,vy,vz,wz*/, double time, 
   return tg;
 }
 
+// TargetTrajectories::getDesiredState: piecewise-linear, clamped at both ends
 inline void target_state(const Target& tg, double t, double* x) {
-  if (t <= tg.t[0]) { memcpy(x, tg.x[0], sizeof(double) * 22); return; }
-  if (t >= tg.t[1]) { memcpy(x, tg.x[1], sizeof(double) * 22); return; }
-  const double a = (t - tg.t[0]) / (tg.t[1] - tg.t[0]);
-  for (int i = 0; i < 22; ++i) x[i] = (1.0 - a) * tg.x[0][i] + a * tg.x[1][i];
+  if (tg.n <= 1 || t <= tg.t[0]) { memcpy(x, tg.x[0], sizeof(double) * 22); return; }
+  if (t >= tg.t[tg.n - 1]) { memcpy(x, tg.x[tg.n - 1], sizeof(double) * 22); return; }
+  int s = 0;
+  while (s + 2 < tg.n && tg.t[s + 1] <= t) ++s;
+  const double a = (t - tg.t[s]) / (tg.t[s + 1] - tg.t[s]);
+  for (int i = 0; i < 22; ++i) x[i] = (1.0 - a) * tg.x[s][i] + a * tg.x[s + 1][i];
 }
 
 struct Node { double t, p, v; };
@@ -209,6 +215,302 @@ inline bool plan_swing(const ModeSchedule& ms, const Target& tg, double init_tim
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// P4: joint references by inverse kinematics (SwitchedModelReferenceManager::calculateJointRef, SwitchedModelReferenceManager.cpp:251-300;
+// InverseKinematics::{computeIK, computeTranslationIK, computeRotationIK}, foot_planner/InverseKinematics.cpp:20-231).
+// The Eigen solvers the reference calls are restated by what they compute:
+//   ColPivHouseholderQR(threshold 0.01)::solve  -> pivot on the largest residual column norm, rank = #pivots > 0.01 * first pivot,
+//                                                  least squares on the pivot columns, zeros elsewhere (basic solution);
+//   FullPivLU::kernel                           -> e_j - sum_P (J_P^-1 J_j)_p e_p for every non-pivot column j, pivot columns P chosen by
+//                                                  complete pivoting.
+
+struct LegKin { double toe[3]; double R[9]; double Jl[15]; double Ja[15]; };   // Jl, Ja: 3x5 row-major, world axes
+
+inline void mat3_mul(const double* A, const double* B, double* C) {
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+inline void rot_zyx_mat(const double* e, double* R) {
+  const double cz = cos(e[0]), sz = sin(e[0]), cy = cos(e[1]), sy = sin(e[1]), cx = cos(e[2]), sx = sin(e[2]);
+  const double M[9] = {cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx, sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx, -sy, cy * sx, cy * cx};
+  memcpy(R, M, sizeof(M));
+}
+inline void axis_angle(const double* a, double q, double* R) {   // Rodrigues, unit axis
+  const double c = cos(q), s = sin(q), v = 1.0 - c;
+  const double M[9] = {c + a[0] * a[0] * v, a[0] * a[1] * v - a[2] * s, a[0] * a[2] * v + a[1] * s,
+                       a[1] * a[0] * v + a[2] * s, c + a[1] * a[1] * v, a[1] * a[2] * v - a[0] * s,
+                       a[2] * a[0] * v - a[1] * s, a[2] * a[1] * v + a[0] * s, c + a[2] * a[2] * v};
+  memcpy(R, M, sizeof(M));
+}
+
+// forward kinematics and frame Jacobian of the toe contact frame of leg (0 left, 1 right): pose = [p(3), zyx(3)], qj = 5 leg joints
+inline void leg_kin(int leg, const double* pose, const double* qj, LegKin& k) {
+  double R[9], o[3] = {pose[0], pose[1], pose[2]}, orig[5][3], ax[5][3];
+  rot_zyx_mat(pose + 3, R);
+  for (int i = 0; i < 5; ++i) {
+    const int b = 1 + 5 * leg + i;
+    const double* xyz = HB_JOINT_XYZ + 3 * b; const double* a = HB_JOINT_AXIS + 3 * b;
+    for (int r = 0; r < 3; ++r) o[r] += R[3 * r] * xyz[0] + R[3 * r + 1] * xyz[1] + R[3 * r + 2] * xyz[2];
+    for (int r = 0; r < 3; ++r) { orig[i][r] = o[r]; ax[i][r] = R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2]; }
+    double Rj[9], Rn[9];
+    axis_angle(a, qj[i], Rj);
+    mat3_mul(R, Rj, Rn);
+    memcpy(R, Rn, sizeof(Rn));
+  }
+  const double* off = HB_CONTACT_OFFSET + 3 * leg;      // contacts 0 / 1 = left / right toe
+  for (int r = 0; r < 3; ++r) k.toe[r] = o[r] + R[3 * r] * off[0] + R[3 * r + 1] * off[1] + R[3 * r + 2] * off[2];
+  memcpy(k.R, R, sizeof(R));
+  for (int i = 0; i < 5; ++i) {
+    const double d[3] = {k.toe[0] - orig[i][0], k.toe[1] - orig[i][1], k.toe[2] - orig[i][2]};
+    k.Jl[i] = ax[i][1] * d[2] - ax[i][2] * d[1];
+    k.Jl[5 + i] = ax[i][2] * d[0] - ax[i][0] * d[2];
+    k.Jl[10 + i] = ax[i][0] * d[1] - ax[i][1] * d[0];
+    for (int r = 0; r < 3; ++r) k.Ja[5 * r + i] = ax[i][r];
+  }
+}
+
+// x = ColPivHouseholderQR(A (m x n, row-major, m <= 3, n <= 5), threshold).solve(b)
+inline void qrcp_solve(const double* A, int m, int n, const double* b, double threshold, double* x) {
+  double Q[3][3];            // orthonormal directions of the chosen columns
+  double coef[3];            // b components along them
+  int piv[3]; double R[3][3] = {{0}};
+  bool used[5] = {false, false, false, false, false};
+  double first = 0.0; int rank = 0;
+  const int kmax = m < n ? m : n;
+  for (int k = 0; k < kmax; ++k) {
+    int best = -1; double bn = -1.0; double bres[3] = {0, 0, 0};
+    for (int j = 0; j < n; ++j) {
+      if (used[j]) continue;
+      double r[3] = {0, 0, 0};
+      for (int i = 0; i < m; ++i) r[i] = A[i * n + j];
+      for (int t = 0; t < k; ++t) { double d = 0; for (int i = 0; i < m; ++i) d += Q[t][i] * r[i]; for (int i = 0; i < m; ++i) r[i] -= d * Q[t][i]; }
+      double nn = 0; for (int i = 0; i < m; ++i) nn += r[i] * r[i];
+      if (nn > bn) { bn = nn; best = j; for (int i = 0; i < m; ++i) bres[i] = r[i]; }
+    }
+    const double pv = sqrt(bn > 0 ? bn : 0.0);
+    if (k == 0) first = pv;
+    if (!(pv > threshold * first) || pv == 0.0) break;
+    used[best] = true; piv[k] = best;
+    for (int i = 0; i < m; ++i) Q[k][i] = bres[i] / pv;
+    for (int t = 0; t <= k; ++t) { double d = 0; for (int i = 0; i < m; ++i) d += Q[t][i] * A[i * n + best]; R[t][k] = d; }
+    double d = 0; for (int i = 0; i < m; ++i) d += Q[k][i] * b[i];
+    coef[k] = d;
+    rank = k + 1;
+  }
+  for (int j = 0; j < n; ++j) x[j] = 0.0;
+  for (int k = rank - 1; k >= 0; --k) {          // back substitution R y = Q^T b on the pivot columns
+    double v = coef[k];
+    for (int t = k + 1; t < rank; ++t) v -= R[k][t] * x[piv[t]];
+    x[piv[k]] = v / R[k][k];
+  }
+}
+
+// FullPivLU(J (3x5)).kernel(): returns the kernel dimension (5 - rank), N is 5 x dim row-major (ld 3)
+inline int fullpiv_kernel(const double* J, double* N) {
+  double M[3][5]; int colp[5] = {0, 1, 2, 3, 4};
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 5; ++j) M[i][j] = J[5 * i + j];
+  int rank = 0; double maxpiv = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    int bi = k, bj = k; double bv = -1.0;
+    for (int i = k; i < 3; ++i) for (int j = k; j < 5; ++j) if (fabs(M[i][j]) > bv) { bv = fabs(M[i][j]); bi = i; bj = j; }
+    if (bv <= 0.0) break;
+    if (k == 0) maxpiv = bv;
+    for (int j = 0; j < 5; ++j) std::swap(M[k][j], M[bi][j]);
+    for (int i = 0; i < 3; ++i) std::swap(M[i][k], M[i][bj]);
+    std::swap(colp[k], colp[bj]);
+    // Eigen's default rank threshold: |pivot| > eps * diagonal size * max pivot
+    if (bv > 2.220446049250313e-16 * 3.0 * maxpiv) rank = k + 1; else break;
+    for (int i = k + 1; i < 3; ++i) { const double f = M[i][k] / M[k][k]; for (int j = k; j < 5; ++j) M[i][j] -= f * M[k][j]; }
+  }
+  const int dim = 5 - rank;
+  for (int i = 0; i < 15; ++i) N[i] = 0.0;
+  for (int c = 0; c < dim; ++c) {
+    // solve U11 y = -U12[:, c] (upper triangular, rank x rank)
+    double y[3] = {0, 0, 0};
+    for (int k = rank - 1; k >= 0; --k) {
+      double v = -M[k][rank + c];
+      for (int t = k + 1; t < rank; ++t) v -= M[k][t] * y[t];
+      y[k] = v / M[k][k];
+    }
+    for (int k = 0; k < rank; ++k) N[3 * colp[k] + c] = y[k];
+    N[3 * colp[rank + c] + c] = 1.0;
+  }
+  return dim;
+}
+
+// pinocchio::log3
+inline void log3(const double* R, double* w) {
+  const double tr = R[0] + R[4] + R[8];
+  const double PI_ = 3.14159265358979323846;
+  double theta;
+  if (tr >= 3.0) theta = 0.0; else if (tr <= -1.0) theta = PI_; else theta = acos((tr - 1.0) * 0.5);
+  const double v[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+  if (theta >= PI_ - 1e-2) {
+    // near pi: axis from the diagonal, signs from the skew part
+    const double c = cos(theta) , s = sin(theta), t1 = 1.0 - c;
+    const double k = theta;
+    (void)s;
+    for (int i = 0; i < 3; ++i) {
+      const double d = (R[4 * i] - c) / t1;
+      const double a = sqrt(d > 0 ? d : 0.0);
+      w[i] = k * (v[i] >= 0 ? a : -a);
+    }
+    return;
+  }
+  const double f = (theta > 1e-8) ? theta / (2.0 * sin(theta)) : 0.5 * (1.0 + theta * theta / 6.0);
+  for (int i = 0; i < 3; ++i) w[i] = f * v[i];
+}
+
+inline double norm3(const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+// InverseKinematics::computeTranslationIK (InverseKinematics.cpp:37-127)
+inline void translation_ik(int leg, const double* pose, double* qj, const double* des) {
+  const double err_tol = 0.01, conv_tol = 0.001, dt = 0.7; const int max_it = 5;
+  LegKin k; leg_kin(leg, pose, qj, k);
+  double err[3] = {k.toe[0] - des[0], k.toe[1] - des[1], k.toe[2] - des[2]};
+  double last = norm3(err);
+  if (last < err_tol) return;
+  int it = 0;
+  while (true) {
+    double vi[5], nq[5];
+    qrcp_solve(k.Jl, 3, 5, err, 0.01, vi);
+    for (int i = 0; i < 5; ++i) {
+      nq[i] = qj[i] - dt * vi[i];
+      nq[i] = std::max(HB_JOINT_LOWER[5 * leg + i], nq[i]);
+      nq[i] = std::min(HB_JOINT_UPPER[5 * leg + i], nq[i]);
+    }
+    LegKin kn; leg_kin(leg, pose, nq, kn);
+    for (int r = 0; r < 3; ++r) err[r] = kn.toe[r] - des[r];
+    const double en = norm3(err);
+    if (en > last) break;
+    if (fabs(en - last) < conv_tol) break;
+    last = en;
+    for (int i = 0; i < 5; ++i) qj[i] = nq[i];
+    k = kn;
+    if (en < err_tol) break;
+    if (++it >= max_it) break;
+  }
+}
+
+// InverseKinematics::computeRotationIK (:135-231): orientation error reduced inside the kernel of the translational Jacobian
+inline void rotation_ik(int leg, const double* pose, double* qj, const double* Rdes) {
+  const double err_tol = 0.01, conv_tol = 0.001, dt = 0.7; const int max_it = 5;
+  auto rot_err = [&](const LegKin& k, double* e) {
+    double M[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M[3 * i + j] = Rdes[i] * k.R[j] + Rdes[3 + i] * k.R[3 + j] + Rdes[6 + i] * k.R[6 + j];   // Rdes^T R
+    log3(M, e);
+  };
+  LegKin k; leg_kin(leg, pose, qj, k);
+  double err[3]; rot_err(k, err);
+  double last = norm3(err);
+  if (last < err_tol) return;
+  int it = 0;
+  while (true) {
+    // LOCAL frame Jacobians: rows rotated by R^T (the kernel of the linear part is unchanged by the rotation)
+    double Jll[15], Jal[15];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 5; ++c) {
+      Jll[5 * r + c] = k.R[r] * k.Jl[c] + k.R[3 + r] * k.Jl[5 + c] + k.R[6 + r] * k.Jl[10 + c];
+      Jal[5 * r + c] = k.R[r] * k.Ja[c] + k.R[3 + r] * k.Ja[5 + c] + k.R[6 + r] * k.Ja[10 + c];
+    }
+    double Nk[15];
+    const int dim = fullpiv_kernel(Jll, Nk);
+    double JN[9] = {0}, y[3] = {0, 0, 0}, vi[5] = {0, 0, 0, 0, 0};
+    if (dim > 0) {
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < dim; ++c) { double d = 0; for (int j = 0; j < 5; ++j) d += Jal[5 * r + j] * Nk[3 * j + c]; JN[r * dim + c] = d; }
+      qrcp_solve(JN, 3, dim, err, 0.01, y);
+      for (int j = 0; j < 5; ++j) { double d = 0; for (int c = 0; c < dim; ++c) d += Nk[3 * j + c] * y[c]; vi[j] = -d; }
+    }
+    double nq[5];
+    for (int i = 0; i < 5; ++i) {
+      nq[i] = qj[i] + dt * vi[i];
+      nq[i] = std::max(HB_JOINT_LOWER[5 * leg + i], nq[i]);
+      nq[i] = std::min(HB_JOINT_UPPER[5 * leg + i], nq[i]);
+    }
+    LegKin kn; leg_kin(leg, pose, nq, kn);
+    rot_err(kn, err);
+    const double en = norm3(err);
+    if (en > last) break;
+    if (fabs(en - last) < conv_tol) break;
+    last = en;
+    for (int i = 0; i < 5; ++i) qj[i] = nq[i];
+    k = kn;
+    if (en < err_tol) break;
+    if (++it >= max_it) break;
+  }
+}
+
+inline double swing_value(const SwingPlan& sp, int c, int a, double t) {
+  const std::vector<Seg>& v = sp.seg[c][a];
+  size_t s = 0;
+  while (s + 1 < v.size() && t > v[s].t1) ++s;       // an event time belongs to the earlier phase (lookup::findIndexInTimeArray)
+  const Seg& g = v[s];
+  const double T = g.t1 - g.t0, tn = (t - g.t0) / T, dp = g.p1 - g.p0, dv = g.v1 - g.v0;
+  const double c0 = g.p0, c1 = g.v0 * T, c2 = -(3.0 * g.v0 + dv) * T + 3.0 * dp, c3 = (2.0 * g.v0 + dv) * T - 2.0 * dp;
+  return ((c3 * tn + c2) * tn + c1) * tn + c0;
+}
+
+// SwitchedModelReferenceManager::calculateJointRef (:251-300): resample the target every 0.15 s and replace the joint part by IK on the
+// planned toe positions, each sample seeded by the previous one. Returns false when the sample count exceeds HB_MAX_TARGETS.
+inline bool joint_references(const SwingPlan& sp, double init_time, double final_time, const double* init_state, Target& tg) {
+  if (tg.n <= 1) return true;
+  const double step = 0.15;
+  const int n = (int)floor((final_time - init_time) / step) + 1;
+  if (n <= 2) return true;
+  if (n > HB_MAX_TARGETS) return false;
+  double Rdes[9];
+  rot_zyx_mat(init_state + 9, Rdes);
+  Target old = tg;
+  tg.n = n;
+  for (int i = 0; i < n; ++i) {
+    // Eigen LinSpaced: low + i * (high - low) / (n - 1), the last point set to high
+    tg.t[i] = (i == n - 1) ? final_time : init_time + i * ((final_time - init_time) / (n - 1));
+    target_state(old, tg.t[i], tg.x[i]);
+  }
+  for (int j = 0; j < 10; ++j) tg.x[0][12 + j] = HB_DEFAULT_JOINT_STATE[j];
+  for (int i = 0; i < n; ++i) {
+    const double* pose = tg.x[i] + 6;
+    double seed[10];
+    memcpy(seed, tg.x[i > 0 ? i - 1 : 0] + 12, sizeof(seed));
+    for (int leg = 0; leg < 2; ++leg) {
+      const double des[3] = {swing_value(sp, leg, 0, tg.t[i]), swing_value(sp, leg, 1, tg.t[i]), swing_value(sp, leg, 2, tg.t[i])};
+      double qj[5];
+      memcpy(qj, seed + 5 * leg, sizeof(qj));
+      translation_ik(leg, pose, qj, des);
+      rotation_ik(leg, pose, qj, Rdes);
+      memcpy(tg.x[i] + 12 + 5 * leg, qj, sizeof(qj));
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// P2: speed-based gait selection (SwitchedModelReferenceManager::{calculateVelAbs, walkGait, trotGait}, :185-249).
+// Returns the gait level after the update (0 stance, 1 trot, 3 "flying trot" level which inserts no template in the reference) and sets
+// *insert to 1 when the reference would insert a template on this call (stance or trot), 0 otherwise. The reference leaves velAvg_
+// uninitialised before the first call; here the history starts empty, which gives the same values from the first call on.
+inline int gait_select(hb_gait_selector* st, int gait_type, const double* cmd_vel /*vx,vy,vz,wz*/, const double* target0 /*22*/, int* insert) {
+  Vec3 c = rot_zyx(target0 + 9, {cmd_vel[0], cmd_vel[1], cmd_vel[2]});
+  const double vc[4] = {c.x, c.y, 0.0, cmd_vel[3] / 3.0};
+  const double ve[4] = {target0[0], target0[1], 0.0, target0[3] / 3.0};
+  double s2 = 0.0;
+  for (int i = 0; i < 4; ++i) { const double m = 0.5 * vc[i] + 0.5 * ve[i]; s2 += m * m; }
+  const double vel_abs = sqrt(s2);
+  st->history[st->head] = vel_abs;                       // ring buffer of the 50 most recent samples
+  st->head = (st->head + 1) % 50;
+  if (st->count < 50) st->count++;
+  double sum = 0.0;
+  for (int i = 0; i < st->count; ++i) sum += st->history[i];
+  st->vel_avg = sum / st->count;
+  *insert = 0;
+  if (gait_type == 0) {                                  // walkGait
+    if (st->vel_avg <= 0.02) { if (st->gait_level != 0) { *insert = 1; st->gait_level = 0; } }
+    else if (st->vel_avg > 0.03 && st->vel_avg < 0.4) { if (st->gait_level != 1) { *insert = 1; st->gait_level = 1; } }
+    else if (st->vel_avg >= 0.4) { if (st->gait_level != 3) st->gait_level = 3; }
+  } else if (gait_type == 2) {                           // trotGait
+    if (st->gait_level != 1) { *insert = 1; st->gait_level = 1; }
+  }
+  return st->gait_level;
+}
+
 inline int fill_reference(const ModeSchedule& ms, const Target& tg, const SwingPlan& sp, double t_lo, double t_hi, hb_reference* out) {
   memset(out, 0, sizeof(*out));
   // mode schedule restricted to the window (events strictly inside), keeping the mode in force at t_lo
@@ -221,8 +523,8 @@ inline int fill_reference(const ModeSchedule& ms, const Target& tg, const SwingP
   out->n_events = ne;
   for (int i = 0; i < ne; ++i) out->event_times[i] = ms.events[first + i];
   for (int i = 0; i <= ne; ++i) out->modes[i] = ms.modes[first + i];
-  out->n_targets = 2;
-  for (int k = 0; k < 2; ++k) { out->target_times[k] = tg.t[k]; memcpy(out->target_states[k], tg.x[k], sizeof(double) * 22); }
+  out->n_targets = tg.n;
+  for (int k = 0; k < tg.n; ++k) { out->target_times[k] = tg.t[k]; memcpy(out->target_states[k], tg.x[k], sizeof(double) * 22); }
   for (int c = 0; c < 4; ++c)
     for (int a = 0; a < 3; ++a) {
       int n = 0;

@@ -11,6 +11,9 @@
  *   hb_mpc_cold_start_batch <-> LeggedRobotInitializer::compute       legged_interface/src/initialization/LeggedRobotInitializer.cpp:67-77
  *   hb_policy_eval_batch    <-> MPC_MRT_Interface::evaluatePolicy     legged_controllers/src/LeggedController.cpp:154-156
  *   hb_control_step_batch   <-> LeggedController::update MPC->policy->WBC->torque law   LeggedController.cpp:137-257
+ *   hb_joint_command_batch  <-> joint command / torque law            LeggedController.cpp:186-257
+ *   hb_plan_references      <-> GaitSchedule tiling + SwingTrajectoryPlanner::update + cmdVelToTargetTrajectories + calculateJointRef
+ *   hb_gait_select          <-> SwitchedModelReferenceManager::calculateVelAbs + walkGait/trotGait   :185-249
  *   hb_rbd_to_centroidal_batch <-> CentroidalModelRbdConversions::computeCentroidalStateFromRbdModel  LeggedController.cpp:336
  *   hb_reference_expand_batch  <-> SwitchedModelReferenceManager::modifyReferences (gait tiling, swing planner, target
  *                               interpolation, evaluated on the node grid)   legged_interface/src/SwitchedModelReferenceManager.cpp:136-171
@@ -54,7 +57,7 @@ typedef struct {
 
 /* compact per-instance reference description consumed by hb_reference_expand_batch */
 #define HB_MAX_EVENTS 32
-#define HB_MAX_TARGETS 8
+#define HB_MAX_TARGETS 16
 #define HB_MAX_SEGMENTS 24
 typedef struct {
   int32_t n_events;                       /* mode schedule: modes[i] holds on (event_times[i-1], event_times[i]] */
@@ -78,9 +81,30 @@ typedef struct {
   double cmd_vel[4];      /* filtered command: vx, vy, vz, yaw rate (body frame)                          */
   double feet_pos[12];    /* current contact positions in world (hb_contact_positions_batch)              */
   int32_t gait;           /* 0 stance, 1 trot, 2 standing_trot, 3 flying_trot (reference.info:54-118)     */
-  int32_t reserved;
+  int32_t joint_ik;       /* 1: resample the target every 0.15 s and fill joint references by IK (calculateJointRef,
+                             SwitchedModelReferenceManager.cpp:251-300); 0: keep the two-sample target with default joints */
 } hb_plan_input;
 
+/* state of the speed-based gait selection of one instance (SwitchedModelReferenceManager velAbsHistory_/velAvg_/gaitLevel_);
+ * zero-initialise, then set gait_level = -1 ("no template chosen yet") or the level in force */
+typedef struct {
+  double history[50];
+  double vel_avg;
+  int32_t head, count;
+  int32_t gait_level;
+  int32_t reserved;
+} hb_gait_selector;
+
+/* joint PD gains of the command law (dynamic_reconfigure parameters, legged_controllers/cfg/Tutorials.cfg:6-16,
+ * LeggedController.cpp:431-447) */
+typedef struct {
+  double kp_position, kd_position;            /* before the controller is loaded                     */
+  double kp_big_stance, kp_big_swing, kd_big; /* hip pitch / knee (joints 2,3,7,8)                   */
+  double kp_small_stance, kp_small_swing, kd_small; /* hip roll / yaw (0,1,5,6) and ankle kp (4,9)   */
+  double kd_feet;                             /* ankle (4,9)                                         */
+} hb_pd_gains;
+
+int hb_default_pd_gains(hb_pd_gains* g);
 int hb_default_config(hb_config* cfg);
 int hb_create(const hb_config* cfg, int device, hb_ctx** out);
 int hb_destroy(hb_ctx* ctx);
@@ -111,6 +135,13 @@ int hb_policy_eval_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x_t
 int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0, const double* x_ref, const double* swing_ref,
                               const int32_t* mode, const double* rbd, double* x_traj, double* u_traj, hb_solve_info* info,
                               double* wbc_sol, double* torque, int32_t* wbc_status);
+/* joint command law (LeggedController.cpp:186-257): posDes = q_mpc + 0.5 qdd dt^2, velDes = qd_mpc + qdd dt, gains by joint class
+ * and planned contact state of the leg, feed-forward = WBC torque; joint-limit protection sets the per-instance emergency stop flag
+ * (in/out) which turns the command into pure damping (0,0,0,1,0). loaded[i] = 0 selects the pre-load position hold (:211-222).
+ * command: B x 10 x 5 = (posDes, velDes, kp, kd, ff) per joint; output_torque: B x 10 = ff + kp (posDes - q) + kd (velDes - qd). */
+int hb_joint_command_batch_dev(hb_ctx* ctx, int B, const hb_pd_gains* gains, double period, const double* x_des, const double* u_des,
+                               const double* wbc_sol, const int32_t* mode_cmd, const double* rbd, const uint8_t* loaded, uint8_t* estop,
+                               double* command, double* output_torque);
 int hb_rbd_to_centroidal_batch_dev(hb_ctx* ctx, int B, const double* rbd, double* x);
 int hb_reference_expand_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                                   int32_t* mode);
@@ -131,6 +162,9 @@ int hb_mpc_solve_batch(hb_ctx* ctx, int B, const double* x0, const double* x_ref
 int hb_control_step_batch(hb_ctx* ctx, int B, double t_rel, const double* x0, const double* x_ref, const double* swing_ref,
                           const int32_t* mode, const double* rbd, double* x_traj, double* u_traj, hb_solve_info* info,
                           double* wbc_sol, double* torque, int32_t* wbc_status);
+int hb_joint_command_batch(hb_ctx* ctx, int B, const hb_pd_gains* gains, double period, const double* x_des, const double* u_des,
+                           const double* wbc_sol, const int32_t* mode_cmd, const double* rbd, const uint8_t* loaded, uint8_t* estop,
+                           double* command, double* output_torque);
 int hb_rbd_to_centroidal_batch(hb_ctx* ctx, int B, const double* rbd, double* x);
 int hb_reference_expand_batch(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                               int32_t* mode);
@@ -139,11 +173,18 @@ int hb_contact_positions_batch(hb_ctx* ctx, int B, const double* x, double* pos 
 
 /* ---- host-only reference preprocessing (no GPU work): gait tiling, swing-foot planner, cmd_vel target ----
  * replaces GaitSchedule::{insert,tile}ModeSequenceTemplate (legged_interface/src/gait/GaitSchedule.cpp:57-161),
- * SwingTrajectoryPlanner::update (src/foot_planner/SwingTrajectoryPlanner.cpp:164-286) and cmdVelToTargetTrajectories
- * (legged_controllers/src/TargetTrajectoriesPublisher.cpp:102-130). latest_stance (B x 12) is the planner's state, in/out.
+ * SwingTrajectoryPlanner::update (src/foot_planner/SwingTrajectoryPlanner.cpp:164-286), cmdVelToTargetTrajectories
+ * (legged_controllers/src/TargetTrajectoriesPublisher.cpp:102-130) and calculateJointRef + InverseKinematics::computeIK
+ * (src/SwitchedModelReferenceManager.cpp:251-300, src/foot_planner/InverseKinematics.cpp:20-231). latest_stance (B x 12) is the planner's state, in/out.
  * Returns 0, or -1 on misuse, or -5 when a schedule does not define the take-off / touch-down of a swing phase (the reference
  * throws there, SwingTrajectoryPlanner.cpp:421-458) or exceeds the capacity of hb_reference. */
 int hb_plan_references(int B, const hb_plan_input* in, double* latest_stance, hb_reference* out);
+/* speed-based gait selection (calculateVelAbs + walkGait / trotGait, src/SwitchedModelReferenceManager.cpp:185-249): updates the
+ * 50-sample moving average of 0.5*(command + target) speed of every instance and applies the thresholds stance <= 0.02 < (no change)
+ * <= 0.03 < trot < 0.4 <= level 3. gait_type: 0 walk (automatic), 2 trot (forced). level[i] = gait level in force after the call,
+ * insert[i] = 1 when a new template is inserted on this call. */
+int hb_gait_select(int B, hb_gait_selector* state, const int32_t* gait_type, const double* cmd_vel /*B x 4*/,
+                   const double* target_state0 /*B x 22*/, int32_t* level, int32_t* insert);
 
 #ifdef __cplusplus
 }

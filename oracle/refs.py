@@ -260,7 +260,152 @@ class SwingPlanner:
         return np.array([s.position(t) for s in sp]), np.array([s.velocity(t) for s in sp])
 
 
-def plan(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event=None, time_to_target=None, latest_stance=None):
+# ------------------------------------------------------------------------------------------------------------------------------
+# P4: joint references by inverse kinematics (SwitchedModelReferenceManager.cpp:251-300, InverseKinematics.cpp:20-231)
+JOINT_XYZ = np.array(_header_array("HB_JOINT_XYZ")).reshape(11, 3)
+JOINT_AXIS = np.array(_header_array("HB_JOINT_AXIS")).reshape(11, 3)
+CONTACT_OFFSET = np.array(_header_array("HB_CONTACT_OFFSET")).reshape(4, 3)
+JOINT_LOWER = np.array(_header_array("HB_JOINT_LOWER"))
+JOINT_UPPER = np.array(_header_array("HB_JOINT_UPPER"))
+
+
+def _rodrigues(a, q):
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + math.sin(q) * K + (1 - math.cos(q)) * (K @ K)
+
+
+def leg_frame(leg, pose, qj):
+    """Toe contact frame of leg (0 left, 1 right): position, rotation, world-aligned linear / angular Jacobians (3x5)."""
+    R = rot_zyx(pose[3:6]); o = np.array(pose[0:3], dtype=float)
+    origins, axes = [], []
+    for i in range(5):
+        b = 1 + 5 * leg + i
+        o = o + R @ JOINT_XYZ[b]
+        origins.append(o.copy()); axes.append(R @ JOINT_AXIS[b])
+        R = R @ _rodrigues(JOINT_AXIS[b], qj[i])
+    toe = o + R @ CONTACT_OFFSET[leg]
+    Jl = np.stack([np.cross(axes[i], toe - origins[i]) for i in range(5)], axis=1)
+    Ja = np.stack(axes, axis=1)
+    return toe, R, Jl, Ja
+
+
+def colpiv_qr_solve(A, b, threshold=0.01):
+    """Eigen::ColPivHouseholderQR(threshold).solve: LAPACK pivoted QR picks the same columns (largest remaining norm)."""
+    import scipy.linalg as sla
+    Q, Rm, P = sla.qr(A, mode="economic", pivoting=True)
+    d = np.abs(np.diag(Rm))
+    rank = int(np.sum(d > threshold * d[0])) if d[0] > 0 else 0
+    x = np.zeros(A.shape[1])
+    if rank:
+        c = Q[:, :rank].T @ b
+        x[P[:rank]] = sla.solve_triangular(Rm[:rank, :rank], c)
+    return x
+
+
+def fullpiv_lu_kernel(J):
+    """Eigen::FullPivLU::kernel: basis vectors e_j - sum_P (J_P^-1 J_j) e_p over the non-pivot columns j of complete pivoting."""
+    M = np.array(J, dtype=float); m, n = M.shape
+    cols = list(range(n)); rows = list(range(m))
+    for k in range(m):
+        sub = np.abs(M[k:, k:])
+        i, j = np.unravel_index(np.argmax(sub), sub.shape)
+        M[[k, k + i]] = M[[k + i, k]]; M[:, [k, k + j]] = M[:, [k + j, k]]
+        cols[k], cols[k + j] = cols[k + j], cols[k]
+        for r in range(k + 1, m):
+            M[r, k:] -= M[r, k] / M[k, k] * M[k, k:]
+    P, F = cols[:m], cols[m:]
+    N = np.zeros((n, n - m))
+    for c, j in enumerate(F):
+        N[P, c] = -np.linalg.solve(J[:, P], J[:, j])
+        N[j, c] = 1.0
+    return N
+
+
+def log3(R):
+    tr = np.trace(R)
+    theta = math.acos(max(-1.0, min(1.0, (tr - 1.0) / 2.0)))
+    v = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    f = theta / (2.0 * math.sin(theta)) if theta > 1e-8 else 0.5 * (1.0 + theta * theta / 6.0)
+    return f * v
+
+
+def _ik_loop(leg, qj, err_of, step_of):
+    err_tol, conv_tol, dt, max_it = 0.01, 0.001, 0.7, 5
+    lo, hi = JOINT_LOWER[5 * leg:5 * leg + 5], JOINT_UPPER[5 * leg:5 * leg + 5]
+    qj = np.array(qj, dtype=float)
+    err = err_of(qj); last = np.linalg.norm(err)
+    if last < err_tol:
+        return qj
+    it = 0
+    while True:
+        new_q = np.minimum(hi, np.maximum(lo, qj + dt * step_of(qj, err)))
+        err = err_of(new_q); en = np.linalg.norm(err)
+        if en > last or abs(en - last) < conv_tol:
+            break
+        last, qj = en, new_q
+        if en < err_tol:
+            break
+        it += 1
+        if it >= max_it:
+            break
+    return qj
+
+
+def translation_ik(pose, qj, leg, des_p):
+    def terr(q):
+        return leg_frame(leg, pose, q)[0] - des_p
+
+    def tstep(q, err):
+        return -colpiv_qr_solve(leg_frame(leg, pose, q)[2], err)
+
+    return _ik_loop(leg, qj, terr, tstep)
+
+
+def rotation_ik(pose, qj, leg, R_des):
+    def rerr(q):
+        return log3(R_des.T @ leg_frame(leg, pose, q)[1])
+
+    def rstep(q, err):
+        _, R, Jl, Ja = leg_frame(leg, pose, q)
+        N = fullpiv_lu_kernel(R.T @ Jl)
+        return -N @ colpiv_qr_solve((R.T @ Ja) @ N, err)
+
+    return _ik_loop(leg, qj, rerr, rstep)
+
+
+def compute_ik(pose, qj, leg, des_p, R_des):
+    return rotation_ik(pose, translation_ik(pose, qj, leg, des_p), leg, R_des)
+
+
+def joint_references(sp, tg, init_time, final_time, init_state):
+    """calculateJointRef: returns the resampled Target with IK joint references (or tg unchanged for short horizons)."""
+    n = int(math.floor((final_time - init_time) / 0.15)) + 1
+    if n <= 2:
+        return tg
+    Ts = [final_time if i == n - 1 else init_time + i * ((final_time - init_time) / (n - 1)) for i in range(n)]
+    states = [tg.state(t) for t in Ts]
+    states[0][12:22] = DEFAULT_JOINTS
+    R_des = rot_zyx(init_state[9:12])
+    for i in range(n):
+        seed = states[max(i - 1, 0)][12:22].copy()
+        for leg in range(2):
+            des = sp.foot(leg, Ts[i])[0]
+            states[i][12 + 5 * leg:17 + 5 * leg] = compute_ik(states[i][6:12], seed[5 * leg:5 * leg + 5], leg, des, R_des)
+    return PiecewiseTarget(Ts, states)
+
+
+class PiecewiseTarget(Target):
+    def state(self, t):
+        if t <= self.times[0]:
+            return self.states[0].copy()
+        if t >= self.times[-1]:
+            return self.states[-1].copy()
+        s = min(bisect.bisect_right(self.times, t) - 1, len(self.times) - 2)
+        a = (t - self.times[s]) / (self.times[s + 1] - self.times[s])
+        return (1 - a) * self.states[s] + a * self.states[s + 1]
+
+
+def plan(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event=None, time_to_target=None, latest_stance=None, joint_ik=True):
     """One instance: returns (ModeSchedule, Target, SwingPlanner) after update, mirroring SwitchedModelReferenceManager::modifyReferences."""
     prev_event = min(t0, gait_start) - 0.5 if prev_event is None else prev_event
     ttt = horizon if time_to_target is None else time_to_target
@@ -270,6 +415,8 @@ def plan(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event=None, 
     sp.body_vel_cmd = np.array([cmd_vel[0], cmd_vel[1], cmd_vel[2], cmd_vel[3], 0.0, 0.0])
     sp.current_feet = np.array(feet_pos, dtype=float).reshape(4, 3)
     sp.update(ms, tg, t0)
+    if joint_ik:
+        tg = joint_references(sp, tg, t0, t0 + horizon, np.asarray(x0, dtype=float))
     return ms, tg, sp
 
 
@@ -316,3 +463,66 @@ def eval_compact(ref, times):
                 cs = CubicSpline((sg[0], sg[2], sg[3]), (sg[1], sg[4], sg[5]))
                 swing[k, 6 * c + a] = cs.position(t); swing[k, 6 * c + 3 + a] = cs.velocity(t)
     return x_ref, swing, mode
+
+
+class GaitSelectorRef:
+    """P2: calculateVelAbs + walkGait / trotGait (SwitchedModelReferenceManager.cpp:185-249) with a deque like the reference."""
+
+    def __init__(self, gait_level=-1):
+        from collections import deque
+        self.hist = deque(); self.level = gait_level; self.avg = 0.0
+
+    def update(self, cmd_vel, target0, gait_type=0):
+        vc = np.zeros(4); vc[:3] = rot_zyx(target0[9:12]) @ np.array(cmd_vel[:3], dtype=float); vc[2] = 0.0; vc[3] = cmd_vel[3] / 3.0
+        ve = np.array(target0[0:4], dtype=float); ve[2] = 0.0; ve[3] = ve[3] / 3.0
+        self.hist.appendleft(float(np.linalg.norm(0.5 * vc + 0.5 * ve)))
+        while len(self.hist) > 50:
+            self.hist.pop()
+        self.avg = sum(self.hist) / len(self.hist)
+        insert = 0
+        if gait_type == 0:
+            if self.avg <= 0.02:
+                if self.level != 0:
+                    insert, self.level = 1, 0
+            elif 0.03 < self.avg < 0.4:
+                if self.level != 1:
+                    insert, self.level = 1, 1
+            elif self.avg >= 0.4:
+                self.level = 3
+        elif gait_type == 2:
+            if self.level != 1:
+                insert, self.level = 1, 1
+        return self.level, insert
+
+
+PD_DEFAULTS = dict(kp_position=10.0, kd_position=3.0, kp_big_stance=40.0, kp_big_swing=30.0, kd_big=2.0, kp_small_stance=30.0,
+                   kp_small_swing=20.0, kd_small=2.0, kd_feet=0.01)     # legged_controllers/cfg/Tutorials.cfg:6-16
+
+
+def joint_command(period, x_des, u_des, wbc_sol, mode_cmd, rbd, loaded=True, estop=False, gains=PD_DEFAULTS):
+    """W6: joint command law of one instance (LeggedController.cpp:186-257). Returns (command 10x5, output_torque 10, estop)."""
+    g = gains
+    cmd = np.zeros((10, 5)); tau = np.zeros(10)
+    pos_des = x_des[12:22] + 0.5 * wbc_sol[6:16] * period * period
+    vel_des = u_des[12:22] + wbc_sol[6:16] * period
+    legs = stance_legs(mode_cmd)
+    for j in range(10):
+        q, qd = rbd[6 + j], rbd[16 + 6 + j]
+        if not estop and loaded and (q > JOINT_UPPER[j] + 0.02 or q < JOINT_LOWER[j] - 0.02):
+            estop = True
+        if not loaded:
+            c = (x_des[12 + j], u_des[12 + j], g["kp_position"], g["kd_feet"] if j in (4, 9) else g["kd_position"], 0.0)
+        else:
+            contact = legs[j // 5]
+            if j in (0, 1, 5, 6):
+                kp, kd = (g["kp_small_stance"] if contact else g["kp_small_swing"]), g["kd_small"]
+            elif j in (4, 9):
+                kp, kd = (g["kp_small_stance"] if contact else g["kp_small_swing"]), g["kd_feet"]
+            else:
+                kp, kd = (g["kp_big_stance"] if contact else g["kp_big_swing"]), g["kd_big"]
+            c = (pos_des[j], vel_des[j], kp, kd, wbc_sol[28 + j])
+        if estop:
+            c = (0.0, 0.0, 0.0, 1.0, 0.0)
+        cmd[j] = c
+        tau[j] = c[4] + c[2] * (c[0] - q) + c[3] * (c[1] - qd)
+    return cmd, tau, estop

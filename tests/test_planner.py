@@ -47,8 +47,56 @@ def test_planner_matches_per_phase_restatement():
         xr, sw, md = R.sample(ms, tg, sp, times)
         xc, sc, mc = R.eval_compact(refs[i], times)
         np.testing.assert_array_equal(md, mc)
-        np.testing.assert_allclose(xc, xr, rtol=0, atol=1e-13)
+        np.testing.assert_allclose(xc, xr, rtol=0, atol=1e-9)     # joint references come out of <= 10 Newton steps per leg
         np.testing.assert_allclose(sc, sw, rtol=0, atol=1e-11)
+
+
+def test_joint_references_by_ik():
+    """P4: the resampled target (0.15 s steps) carries IK joint angles: same numbers as the restatement, inside the joint limits,
+    and the toe of the IK configuration is closer to the planned toe position than the seed configuration was."""
+    n = 16
+    x0, gaits, cmd, t0, start, feet, latest = _cases(n, seed=23)
+    refs, _ = hb.plan_references(t0, T, x0, cmd, feet, gaits, start, latest_stance=latest)
+    refs0, _ = hb.plan_references(t0, T, x0, cmd, feet, gaits, start, latest_stance=latest, joint_ik=False)
+    moved = 0
+    for i in range(n):
+        ms, tg, sp = R.plan(t0[i], T, x0[i], cmd[i], feet[i], gaits[i], start[i], latest_stance=latest[i])
+        ns = int(np.floor(T / 0.15)) + 1
+        assert refs[i].n_targets == ns == len(tg.times) and refs0[i].n_targets == 2
+        for k in range(ns):
+            assert abs(refs[i].target_times[k] - tg.times[k]) < 1e-15
+            got = np.array(refs[i].target_states[k][:])
+            np.testing.assert_allclose(got, tg.states[k], rtol=0, atol=1e-9)
+            assert np.all(got[12:22] >= R.JOINT_LOWER - 1e-15) and np.all(got[12:22] <= R.JOINT_UPPER + 1e-15)
+            seed = R.DEFAULT_JOINTS if k == 0 else np.array(refs[i].target_states[k - 1][12:22])
+            for leg in range(2):
+                des = sp.foot(leg, tg.times[k])[0]
+                Rd = R.rot_zyx(x0[i, 9:12])
+                q0 = seed[5 * leg:5 * leg + 5]
+                q1 = R.translation_ik(got[6:12], q0, leg, des)
+                q2 = R.rotation_ik(got[6:12], q1, leg, Rd)
+                np.testing.assert_allclose(q2, got[12 + 5 * leg:17 + 5 * leg], rtol=0, atol=1e-9)
+                e0 = np.linalg.norm(R.leg_frame(leg, got[6:12], q0)[0] - des)
+                e1 = np.linalg.norm(R.leg_frame(leg, got[6:12], q1)[0] - des)
+                r1 = np.linalg.norm(R.log3(Rd.T @ R.leg_frame(leg, got[6:12], q1)[1]))
+                r2 = np.linalg.norm(R.log3(Rd.T @ R.leg_frame(leg, got[6:12], q2)[1]))
+                assert e1 <= e0 + 1e-15 and r2 <= r1 + 1e-15
+                if e0 >= 0.01 and e1 < e0:      # below err_tol the reference does not move the leg for position
+                    moved += 1
+    assert moved > 20
+
+
+def test_ik_building_blocks():
+    """Pivoted-QR basic solution and complete-pivoting kernel: defining properties on random 3x5 Jacobians."""
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        J = rng.normal(size=(3, 5)); b = rng.normal(size=3)
+        x = R.colpiv_qr_solve(J, b)
+        assert np.sum(x != 0) == 3 and np.allclose(J @ x, b, atol=1e-10)
+        N = R.fullpiv_lu_kernel(J)
+        assert N.shape == (5, 2) and np.abs(J @ N).max() < 1e-12 and np.linalg.matrix_rank(N) == 2
+    w = np.array([0.3, -0.2, 0.5])
+    np.testing.assert_allclose(R.log3(R._rodrigues(w / np.linalg.norm(w), np.linalg.norm(w))), w, atol=1e-14)
 
 
 def test_planner_continuity_and_footholds():
@@ -85,6 +133,40 @@ def test_planner_latest_stance_update():
     assert np.all(ls[:, :, 2] == R.NEXT_Z)
 
 
+def test_gait_selector_matches_restatement():
+    """P2: 50-sample moving average + thresholds, driven by a speed profile that crosses every threshold in both directions."""
+    B, steps = 6, 260
+    rng = np.random.default_rng(4)
+    sel = hb.GaitSelector(B)
+    ref = [R.GaitSelectorRef() for _ in range(B)]
+    yaw = rng.uniform(-1, 1, B)
+    seen = set()
+    for k in range(steps):
+        speed = 0.5 * (1 - np.cos(2 * np.pi * k / 130.0)) * np.linspace(0.1, 0.9, B)      # 0 -> peak -> 0 -> peak
+        cmd = np.stack([speed, 0.1 * speed, np.zeros(B), 0.3 * speed], axis=1)
+        tgt = np.zeros((B, 22)); tgt[:, 9] = yaw
+        for i in range(B):
+            tgt[i, 0:3] = R.rot_zyx([yaw[i], 0, 0]) @ cmd[i, :3]
+        gt = np.array([0, 0, 0, 0, 2, 0], dtype=np.int32)
+        level, insert = sel.update(cmd, tgt, gt)
+        for i in range(B):
+            l, ins = ref[i].update(cmd[i], tgt[i], int(gt[i]))
+            assert (level[i], insert[i]) == (l, ins)
+            assert abs(sel.vel_avg[i] - ref[i].avg) < 1e-14
+            seen.add(int(level[i]))
+    assert seen >= {0, 1, 3}
+
+
+def test_planner_threads_give_identical_bytes(monkeypatch):
+    n = 200
+    x0, gaits, cmd, t0, start, feet, latest = _cases(n, seed=31)
+    monkeypatch.setenv("HB_PLAN_THREADS", "1")
+    r1, l1 = hb.plan_references(t0, T, x0, cmd, feet, gaits, start, latest_stance=latest)
+    monkeypatch.setenv("HB_PLAN_THREADS", "3")
+    r3, l3 = hb.plan_references(t0, T, x0, cmd, feet, gaits, start, latest_stance=latest)
+    assert bytes(r1) == bytes(r3) and np.array_equal(l1, l3)
+
+
 def test_planner_rejects_bad_input():
     x0, gaits, cmd, t0, start, feet, latest = _cases(2)
     with pytest.raises(RuntimeError):
@@ -115,4 +197,29 @@ def test_plan_then_expand_on_device():
         np.testing.assert_array_equal(md[i][ok], mo[ok])
         np.testing.assert_allclose(xr[i], xo, rtol=0, atol=1e-13)
         np.testing.assert_allclose(sw[i][ok], so[ok], rtol=0, atol=1e-11)
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_joint_command_law():
+    """W6: command (posDes, velDes, kp, kd, ff) and output torque per joint, limit protection and pre-load hold."""
+    ctx = hb.Context(horizon_N=N, dt=DT, max_batch=64, device=0)
+    B = 48
+    rng = np.random.default_rng(8)
+    x_des = rng.normal(size=(B, 22)); u_des = rng.normal(size=(B, 22)); sol = rng.normal(size=(B, 38)) * 5
+    rbd = rng.normal(size=(B, 32)) * 0.3
+    rbd[:, 6:16] = np.clip(rbd[:, 6:16] + R.DEFAULT_JOINTS, R.JOINT_LOWER, R.JOINT_UPPER)
+    rbd[5, 6 + 3] = R.JOINT_UPPER[3] + 0.05          # knee beyond the limit: emergency stop from joint 3 on
+    rbd[6, 6 + 0] = R.JOINT_LOWER[0] - 0.019         # inside the 0.02 margin: no stop
+    mode = rng.integers(0, 4, B).astype(np.int32)
+    loaded = np.ones(B, dtype=np.uint8); loaded[10:14] = 0
+    estop = np.zeros(B, dtype=np.uint8); estop[20] = 1
+    cmd, tau, es = ctx.joint_command(0.002, x_des, u_des, sol, mode, rbd, loaded=loaded, estop=estop)
+    for i in range(B):
+        c, t, e = R.joint_command(0.002, x_des[i], u_des[i], sol[i], int(mode[i]), rbd[i], loaded=bool(loaded[i]), estop=bool(estop[i]))
+        np.testing.assert_allclose(cmd[i], c, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(tau[i], t, rtol=1e-12, atol=1e-12)
+        assert bool(es[i]) == e
+    assert es[5] == 1 and es[6] == 0 and es[20] == 1
+    assert np.all(cmd[5, :3, 2] > 0) and np.all(cmd[5, 3:, 3] == 1.0)
     ctx.close()
