@@ -77,10 +77,12 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-def workload(B, seed_offset=0):
+def workload(B, seed_offset=0, with_compact=False):
     from hunter_bipedal_control_b200 import scenarios as S
-    x0, x_ref, swing, mode = S.make_batch(B, HORIZON_N, DT, gait="trot", cmd_vel=(0.2, 0.0, 0.0, 0.0), seed=20240901 + seed_offset)
+    x0, x_ref, swing, mode, compacts = S.make_batch(B, HORIZON_N, DT, gait="trot", cmd_vel=(0.2, 0.0, 0.0, 0.0), seed=20240901 + seed_offset, return_compact=True)
     rbd = S.consistent_rbd(x0, np.random.default_rng(20240901 + seed_offset), 0.0)
+    if with_compact:
+        return x0, x_ref, swing, mode, rbd, S.pack_references(compacts, 2 * HORIZON_N * DT)
     return x0, x_ref, swing, mode, rbd
 
 
@@ -152,7 +154,7 @@ def main():
     B = args.batch
     total_B = B * world
     lo, hi = sharding.partition(total_B, world, rank)
-    x0, x_ref, swing, mode, rbd = workload(B, seed_offset=lo)     # instance index = global index
+    x0, x_ref, swing, mode, rbd, refs = workload(B, seed_offset=lo, with_compact=True)     # instance index = global index
     ctx = hb.Context(horizon_N=HORIZON_N, dt=DT, max_batch=B, device=local)
     stream = torch.cuda.ExternalStream(ctx.stream_handle, device=dev)
     to = lambda a, dt_=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt_)
@@ -201,21 +203,45 @@ def main():
     launches = ctx.launch_count - l0
     prof = ctx.profile_read()
     ctx.profile_enable(False)
-    # ---------------- end-to-end through the host-pointer C ABI, pinned host buffers, copies inside the timed region
+    # ---------------- end-to-end through the host-pointer C ABI, pinned host buffers, copies inside the timed region.
+    # e2e      : hb_resident_cycle_batch -- the closed-loop call: t0 / x0 / compact references / rbd in, info / WBC solution / torques out;
+    #            reference expansion and the initializer cold start run on the device, the primal solution stays resident.
+    # e2e_full : hb_control_step_batch -- node-sampled references and the full state / input trajectories cross PCIe both ways.
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_x0, h_xref, h_swing, h_rbd, h_mode = pin(x0), pin(x_ref), pin(swing), pin(rbd), pin(mode)
-    # every e2e step gets its own pre-initialised in/out trajectory buffers (cold start), so no host-side reset sits in the timed region
-    n_e2e = args.steps + 2
-    h_xts = [d_xt0.cpu().pin_memory() for _ in range(n_e2e)]; h_uts = [d_ut0.cpu().pin_memory() for _ in range(n_e2e)]
-    h_xt, h_ut = h_xts[0], h_uts[0]
+    import ctypes as C
+    ref_bytes = C.sizeof(refs)
+    h_refs = torch.empty(ref_bytes, dtype=torch.uint8).pin_memory()
+    C.memmove(h_refs.data_ptr(), C.addressof(refs), ref_bytes)
+    h_t0 = torch.zeros(B, dtype=torch.float64).pin_memory()
     h_info = torch.zeros((B, 7), dtype=torch.float64).pin_memory(); h_sol = torch.zeros((B, 38), dtype=torch.float64).pin_memory()
     h_tau = torch.zeros((B, 10), dtype=torch.float64).pin_memory(); h_st = torch.zeros(B, dtype=torch.int32).pin_memory()
     lib = hb.load_library()
-    import ctypes as C
     P = lambda t: C.c_void_p(t.data_ptr())
-    e2e_i = [0]
 
     def step_e2e():
+        rc = lib.hb_resident_cycle_batch(ctx._h, B, 1, C.c_double(T_POLICY), P(h_t0), P(h_x0), P(h_refs), P(h_rbd), P(h_info), P(h_sol), P(h_tau), P(h_st))
+        assert rc == 0, rc
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    _td = d_tau.cpu().numpy()
+    e2e_tau_diff = float(np.abs(h_tau.numpy() - _td).max() / max(1e-300, np.abs(_td).max()))     # same work as the device-resident step
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = (h_t0.numel() + h_x0.numel() + h_rbd.numel()) * 8 + ref_bytes
+    d2h = (h_info.numel() + h_sol.numel() + h_tau.numel()) * 8 + h_st.numel() * 4
+    # every full-trajectory step gets its own pre-initialised in/out trajectory buffers (cold start): no host-side reset in the timed region
+    n_e2e = args.steps + 2
+    h_xts = [d_xt0.cpu().pin_memory() for _ in range(n_e2e)]; h_uts = [d_ut0.cpu().pin_memory() for _ in range(n_e2e)]
+    h_xt, h_ut = h_xts[0], h_uts[0]
+    e2e_i = [0]
+
+    def step_e2e_full():
         xt_, ut_ = h_xts[e2e_i[0]], h_uts[e2e_i[0]]
         e2e_i[0] += 1
         rc = lib.hb_control_step_batch(ctx._h, B, C.c_double(T_POLICY), P(h_x0), P(h_xref), P(h_swing), P(h_mode), P(h_rbd), P(xt_), P(ut_), P(h_info),
@@ -223,23 +249,23 @@ def main():
         assert rc == 0, rc
 
     for _ in range(2):
-        step_e2e()
+        step_e2e_full()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step_e2e()
+        step_e2e_full()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    h2d = (h_x0.numel() + h_xref.numel() + h_swing.numel() + h_rbd.numel() + h_xt.numel() + h_ut.numel()) * 8 + h_mode.numel() * 4
-    d2h = (h_xt.numel() + h_ut.numel() + h_info.numel() + h_sol.numel() + h_tau.numel()) * 8 + h_st.numel() * 4
+    full_s = time.perf_counter() - t0
+    full_h2d = (h_x0.numel() + h_xref.numel() + h_swing.numel() + h_rbd.numel() + h_xt.numel() + h_ut.numel()) * 8 + h_mode.numel() * 4
+    full_d2h = (h_xt.numel() + h_ut.numel() + h_info.numel() + h_sol.numel() + h_tau.numel()) * 8 + h_st.numel() * 4
     clocks = sampler.stop() if rank == 0 else None
     # ---------------- max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_s * 1e3, full_s * 1e3], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        ms, e2e_ms, full_ms = float(t[0]), float(t[1]), float(t[2])
     else:
-        e2e_ms = e2e_s * 1e3
+        e2e_ms, full_ms = e2e_s * 1e3, full_s * 1e3
     ok = bool((d_st == 0).all().item())
     if rank == 0:
         peaks, src = load_peaks()
@@ -263,8 +289,13 @@ def main():
                 "config": {"workload": "configs[1]: %d Hunter instances per GPU, trot gait, N=100 dt=10 ms, randomised initial base pose (seed 20240901+i), "
                            "one SQP iteration from the initializer cold start + policy eval at 2 ms + WeightedWbc QP" % B,
                            "instances_total": total_B, "parallelism": "instances sharded in contiguous blocks, NCCL gather of torques" if world > 1 else "single GPU",
-                           "l2": "per-step working set (node records %.0f MB + references/trajectories %.0f MB) exceeds the 126 MB L2" % (B * HORIZON_N * (1200 + 2320 + 368) * 8 / 1e6, h2d / 1e6)},
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+                           "l2": "per-step working set (node records %.0f MB + references/trajectories %.0f MB) exceeds the 126 MB L2" % (B * HORIZON_N * (1200 + 2320 + 368) * 8 / 1e6, full_h2d / 1e6)},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
+                        "call": "hb_resident_cycle_batch(cold_start=1): t0, x0, compact references, rbd in; info, WBC solution, torques, status out",
+                        "torque_max_rel_diff_vs_device_path": e2e_tau_diff},
+                "e2e_full_trajectories": {"value": total_B * args.steps / (full_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(full_h2d),
+                                          "d2h_bytes_per_step": int(full_d2h), "ms_per_step": full_ms / args.steps,
+                                          "call": "hb_control_step_batch: node-sampled references and full trajectories both ways"},
                 "gpu_launches": int(launches),
                 "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
                 "roofline": {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_last_cuda_error", "hb_launch_count", "hb_stream", "hb_profile_enable", "hb_profile_read",
     "hb_wbc_qp_batch_dev", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
     "hb_policy_eval_batch_dev", "hb_control_step_batch_dev", "hb_rbd_to_centroidal_batch_dev", "hb_reference_expand_batch_dev",
-    "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references", "hb_gait_select", "hb_default_pd_gains", "hb_joint_command_batch_dev", "hb_joint_command_batch",
+    "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references", "hb_gait_select", "hb_resident_cycle_batch_dev", "hb_resident_cycle_batch", "hb_resident_read_batch", "hb_default_pd_gains", "hb_joint_command_batch_dev", "hb_joint_command_batch",
     "hb_wbc_qp_batch", "hb_wbc_solve_batch", "hb_mpc_cold_start_batch", "hb_mpc_solve_batch", "hb_control_step_batch",
     "hb_rbd_to_centroidal_batch", "hb_reference_expand_batch", "hb_probe_flow_map",
 ]
@@ -249,6 +249,19 @@ class Context:
                                                _ptr(info), _ptr(sol), _ptr(tau), _ptr(st)), "hb_control_step_batch", self._h)
         return xt, ut, info, sol, tau, st
 
+    def resident_cycle(self, cold_start, t_rel, t0, x0, refs, rbd):
+        """Resident closed-loop cycle (hb_resident_cycle_batch); refs: ctypes array of HbReference. Returns (info, sol, torque, status)."""
+        t0, x0, rbd = _f64(t0), _f64(x0), _f64(rbd); B = x0.shape[0]
+        info = np.zeros(B, dtype=INFO_DTYPE); sol = np.zeros((B, NWBC)); tau = np.zeros((B, NJ)); st = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_resident_cycle_batch(self._h, B, 1 if cold_start else 0, C.c_double(t_rel), _ptr(t0), _ptr(x0), C.cast(refs, C.c_void_p),
+                                                 _ptr(rbd), _ptr(info), _ptr(sol), _ptr(tau), _ptr(st)), "hb_resident_cycle_batch", self._h)
+        return info, sol, tau, st
+
+    def resident_read(self, B):
+        t0 = np.zeros(B); xt = np.zeros((B, self.N + 1, NX)); ut = np.zeros((B, self.N, NU))
+        _check(self._lib.hb_resident_read_batch(self._h, B, _ptr(t0), _ptr(xt), _ptr(ut)), "hb_resident_read_batch", self._h)
+        return t0, xt, ut
+
     def joint_command(self, period, x_des, u_des, wbc_sol, mode_cmd, rbd, loaded=None, estop=None, gains=None):
         """Joint command law (LeggedController.cpp:186-257): returns (command [B,10,5], output_torque [B,10], estop [B])."""
         x_des, u_des, wbc_sol, rbd = _f64(x_des), _f64(u_des), _f64(wbc_sol), _f64(rbd); B = x_des.shape[0]
@@ -304,6 +317,10 @@ class Context:
     def wbc_qp_dev(self, n, m, H, g, A, lbA, ubA, x, status=None, iters=None):
         _check(self._lib.hb_wbc_qp_batch_dev(self._h, g.shape[0], n, m, _ptr(H), _ptr(g), _ptr(A), _ptr(lbA), _ptr(ubA), _ptr(x), _ptr(status), _ptr(iters)),
                "hb_wbc_qp_batch_dev")
+
+    def resident_cycle_dev(self, cold_start, t_rel, t0, x0, refs_dev_ptr, rbd, info, sol, tau, status=None):
+        _check(self._lib.hb_resident_cycle_batch_dev(self._h, x0.shape[0], 1 if cold_start else 0, C.c_double(t_rel), _ptr(t0), _ptr(x0), C.c_void_p(refs_dev_ptr),
+                                                     _ptr(rbd), _ptr(info), _ptr(sol), _ptr(tau), _ptr(status)), "hb_resident_cycle_batch_dev", self._h)
 
     def control_step_dev(self, t_rel, x0, x_ref, swing, mode, rbd, xt, ut, info, sol, tau, status=None):
         _check(self._lib.hb_control_step_batch_dev(self._h, x0.shape[0], C.c_double(t_rel), _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(rbd), _ptr(xt),

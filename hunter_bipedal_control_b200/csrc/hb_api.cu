@@ -148,6 +148,58 @@ __global__ void cold_start_kernel(int B, int N, const double* x0, const int32_t*
   }
 }
 
+// Warm start of the next solve from the resident primal solution (ocs2::SqpSolver::initializeStateInputTrajectories; mpc.coldStart
+// false, task.info:146): x[0] = measured state; interval i takes u[i] = previous input at t_i and x[i+1] = previous state at t_{i+1}
+// while t_{i+1} lies inside the previous horizon, otherwise the initializer (weight-compensating input, state kept,
+// LeggedRobotInitializer.cpp:67-77). One block per instance; the previous trajectories are staged in shared memory so that the
+// update can be done in place.
+__global__ void __launch_bounds__(128) warm_shift_kernel(int B, int N, double dt, const double* t0_new, double* t0_res, const double* x0,
+                                                          const int32_t* mode, double* xt, double* ut) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* px = reinterpret_cast<double*>(smem_raw);
+  double* pu = px + (size_t)(N + 1) * NX;
+  const int inst = blockIdx.x;
+  double* x = xt + (size_t)inst * (N + 1) * NX; double* u = ut + (size_t)inst * N * NU;
+  for (int i = threadIdx.x; i < (N + 1) * NX; i += blockDim.x) px[i] = x[i];
+  for (int i = threadIdx.x; i < N * NU; i += blockDim.x) pu[i] = u[i];
+  __syncthreads();
+  const double tp = t0_res[inst], tn = t0_new[inst], t_end = tp + N * dt;
+  auto prev_state = [&](double t, int j) {
+    double s = (t - tp) / dt; s = s < 0.0 ? 0.0 : (s > (double)N ? (double)N : s);
+    int k = (int)floor(s); if (k >= N) k = N - 1;
+    const double al = s - k;
+    return (1.0 - al) * px[k * NX + j] + al * px[(k + 1) * NX + j];
+  };
+  auto prev_input = [&](double t, int j) {
+    double s = (t - tp) / dt; s = s < 0.0 ? 0.0 : (s > (double)N ? (double)N : s);
+    int k = (int)floor(s); if (k >= N) k = N - 1;
+    const double al = s - k;
+    const int k1 = (k + 1 < N) ? k + 1 : N - 1;
+    return (1.0 - al) * pu[k * NU + j] + al * pu[k1 * NU + j];
+  };
+  // first interval that falls back to the initializer: smallest i with t_{i+1} > t_end (1e-9 guards the grid-aligned case)
+  int istar = N;
+  for (int i = 0; i < N; ++i) if (tn + (i + 1) * dt > t_end + 1e-9) { istar = i; break; }
+  for (int idx = threadIdx.x; idx < (N + 1) * NX; idx += blockDim.x) {
+    const int k = idx / NX, j = idx - k * NX;
+    const int ks = k <= istar ? k : istar;                 // the initializer keeps the state of node istar
+    x[idx] = (ks == 0) ? x0[(size_t)inst * NX + j] : prev_state(tn + ks * dt, j);
+  }
+  for (int idx = threadIdx.x; idx < N * NU; idx += blockDim.x) {
+    const int k = idx / NU, j = idx - k * NU;
+    double v;
+    if (k < istar) v = prev_input(tn + k * dt, j);
+    else {
+      const int md = mode[(size_t)inst * (N + 1) + k];
+      int ns = 0;
+      for (int c = 0; c < 4; ++c) ns += contact_flag(md, c);
+      v = (j < 12 && (j % 3) == 2 && contact_flag(md, j / 3)) ? c_model.total_mass * HB_GRAVITY / ns : 0.0;
+    }
+    u[idx] = v;
+  }
+  if (threadIdx.x == 0) t0_res[inst] = tn;
+}
+
 // MPC_MRT_Interface::evaluatePolicy with the feed-forward policy (LeggedController.cpp:154-156, task.info:93):
 // linear interpolation of the state / input trajectories at t0 + t_rel; mode = mode in force at that time.
 __global__ void policy_eval_kernel(int B, int N, double dt, double t_rel, const double* xt, const double* ut, const int32_t* mode, double* x_des,
@@ -322,6 +374,8 @@ struct hb_ctx {
   int32_t *qm, *wstatus, *witers, *wmode;
   // staging for host-pointer calls
   double *s_x0, *s_xref, *s_swing, *s_xt, *s_ut, *s_rbd, *s_xd, *s_ud, *s_sol, *s_tau, *s_t0, *s_misc;
+  double *res_xt = nullptr, *res_ut = nullptr, *res_t0 = nullptr;   // resident primal solution (hb_resident_cycle_batch)
+  int res_valid = 0;                                                // number of instances holding a previous solution
   int32_t *s_mode, *s_imode, *s_status, *s_iters;
   uint8_t* s_stance;
   hb_solve_info* s_info;
@@ -445,6 +499,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   ok = ok && dalloc(&ctx->xdes, B * NX) == cudaSuccess && dalloc(&ctx->udes, B * NU) == cudaSuccess && dalloc(&ctx->wsol, B * NWBC) == cudaSuccess;
   ok = ok && dalloc(&ctx->wstatus, B) == cudaSuccess && dalloc(&ctx->witers, B) == cudaSuccess && dalloc(&ctx->wmode, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_x0, B * NX) == cudaSuccess && dalloc(&ctx->s_xref, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_swing, B * (N + 1) * 24) == cudaSuccess;
+  ok = ok && dalloc(&ctx->res_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->res_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->res_t0, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->s_rbd, B * 32) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_xd, B * NX) == cudaSuccess && dalloc(&ctx->s_ud, B * NU) == cudaSuccess && dalloc(&ctx->s_sol, B * NWBC) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_tau, B * NJ) == cudaSuccess && dalloc(&ctx->s_t0, B) == cudaSuccess && dalloc(&ctx->s_misc, B * (size_t)(NX + 2 * TS + 24 + 36 * NX)) == cudaSuccess;
@@ -470,7 +525,7 @@ int hb_destroy(hb_ctx* ctx) {
   void* ptrs[] = {ctx->lin, ctx->proj, ctx->rk, ctx->gains, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->qH, ctx->qg, ctx->qA, ctx->qlb, ctx->qub, ctx->qm, ctx->xdes, ctx->udes,
                   ctx->wsol, ctx->wstatus, ctx->witers, ctx->wmode, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_xt, ctx->s_ut, ctx->s_rbd, ctx->s_xd,
                   ctx->s_ud, ctx->s_sol, ctx->s_tau, ctx->s_t0, ctx->s_misc, ctx->s_mode, ctx->s_imode, ctx->s_status, ctx->s_iters, ctx->s_stance,
-                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA};
+                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
   if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
@@ -667,6 +722,39 @@ int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0
   return HB_OK;
 }
 
+// store the solve time of a cold-started resident solution
+__global__ void set_times_kernel(int B, const double* t0_new, double* t0_res) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) t0_res[i] = t0_new[i];
+}
+
+int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0, const hb_reference* refs,
+                                const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque, int32_t* wbc_status) {
+  if (!ctx || B < 0 || !t0 || !x0 || !refs || !rbd || !wbc_sol) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (ctx->base + B > ctx->cfg.max_batch) return HB_ECAP;
+  if (!cold_start && ctx->res_valid < ctx->base + B) return HB_EINVAL;     // no previous solution to shift
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t N = ctx->cfg.horizon_N, o = (size_t)ctx->base;
+  double* xref = ctx->s_xref + o * (N + 1) * NX; double* swing = ctx->s_swing + o * (N + 1) * 24; int32_t* mode = ctx->s_mode + o * (N + 1);
+  double* xt = ctx->res_xt + o * (N + 1) * NX; double* ut = ctx->res_ut + o * N * NU; double* tres = ctx->res_t0 + o;
+  int rc = hb_reference_expand_batch_dev(ctx, B, t0, refs, xref, swing, mode);
+  if (rc) return rc;
+  if (cold_start) {
+    rc = hb_mpc_cold_start_batch_dev(ctx, B, x0, mode, xt, ut);
+    if (rc) return rc;
+    set_times_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, t0, tres);
+  } else {
+    const size_t smem = sizeof(double) * ((N + 1) * NX + N * NU);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(warm_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    warm_shift_kernel<<<B, 128, smem, ctx->stream>>>(B, (int)N, ctx->cfg.dt, t0, tres, x0, mode, xt, ut);
+  }
+  ctx->launches++;
+  CK(cudaGetLastError());
+  if (ctx->res_valid < ctx->base + B) ctx->res_valid = ctx->base + B;
+  return hb_control_step_batch_dev(ctx, B, t_rel, x0, xref, swing, mode, rbd, xt, ut, info, wbc_sol, torque, wbc_status);
+}
+
 int hb_default_pd_gains(hb_pd_gains* g) {
   if (!g) return HB_EINVAL;
   g->kp_position = 10.0; g->kd_position = 3.0;
@@ -848,6 +936,57 @@ int hb_control_step_batch(hb_ctx* ctx, int B, double t_rel, const double* x0, co
   if (rc) return rc;
   if (e0 != cudaSuccess || e1 != cudaSuccess) { ctx->last_cuda = (int)(e0 != cudaSuccess ? e0 : e1); return HB_ECUDA; }
   return HB_OK;
+}
+
+int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0, const hb_reference* refs,
+                            const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque, int32_t* wbc_status) {
+  if (!ctx || B < 0 || !t0 || !x0 || !refs || !rbd) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (!cold_start && ctx->res_valid < B) return HB_EINVAL;
+  if (set_device(ctx)) return HB_ECUDA;
+  // Two half-batches on two streams, as in hb_control_step_batch; only the small per-instance inputs and results cross PCIe.
+  const int nchunk = (B >= 256 && ctx->sqp_version == 2) ? 2 : 1;
+  int rc = HB_OK;
+  for (int c = 0; c < nchunk && rc == HB_OK; ++c) {
+    const size_t lo = (size_t)B * c / nchunk, hi = (size_t)B * (c + 1) / nchunk, n = hi - lo;
+    ctx->stream = (c == 0) ? ctx->stream_main : ctx->stream_aux;
+    ctx->base = (int)lo;
+    cudaError_t e = cudaSuccess;
+    auto h2d = [&](void* d, const void* h, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream); };
+    auto d2h = [&](void* h, const void* d, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream); };
+    h2d(ctx->s_t0 + lo, t0 + lo, sizeof(double) * n);
+    h2d(ctx->s_x0 + lo * NX, x0 + lo * NX, sizeof(double) * n * NX);
+    h2d(ctx->s_refs + lo, refs + lo, sizeof(hb_reference) * n);
+    h2d(ctx->s_rbd + lo * 32, rbd + lo * 32, sizeof(double) * n * 32);
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = HB_ECUDA; break; }
+    rc = hb_resident_cycle_batch_dev(ctx, (int)n, cold_start, t_rel, ctx->s_t0 + lo, ctx->s_x0 + lo * NX, ctx->s_refs + lo, ctx->s_rbd + lo * 32,
+                                     ctx->s_info + lo, ctx->s_sol + lo * NWBC, ctx->s_tau + lo * NJ, ctx->s_status + lo);
+    if (rc) break;
+    if (info) d2h(info + lo, ctx->s_info + lo, sizeof(hb_solve_info) * n);
+    if (wbc_sol) d2h(wbc_sol + lo * NWBC, ctx->s_sol + lo * NWBC, sizeof(double) * n * NWBC);
+    if (torque) d2h(torque + lo * NJ, ctx->s_tau + lo * NJ, sizeof(double) * n * NJ);
+    if (wbc_status) d2h(wbc_status + lo, ctx->s_status + lo, sizeof(int32_t) * n);
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = HB_ECUDA; }
+  }
+  ctx->stream = ctx->stream_main;
+  ctx->base = 0;
+  cudaError_t e1 = cudaStreamSynchronize(ctx->stream_aux), e0 = cudaStreamSynchronize(ctx->stream_main);
+  if (rc) return rc;
+  if (e0 != cudaSuccess || e1 != cudaSuccess) { ctx->last_cuda = (int)(e0 != cudaSuccess ? e0 : e1); return HB_ECUDA; }
+  return HB_OK;
+}
+
+int hb_resident_read_batch(hb_ctx* ctx, int B, double* t0, double* x_traj, double* u_traj) {
+  if (!ctx || B < 0) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->res_valid) return HB_EINVAL;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t N = ctx->cfg.horizon_N;
+  if (t0) D2H(t0, ctx->res_t0, sizeof(double) * B);
+  if (x_traj) D2H(x_traj, ctx->res_xt, sizeof(double) * B * (N + 1) * NX);
+  if (u_traj) D2H(u_traj, ctx->res_ut, sizeof(double) * B * N * NU);
+  return hb_sync(ctx);
 }
 
 int hb_joint_command_batch(hb_ctx* ctx, int B, const hb_pd_gains* gains, double period, const double* x_des, const double* u_des,

@@ -155,14 +155,17 @@ def make_reference(x0, cmd_vel, gait, N, dt, t0=0.0, phase=0.0):
     return x_ref, swing.reshape(N + 1, 24), mode, compact
 
 
-def make_batch(B, N=100, dt=0.01, gait="trot", cmd_vel=(0.2, 0.0, 0.0, 0.0), seed=20240901, gaits=None, cmd_vels=None):
+def make_batch(B, N=100, dt=0.01, gait="trot", cmd_vel=(0.2, 0.0, 0.0, 0.0), seed=20240901, gaits=None, cmd_vels=None, return_compact=False):
     x0 = random_initial_states(B, seed)
     x_ref = np.zeros((B, N + 1, 22)); swing = np.zeros((B, N + 1, 24)); mode = np.zeros((B, N + 1), dtype=np.int32)
-    cache = {}
+    compacts = []
     for i in range(B):
         g = gaits[i] if gaits is not None else gait
         cv = cmd_vels[i] if cmd_vels is not None else cmd_vel
-        x_ref[i], swing[i], mode[i], _ = make_reference(x0[i], cv, g, N, dt)
+        x_ref[i], swing[i], mode[i], c = make_reference(x0[i], cv, g, N, dt)
+        compacts.append(c)
+    if return_compact:
+        return x0, x_ref, swing, mode, compacts
     return x0, x_ref, swing, mode
 
 
@@ -175,3 +178,30 @@ def consistent_rbd(x, rng=None, noise=0.0):
         rbd[:, 0:16] += noise * rng.uniform(-1, 1, (B, 16))
         rbd[:, 16:32] = rng.uniform(-0.3, 0.3, (B, 16))
     return rbd
+
+
+def pack_references(compacts, horizon):
+    """Compact descriptions returned by make_reference (4th value) -> ctypes array of HbReference for the device expansion."""
+    from .api import HbReference, HB_MAX_SEGMENTS
+    refs = (HbReference * len(compacts))()
+    for r, c in zip(refs, compacts):
+        r.n_events = len(c["events"])
+        for k, t in enumerate(c["events"]):
+            r.event_times[k] = t
+        for k, m in enumerate(c["modes"]):
+            r.modes[k] = m
+        r.n_targets = len(c["target_times"])
+        for k in range(r.n_targets):
+            r.target_times[k] = c["target_times"][k]
+            for j in range(22):
+                r.target_states[k][j] = c["target_states"][k][j]
+        for cc in range(4):
+            for a in range(3):
+                segs = [sg for sg in c["segments"][cc][a] if sg[0] <= horizon + 1e-9]      # only what the horizon can see
+                if len(segs) > HB_MAX_SEGMENTS:
+                    raise ValueError("too many swing segments for hb_reference")
+                r.n_segments[cc][a] = len(segs)
+                for si, sg in enumerate(segs):
+                    for j in range(6):
+                        r.segments[cc][a][si][j] = sg[j]
+    return refs

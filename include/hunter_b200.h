@@ -11,6 +11,7 @@
  *   hb_mpc_cold_start_batch <-> LeggedRobotInitializer::compute       legged_interface/src/initialization/LeggedRobotInitializer.cpp:67-77
  *   hb_policy_eval_batch    <-> MPC_MRT_Interface::evaluatePolicy     legged_controllers/src/LeggedController.cpp:154-156
  *   hb_control_step_batch   <-> LeggedController::update MPC->policy->WBC->torque law   LeggedController.cpp:137-257
+ *   hb_resident_cycle_batch <-> SqpSolver::run with its resident primalSolution_ (warm start) + the rest of LeggedController::update
  *   hb_joint_command_batch  <-> joint command / torque law            LeggedController.cpp:186-257
  *   hb_plan_references      <-> GaitSchedule tiling + SwingTrajectoryPlanner::update + cmdVelToTargetTrajectories + calculateJointRef
  *   hb_gait_select          <-> SwitchedModelReferenceManager::calculateVelAbs + walkGait/trotGait   :185-249
@@ -142,6 +143,14 @@ int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0
 int hb_joint_command_batch_dev(hb_ctx* ctx, int B, const hb_pd_gains* gains, double period, const double* x_des, const double* u_des,
                                const double* wbc_sol, const int32_t* mode_cmd, const double* rbd, const uint8_t* loaded, uint8_t* estop,
                                double* command, double* output_torque);
+/* Resident closed-loop cycle: the context keeps the primal solution on the device like ocs2::SqpSolver keeps primalSolution_.
+ * One call = reference expansion (hb_reference -> node grid) + warm start (previous solution interpolated on the new grid, tail from
+ * the initializer; mpc.coldStart false, task.info:146 -- or the initializer everywhere when cold_start != 0) + one SQP iteration +
+ * policy evaluation at t0 + t_rel + WeightedWbc + torque law. Only t0, x0, refs, rbd go in and info / wbc_sol / torque / status come
+ * out; hb_resident_read_batch copies the resident trajectories out when the caller wants them (PrimalSolution). */
+int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0,
+                                const hb_reference* refs, const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque,
+                                int32_t* wbc_status);
 int hb_rbd_to_centroidal_batch_dev(hb_ctx* ctx, int B, const double* rbd, double* x);
 int hb_reference_expand_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                                   int32_t* mode);
@@ -165,6 +174,9 @@ int hb_control_step_batch(hb_ctx* ctx, int B, double t_rel, const double* x0, co
 int hb_joint_command_batch(hb_ctx* ctx, int B, const hb_pd_gains* gains, double period, const double* x_des, const double* u_des,
                            const double* wbc_sol, const int32_t* mode_cmd, const double* rbd, const uint8_t* loaded, uint8_t* estop,
                            double* command, double* output_torque);
+int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0, const hb_reference* refs,
+                            const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque, int32_t* wbc_status);
+int hb_resident_read_batch(hb_ctx* ctx, int B, double* t0 /*nullable*/, double* x_traj /*nullable*/, double* u_traj /*nullable*/);
 int hb_rbd_to_centroidal_batch(hb_ctx* ctx, int B, const double* rbd, double* x);
 int hb_reference_expand_batch(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                               int32_t* mode);

@@ -526,3 +526,34 @@ def joint_command(period, x_des, u_des, wbc_sol, mode_cmd, rbd, loaded=True, est
         cmd[j] = c
         tau[j] = c[4] + c[2] * (c[0] - q) + c[3] * (c[1] - qd)
     return cmd, tau, estop
+
+
+def warm_start_shift(t0_prev, t0_new, dt, x_prev, u_prev, x0, mode_new, mass, g=9.81):
+    """SqpSolver::initializeStateInputTrajectories with a previous solution (restated from OCS2 ocs2_sqp, un-vendored): x[0] = x0;
+    interval i: if t_{i+1} is inside the previous horizon, u[i] = prev input at t_i and x[i+1] = prev state at t_{i+1} (linear
+    interpolation; the input trajectory repeats its last sample at the final node); otherwise the initializer
+    (LeggedRobotInitializer.cpp:67-77): weight-compensating input for the mode of the interval, state kept."""
+    N = u_prev.shape[0]
+    t_end = t0_prev + N * dt
+    u_ext = np.vstack([u_prev, u_prev[-1:]])
+
+    def interp(arr, t):
+        s = min(max((t - t0_prev) / dt, 0.0), float(N))
+        k = min(int(math.floor(s)), N - 1)
+        a = s - k
+        return (1 - a) * arr[k] + a * arr[k + 1]
+
+    x = np.zeros((N + 1, 22)); u = np.zeros((N, 22))
+    x[0] = x0
+    for i in range(N):
+        ti, tn = t0_new + i * dt, t0_new + (i + 1) * dt
+        if tn > t_end + 1e-9:
+            legs = stance_legs(int(mode_new[i])); ns = sum(legs)
+            for c in range(4):
+                if legs[c]:
+                    u[i, 3 * c + 2] = mass * g / ns
+            x[i + 1] = x[i]
+        else:
+            u[i] = interp(u_ext, ti)
+            x[i + 1] = interp(x_prev, tn)
+    return x, u
