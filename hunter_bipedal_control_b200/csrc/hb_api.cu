@@ -946,11 +946,12 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
   if (!cold_start && ctx->res_valid < B) return HB_EINVAL;
   if (set_device(ctx)) return HB_ECUDA;
   // Two half-batches on two streams, as in hb_control_step_batch; only the small per-instance inputs and results cross PCIe.
-  const int nchunk = (B >= 256 && ctx->sqp_version == 2) ? 2 : 1;
+  int nchunk = (B >= 256 && ctx->sqp_version == 2) ? 2 : 1;
+  if (const char* e = getenv("HB_E2E_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= 8 && B >= 64 * v && ctx->sqp_version == 2) nchunk = v; }
   int rc = HB_OK;
   for (int c = 0; c < nchunk && rc == HB_OK; ++c) {
     const size_t lo = (size_t)B * c / nchunk, hi = (size_t)B * (c + 1) / nchunk, n = hi - lo;
-    ctx->stream = (c == 0) ? ctx->stream_main : ctx->stream_aux;
+    ctx->stream = (c % 2 == 0) ? ctx->stream_main : ctx->stream_aux;
     ctx->base = (int)lo;
     cudaError_t e = cudaSuccess;
     auto h2d = [&](void* d, const void* h, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream); };

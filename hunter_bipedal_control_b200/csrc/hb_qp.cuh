@@ -24,8 +24,8 @@ struct QpWorkspace {
   double *kdi, *sdi;
   double *g, *x, *rd, *dx, *t1, *t2;
   double *beq, *y, *rp, *dy, *t3;
-  double *f, *s, *z, *rs, *ds, *dz, *rc, *sgn;
-  int *in_row, *in_c0, *in_c1, *in_pair, *eq_row;   // in_pair: partner entry of a two-sided row (-1 none, -2 merged into its partner)
+  double *f, *s, *z, *rs, *ds, *dz, *rc, *sgn, *wt;   // wt: per-entry weight / coefficient scratch (two-sided rows merged on their first entry)
+  int *in_row, *in_c0, *in_c1, *in_pair, *ord, *eq_row;   // ord: entries in processing order, wide rows first, merged partners left out   // in_pair: partner entry of a two-sided row (-1 none, -2 merged into its partner)
   int ldn, ldv, lds;
   int me_cap, mi_cap;   // capacity of the equality / one-sided inequality lists
 };
@@ -44,8 +44,8 @@ __host__ __device__ inline size_t qp_workspace_doubles(int n, int me_cap = QP_MA
   d += n + me_cap;                 // kdi, sdi
   d += 6 * (size_t)n;              // g x rd dx t1 t2
   d += 5 * (size_t)me_cap;         // beq y rp dy t3
-  d += 8 * (size_t)mi_cap;         // f s z rs ds dz rc sgn
-  d += (4 * (size_t)mi_cap + me_cap + 1) / 2 + 1;  // int arrays
+  d += 9 * (size_t)mi_cap;         // f s z rs ds dz rc sgn wt
+  d += (5 * (size_t)mi_cap + me_cap + 1) / 2 + 1;  // int arrays
   return d;
 }
 
@@ -63,9 +63,9 @@ __device__ inline void qp_carve(double* base, int n, QpWorkspace& w, int me_cap 
   w.g = p; p += n; w.x = p; p += n; w.rd = p; p += n; w.dx = p; p += n; w.t1 = p; p += n; w.t2 = p; p += n;
   w.beq = p; p += me_cap; w.y = p; p += me_cap; w.rp = p; p += me_cap; w.dy = p; p += me_cap; w.t3 = p; p += me_cap;
   w.f = p; p += mi_cap; w.s = p; p += mi_cap; w.z = p; p += mi_cap; w.rs = p; p += mi_cap;
-  w.ds = p; p += mi_cap; w.dz = p; p += mi_cap; w.rc = p; p += mi_cap; w.sgn = p; p += mi_cap;
+  w.ds = p; p += mi_cap; w.dz = p; p += mi_cap; w.rc = p; p += mi_cap; w.sgn = p; p += mi_cap; w.wt = p; p += mi_cap;
   int* ip = reinterpret_cast<int*>(p);
-  w.in_row = ip; ip += mi_cap; w.in_c0 = ip; ip += mi_cap; w.in_c1 = ip; ip += mi_cap; w.in_pair = ip; ip += mi_cap; w.eq_row = ip;
+  w.in_row = ip; ip += mi_cap; w.in_c0 = ip; ip += mi_cap; w.in_c1 = ip; ip += mi_cap; w.in_pair = ip; ip += mi_cap; w.ord = ip; ip += mi_cap; w.eq_row = ip;
 }
 
 // In-place Cholesky M = L L' (lower triangle) followed by Li = L^-1, stored transposed in the strict upper triangle
@@ -189,6 +189,29 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
     return res;
   }
   __syncwarp();
+  // processing order of the inequality entries: "wide" rows (span > 8 columns, e.g. the dense torque rows of the WBC) first, then
+  // the narrow ones (friction pyramid rows: 3 columns); the second entry of a two-sided row is merged into the first
+  int nwide = 0, nact = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int j0 = 0; j0 < mi; j0 += 32) {
+      const int j = j0 + lane;
+      const bool sel = j < mi && w.in_pair[j] != -2 && ((w.in_c1[j] - w.in_c0[j] > 8) == (pass == 0));
+      const unsigned msk = __ballot_sync(HB_FULL_MASK, sel);
+      if (sel) w.ord[nact + __popc(msk & ((1u << lane) - 1u))] = j;
+      nact += __popc(msk);
+    }
+    if (pass == 0) nwide = nact;
+  }
+  __syncwarp();
+  // a = base + sum_j wt[j] A[row_j][i] over the ordered entries (A' times the merged coefficient vector), lane i
+  auto at_mul = [&](int i, double a) {
+    for (int q = 0; q < nwide; ++q) { const int j = w.ord[q]; a = fma(w.wt[j], A[(size_t)w.in_row[j] * n + i], a); }
+    for (int q = nwide; q < nact; ++q) {
+      const int j = w.ord[q];
+      if (i >= w.in_c0[j] && i < w.in_c1[j]) a = fma(w.wt[j], A[(size_t)w.in_row[j] * n + i], a);
+    }
+    return a;
+  };
   // ---------------- stage H, Aeq, g; initial point
   // H == nullptr: the caller assembled the Hessian directly in w.H (leading dimension ldn)
   if (H != nullptr) for (int idx = lane; idx < n * n; idx += 32) { const int i = idx / n, c = idx - i * n; w.H[i * ldn + c] = H[idx]; }
@@ -212,13 +235,19 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
   int it = 0;
   for (; it < max_iter; ++it) {
     // ---------------- residuals
+    for (int j = lane; j < mi; j += 32) {
+      const int pr = w.in_pair[j];
+      double cj = w.sgn[j] * w.z[j];
+      if (pr >= 0) cj += w.sgn[pr] * w.z[pr];
+      w.wt[j] = cj;
+    }
+    __syncwarp();
     for (int i = lane; i < n; i += 32) {
       double a = w.g[i] + rho * w.x[i];
       const double* hr = w.H + i * ldn;
       for (int c = 0; c < n; ++c) a += hr[c] * w.x[c];
       for (int e = 0; e < me; ++e) a += w.Aeq[e * ldn + i] * w.y[e];
-      for (int j = 0; j < mi; ++j) if (i >= w.in_c0[j] && i < w.in_c1[j]) a += w.sgn[j] * w.z[j] * A[(size_t)w.in_row[j] * n + i];
-      w.rd[i] = a;
+      w.rd[i] = at_mul(i, a);
     }
     for (int e = lane; e < me; e += 32) {
       double a = -w.beq[e];
@@ -245,14 +274,45 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
     // ---------------- K = H + rho I + D' W D
     for (int idx = lane; idx < n * ldn; idx += 32) { const int i = idx / ldn, c = idx - i * ldn; w.K[idx] = w.H[idx] + ((i == c) ? rho : 0.0); }
     __syncwarp();
-    // lower triangle only; a two-sided row contributes once with the sum of its two weights; rows of the span are swept
-    // uniformly and lanes own the columns c <= i (no integer division on the hot path)
-    for (int j = 0; j < mi; ++j) {
+    // lower triangle only; a two-sided row contributes once with the sum of its two weights
+    for (int j = lane; j < mi; j += 32) {
       const int pr = w.in_pair[j];
-      if (pr == -2) continue;
-      const int c0 = w.in_c0[j], c1 = w.in_c1[j];
       double wj = w.z[j] / w.s[j];
       if (pr >= 0) wj += w.z[pr] / w.s[pr];
+      w.wt[j] = wj;
+    }
+    __syncwarp();
+    // wide rows as a product: lane c owns column c of the lower triangle, K[i][c] += sum_j (wt_j a_j[c]) a_j[i]; the per-row
+    // factors wt_j a_j[c] stay in registers and a_j[i] is a broadcast load
+    {
+      constexpr int WCH = 10;
+      for (int cb = 0; cb < n; cb += 32) {
+        const int c = cb + lane;
+        const bool act = c < n;
+        for (int q0 = 0; q0 < nwide; q0 += WCH) {
+          double t[WCH]; int roff[WCH];
+#pragma unroll
+          for (int q = 0; q < WCH; ++q) {
+            const bool on = q0 + q < nwide;
+            const int j = on ? w.ord[q0 + q] : 0;
+            roff[q] = on ? w.in_row[j] * n : 0;
+            t[q] = (on && act) ? w.wt[j] * A[(size_t)roff[q] + c] : 0.0;
+          }
+          for (int i = cb; i < n; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < WCH; ++q) acc = fma(t[q], A[(size_t)roff[q] + i], acc);
+            if (act && i >= c) w.K[i * ldn + c] += acc;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // narrow rows: rank-1 update inside the span, lanes own the columns c <= i
+    for (int q = nwide; q < nact; ++q) {
+      const int j = w.ord[q];
+      const int c0 = w.in_c0[j], c1 = w.in_c1[j];
+      const double wj = w.wt[j];
       const double* a = A + (size_t)w.in_row[j] * n;
       for (int i = c0; i < c1; ++i) {
         const double ai = wj * a[i];
@@ -294,12 +354,14 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
 
     // Newton solve for the complementarity target in w.rc; results in dx, dy, ds, dz
     auto newton = [&]() {
-      for (int i = lane; i < n; i += 32) {
-        double a = -w.rd[i];
-        for (int j = 0; j < mi; ++j)
-          if (i >= w.in_c0[j] && i < w.in_c1[j]) a += w.sgn[j] * A[(size_t)w.in_row[j] * n + i] * ((w.rc[j] - w.z[j] * w.rs[j]) / w.s[j]);
-        w.t2[i] = a;
+      for (int j = lane; j < mi; j += 32) {
+        const int pr = w.in_pair[j];
+        double cj = w.sgn[j] * ((w.rc[j] - w.z[j] * w.rs[j]) / w.s[j]);
+        if (pr >= 0) cj += w.sgn[pr] * ((w.rc[pr] - w.z[pr] * w.rs[pr]) / w.s[pr]);
+        w.wt[j] = cj;
       }
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) w.t2[i] = at_mul(i, -w.rd[i]);
       __syncwarp();
       warp_li_mv(w.K, n, ldn, w.kdi, w.t2, w.t1, lane);  // t1 = Li r1
       if (me > 0) {

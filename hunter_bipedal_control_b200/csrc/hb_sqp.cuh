@@ -234,6 +234,27 @@ struct LqShared {
 constexpr int LQ_G = 0, LQ_GL = 34, LQ_T1 = 340, LQ_BT = 560, LQ_PXV = 912;   // G 10x34, T1 10x22, Bt 22x16, Pxv 10x22 (ends at 1132)
 static_assert(LQ_PXV + NJ * NX <= LIN_STRIDE, "aliased area overflow");
 
+template <int MR>
+__device__ __forceinline__ void lq_build_tableau(const LqShared& sh, double* __restrict__ G, int lane) {
+  constexpr int GL = LQ_GL;
+  double xr[MR];
+#pragma unroll
+  for (int r = 0; r < MR; ++r) xr[r] = (lane < NJ) ? sh.Dv[r * NJ + lane] : -sh.Cv[r * NX + lane - NJ];
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < MR; ++r) s = fma(sh.Dv[r * NJ + i], xr[r], s);
+    G[i * GL + lane] = s;
+  }
+  if (lane < NJ) {
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < MR; ++r) s = fma(-sh.Dv[r * NJ + lane], sh.ev[r], s);
+    G[lane * GL + NJ + NX] = s;
+  }
+}
+
 __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LqShared& sh = *reinterpret_cast<LqShared*>(smem_raw);
@@ -460,13 +481,20 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
   double* G = sh.rec + LQ_G; double* T1 = sh.rec + LQ_T1; double* Bt = sh.rec + LQ_BT; double* Pxv = sh.rec + LQ_PXV;
   // ---- least-squares projection on vj: G = Dv'Dv, rhs = -Dv'[Cv | ev]  (10 x 33, ld 34), entries spread over all lanes
   constexpr int GW = NJ + NX + 1, GL = LQ_GL;
-  for (int idx = lane; idx < NJ * GW; idx += 32) {
-    const int i = idx / GW, j = idx - i * GW;
-    double s = 0.0;
-    if (j < NJ) { for (int r = 0; r < mr; ++r) s = fma(sh.Dv[r * NJ + i], sh.Dv[r * NJ + j], s); }
-    else if (j < NJ + NX) { for (int r = 0; r < mr; ++r) s = fma(-sh.Dv[r * NJ + i], sh.Cv[r * NX + j - NJ], s); }
-    else { for (int r = 0; r < mr; ++r) s = fma(-sh.Dv[r * NJ + i], sh.ev[r], s); }
-    G[i * GL + j] = s;
+  // lane j owns column j of the tableau: its right operand X[r][j] (Dv, -Cv) stays in registers, Dv[r][i] is a broadcast load.
+  // mr is 4 (flight), 8 (single support) or 12 (stance) for the contact pairs of this robot.
+  if (mr == 4) lq_build_tableau<4>(sh, G, lane);
+  else if (mr == 8) lq_build_tableau<8>(sh, G, lane);
+  else if (mr == 12) lq_build_tableau<12>(sh, G, lane);
+  else {
+    for (int idx = lane; idx < NJ * GW; idx += 32) {
+      const int i = idx / GW, j = idx - i * GW;
+      double s = 0.0;
+      if (j < NJ) { for (int r = 0; r < mr; ++r) s = fma(sh.Dv[r * NJ + i], sh.Dv[r * NJ + j], s); }
+      else if (j < NJ + NX) { for (int r = 0; r < mr; ++r) s = fma(-sh.Dv[r * NJ + i], sh.Cv[r * NX + j - NJ], s); }
+      else { for (int r = 0; r < mr; ++r) s = fma(-sh.Dv[r * NJ + i], sh.ev[r], s); }
+      G[i * GL + j] = s;
+    }
   }
   if (lane < NJ) sh.piv[lane] = 0;
   __syncwarp();
@@ -487,19 +515,20 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     if (!(dv > tol)) break;
     const int p = pi;
     const double inv = 1.0 / dv;
-    for (int j = lane; j < GW; j += 32) G[p * GL + j] *= inv;
-    if (lane == 0) sh.piv[p] = 1;
-    __syncwarp();
+    // lane j owns column j (j < 32) of the 10 x 33 tableau; the last column (index 32) is updated by lane i for row i
+    static_assert(GW == 33, "column ownership below assumes 33 columns");
+    const double pj = G[p * GL + lane] * inv;                   // scaled pivot-row entry of this lane's column
+    const double p32 = G[p * GL + 32] * inv;
     const double colv = (lane < NJ) ? G[lane * GL + p] : 0.0;   // column p before elimination, one entry per lane
     __syncwarp();
-#pragma unroll 1
-    for (int t = 0; t < (NJ * GW + 31) / 32; ++t) {
-      const int idx = lane + 32 * t;
-      const bool valid = idx < NJ * GW;
-      const int i = valid ? idx / GW : 0, j = valid ? idx - i * GW : 0;
+    G[p * GL + lane] = pj;
+    if (lane == 0) { G[p * GL + 32] = p32; sh.piv[p] = 1; }
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
       const double ci = __shfl_sync(HB_FULL_MASK, colv, i);
-      if (valid && i != p) G[i * GL + j] -= ci * G[p * GL + j];
+      if (i != p) G[i * GL + lane] -= ci * pj;
     }
+    if (lane < NJ && lane != p) G[lane * GL + 32] -= colv * p32;
     __syncwarp();
   }
   int nv = 0;
