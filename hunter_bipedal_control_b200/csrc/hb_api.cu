@@ -678,7 +678,7 @@ int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x
   ctx->launches++;
   CK(cudaGetLastError());
   prof_begin(ctx, K_BACKWARD);
-  riccati_kernel<<<B, 32, sizeof(RicShared), ctx->stream>>>(a);
+  riccati_kernel<<<B, 64, sizeof(RicShared), ctx->stream>>>(a);
   prof_end(ctx);
   ctx->launches++;
   CK(cudaGetLastError());

@@ -632,7 +632,15 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     sh.bt[i] = s;
   }
   __syncwarp();
-  // Rt (ntp x ntp), Pt (ntp x 22), rt (ntp); RN = Rvv Nv computed on the fly per entry
+  // Rt (ntp x ntp), Pt (ntp x 22), rt (ntp); RN = Rvv Nv (10 x nv) goes into the dead constraint-row storage first
+  double* RN = sh.Cv;
+  for (int idx = lane; idx < NJ * NVMAX; idx += 32) {
+    const int p = idx / NVMAX, cj = idx - p * NVMAX;
+    double t = 0.0;
+    if (cj < nv) { for (int qq = 0; qq < NJ; ++qq) t = fma(sh.Rvv[p * NJ + qq], sh.Nv[qq * NVMAX + cj], t); }
+    RN[idx] = t;
+  }
+  __syncwarp();
   for (int idx = lane; idx < NTMAX * NTMAX; idx += 32) {
     const int i = idx / NTMAX, j = idx - i * NTMAX;
     double s = 0.0;
@@ -640,7 +648,7 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     else if (i < nf && j < nf) s = sh.RFF[sh.stidx[i] * 12 + sh.stidx[j]];
     else if (i >= nf && j >= nf) {
       const int ci = i - nf, cj = j - nf;
-      for (int p = 0; p < NJ; ++p) { double t = 0.0; for (int qq = 0; qq < NJ; ++qq) t = fma(sh.Rvv[p * NJ + qq], sh.Nv[qq * NVMAX + cj], t); s = fma(sh.Nv[p * NVMAX + ci], t, s); }
+      for (int p = 0; p < NJ; ++p) s = fma(sh.Nv[p * NVMAX + ci], RN[p * NVMAX + cj], s);
     }
     out[PJ_RT + i * NTMAX + j] = dt * s;
   }
@@ -718,116 +726,138 @@ __device__ __forceinline__ void ric_prefetch(RicNodeIn& n, const double* __restr
   cp_async_commit();
 }
 
+// One node of the recursion, executed by the TWO warps of the block. The products that do not depend on each other are split
+// between the warps (by result columns, so that every row-owner product keeps its full lane utilisation); the Cholesky of Huu and
+// the gain solve (one warp, latency bound) overlap with the largest product At' S At of the other warp.
 template <int NTP>
-__device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, const double* __restrict__ rec, double* __restrict__ rk, bool& fail) {
+__device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, const double* __restrict__ rec, double* __restrict__ rk, bool& fail,
+                                          int warp) {
   const int lane = lane_id();
   double* SB = sh.SBK; double* K = sh.SBK;
-  // SA = S At ; SB = S Bt ; sb = s + S bt
-  rowmm<NX, false, 0>(sh.SA, NX, sh.S, NX, in.At, NX, NX, NX);
-  rowmm<NTP, false, 0>(SB, NTMAX, sh.S, NX, in.Bt, NTMAX, NX, NX);
-  if (lane < NX) {
-    double s0 = sh.sv[lane], s1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < NX; k += 2) { s0 = fma(sh.S[lane * NX + k], in.bt[k], s0); s1 = fma(sh.S[lane * NX + k + 1], in.bt[k + 1], s1); }
-    sh.sb[lane] = s0 + s1;
-  }
-  __syncwarp();
-  // S is dead until the end of the node: stage Qt into it now (arrives while the gains are computed)
-  for (int i = 2 * lane; i < TS; i += 64) cp_async16(sh.S + i, rec + PJ_QT + i);
-  cp_async_commit();
-  // Hux^T (22 x NTP) = Pt^T + SA^T Bt ; Huu (NTP x NTP) = Rt + Bt^T SB ; hu = rt + Bt^T sb   (Pt^T, Rt were staged at node start)
-  rowmm<NTP, true, 1>(sh.HuxT, NTMAX, sh.SA, NX, in.Bt, NTMAX, NX, NX);
-  rowmm<NTP, true, 1>(sh.Huu, 18, in.Bt, NTMAX, SB, NTMAX, NTP, NX);
-  if (lane < NTP) {
-    double s0 = in.rt[lane];
-#pragma unroll
-    for (int k = 0; k < NX; ++k) s0 = fma(in.Bt[k * NTMAX + lane], sh.sb[k], s0);
-    sh.hu[lane] = s0;
-  }
-  __syncwarp();
-  if (lane < NTP) {
-#pragma unroll
-    for (int c = 0; c < NTP; ++c) if (c < lane) sh.Huu[lane * 18 + c] = 0.5 * (sh.Huu[lane * 18 + c] + sh.Huu[c * 18 + lane]);
-  }
-  __syncwarp();
-  if (!warp_chol_inv(sh.Huu, NTP, 18, sh.idg, lane)) fail = true;
-  if (lane <= NX) {
-    double col[NTP], y[NTP];
-#pragma unroll
-    for (int c = 0; c < NTP; ++c) col[c] = (lane < NX) ? sh.HuxT[lane * NTMAX + c] : sh.hu[c];
-#pragma unroll
-    for (int c = 0; c < NTP; ++c) {
-      double s = sh.idg[c] * col[c];
-#pragma unroll
-      for (int kk = 0; kk < c; ++kk) s = fma(sh.Huu[kk * 18 + c], col[kk], s);
-      y[c] = s;
-    }
-#pragma unroll
-    for (int c = 0; c < NTP; ++c) {
-      double s = sh.idg[c] * y[c];
-#pragma unroll
-      for (int kk = c + 1; kk < NTP; ++kk) s = fma(sh.Huu[c * 18 + kk], y[kk], s);
-      col[c] = -s;
-    }
+  // ---- phase A: [SA | SB | sb] = S [At | Bt | bt] (+ s): 22 + NTP + 1 result columns, split 16 / rest
+  if (warp == 0) {
+    rowmm<16, false, 0>(sh.SA, NX, sh.S, NX, in.At, NX, NX, NX);
+    cp_async_wait<0>();                       // Pt^T / Rt staged by this warp at the top of the node
+  } else {
+    rowmm<6, false, 0>(sh.SA + 16, NX, sh.S, NX, in.At + 16, NX, NX, NX);
+    rowmm<NTP, false, 0>(SB, NTMAX, sh.S, NX, in.Bt, NTMAX, NX, NX);
     if (lane < NX) {
+      double s0 = sh.sv[lane], s1 = 0.0;
 #pragma unroll
-      for (int c = 0; c < NTP; ++c) { K[c * NX + lane] = col[c]; rk[c * NX + lane] = col[c]; }     // SB is dead: K takes its place
-    } else {
-#pragma unroll
-      for (int c = 0; c < NTP; ++c) { sh.kff[c] = col[c]; rk[NTMAX * NX + c] = col[c]; }
+      for (int k = 0; k < NX; k += 2) { s0 = fma(sh.S[lane * NX + k], in.bt[k], s0); s1 = fma(sh.S[lane * NX + k + 1], in.bt[k + 1], s1); }
+      sh.sb[lane] = s0 + s1;
     }
   }
-  __syncwarp();
-  // s <- qt + At' sb + Hux' kff
-  if (lane < NX) {
-    double s0 = in.qt[lane], s1 = 0.0;
+  __syncthreads();
+  // ---- phase B: Hux^T (22 x NTP) = Pt^T + SA^T Bt (warp 0) ; Huu = Rt + Bt^T SB, hu = rt + Bt^T sb (warp 1)
+  if (warp == 0) {
+    rowmm<NTP, true, 1>(sh.HuxT, NTMAX, sh.SA, NX, in.Bt, NTMAX, NX, NX);
+  } else {
+    // S is dead until phase D: stage Qt into it now (arrives while Huu is formed)
+    for (int i = 2 * lane; i < TS; i += 64) cp_async16(sh.S + i, rec + PJ_QT + i);
+    cp_async_commit();
+    rowmm<NTP, true, 1>(sh.Huu, 18, in.Bt, NTMAX, SB, NTMAX, NTP, NX);
+    if (lane < NTP) {
+      double s0 = in.rt[lane];
 #pragma unroll
-    for (int k = 0; k < NX; k += 2) { s0 = fma(in.At[k * NX + lane], sh.sb[k], s0); s1 = fma(in.At[(k + 1) * NX + lane], sh.sb[k + 1], s1); }
-#pragma unroll
-    for (int c = 0; c < NTP; ++c) s0 = fma(sh.HuxT[lane * NTMAX + c], sh.kff[c], s0);
-    sh.sv[lane] = s0 + s1;
+      for (int k = 0; k < NX; ++k) s0 = fma(in.Bt[k * NTMAX + lane], sh.sb[k], s0);
+      sh.hu[lane] = s0;
+    }
   }
-  cp_async_wait<0>();   // Qt has landed in S
-  __syncwarp();
-  // S = Qt + At' SA + Hux' K
-  rowmm<NX, true, 1>(sh.S, NX, in.At, NX, sh.SA, NX, NX, NX);
-  rowmm<NX, false, 1>(sh.S, NX, sh.HuxT, NTMAX, K, NX, NX, NTP);
-  for (int idx = lane; idx < TS; idx += 32) { const int i = idx / NX, j = idx - i * NX; if (j > i) { const double v = 0.5 * (sh.S[idx] + sh.S[j * NX + i]); sh.S[idx] = v; sh.S[j * NX + i] = v; } }
-  __syncwarp();
+  __syncthreads();
+  // ---- phase C: gains (warp 0) || S = Qt + At' SA (warp 1)
+  if (warp == 0) {
+    if (lane < NTP) {
+#pragma unroll
+      for (int c = 0; c < NTP; ++c) if (c < lane) sh.Huu[lane * 18 + c] = 0.5 * (sh.Huu[lane * 18 + c] + sh.Huu[c * 18 + lane]);
+    }
+    __syncwarp();
+    if (!warp_chol_inv(sh.Huu, NTP, 18, sh.idg, lane)) fail = true;
+    if (lane <= NX) {
+      double col[NTP], y[NTP];
+#pragma unroll
+      for (int c = 0; c < NTP; ++c) col[c] = (lane < NX) ? sh.HuxT[lane * NTMAX + c] : sh.hu[c];
+#pragma unroll
+      for (int c = 0; c < NTP; ++c) {
+        double s = sh.idg[c] * col[c];
+#pragma unroll
+        for (int kk = 0; kk < c; ++kk) s = fma(sh.Huu[kk * 18 + c], col[kk], s);
+        y[c] = s;
+      }
+#pragma unroll
+      for (int c = 0; c < NTP; ++c) {
+        double s = sh.idg[c] * y[c];
+#pragma unroll
+        for (int kk = c + 1; kk < NTP; ++kk) s = fma(sh.Huu[c * 18 + kk], y[kk], s);
+        col[c] = -s;
+      }
+      if (lane < NX) {
+#pragma unroll
+        for (int c = 0; c < NTP; ++c) { K[c * NX + lane] = col[c]; rk[c * NX + lane] = col[c]; }     // SB is dead: K takes its place
+      } else {
+#pragma unroll
+        for (int c = 0; c < NTP; ++c) { sh.kff[c] = col[c]; rk[NTMAX * NX + c] = col[c]; }
+      }
+    }
+    __syncwarp();
+    // s <- qt + At' sb + Hux' kff
+    if (lane < NX) {
+      double s0 = in.qt[lane], s1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < NX; k += 2) { s0 = fma(in.At[k * NX + lane], sh.sb[k], s0); s1 = fma(in.At[(k + 1) * NX + lane], sh.sb[k + 1], s1); }
+#pragma unroll
+      for (int c = 0; c < NTP; ++c) s0 = fma(sh.HuxT[lane * NTMAX + c], sh.kff[c], s0);
+      sh.sv[lane] = s0 + s1;
+    }
+  } else {
+    cp_async_wait<0>();   // Qt has landed in S (and the next node's inputs, issued by this warp at the top of the node)
+    __syncwarp();
+    rowmm<NX, true, 1>(sh.S, NX, in.At, NX, sh.SA, NX, NX, NX);
+  }
+  __syncthreads();
+  // ---- phase D: S += Hux' K, result columns split 12 / 10
+  if (warp == 0) rowmm<12, false, 1>(sh.S, NX, sh.HuxT, NTMAX, K, NX, NX, NTP);
+  else rowmm<10, false, 1>(sh.S + 12, NX, sh.HuxT, NTMAX, K + 12, NX, NX, NTP);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TS; idx += 64) { const int i = idx / NX, j = idx - i * NX; if (j > i) { const double v = 0.5 * (sh.S[idx] + sh.S[j * NX + i]); sh.S[idx] = v; sh.S[j * NX + i] = v; } }
+  __syncthreads();
 }
 
-__global__ void __launch_bounds__(32) riccati_kernel(SqpArgs a) {
+__global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RicShared& sh = *reinterpret_cast<RicShared*>(smem_raw);
-  const int inst = blockIdx.x, lane = threadIdx.x, N = a.N;
+  const int inst = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, N = a.N;
   const double* proj = a.proj + (size_t)inst * N * PJ_STRIDE;
-  ric_prefetch(sh.in[(N - 1) & 1], proj + (size_t)(N - 1) * PJ_STRIDE, lane);
-  for (int idx = lane; idx < TS; idx += 32) sh.S[idx] = 0.0;   // no terminal cost
-  if (lane < NX) sh.sv[lane] = 0.0;
-  __syncwarp();
+  // warp 1 owns the node-input prefetch (and the Qt staging), warp 0 the Pt^T / Rt staging; each waits for its own groups
+  if (warp == 1) ric_prefetch(sh.in[(N - 1) & 1], proj + (size_t)(N - 1) * PJ_STRIDE, lane);
+  for (int idx = threadIdx.x; idx < TS; idx += 64) sh.S[idx] = 0.0;   // no terminal cost
+  if (threadIdx.x < NX) sh.sv[threadIdx.x] = 0.0;
   bool fail = false;
   double merit = 0.0, dyn = 0.0, eqs = 0.0;
   for (int k = N - 1; k >= 0; --k) {
     const double* rec = proj + (size_t)k * PJ_STRIDE;
     double* rk = a.rk + ((size_t)inst * N + k) * RK_STRIDE;
-    // stage Pt^T -> HuxT (22 x 16) and Rt -> Huu (16 rows of 16, leading dimension 18) for this node, then the next node's inputs
-    for (int i = 2 * lane; i < NX * NTMAX; i += 64) cp_async16(sh.HuxT + i, rec + PJ_PT + i);
-    for (int c = lane; c < NTMAX * 8; c += 32) { const int r = c >> 3, q = c & 7; cp_async16(sh.Huu + r * 18 + 2 * q, rec + PJ_RT + r * NTMAX + 2 * q); }
-    cp_async_commit();
-    if (k > 0) { ric_prefetch(sh.in[(k - 1) & 1], proj + (size_t)(k - 1) * PJ_STRIDE, lane); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
-    __syncwarp();
+    if (warp == 1) cp_async_wait<0>();        // inputs of node k (prefetched one node ahead)
+    __syncthreads();
+    if (warp == 0) {
+      // stage Pt^T -> HuxT (22 x 16) and Rt -> Huu (16 rows of 16, leading dimension 18) for this node
+      for (int i = 2 * lane; i < NX * NTMAX; i += 64) cp_async16(sh.HuxT + i, rec + PJ_PT + i);
+      for (int c = lane; c < NTMAX * 8; c += 32) { const int r = c >> 3, q = c & 7; cp_async16(sh.Huu + r * 18 + 2 * q, rec + PJ_RT + r * NTMAX + 2 * q); }
+      cp_async_commit();
+    } else if (k > 0) {
+      ric_prefetch(sh.in[(k - 1) & 1], proj + (size_t)(k - 1) * PJ_STRIDE, lane);
+    }
     const RicNodeIn& in = sh.in[k & 1];
     const int nt = (int)in.meta[0];
     merit += a.dt * in.meta[3]; dyn += a.dt * in.meta[4]; eqs += a.dt * in.meta[5];
     if (in.meta[6] != 0.0) fail = true;
     const int ntp = ntp_of(nt);
-    if (ntp == 12) riccati_node<12>(sh, in, rec, rk, fail);
-    else if (ntp == 10) riccati_node<10>(sh, in, rec, rk, fail);
-    else if (ntp == 6) riccati_node<6>(sh, in, rec, rk, fail);
-    else riccati_node<16>(sh, in, rec, rk, fail);
+    if (ntp == 12) riccati_node<12>(sh, in, rec, rk, fail, warp);
+    else if (ntp == 10) riccati_node<10>(sh, in, rec, rk, fail, warp);
+    else if (ntp == 6) riccati_node<6>(sh, in, rec, rk, fail, warp);
+    else riccati_node<16>(sh, in, rec, rk, fail, warp);
   }
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
     double* pf = a.perf + (size_t)inst * 4;
     pf[0] = merit; pf[1] = dyn; pf[2] = eqs; pf[3] = 0.0;
     a.flags[inst] = fail ? 1 : 0;
