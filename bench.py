@@ -235,6 +235,29 @@ def main():
     e2e_s = time.perf_counter() - t0
     h2d = (h_t0.numel() + h_x0.numel() + h_rbd.numel()) * 8 + ref_bytes
     d2h = (h_info.numel() + h_sol.numel() + h_tau.numel()) * 8 + h_st.numel() * 4
+    # e2e_plan_cycle: hb_resident_plan_cycle_batch -- plan inputs (t0, x0, cmd_vel, gait; 352 B per instance) and rbd in; foot positions, the
+    # reference planner (gait tiling, swing planner, IK joint references), expansion, cold start, solve, WBC all on the device.
+    ins = hb.make_plan_inputs(np.zeros(B), HORIZON_N * DT, x0, (0.2, 0.0, 0.0, 0.0), None, "trot", 0.1)
+    plan_bytes = C.sizeof(ins)
+    h_ins = torch.empty(plan_bytes, dtype=torch.uint8).pin_memory()
+    C.memmove(h_ins.data_ptr(), C.addressof(ins), plan_bytes)
+    h_ps = torch.zeros(B, dtype=torch.int32).pin_memory()
+
+    def step_plan():
+        rc = lib.hb_resident_plan_cycle_batch(ctx._h, B, 1, C.c_double(T_POLICY), P(h_ins), P(h_rbd), P(h_info), P(h_sol), P(h_tau), P(h_st), P(h_ps))
+        assert rc == 0, rc
+
+    for _ in range(2):
+        step_plan()
+    barrier()
+    plan_ok = bool((h_ps.numpy() == 0).all() and (h_st.numpy() == 0).all())
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_plan()
+    barrier()
+    plan_s = time.perf_counter() - t0
+    plan_h2d = plan_bytes + h_rbd.numel() * 8
+    plan_d2h = (h_info.numel() + h_sol.numel() + h_tau.numel()) * 8 + h_st.numel() * 4 + h_ps.numel() * 4
     # every full-trajectory step gets its own pre-initialised in/out trajectory buffers (cold start): no host-side reset in the timed region
     n_e2e = args.steps + 2
     h_xts = [d_xt0.cpu().pin_memory() for _ in range(n_e2e)]; h_uts = [d_ut0.cpu().pin_memory() for _ in range(n_e2e)]
@@ -261,11 +284,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     # ---------------- max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_s * 1e3, full_s * 1e3], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_s * 1e3, full_s * 1e3, plan_s * 1e3], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, full_ms = float(t[0]), float(t[1]), float(t[2])
+        ms, e2e_ms, full_ms, plan_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     else:
-        e2e_ms, full_ms = e2e_s * 1e3, full_s * 1e3
+        e2e_ms, full_ms, plan_ms = e2e_s * 1e3, full_s * 1e3, plan_s * 1e3
     ok = bool((d_st == 0).all().item())
     if rank == 0:
         peaks, src = load_peaks()
@@ -293,6 +316,9 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
                         "call": "hb_resident_cycle_batch(cold_start=1): t0, x0, compact references, rbd in; info, WBC solution, torques, status out",
                         "torque_max_rel_diff_vs_device_path": e2e_tau_diff},
+                "e2e_plan_cycle": {"value": total_B * args.steps / (plan_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(plan_h2d), "d2h_bytes_per_step": int(plan_d2h),
+                                   "ms_per_step": plan_ms / args.steps, "all_planned_and_solved": plan_ok,
+                                   "call": "hb_resident_plan_cycle_batch(cold_start=1): plan inputs + rbd in; reference planner (P1, P3, P4, P5) on the device; same gait / command as the workload"},
                 "e2e_full_trajectories": {"value": total_B * args.steps / (full_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(full_h2d),
                                           "d2h_bytes_per_step": int(full_d2h), "ms_per_step": full_ms / args.steps,
                                           "call": "hb_control_step_batch: node-sampled references and full trajectories both ways"},

@@ -23,7 +23,8 @@ EXPORTED_SYMBOLS = [
     "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_last_cuda_error", "hb_launch_count", "hb_stream", "hb_profile_enable", "hb_profile_read",
     "hb_wbc_qp_batch_dev", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
     "hb_policy_eval_batch_dev", "hb_control_step_batch_dev", "hb_rbd_to_centroidal_batch_dev", "hb_reference_expand_batch_dev",
-    "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references", "hb_gait_select", "hb_resident_cycle_batch_dev", "hb_resident_cycle_batch", "hb_resident_read_batch", "hb_default_pd_gains", "hb_joint_command_batch_dev", "hb_joint_command_batch",
+    "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references", "hb_gait_select", "hb_resident_cycle_batch_dev", "hb_resident_cycle_batch", "hb_resident_read_batch", "hb_plan_references_batch_dev",
+    "hb_plan_references_gpu", "hb_resident_plan_cycle_batch", "hb_default_pd_gains", "hb_joint_command_batch_dev", "hb_joint_command_batch",
     "hb_wbc_qp_batch", "hb_wbc_solve_batch", "hb_mpc_cold_start_batch", "hb_mpc_solve_batch", "hb_control_step_batch",
     "hb_rbd_to_centroidal_batch", "hb_reference_expand_batch", "hb_probe_flow_map",
 ]
@@ -89,6 +90,25 @@ class GaitSelector:
 
 
 GAIT_IDS = {"stance": 0, "trot": 1, "standing_trot": 2, "flying_trot": 3}
+
+
+def make_plan_inputs(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event=None, time_to_target=None, joint_ik=True):
+    """ctypes array of HbPlanInput for a batch (feet_pos may be None when the device computes it)."""
+    x0 = _f64(x0); B = x0.shape[0]
+    cmd_vel = np.broadcast_to(_f64(cmd_vel), (B, 4))
+    feet_pos = np.zeros((B, 12)) if feet_pos is None else _f64(feet_pos).reshape(B, 12)
+    t0 = np.broadcast_to(_f64(t0), (B,)); gait_start = np.broadcast_to(_f64(gait_start), (B,))
+    ins = (HbPlanInput * B)()
+    for i in range(B):
+        p = ins[i]
+        p.t0 = t0[i]; p.horizon = horizon; p.time_to_target = horizon if time_to_target is None else time_to_target
+        p.gait_start = gait_start[i]; p.prev_event = (min(t0[i], gait_start[i]) - 0.5) if prev_event is None else prev_event
+        p.gait = GAIT_IDS[gait[i]] if isinstance(gait, (list, tuple)) else GAIT_IDS[gait]
+        p.joint_ik = 1 if joint_ik else 0
+        for j in range(22): p.x0[j] = x0[i, j]
+        for j in range(4): p.cmd_vel[j] = cmd_vel[i, j]
+        for j in range(12): p.feet_pos[j] = feet_pos[i, j]
+    return ins
 
 
 def plan_references(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event=None, time_to_target=None, latest_stance=None, joint_ik=True):
@@ -261,6 +281,22 @@ class Context:
         t0 = np.zeros(B); xt = np.zeros((B, self.N + 1, NX)); ut = np.zeros((B, self.N, NU))
         _check(self._lib.hb_resident_read_batch(self._h, B, _ptr(t0), _ptr(xt), _ptr(ut)), "hb_resident_read_batch", self._h)
         return t0, xt, ut
+
+    def plan_references_gpu(self, ins, latest_stance=None):
+        """Device planner with host pointers: returns (refs, latest_stance, status)."""
+        B = len(ins)
+        ls = np.zeros((B, 12)) if latest_stance is None else _f64(latest_stance).copy()
+        refs = (HbReference * B)(); st = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_plan_references_gpu(self._h, B, ins, _ptr(ls), refs, _ptr(st)), "hb_plan_references_gpu", self._h)
+        return refs, ls, st
+
+    def resident_plan_cycle(self, cold_start, t_rel, ins, rbd):
+        """Whole cycle from plan inputs (hb_resident_plan_cycle_batch). Returns (info, sol, torque, wbc_status, plan_status)."""
+        rbd = _f64(rbd); B = len(ins)
+        info = np.zeros(B, dtype=INFO_DTYPE); sol = np.zeros((B, NWBC)); tau = np.zeros((B, NJ)); st = np.zeros(B, dtype=np.int32); ps = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_resident_plan_cycle_batch(self._h, B, 1 if cold_start else 0, C.c_double(t_rel), ins, _ptr(rbd), _ptr(info), _ptr(sol), _ptr(tau),
+                                                      _ptr(st), _ptr(ps)), "hb_resident_plan_cycle_batch", self._h)
+        return info, sol, tau, st, ps
 
     def joint_command(self, period, x_des, u_des, wbc_sol, mode_cmd, rbd, loaded=None, estop=None, gains=None):
         """Joint command law (LeggedController.cpp:186-257): returns (command [B,10,5], output_torque [B,10], estop [B])."""

@@ -11,7 +11,9 @@
 #include "hb_common.cuh"
 #include "hb_mpc.cuh"
 #include "hb_planner.h"
+#include <algorithm>
 #include <thread>
+#include <vector>
 #include "hb_qp.cuh"
 #include "hb_rbd.cuh"
 #include "hb_sqp.cuh"
@@ -336,6 +338,38 @@ __global__ void contact_positions_kernel(int B, const double* x, double* pos) {
   for (int i = 0; i < 12; ++i) pos[(size_t)inst * 12 + i] = o.cpos[i];
 }
 
+// Device planner (row N1): one thread per instance runs the same source as the host planner (csrc/hb_planner.h).
+// plan_prepare_kernel unpacks t0 / x0 from the plan inputs and evaluates computeFootPos at x0 (the planner's current_feet input).
+__global__ void plan_prepare_kernel(int B, const hb_plan_input* in, double* t0, double* x0, double* feet) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= B) return;
+  const hb_plan_input& p = in[inst];
+  double q[NQ], v[NQ];
+  for (int i = 0; i < NX; ++i) x0[(size_t)inst * NX + i] = p.x0[i];
+  for (int i = 0; i < NQ; ++i) { q[i] = p.x0[6 + i]; v[i] = 0.0; }
+  t0[inst] = p.t0;
+  KinOut<double> o;
+  kin_pass<double>(q, v, o);
+  for (int i = 0; i < 12; ++i) feet[(size_t)inst * 12 + i] = o.cpos[i];
+}
+
+__global__ void __launch_bounds__(8) plan_references_kernel(int B, const hb_plan_input* in, const double* feet, double* latest_stance, hb_reference* out,
+                                                            int32_t* status, hbplan::PlanConsts pc) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= B) return;
+  hb_plan_input p = in[inst];
+  if (feet) for (int i = 0; i < 12; ++i) p.feet_pos[i] = feet[(size_t)inst * 12 + i];
+  hb_reference* o = out + inst;
+  const int rc = hbplan::plan_one(pc, p, latest_stance + (size_t)inst * 12, o, false);
+  if (rc != 0) {
+    // a safe, empty reference (stance, target = current pose) so that the rest of the cycle stays well defined; status reports the error
+    o->n_events = 0; o->modes[0] = 3; o->n_targets = 1; o->target_times[0] = p.t0;
+    for (int i = 0; i < 22; ++i) o->target_states[0][i] = (i < 6) ? 0.0 : p.x0[i];
+    for (int c = 0; c < 4; ++c) for (int a = 0; a < 3; ++a) o->n_segments[c][a] = 0;
+  }
+  if (status) status[inst] = rc;
+}
+
 // parity probe: flow map value, Jacobians and contact kinematics from the warp-cooperative linearisation
 __global__ void __launch_bounds__(32) probe_flow_map_kernel(int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -376,6 +410,7 @@ struct hb_ctx {
   double *s_x0, *s_xref, *s_swing, *s_xt, *s_ut, *s_rbd, *s_xd, *s_ud, *s_sol, *s_tau, *s_t0, *s_misc;
   double *res_xt = nullptr, *res_ut = nullptr, *res_t0 = nullptr;   // resident primal solution (hb_resident_cycle_batch)
   int res_valid = 0;                                                // number of instances holding a previous solution
+  hb_plan_input* s_plan = nullptr; double* res_stance = nullptr; int32_t* s_pstatus = nullptr;   // device planner (row N1)
   int32_t *s_mode, *s_imode, *s_status, *s_iters;
   uint8_t* s_stance;
   hb_solve_info* s_info;
@@ -499,6 +534,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   ok = ok && dalloc(&ctx->xdes, B * NX) == cudaSuccess && dalloc(&ctx->udes, B * NU) == cudaSuccess && dalloc(&ctx->wsol, B * NWBC) == cudaSuccess;
   ok = ok && dalloc(&ctx->wstatus, B) == cudaSuccess && dalloc(&ctx->witers, B) == cudaSuccess && dalloc(&ctx->wmode, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_x0, B * NX) == cudaSuccess && dalloc(&ctx->s_xref, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_swing, B * (N + 1) * 24) == cudaSuccess;
+  ok = ok && dalloc(&ctx->s_plan, B) == cudaSuccess && dalloc(&ctx->res_stance, B * 12) == cudaSuccess && dalloc(&ctx->s_pstatus, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->res_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->res_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->res_t0, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->s_rbd, B * 32) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_xd, B * NX) == cudaSuccess && dalloc(&ctx->s_ud, B * NU) == cudaSuccess && dalloc(&ctx->s_sol, B * NWBC) == cudaSuccess;
@@ -525,7 +561,7 @@ int hb_destroy(hb_ctx* ctx) {
   void* ptrs[] = {ctx->lin, ctx->proj, ctx->rk, ctx->gains, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->qH, ctx->qg, ctx->qA, ctx->qlb, ctx->qub, ctx->qm, ctx->xdes, ctx->udes,
                   ctx->wsol, ctx->wstatus, ctx->witers, ctx->wmode, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_xt, ctx->s_ut, ctx->s_rbd, ctx->s_xd,
                   ctx->s_ud, ctx->s_sol, ctx->s_tau, ctx->s_t0, ctx->s_misc, ctx->s_mode, ctx->s_imode, ctx->s_status, ctx->s_iters, ctx->s_stance,
-                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0};
+                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
   if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
@@ -755,6 +791,18 @@ int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel
   return hb_control_step_batch_dev(ctx, B, t_rel, x0, xref, swing, mode, rbd, xt, ut, info, wbc_sol, torque, wbc_status);
 }
 
+int hb_plan_references_batch_dev(hb_ctx* ctx, int B, const hb_plan_input* in, const double* feet, double* latest_stance, hb_reference* out,
+                                 int32_t* status) {
+  if (!ctx || B < 0 || !in || !latest_stance || !out) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  static const hbplan::PlanConsts pc = hbplan::make_consts();
+  plan_references_kernel<<<(B + 7) / 8, 8, 0, ctx->stream>>>(B, in, feet, latest_stance, out, status, pc);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
 int hb_default_pd_gains(hb_pd_gains* g) {
   if (!g) return HB_EINVAL;
   g->kp_position = 10.0; g->kd_position = 3.0;
@@ -978,6 +1026,64 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
   return HB_OK;
 }
 
+int hb_plan_references_gpu(hb_ctx* ctx, int B, const hb_plan_input* in, double* latest_stance, hb_reference* out, int32_t* status) {
+  if (!ctx || B < 0 || !in || !latest_stance || !out) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  H2D(ctx->s_plan, in, sizeof(hb_plan_input) * B);
+  H2D(ctx->s_misc, latest_stance, sizeof(double) * B * 12);
+  int rc = hb_plan_references_batch_dev(ctx, B, ctx->s_plan, nullptr, ctx->s_misc, ctx->s_refs, ctx->s_pstatus);
+  if (rc) return rc;
+  D2H(out, ctx->s_refs, sizeof(hb_reference) * B);
+  D2H(latest_stance, ctx->s_misc, sizeof(double) * B * 12);
+  if (status) D2H(status, ctx->s_pstatus, sizeof(int32_t) * B);
+  return hb_sync(ctx);
+}
+
+int hb_resident_plan_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, const hb_plan_input* in, const double* rbd, hb_solve_info* info,
+                                 double* wbc_sol, double* torque, int32_t* wbc_status, int32_t* plan_status) {
+  if (!ctx || B < 0 || !in || !rbd) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (!cold_start && ctx->res_valid < B) return HB_EINVAL;
+  if (set_device(ctx)) return HB_ECUDA;
+  const int nchunk = (B >= 256 && ctx->sqp_version == 2) ? 2 : 1;
+  int rc = HB_OK;
+  for (int c = 0; c < nchunk && rc == HB_OK; ++c) {
+    const size_t lo = (size_t)B * c / nchunk, hi = (size_t)B * (c + 1) / nchunk, n = hi - lo;
+    ctx->stream = (c % 2 == 0) ? ctx->stream_main : ctx->stream_aux;
+    ctx->base = (int)lo;
+    cudaError_t e = cudaSuccess;
+    auto h2d = [&](void* d, const void* h, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream); };
+    auto d2h = [&](void* h, const void* d, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream); };
+    h2d(ctx->s_plan + lo, in + lo, sizeof(hb_plan_input) * n);
+    h2d(ctx->s_rbd + lo * 32, rbd + lo * 32, sizeof(double) * n * 32);
+    if (cold_start && e == cudaSuccess) e = cudaMemsetAsync(ctx->res_stance + lo * 12, 0, sizeof(double) * n * 12, ctx->stream);   // latestStanceposition_ starts at zero
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = HB_ECUDA; break; }
+    double* feet = ctx->s_misc + lo * 12;
+    plan_prepare_kernel<<<((int)n + 63) / 64, 64, 0, ctx->stream>>>((int)n, ctx->s_plan + lo, ctx->s_t0 + lo, ctx->s_x0 + lo * NX, feet);
+    ctx->launches++;
+    rc = hb_plan_references_batch_dev(ctx, (int)n, ctx->s_plan + lo, feet, ctx->res_stance + lo * 12, ctx->s_refs + lo, ctx->s_pstatus + lo);
+    if (rc) break;
+    rc = hb_resident_cycle_batch_dev(ctx, (int)n, cold_start, t_rel, ctx->s_t0 + lo, ctx->s_x0 + lo * NX, ctx->s_refs + lo, ctx->s_rbd + lo * 32,
+                                     ctx->s_info + lo, ctx->s_sol + lo * NWBC, ctx->s_tau + lo * NJ, ctx->s_status + lo);
+    if (rc) break;
+    if (info) d2h(info + lo, ctx->s_info + lo, sizeof(hb_solve_info) * n);
+    if (wbc_sol) d2h(wbc_sol + lo * NWBC, ctx->s_sol + lo * NWBC, sizeof(double) * n * NWBC);
+    if (torque) d2h(torque + lo * NJ, ctx->s_tau + lo * NJ, sizeof(double) * n * NJ);
+    if (wbc_status) d2h(wbc_status + lo, ctx->s_status + lo, sizeof(int32_t) * n);
+    if (plan_status) d2h(plan_status + lo, ctx->s_pstatus + lo, sizeof(int32_t) * n);
+    if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = HB_ECUDA; }
+  }
+  ctx->stream = ctx->stream_main;
+  ctx->base = 0;
+  cudaError_t e1 = cudaStreamSynchronize(ctx->stream_aux), e0 = cudaStreamSynchronize(ctx->stream_main);
+  if (rc) return rc;
+  if (e0 != cudaSuccess || e1 != cudaSuccess) { ctx->last_cuda = (int)(e0 != cudaSuccess ? e0 : e1); return HB_ECUDA; }
+  return HB_OK;
+}
+
 int hb_resident_read_batch(hb_ctx* ctx, int B, double* t0, double* x_traj, double* u_traj) {
   if (!ctx || B < 0) return HB_EINVAL;
   if (B == 0) return HB_OK;
@@ -1050,18 +1156,10 @@ int hb_contact_positions_batch(hb_ctx* ctx, int B, const double* x, double* pos)
 }
 
 static int plan_range(int lo, int hi, const hb_plan_input* in, double* latest_stance, hb_reference* out) {
+  static const hbplan::PlanConsts pc = hbplan::make_consts();
   for (int i = lo; i < hi; ++i) {
-    const hb_plan_input& p = in[i];
-    if (!(p.horizon > 0.0) || !(p.prev_event < p.gait_start) || p.gait < 0 || p.gait > 3) return HB_EINVAL;
-    const double tf = p.t0 + p.horizon;
-    // the reference tiles over [t0 - T, tf + T] (SwitchedModelReferenceManager.cpp:147)
-    hbplan::ModeSchedule ms = hbplan::tile_gait(p.gait, p.prev_event, p.gait_start, tf + p.horizon);
-    hbplan::Target tg = hbplan::cmd_vel_to_target(p.cmd_vel, p.t0, p.x0, p.time_to_target);
-    const double body_vel_cmd[6] = {p.cmd_vel[0], p.cmd_vel[1], p.cmd_vel[2], p.cmd_vel[3], 0.0, 0.0};
-    hbplan::SwingPlan sp;
-    if (!hbplan::plan_swing(ms, tg, p.t0, p.feet_pos, body_vel_cmd, latest_stance + (size_t)i * 12, sp)) return HB_EPLAN;
-    if (p.joint_ik && !hbplan::joint_references(sp, p.t0, tf, p.x0, tg)) return HB_EPLAN;
-    if (hbplan::fill_reference(ms, tg, sp, p.t0 - 1e-9, tf + 1e-9, out + i) != 0) return HB_EPLAN;
+    const int rc = hbplan::plan_one(pc, in[i], latest_stance + (size_t)i * 12, out + i, true);
+    if (rc) return rc;
   }
   return HB_OK;
 }

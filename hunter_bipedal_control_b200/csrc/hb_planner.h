@@ -4,81 +4,112 @@
 //   P3  SwingTrajectoryPlanner::{update, calNextFootPos, genSwingTrajs}           legged_interface/src/foot_planner/SwingTrajectoryPlanner.cpp:164-358
 //       CubicSpline nodes (time, position, velocity)                              legged_interface/src/foot_planner/CubicSpline.cpp:46-70
 //   P5  cmdVelToTargetTrajectories / targetPoseToTargetTrajectories               legged_controllers/src/TargetTrajectoriesPublisher.cpp:41-130
-// The output is the compact hb_reference consumed by hb_reference_expand_batch (device). P2 (speed-based gait switching) is a
+// The output is the compact hb_reference consumed by hb_reference_expand_batch (device).
 //   P4  calculateJointRef + InverseKinematics::computeIK                        legged_interface/src/SwitchedModelReferenceManager.cpp:251-300,
 //                                                                                 src/foot_planner/InverseKinematics.cpp:20-231
 //   P2  calculateVelAbs / walkGait (speed-based gait selection)                   legged_interface/src/SwitchedModelReferenceManager.cpp:185-249
+//
+// Everything here is fixed-capacity, allocation-free code that compiles for the host (hb_plan_references, threaded over instances)
+// AND for the device (plan_references_kernel, one thread per instance; row N1): the same source, so both produce the same plan.
 #pragma once
 #include <math.h>
 #include <string.h>
 
-#include <algorithm>
-#include <vector>
-
 #include "../../include/hunter_b200.h"
 #include "../../include/hunter_model_constants.h"
 
+#if defined(__CUDACC__)
+#define HBP_HD __host__ __device__
+#else
+#define HBP_HD
+#endif
+
 namespace hbplan {
 
+constexpr int MAX_PHASES = 128;     // phases of the tiled schedule kept around one solve (about 3 horizons + one gait period)
+
+// model constants the planner needs, passed by value to the device kernel (host static arrays are not visible to device code)
+struct PlanConsts {
+  double joint_xyz[33], joint_axis[33], contact_offset[12], lower[10], upper[10], default_joints[10];
+};
+inline PlanConsts make_consts() {
+  PlanConsts pc;
+  for (int i = 0; i < 33; ++i) { pc.joint_xyz[i] = HB_JOINT_XYZ[i]; pc.joint_axis[i] = HB_JOINT_AXIS[i]; }
+  for (int i = 0; i < 12; ++i) pc.contact_offset[i] = HB_CONTACT_OFFSET[i];
+  for (int i = 0; i < 10; ++i) { pc.lower[i] = HB_JOINT_LOWER[i]; pc.upper[i] = HB_JOINT_UPPER[i]; pc.default_joints[i] = HB_DEFAULT_JOINT_STATE[i]; }
+  return pc;
+}
+
+HBP_HD inline double dmin(double a, double b) { return a < b ? a : b; }
+HBP_HD inline double dmax(double a, double b) { return a > b ? a : b; }
+
 struct Vec3 { double x, y, z; };
-inline Vec3 operator+(Vec3 a, Vec3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-inline Vec3 operator-(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-inline Vec3 operator*(double s, Vec3 a) { return {s * a.x, s * a.y, s * a.z}; }
-inline Vec3 cross(Vec3 a, Vec3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+HBP_HD inline Vec3 operator+(Vec3 a, Vec3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+HBP_HD inline Vec3 operator-(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+HBP_HD inline Vec3 operator*(double s, Vec3 a) { return {s * a.x, s * a.y, s * a.z}; }
+HBP_HD inline Vec3 cross(Vec3 a, Vec3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 
 // getRotationMatrixFromZyxEulerAngles applied to a vector
-inline Vec3 rot_zyx(const double* e, Vec3 v) {
+HBP_HD inline Vec3 rot_zyx(const double* e, Vec3 v) {
   const double cz = cos(e[0]), sz = sin(e[0]), cy = cos(e[1]), sy = sin(e[1]), cx = cos(e[2]), sx = sin(e[2]);
   const double R[9] = {cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx, sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx, -sy, cy * sx, cy * cx};
   return {R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z};
 }
 
 // MotionPhaseDefinition.h:55-87
-inline bool contact_flag(int mode, int c) { return (c & 1) ? (mode == 1 || mode == 3) : (mode == 2 || mode == 3); }
+HBP_HD inline bool contact_flag(int mode, int c) { return (c & 1) ? (mode == 1 || mode == 3) : (mode == 2 || mode == 3); }
 
-struct ModeSchedule { std::vector<double> events; std::vector<int> modes; };
+struct ModeSchedule { int n_events; double events[MAX_PHASES]; int modes[MAX_PHASES + 1]; };   // n_events + 1 modes
 
-// reference.info:54-118
-inline void gait_template(int gait, std::vector<int>& modes, std::vector<double>& times) {
+// reference.info:54-118; returns the number of phases of the template
+HBP_HD inline int gait_template(int gait, int* modes, double* times) {
   switch (gait) {
-    case 1: modes = {2, 1}; times = {0.0, 0.3, 0.6}; break;                       // trot
-    case 2: modes = {2, 3, 1, 3}; times = {0.0, 0.25, 0.3, 0.55, 0.6}; break;     // standing_trot
-    case 3: modes = {2, 0, 1, 0}; times = {0.0, 0.15, 0.2, 0.35, 0.4}; break;     // flying_trot
-    default: modes = {3}; times = {0.0, 0.5}; break;                              // stance
+    case 1: modes[0] = 2; modes[1] = 1; times[0] = 0.0; times[1] = 0.3; times[2] = 0.6; return 2;                           // trot
+    case 2: modes[0] = 2; modes[1] = 3; modes[2] = 1; modes[3] = 3;
+            times[0] = 0.0; times[1] = 0.25; times[2] = 0.3; times[3] = 0.55; times[4] = 0.6; return 4;                     // standing_trot
+    case 3: modes[0] = 2; modes[1] = 0; modes[2] = 1; modes[3] = 0;
+            times[0] = 0.0; times[1] = 0.15; times[2] = 0.2; times[3] = 0.35; times[4] = 0.4; return 4;                     // flying_trot
+    default: modes[0] = 3; times[0] = 0.0; times[1] = 0.5; return 1;                                                          // stance
   }
 }
 
 // A schedule that is STANCE (two phases split at `prev_event`, like the reference's initialModeSchedule {STANCE, STANCE},
 // reference.info:21-32) until `start`, then the template tiled up to `final_time` and closed by a STANCE phase:
 // GaitSchedule.cpp:57-93 (insert; the last mode before insertion is STANCE, so no extra transition phase) and :123-161 (tile).
-inline ModeSchedule tile_gait(int gait, double prev_event, double start, double final_time) {
-  ModeSchedule ms;
-  ms.modes.push_back(3);
-  ms.events.push_back(prev_event);
-  ms.modes.push_back(3);
-  std::vector<int> tm; std::vector<double> tt;
-  gait_template(gait, tm, tt);
-  ms.events.push_back(start);
-  while (ms.events.back() < final_time) {
-    for (size_t i = 0; i < tm.size(); ++i) {
-      ms.modes.push_back(tm[i]);
-      ms.events.push_back(ms.events.back() + (tt[i + 1] - tt[i]));
+// Like GaitSchedule::getModeSchedule (:95-121), which drops the phases older than its lower bound, whole template periods that end
+// before `t_keep` are skipped; the schedule inside [t_keep, final_time] is unchanged. Returns false when MAX_PHASES is exceeded.
+HBP_HD inline bool tile_gait(int gait, double prev_event, double start, double t_keep, double final_time, ModeSchedule& ms) {
+  int tm[4]; double tt[5];
+  const int np = gait_template(gait, tm, tt);
+  const double period = tt[np];
+  if (start < t_keep) start += floor((t_keep - start) / period) * period;
+  int ne = 0;
+  ms.modes[0] = 3; ms.events[ne++] = prev_event;
+  ms.modes[1] = 3; ms.events[ne++] = start;
+  while (ms.events[ne - 1] < final_time) {
+    if (ne + np + 1 > MAX_PHASES) return false;
+    for (int i = 0; i < np; ++i) {
+      ms.modes[ne] = tm[i];
+      ms.events[ne] = ms.events[ne - 1] + (tt[i + 1] - tt[i]);
+      ++ne;
     }
   }
-  ms.modes.push_back(3);
-  return ms;
+  ms.modes[ne] = 3;
+  ms.n_events = ne;
+  return true;
 }
 
 // ModeSchedule::modeAtTime: lower_bound on the event times (an event time itself belongs to the earlier mode)
-inline int mode_at(const ModeSchedule& ms, double t) {
-  const size_t idx = std::lower_bound(ms.events.begin(), ms.events.end(), t) - ms.events.begin();
+HBP_HD inline int mode_at(const ModeSchedule& ms, double t) {
+  int idx = 0;
+  while (idx < ms.n_events && ms.events[idx] < t) ++idx;
   return ms.modes[idx];
 }
 
 struct Target { int n; double t[HB_MAX_TARGETS]; double x[HB_MAX_TARGETS][22]; };
 
 // cmdVelToTargetTrajectories (TargetTrajectoriesPublisher.cpp:102-130) with targetPoseToTargetTrajectories (:41-62)
-inline Target cmd_vel_to_target(const double* cmd /*vx,vy,vz,wz*/, double time, const double* state, double time_to_target) {
+HBP_HD inline Target cmd_vel_to_target(const PlanConsts& pc, const double* cmd /*vx,vy,vz,wz*/, double time, const double* state, double time_to_target) {
   const double* pose = state + 6;
   Vec3 v = rot_zyx(pose + 3, {cmd[0], cmd[1], cmd[2]});
   if (fabs(v.x) < 0.06) v.x = 0.0;
@@ -86,7 +117,7 @@ inline Target cmd_vel_to_target(const double* cmd /*vx,vy,vz,wz*/, double time, 
   double target[6] = {pose[0] + v.x * time_to_target, pose[1] + v.y * time_to_target, HB_COM_HEIGHT, pose[3] + cmd[3] * time_to_target, 0.0, 0.0};
   double cur[6] = {pose[0], pose[1], pose[2], pose[3], 0.0, 0.0};
   double dz = HB_COM_HEIGHT - pose[2];
-  dz = dz > 0 ? fmin(dz, 0.04) : fmax(dz, -0.04);      // changeLimit_[2] (TargetTrajectoriesPublisher.h:97)
+  dz = dz > 0 ? dmin(dz, 0.04) : dmax(dz, -0.04);      // changeLimit_[2] (TargetTrajectoriesPublisher.h:97)
   cur[2] = pose[2] + dz;
   Target tg;
   tg.n = 2;
@@ -94,14 +125,14 @@ inline Target cmd_vel_to_target(const double* cmd /*vx,vy,vz,wz*/, double time, 
   for (int k = 0; k < 2; ++k) {
     for (int i = 0; i < 22; ++i) tg.x[k][i] = 0.0;
     for (int i = 0; i < 6; ++i) tg.x[k][6 + i] = (k == 0) ? cur[i] : target[i];
-    for (int j = 0; j < 10; ++j) tg.x[k][12 + j] = HB_DEFAULT_JOINT_STATE[j];
+    for (int j = 0; j < 10; ++j) tg.x[k][12 + j] = pc.default_joints[j];
     tg.x[k][0] = v.x; tg.x[k][1] = v.y; tg.x[k][2] = v.z;    // stateTrajectory[.].head(3) = cmdVelRot (:127-128)
   }
   return tg;
 }
 
 // TargetTrajectories::getDesiredState: piecewise-linear, clamped at both ends
-inline void target_state(const Target& tg, double t, double* x) {
+HBP_HD inline void target_state(const Target& tg, double t, double* x) {
   if (tg.n <= 1 || t <= tg.t[0]) { memcpy(x, tg.x[0], sizeof(double) * 22); return; }
   if (t >= tg.t[tg.n - 1]) { memcpy(x, tg.x[tg.n - 1], sizeof(double) * 22); return; }
   int s = 0;
@@ -113,20 +144,27 @@ inline void target_state(const Target& tg, double t, double* x) {
 struct Node { double t, p, v; };
 struct Seg { double t0, t1, p0, v0, p1, v1; };
 
-struct SwingPlan { std::vector<Seg> seg[4][3]; };
+// The planned segments go straight into the output hb_reference, restricted to the window [t_lo, t_hi] the solver can see.
+struct SwingOut { hb_reference* ref; double t_lo, t_hi; bool overflow; };
+HBP_HD inline void emit(SwingOut& so, int c, int a, const Seg& g) {
+  if (g.t1 <= so.t_lo || g.t0 >= so.t_hi) return;
+  int& n = so.ref->n_segments[c][a];
+  if (n >= HB_MAX_SEGMENTS) { so.overflow = true; return; }
+  double* d = so.ref->segments[c][a][n++];
+  d[0] = g.t0; d[1] = g.t1; d[2] = g.p0; d[3] = g.v0; d[4] = g.p1; d[5] = g.v1;
+}
 
 // SwingTrajectoryPlanner::findIndex (SwingTrajectoryPlanner.cpp:394-419)
-inline void find_index(size_t index, const std::vector<bool>& stock, int& start_idx, int& final_idx) {
-  const int n = (int)stock.size();
+HBP_HD inline void find_index(int index, const bool* stock, int n, int& start_idx, int& final_idx) {
   start_idx = 0;
-  for (int ip = (int)index - 1; ip >= 0; --ip) if (stock[ip] != stock[index]) { start_idx = ip; break; }
+  for (int ip = index - 1; ip >= 0; --ip) if (stock[ip] != stock[index]) { start_idx = ip; break; }
   final_idx = n - 2;
-  for (int ip = (int)index + 1; ip < n; ++ip) if (stock[ip] != stock[index]) { final_idx = ip - 1; break; }
+  for (int ip = index + 1; ip < n; ++ip) if (stock[ip] != stock[index]) { final_idx = ip - 1; break; }
 }
 
 // SwingTrajectoryPlanner::calNextFootPos (:289-312). body_vel_cmd = [vx, vy, vz, wz, 0, 0] as set from /cmd_vel_filtered
 // (SwitchedModelReferenceManager.cpp:91-101): its tail(3) = (wz, 0, 0) is used as the commanded angular velocity, as the reference does.
-inline Vec3 next_foot_pos(int foot, double current_time, double stop_time, double next_middle_time, const double* next_middle_body_pos,
+HBP_HD inline Vec3 next_foot_pos(int foot, double current_time, double stop_time, double next_middle_time, const double* next_middle_body_pos,
                           const double* current_body_pos, Vec3 current_body_vel, const double* body_vel_cmd) {
   const Vec3 bias[4] = {{HB_FEET_BIAS_X1, HB_FEET_BIAS_Y, HB_FEET_BIAS_Z}, {HB_FEET_BIAS_X1, -HB_FEET_BIAS_Y, HB_FEET_BIAS_Z},
                         {HB_FEET_BIAS_X2, HB_FEET_BIAS_Y, HB_FEET_BIAS_Z}, {HB_FEET_BIAS_X2, -HB_FEET_BIAS_Y, HB_FEET_BIAS_Z}};
@@ -144,44 +182,44 @@ inline Vec3 next_foot_pos(int foot, double current_time, double stop_time, doubl
 }
 
 // SwingTrajectoryPlanner::genSwingTrajs (:314-358): x/y three-node, z four-node Hermite splines with the reference's shape constants
-inline void gen_swing(SwingPlan& sp, int foot, double t0, double t1, Vec3 a, Vec3 b) {
+HBP_HD inline void gen_swing(SwingOut& sp, int foot, double t0, double t1, Vec3 a, Vec3 b) {
   const double xy_a1 = 0.417, xy_l1 = 0.650, xy_k1 = 1.770;
   const double pa[3] = {a.x, a.y, a.z}, pb[3] = {b.x, b.y, b.z};
   for (int ax = 0; ax < 2; ++ax) {
     const Node n0{t0, pa[ax], 0.0}, n1{(1 - xy_a1) * t0 + xy_a1 * t1, (1 - xy_l1) * pa[ax] + xy_l1 * pb[ax], xy_k1 * (pb[ax] - pa[ax]) / (t1 - t0)}, n2{t1, pb[ax], 0.0};
-    sp.seg[foot][ax].push_back({n0.t, n1.t, n0.p, n0.v, n1.p, n1.v});
-    sp.seg[foot][ax].push_back({n1.t, n2.t, n1.p, n1.v, n2.p, n2.v});
+    emit(sp, foot, ax, Seg{n0.t, n1.t, n0.p, n0.v, n1.p, n1.v});
+    emit(sp, foot, ax, Seg{n1.t, n2.t, n1.p, n1.v, n2.p, n2.v});
   }
-  const double scaling = std::min(1.0, (t1 - t0) / HB_SWING_TIME_SCALE);
-  const double max_z = std::max(a.z, b.z) + scaling * HB_SWING_HEIGHT;
+  const double scaling = dmin(1.0, (t1 - t0) / HB_SWING_TIME_SCALE);
+  const double max_z = dmax(a.z, b.z) + scaling * HB_SWING_HEIGHT;
   const double z_a1 = 0.251, z_l1 = 0.749, z_k1 = 1.338, z_a2 = 0.630, z_l2 = 0.570, z_k2 = 1.633, z_k3 = 0.0;
   const Node n0{t0, a.z, 0.0};
   const Node n1{(1 - z_a1) * t0 + z_a1 * t1, z_l1 * max_z, z_k1 * (z_l1 * (max_z - a.z)) / (z_a1 * (t1 - t0))};
   const Node n2{(1 - z_a2) * t0 + z_a2 * t1, z_l2 * max_z + (1 - z_l2) * b.z, z_k2 * z_l2 * (b.z - max_z) / ((1 - z_a2) * (t1 - t0))};
   const Node n3{t1, b.z, z_k3 * z_l2 * (b.z - max_z) / ((1 - z_a2) * (t1 - t0))};
-  sp.seg[foot][2].push_back({n0.t, n1.t, n0.p, n0.v, n1.p, n1.v});
-  sp.seg[foot][2].push_back({n1.t, n2.t, n1.p, n1.v, n2.p, n2.v});
-  sp.seg[foot][2].push_back({n2.t, n3.t, n2.p, n2.v, n3.p, n3.v});
+  emit(sp, foot, 2, Seg{n0.t, n1.t, n0.p, n0.v, n1.p, n1.v});
+  emit(sp, foot, 2, Seg{n1.t, n2.t, n1.p, n1.v, n2.p, n2.v});
+  emit(sp, foot, 2, Seg{n2.t, n3.t, n2.p, n2.v, n3.p, n3.v});
 }
 
 // SwingTrajectoryPlanner::update (:164-286). latest_stance (4x3) is the planner's state (in/out).
 // Returns false where the reference would throw (swing phase without a defined take-off / touch-down, :421-458).
-inline bool plan_swing(const ModeSchedule& ms, const Target& tg, double init_time, const double* current_feet /*12*/, const double* body_vel_cmd /*6*/,
-                       double* latest_stance /*12*/, SwingPlan& sp) {
-  const int np = (int)ms.modes.size();
+HBP_HD inline bool plan_swing(const ModeSchedule& ms, const Target& tg, double init_time, const double* current_feet /*12*/, const double* body_vel_cmd /*6*/,
+                              double* latest_stance /*12*/, SwingOut& sp) {
+  const int np = ms.n_events + 1;
   const int mode_now = mode_at(ms, init_time + 0.001);
   for (int i = 0; i < 4; ++i) {
     if (contact_flag(mode_now, i)) for (int a = 0; a < 3; ++a) latest_stance[3 * i + a] = current_feet[3 * i + a];
     latest_stance[3 * i + 2] = HB_NEXT_POSITION_Z;
   }
   for (int j = 0; j < 4; ++j) {
-    std::vector<bool> stock(np);
+    bool stock[MAX_PHASES + 1];
     for (int p = 0; p < np; ++p) stock[p] = contact_flag(ms.modes[p], j);
     Vec3 last{latest_stance[3 * j], latest_stance[3 * j + 1], latest_stance[3 * j + 2]}, next = last;
     int last_final_idx = 0;
     for (int p = 0; p < np; ++p) {
       int si, fi;
-      find_index(p, stock, si, fi);
+      find_index(p, stock, np, si, fi);
       if (!stock[p]) {
         if (si < 0 || fi >= np - 1) return false;      // checkThatIndicesAreValid
         const double t_start = ms.events[si], t_final = ms.events[fi];
@@ -190,7 +228,7 @@ inline bool plan_swing(const ModeSchedule& ms, const Target& tg, double init_tim
           double next_middle_time;
           if (fi < np - 1) {
             int si2, fi2;
-            find_index(fi + 1, stock, si2, fi2);
+            find_index(fi + 1, stock, np, si2, fi2);
             next_middle_time = 0.5 * (t_final + ms.events[fi2]);
           } else next_middle_time = t_final;
           double xm[22], xc[22];
@@ -205,9 +243,9 @@ inline bool plan_swing(const ModeSchedule& ms, const Target& tg, double init_tim
         if (p == 0 || stock[p - 1]) gen_swing(sp, j, t_start, t_final, last, next);
       } else {
         if (p == 0 || !stock[p - 1]) {
-          const double t_start = ms.events[si], t_final = (fi >= 0 && fi < (int)ms.events.size()) ? ms.events[fi] : ms.events.back();
+          const double t_start = ms.events[si], t_final = (fi >= 0 && fi < ms.n_events) ? ms.events[fi] : ms.events[ms.n_events - 1];
           const double pn[3] = {next.x, next.y, next.z};
-          for (int a = 0; a < 3; ++a) sp.seg[j][a].push_back({t_start, t_final, pn[a], 0.0, pn[a], 0.0});
+          for (int a = 0; a < 3; ++a) emit(sp, j, a, Seg{t_start, t_final, pn[a], 0.0, pn[a], 0.0});
         }
       }
     }
@@ -226,15 +264,15 @@ inline bool plan_swing(const ModeSchedule& ms, const Target& tg, double init_tim
 
 struct LegKin { double toe[3]; double R[9]; double Jl[15]; double Ja[15]; };   // Jl, Ja: 3x5 row-major, world axes
 
-inline void mat3_mul(const double* A, const double* B, double* C) {
+HBP_HD inline void mat3_mul(const double* A, const double* B, double* C) {
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
-inline void rot_zyx_mat(const double* e, double* R) {
+HBP_HD inline void rot_zyx_mat(const double* e, double* R) {
   const double cz = cos(e[0]), sz = sin(e[0]), cy = cos(e[1]), sy = sin(e[1]), cx = cos(e[2]), sx = sin(e[2]);
   const double M[9] = {cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx, sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx, -sy, cy * sx, cy * cx};
   memcpy(R, M, sizeof(M));
 }
-inline void axis_angle(const double* a, double q, double* R) {   // Rodrigues, unit axis
+HBP_HD inline void axis_angle(const double* a, double q, double* R) {   // Rodrigues, unit axis
   const double c = cos(q), s = sin(q), v = 1.0 - c;
   const double M[9] = {c + a[0] * a[0] * v, a[0] * a[1] * v - a[2] * s, a[0] * a[2] * v + a[1] * s,
                        a[1] * a[0] * v + a[2] * s, c + a[1] * a[1] * v, a[1] * a[2] * v - a[0] * s,
@@ -243,12 +281,12 @@ inline void axis_angle(const double* a, double q, double* R) {   // Rodrigues, u
 }
 
 // forward kinematics and frame Jacobian of the toe contact frame of leg (0 left, 1 right): pose = [p(3), zyx(3)], qj = 5 leg joints
-inline void leg_kin(int leg, const double* pose, const double* qj, LegKin& k) {
+HBP_HD inline void leg_kin(const PlanConsts& pc, int leg, const double* pose, const double* qj, LegKin& k) {
   double R[9], o[3] = {pose[0], pose[1], pose[2]}, orig[5][3], ax[5][3];
   rot_zyx_mat(pose + 3, R);
   for (int i = 0; i < 5; ++i) {
     const int b = 1 + 5 * leg + i;
-    const double* xyz = HB_JOINT_XYZ + 3 * b; const double* a = HB_JOINT_AXIS + 3 * b;
+    const double* xyz = pc.joint_xyz + 3 * b; const double* a = pc.joint_axis + 3 * b;
     for (int r = 0; r < 3; ++r) o[r] += R[3 * r] * xyz[0] + R[3 * r + 1] * xyz[1] + R[3 * r + 2] * xyz[2];
     for (int r = 0; r < 3; ++r) { orig[i][r] = o[r]; ax[i][r] = R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2]; }
     double Rj[9], Rn[9];
@@ -256,7 +294,7 @@ inline void leg_kin(int leg, const double* pose, const double* qj, LegKin& k) {
     mat3_mul(R, Rj, Rn);
     memcpy(R, Rn, sizeof(Rn));
   }
-  const double* off = HB_CONTACT_OFFSET + 3 * leg;      // contacts 0 / 1 = left / right toe
+  const double* off = pc.contact_offset + 3 * leg;      // contacts 0 / 1 = left / right toe
   for (int r = 0; r < 3; ++r) k.toe[r] = o[r] + R[3 * r] * off[0] + R[3 * r + 1] * off[1] + R[3 * r + 2] * off[2];
   memcpy(k.R, R, sizeof(R));
   for (int i = 0; i < 5; ++i) {
@@ -269,7 +307,7 @@ inline void leg_kin(int leg, const double* pose, const double* qj, LegKin& k) {
 }
 
 // x = ColPivHouseholderQR(A (m x n, row-major, m <= 3, n <= 5), threshold).solve(b)
-inline void qrcp_solve(const double* A, int m, int n, const double* b, double threshold, double* x) {
+HBP_HD inline void qrcp_solve(const double* A, int m, int n, const double* b, double threshold, double* x) {
   double Q[3][3];            // orthonormal directions of the chosen columns
   double coef[3];            // b components along them
   int piv[3]; double R[3][3] = {{0}};
@@ -305,7 +343,7 @@ inline void qrcp_solve(const double* A, int m, int n, const double* b, double th
 }
 
 // FullPivLU(J (3x5)).kernel(): returns the kernel dimension (5 - rank), N is 5 x dim row-major (ld 3)
-inline int fullpiv_kernel(const double* J, double* N) {
+HBP_HD inline int fullpiv_kernel(const double* J, double* N) {
   double M[3][5]; int colp[5] = {0, 1, 2, 3, 4};
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 5; ++j) M[i][j] = J[5 * i + j];
   int rank = 0; double maxpiv = 0.0;
@@ -314,9 +352,9 @@ inline int fullpiv_kernel(const double* J, double* N) {
     for (int i = k; i < 3; ++i) for (int j = k; j < 5; ++j) if (fabs(M[i][j]) > bv) { bv = fabs(M[i][j]); bi = i; bj = j; }
     if (bv <= 0.0) break;
     if (k == 0) maxpiv = bv;
-    for (int j = 0; j < 5; ++j) std::swap(M[k][j], M[bi][j]);
-    for (int i = 0; i < 3; ++i) std::swap(M[i][k], M[i][bj]);
-    std::swap(colp[k], colp[bj]);
+    for (int j = 0; j < 5; ++j) { const double t = M[k][j]; M[k][j] = M[bi][j]; M[bi][j] = t; }
+    for (int i = 0; i < 3; ++i) { const double t = M[i][k]; M[i][k] = M[i][bj]; M[i][bj] = t; }
+    { const int t = colp[k]; colp[k] = colp[bj]; colp[bj] = t; }
     // Eigen's default rank threshold: |pivot| > eps * diagonal size * max pivot
     if (bv > 2.220446049250313e-16 * 3.0 * maxpiv) rank = k + 1; else break;
     for (int i = k + 1; i < 3; ++i) { const double f = M[i][k] / M[k][k]; for (int j = k; j < 5; ++j) M[i][j] -= f * M[k][j]; }
@@ -338,7 +376,7 @@ inline int fullpiv_kernel(const double* J, double* N) {
 }
 
 // pinocchio::log3
-inline void log3(const double* R, double* w) {
+HBP_HD inline void log3(const double* R, double* w) {
   const double tr = R[0] + R[4] + R[8];
   const double PI_ = 3.14159265358979323846;
   double theta;
@@ -360,12 +398,12 @@ inline void log3(const double* R, double* w) {
   for (int i = 0; i < 3; ++i) w[i] = f * v[i];
 }
 
-inline double norm3(const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+HBP_HD inline double norm3(const double* v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 
 // InverseKinematics::computeTranslationIK (InverseKinematics.cpp:37-127)
-inline void translation_ik(int leg, const double* pose, double* qj, const double* des) {
+HBP_HD inline void translation_ik(const PlanConsts& pc, int leg, const double* pose, double* qj, const double* des) {
   const double err_tol = 0.01, conv_tol = 0.001, dt = 0.7; const int max_it = 5;
-  LegKin k; leg_kin(leg, pose, qj, k);
+  LegKin k; leg_kin(pc, leg, pose, qj, k);
   double err[3] = {k.toe[0] - des[0], k.toe[1] - des[1], k.toe[2] - des[2]};
   double last = norm3(err);
   if (last < err_tol) return;
@@ -375,10 +413,10 @@ inline void translation_ik(int leg, const double* pose, double* qj, const double
     qrcp_solve(k.Jl, 3, 5, err, 0.01, vi);
     for (int i = 0; i < 5; ++i) {
       nq[i] = qj[i] - dt * vi[i];
-      nq[i] = std::max(HB_JOINT_LOWER[5 * leg + i], nq[i]);
-      nq[i] = std::min(HB_JOINT_UPPER[5 * leg + i], nq[i]);
+      nq[i] = dmax(pc.lower[5 * leg + i], nq[i]);
+      nq[i] = dmin(pc.upper[5 * leg + i], nq[i]);
     }
-    LegKin kn; leg_kin(leg, pose, nq, kn);
+    LegKin kn; leg_kin(pc, leg, pose, nq, kn);
     for (int r = 0; r < 3; ++r) err[r] = kn.toe[r] - des[r];
     const double en = norm3(err);
     if (en > last) break;
@@ -392,14 +430,14 @@ inline void translation_ik(int leg, const double* pose, double* qj, const double
 }
 
 // InverseKinematics::computeRotationIK (:135-231): orientation error reduced inside the kernel of the translational Jacobian
-inline void rotation_ik(int leg, const double* pose, double* qj, const double* Rdes) {
+HBP_HD inline void rotation_ik(const PlanConsts& pc, int leg, const double* pose, double* qj, const double* Rdes) {
   const double err_tol = 0.01, conv_tol = 0.001, dt = 0.7; const int max_it = 5;
   auto rot_err = [&](const LegKin& k, double* e) {
     double M[9];
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M[3 * i + j] = Rdes[i] * k.R[j] + Rdes[3 + i] * k.R[3 + j] + Rdes[6 + i] * k.R[6 + j];   // Rdes^T R
     log3(M, e);
   };
-  LegKin k; leg_kin(leg, pose, qj, k);
+  LegKin k; leg_kin(pc, leg, pose, qj, k);
   double err[3]; rot_err(k, err);
   double last = norm3(err);
   if (last < err_tol) return;
@@ -422,10 +460,10 @@ inline void rotation_ik(int leg, const double* pose, double* qj, const double* R
     double nq[5];
     for (int i = 0; i < 5; ++i) {
       nq[i] = qj[i] + dt * vi[i];
-      nq[i] = std::max(HB_JOINT_LOWER[5 * leg + i], nq[i]);
-      nq[i] = std::min(HB_JOINT_UPPER[5 * leg + i], nq[i]);
+      nq[i] = dmax(pc.lower[5 * leg + i], nq[i]);
+      nq[i] = dmin(pc.upper[5 * leg + i], nq[i]);
     }
-    LegKin kn; leg_kin(leg, pose, nq, kn);
+    LegKin kn; leg_kin(pc, leg, pose, nq, kn);
     rot_err(kn, err);
     const double en = norm3(err);
     if (en > last) break;
@@ -438,19 +476,19 @@ inline void rotation_ik(int leg, const double* pose, double* qj, const double* R
   }
 }
 
-inline double swing_value(const SwingPlan& sp, int c, int a, double t) {
-  const std::vector<Seg>& v = sp.seg[c][a];
-  size_t s = 0;
-  while (s + 1 < v.size() && t > v[s].t1) ++s;       // an event time belongs to the earlier phase (lookup::findIndexInTimeArray)
-  const Seg& g = v[s];
-  const double T = g.t1 - g.t0, tn = (t - g.t0) / T, dp = g.p1 - g.p0, dv = g.v1 - g.v0;
-  const double c0 = g.p0, c1 = g.v0 * T, c2 = -(3.0 * g.v0 + dv) * T + 3.0 * dp, c3 = (2.0 * g.v0 + dv) * T - 2.0 * dp;
+HBP_HD inline double swing_value(const hb_reference* ref, int c, int a, double t) {
+  const int n = ref->n_segments[c][a];
+  int s = 0;
+  while (s + 1 < n && t > ref->segments[c][a][s][1]) ++s;       // an event time belongs to the earlier phase (lookup::findIndexInTimeArray)
+  const double* g = ref->segments[c][a][s];
+  const double T = g[1] - g[0], tn = (t - g[0]) / T, dp = g[4] - g[2], dv = g[5] - g[3];
+  const double c0 = g[2], c1 = g[3] * T, c2 = -(3.0 * g[3] + dv) * T + 3.0 * dp, c3 = (2.0 * g[3] + dv) * T - 2.0 * dp;
   return ((c3 * tn + c2) * tn + c1) * tn + c0;
 }
 
 // SwitchedModelReferenceManager::calculateJointRef (:251-300): resample the target every 0.15 s and replace the joint part by IK on the
 // planned toe positions, each sample seeded by the previous one. Returns false when the sample count exceeds HB_MAX_TARGETS.
-inline bool joint_references(const SwingPlan& sp, double init_time, double final_time, const double* init_state, Target& tg) {
+HBP_HD inline bool joint_references(const PlanConsts& pc, const hb_reference* sp, double init_time, double final_time, const double* init_state, Target& tg) {
   if (tg.n <= 1) return true;
   const double step = 0.15;
   const int n = (int)floor((final_time - init_time) / step) + 1;
@@ -465,7 +503,7 @@ inline bool joint_references(const SwingPlan& sp, double init_time, double final
     tg.t[i] = (i == n - 1) ? final_time : init_time + i * ((final_time - init_time) / (n - 1));
     target_state(old, tg.t[i], tg.x[i]);
   }
-  for (int j = 0; j < 10; ++j) tg.x[0][12 + j] = HB_DEFAULT_JOINT_STATE[j];
+  for (int j = 0; j < 10; ++j) tg.x[0][12 + j] = pc.default_joints[j];
   for (int i = 0; i < n; ++i) {
     const double* pose = tg.x[i] + 6;
     double seed[10];
@@ -474,8 +512,8 @@ inline bool joint_references(const SwingPlan& sp, double init_time, double final
       const double des[3] = {swing_value(sp, leg, 0, tg.t[i]), swing_value(sp, leg, 1, tg.t[i]), swing_value(sp, leg, 2, tg.t[i])};
       double qj[5];
       memcpy(qj, seed + 5 * leg, sizeof(qj));
-      translation_ik(leg, pose, qj, des);
-      rotation_ik(leg, pose, qj, Rdes);
+      translation_ik(pc, leg, pose, qj, des);
+      rotation_ik(pc, leg, pose, qj, Rdes);
       memcpy(tg.x[i] + 12 + 5 * leg, qj, sizeof(qj));
     }
   }
@@ -487,7 +525,7 @@ inline bool joint_references(const SwingPlan& sp, double init_time, double final
 // Returns the gait level after the update (0 stance, 1 trot, 3 "flying trot" level which inserts no template in the reference) and sets
 // *insert to 1 when the reference would insert a template on this call (stance or trot), 0 otherwise. The reference leaves velAvg_
 // uninitialised before the first call; here the history starts empty, which gives the same values from the first call on.
-inline int gait_select(hb_gait_selector* st, int gait_type, const double* cmd_vel /*vx,vy,vz,wz*/, const double* target0 /*22*/, int* insert) {
+HBP_HD inline int gait_select(hb_gait_selector* st, int gait_type, const double* cmd_vel /*vx,vy,vz,wz*/, const double* target0 /*22*/, int* insert) {
   Vec3 c = rot_zyx(target0 + 9, {cmd_vel[0], cmd_vel[1], cmd_vel[2]});
   const double vc[4] = {c.x, c.y, 0.0, cmd_vel[3] / 3.0};
   const double ve[4] = {target0[0], target0[1], 0.0, target0[3] / 3.0};
@@ -511,31 +549,33 @@ inline int gait_select(hb_gait_selector* st, int gait_type, const double* cmd_ve
   return st->gait_level;
 }
 
-inline int fill_reference(const ModeSchedule& ms, const Target& tg, const SwingPlan& sp, double t_lo, double t_hi, hb_reference* out) {
-  memset(out, 0, sizeof(*out));
+// One instance, start to finish: schedule, target, swing planner, IK joint references, compact output.
+// Returns 0, -1 (invalid input) or -5 (schedule / reference capacity exceeded, or a swing phase without take-off / touch-down time).
+HBP_HD inline int plan_one(const PlanConsts& pc, const hb_plan_input& p, double* latest_stance /*12, in/out*/, hb_reference* out, bool zero_fill) {
+  if (!(p.horizon > 0.0) || !(p.prev_event < p.gait_start) || p.gait < 0 || p.gait > 3) return -1;
+  const double tf = p.t0 + p.horizon;
+  if (zero_fill) memset(out, 0, sizeof(*out));
+  ModeSchedule ms;
+  // the reference tiles over [t0 - T, tf + T] (SwitchedModelReferenceManager.cpp:147)
+  if (!tile_gait(p.gait, p.prev_event, p.gait_start, p.t0 - p.horizon, tf + p.horizon, ms)) return -5;
+  Target tg = cmd_vel_to_target(pc, p.cmd_vel, p.t0, p.x0, p.time_to_target);
+  const double body_vel_cmd[6] = {p.cmd_vel[0], p.cmd_vel[1], p.cmd_vel[2], p.cmd_vel[3], 0.0, 0.0};
+  SwingOut so{out, p.t0 - 1e-9, tf + 1e-9, false};
+  for (int c = 0; c < 4; ++c) for (int a = 0; a < 3; ++a) out->n_segments[c][a] = 0;
+  if (!plan_swing(ms, tg, p.t0, p.feet_pos, body_vel_cmd, latest_stance, so) || so.overflow) return -5;
+  if (p.joint_ik && !joint_references(pc, out, p.t0, tf, p.x0, tg)) return -5;
   // mode schedule restricted to the window (events strictly inside), keeping the mode in force at t_lo
-  size_t first = 0;
-  while (first < ms.events.size() && ms.events[first] <= t_lo) ++first;
-  size_t last = first;
-  while (last < ms.events.size() && ms.events[last] < t_hi) ++last;
-  const int ne = (int)(last - first);
-  if (ne > HB_MAX_EVENTS) return -1;
+  int first = 0;
+  while (first < ms.n_events && ms.events[first] <= so.t_lo) ++first;
+  int last = first;
+  while (last < ms.n_events && ms.events[last] < so.t_hi) ++last;
+  const int ne = last - first;
+  if (ne > HB_MAX_EVENTS) return -5;
   out->n_events = ne;
   for (int i = 0; i < ne; ++i) out->event_times[i] = ms.events[first + i];
   for (int i = 0; i <= ne; ++i) out->modes[i] = ms.modes[first + i];
   out->n_targets = tg.n;
   for (int k = 0; k < tg.n; ++k) { out->target_times[k] = tg.t[k]; memcpy(out->target_states[k], tg.x[k], sizeof(double) * 22); }
-  for (int c = 0; c < 4; ++c)
-    for (int a = 0; a < 3; ++a) {
-      int n = 0;
-      for (const Seg& s : sp.seg[c][a]) {
-        if (s.t1 <= t_lo || s.t0 >= t_hi) continue;
-        if (n >= HB_MAX_SEGMENTS) return -1;
-        double* d = out->segments[c][a][n++];
-        d[0] = s.t0; d[1] = s.t1; d[2] = s.p0; d[3] = s.v0; d[4] = s.p1; d[5] = s.v1;
-      }
-      out->n_segments[c][a] = n;
-    }
   return 0;
 }
 

@@ -151,6 +151,10 @@ int hb_joint_command_batch_dev(hb_ctx* ctx, int B, const hb_pd_gains* gains, dou
 int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0,
                                 const hb_reference* refs, const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque,
                                 int32_t* wbc_status);
+/* device planner: the same planner source as hb_plan_references, one thread per instance. feet != NULL
+ * overrides in[i].feet_pos (B x 12, e.g. from hb_contact_positions_batch_dev); status[i] = 0, -1 or -5 like hb_plan_references. */
+int hb_plan_references_batch_dev(hb_ctx* ctx, int B, const hb_plan_input* in, const double* feet, double* latest_stance,
+                                 hb_reference* out, int32_t* status /*nullable*/);
 int hb_rbd_to_centroidal_batch_dev(hb_ctx* ctx, int B, const double* rbd, double* x);
 int hb_reference_expand_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                                   int32_t* mode);
@@ -177,6 +181,14 @@ int hb_joint_command_batch(hb_ctx* ctx, int B, const hb_pd_gains* gains, double 
 int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0, const hb_reference* refs,
                             const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque, int32_t* wbc_status);
 int hb_resident_read_batch(hb_ctx* ctx, int B, double* t0 /*nullable*/, double* x_traj /*nullable*/, double* u_traj /*nullable*/);
+/* hb_plan_references on the device, host pointers in and out (parity checks of the device planner against the host planner) */
+int hb_plan_references_gpu(hb_ctx* ctx, int B, const hb_plan_input* in, double* latest_stance, hb_reference* out, int32_t* status /*nullable*/);
+/* The whole cycle from the plan inputs: computeFootPos at x0 + planner (P1, P3, P4, P5) + hb_resident_cycle_batch, all on the device.
+ * in[i].feet_pos is ignored (computed from in[i].x0); the planner's latest-stance state is resident (zeroed by cold_start, like
+ * SwingTrajectoryPlanner's latestStanceposition_). Per instance 352 B + rbd go in, info / wbc_sol / torque / statuses come out.
+ * plan_status[i] != 0: the planner rejected the instance (an all-stance reference at the current pose was used instead). */
+int hb_resident_plan_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, const hb_plan_input* in, const double* rbd,
+                                 hb_solve_info* info, double* wbc_sol, double* torque, int32_t* wbc_status, int32_t* plan_status);
 int hb_rbd_to_centroidal_batch(hb_ctx* ctx, int B, const double* rbd, double* x);
 int hb_reference_expand_batch(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                               int32_t* mode);

@@ -167,6 +167,25 @@ def test_planner_threads_give_identical_bytes(monkeypatch):
     assert bytes(r1) == bytes(r3) and np.array_equal(l1, l3)
 
 
+def test_long_running_gait_is_trimmed_not_truncated():
+    """A gait that started minutes ago: whole periods older than t0 - T are skipped (GaitSchedule::getModeSchedule drops them too);
+    the window the solver sees is the same as in the untrimmed restatement."""
+    n = 6
+    x0, gaits, cmd, t0, start, feet, latest = _cases(n, seed=37)
+    gaits = ["trot", "flying_trot", "standing_trot", "trot", "flying_trot", "standing_trot"]
+    t0 = t0 + 200.0
+    start = t0 - np.array([50.3, 77.77, 120.0, 31.0, 64.2, 199.0])
+    refs, ls = hb.plan_references(t0, T, x0, cmd, feet, gaits, start, latest_stance=latest, joint_ik=False)
+    for i in range(n):
+        ms, tg, sp = R.plan(t0[i], T, x0[i], cmd[i], feet[i], gaits[i], start[i], latest_stance=latest[i], joint_ik=False)
+        times = t0[i] + np.linspace(0, T, 57)
+        times = np.array([t for t in times if min([abs(t - e) for e in ms.events]) > 1e-6])
+        xr, sw, md = R.sample(ms, tg, sp, times)
+        xc, sc, mc = R.eval_compact(refs[i], times)
+        np.testing.assert_array_equal(md, mc)
+        np.testing.assert_allclose(sc, sw, rtol=0, atol=1e-9)      # event times accumulate differently over hundreds of periods
+
+
 def test_planner_rejects_bad_input():
     x0, gaits, cmd, t0, start, feet, latest = _cases(2)
     with pytest.raises(RuntimeError):
@@ -222,4 +241,64 @@ def test_joint_command_law():
         assert bool(es[i]) == e
     assert es[5] == 1 and es[6] == 0 and es[20] == 1
     assert np.all(cmd[5, :3, 2] > 0) and np.all(cmd[5, 3:, 3] == 1.0)
+    ctx.close()
+
+
+def _ref_fields(r):
+    ne, nt = r.n_events, r.n_targets
+    segs = [[np.array([list(r.segments[c][a][k][:]) for k in range(r.n_segments[c][a])]).reshape(-1, 6) for a in range(3)] for c in range(4)]
+    return (ne, nt, np.array(r.event_times[:ne]), np.array(r.modes[:ne + 1]), np.array(r.target_times[:nt]),
+            np.array([list(r.target_states[k][:]) for k in range(nt)]), segs)
+
+
+@pytest.mark.gpu
+def test_device_planner_matches_host_planner():
+    """Row N1: the planner source compiled for the device (one thread per instance) gives the host planner's plan."""
+    ctx = hb.Context(horizon_N=N, dt=DT, max_batch=256, device=0)
+    n = 200
+    x0, gaits, cmd, t0, start, feet, latest = _cases(n, seed=53)
+    ins = hb.make_plan_inputs(t0, T, x0, cmd, feet, gaits, start)
+    rd, lsd, st = ctx.plan_references_gpu(ins, latest)
+    rh, lsh = hb.plan_references(t0, T, x0, cmd, feet, gaits, start, latest_stance=latest)
+    assert (st == 0).all()
+    np.testing.assert_allclose(lsd, lsh, rtol=0, atol=1e-14)
+    for i in range(n):
+        a, b = _ref_fields(rd[i]), _ref_fields(rh[i])
+        assert a[0] == b[0] and a[1] == b[1]
+        np.testing.assert_allclose(a[2], b[2], rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(a[3], b[3])
+        np.testing.assert_allclose(a[4], b[4], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(a[5], b[5], rtol=0, atol=1e-8)       # IK joint angles: fused multiply-adds on the device
+        for c in range(4):
+            for ax in range(3):
+                assert a[6][c][ax].shape == b[6][c][ax].shape
+                np.testing.assert_allclose(a[6][c][ax], b[6][c][ax], rtol=0, atol=1e-11)
+    # invalid input is reported per instance and replaced by a safe all-stance reference
+    ins[3].horizon = -1.0
+    rd, _, st = ctx.plan_references_gpu(ins, latest)
+    assert st[3] == -1 and (np.delete(st, 3) == 0).all() and rd[3].n_events == 0 and rd[3].modes[0] == 3
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_plan_cycle_on_device_equals_host_plan_plus_cycle():
+    ctx = hb.Context(horizon_N=N, dt=DT, max_batch=512, device=0)
+    from hunter_bipedal_control_b200 import scenarios as sc
+    for n in (40, 300):
+        x0, gaits, cmd, t0, start, _, _ = _cases(n, seed=59)
+        rbd = sc.consistent_rbd(x0)
+        ins = hb.make_plan_inputs(t0, T, x0, cmd, None, gaits, start)
+        info, sol, tau, st, ps = ctx.resident_plan_cycle(True, 0.002, ins, rbd)
+        assert (ps == 0).all()
+        feet = ctx.contact_positions(x0)
+        refs, _ = hb.plan_references(t0, T, x0, cmd, feet, gaits, start, latest_stance=np.zeros((n, 12)))
+        info2, sol2, tau2, st2 = ctx.resident_cycle(True, 0.002, t0, x0, refs, rbd)
+        assert np.array_equal(st, st2)
+        assert np.abs(tau - tau2).max() < 1e-6 * np.abs(tau2).max()
+        assert np.array_equal(info["alpha"], info2["alpha"])
+    # second cycle: warm start + planner state (latest stance) carried on the device
+    t1 = t0 + 0.02
+    ins1 = hb.make_plan_inputs(t1, T, x0, cmd, None, gaits, start)
+    info, sol, tau, st, ps = ctx.resident_plan_cycle(False, 0.002, ins1, rbd)
+    assert (ps == 0).all() and np.isfinite(tau).all()
     ctx.close()
