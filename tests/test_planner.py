@@ -286,6 +286,8 @@ def test_plan_cycle_on_device_equals_host_plan_plus_cycle():
     from hunter_bipedal_control_b200 import scenarios as sc
     for n in (40, 300):
         x0, gaits, cmd, t0, start, _, _ = _cases(n, seed=59)
+        start = t0 + np.random.default_rng(n).uniform(0.05, 0.3, n)     # standing at t0 (as at controller start): every foot has a stance history
+        cmd = 0.5 * cmd
         rbd = sc.consistent_rbd(x0)
         ins = hb.make_plan_inputs(t0, T, x0, cmd, None, gaits, start)
         info, sol, tau, st, ps = ctx.resident_plan_cycle(True, 0.002, ins, rbd)
@@ -293,7 +295,7 @@ def test_plan_cycle_on_device_equals_host_plan_plus_cycle():
         feet = ctx.contact_positions(x0)
         refs, _ = hb.plan_references(t0, T, x0, cmd, feet, gaits, start, latest_stance=np.zeros((n, 12)))
         info2, sol2, tau2, st2 = ctx.resident_cycle(True, 0.002, t0, x0, refs, rbd)
-        assert np.array_equal(st, st2)
+        assert (st == 0).all() and (st2 == 0).all()
         assert np.abs(tau - tau2).max() < 1e-6 * np.abs(tau2).max()
         assert np.array_equal(info["alpha"], info2["alpha"])
     # second cycle: warm start + planner state (latest stance) carried on the device
