@@ -767,36 +767,47 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
   __syncthreads();
   // ---- phase C: gains (warp 0) || S = Qt + At' SA (warp 1)
   if (warp == 0) {
-    if (lane < NTP) {
+    // Cholesky of the symmetrised Huu entirely in registers: lane i owns row i (right-looking, column by column, the pivot column is
+    // broadcast with shuffles), then forward / backward substitution of the 22 + 1 right-hand sides, one per lane, with the factor
+    // entries fetched from their owner lanes. No shared-memory round trips on this latency-bound stretch.
+    {
+      double a[NTP], rinv[NTP];
 #pragma unroll
-      for (int c = 0; c < NTP; ++c) if (c < lane) sh.Huu[lane * 18 + c] = 0.5 * (sh.Huu[lane * 18 + c] + sh.Huu[c * 18 + lane]);
-    }
-    __syncwarp();
-    if (!warp_chol_inv(sh.Huu, NTP, 18, sh.idg, lane)) fail = true;
-    if (lane <= NX) {
+      for (int c = 0; c < NTP; ++c) a[c] = (lane < NTP && c <= lane) ? 0.5 * (sh.Huu[lane * 18 + c] + sh.Huu[c * 18 + lane]) : 0.0;
+#pragma unroll
+      for (int j = 0; j < NTP; ++j) {
+        double d = __shfl_sync(HB_FULL_MASK, a[j], j);
+        if (!(d > 0.0)) { fail = true; d = 1.0; }
+        const double r = 1.0 / sqrt(d);
+        rinv[j] = r;
+        const double l = a[j] * r;              // L[i][j] on lane i >= j
+        a[j] = l;
+#pragma unroll
+        for (int k = j + 1; k < NTP; ++k) a[k] = fma(-l, __shfl_sync(HB_FULL_MASK, l, k), a[k]);
+      }
       double col[NTP], y[NTP];
 #pragma unroll
-      for (int c = 0; c < NTP; ++c) col[c] = (lane < NX) ? sh.HuxT[lane * NTMAX + c] : sh.hu[c];
+      for (int c = 0; c < NTP; ++c) col[c] = (lane < NX) ? sh.HuxT[lane * NTMAX + c] : ((lane == NX) ? sh.hu[c] : 0.0);
 #pragma unroll
       for (int c = 0; c < NTP; ++c) {
-        double s = sh.idg[c] * col[c];
+        double sacc = col[c];
 #pragma unroll
-        for (int kk = 0; kk < c; ++kk) s = fma(sh.Huu[kk * 18 + c], col[kk], s);
-        y[c] = s;
+        for (int kk = 0; kk < c; ++kk) sacc = fma(-__shfl_sync(HB_FULL_MASK, a[kk], c), y[kk], sacc);
+        y[c] = sacc * rinv[c];
       }
 #pragma unroll
-      for (int c = 0; c < NTP; ++c) {
-        double s = sh.idg[c] * y[c];
+      for (int c = NTP - 1; c >= 0; --c) {
+        double sacc = y[c];
 #pragma unroll
-        for (int kk = c + 1; kk < NTP; ++kk) s = fma(sh.Huu[c * 18 + kk], y[kk], s);
-        col[c] = -s;
+        for (int kk = c + 1; kk < NTP; ++kk) sacc = fma(-__shfl_sync(HB_FULL_MASK, a[c], kk), col[kk], sacc);
+        col[c] = sacc * rinv[c];                 // solution of Huu x = rhs; the gain is its negative
       }
       if (lane < NX) {
 #pragma unroll
-        for (int c = 0; c < NTP; ++c) { K[c * NX + lane] = col[c]; rk[c * NX + lane] = col[c]; }     // SB is dead: K takes its place
-      } else {
+        for (int c = 0; c < NTP; ++c) { K[c * NX + lane] = -col[c]; rk[c * NX + lane] = -col[c]; }     // SB is dead: K takes its place
+      } else if (lane == NX) {
 #pragma unroll
-        for (int c = 0; c < NTP; ++c) { sh.kff[c] = col[c]; rk[NTMAX * NX + c] = col[c]; }
+        for (int c = 0; c < NTP; ++c) { sh.kff[c] = -col[c]; rk[NTMAX * NX + c] = -col[c]; }
       }
     }
     __syncwarp();

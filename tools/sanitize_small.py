@@ -11,3 +11,19 @@ xt1, ut1, info = ctx.mpc_solve(g["x0"], g["x_ref"], g["swing"], g["mode"], xt, u
 print("alpha", info["alpha"], "max dx", np.abs(xt1 - g["xt1"]).max())
 sol, st = ctx.wbc_solve(g["wx"], g["wu"], g["wrbd"], g["wmode"], g["wstance"])
 print("wbc status", st, "max err", np.abs(sol - g["wsol"]).max())
+# planner on the device + resident closed-loop cycle (cold, then warm) + joint command law
+from hunter_bipedal_control_b200 import scenarios as sc
+B = 6
+x0 = sc.random_initial_states(B, seed=3)
+rbd = sc.consistent_rbd(x0)
+gaits = ["trot", "standing_trot", "flying_trot", "stance", "trot", "flying_trot"]
+ins = hb.make_plan_inputs(np.zeros(B), N * dt, x0, (0.3, 0.0, 0.0, 0.1), None, gaits, 0.1)
+info, sol, tau, st, ps = ctx.resident_plan_cycle(True, 0.002, ins, rbd)
+ins1 = hb.make_plan_inputs(np.full(B, 0.02), N * dt, x0, (0.3, 0.0, 0.0, 0.1), None, gaits, 0.1)
+info, sol, tau, st, ps = ctx.resident_plan_cycle(False, 0.002, ins1, rbd)
+print("plan cycle: plan status", ps, "wbc status", st, "finite", np.isfinite(tau).all())
+feet = ctx.contact_positions(x0)
+refs, _ = hb.plan_references(np.zeros(B), N * dt, x0, (0.3, 0.0, 0.0, 0.1), feet, gaits, 0.1)
+info, sol, tau, st = ctx.resident_cycle(True, 0.002, np.zeros(B), x0, refs, rbd)
+cmd, out_tau, es = ctx.joint_command(0.002, x0, np.zeros((B, 22)), sol, np.full(B, 3, dtype=np.int32), rbd)
+print("resident cycle wbc status", st, "command finite", np.isfinite(cmd).all())
