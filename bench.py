@@ -331,7 +331,7 @@ def main():
                 "roofline_fp64": {"achieved_tflops": value / world * FLOPS_PER_SOLVE / 1e12, "peak_tflops_nominal": FP64_NOMINAL_TFLOPS,
                                   "frac": value / world * FLOPS_PER_SOLVE / 1e12 / FP64_NOMINAL_TFLOPS},
                 "clocks": clocks, "all_converged": ok}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # reported on rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             n = max(cores, 4)
             data = [d[:n] for d in (x0, x_ref, swing, mode, rbd)]
