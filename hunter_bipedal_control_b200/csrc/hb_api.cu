@@ -547,7 +547,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   cudaFuncSetAttribute(mpc_forward_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsShared));
   cudaFuncSetAttribute(qp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(wbc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wbc_fused_doubles() * sizeof(double)));
-  cudaFuncSetAttribute(lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(LinHalf)));
+  cudaFuncSetAttribute(lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(LinHalf) + sizeof(ChainModel)));
   cudaFuncSetAttribute(lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqShared));
   cudaFuncSetAttribute(riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicShared));
   cudaFuncSetAttribute(forward_linesearch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fw2Shared));
@@ -704,7 +704,7 @@ int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x
   const int N = a.N, NP = (N + 1) / 2;
   const long long nw = (long long)B * NP;
   prof_begin(ctx, K_LIN);
-  lin_kernel<<<(unsigned)((nw + 1) / 2), 64, 4 * sizeof(LinHalf), ctx->stream>>>(a);
+  lin_kernel<<<(unsigned)((nw + 1) / 2), 64, 4 * sizeof(LinHalf) + sizeof(ChainModel), ctx->stream>>>(a);
   prof_end(ctx);
   ctx->launches++;
   CK(cudaGetLastError());

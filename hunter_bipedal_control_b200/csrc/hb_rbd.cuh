@@ -226,6 +226,94 @@ __device__ __forceinline__ void kin_pass_f(QF qf, VF vf, SCF scf, OF of) {
   for (int i = 0; i < 3; ++i) { of.h(i, P[i]); of.h(3 + i, Lo[i] - cxP[i]); }
 }
 
+// ---- chain-split sweep (used by the node linearisation): a lane evaluates the base frame and ONE leg chain only.
+// Bodies outside the chain do not depend on the chain's joint coordinates / velocities, so a joint-seeded lane needs nothing else;
+// base-seeded quantities are the sum of a (base + left chain) lane and a (right chain) lane. The model constants of the chain pass
+// live in shared memory because lanes of one warp walk different chains (constant memory would serialise the diverging addresses).
+struct ChainModel {
+  double joint_xyz[NBODY * 3], com[NBODY * 3], inertia[NBODY * 9], mass[NBODY], contact_offset[NC * 3];
+  int joint_axis[NBODY];
+};
+__device__ __forceinline__ void chain_model_load(ChainModel& cm, int tid, int nthreads) {
+  const Model& md = c_model;
+  for (int i = tid; i < NBODY * 3; i += nthreads) { cm.joint_xyz[i] = md.joint_xyz[i]; cm.com[i] = md.com[i]; }
+  for (int i = tid; i < NBODY * 9; i += nthreads) cm.inertia[i] = md.inertia[i];
+  for (int i = tid; i < NBODY; i += nthreads) { cm.mass[i] = md.mass[i]; cm.joint_axis[i] = md.joint_axis[i]; }
+  for (int i = tid; i < NC * 3; i += nthreads) cm.contact_offset[i] = md.contact_offset[i];
+}
+
+template <class T> struct ChainOut {
+  T P[3], Lo[3], mc[3];   // partial sums over the bodies visited: linear momentum, angular momentum about the origin, mass * position
+  T cpos[6], cvel[6];     // toe (contact `leg`) then heel (contact 2 + leg) of this chain
+};
+
+template <class T, class QF, class VF, class SCF>
+__device__ __forceinline__ void kin_chain_f(const ChainModel& md, int leg, bool with_base, QF qf, VF vf, SCF scf, ChainOut<T>& o) {
+  T R[9], ax0[9];
+  {
+    T sz, cz, sy, cy, sx, cx;
+    scf(0, sz, cz); scf(1, sy, cy); scf(2, sx, cx);
+    R[0] = cz * cy; R[1] = cz * sy * sx - sz * cx; R[2] = cz * sy * cx + sz * sx;
+    R[3] = sz * cy; R[4] = sz * sy * sx + cz * cx; R[5] = sz * sy * cx - cz * sx;
+    R[6] = -sy;     R[7] = cy * sx;                R[8] = cy * cx;
+    ax0[0] = T(0.0); ax0[1] = T(0.0); ax0[2] = T(1.0);
+    ax0[3] = -sz; ax0[4] = cz; ax0[5] = T(0.0);
+    ax0[6] = cz * cy; ax0[7] = sz * cy; ax0[8] = -sy;
+  }
+  T w[3], p[3] = {qf(0), qf(1), qf(2)}, vl[3] = {vf(0), vf(1), vf(2)};
+  {
+    const T v3 = vf(3), v4 = vf(4), v5 = vf(5);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[i] = ax0[i] * v3 + ax0[3 + i] * v4 + ax0[6 + i] * v5;
+  }
+#pragma unroll
+  T P[3], Lo[3], mc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { P[i] = T(0.0); Lo[i] = T(0.0); mc[i] = T(0.0); }
+  auto add_body = [&](int b) {
+    T r[3], wxr[3], vc[3], cw[3], l[3], wl[3], Iwl[3], Iw[3];
+    rot_const(R, &md.com[3 * b], r);
+    cross(w, r, wxr);
+    const double mb = md.mass[b];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { vc[i] = (vl[i] + wxr[i]) * mb; cw[i] = p[i] + r[i]; }
+    cross(cw, vc, l);
+    rotT(R, w, wl);
+    const double* I = &md.inertia[9 * b];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Iwl[i] = wl[0] * I[3 * i] + wl[1] * I[3 * i + 1] + wl[2] * I[3 * i + 2];
+    rot(R, Iwl, Iw);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { P[i] = P[i] + vc[i]; Lo[i] = Lo[i] + l[i] + Iw[i]; mc[i] = mc[i] + cw[i] * mb; }
+  };
+  if (with_base) add_body(0);
+  for (int j = 0; j < 5; ++j) {
+    const int b = 1 + 5 * leg + j;
+    T d[3], wxd[3], a[3], sj, cj;
+    rot_const(R, &md.joint_xyz[3 * b], d);
+    cross(w, d, wxd);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { p[i] = p[i] + d[i]; vl[i] = vl[i] + wxd[i]; }
+    scf(2 + b, sj, cj);
+    joint_rotate_sc(R, md.joint_axis[b], sj, cj, a);
+    const T vb = vf(5 + b);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[i] = w[i] + a[i] * vb;
+    add_body(b);
+  }
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int c = leg + 2 * t;
+    T off[3], wxo[3];
+    rot_const(R, &md.contact_offset[3 * c], off);
+    cross(w, off, wxo);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { o.cpos[3 * t + i] = p[i] + off[i]; o.cvel[3 * t + i] = vl[i] + wxo[i]; }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { o.P[i] = P[i]; o.Lo[i] = Lo[i]; o.mc[i] = mc[i]; }
+}
+
 template <class T> struct KinOutSink {
   KinOut<T>& o;
   __device__ __forceinline__ void h(int i, const T& x) { o.h[i] = x; }

@@ -39,26 +39,71 @@ struct LinHalf {
   double Acm[6 * 16], Jc[12 * 16], dh[6 * NDIR], dcom[3 * NDIR], dp[12 * NDIR], dv[12 * NDIR];
   double Abinv[36], AbinvAj[6 * NJ], dvb[6 * NDIR], vgen[16], epos[12], evel[12], com[3];
   double sn[NDIR], cs[NDIR];   // sines / cosines of yaw, pitch, roll and the ten joint angles, shared by all sweeps of a stage
+  double part[16 * 9];         // per-lane partial sums of a chain-split sweep: P(3), Lo(3), mc(3)
+  double vals[2 * 6];          // values from the two base-seeded lanes 0 (base + left chain) and 3 (right chain): P(3), mc(3)
 };
 
 // Linearise the flow map of one node at state xs (half-warp cooperative; `hl` = lane within the half, `act` = node exists).
 // Writes f, compact A rows 3..11 (9x22), Bf rows 3..5 (3x12), Bv rows 6..11 (6x10); with want_ee the contact kinematics record.
-__device__ __noinline__ void lin_half(LinHalf& sh, const double* xs, int hl, bool act, double* rec_f, double* rec_A, double* rec_Bf,
+__device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const double* xs, int hl, bool act, double* rec_f, double* rec_A, double* rec_Bf,
                                       double* rec_Bv, bool want_ee, double* rec) {
   const double m = c_model.total_mass;
   if (hl < NDIR) { double s, c; sincos(xs[9 + hl], &s, &c); sh.sn[hl] = s; sh.cs[hl] = c; }
   __syncwarp();
+  // Lane tasks of the two chain-split sweeps (16 lanes, all busy):
+  //   hl 0..2  : Euler coordinate hl,     base body + left chain        hl 3..5  : Euler coordinate hl-3, right chain
+  //   hl 6..10 : left joint hl-6, left chain                            hl 11..15: right joint hl-11, right chain
+  // `gen` is the generalised coordinate the lane seeds (for joints it equals the lane index). A joint coordinate only moves its own
+  // chain; the three translation coordinates have closed-form columns.
+  const bool euler = hl < 6;
+  const int leg = (hl < 3 || (hl >= 6 && hl < 11)) ? 0 : 1;
+  const int gen = euler ? 3 + (hl % 3) : hl;
+  const bool with_base = hl < 3;
+  const bool vlane = (hl == 0 || hl == 3);   // lanes whose VALUES (not seeds) are used: base + left chain, right chain
   {
-    // sweep 1: unit generalised velocity e_hl -> column hl of the centroidal momentum matrix and of the contact Jacobians
-    struct Sink1 {
-      LinHalf& sh; int hl;
-      __device__ __forceinline__ void h(int i, double x) { sh.Acm[i * 16 + hl] = x; }
-      __device__ __forceinline__ void com(int i, double x) { if (hl == 0) sh.com[i] = x; }
-      __device__ __forceinline__ void cpos(int i, double x) { if (hl == 0) sh.epos[i] = x; }
-      __device__ __forceinline__ void cvel(int i, double x) { sh.Jc[i * 16 + hl] = x; }
-    } sink{sh, hl};
-    kin_pass_f<double>([&](int i) { return xs[6 + i]; }, [&](int i) { return (i == hl) ? 1.0 : 0.0; },
-                       [&](int k, double& s, double& c) { s = sh.sn[k]; c = sh.cs[k]; }, sink);
+    // sweep 1: unit generalised velocity e_gen -> column gen of the centroidal momentum matrix and of the contact Jacobians
+    ChainOut<double> co;
+    kin_chain_f<double>(cm, leg, with_base, [&](int i) { return xs[6 + i]; }, [&](int i) { return (i == gen) ? 1.0 : 0.0; },
+                        [&](int k, double& s, double& c) { s = sh.sn[k]; c = sh.cs[k]; }, co);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { sh.part[hl * 9 + i] = co.P[i]; sh.part[hl * 9 + 3 + i] = co.Lo[i]; }
+    if (vlane) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) sh.vals[(hl / 3) * 6 + 3 + i] = co.mc[i];
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int c = leg + 2 * t;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        sh.Jc[(3 * c + i) * 16 + gen] = co.cvel[3 * t + i];
+        if (!euler) sh.Jc[(3 * (c ^ 1) + i) * 16 + gen] = 0.0;      // the other leg's contacts do not move
+        if (vlane) sh.epos[3 * c + i] = co.cpos[3 * t + i];
+      }
+    }
+    if (hl < 3) {   // translation columns: h = [m e; 0], every contact moves with e
+#pragma unroll
+      for (int r = 0; r < 6; ++r) sh.Acm[r * 16 + hl] = (r == hl) ? m : 0.0;
+#pragma unroll
+      for (int r = 0; r < 12; ++r) sh.Jc[r * 16 + hl] = ((r % 3) == hl) ? 1.0 : 0.0;
+    }
+  }
+  __syncwarp();
+  if (hl < NDIR) {
+    // column g = 3 + hl: sum the chain parts, then refer the angular momentum to the centre of mass
+    const int g = 3 + hl, la = (hl < 3) ? hl : g;
+    double P[3], Lo[3], com[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      P[i] = sh.part[la * 9 + i]; Lo[i] = sh.part[la * 9 + 3 + i];
+      if (hl < 3) { P[i] += sh.part[(3 + hl) * 9 + i]; Lo[i] += sh.part[(3 + hl) * 9 + 3 + i]; }
+      com[i] = (sh.vals[3 + i] + sh.vals[9 + i]) / m;
+    }
+    sh.Acm[0 * 16 + g] = P[0]; sh.Acm[1 * 16 + g] = P[1]; sh.Acm[2 * 16 + g] = P[2];
+    sh.Acm[3 * 16 + g] = Lo[0] - (com[1] * P[2] - com[2] * P[1]);
+    sh.Acm[4 * 16 + g] = Lo[1] - (com[2] * P[0] - com[0] * P[2]);
+    sh.Acm[5 * 16 + g] = Lo[2] - (com[0] * P[1] - com[1] * P[0]);
+    if (hl == 0) { sh.com[0] = com[0]; sh.com[1] = com[1]; sh.com[2] = com[2]; }
   }
   __syncwarp();
   if (hl < 7) {
@@ -89,18 +134,50 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const double* xs, int hl, boo
 #pragma unroll
     for (int r = 0; r < 6; ++r) { double s = 0.0; for (int c = 0; c < 6; ++c) s += sh.Abinv[6 * r + c] * sh.Acm[c * 16 + 6 + hl]; sh.AbinvAj[r * NJ + hl] = s; }
   }
+  {
+    // sweep 2: dual numbers seeded along configuration coordinate gen (direction gen - 3), generalised velocity held fixed
+    const int dir = gen - 3;
+    ChainOut<D1> co;
+    kin_chain_f<D1>(cm, leg, with_base, [&](int i) { return D1(xs[6 + i], (i == gen) ? 1.0 : 0.0); }, [&](int i) { return D1(sh.vgen[i], 0.0); },
+                    [&](int k, D1& s, D1& c) { const double sv = sh.sn[k], cv = sh.cs[k]; const double on = (k == dir) ? 1.0 : 0.0; s = D1(sv, cv * on); c = D1(cv, -sv * on); },
+                    co);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { sh.part[hl * 9 + i] = co.P[i].d; sh.part[hl * 9 + 3 + i] = co.Lo[i].d; sh.part[hl * 9 + 6 + i] = co.mc[i].d; }
+    if (vlane) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { sh.vals[(hl / 3) * 6 + i] = co.P[i].v; sh.vals[(hl / 3) * 6 + 3 + i] = co.mc[i].v; }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int c = leg + 2 * t;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int row = 3 * c + i;
+        sh.dp[row * NDIR + dir] = co.cpos[3 * t + i].d;
+        sh.dv[row * NDIR + dir] = co.cvel[3 * t + i].d;
+        if (!euler) { sh.dp[(3 * (c ^ 1) + i) * NDIR + dir] = 0.0; sh.dv[(3 * (c ^ 1) + i) * NDIR + dir] = 0.0; }
+        if (vlane) sh.evel[row] = co.cvel[3 * t + i].v;
+      }
+    }
+  }
+  __syncwarp();
   if (hl < NDIR) {
-    // sweep 2: dual numbers seeded along configuration direction 3+hl, generalised velocity held fixed
-    struct Sink2 {
-      LinHalf& sh; int hl;
-      __device__ __forceinline__ void h(int i, D1 x) { sh.dh[i * NDIR + hl] = x.d; }
-      __device__ __forceinline__ void com(int i, D1 x) { sh.dcom[i * NDIR + hl] = x.d; }
-      __device__ __forceinline__ void cpos(int i, D1 x) { sh.dp[i * NDIR + hl] = x.d; }
-      __device__ __forceinline__ void cvel(int i, D1 x) { sh.dv[i * NDIR + hl] = x.d; if (hl == 0) sh.evel[i] = x.v; }
-    } sink{sh, hl};
-    kin_pass_f<D1>([&](int i) { return D1(xs[6 + i], (i == 3 + hl) ? 1.0 : 0.0); }, [&](int i) { return D1(sh.vgen[i], 0.0); },
-                   [&](int k, D1& s, D1& c) { const double sv = sh.sn[k], cv = sh.cs[k]; const double on = (k == hl) ? 1.0 : 0.0; s = D1(sv, cv * on); c = D1(cv, -sv * on); },
-                   sink);
+    const int la = (hl < 3) ? hl : 3 + hl;
+    double Pd[3], Ld[3], dc[3], Pv[3], cv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      Pd[i] = sh.part[la * 9 + i]; Ld[i] = sh.part[la * 9 + 3 + i]; dc[i] = sh.part[la * 9 + 6 + i];
+      if (hl < 3) { Pd[i] += sh.part[(3 + hl) * 9 + i]; Ld[i] += sh.part[(3 + hl) * 9 + 3 + i]; dc[i] += sh.part[(3 + hl) * 9 + 6 + i]; }
+      dc[i] /= m;
+      Pv[i] = sh.vals[i] + sh.vals[6 + i];
+      cv[i] = (sh.vals[3 + i] + sh.vals[9 + i]) / m;
+    }
+    // d/dq of h = [P ; Lo - com x P]
+    sh.dh[0 * NDIR + hl] = Pd[0]; sh.dh[1 * NDIR + hl] = Pd[1]; sh.dh[2 * NDIR + hl] = Pd[2];
+    sh.dh[3 * NDIR + hl] = Ld[0] - ((dc[1] * Pv[2] - dc[2] * Pv[1]) + (cv[1] * Pd[2] - cv[2] * Pd[1]));
+    sh.dh[4 * NDIR + hl] = Ld[1] - ((dc[2] * Pv[0] - dc[0] * Pv[2]) + (cv[2] * Pd[0] - cv[0] * Pd[2]));
+    sh.dh[5 * NDIR + hl] = Ld[2] - ((dc[0] * Pv[1] - dc[1] * Pv[0]) + (cv[0] * Pd[1] - cv[1] * Pd[0]));
+    sh.dcom[0 * NDIR + hl] = dc[0]; sh.dcom[1 * NDIR + hl] = dc[1]; sh.dcom[2 * NDIR + hl] = dc[2];
   }
   __syncwarp();
   if (hl < NDIR) {
@@ -191,6 +268,9 @@ __global__ void __launch_bounds__(64) lin_kernel(SqpArgs a) {
   const int warp_in_block = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
   LinHalf& sh = reinterpret_cast<LinHalf*>(smem_raw)[warp_in_block * 2 + half];
+  ChainModel& cm = *reinterpret_cast<ChainModel*>(smem_raw + 4 * sizeof(LinHalf));
+  chain_model_load(cm, threadIdx.x, blockDim.x);
+  __syncthreads();
   const int N = a.N, NP = (N + 1) >> 1;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
   if (w >= (long long)a.B * NP) return;
@@ -203,10 +283,10 @@ __global__ void __launch_bounds__(64) lin_kernel(SqpArgs a) {
   for (int i = hl; i < NX; i += 16) { sh.x[i] = xk[i]; sh.u[i] = uk[i]; }
   __syncwarp();
   double* rec = a.lin + ((size_t)inst * N + kk) * LIN_STRIDE;
-  lin_half(sh, sh.x, hl, act, rec + LIN_F1, rec + LIN_A1, rec + LIN_BF1, rec + LIN_BV1, true, rec);
+  lin_half(sh, cm, sh.x, hl, act, rec + LIN_F1, rec + LIN_A1, rec + LIN_BF1, rec + LIN_BV1, true, rec);
   for (int i = hl; i < NX; i += 16) sh.x2[i] = sh.x[i] + a.dt * sh.f[i];
   __syncwarp();
-  lin_half(sh, sh.x2, hl, act, rec + LIN_F2, rec + LIN_A2, rec + LIN_BF2, rec + LIN_BV2, false, rec);
+  lin_half(sh, cm, sh.x2, hl, act, rec + LIN_F2, rec + LIN_A2, rec + LIN_BF2, rec + LIN_BV2, false, rec);
 }
 
 // ---------------------------------------------------------------- K1
