@@ -24,7 +24,8 @@ EXPORTED_SYMBOLS = [
     "hb_wbc_qp_batch_dev", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
     "hb_policy_eval_batch_dev", "hb_control_step_batch_dev", "hb_rbd_to_centroidal_batch_dev", "hb_reference_expand_batch_dev",
     "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references", "hb_gait_select", "hb_resident_cycle_batch_dev", "hb_resident_cycle_batch", "hb_resident_read_batch", "hb_plan_references_batch_dev",
-    "hb_plan_references_gpu", "hb_resident_plan_cycle_batch", "hb_default_pd_gains", "hb_joint_command_batch_dev", "hb_joint_command_batch",
+    "hb_plan_references_gpu", "hb_resident_plan_cycle_batch", "hb_default_kf_params", "hb_kf_reset", "hb_estimator_update_batch_dev",
+    "hb_estimator_update_batch", "hb_default_pd_gains", "hb_joint_command_batch_dev", "hb_joint_command_batch",
     "hb_wbc_qp_batch", "hb_wbc_solve_batch", "hb_mpc_cold_start_batch", "hb_mpc_solve_batch", "hb_control_step_batch",
     "hb_rbd_to_centroidal_batch", "hb_reference_expand_batch", "hb_probe_flow_map",
 ]
@@ -60,6 +61,28 @@ def default_pd_gains():
     g = HbPdGains()
     _check(load_library().hb_default_pd_gains(C.byref(g)), "hb_default_pd_gains")
     return g
+
+
+class HbKfState(C.Structure):
+    _fields_ = [("x_hat", C.c_double * 18), ("P", C.c_double * 324), ("feet_heights", C.c_double * 4)]
+
+
+class HbKfParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("foot_radius", "imu_process_noise_position", "imu_process_noise_velocity", "foot_process_noise_position",
+                                          "foot_sensor_noise_position", "foot_sensor_noise_velocity", "foot_height_sensor_noise")]
+
+
+def default_kf_params():
+    p = HbKfParams()
+    _check(load_library().hb_default_kf_params(C.byref(p)), "hb_default_kf_params")
+    return p
+
+
+def kf_states(B):
+    """Freshly reset filter states (x_hat = 0, P = 100 I)."""
+    st = (HbKfState * B)()
+    _check(load_library().hb_kf_reset(B, st), "hb_kf_reset")
+    return st
 
 
 class HbGaitSelector(C.Structure):
@@ -297,6 +320,17 @@ class Context:
         _check(self._lib.hb_resident_plan_cycle_batch(self._h, B, 1 if cold_start else 0, C.c_double(t_rel), ins, _ptr(rbd), _ptr(info), _ptr(sol), _ptr(tau),
                                                       _ptr(st), _ptr(ps)), "hb_resident_plan_cycle_batch", self._h)
         return info, sol, tau, st, ps
+
+    def estimator_update(self, dt, state, quat, ang_vel_local, lin_acc_local, joint_pos, joint_vel, contact_flag, params=None):
+        """KalmanFilterEstimate::update for a batch; `state` (ctypes array of HbKfState) is updated in place. Returns rbd [B,32]."""
+        quat, ang_vel_local, lin_acc_local, joint_pos, joint_vel = map(_f64, (quat, ang_vel_local, lin_acc_local, joint_pos, joint_vel))
+        B = quat.shape[0]
+        flags = np.ascontiguousarray(contact_flag, dtype=np.uint8).reshape(B, 4)
+        params = params or default_kf_params()
+        rbd = np.zeros((B, 32))
+        _check(self._lib.hb_estimator_update_batch(self._h, B, C.byref(params), C.c_double(dt), state, _ptr(quat), _ptr(ang_vel_local), _ptr(lin_acc_local),
+                                                   _ptr(joint_pos), _ptr(joint_vel), _ptr(flags), _ptr(rbd)), "hb_estimator_update_batch", self._h)
+        return rbd
 
     def joint_command(self, period, x_des, u_des, wbc_sol, mode_cmd, rbd, loaded=None, estop=None, gains=None):
         """Joint command law (LeggedController.cpp:186-257): returns (command [B,10,5], output_torque [B,10], estop [B])."""

@@ -265,6 +265,148 @@ __global__ void joint_command_kernel(int B, hb_pd_gains g, double dt, const doub
   if (estop) estop[inst] = stop ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------------------- state estimator (row N3)
+// KalmanFilterEstimate::update (legged_estimation/src/LinearKalmanFilter.cpp:72-185), one warp per instance. The constant matrices
+// of the filter are never formed: A = I + dt E (position <- velocity), C = rows of +-1 (foot - base position, base velocity,
+// foot height), so A P A' and C M are index arithmetic. With S = C Pm C' + R = L L', Y = L^-1 C Pm and z = L^-1 (y - C x):
+//   x <- x + Y' z ,  P <- Pm - Y' Y   ( = (I - Pm C' S^-1 C) Pm, symmetric by construction).
+struct KfShared {
+  double P[18 * 18], Pm[18 * 18], T[28 * 18], S[28 * 29], Y[28 * 18];
+  double x[18], ey[28], z[28], sdi[28], qd[18], rd[28];
+};
+// row r of C applied to the 18 rows of a matrix stored row-major with leading dimension ld: (C M)[r][c]
+__device__ __forceinline__ double kf_c_row(const double* M, int ld, int r, int c) {
+  if (r < 12) return M[(r % 3) * ld + c] - M[(6 + r) * ld + c];
+  if (r < 24) return M[(3 + (r % 3)) * ld + c];
+  return M[(8 + 3 * (r - 24)) * ld + c];
+}
+__global__ void __launch_bounds__(32) kf_update_kernel(int B, hb_kf_params prm, double dt, hb_kf_state* state, const double* quat, const double* angl,
+                                                       const double* accl, const double* jpos, const double* jvel, const uint8_t* cflag, double* rbd_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KfShared& sh = *reinterpret_cast<KfShared*>(smem_raw);
+  const int inst = blockIdx.x, lane = threadIdx.x;
+  hb_kf_state& st = state[inst];
+  // ---- updateImu: quaternion -> ZYX angles, local angular velocity -> Euler rates -> global angular velocity (every lane, registers)
+  const double qx = quat[4 * inst], qy = quat[4 * inst + 1], qz = quat[4 * inst + 2], qw = quat[4 * inst + 3];
+  double zyx[3];
+  zyx[0] = atan2(2.0 * (qx * qy + qw * qz), qw * qw + qx * qx - qy * qy - qz * qz);
+  zyx[1] = asin(fmin(-2.0 * (qx * qz - qw * qy), .99999));
+  zyx[2] = atan2(2.0 * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz);
+  double sz, cz, sy, cy, sx, cx;
+  sincos(zyx[0], &sz, &cz); sincos(zyx[1], &sy, &cy); sincos(zyx[2], &sx, &cx);
+  const double wlx = angl[3 * inst], wly = angl[3 * inst + 1], wlz = angl[3 * inst + 2];
+  const double dzr = (sx * wly + cx * wlz) / cy, dyr = cx * wly - sx * wlz, dxr = wlx + sy * dzr;   // yaw, pitch, roll rates
+  const double wg[3] = {-sz * dyr + cy * cz * dxr, cz * dyr + cy * sz * dxr, dzr - sy * dxr};
+  // ---- contact kinematics with the base at the origin and zero base linear velocity (:84-100)
+  double q[NQ], v[NQ];
+  q[0] = q[1] = q[2] = 0.0; q[3] = zyx[0]; q[4] = zyx[1]; q[5] = zyx[2];
+  v[0] = v[1] = v[2] = 0.0;
+  {
+    const double r = (cz * wg[0] + sz * wg[1]) / cy;      // getEulerAnglesZyxDerivativesFromGlobalAngularVelocity
+    v[5] = r; v[4] = -sz * wg[0] + cz * wg[1]; v[3] = wg[2] + sy * r;
+  }
+  for (int j = 0; j < NJ; ++j) { q[6 + j] = jpos[(size_t)inst * NJ + j]; v[6 + j] = jvel[(size_t)inst * NJ + j]; }
+  KinOut<double> ko;
+  kin_pass<double>(q, v, ko);
+  // world acceleration (:133-134)
+  double acc[3];
+  {
+    const double R[9] = {cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx, sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx, -sy, cy * sx, cy * cx};
+    const double a0 = accl[3 * inst], a1 = accl[3 * inst + 1], a2 = accl[3 * inst + 2];
+    acc[0] = R[0] * a0 + R[1] * a1 + R[2] * a2; acc[1] = R[3] * a0 + R[4] * a1 + R[5] * a2; acc[2] = R[6] * a0 + R[7] * a1 + R[8] * a2 - 9.81;
+  }
+  // ---- noise covariances (diagonal), prediction of the state
+  for (int i = lane; i < 324; i += 32) sh.P[i] = st.P[i];
+  if (lane < 18) {
+    const double xo = st.x_hat[lane];
+    double xn = xo;
+    if (lane < 3) xn = xo + dt * st.x_hat[3 + lane] + 0.5 * dt * dt * acc[lane];
+    else if (lane < 6) xn = xo + dt * acc[lane - 3];
+    sh.x[lane] = xn;
+    double qv;
+    if (lane < 3) qv = (dt / 20.0) * prm.imu_process_noise_position;
+    else if (lane < 6) qv = (dt * (double)9.81f / 20.0) * prm.imu_process_noise_velocity;
+    else qv = dt * prm.foot_process_noise_position * (cflag[4 * inst + (lane - 6) / 3] ? 1.0 : 100.0);
+    sh.qd[lane] = qv;
+  }
+  if (lane < 28) {
+    double rv;
+    if (lane < 12) rv = prm.foot_sensor_noise_position * (cflag[4 * inst + lane / 3] ? 1.0 : 100.0);
+    else if (lane < 24) rv = prm.foot_sensor_noise_velocity * (cflag[4 * inst + (lane - 12) / 3] ? 1.0 : 100.0);
+    else rv = prm.foot_height_sensor_noise * (cflag[4 * inst + lane - 24] ? 1.0 : 100.0);
+    sh.rd[lane] = rv;
+  }
+  __syncwarp();
+  // Pm = A P A' + Q
+  for (int idx = lane; idx < 324; idx += 32) {
+    const int r = idx / 18, c = idx - 18 * r;
+    double s = sh.P[idx];
+    if (r < 3) s += dt * sh.P[(r + 3) * 18 + c];
+    if (c < 3) s += dt * sh.P[r * 18 + c + 3];
+    if (r < 3 && c < 3) s += dt * dt * sh.P[(r + 3) * 18 + c + 3];
+    if (r == c) s += sh.qd[r];
+    sh.Pm[idx] = s;
+  }
+  // innovation y - C x (:137-143): ps = -eePos (+ footRadius on z), vs = -eeVel, feet heights
+  if (lane < 28) {
+    double y;
+    if (lane < 12) y = -ko.cpos[lane] + ((lane % 3) == 2 ? prm.foot_radius : 0.0);
+    else if (lane < 24) y = -ko.cvel[lane - 12];
+    else y = st.feet_heights[lane - 24];
+    sh.ey[lane] = y - kf_c_row(sh.x, 1, lane, 0);
+  }
+  __syncwarp();
+  // T = C Pm (28 x 18), S = T C' + R (28 x 28, ld 29; C' applied to the columns = C applied to the rows of T')
+  for (int idx = lane; idx < 28 * 18; idx += 32) { const int r = idx / 18, c = idx - 18 * r; sh.T[idx] = kf_c_row(sh.Pm, 18, r, c); }
+  __syncwarp();
+  for (int idx = lane; idx < 28 * 28; idx += 32) {
+    const int i = idx / 28, j = idx - 28 * i;
+    const double* Ti = sh.T + i * 18;
+    double s;
+    if (j < 12) s = Ti[j % 3] - Ti[6 + j];
+    else if (j < 24) s = Ti[3 + (j % 3)];
+    else s = Ti[8 + 3 * (j - 24)];
+    if (i == j) s += sh.rd[i];
+    sh.S[i * 29 + j] = s;
+  }
+  __syncwarp();
+  warp_chol_inv(sh.S, 28, 29, sh.sdi, lane);
+  // Y = L^-1 T (28 x 18), z = L^-1 ey
+  for (int idx = lane; idx < 28 * 18; idx += 32) {
+    const int i = idx / 18, c = idx - 18 * i;
+    double s = sh.sdi[i] * sh.T[i * 18 + c];
+    for (int k = 0; k < i; ++k) s = fma(sh.S[k * 29 + i], sh.T[k * 18 + c], s);
+    sh.Y[idx] = s;
+  }
+  warp_li_mv(sh.S, 28, 29, sh.sdi, sh.ey, sh.z, lane);
+  __syncwarp();
+  if (lane < 18) {
+    double s = sh.x[lane];
+    for (int k = 0; k < 28; ++k) s = fma(sh.Y[k * 18 + lane], sh.z[k], s);
+    sh.x[lane] = s;
+  }
+  for (int idx = lane; idx < 324; idx += 32) {
+    const int r = idx / 18, c = idx - 18 * r;
+    double s = 0.5 * (sh.Pm[idx] + sh.Pm[c * 18 + r]);
+    for (int k = 0; k < 28; ++k) s = fma(-sh.Y[k * 18 + r], sh.Y[k * 18 + c], s);
+    sh.P[idx] = s;
+  }
+  __syncwarp();
+  // :151-156: once the xy position is observed well enough, decouple it and shrink its covariance
+  const bool decouple = sh.P[0] * sh.P[19] - sh.P[1] * sh.P[18] > 0.000001;
+  for (int idx = lane; idx < 324; idx += 32) {
+    const int r = idx / 18, c = idx - 18 * r;
+    double vP = sh.P[idx];
+    if (decouple) { if ((r < 2) != (c < 2)) vP = 0.0; else if (r < 2 && c < 2) vP /= 10.0; }
+    st.P[idx] = vP;
+  }
+  if (lane < 18) st.x_hat[lane] = sh.x[lane];
+  // ---- rbd state (StateEstimateBase.cpp:73-106): [zyx, p, q_j, omega_world, v, qd_j]
+  double* rb = rbd_out + (size_t)inst * 32;
+  if (lane < 3) { rb[lane] = zyx[lane]; rb[3 + lane] = sh.x[lane]; rb[16 + lane] = wg[lane]; rb[19 + lane] = sh.x[3 + lane]; }
+  if (lane < NJ) { rb[6 + lane] = q[6 + lane]; rb[22 + lane] = v[6 + lane]; }
+}
+
 // computeCentroidalStateFromRbdModel (LeggedController.cpp:336)
 __global__ void rbd_to_centroidal_kernel(int B, const double* rbd, double* x) {
   const int inst = blockIdx.x * blockDim.x + threadIdx.x;
@@ -411,6 +553,7 @@ struct hb_ctx {
   double *res_xt = nullptr, *res_ut = nullptr, *res_t0 = nullptr;   // resident primal solution (hb_resident_cycle_batch)
   int res_valid = 0;                                                // number of instances holding a previous solution
   hb_plan_input* s_plan = nullptr; double* res_stance = nullptr; int32_t* s_pstatus = nullptr;   // device planner (row N1)
+  hb_kf_state* s_kf = nullptr;                                                                  // estimator staging (row N3)
   int32_t *s_mode, *s_imode, *s_status, *s_iters;
   uint8_t* s_stance;
   hb_solve_info* s_info;
@@ -534,6 +677,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   ok = ok && dalloc(&ctx->xdes, B * NX) == cudaSuccess && dalloc(&ctx->udes, B * NU) == cudaSuccess && dalloc(&ctx->wsol, B * NWBC) == cudaSuccess;
   ok = ok && dalloc(&ctx->wstatus, B) == cudaSuccess && dalloc(&ctx->witers, B) == cudaSuccess && dalloc(&ctx->wmode, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_x0, B * NX) == cudaSuccess && dalloc(&ctx->s_xref, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_swing, B * (N + 1) * 24) == cudaSuccess;
+  ok = ok && dalloc(&ctx->s_kf, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_plan, B) == cudaSuccess && dalloc(&ctx->res_stance, B * 12) == cudaSuccess && dalloc(&ctx->s_pstatus, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->res_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->res_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->res_t0, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->s_rbd, B * 32) == cudaSuccess;
@@ -561,7 +705,7 @@ int hb_destroy(hb_ctx* ctx) {
   void* ptrs[] = {ctx->lin, ctx->proj, ctx->rk, ctx->gains, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->qH, ctx->qg, ctx->qA, ctx->qlb, ctx->qub, ctx->qm, ctx->xdes, ctx->udes,
                   ctx->wsol, ctx->wstatus, ctx->witers, ctx->wmode, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_xt, ctx->s_ut, ctx->s_rbd, ctx->s_xd,
                   ctx->s_ud, ctx->s_sol, ctx->s_tau, ctx->s_t0, ctx->s_misc, ctx->s_mode, ctx->s_imode, ctx->s_status, ctx->s_iters, ctx->s_stance,
-                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus};
+                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
   if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
@@ -798,6 +942,35 @@ int hb_plan_references_batch_dev(hb_ctx* ctx, int B, const hb_plan_input* in, co
   if (set_device(ctx)) return HB_ECUDA;
   static const hbplan::PlanConsts pc = hbplan::make_consts();
   plan_references_kernel<<<(B + 7) / 8, 8, 0, ctx->stream>>>(B, in, feet, latest_stance, out, status, pc);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_default_kf_params(hb_kf_params* p) {
+  if (!p) return HB_EINVAL;
+  p->foot_radius = 0.02; p->imu_process_noise_position = 0.02; p->imu_process_noise_velocity = 0.02; p->foot_process_noise_position = 0.5;
+  p->foot_sensor_noise_position = 0.5; p->foot_sensor_noise_velocity = 0.1; p->foot_height_sensor_noise = 0.01;
+  return HB_OK;
+}
+
+int hb_kf_reset(int B, hb_kf_state* state) {
+  if (B < 0 || !state) return HB_EINVAL;
+  for (int i = 0; i < B; ++i) {
+    memset(&state[i], 0, sizeof(hb_kf_state));
+    for (int k = 0; k < 18; ++k) state[i].P[k * 18 + k] = 100.0;
+  }
+  return HB_OK;
+}
+
+int hb_estimator_update_batch_dev(hb_ctx* ctx, int B, const hb_kf_params* params, double dt, hb_kf_state* state, const double* quat,
+                                  const double* ang_vel_local, const double* lin_acc_local, const double* joint_pos, const double* joint_vel,
+                                  const uint8_t* contact_flag, double* rbd_out) {
+  if (!ctx || B < 0 || !params || !state || !quat || !ang_vel_local || !lin_acc_local || !joint_pos || !joint_vel || !contact_flag || !rbd_out) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  kf_update_kernel<<<B, 32, sizeof(KfShared), ctx->stream>>>(B, *params, dt, state, quat, ang_vel_local, lin_acc_local, joint_pos, joint_vel, contact_flag,
+                                                            rbd_out);
   ctx->launches++;
   CK(cudaGetLastError());
   return HB_OK;
@@ -1114,6 +1287,26 @@ int hb_joint_command_batch(hb_ctx* ctx, int B, const hb_pd_gains* gains, double 
   if (rc) return rc;
   D2H(command, ctx->s_misc, sizeof(double) * B * NJ * 5); D2H(output_torque, ctx->s_tau, sizeof(double) * B * NJ);
   if (estop) D2H(estop, d_estop, B);
+  return hb_sync(ctx);
+}
+
+int hb_estimator_update_batch(hb_ctx* ctx, int B, const hb_kf_params* params, double dt, hb_kf_state* state, const double* quat,
+                              const double* ang_vel_local, const double* lin_acc_local, const double* joint_pos, const double* joint_vel,
+                              const uint8_t* contact_flag, double* rbd_out) {
+  if (!ctx || B < 0 || !params || !state || !quat || !ang_vel_local || !lin_acc_local || !joint_pos || !joint_vel || !contact_flag || !rbd_out) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  double* d_quat = ctx->s_misc; double* d_w = d_quat + (size_t)B * 4; double* d_a = d_w + (size_t)B * 3; double* d_jp = d_a + (size_t)B * 3;
+  double* d_jv = d_jp + (size_t)B * NJ;
+  uint8_t* d_flag = (uint8_t*)ctx->s_status;      // B int32 words hold B x 4 flags
+  H2D(ctx->s_kf, state, sizeof(hb_kf_state) * B);
+  H2D(d_quat, quat, sizeof(double) * B * 4); H2D(d_w, ang_vel_local, sizeof(double) * B * 3); H2D(d_a, lin_acc_local, sizeof(double) * B * 3);
+  H2D(d_jp, joint_pos, sizeof(double) * B * NJ); H2D(d_jv, joint_vel, sizeof(double) * B * NJ); H2D(d_flag, contact_flag, (size_t)B * 4);
+  int rc = hb_estimator_update_batch_dev(ctx, B, params, dt, ctx->s_kf, d_quat, d_w, d_a, d_jp, d_jv, d_flag, ctx->s_rbd);
+  if (rc) return rc;
+  D2H(state, ctx->s_kf, sizeof(hb_kf_state) * B);
+  D2H(rbd_out, ctx->s_rbd, sizeof(double) * B * 32);
   return hb_sync(ctx);
 }
 

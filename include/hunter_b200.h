@@ -12,6 +12,7 @@
  *   hb_policy_eval_batch    <-> MPC_MRT_Interface::evaluatePolicy     legged_controllers/src/LeggedController.cpp:154-156
  *   hb_control_step_batch   <-> LeggedController::update MPC->policy->WBC->torque law   LeggedController.cpp:137-257
  *   hb_resident_cycle_batch <-> SqpSolver::run with its resident primalSolution_ (warm start) + the rest of LeggedController::update
+ *   hb_estimator_update_batch <-> KalmanFilterEstimate::update        legged_estimation/src/LinearKalmanFilter.cpp:72-185
  *   hb_joint_command_batch  <-> joint command / torque law            LeggedController.cpp:186-257
  *   hb_plan_references      <-> GaitSchedule tiling + SwingTrajectoryPlanner::update + cmdVelToTargetTrajectories + calculateJointRef
  *   hb_gait_select          <-> SwitchedModelReferenceManager::calculateVelAbs + walkGait/trotGait   :185-249
@@ -105,6 +106,21 @@ typedef struct {
   double kd_feet;                             /* ankle (4,9)                                         */
 } hb_pd_gains;
 
+/* ---- state estimator: linear Kalman filter of legged_estimation/src/LinearKalmanFilter.cpp:72-185 ---- */
+typedef struct {
+  double x_hat[18];        /* base position(3), base linear velocity(3), four contact positions(12), world frame */
+  double P[18 * 18];       /* covariance, row-major                                                              */
+  double feet_heights[4];  /* terrain height under each contact (measurement rows 24..27)                        */
+} hb_kf_state;
+
+typedef struct {           /* task.info:336-345 */
+  double foot_radius, imu_process_noise_position, imu_process_noise_velocity, foot_process_noise_position;
+  double foot_sensor_noise_position, foot_sensor_noise_velocity, foot_height_sensor_noise;
+} hb_kf_params;
+
+int hb_default_kf_params(hb_kf_params* p);
+/* x_hat = 0, P = 100 I, heights = 0 (KalmanFilterEstimate constructor, LinearKalmanFilter.cpp:24-63); host only */
+int hb_kf_reset(int B, hb_kf_state* state);
 int hb_default_pd_gains(hb_pd_gains* g);
 int hb_default_config(hb_config* cfg);
 int hb_create(const hb_config* cfg, int device, hb_ctx** out);
@@ -155,6 +171,13 @@ int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel
  * overrides in[i].feet_pos (B x 12, e.g. from hb_contact_positions_batch_dev); status[i] = 0, -1 or -5 like hb_plan_references. */
 int hb_plan_references_batch_dev(hb_ctx* ctx, int B, const hb_plan_input* in, const double* feet, double* latest_stance,
                                  hb_reference* out, int32_t* status /*nullable*/);
+/* One estimator update per instance (StateEstimateBase::updateJointStates / updateImu, StateEstimateBase.cpp:73-106, then
+ * KalmanFilterEstimate::update): quat = (x, y, z, w); contact_flag: B x 4 (0 = the filter distrusts that foot, x100 noise);
+ * rbd_out: B x 32 measured rbd state [zyx, p, q_j, omega_world, v, qd_j]. The odometry topic fusion (updateFromTopic) is ROS glue
+ * and not part of it; zyxOffset_ is taken as zero. */
+int hb_estimator_update_batch_dev(hb_ctx* ctx, int B, const hb_kf_params* params, double dt, hb_kf_state* state, const double* quat,
+                                  const double* ang_vel_local, const double* lin_acc_local, const double* joint_pos,
+                                  const double* joint_vel, const uint8_t* contact_flag, double* rbd_out);
 int hb_rbd_to_centroidal_batch_dev(hb_ctx* ctx, int B, const double* rbd, double* x);
 int hb_reference_expand_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                                   int32_t* mode);
@@ -189,6 +212,9 @@ int hb_plan_references_gpu(hb_ctx* ctx, int B, const hb_plan_input* in, double* 
  * plan_status[i] != 0: the planner rejected the instance (an all-stance reference at the current pose was used instead). */
 int hb_resident_plan_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, const hb_plan_input* in, const double* rbd,
                                  hb_solve_info* info, double* wbc_sol, double* torque, int32_t* wbc_status, int32_t* plan_status);
+int hb_estimator_update_batch(hb_ctx* ctx, int B, const hb_kf_params* params, double dt, hb_kf_state* state, const double* quat,
+                              const double* ang_vel_local, const double* lin_acc_local, const double* joint_pos, const double* joint_vel,
+                              const uint8_t* contact_flag, double* rbd_out);
 int hb_rbd_to_centroidal_batch(hb_ctx* ctx, int B, const double* rbd, double* x);
 int hb_reference_expand_batch(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                               int32_t* mode);

@@ -557,3 +557,84 @@ def warm_start_shift(t0_prev, t0_new, dt, x_prev, u_prev, x0, mode_new, mass, g=
             u[i] = interp(u_ext, ti)
             x[i + 1] = interp(x_prev, tn)
     return x, u
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# N3: KalmanFilterEstimate::update (legged_estimation/src/LinearKalmanFilter.cpp:24-185), dense matrices as in the reference
+KF_PARAMS = dict(footRadius=0.02, imuProcessNoisePosition=0.02, imuProcessNoiseVelocity=0.02, footProcessNoisePosition=0.5,
+                 footSensorNoisePosition=0.5, footSensorNoiseVelocity=0.1, footHeightSensorNoise=0.01)     # task.info:336-345
+
+
+def quat_to_zyx(q):
+    x, y, z, w = q
+    a = min(-2.0 * (x * z - w * y), .99999)
+    return np.array([math.atan2(2 * (x * y + w * z), w * w + x * x - y * y - z * z), math.asin(a),
+                     math.atan2(2 * (y * z + w * x), w * w - x * x - y * y + z * z)])
+
+
+def euler_rates_from_local(zyx, wl):
+    sy, cy, sx, cx = math.sin(zyx[1]), math.cos(zyx[1]), math.sin(zyx[2]), math.cos(zyx[2])
+    t = sx * wl[1] / cy + cx * wl[2] / cy
+    return np.array([t, cx * wl[1] - sx * wl[2], wl[0] + sy * t])
+
+
+def global_from_euler_rates(zyx, d):
+    sz, cz, sy, cy = math.sin(zyx[0]), math.cos(zyx[0]), math.sin(zyx[1]), math.cos(zyx[1])
+    return np.array([-sz * d[1] + cy * cz * d[2], cz * d[1] + cy * sz * d[2], d[0] - sy * d[2]])
+
+
+def euler_rates_from_global(zyx, w):
+    sz, cz, sy, cy = math.sin(zyx[0]), math.cos(zyx[0]), math.sin(zyx[1]), math.cos(zyx[1])
+    r = (cz * w[0] + sz * w[1]) / cy
+    return np.array([w[2] + sy * r, -sz * w[0] + cz * w[1], r])
+
+
+class KalmanFilterRef:
+    def __init__(self):
+        self.x = np.zeros(18); self.P = 100.0 * np.eye(18); self.heights = np.zeros(4)
+        self.a = np.eye(18); self.b = np.zeros((18, 3))
+        c = np.zeros((28, 18))
+        for i in range(4):
+            c[3 * i:3 * i + 3, 0:3] = np.eye(3); c[12 + 3 * i:15 + 3 * i, 3:6] = np.eye(3)
+        c[0:12, 6:18] = -np.eye(12)
+        c[27, 17] = c[26, 14] = c[25, 11] = c[24, 8] = 1.0
+        self.c = c
+
+    def update(self, dt, quat, wl, al, jpos, jvel, contact, kin, prm=KF_PARAMS):
+        """kin(q16, v16) -> (contact positions 12, contact velocities 12)."""
+        zyx = quat_to_zyx(quat)
+        wg = global_from_euler_rates(zyx, euler_rates_from_local(zyx, wl))
+        a, b = self.a.copy(), self.b.copy()
+        a[0:3, 3:6] = dt * np.eye(3); b[0:3] = 0.5 * dt * dt * np.eye(3); b[3:6] = dt * np.eye(3)
+        q = np.eye(18)
+        q[0:3, 0:3] *= (dt / 20.0) * prm["imuProcessNoisePosition"]
+        q[3:6, 3:6] *= (dt * float(np.float32(9.81)) / 20.0) * prm["imuProcessNoiseVelocity"]
+        q[6:18, 6:18] *= dt * prm["footProcessNoisePosition"]
+        r = np.eye(28)
+        r[0:12, 0:12] *= prm["footSensorNoisePosition"]; r[12:24, 12:24] *= prm["footSensorNoiseVelocity"]; r[24:28, 24:28] *= prm["footHeightSensorNoise"]
+        qp = np.zeros(16); vp = np.zeros(16)
+        qp[3:6] = zyx; qp[6:16] = jpos
+        vp[3:6] = euler_rates_from_global(zyx, wg); vp[6:16] = jvel
+        ee_pos, ee_vel = kin(qp, vp)
+        ps = np.zeros(12); vs = np.zeros(12)
+        for i in range(4):
+            k = 1.0 if contact[i] else 100.0
+            q[6 + 3 * i:9 + 3 * i, 6 + 3 * i:9 + 3 * i] *= k
+            r[3 * i:3 * i + 3, 3 * i:3 * i + 3] *= k; r[12 + 3 * i:15 + 3 * i, 12 + 3 * i:15 + 3 * i] *= k; r[24 + i, 24 + i] *= k
+            ps[3 * i:3 * i + 3] = -ee_pos[3 * i:3 * i + 3]; ps[3 * i + 2] += prm["footRadius"]
+            vs[3 * i:3 * i + 3] = -ee_vel[3 * i:3 * i + 3]
+        accel = rot_zyx(zyx) @ np.asarray(al, dtype=float) + np.array([0, 0, -9.81])
+        y = np.concatenate([ps, vs, self.heights])
+        self.x = a @ self.x + b @ accel
+        pm = a @ self.P @ a.T + q
+        ey = y - self.c @ self.x
+        s = self.c @ pm @ self.c.T + r
+        self.x = self.x + pm @ self.c.T @ np.linalg.solve(s, ey)
+        p = (np.eye(18) - pm @ self.c.T @ np.linalg.solve(s, self.c)) @ pm
+        p = (p + p.T) / 2.0
+        if np.linalg.det(p[0:2, 0:2]) > 0.000001:
+            p[0:2, 2:18] = 0.0; p[2:18, 0:2] = 0.0; p[0:2, 0:2] /= 10.0
+        self.P = p
+        rbd = np.zeros(32)
+        rbd[0:3] = zyx; rbd[3:6] = self.x[0:3]; rbd[6:16] = jpos; rbd[16:19] = wg; rbd[19:22] = self.x[3:6]; rbd[22:32] = jvel
+        return rbd

@@ -27,3 +27,8 @@ refs, _ = hb.plan_references(np.zeros(B), N * dt, x0, (0.3, 0.0, 0.0, 0.1), feet
 info, sol, tau, st = ctx.resident_cycle(True, 0.002, np.zeros(B), x0, refs, rbd)
 cmd, out_tau, es = ctx.joint_command(0.002, x0, np.zeros((B, 22)), sol, np.full(B, 3, dtype=np.int32), rbd)
 print("resident cycle wbc status", st, "command finite", np.isfinite(cmd).all())
+# state estimator
+st = hb.kf_states(B)
+quat = np.tile([0.0, 0.0, 0.0, 1.0], (B, 1))
+rb = ctx.estimator_update(0.002, st, quat, np.zeros((B, 3)), np.tile([0, 0, 9.81], (B, 1)), x0[:, 12:22], np.zeros((B, 10)), np.ones((B, 4), dtype=np.uint8))
+print("estimator rbd finite", np.isfinite(rb).all(), "height", rb[0, 5])
