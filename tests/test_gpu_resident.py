@@ -76,3 +76,37 @@ def test_warm_cycle_requires_previous_solution():
     with pytest.raises(RuntimeError):
         ctx.resident_cycle(False, 0.002, np.zeros(4), x0, refs, rbd)
     ctx.close()
+
+
+def test_kinematic_closed_loop_rollout():
+    """Closed loop without a simulator: the measured state of the next cycle is the planned state one node ahead (perfect tracking).
+    Exercises planner state, device planner, warm-start shift and the solve over many consecutive cycles (towards SURVEY 8f row N2)."""
+    ctx = hb.Context(horizon_N=N, dt=DT, max_batch=16, device=0)
+    B, cycles = 8, 40
+    x = scenarios.random_initial_states(B, seed=71)
+    x[:, 0:6] = 0.0
+    cmd = np.tile([0.3, 0.0, 0.0, 0.0], (B, 1)); cmd[B // 2:, 0] = -0.2
+    gaits = ["trot"] * (B // 2) + ["standing_trot"] * (B - B // 2)
+    x_start = x.copy()
+    t = 0.0
+    worst_tau = 0.0
+    for c in range(cycles):
+        rbd = scenarios.consistent_rbd(x)
+        ins = hb.make_plan_inputs(np.full(B, t), N * DT, x, cmd, None, gaits, 0.2)
+        info, sol, tau, st, ps = ctx.resident_plan_cycle(c == 0, 0.002, ins, rbd)
+        assert (ps == 0).all(), (c, ps)
+        assert (info["status"] == 0).all(), (c, info["status"])
+        assert (st == 0).all(), (c, st)
+        worst_tau = max(worst_tau, np.abs(tau).max())
+        _, xt, ut = ctx.resident_read(B)
+        x = xt[:, 1].copy()                      # perfect tracking of the plan over one node
+        t += DT
+    T_total = cycles * DT
+    assert np.isfinite(x).all() and worst_tau <= 60.0 + 1e-6
+    # the robots kept their height and moved in the commanded direction (the gait starts after 0.2 s of stance)
+    assert np.all(np.abs(x[:, 8] - 0.63) < 0.05)
+    yaw = x_start[:, 9]
+    fwd = (x[:, 6] - x_start[:, 6]) * np.cos(yaw) + (x[:, 7] - x_start[:, 7]) * np.sin(yaw)
+    assert np.all(fwd[:B // 2] > 0.05) and np.all(fwd[B // 2:] < -0.03), fwd
+    assert np.all(np.abs(fwd) < 1.5 * np.abs(cmd[:, 0]) * T_total + 0.05)
+    ctx.close()
