@@ -553,6 +553,7 @@ struct hb_ctx {
   double *res_xt = nullptr, *res_ut = nullptr, *res_t0 = nullptr;   // resident primal solution (hb_resident_cycle_batch)
   int res_valid = 0;                                                // number of instances holding a previous solution
   hb_plan_input* s_plan = nullptr; double* res_stance = nullptr; int32_t* s_pstatus = nullptr;   // device planner (row N1)
+  double* res_sol = nullptr; int res_sol_valid = 0;   // last good WBC solution per instance (WeightedWbc fallback, W5)
   hb_kf_state* s_kf = nullptr;                                                                  // estimator staging (row N3)
   int32_t *s_mode, *s_imode, *s_status, *s_iters;
   uint8_t* s_stance;
@@ -677,7 +678,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   ok = ok && dalloc(&ctx->xdes, B * NX) == cudaSuccess && dalloc(&ctx->udes, B * NU) == cudaSuccess && dalloc(&ctx->wsol, B * NWBC) == cudaSuccess;
   ok = ok && dalloc(&ctx->wstatus, B) == cudaSuccess && dalloc(&ctx->witers, B) == cudaSuccess && dalloc(&ctx->wmode, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_x0, B * NX) == cudaSuccess && dalloc(&ctx->s_xref, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_swing, B * (N + 1) * 24) == cudaSuccess;
-  ok = ok && dalloc(&ctx->s_kf, B) == cudaSuccess;
+  ok = ok && dalloc(&ctx->s_kf, B) == cudaSuccess && dalloc(&ctx->res_sol, B * NWBC) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_plan, B) == cudaSuccess && dalloc(&ctx->res_stance, B * 12) == cudaSuccess && dalloc(&ctx->s_pstatus, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->res_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->res_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->res_t0, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->s_rbd, B * 32) == cudaSuccess;
@@ -705,7 +706,7 @@ int hb_destroy(hb_ctx* ctx) {
   void* ptrs[] = {ctx->lin, ctx->proj, ctx->rk, ctx->gains, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->qH, ctx->qg, ctx->qA, ctx->qlb, ctx->qub, ctx->qm, ctx->xdes, ctx->udes,
                   ctx->wsol, ctx->wstatus, ctx->witers, ctx->wmode, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_xt, ctx->s_ut, ctx->s_rbd, ctx->s_xd,
                   ctx->s_ud, ctx->s_sol, ctx->s_tau, ctx->s_t0, ctx->s_misc, ctx->s_mode, ctx->s_imode, ctx->s_status, ctx->s_iters, ctx->s_stance,
-                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf};
+                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf, ctx->res_sol};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
   if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
@@ -902,6 +903,21 @@ int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0
   return HB_OK;
 }
 
+// WeightedWbc::update fallback (WeightedWbc.cpp:57-64): a QP that did not solve returns the previous solution of that instance; a solved
+// one becomes the new "previous". `have_prev` is 0 on the first cycle after a cold start (the reference then returns the unsolved iterate).
+__global__ void wbc_fallback_kernel(int B, int have_prev, const int32_t* status, double* sol, double* prev, double* torque) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * NWBC) return;
+  const int i = idx / NWBC, j = idx - i * NWBC;
+  if (status[i] != 0 && have_prev) {
+    const double v = prev[idx];
+    sol[idx] = v;
+    if (torque && j >= 28) torque[(size_t)i * NJ + j - 28] = v;
+  } else {
+    prev[idx] = sol[idx];
+  }
+}
+
 // store the solve time of a cold-started resident solution
 __global__ void set_times_kernel(int B, const double* t0_new, double* t0_res) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -932,7 +948,16 @@ int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel
   ctx->launches++;
   CK(cudaGetLastError());
   if (ctx->res_valid < ctx->base + B) ctx->res_valid = ctx->base + B;
-  return hb_control_step_batch_dev(ctx, B, t_rel, x0, xref, swing, mode, rbd, xt, ut, info, wbc_sol, torque, wbc_status);
+  rc = hb_control_step_batch_dev(ctx, B, t_rel, x0, xref, swing, mode, rbd, xt, ut, info, wbc_sol, torque, wbc_status);
+  if (rc) return rc;
+  if (wbc_status) {
+    const int have_prev = (!cold_start && ctx->res_sol_valid >= ctx->base + B) ? 1 : 0;
+    wbc_fallback_kernel<<<(B * NWBC + 127) / 128, 128, 0, ctx->stream>>>(B, have_prev, wbc_status, wbc_sol, ctx->res_sol + o * NWBC, torque);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (ctx->res_sol_valid < ctx->base + B) ctx->res_sol_valid = ctx->base + B;
+  }
+  return HB_OK;
 }
 
 int hb_plan_references_batch_dev(hb_ctx* ctx, int B, const hb_plan_input* in, const double* feet, double* latest_stance, hb_reference* out,

@@ -266,7 +266,6 @@ __device__ __forceinline__ void kin_chain_f(const ChainModel& md, int leg, bool 
 #pragma unroll
     for (int i = 0; i < 3; ++i) w[i] = ax0[i] * v3 + ax0[3 + i] * v4 + ax0[6 + i] * v5;
   }
-#pragma unroll
   T P[3], Lo[3], mc[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) { P[i] = T(0.0); Lo[i] = T(0.0); mc[i] = T(0.0); }

@@ -163,7 +163,9 @@ int hb_joint_command_batch_dev(hb_ctx* ctx, int B, const hb_pd_gains* gains, dou
  * One call = reference expansion (hb_reference -> node grid) + warm start (previous solution interpolated on the new grid, tail from
  * the initializer; mpc.coldStart false, task.info:146 -- or the initializer everywhere when cold_start != 0) + one SQP iteration +
  * policy evaluation at t0 + t_rel + WeightedWbc + torque law. Only t0, x0, refs, rbd go in and info / wbc_sol / torque / status come
- * out; hb_resident_read_batch copies the resident trajectories out when the caller wants them (PrimalSolution). */
+ * out; hb_resident_read_batch copies the resident trajectories out when the caller wants them (PrimalSolution). The WeightedWbc
+ * fallback is applied on the device: an instance whose QP did not solve (wbc_status != 0) returns its previous solution and torques
+ * (WeightedWbc.cpp:57-64) from the second cycle on. */
 int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0,
                                 const hb_reference* refs, const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque,
                                 int32_t* wbc_status);

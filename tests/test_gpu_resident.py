@@ -110,3 +110,23 @@ def test_kinematic_closed_loop_rollout():
     assert np.all(fwd[:B // 2] > 0.05) and np.all(fwd[B // 2:] < -0.03), fwd
     assert np.all(np.abs(fwd) < 1.5 * np.abs(cmd[:, 0]) * T_total + 0.05)
     ctx.close()
+
+
+def test_wbc_fallback_returns_previous_solution():
+    """W5 (WeightedWbc.cpp:57-64): an instance whose QP does not solve keeps the solution of its previous cycle."""
+    ctx = hb.Context(horizon_N=N, dt=DT, max_batch=16, device=0)
+    B = 6
+    x0, refs, rbd = _setup(B, seed=47)
+    t0 = np.zeros(B)
+    info, sol0, tau0, st0 = ctx.resident_cycle(True, 0.002, t0, x0, refs, rbd)
+    assert (st0 == 0).all()
+    bad = rbd.copy()
+    bad[2, 22:32] = 1e7          # absurd joint velocities: the torque-limit rows cannot be met
+    bad[4, 6:16] = np.nan        # NaN measurement
+    info, sol1, tau1, st1 = ctx.resident_cycle(False, 0.002, t0 + DT, x0, refs, bad)
+    assert st1[2] != 0 and st1[4] != 0 and (np.delete(st1, [2, 4]) == 0).all()
+    for i in (2, 4):
+        assert np.array_equal(sol1[i], sol0[i]) and np.array_equal(tau1[i], tau0[i])
+    for i in (0, 1, 3, 5):
+        assert not np.array_equal(sol1[i], sol0[i])
+    ctx.close()
