@@ -325,15 +325,15 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
     bool ok = warp_chol_inv(w.K, n, ldn, w.kdi, lane, 1e-10);
     // ---------------- V = Li Aeq'  (n x me), lane per equality row
     if (me > 0) {
-      if (lane < me) {
-        const double* ar = w.Aeq + lane * ldn;
-        for (int i = 0; i < n; ++i) {
-          double a0 = w.kdi[i] * ar[i], a1 = 0.0;
-          int k = 0;
-          for (; k + 1 < i; k += 2) { a0 += w.K[k * ldn + i] * ar[k]; a1 += w.K[(k + 1) * ldn + i] * ar[k + 1]; }
-          if (k < i) a0 += w.K[k * ldn + i] * ar[k];
-          w.V[i * ldv + lane] = a0 + a1;
-        }
+      // entries (i, e) spread over all lanes (a lane per equality row would leave most of the warp idle: me is 6 for the WBC)
+      for (int idx = lane; idx < n * me; idx += 32) {
+        const int i = idx / me, e = idx - i * me;
+        const double* ar = w.Aeq + e * ldn;
+        double a0 = w.kdi[i] * ar[i], a1 = 0.0;
+        int k = 0;
+        for (; k + 1 < i; k += 2) { a0 += w.K[k * ldn + i] * ar[k]; a1 += w.K[(k + 1) * ldn + i] * ar[k + 1]; }
+        if (k < i) a0 += w.K[k * ldn + i] * ar[k];
+        w.V[i * ldv + e] = a0 + a1;
       }
       __syncwarp();
       // S = V'V (lower), then Cholesky + inverse
