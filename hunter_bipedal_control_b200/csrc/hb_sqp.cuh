@@ -301,7 +301,7 @@ template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volat
 // discretisation, cost and constraint rows are built it is dead and re-used for the projection workspace and the projected model.
 struct LqShared {
   double rec[LIN_STRIDE];
-  double Ad[TS];                       // discrete A, then At
+  double Ad[9 * NX];                   // rows 3..11 of the discrete A, then of At (the other rows are identity / identity + dt Pxv and are formed on the way out)
   double BdF[9 * 12], Bdv[9 * NJ];     // rows 3..11 of Bd
   double Cv[12 * NX], Dv[12 * NJ], ev[12];
   double Nv[NJ * NVMAX], pev[NJ];
@@ -384,12 +384,8 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
       double s = 0.0;
 #pragma unroll
       for (int kk = 0; kk < 9; ++kk) s = fma(A2c[i * NX + 3 + kk], c1[kk], s);
-      sh.Ad[(3 + i) * NX + j] = 0.5 * dt * (c1[i] + A2c[i * NX + j] + dt * s) + ((3 + i == j) ? 1.0 : 0.0);
+      sh.Ad[i * NX + j] = 0.5 * dt * (c1[i] + A2c[i * NX + j] + dt * s) + ((3 + i == j) ? 1.0 : 0.0);
     }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) sh.Ad[i * NX + j] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-    for (int i = 12; i < NX; ++i) sh.Ad[i * NX + j] = (i == j) ? 1.0 : 0.0;
     if (j < 12) {
       // B1 force column j = [e_a / m ; Bf1[:, j] ; 0]: (A2 B1)[i][j] = A2c[i][a] / m + A2c[i][3:6] Bf1[:, j]
       const double b0 = Bf1[j], b1 = Bf1[12 + j], b2 = Bf1[24 + j];
@@ -638,13 +634,11 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     // At = Ad + Bd_v Pxv : rows 3..11 += Bdv Pxv ; rows 12..21 += dt Pxv
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-      double s = sh.Ad[(3 + i) * NX + j];
+      double s = sh.Ad[i * NX + j];
 #pragma unroll
       for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Bdv[i * NJ + kk], pc[kk], s);
-      sh.Ad[(3 + i) * NX + j] = s;
+      sh.Ad[i * NX + j] = s;
     }
-#pragma unroll
-    for (int kk = 0; kk < NJ; ++kk) sh.Ad[(12 + kk) * NX + j] += dt * pc[kk];
     // PRPx_v = Pv + Rvv Pxv (10 x 22)
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
@@ -748,7 +742,14 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     out[PJ_RV + lane] = dt * s;
   }
   // ---- write the rest of the record
-  for (int idx = lane; idx < TS; idx += 32) out[PJ_AT + idx] = sh.Ad[idx];
+  for (int idx = lane; idx < TS; idx += 32) {
+    const int i = idx / NX, j = idx - i * NX;
+    double v;
+    if (i < 3) v = (i == j) ? 1.0 : 0.0;                                   // momentum rows: identity
+    else if (i < 12) v = sh.Ad[idx - 3 * NX];
+    else v = ((i == j) ? 1.0 : 0.0) + dt * Pxv[(i - 12) * NX + j];         // joint rows: I + dt Pxv
+    out[PJ_AT + idx] = v;
+  }
   for (int idx = lane; idx < NX * NTMAX; idx += 32) out[PJ_BT + idx] = Bt[idx];
   if (lane < NX) out[PJ_BTV + lane] = sh.bt[lane];
   for (int idx = lane; idx < NJ * NX; idx += 32) out[PJ_PXV + idx] = Pxv[idx];
@@ -1083,8 +1084,18 @@ __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int 
     }
   }
   if (accepted) {
-    for (int idx = lane; idx < (N + 1) * NX; idx += 32) xt[idx] += alpha * dxt[idx];
-    for (int idx = lane; idx < N * NU; idx += 32) ut[idx] += alpha * dut[idx];
+    // accepted step: x += alpha dx, u += alpha du; four independent loads in flight per lane (one warp streams 70 KB here)
+    auto axpy = [&](double* y, const double* d, int n) {
+      int idx = lane;
+      for (; idx + 96 < n; idx += 128) {
+        const double y0 = y[idx], y1 = y[idx + 32], y2 = y[idx + 64], y3 = y[idx + 96];
+        const double d0 = d[idx], d1 = d[idx + 32], d2 = d[idx + 64], d3 = d[idx + 96];
+        y[idx] = fma(alpha, d0, y0); y[idx + 32] = fma(alpha, d1, y1); y[idx + 64] = fma(alpha, d2, y2); y[idx + 96] = fma(alpha, d3, y3);
+      }
+      for (; idx < n; idx += 32) y[idx] = fma(alpha, d[idx], y[idx]);
+    };
+    axpy(xt, dxt, (N + 1) * NX);
+    axpy(ut, dut, N * NU);
   }
   if (lane == 0 && info_out) {
     struct Info { double alpha, merit0, merit1, viol0, viol1, armijo; int32_t status, n_trials; };
