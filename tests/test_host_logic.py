@@ -131,3 +131,23 @@ def test_gloo_world_size_2_gather(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK" in outs[0]
+
+
+def test_host_only_entry_points_reject_misuse():
+    """The host-only calls of the ABI (no GPU needed) report misuse through their return code."""
+    import ctypes as C
+    import hunter_bipedal_control_b200 as hb
+    lib = hb.load_library()
+    assert lib.hb_plan_references(1, None, None, None) == -1
+    assert lib.hb_gait_select(1, None, None, None, None, None, None) == -1
+    assert lib.hb_kf_reset(1, None) == -1 and lib.hb_default_kf_params(None) == -1 and lib.hb_default_pd_gains(None) == -1
+    assert lib.hb_plan_references(0, (hb.HbPlanInput * 1)(), (C.c_double * 12)(), (hb.HbReference * 1)()) == 0       # empty batch
+    sel = hb.GaitSelector(1)
+    sel.state[0].head = 77                                                                                           # corrupted ring-buffer index
+    with pytest.raises(RuntimeError):
+        sel.update([0.1, 0, 0, 0], np.zeros((1, 22)))
+    st = hb.kf_states(3)
+    assert st[2].P[0] == 100.0 and st[2].P[1] == 0.0 and st[2].P[19] == 100.0 and st[1].x_hat[5] == 0.0
+    g = hb.default_pd_gains(); k = hb.default_kf_params()
+    assert (g.kp_big_stance, g.kd_feet) == (40.0, 0.01) and (k.foot_radius, k.foot_sensor_noise_velocity) == (0.02, 0.1)
+    assert b"capacity" in lib.hb_strerror(-5) or b"planner" in lib.hb_strerror(-5)
