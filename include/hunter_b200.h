@@ -12,6 +12,7 @@
  *   hb_policy_eval_batch    <-> MPC_MRT_Interface::evaluatePolicy     legged_controllers/src/LeggedController.cpp:154-156
  *   hb_control_step_batch   <-> LeggedController::update MPC->policy->WBC->torque law   LeggedController.cpp:137-257
  *   hb_resident_cycle_batch <-> SqpSolver::run with its resident primalSolution_ (warm start) + the rest of LeggedController::update
+ *   hb_resident_plan_cycle_batch <-> ReferenceManager::preSolverRun (planner on the device) + hb_resident_cycle_batch
  *   hb_estimator_update_batch <-> KalmanFilterEstimate::update        legged_estimation/src/LinearKalmanFilter.cpp:72-185
  *   hb_joint_command_batch  <-> joint command / torque law            LeggedController.cpp:186-257
  *   hb_plan_references      <-> GaitSchedule tiling + SwingTrajectoryPlanner::update + cmdVelToTargetTrajectories + calculateJointRef
