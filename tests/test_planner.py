@@ -304,3 +304,36 @@ def test_plan_cycle_on_device_equals_host_plan_plus_cycle():
     info, sol, tau, st, ps = ctx.resident_plan_cycle(False, 0.002, ins1, rbd)
     assert (ps == 0).all() and np.isfinite(tau).all()
     ctx.close()
+
+
+def test_planner_fuzz_capacity_and_finiteness():
+    """Random solve times, gait phases, commands and horizons up to 2 s: the planner never overflows hb_reference for the shipped gaits,
+    every number it writes is finite, and horizons beyond the target capacity are refused with -5 instead of truncated."""
+    rng = np.random.default_rng(77)
+    n = 400
+    x0 = scenarios.random_initial_states(n, seed=77)
+    gaits = [["trot", "standing_trot", "flying_trot", "stance"][i % 4] for i in range(n)]
+    cmd = np.stack([rng.uniform(-0.8, 0.8, n), rng.uniform(-0.3, 0.3, n), np.zeros(n), rng.uniform(-0.8, 0.8, n)], axis=1)
+    t0 = rng.uniform(0.0, 500.0, n)
+    start = t0 - rng.uniform(-0.3, 300.0, n)
+    feet = np.zeros((n, 12))
+    for i in range(n):
+        Ry = R.rot_zyx([x0[i, 9], 0, 0])
+        feet[i] = np.concatenate([x0[i, 6:9] + Ry @ np.array(b) for b in R.FEET_BIAS])
+    for horizon in (0.3, 1.0, 2.0):
+        refs, ls = hb.plan_references(t0, horizon, x0, cmd, feet, gaits, start, latest_stance=feet)
+        assert np.isfinite(ls).all()
+        for i in range(0, n, 7):
+            r = refs[i]
+            assert 0 <= r.n_events <= 32 and 2 <= r.n_targets <= 16
+            for k in range(r.n_targets):
+                assert np.isfinite(np.array(r.target_states[k][:])).all()
+            for c in range(4):
+                for a in range(3):
+                    ns = r.n_segments[c][a]
+                    assert 1 <= ns <= 24
+                    seg = np.array([list(r.segments[c][a][s][:]) for s in range(ns)])
+                    assert np.isfinite(seg).all() and np.all(seg[:, 1] > seg[:, 0])
+                    assert seg[0, 0] <= t0[i] + 1e-9 and seg[-1, 1] >= t0[i] + horizon - 1e-9       # the window is covered
+    with pytest.raises(RuntimeError):
+        hb.plan_references(t0[:4], 3.0, x0[:4], cmd[:4], feet[:4], gaits[:4], start[:4])          # 21 samples > HB_MAX_TARGETS
