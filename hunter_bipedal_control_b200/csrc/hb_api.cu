@@ -512,6 +512,59 @@ __global__ void __launch_bounds__(8) plan_references_kernel(int B, const hb_plan
   if (status) status[inst] = rc;
 }
 
+// Cooperative form of the device planner: four threads per instance (eight instances per 32-thread block). Thread r plans foot r
+// (the feet are independent), then threads 0 and 1 run the IK of the left / right leg on the resampled target kept in shared
+// memory, then thread 0 writes the schedule and the targets. Same functions as the host planner, so the plan is the same.
+__global__ void __launch_bounds__(32) plan_references_coop_kernel(int B, const hb_plan_input* in, const double* feet, double* latest_stance,
+                                                                  hb_reference* out, int32_t* status, hbplan::PlanConsts pc) {
+  __shared__ hbplan::Target s_tg[8];
+  __shared__ int s_rc[8];
+  const int g = threadIdx.x >> 2, r = threadIdx.x & 3;
+  const int inst = blockIdx.x * 8 + g;
+  const bool active = inst < B;
+  hb_plan_input p;
+  hbplan::ModeSchedule ms;
+  hb_reference* o = out + (active ? inst : 0);
+  double t_lo = 0.0, t_hi = 0.0, tf = 0.0;
+  int rc = 0;
+  if (r == 0) s_rc[g] = 0;
+  __syncwarp();
+  if (active) {
+    p = in[inst];
+    if (feet) for (int i = 0; i < 12; ++i) p.feet_pos[i] = feet[(size_t)inst * 12 + i];
+    if (!(p.horizon > 0.0) || !(p.prev_event < p.gait_start) || p.gait < 0 || p.gait > 3) rc = -1;
+    tf = p.t0 + p.horizon; t_lo = p.t0 - 1e-9; t_hi = tf + 1e-9;
+    if (rc == 0 && !hbplan::tile_gait(p.gait, p.prev_event, p.gait_start, p.t0 - p.horizon, tf + p.horizon, ms)) rc = -5;
+    if (rc == 0) {
+      // phase A: foot r (every thread holds its own copy of the two-sample target; it is cheap)
+      hbplan::Target tg2 = hbplan::cmd_vel_to_target(pc, p.cmd_vel, p.t0, p.x0, p.time_to_target);
+      const double body_vel_cmd[6] = {p.cmd_vel[0], p.cmd_vel[1], p.cmd_vel[2], p.cmd_vel[3], 0.0, 0.0};
+      hbplan::SwingOut so{o, t_lo, t_hi, false};
+      for (int a = 0; a < 3; ++a) o->n_segments[r][a] = 0;
+      if (!hbplan::plan_swing(ms, tg2, p.t0, p.feet_pos, body_vel_cmd, latest_stance + (size_t)inst * 12, so, r, r + 1) || so.overflow) rc = -5;
+      if (r == 0) {
+        s_tg[g] = tg2;
+        if (p.joint_ik) { const int n = hbplan::joint_refs_resample(pc, p.t0, tf, s_tg[g]); if (n < 0) rc = -5; }
+      }
+    }
+    if (rc != 0) atomicMin(&s_rc[g], rc);
+  }
+  __syncwarp();
+  // phase B: IK per leg on the shared target (segments of every foot are in place after the barrier)
+  if (active && s_rc[g] == 0 && p.joint_ik && s_tg[g].n > 2 && r < 2) hbplan::joint_refs_leg(pc, o, r, p.x0, s_tg[g]);
+  __syncwarp();
+  if (active && r == 0) {
+    int frc = s_rc[g];
+    if (frc == 0) frc = hbplan::write_schedule_and_targets(ms, s_tg[g], t_lo, t_hi, o);
+    if (frc != 0) {
+      o->n_events = 0; o->modes[0] = 3; o->n_targets = 1; o->target_times[0] = p.t0;
+      for (int i = 0; i < 22; ++i) o->target_states[0][i] = (i < 6) ? 0.0 : p.x0[i];
+      for (int c = 0; c < 4; ++c) for (int a = 0; a < 3; ++a) o->n_segments[c][a] = 0;
+    }
+    if (status) status[inst] = frc;
+  }
+}
+
 // parity probe: flow map value, Jacobians and contact kinematics from the warp-cooperative linearisation
 __global__ void __launch_bounds__(32) probe_flow_map_kernel(int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -966,7 +1019,9 @@ int hb_plan_references_batch_dev(hb_ctx* ctx, int B, const hb_plan_input* in, co
   if (B == 0) return HB_OK;
   if (set_device(ctx)) return HB_ECUDA;
   static const hbplan::PlanConsts pc = hbplan::make_consts();
-  plan_references_kernel<<<(B + 7) / 8, 8, 0, ctx->stream>>>(B, in, feet, latest_stance, out, status, pc);
+  static const bool coop = [] { const char* e = getenv("HB_PLAN_COOP"); return e && e[0] == '1'; }();
+  if (coop) plan_references_coop_kernel<<<(B + 7) / 8, 32, 0, ctx->stream>>>(B, in, feet, latest_stance, out, status, pc);
+  else plan_references_kernel<<<(B + 7) / 8, 8, 0, ctx->stream>>>(B, in, feet, latest_stance, out, status, pc);
   ctx->launches++;
   CK(cudaGetLastError());
   return HB_OK;

@@ -204,15 +204,17 @@ HBP_HD inline void gen_swing(SwingOut& sp, int foot, double t0, double t1, Vec3 
 
 // SwingTrajectoryPlanner::update (:164-286). latest_stance (4x3) is the planner's state (in/out).
 // Returns false where the reference would throw (swing phase without a defined take-off / touch-down, :421-458).
+// The feet are independent of each other: [j_begin, j_end) selects the ones this call plans (the host planner passes 0..4, the
+// cooperative device kernel one foot per thread).
 HBP_HD inline bool plan_swing(const ModeSchedule& ms, const Target& tg, double init_time, const double* current_feet /*12*/, const double* body_vel_cmd /*6*/,
-                              double* latest_stance /*12*/, SwingOut& sp) {
+                              double* latest_stance /*12*/, SwingOut& sp, int j_begin = 0, int j_end = 4) {
   const int np = ms.n_events + 1;
   const int mode_now = mode_at(ms, init_time + 0.001);
-  for (int i = 0; i < 4; ++i) {
+  for (int i = j_begin; i < j_end; ++i) {
     if (contact_flag(mode_now, i)) for (int a = 0; a < 3; ++a) latest_stance[3 * i + a] = current_feet[3 * i + a];
     latest_stance[3 * i + 2] = HB_NEXT_POSITION_Z;
   }
-  for (int j = 0; j < 4; ++j) {
+  for (int j = j_begin; j < j_end; ++j) {
     bool stock[MAX_PHASES + 1];
     for (int p = 0; p < np; ++p) stock[p] = contact_flag(ms.modes[p], j);
     Vec3 last{latest_stance[3 * j], latest_stance[3 * j + 1], latest_stance[3 * j + 2]}, next = last;
@@ -488,14 +490,14 @@ HBP_HD inline double swing_value(const hb_reference* ref, int c, int a, double t
 
 // SwitchedModelReferenceManager::calculateJointRef (:251-300): resample the target every 0.15 s and replace the joint part by IK on the
 // planned toe positions, each sample seeded by the previous one. Returns false when the sample count exceeds HB_MAX_TARGETS.
-HBP_HD inline bool joint_references(const PlanConsts& pc, const hb_reference* sp, double init_time, double final_time, const double* init_state, Target& tg) {
-  if (tg.n <= 1) return true;
+// Step 1 of calculateJointRef: the resampled target (sample times, interpolated states, default joints in sample 0).
+// Returns the number of samples n (0: horizon too short, the two-sample target stays; -1: more than HB_MAX_TARGETS samples).
+HBP_HD inline int joint_refs_resample(const PlanConsts& pc, double init_time, double final_time, Target& tg) {
+  if (tg.n <= 1) return 0;
   const double step = 0.15;
   const int n = (int)floor((final_time - init_time) / step) + 1;
-  if (n <= 2) return true;
-  if (n > HB_MAX_TARGETS) return false;
-  double Rdes[9];
-  rot_zyx_mat(init_state + 9, Rdes);
+  if (n <= 2) return 0;
+  if (n > HB_MAX_TARGETS) return -1;
   Target old = tg;
   tg.n = n;
   for (int i = 0; i < n; ++i) {
@@ -504,19 +506,31 @@ HBP_HD inline bool joint_references(const PlanConsts& pc, const hb_reference* sp
     target_state(old, tg.t[i], tg.x[i]);
   }
   for (int j = 0; j < 10; ++j) tg.x[0][12 + j] = pc.default_joints[j];
-  for (int i = 0; i < n; ++i) {
-    const double* pose = tg.x[i] + 6;
-    double seed[10];
-    memcpy(seed, tg.x[i > 0 ? i - 1 : 0] + 12, sizeof(seed));
-    for (int leg = 0; leg < 2; ++leg) {
-      const double des[3] = {swing_value(sp, leg, 0, tg.t[i]), swing_value(sp, leg, 1, tg.t[i]), swing_value(sp, leg, 2, tg.t[i])};
-      double qj[5];
-      memcpy(qj, seed + 5 * leg, sizeof(qj));
-      translation_ik(pc, leg, pose, qj, des);
-      rotation_ik(pc, leg, pose, qj, Rdes);
-      memcpy(tg.x[i] + 12 + 5 * leg, qj, sizeof(qj));
-    }
+  return n;
+}
+
+// Step 2 for one leg: IK at every sample, seeded by the previous sample's solution of the same leg (the legs do not interact).
+HBP_HD inline void joint_refs_leg(const PlanConsts& pc, const hb_reference* sp, int leg, const double* init_state, Target& tg) {
+  double Rdes[9];
+  rot_zyx_mat(init_state + 9, Rdes);
+  double qj[5];
+  for (int k = 0; k < 5; ++k) qj[k] = tg.x[0][12 + 5 * leg + k];
+  for (int i = 0; i < tg.n; ++i) {
+    const double des[3] = {swing_value(sp, leg, 0, tg.t[i]), swing_value(sp, leg, 1, tg.t[i]), swing_value(sp, leg, 2, tg.t[i])};
+    translation_ik(pc, leg, tg.x[i] + 6, qj, des);
+    rotation_ik(pc, leg, tg.x[i] + 6, qj, Rdes);
+    for (int k = 0; k < 5; ++k) tg.x[i][12 + 5 * leg + k] = qj[k];
   }
+}
+
+// SwitchedModelReferenceManager::calculateJointRef (:251-300): resample the target every 0.15 s and replace the joint part by IK on the
+// planned toe positions, each sample seeded by the previous one. Returns false when the sample count exceeds HB_MAX_TARGETS.
+HBP_HD inline bool joint_references(const PlanConsts& pc, const hb_reference* sp, double init_time, double final_time, const double* init_state, Target& tg) {
+  const int n = joint_refs_resample(pc, init_time, final_time, tg);
+  if (n < 0) return false;
+  if (n == 0) return true;
+  joint_refs_leg(pc, sp, 0, init_state, tg);
+  joint_refs_leg(pc, sp, 1, init_state, tg);
   return true;
 }
 
@@ -549,6 +563,22 @@ HBP_HD inline int gait_select(hb_gait_selector* st, int gait_type, const double*
   return st->gait_level;
 }
 
+// mode schedule restricted to the window (events strictly inside), keeping the mode in force at t_lo; target samples
+HBP_HD inline int write_schedule_and_targets(const ModeSchedule& ms, const Target& tg, double t_lo, double t_hi, hb_reference* out) {
+  int first = 0;
+  while (first < ms.n_events && ms.events[first] <= t_lo) ++first;
+  int last = first;
+  while (last < ms.n_events && ms.events[last] < t_hi) ++last;
+  const int ne = last - first;
+  if (ne > HB_MAX_EVENTS) return -5;
+  out->n_events = ne;
+  for (int i = 0; i < ne; ++i) out->event_times[i] = ms.events[first + i];
+  for (int i = 0; i <= ne; ++i) out->modes[i] = ms.modes[first + i];
+  out->n_targets = tg.n;
+  for (int k = 0; k < tg.n; ++k) { out->target_times[k] = tg.t[k]; memcpy(out->target_states[k], tg.x[k], sizeof(double) * 22); }
+  return 0;
+}
+
 // One instance, start to finish: schedule, target, swing planner, IK joint references, compact output.
 // Returns 0, -1 (invalid input) or -5 (schedule / reference capacity exceeded, or a swing phase without take-off / touch-down time).
 HBP_HD inline int plan_one(const PlanConsts& pc, const hb_plan_input& p, double* latest_stance /*12, in/out*/, hb_reference* out, bool zero_fill) {
@@ -564,19 +594,7 @@ HBP_HD inline int plan_one(const PlanConsts& pc, const hb_plan_input& p, double*
   for (int c = 0; c < 4; ++c) for (int a = 0; a < 3; ++a) out->n_segments[c][a] = 0;
   if (!plan_swing(ms, tg, p.t0, p.feet_pos, body_vel_cmd, latest_stance, so) || so.overflow) return -5;
   if (p.joint_ik && !joint_references(pc, out, p.t0, tf, p.x0, tg)) return -5;
-  // mode schedule restricted to the window (events strictly inside), keeping the mode in force at t_lo
-  int first = 0;
-  while (first < ms.n_events && ms.events[first] <= so.t_lo) ++first;
-  int last = first;
-  while (last < ms.n_events && ms.events[last] < so.t_hi) ++last;
-  const int ne = last - first;
-  if (ne > HB_MAX_EVENTS) return -5;
-  out->n_events = ne;
-  for (int i = 0; i < ne; ++i) out->event_times[i] = ms.events[first + i];
-  for (int i = 0; i <= ne; ++i) out->modes[i] = ms.modes[first + i];
-  out->n_targets = tg.n;
-  for (int k = 0; k < tg.n; ++k) { out->target_times[k] = tg.t[k]; memcpy(out->target_states[k], tg.x[k], sizeof(double) * 22); }
-  return 0;
+  return write_schedule_and_targets(ms, tg, so.t_lo, so.t_hi, out);
 }
 
 }  // namespace hbplan
