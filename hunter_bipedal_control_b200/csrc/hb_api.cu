@@ -1019,7 +1019,7 @@ int hb_plan_references_batch_dev(hb_ctx* ctx, int B, const hb_plan_input* in, co
   if (B == 0) return HB_OK;
   if (set_device(ctx)) return HB_ECUDA;
   static const hbplan::PlanConsts pc = hbplan::make_consts();
-  static const bool coop = [] { const char* e = getenv("HB_PLAN_COOP"); return e && e[0] == '1'; }();
+  static const bool coop = [] { const char* e = getenv("HB_PLAN_COOP"); return !(e && e[0] == '0'); }();   // HB_PLAN_COOP=0: one thread per instance
   if (coop) plan_references_coop_kernel<<<(B + 7) / 8, 32, 0, ctx->stream>>>(B, in, feet, latest_stance, out, status, pc);
   else plan_references_kernel<<<(B + 7) / 8, 8, 0, ctx->stream>>>(B, in, feet, latest_stance, out, status, pc);
   ctx->launches++;
