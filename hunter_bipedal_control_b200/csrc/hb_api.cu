@@ -480,7 +480,8 @@ __global__ void contact_positions_kernel(int B, const double* x, double* pos) {
   for (int i = 0; i < 12; ++i) pos[(size_t)inst * 12 + i] = o.cpos[i];
 }
 
-// Device planner (row N1): one thread per instance runs the same source as the host planner (csrc/hb_planner.h).
+// Device planner (row N1), simple form: one thread per instance runs the same source as the host planner (csrc/hb_planner.h);
+// kept for HB_PLAN_COOP=0, the default is the cooperative kernel below.
 // plan_prepare_kernel unpacks t0 / x0 from the plan inputs and evaluates computeFootPos at x0 (the planner's current_feet input).
 __global__ void plan_prepare_kernel(int B, const hb_plan_input* in, double* t0, double* x0, double* feet) {
   const int inst = blockIdx.x * blockDim.x + threadIdx.x;

@@ -10,7 +10,7 @@
 //   P2  calculateVelAbs / walkGait (speed-based gait selection)                   legged_interface/src/SwitchedModelReferenceManager.cpp:185-249
 //
 // Everything here is fixed-capacity, allocation-free code that compiles for the host (hb_plan_references, threaded over instances)
-// AND for the device (plan_references_kernel, one thread per instance; row N1): the same source, so both produce the same plan.
+// AND for the device (plan_references_coop_kernel, four threads per instance; row N1): the same source, so both produce the same plan.
 #pragma once
 #include <math.h>
 #include <string.h>

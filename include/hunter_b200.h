@@ -170,7 +170,7 @@ int hb_joint_command_batch_dev(hb_ctx* ctx, int B, const hb_pd_gains* gains, dou
 int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0,
                                 const hb_reference* refs, const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque,
                                 int32_t* wbc_status);
-/* device planner: the same planner source as hb_plan_references, one thread per instance. feet != NULL
+/* device planner: the same planner source as hb_plan_references, four cooperating threads per instance. feet != NULL
  * overrides in[i].feet_pos (B x 12, e.g. from hb_contact_positions_batch_dev); status[i] = 0, -1 or -5 like hb_plan_references. */
 int hb_plan_references_batch_dev(hb_ctx* ctx, int B, const hb_plan_input* in, const double* feet, double* latest_stance,
                                  hb_reference* out, int32_t* status /*nullable*/);
