@@ -571,7 +571,10 @@ void rotation_error_world(const double* Rref, const double* Rmeas, double* err) 
 struct WbcQP { double H[38 * 38], g[38], A[60 * 38], lbA[60], ubA[60]; int m; };
 constexpr double QP_INF = 1e20;  // qpOASES::INFTY
 
-void wbc_assemble(const double* x_des, const double* u_des, const double* rbd, int mode, bool stance_mode, WbcQP& qp) {
+// `terms` (optional) receives the pieces the hierarchical WBC stacks by priority instead of by weight: the weighted task rows
+// (Aw 24x38, bw 24, row count), the contact Jacobian (12x16) and dJ/dt v (12).
+struct WbcTerms { double Aw[24 * 38], bw[24], J[12 * NQ], dJv[12]; int rw; };
+void wbc_assemble(const double* x_des, const double* u_des, const double* rbd, int mode, bool stance_mode, WbcQP& qp, WbcTerms* terms = nullptr) {
   bool fl[4]; mode_to_flags(mode, fl);
   int nc = fl[0] + fl[1] + fl[2] + fl[3];
   const int NV = 38;
@@ -700,6 +703,10 @@ void wbc_assemble(const double* x_des, const double* u_des, const double* rbd, i
       ++rw;
     }
     // contact force task has weight 0 (task.info:328-333): rows vanish from H and g
+  }
+  if (terms) {
+    std::memcpy(terms->Aw, Aw, sizeof(Aw)); std::memcpy(terms->bw, bw, sizeof(bw)); terms->rw = rw;
+    std::memcpy(terms->J, J, sizeof(J)); std::memcpy(terms->dJv, dJv, sizeof(dJv));
   }
   for (int i = 0; i < NV; ++i) {
     for (int j = 0; j < NV; ++j) { double s = 0.0; for (int r = 0; r < rw; ++r) s += Aw[r * NV + i] * Aw[r * NV + j]; qp.H[i * NV + j] = s; }
@@ -955,6 +962,14 @@ void hbo_wbc_assemble(const double* x_des, const double* u_des, const double* rb
   std::memcpy(A, qp.A, sizeof(double) * qp.m * 38);
   std::memcpy(lbA, qp.lbA, sizeof(double) * qp.m); std::memcpy(ubA, qp.ubA, sizeof(double) * qp.m);
   *m = qp.m;
+}
+
+void hbo_wbc_terms(const double* x_des, const double* u_des, const double* rbd, int mode, double* Aw, double* bw, int* rw, double* J, double* dJv) {
+  static thread_local WbcQP qp;
+  static thread_local WbcTerms t;
+  wbc_assemble(x_des, u_des, rbd, mode, false, qp, &t);
+  std::memcpy(Aw, t.Aw, sizeof(t.Aw)); std::memcpy(bw, t.bw, sizeof(t.bw)); *rw = t.rw;
+  std::memcpy(J, t.J, sizeof(t.J)); std::memcpy(dJv, t.dJv, sizeof(t.dJv));
 }
 
 int hbo_qp_solve(int n, int m, const double* H, const double* g, const double* A, const double* lbA, const double* ubA, double rho,

@@ -50,6 +50,7 @@ void hbo_mpc_iteration(const hbo_horizon* hz, const double* x0, const double* x_
                        double* x_traj, double* u_traj, hbo_solve_info* info);
 void hbo_mpc_cold_start(const hbo_horizon* hz, const double* x0, const int32_t* mode, double* x_traj, double* u_traj);
 // WBC (W1-W4)
+void hbo_wbc_terms(const double* x_des, const double* u_des, const double* rbd, int mode, double* Aw, double* bw, int* rw, double* J, double* dJv);
 void hbo_wbc_assemble(const double* x_des, const double* u_des, const double* rbd, int mode, int stance_mode,
                       double* H /*38x38*/, double* g /*38*/, double* A /*60x38 row-major*/, double* lbA, double* ubA, int* m);
 int hbo_qp_solve(int n, int m, const double* H, const double* g, const double* A, const double* lbA, const double* ubA,

@@ -124,6 +124,14 @@ def wbc_assemble(x_des, u_des, rbd_state, mode, stance_mode=False):
     return H, g, A[:m.value].copy(), lb[:m.value].copy(), ub[:m.value].copy()
 
 
+def wbc_terms(x_des, u_des, rbd_state, mode):
+    """Pieces of the WBC problem for the hierarchical formulation: weighted task rows (Aw, bw), contact Jacobian J, dJ/dt v."""
+    x_des, u_des, r = _d(x_des), _d(u_des), _d(rbd_state)
+    Aw = np.zeros((24, 38)); bw = np.zeros(24); J = np.zeros((12, 16)); dJv = np.zeros(12); rw = C.c_int(0)
+    lib().hbo_wbc_terms(_p(x_des), _p(u_des), _p(r), C.c_int(mode), _p(Aw), _p(bw), C.byref(rw), _p(J), _p(dJv))
+    return Aw[:rw.value].copy(), bw[:rw.value].copy(), J, dJv
+
+
 def qp_solve(H, g, A, lbA, ubA, rho):
     H, g, A, lbA, ubA = map(_d, (H, g, A, lbA, ubA))
     n = g.size; m = lbA.size; x = np.zeros(n); it = C.c_int(0)

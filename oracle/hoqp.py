@@ -73,3 +73,33 @@ class HoQp:
 
     def solution(self):
         return self.x
+
+
+def hierarchical_wbc(x_des, u_des, rbd, mode):
+    """legged::HierarchicalWbc::update (legged_wbc/src/HierarchicalWbc.cpp:18-31) on the oracle's WBC pieces:
+       task0 = floating-base EoM + torque limits + friction cone (incl. zero swing forces) + no contact motion,
+       task1 = base acceleration (xy, height, angular),  task2 = 0.1 * contact force + swing leg.
+    Decision vector x = [qdd(16), F(12), tau(10)] as in the weighted formulation. Returns (x, [HoQp levels])."""
+    from . import hbo
+    H, g, A, lb, ub = hbo.wbc_assemble(x_des, u_des, rbd, mode, False)
+    Aw, bw, J, dJv = hbo.wbc_terms(x_des, u_des, rbd, mode)
+    keep = np.abs(A).sum(axis=1) > 0
+    A, lb, ub = A[keep], lb[keep], ub[keep]
+    eq = lb == ub
+    a0, b0 = A[eq], ub[eq]
+    up = (~eq) & (ub < 1e19); dn = (~eq) & (lb > -1e19)
+    d0 = np.vstack([A[up], -A[dn]]); f0 = np.concatenate([ub[up], -lb[dn]])
+    stance = [mode in (2, 3), mode in (1, 3), mode in (2, 3), mode in (1, 3)]
+    rows = [3 * c + k for c in range(4) if stance[c] for k in range(3)]
+    ncm_a = np.zeros((len(rows), 38)); ncm_a[:, :16] = J[rows]; ncm_b = -dJv[rows]          # formulateNoContactMotionTask (WbcBase.cpp:169-188)
+    task0 = Task(np.vstack([a0, ncm_a]), np.concatenate([b0, ncm_b]), d0, f0)
+    nsw = 3 * (4 - sum(stance))
+    w_swing, w_base = 100.0, 1.0                                                              # task.info:328-333 (weights divided out again)
+    swing = Task(Aw[:nsw] / w_swing, bw[:nsw] / w_swing, n=38)
+    base = Task(Aw[nsw:] / w_base, bw[nsw:] / w_base, n=38)
+    cf_a = np.zeros((12, 38)); cf_a[:, 16:28] = np.eye(12)
+    force = Task(cf_a, np.asarray(u_des[:12], dtype=float), n=38)                             # formulateContactForceTask (WbcBase.cpp:325-338)
+    task1 = base
+    task2 = force * 0.1 + swing * 1.0
+    l0 = HoQp(task0); l1 = HoQp(task1, l0); l2 = HoQp(task2, l1)
+    return l2.solution(), [l0, l1, l2], (task0, task1, task2)

@@ -56,3 +56,28 @@ def test_strict_priority_and_slack_carry_over():
     assert h1.stacked_z.shape[1] == n - 6 and h2.stacked_z.shape[1] == 0 and h2.stacked_slack.size == 5
     # the last level uses the two remaining degrees of freedom to reduce its own residual
     assert np.linalg.norm(t2.a @ h2.solution() - t2.b) < np.linalg.norm(t2.a @ h1.solution() - t2.b)
+
+
+def test_hierarchical_wbc_priorities(oracle):
+    """HierarchicalWbc on the oracle's WBC terms: the physics level (EoM, limits, friction, planted stance feet) holds exactly, the base
+    task is met as well as the physics allows, and the lowest level cannot change either."""
+    from oracle.hoqp import hierarchical_wbc
+    from hunter_bipedal_control_b200 import scenarios
+    x = scenarios.random_initial_states(3, seed=9)
+    for i, mode in enumerate((3, 2, 1)):
+        u = np.zeros(22)
+        st = [mode in (2, 3), mode in (1, 3), mode in (2, 3), mode in (1, 3)]
+        for c in range(4):
+            if st[c]:
+                u[3 * c + 2] = 12.586944 * 9.81 / sum(st)
+        rbd = scenarios.consistent_rbd(x[i:i + 1])[0]
+        sol, levels, tasks = hierarchical_wbc(x[i], u, rbd, mode)
+        t0, t1, t2 = tasks
+        assert np.abs(t0.a @ sol - t0.b).max() < 1e-6                       # EoM, zero swing forces, no contact motion
+        assert np.all(t0.d @ sol <= t0.f + 1e-5)                            # torque limits, friction pyramid
+        assert np.allclose(t1.a @ sol, t1.a @ levels[1].solution(), atol=1e-5)
+        # the weighted WBC solves the same physics with soft priorities: its residual on the base task cannot be smaller
+        wsol, wst = oracle.wbc_solve(x[i], u, rbd, mode, False, 1e-8)
+        assert wst == 0
+        assert np.linalg.norm(t1.a @ sol - t1.b) <= np.linalg.norm(t1.a @ wsol - t1.b) + 1e-4
+        assert np.isfinite(sol).all() and np.abs(sol[28:]).max() <= 60 + 1e-6
