@@ -1,6 +1,6 @@
 """Quick GPU-vs-oracle parity report (development aid; the parity tests proper live in tests/)."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import hunter_bipedal_control_b200 as hb
 from hunter_bipedal_control_b200 import scenarios as S
