@@ -1,17 +1,23 @@
-"""CPU restatement of the reference's per-solve reference preprocessing. TEST INFRASTRUCTURE ONLY.
+"""CPU restatements of the steps around the solve. TEST INFRASTRUCTURE ONLY (tests/, smoke and the bench baseline may import it).
 
-Unlike the product's flattened segment lists (csrc/hb_planner.h) this follows the reference's own object structure: one spline
-object per *phase index* and per axis, looked up by lower_bound on the event times, so that the two implementations only agree
-if both are right.
+  P1  GaitSchedule::{insert,tile}ModeSequenceTemplate     legged_interface/src/gait/GaitSchedule.cpp:57-161
+  P2  calculateVelAbs / walkGait / trotGait               legged_interface/src/SwitchedModelReferenceManager.cpp:185-249   (GaitSelectorRef)
+  P3  SwingTrajectoryPlanner::update/calNextFootPos/...   legged_interface/src/foot_planner/SwingTrajectoryPlanner.cpp:164-358, 394-458
+      CubicSpline / MultiCubicSpline                      legged_interface/src/foot_planner/{CubicSpline,MultiCubicSpline}.cpp
+  P4  calculateJointRef + InverseKinematics::computeIK    SwitchedModelReferenceManager.cpp:251-300, foot_planner/InverseKinematics.cpp:20-231
+  P5  cmdVelToTargetTrajectories                          legged_controllers/src/TargetTrajectoriesPublisher.cpp:41-130
+  W6  joint command law                                   legged_controllers/src/LeggedController.cpp:186-257               (joint_command)
+  N3  KalmanFilterEstimate::update                        legged_estimation/src/LinearKalmanFilter.cpp:24-185               (KalmanFilterRef)
+  --  warm start of the next solve                        ocs2_sqp SqpSolver::initializeStateInputTrajectories (un-vendored) (warm_start_shift)
+  constants                                               legged_controllers/config/hunter/{reference,task}.info
 
-  GaitSchedule::{insert,tile}ModeSequenceTemplate     legged_interface/src/gait/GaitSchedule.cpp:57-161
-  SwingTrajectoryPlanner::update/calNextFootPos/...   legged_interface/src/foot_planner/SwingTrajectoryPlanner.cpp:164-358, 394-458
-  CubicSpline / MultiCubicSpline                      legged_interface/src/foot_planner/{CubicSpline,MultiCubicSpline}.cpp
-  cmdVelToTargetTrajectories                          legged_controllers/src/TargetTrajectoriesPublisher.cpp:41-130
-  constants                                           legged_controllers/config/hunter/{reference,task}.info
+Unlike the product's flattened segment lists (csrc/hb_planner.h) the planner part follows the reference's own object structure: one
+spline object per *phase index* and per axis, looked up by lower_bound on the event times; Eigen's pivoted QR is LAPACK's, the
+kernel basis comes from numpy solves, the Kalman filter uses dense A, B, C matrices and np.linalg.solve -- so product and
+restatement only agree if both follow the reference.
 
-parity: pinned only through the reference's published constants and the properties tested in tests/test_planner.py (the
-reference has no fixtures for this layer and it cannot be imported: it is C++ against OCS2).
+parity: these layers have no fixtures in the reference and it cannot be imported (C++ against OCS2 / ROS): pinned through the
+reference's published constants, the properties in tests/test_planner.py and the leg kinematics against the MuJoCo-pinned oracle.
 """
 import bisect
 import math
