@@ -449,6 +449,7 @@ bool riccati_step(const NodeLQ& lq, const Projection& pr, double dt, double* S, 
 }
 
 struct Perf { double merit, dynSSE, eqSSE; };
+inline double dt_of(const hbo_horizon& hz, int k) { return hz.dts ? hz.dts[k] : hz.dt; }
 inline double total_violation(const Perf& p) { return std::sqrt(p.dynSSE + p.eqSSE); }
 
 // computePerformance (S6): merit = sum dt*cost, SSE = dt*||defect||^2, dt*||eq||^2
@@ -457,17 +458,18 @@ Perf performance(const hbo_horizon& hz, const double* xt, const double* ut, cons
   Perf pf{0.0, 0.0, 0.0};
   NodeLQ tmp;
   for (int k = 0; k < hz.N; ++k) {
+    const double dtk = dt_of(hz, k);
     const double* x = xt + k * NX; const double* u = ut + k * NU;
     double f1[NX], f2[NX], x2[NX], ep[12], ev[12];
     flow_map_T<double>(x, u, f1, ep, ev);
-    for (int i = 0; i < NX; ++i) x2[i] = x[i] + hz.dt * f1[i];
+    for (int i = 0; i < NX; ++i) x2[i] = x[i] + dtk * f1[i];
     flow_map_T<double>(x2, u, f2, nullptr, nullptr);
     double d2 = 0.0;
-    for (int i = 0; i < NX; ++i) { double d = x[i] + 0.5 * hz.dt * (f1[i] + f2[i]) - xt[(k + 1) * NX + i]; d2 += d * d; }
+    for (int i = 0; i < NX; ++i) { double d = x[i] + 0.5 * dtk * (f1[i] + f2[i]) - xt[(k + 1) * NX + i]; d2 += d * d; }
     node_cost_constraints(x, u, x_ref + k * NX, swing + k * 24, mode[k], ep, ev, nullptr, tmp);
     double e2 = 0.0;
     for (int i = 0; i < tmp.m; ++i) e2 += tmp.e[i] * tmp.e[i];
-    pf.merit += hz.dt * tmp.cost; pf.dynSSE += hz.dt * d2; pf.eqSSE += hz.dt * e2;
+    pf.merit += dtk * tmp.cost; pf.dynSSE += dtk * d2; pf.eqSSE += dtk * e2;
   }
   return pf;
 }
@@ -484,13 +486,14 @@ void mpc_iteration(const hbo_horizon& hz, const double* x0, const double* x_ref,
   Projection pr;
   bool ok = true;
   for (int k = N - 1; k >= 0; --k) {
-    node_lq(hz.dt, xt + k * NX, ut + k * NU, xt + (k + 1) * NX, x_ref + k * NX, swing + k * 24, mode[k], lq);
+    const double dtk = dt_of(hz, k);
+    node_lq(dtk, xt + k * NX, ut + k * NU, xt + (k + 1) * NX, x_ref + k * NX, swing + k * 24, mode[k], lq);
     double d2 = 0.0, e2 = 0.0;
     for (int i = 0; i < NX; ++i) d2 += lq.b[i] * lq.b[i];
     for (int i = 0; i < lq.m; ++i) e2 += lq.e[i] * lq.e[i];
-    base.merit += hz.dt * lq.cost; base.dynSSE += hz.dt * d2; base.eqSSE += hz.dt * e2;
+    base.merit += dtk * lq.cost; base.dynSSE += dtk * d2; base.eqSSE += dtk * e2;
     project_constraints(lq, pr);
-    ok = ok && riccati_step(lq, pr, hz.dt, S, s, gains[k]);
+    ok = ok && riccati_step(lq, pr, dtk, S, s, gains[k]);
   }
   // forward pass
   std::vector<double> dx((N + 1) * NX, 0.0), du(N * NU, 0.0);

@@ -20,7 +20,9 @@ extern "C" {
 //   mode    [(N+1)]        mode number (MotionPhaseDefinition.h:55-87) in force on interval k
 typedef struct {
   int N;
-  double dt;
+  double dt;          // uniform interval length, used when dts == NULL
+  const double* dts;  // optional: N interval lengths dt_k = t_{k+1} - t_k (non-uniform grids: OCS2's time discretisation re-anchors
+                      // the grid at every mode switch)
 } hbo_horizon;
 
 typedef struct {

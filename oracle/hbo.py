@@ -13,7 +13,16 @@ NX, NU, NQ = 22, 22, 16
 
 
 class Horizon(C.Structure):
-    _fields_ = [("N", C.c_int), ("dt", C.c_double)]
+    _fields_ = [("N", C.c_int), ("dt", C.c_double), ("dts", C.c_void_p)]
+
+
+def _horizon(N, dt):
+    """dt: scalar (uniform grid) or an array of N interval lengths (non-uniform grid). Returns (Horizon, keep-alive array)."""
+    if np.ndim(dt) == 0:
+        return Horizon(N, float(dt), None), None
+    dts = np.ascontiguousarray(dt, dtype=np.float64)
+    assert dts.shape == (N,)
+    return Horizon(N, float(dts[0]), dts.ctypes.data), dts
 
 
 class SolveInfo(C.Structure):
@@ -90,14 +99,14 @@ def node_lq(dt, x, u, xn, xref, swing, mode):
 
 
 def mpc_cold_start(N, dt, x0, mode):
-    hz = Horizon(N, dt); x0 = _d(x0); mode = np.ascontiguousarray(mode, dtype=np.int32)
+    hz, _keep = _horizon(N, dt); x0 = _d(x0); mode = np.ascontiguousarray(mode, dtype=np.int32)
     xt = np.zeros((N + 1, 22)); ut = np.zeros((N, 22))
     lib().hbo_mpc_cold_start(C.byref(hz), _p(x0), _p(mode), _p(xt), _p(ut))
     return xt, ut
 
 
 def mpc_iteration(N, dt, x0, x_ref, swing, mode, xt, ut):
-    hz = Horizon(N, dt)
+    hz, _keep = _horizon(N, dt)
     x0, x_ref, swing = _d(x0), _d(x_ref), _d(swing)
     mode = np.ascontiguousarray(mode, dtype=np.int32)
     xt = _d(xt).copy(); ut = _d(ut).copy()
@@ -107,7 +116,7 @@ def mpc_iteration(N, dt, x0, x_ref, swing, mode, xt, ut):
 
 
 def mpc_iteration_batch(N, dt, x0, x_ref, swing, mode, xt, ut, threads=1):
-    hz = Horizon(N, dt)
+    hz, _keep = _horizon(N, dt)
     B = x0.shape[0]
     x0, x_ref, swing = _d(x0), _d(x_ref), _d(swing)
     mode = np.ascontiguousarray(mode, dtype=np.int32)

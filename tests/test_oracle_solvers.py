@@ -201,3 +201,31 @@ def test_wbc_qp_against_independent_solver(oracle, mode):
     # the optimal face is nearly flat (rank-deficient H, rho = 1e-6), so an independent solver that stops at a relative objective
     # accuracy of 1e-6 only pins the torques loosely; the KKT certificate test above is the sharp statement
     assert np.abs(res.x[28:] - x_ip[28:]).max() < 0.05 * np.abs(x_ip[28:]).max()
+
+
+def test_nonuniform_grid_iteration(oracle):
+    """Per-interval dt_k in the oracle's SQP iteration (groundwork for SURVEY 8a row S1: OCS2 re-anchors the grid at mode switches).
+    A uniform array reproduces the scalar path bit for bit; on a grid whose intervals are split in two the iteration stays close to
+    the coarse one at the shared nodes; an interval shortened to land on an event keeps the iteration well defined."""
+    from hunter_bipedal_control_b200 import scenarios as sc
+    N, dt = 20, 0.02
+    x0 = sc.random_initial_states(1, seed=4)[0]
+    xr, sw, md, _ = sc.make_reference(x0, (0.2, 0, 0, 0), "trot", N, dt)
+    xt, ut = oracle.mpc_cold_start(N, dt, x0, md)
+    a = oracle.mpc_iteration(N, dt, x0, xr, sw, md, xt, ut)
+    b = oracle.mpc_iteration(N, np.full(N, dt), x0, xr, sw, md, xt, ut)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2]["alpha"] == b[2]["alpha"]
+    # refined grid: 2N intervals of dt/2, references sampled on it
+    xr2, sw2, md2, _ = sc.make_reference(x0, (0.2, 0, 0, 0), "trot", 2 * N, dt / 2)
+    xt2, ut2 = oracle.mpc_cold_start(2 * N, dt / 2, x0, md2)
+    c = oracle.mpc_iteration(2 * N, np.full(2 * N, dt / 2), x0, xr2, sw2, md2, xt2, ut2)
+    assert c[2]["status"] == 0 and c[2]["alpha"] > 0
+    assert np.abs(c[0][::2] - a[0]).max() < 0.05 * max(1.0, np.abs(a[0]).max())     # same problem, finer discretisation
+    # non-uniform: the first interval is cut short (a node dropped onto an event at 0.3 dt), the rest re-anchored there
+    dts = np.full(N, dt); dts[0] = 0.3 * dt
+    times = np.concatenate([[0.0], np.cumsum(dts)])
+    xr3 = np.stack([xr[0] + (xr[-1] - xr[0]) * (t / (N * dt)) for t in times])
+    d = oracle.mpc_iteration(N, dts, x0, xr3, sw, md, xt, ut)
+    assert d[2]["status"] == 0 and np.isfinite(d[0]).all() and d[2]["alpha"] > 0
+    # the short interval moves the state less than a full one
+    assert np.abs(d[0][1] - x0).max() < np.abs(a[0][1] - x0).max() + 1e-12
