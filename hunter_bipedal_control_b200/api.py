@@ -21,7 +21,7 @@ HB_MAX_EVENTS, HB_MAX_TARGETS, HB_MAX_SEGMENTS = 32, 16, 24
 
 EXPORTED_SYMBOLS = [
     "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_last_cuda_error", "hb_launch_count", "hb_stream", "hb_profile_enable", "hb_profile_read",
-    "hb_wbc_qp_batch_dev", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
+    "hb_wbc_qp_batch_dev", "hb_wbc_qp_rows_batch_dev", "hb_wbc_assemble_batch_dev", "hb_wbc_assemble_batch", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
     "hb_policy_eval_batch_dev", "hb_control_step_batch_dev", "hb_rbd_to_centroidal_batch_dev", "hb_reference_expand_batch_dev",
     "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references", "hb_gait_select", "hb_resident_cycle_batch_dev", "hb_resident_cycle_batch", "hb_resident_read_batch", "hb_plan_references_batch_dev",
     "hb_plan_references_gpu", "hb_resident_plan_cycle_batch", "hb_default_kf_params", "hb_kf_reset", "hb_estimator_update_batch_dev",
@@ -115,9 +115,22 @@ class GaitSelector:
 GAIT_IDS = {"stance": 0, "trot": 1, "standing_trot": 2, "flying_trot": 3}
 
 
+def _gait_ids(gait, B):
+    """Gait name (one for the batch) or any sequence / ndarray of names or ids (one per instance) -> int ids [B]."""
+    if isinstance(gait, str):
+        return [GAIT_IDS[gait]] * B
+    if np.ndim(gait) == 0:
+        return [int(gait)] * B
+    ids = [GAIT_IDS[g] if isinstance(g, str) else int(g) for g in list(gait)]
+    if len(ids) != B:
+        raise ValueError("gait: expected one name or %d per-instance entries, got %d" % (B, len(ids)))
+    return ids
+
+
 def make_plan_inputs(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event=None, time_to_target=None, joint_ik=True):
     """ctypes array of HbPlanInput for a batch (feet_pos may be None when the device computes it)."""
     x0 = _f64(x0); B = x0.shape[0]
+    gids = _gait_ids(gait, B)
     cmd_vel = np.broadcast_to(_f64(cmd_vel), (B, 4))
     feet_pos = np.zeros((B, 12)) if feet_pos is None else _f64(feet_pos).reshape(B, 12)
     t0 = np.broadcast_to(_f64(t0), (B,)); gait_start = np.broadcast_to(_f64(gait_start), (B,))
@@ -126,7 +139,7 @@ def make_plan_inputs(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_
         p = ins[i]
         p.t0 = t0[i]; p.horizon = horizon; p.time_to_target = horizon if time_to_target is None else time_to_target
         p.gait_start = gait_start[i]; p.prev_event = (min(t0[i], gait_start[i]) - 0.5) if prev_event is None else prev_event
-        p.gait = GAIT_IDS[gait[i]] if isinstance(gait, (list, tuple)) else GAIT_IDS[gait]
+        p.gait = gids[i]
         p.joint_ik = 1 if joint_ik else 0
         for j in range(22): p.x0[j] = x0[i, j]
         for j in range(4): p.cmd_vel[j] = cmd_vel[i, j]
@@ -137,19 +150,8 @@ def make_plan_inputs(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_
 def plan_references(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event=None, time_to_target=None, latest_stance=None, joint_ik=True):
     """Host-side reference planner (hb_plan_references): returns (ctypes array of HbReference, latest_stance[B,12])."""
     lib = load_library()
-    x0 = _f64(x0); B = x0.shape[0]
-    cmd_vel = np.broadcast_to(_f64(cmd_vel), (B, 4)); feet_pos = _f64(feet_pos).reshape(B, 12)
-    t0 = np.broadcast_to(_f64(t0), (B,)); gait_start = np.broadcast_to(_f64(gait_start), (B,))
-    ins = (HbPlanInput * B)()
-    for i in range(B):
-        p = ins[i]
-        p.t0 = t0[i]; p.horizon = horizon; p.time_to_target = horizon if time_to_target is None else time_to_target
-        p.gait_start = gait_start[i]; p.prev_event = (min(t0[i], gait_start[i]) - 0.5) if prev_event is None else prev_event
-        p.gait = GAIT_IDS[gait[i]] if isinstance(gait, (list, tuple)) else GAIT_IDS[gait]
-        p.joint_ik = 1 if joint_ik else 0
-        for j in range(22): p.x0[j] = x0[i, j]
-        for j in range(4): p.cmd_vel[j] = cmd_vel[i, j]
-        for j in range(12): p.feet_pos[j] = feet_pos[i, j]
+    ins = make_plan_inputs(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event, time_to_target, joint_ik)
+    B = len(ins)
     ls = np.zeros((B, 12)) if latest_stance is None else _f64(latest_stance).copy()
     refs = (HbReference * B)()
     _check(lib.hb_plan_references(B, ins, _ptr(ls), refs), "hb_plan_references")
@@ -264,6 +266,18 @@ class Context:
         sol = np.zeros((B, NWBC)); st = np.zeros(B, dtype=np.int32)
         _check(self._lib.hb_wbc_solve_batch(self._h, B, _ptr(x_des), _ptr(u_des), _ptr(rbd), _ptr(mode), _ptr(sm), _ptr(sol), _ptr(st)), "hb_wbc_solve_batch", self._h)
         return sol, st
+
+    def wbc_assemble(self, x_des, u_des, rbd, mode, stance_mode=None):
+        """WeightedWbc's QP in the layout handed to qpOASES: returns (H [B,38,38], g [B,38], A [B,60,38], lbA, ubA [B,60], m_rows [B])."""
+        x_des, u_des, rbd = map(_f64, (x_des, u_des, rbd))
+        B = x_des.shape[0]
+        mode = np.ascontiguousarray(mode, dtype=np.int32)
+        sm = None if stance_mode is None else np.ascontiguousarray(stance_mode, dtype=np.uint8)
+        H = np.zeros((B, NWBC, NWBC)); g = np.zeros((B, NWBC)); A = np.zeros((B, 60, NWBC)); lb = np.zeros((B, 60)); ub = np.zeros((B, 60))
+        m = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_wbc_assemble_batch(self._h, B, _ptr(x_des), _ptr(u_des), _ptr(rbd), _ptr(mode), _ptr(sm), _ptr(H), _ptr(g), _ptr(A), _ptr(lb),
+                                               _ptr(ub), _ptr(m)), "hb_wbc_assemble_batch", self._h)
+        return H, g, A, lb, ub, m
 
     def mpc_cold_start(self, x0, mode):
         x0 = _f64(x0); B = x0.shape[0]
@@ -382,11 +396,11 @@ class Context:
 
     def wbc_solve_dev(self, x_des, u_des, rbd, mode, stance_mode, sol, status=None):
         _check(self._lib.hb_wbc_solve_batch_dev(self._h, x_des.shape[0], _ptr(x_des), _ptr(u_des), _ptr(rbd), _ptr(mode), _ptr(stance_mode), _ptr(sol), _ptr(status)),
-               "hb_wbc_solve_batch_dev")
+               "hb_wbc_solve_batch_dev", self._h)
 
     def wbc_qp_dev(self, n, m, H, g, A, lbA, ubA, x, status=None, iters=None):
         _check(self._lib.hb_wbc_qp_batch_dev(self._h, g.shape[0], n, m, _ptr(H), _ptr(g), _ptr(A), _ptr(lbA), _ptr(ubA), _ptr(x), _ptr(status), _ptr(iters)),
-               "hb_wbc_qp_batch_dev")
+               "hb_wbc_qp_batch_dev", self._h)
 
     def resident_cycle_dev(self, cold_start, t_rel, t0, x0, refs_dev_ptr, rbd, info, sol, tau, status=None):
         _check(self._lib.hb_resident_cycle_batch_dev(self._h, x0.shape[0], 1 if cold_start else 0, C.c_double(t_rel), _ptr(t0), _ptr(x0), C.c_void_p(refs_dev_ptr),
@@ -447,10 +461,10 @@ class SqpMpc:
         mode = np.asarray(mode, dtype=np.int32)[None]
         if self._xt is None:
             self._xt, self._ut = self._ctx.mpc_cold_start(x0, mode)
-        self._xt, self._ut, info = self._ctx.mpc_solve(x0, np.asarray(x_ref)[None], np.asarray(swing)[None], mode, self._xt, self._ut)
-        self._mode = mode
-        if info["status"][0] != 0:
+        xt, ut, info = self._ctx.mpc_solve(x0, np.asarray(x_ref)[None], np.asarray(swing)[None], mode, self._xt, self._ut)
+        if info["status"][0] != 0:      # a failed iteration must not poison the next warm start: the previous solution stays
             raise HunterB200Error("[SqpMpc] numerical failure in the SQP iteration")   # the reference's MPC thread stops the controller (LeggedController.cpp:413-418)
+        self._xt, self._ut, self._mode = xt, ut, mode
         return info[0]
 
     def evaluatePolicy(self, t_rel):

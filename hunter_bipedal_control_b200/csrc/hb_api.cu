@@ -432,33 +432,37 @@ __global__ void reference_expand_kernel(int B, int N, double dt, const double* t
                                         int32_t* mode) {
   const int inst = blockIdx.x;
   const hb_reference& rf = refs[inst];
+  // counts are clamped to the capacities of hb_reference: a malformed struct cannot index out of bounds (the host-pointer entry
+  // points reject it with HB_EINVAL before it gets here; device-pointer callers own their data)
+  const int n_events = min(max(rf.n_events, 0), HB_MAX_EVENTS), n_targets = min(max(rf.n_targets, 1), HB_MAX_TARGETS);
   for (int k = threadIdx.x; k <= N; k += blockDim.x) {
     const double t = t0[inst] + k * dt;
     // mode in force on the interval starting at t (post-event mode when t coincides with an event)
     int idx = 0;
-    while (idx < rf.n_events && rf.event_times[idx] <= t + 1e-9) ++idx;
+    while (idx < n_events && rf.event_times[idx] <= t + 1e-9) ++idx;
     mode[(size_t)inst * (N + 1) + k] = rf.modes[idx];
     // target state: linear interpolation, clamped
     double* xr = x_ref + ((size_t)inst * (N + 1) + k) * NX;
-    if (rf.n_targets <= 1 || t <= rf.target_times[0]) { for (int i = 0; i < NX; ++i) xr[i] = rf.target_states[0][i]; }
-    else if (t >= rf.target_times[rf.n_targets - 1]) { for (int i = 0; i < NX; ++i) xr[i] = rf.target_states[rf.n_targets - 1][i]; }
+    if (n_targets <= 1 || t <= rf.target_times[0]) { for (int i = 0; i < NX; ++i) xr[i] = rf.target_states[0][i]; }
+    else if (t >= rf.target_times[n_targets - 1]) { for (int i = 0; i < NX; ++i) xr[i] = rf.target_states[n_targets - 1][i]; }
     else {
       int s = 0;
-      while (s + 2 < rf.n_targets && rf.target_times[s + 1] <= t) ++s;
-      const double al = (t - rf.target_times[s]) / (rf.target_times[s + 1] - rf.target_times[s]);
+      while (s + 2 < n_targets && rf.target_times[s + 1] <= t) ++s;
+      const double span = rf.target_times[s + 1] - rf.target_times[s];
+      const double al = span > 0.0 ? (t - rf.target_times[s]) / span : 0.0;
       for (int i = 0; i < NX; ++i) xr[i] = (1.0 - al) * rf.target_states[s][i] + al * rf.target_states[s + 1][i];
     }
     // swing references: cubic Hermite segments
     double* sw = swing + ((size_t)inst * (N + 1) + k) * 24;
     for (int c = 0; c < 4; ++c)
       for (int a = 0; a < 3; ++a) {
-        const int ns = rf.n_segments[c][a];
+        const int ns = min(max(rf.n_segments[c][a], 0), HB_MAX_SEGMENTS);
         double pos = 0.0, vel = 0.0;
         if (ns > 0) {
           int s = 0;
           while (s + 1 < ns && t >= rf.segments[c][a][s][1]) ++s;
           const double* sg = rf.segments[c][a][s];
-          const double T = sg[1] - sg[0], tn = (t - sg[0]) / T;
+          const double Tr = sg[1] - sg[0], T = Tr > 0.0 ? Tr : 1.0, tn = (t - sg[0]) / T;
           const double dp = sg[4] - sg[2], dvv = sg[5] - sg[3];
           const double c0 = sg[2], c1 = sg[3] * T, c2 = -(3.0 * sg[3] + dvv) * T + 3.0 * dp, c3 = (2.0 * sg[3] + dvv) * T - 2.0 * dp;
           pos = ((c3 * tn + c2) * tn + c1) * tn + c0;
@@ -480,8 +484,6 @@ __global__ void contact_positions_kernel(int B, const double* x, double* pos) {
   for (int i = 0; i < 12; ++i) pos[(size_t)inst * 12 + i] = o.cpos[i];
 }
 
-// Device planner (row N1), simple form: one thread per instance runs the same source as the host planner (csrc/hb_planner.h);
-// kept for HB_PLAN_COOP=0, the default is the cooperative kernel below.
 // plan_prepare_kernel unpacks t0 / x0 from the plan inputs and evaluates computeFootPos at x0 (the planner's current_feet input).
 __global__ void plan_prepare_kernel(int B, const hb_plan_input* in, double* t0, double* x0, double* feet) {
   const int inst = blockIdx.x * blockDim.x + threadIdx.x;
@@ -496,24 +498,7 @@ __global__ void plan_prepare_kernel(int B, const hb_plan_input* in, double* t0, 
   for (int i = 0; i < 12; ++i) feet[(size_t)inst * 12 + i] = o.cpos[i];
 }
 
-__global__ void __launch_bounds__(8) plan_references_kernel(int B, const hb_plan_input* in, const double* feet, double* latest_stance, hb_reference* out,
-                                                            int32_t* status, hbplan::PlanConsts pc) {
-  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
-  if (inst >= B) return;
-  hb_plan_input p = in[inst];
-  if (feet) for (int i = 0; i < 12; ++i) p.feet_pos[i] = feet[(size_t)inst * 12 + i];
-  hb_reference* o = out + inst;
-  const int rc = hbplan::plan_one(pc, p, latest_stance + (size_t)inst * 12, o, false);
-  if (rc != 0) {
-    // a safe, empty reference (stance, target = current pose) so that the rest of the cycle stays well defined; status reports the error
-    o->n_events = 0; o->modes[0] = 3; o->n_targets = 1; o->target_times[0] = p.t0;
-    for (int i = 0; i < 22; ++i) o->target_states[0][i] = (i < 6) ? 0.0 : p.x0[i];
-    for (int c = 0; c < 4; ++c) for (int a = 0; a < 3; ++a) o->n_segments[c][a] = 0;
-  }
-  if (status) status[inst] = rc;
-}
-
-// Cooperative form of the device planner: four threads per instance (eight instances per 32-thread block). Thread r plans foot r
+// Device planner (row N1): the same source as the host planner (csrc/hb_planner.h), four threads per instance (eight instances per 32-thread block). Thread r plans foot r
 // (the feet are independent), then threads 0 and 1 run the IK of the left / right leg on the resampled target kept in shared
 // memory, then thread 0 writes the schedule and the targets. Same functions as the host planner, so the plan is the same.
 __global__ void __launch_bounds__(32) plan_references_coop_kernel(int B, const hb_plan_input* in, const double* feet, double* latest_stance,
@@ -566,20 +551,48 @@ __global__ void __launch_bounds__(32) plan_references_coop_kernel(int B, const h
   }
 }
 
-// parity probe: flow map value, Jacobians and contact kinematics from the warp-cooperative linearisation
+// parity probe of the SHIPPING linearisation (lin_half of K0): flow map value, the full Jacobian tiles rebuilt from the compact
+// record (rows 3..11 of df/dx, the force / joint-velocity blocks of df/du) and the contact kinematics with their Jacobians.
+struct ProbeShared { LinHalf h[2]; ChainModel cm; double rec[LIN_STRIDE]; double dummy[LIN_STRIDE]; };
 __global__ void __launch_bounds__(32) probe_flow_map_kernel(int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  MpcShared& sh = *reinterpret_cast<MpcShared*>(smem_raw);
-  const int inst = blockIdx.x, lane = threadIdx.x;
-  if (lane < NX) { sh.x[lane] = x[(size_t)inst * NX + lane]; sh.u[lane] = u[(size_t)inst * NU + lane]; }
+  ProbeShared& ps = *reinterpret_cast<ProbeShared*>(smem_raw);
+  const int inst = blockIdx.x, lane = threadIdx.x, half = lane >> 4, hl = lane & 15;
+  chain_model_load(ps.cm, threadIdx.x, blockDim.x);
+  LinHalf& sh = ps.h[half];
+  for (int i = hl; i < NX; i += 16) { sh.x[i] = x[(size_t)inst * NX + i]; sh.u[i] = u[(size_t)inst * NU + i]; }
   __syncwarp();
-  flow_lin_warp(sh, sh.x, sh.f1, sh.A1, sh.B1, true);
-  if (lane < NX) f[(size_t)inst * NX + lane] = sh.f1[lane];
-  for (int idx = lane; idx < TS; idx += 32) { A[(size_t)inst * TS + idx] = sh.A1[idx]; Bm[(size_t)inst * TS + idx] = sh.B1[idx]; }
+  // both halves linearise the same node; only half 0 writes the record (half 1 runs with act = false into a dummy record)
+  double* rec = half == 0 ? ps.rec : ps.dummy;
+  lin_half(sh, ps.cm, sh.x, hl, half == 0, rec + LIN_F1, rec + LIN_A1, rec + LIN_BF1, rec + LIN_BV1, true, rec);
+  __syncwarp();
+  const double im = 1.0 / c_model.total_mass;
+  if (lane < NX) f[(size_t)inst * NX + lane] = ps.rec[LIN_F1 + lane];
+  for (int idx = lane; idx < TS; idx += 32) {
+    const int i = idx / NX, j = idx - i * NX;
+    double a = 0.0, b = 0.0;
+    if (i >= 3 && i < 12) a = ps.rec[LIN_A1 + (i - 3) * NX + j];
+    if (j < 12) {
+      if (i < 3) b = (j % 3 == i) ? im : 0.0;
+      else if (i < 6) b = ps.rec[LIN_BF1 + (i - 3) * 12 + j];
+    } else {
+      if (i >= 6 && i < 12) b = ps.rec[LIN_BV1 + (i - 6) * NJ + j - 12];
+      else if (i >= 12) b = (i == j) ? 1.0 : 0.0;
+    }
+    A[(size_t)inst * TS + idx] = a; Bm[(size_t)inst * TS + idx] = b;
+  }
   if (ee) {
     double* o = ee + (size_t)inst * (24 + 3 * 12 * NX);
-    if (lane < 12) { o[lane] = sh.epos[lane]; o[12 + lane] = sh.evel[lane]; }
-    for (int idx = lane; idx < 3 * 12 * NX; idx += 32) o[24 + idx] = sh.EJ[idx];
+    if (lane < 12) { o[lane] = ps.rec[LIN_EPOS + lane]; o[12 + lane] = ps.rec[LIN_EVEL + lane]; }
+    for (int idx = lane; idx < 12 * NX; idx += 32) {
+      const int r = idx / NX, j = idx - r * NX;
+      double dp = 0.0;
+      if (j >= 6 && j < 9) dp = (j - 6 == r % 3) ? 1.0 : 0.0;
+      else if (j >= 9) dp = ps.rec[LIN_DPQ + r * NDIR + j - 9];
+      o[24 + idx] = dp;
+      o[24 + 12 * NX + idx] = ps.rec[LIN_DVX + idx];
+      o[24 + 24 * NX + idx] = (j >= 12) ? ps.rec[LIN_DVV + r * NJ + j - 12] : 0.0;
+    }
   }
 }
 
@@ -594,14 +607,12 @@ struct hb_ctx {
   int base;                               // instance offset into the per-instance scratch (chunked calls)
   int64_t launches;
   // MPC scratch
-  double *gains, *dxt, *dut, *perf;
-  double *lin, *proj, *rk;   // version-2 pipeline records
-  int wbc_generic;           // HB_WBC_GENERIC=1: assemble the reference-layout QP and run the generic solver (A/B comparison)
-  int sqp_version;           // 2 (default) or 1 (HB_SQP_VERSION=1: fused backward sweep, kept for A/B comparison)
+  double *dxt, *dut, *perf;
+  double *lin, *proj, *rk;   // node records of the SQP pipeline (K0 -> K1 -> K2/K3)
   int32_t* flags;
   // WBC scratch
-  double *qH, *qg, *qA, *qlb, *qub, *xdes, *udes, *wsol;
-  int32_t *qm, *wstatus, *witers, *wmode;
+  double *xdes, *udes, *wsol;
+  int32_t *wstatus, *witers, *wmode;
   // staging for host-pointer calls
   double *s_x0, *s_xref, *s_swing, *s_xt, *s_ut, *s_rbd, *s_xd, *s_ud, *s_sol, *s_tau, *s_t0, *s_misc;
   double *res_xt = nullptr, *res_ut = nullptr, *res_t0 = nullptr;   // resident primal solution (hb_resident_cycle_batch)
@@ -648,6 +659,25 @@ inline void prof_end(hb_ctx* ctx) {
 
 int set_device(hb_ctx* ctx) { return cudaSetDevice(ctx->device) == cudaSuccess ? HB_OK : HB_ECUDA; }
 
+// Caller-supplied hb_reference structs (host-pointer entry points): counts within the capacities, monotone times, positive segment
+// lengths, modes in 0..3. The device expansion indexes with these counts, so a malformed struct is rejected here with HB_EINVAL.
+bool references_valid(int B, const hb_reference* refs) {
+  for (int i = 0; i < B; ++i) {
+    const hb_reference& r = refs[i];
+    if (r.n_events < 0 || r.n_events > HB_MAX_EVENTS || r.n_targets < 1 || r.n_targets > HB_MAX_TARGETS) return false;
+    for (int k = 0; k <= r.n_events; ++k) if (r.modes[k] < 0 || r.modes[k] > 3) return false;
+    for (int k = 0; k < r.n_events; ++k) if (!(r.event_times[k] == r.event_times[k]) || (k > 0 && r.event_times[k] < r.event_times[k - 1])) return false;
+    for (int k = 0; k < r.n_targets; ++k) if (!(r.target_times[k] == r.target_times[k]) || (k > 0 && !(r.target_times[k] > r.target_times[k - 1]))) return false;
+    for (int c = 0; c < 4; ++c)
+      for (int a = 0; a < 3; ++a) {
+        const int ns = r.n_segments[c][a];
+        if (ns < 0 || ns > HB_MAX_SEGMENTS) return false;
+        for (int q = 0; q < ns; ++q) if (!(r.segments[c][a][q][1] > r.segments[c][a][q][0])) return false;
+      }
+  }
+  return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -676,16 +706,18 @@ const char* hb_strerror(int code) {
 }
 
 int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
-  if (!cfg || !out || cfg->horizon_N < 1 || cfg->horizon_N > 4096 || cfg->max_batch < 1 || !(cfg->dt > 0.0)) return HB_EINVAL;
+  // horizon cap: the warm shift stages one instance's previous trajectories in shared memory ((2N+1) x 22 doubles <= 227 KB)
+  if (!cfg || !out || cfg->horizon_N < 1 || cfg->horizon_N > HB_MAX_HORIZON || cfg->max_batch < 1 || !(cfg->dt > 0.0)) return HB_EINVAL;
   hb_ctx* ctx = new (std::nothrow) hb_ctx();
   if (!ctx) return HB_ENOMEM;
   memset(ctx, 0, sizeof(*ctx));
   ctx->cfg = *cfg;
   ctx->device = device;
-  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return HB_ECUDA; }
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HB_ECUDA; }
+  // every failure below goes through hb_destroy (streams and partial allocations are released there)
+  if (cudaSetDevice(device) != cudaSuccess) { hb_destroy(ctx); return HB_ECUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->stream = nullptr; hb_destroy(ctx); return HB_ECUDA; }
   ctx->stream_main = ctx->stream;
-  if (cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return HB_ECUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) != cudaSuccess) { ctx->stream_aux = nullptr; hb_destroy(ctx); return HB_ECUDA; }
   // model constants
   Model* m = new Model();
   memset(m, 0, sizeof(Model));
@@ -717,18 +749,9 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   if (e != cudaSuccess) { ctx->last_cuda = (int)e; hb_destroy(ctx); return HB_ECUDA; }
   const size_t B = cfg->max_batch, N = cfg->horizon_N;
   bool ok = true;
-  {
-    const char* v = getenv("HB_SQP_VERSION");
-    ctx->sqp_version = (v && v[0] == '1') ? 1 : 2;
-    const char* g = getenv("HB_WBC_GENERIC");
-    ctx->wbc_generic = (g && g[0] == '1') ? 1 : 0;
-  }
-  if (ctx->sqp_version == 1) ok = ok && dalloc(&ctx->gains, B * N * GAIN_STRIDE) == cudaSuccess;
-  else ok = ok && dalloc(&ctx->lin, B * N * LIN_STRIDE) == cudaSuccess && dalloc(&ctx->proj, B * N * PJ_STRIDE) == cudaSuccess && dalloc(&ctx->rk, B * N * RK_STRIDE) == cudaSuccess;
+  ok = ok && dalloc(&ctx->lin, B * N * LIN_STRIDE) == cudaSuccess && dalloc(&ctx->proj, B * N * PJ_STRIDE) == cudaSuccess && dalloc(&ctx->rk, B * N * RK_STRIDE) == cudaSuccess;
   ok = ok && dalloc(&ctx->dxt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->dut, B * N * NU) == cudaSuccess;
   ok = ok && dalloc(&ctx->perf, B * 4) == cudaSuccess && dalloc(&ctx->flags, B) == cudaSuccess;
-  ok = ok && dalloc(&ctx->qH, B * QP_STRIDE_H) == cudaSuccess && dalloc(&ctx->qg, B * NWBC) == cudaSuccess && dalloc(&ctx->qA, B * QP_STRIDE_A) == cudaSuccess;
-  ok = ok && dalloc(&ctx->qlb, B * WBC_ROWS) == cudaSuccess && dalloc(&ctx->qub, B * WBC_ROWS) == cudaSuccess && dalloc(&ctx->qm, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->xdes, B * NX) == cudaSuccess && dalloc(&ctx->udes, B * NU) == cudaSuccess && dalloc(&ctx->wsol, B * NWBC) == cudaSuccess;
   ok = ok && dalloc(&ctx->wstatus, B) == cudaSuccess && dalloc(&ctx->witers, B) == cudaSuccess && dalloc(&ctx->wmode, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_x0, B * NX) == cudaSuccess && dalloc(&ctx->s_xref, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_swing, B * (N + 1) * 24) == cudaSuccess;
@@ -741,15 +764,19 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   ok = ok && dalloc(&ctx->s_mode, B * (N + 1)) == cudaSuccess && dalloc(&ctx->s_imode, B) == cudaSuccess && dalloc(&ctx->s_status, B) == cudaSuccess && dalloc(&ctx->s_iters, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_stance, B) == cudaSuccess && dalloc(&ctx->s_info, B) == cudaSuccess && dalloc(&ctx->s_refs, B) == cudaSuccess;
   if (!ok) { hb_destroy(ctx); return HB_ENOMEM; }
-  cudaFuncSetAttribute(mpc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MpcShared));
-  cudaFuncSetAttribute(probe_flow_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MpcShared));
-  cudaFuncSetAttribute(mpc_forward_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LsShared));
-  cudaFuncSetAttribute(qp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(wbc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wbc_fused_doubles() * sizeof(double)));
-  cudaFuncSetAttribute(lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(LinHalf) + sizeof(ChainModel)));
-  cudaFuncSetAttribute(lq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LqShared));
-  cudaFuncSetAttribute(riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RicShared));
-  cudaFuncSetAttribute(forward_linesearch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fw2Shared));
+  {
+    cudaError_t fe = cudaSuccess;
+    auto attr = [&](const void* fn, size_t bytes) { if (fe == cudaSuccess) fe = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); };
+    attr((const void*)probe_flow_map_kernel, sizeof(ProbeShared));
+    attr((const void*)qp_batch_kernel, 200 * 1024);
+    attr((const void*)wbc_fused_kernel, wbc_fused_doubles() * sizeof(double));
+    attr((const void*)lin_kernel, 4 * sizeof(LinHalf) + sizeof(ChainModel));
+    attr((const void*)lq_kernel, sizeof(LqShared));
+    attr((const void*)riccati_kernel, sizeof(RicShared));
+    attr((const void*)forward_linesearch2_kernel, sizeof(Fw2Shared));
+    attr((const void*)warm_shift_kernel, sizeof(double) * ((N + 1) * NX + N * NU));
+    if (fe != cudaSuccess) { ctx->last_cuda = (int)fe; hb_destroy(ctx); return HB_ECUDA; }
+  }
   *out = ctx;
   return HB_OK;
 }
@@ -757,7 +784,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
 int hb_destroy(hb_ctx* ctx) {
   if (!ctx) return HB_EINVAL;
   cudaSetDevice(ctx->device);
-  void* ptrs[] = {ctx->lin, ctx->proj, ctx->rk, ctx->gains, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->qH, ctx->qg, ctx->qA, ctx->qlb, ctx->qub, ctx->qm, ctx->xdes, ctx->udes,
+  void* ptrs[] = {ctx->lin, ctx->proj, ctx->rk, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->xdes, ctx->udes,
                   ctx->wsol, ctx->wstatus, ctx->witers, ctx->wmode, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_xt, ctx->s_ut, ctx->s_rbd, ctx->s_xd,
                   ctx->s_ud, ctx->s_sol, ctx->s_tau, ctx->s_t0, ctx->s_misc, ctx->s_mode, ctx->s_imode, ctx->s_status, ctx->s_iters, ctx->s_stance,
                   ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf, ctx->res_sol};
@@ -765,6 +792,7 @@ int hb_destroy(hb_ctx* ctx) {
   if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
   if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
   if (ctx->stream_main) cudaStreamDestroy(ctx->stream_main);
+  else if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return HB_OK;
 }
@@ -840,25 +868,36 @@ int hb_wbc_solve_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double
   if (B == 0) return HB_OK;
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (set_device(ctx)) return HB_ECUDA;
-  if (!ctx->wbc_generic) {
-    const size_t per_warp = wbc_fused_doubles() * sizeof(double);
-    prof_begin(ctx, K_QP);
-    wbc_fused_kernel<<<B, 32, per_warp, ctx->stream>>>(B, x_des, u_des, rbd, mode, stance_mode, ctx->cfg.wbc_rho, ctx->cfg.qp_max_iter, sol,
-                                                        status ? status : ctx->wstatus + ctx->base, ctx->witers + ctx->base);
-    prof_end(ctx);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return HB_OK;
-  }
-  const int wpb = 4;
-  prof_begin(ctx, K_WBC_ASSEMBLE);
-  wbc_assemble_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, sizeof(WbcShared) * wpb, ctx->stream>>>(B, x_des, u_des, rbd, mode, stance_mode, ctx->qH, ctx->qg,
-                                                                                               ctx->qA, ctx->qlb, ctx->qub, ctx->qm);
+  const size_t per_warp = wbc_fused_doubles() * sizeof(double);
+  prof_begin(ctx, K_QP);
+  wbc_fused_kernel<<<B, 32, per_warp, ctx->stream>>>(B, x_des, u_des, rbd, mode, stance_mode, ctx->cfg.wbc_rho, ctx->cfg.qp_max_iter, sol,
+                                                      status ? status : ctx->wstatus + ctx->base, ctx->witers + ctx->base);
   prof_end(ctx);
   ctx->launches++;
   CK(cudaGetLastError());
-  return launch_qp(ctx, B, NWBC, WBC_ROWS, ctx->qH, ctx->qg, ctx->qA, ctx->qlb, ctx->qub, QP_STRIDE_H, QP_STRIDE_A, WBC_ROWS, ctx->qm, sol,
-                   status ? status : ctx->wstatus, ctx->witers);
+  return HB_OK;
+}
+
+int hb_wbc_assemble_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                              const uint8_t* stance_mode, double* H, double* g, double* A, double* lbA, double* ubA, int32_t* m_rows) {
+  if (!ctx || B < 0 || !x_des || !u_des || !rbd || !mode || !H || !g || !A || !lbA || !ubA || !m_rows) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  const int wpb = 4;
+  prof_begin(ctx, K_WBC_ASSEMBLE);
+  wbc_assemble_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, sizeof(WbcShared) * wpb, ctx->stream>>>(B, x_des, u_des, rbd, mode, stance_mode, H, g, A, lbA, ubA, m_rows);
+  prof_end(ctx);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_wbc_qp_rows_batch_dev(hb_ctx* ctx, int B, int n, int m_alloc, const int32_t* m_rows, const double* H, const double* g, const double* A,
+                             const double* lbA, const double* ubA, double* x, int32_t* status, int32_t* iters) {
+  if (!ctx || B < 0 || !m_rows || !H || !g || !A || !lbA || !ubA || !x) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  return launch_qp(ctx, B, n, m_alloc, H, g, A, lbA, ubA, (size_t)n * n, (size_t)m_alloc * n, (size_t)m_alloc, m_rows, x, status, iters);
 }
 
 int hb_mpc_cold_start_batch_dev(hb_ctx* ctx, int B, const double* x0, const int32_t* mode, double* x_traj, double* u_traj) {
@@ -877,22 +916,6 @@ int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x
   if (B == 0) return HB_OK;
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (set_device(ctx)) return HB_ECUDA;
-  if (ctx->sqp_version == 1) {
-    MpcArgs a;
-    a.B = B; a.N = ctx->cfg.horizon_N; a.dt = ctx->cfg.dt; a.x_ref = x_ref; a.swing = swing_ref; a.mode = mode; a.xt = x_traj; a.ut = u_traj;
-    a.gains = ctx->gains; a.dxt = ctx->dxt; a.dut = ctx->dut; a.perf = ctx->perf; a.flags = ctx->flags; a.x0 = x0;
-    prof_begin(ctx, K_BACKWARD);
-    mpc_backward_kernel<<<B, 32, sizeof(MpcShared), ctx->stream>>>(a);
-    prof_end(ctx);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    prof_begin(ctx, K_FORWARD_LS);
-    mpc_forward_linesearch_kernel<<<B, 32, sizeof(LsShared), ctx->stream>>>(a, ctx->cfg.line_search_max_trials, info);
-    prof_end(ctx);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return HB_OK;
-  }
   SqpArgs a;
   a.B = B; a.N = ctx->cfg.horizon_N; a.dt = ctx->cfg.dt; a.x_ref = x_ref; a.swing = swing_ref; a.mode = mode; a.xt = x_traj; a.ut = u_traj;
   {
@@ -995,8 +1018,7 @@ int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel
     if (rc) return rc;
     set_times_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, t0, tres);
   } else {
-    const size_t smem = sizeof(double) * ((N + 1) * NX + N * NU);
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(warm_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = sizeof(double) * ((N + 1) * NX + N * NU);     // opted in at hb_create
     warm_shift_kernel<<<B, 128, smem, ctx->stream>>>(B, (int)N, ctx->cfg.dt, t0, tres, x0, mode, xt, ut);
   }
   ctx->launches++;
@@ -1020,9 +1042,7 @@ int hb_plan_references_batch_dev(hb_ctx* ctx, int B, const hb_plan_input* in, co
   if (B == 0) return HB_OK;
   if (set_device(ctx)) return HB_ECUDA;
   static const hbplan::PlanConsts pc = hbplan::make_consts();
-  static const bool coop = [] { const char* e = getenv("HB_PLAN_COOP"); return !(e && e[0] == '0'); }();   // HB_PLAN_COOP=0: one thread per instance
-  if (coop) plan_references_coop_kernel<<<(B + 7) / 8, 32, 0, ctx->stream>>>(B, in, feet, latest_stance, out, status, pc);
-  else plan_references_kernel<<<(B + 7) / 8, 8, 0, ctx->stream>>>(B, in, feet, latest_stance, out, status, pc);
+  plan_references_coop_kernel<<<(B + 7) / 8, 32, 0, ctx->stream>>>(B, in, feet, latest_stance, out, status, pc);
   ctx->launches++;
   CK(cudaGetLastError());
   return HB_OK;
@@ -1113,7 +1133,7 @@ int hb_probe_flow_map_dev(hb_ctx* ctx, int B, const double* x, const double* u, 
   if (!ctx || B < 0 || !x || !u || !f || !A || !Bm) return HB_EINVAL;
   if (B == 0) return HB_OK;
   if (set_device(ctx)) return HB_ECUDA;
-  probe_flow_map_kernel<<<B, 32, sizeof(MpcShared), ctx->stream>>>(B, x, u, f, A, Bm, ee);
+  probe_flow_map_kernel<<<B, 32, sizeof(ProbeShared), ctx->stream>>>(B, x, u, f, A, Bm, ee);
   ctx->launches++;
   CK(cudaGetLastError());
   return HB_OK;
@@ -1123,6 +1143,16 @@ int hb_probe_flow_map_dev(hb_ctx* ctx, int B, const double* x, const double* u, 
 #define H2D(dst, src, n) CK(cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, ctx->stream))
 #define D2H(dst, src, n) CK(cudaMemcpyAsync(dst, src, (n), cudaMemcpyDeviceToHost, ctx->stream))
 
+static int qp_staging_reserve(hb_ctx* ctx, size_t need) {
+  if (need > ctx->s_qp_cap) {
+    if (ctx->s_qpH) cudaFree(ctx->s_qpH);
+    ctx->s_qpH = nullptr; ctx->s_qp_cap = 0;
+    CK(dalloc(&ctx->s_qpH, need));
+    ctx->s_qp_cap = need;
+  }
+  return HB_OK;
+}
+
 int hb_wbc_qp_batch(hb_ctx* ctx, int B, int n, int m, const double* H, const double* g, const double* A, const double* lbA, const double* ubA,
                     double* x, int32_t* status, int32_t* iters) {
   if (!ctx || B < 0 || !H || !g || !A || !lbA || !ubA || !x) return HB_EINVAL;
@@ -1130,12 +1160,7 @@ int hb_wbc_qp_batch(hb_ctx* ctx, int B, int n, int m, const double* H, const dou
   if (n < 1 || n > QP_MAX_N || m < 0 || m > QP_MAX_M) return HB_EINVAL;
   if (set_device(ctx)) return HB_ECUDA;
   const size_t need = (size_t)B * ((size_t)n * n + (size_t)m * n + 3 * (size_t)n + 2 * (size_t)m + 2);
-  if (need > ctx->s_qp_cap) {
-    if (ctx->s_qpH) cudaFree(ctx->s_qpH);
-    ctx->s_qpH = nullptr; ctx->s_qp_cap = 0;
-    CK(dalloc(&ctx->s_qpH, need));
-    ctx->s_qp_cap = need;
-  }
+  { const int rc0 = qp_staging_reserve(ctx, need); if (rc0) return rc0; }
   double* dH = ctx->s_qpH; double* dA = dH + (size_t)B * n * n; double* dg = dA + (size_t)B * m * n; double* dlb = dg + (size_t)B * n;
   double* dub = dlb + (size_t)B * m; double* dx = dub + (size_t)B * m; int32_t* dst = reinterpret_cast<int32_t*>(dx + (size_t)B * n); int32_t* dit = dst + B;
   H2D(dH, H, sizeof(double) * B * n * n); H2D(dA, A, sizeof(double) * B * m * n); H2D(dg, g, sizeof(double) * B * n);
@@ -1145,6 +1170,27 @@ int hb_wbc_qp_batch(hb_ctx* ctx, int B, int n, int m, const double* H, const dou
   D2H(x, dx, sizeof(double) * B * n);
   if (status) D2H(status, dst, sizeof(int32_t) * B);
   if (iters) D2H(iters, dit, sizeof(int32_t) * B);
+  return hb_sync(ctx);
+}
+
+int hb_wbc_assemble_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                          const uint8_t* stance_mode, double* H, double* g, double* A, double* lbA, double* ubA, int32_t* m_rows) {
+  if (!ctx || B < 0 || !x_des || !u_des || !rbd || !mode || !H || !g || !A || !lbA || !ubA || !m_rows) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t per = (size_t)QP_STRIDE_H + QP_STRIDE_A + NWBC + 2 * WBC_ROWS + 1;
+  int rc = qp_staging_reserve(ctx, (size_t)B * per);
+  if (rc) return rc;
+  double* dH = ctx->s_qpH; double* dA = dH + (size_t)B * QP_STRIDE_H; double* dg = dA + (size_t)B * QP_STRIDE_A; double* dlb = dg + (size_t)B * NWBC;
+  double* dub = dlb + (size_t)B * WBC_ROWS; int32_t* dm = reinterpret_cast<int32_t*>(dub + (size_t)B * WBC_ROWS);
+  H2D(ctx->s_xd, x_des, sizeof(double) * B * NX); H2D(ctx->s_ud, u_des, sizeof(double) * B * NU); H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32);
+  H2D(ctx->s_imode, mode, sizeof(int32_t) * B);
+  if (stance_mode) H2D(ctx->s_stance, stance_mode, B);
+  rc = hb_wbc_assemble_batch_dev(ctx, B, ctx->s_xd, ctx->s_ud, ctx->s_rbd, ctx->s_imode, stance_mode ? ctx->s_stance : nullptr, dH, dg, dA, dlb, dub, dm);
+  if (rc) return rc;
+  D2H(H, dH, sizeof(double) * B * QP_STRIDE_H); D2H(A, dA, sizeof(double) * B * QP_STRIDE_A); D2H(g, dg, sizeof(double) * B * NWBC);
+  D2H(lbA, dlb, sizeof(double) * B * WBC_ROWS); D2H(ubA, dub, sizeof(double) * B * WBC_ROWS); D2H(m_rows, dm, sizeof(int32_t) * B);
   return hb_sync(ctx);
 }
 
@@ -1203,7 +1249,7 @@ int hb_control_step_batch(hb_ctx* ctx, int B, double t_rel, const double* x0, co
   if (set_device(ctx)) return HB_ECUDA;
   const size_t N = ctx->cfg.horizon_N;
   // Two half-batches on two streams: the copies of one half overlap the kernels of the other (pinned host memory assumed).
-  const int nchunk = (B >= 256 && ctx->sqp_version == 2) ? 2 : 1;
+  const int nchunk = (B >= 256) ? 2 : 1;
   int rc = HB_OK;
   for (int c = 0; c < nchunk && rc == HB_OK; ++c) {
     const size_t lo = (size_t)B * c / nchunk, hi = (size_t)B * (c + 1) / nchunk, n = hi - lo;
@@ -1246,10 +1292,10 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
   if (B == 0) return HB_OK;
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (!cold_start && ctx->res_valid < B) return HB_EINVAL;
+  if (!references_valid(B, refs)) return HB_EINVAL;
   if (set_device(ctx)) return HB_ECUDA;
   // Two half-batches on two streams, as in hb_control_step_batch; only the small per-instance inputs and results cross PCIe.
-  int nchunk = (B >= 256 && ctx->sqp_version == 2) ? 2 : 1;
-  if (const char* e = getenv("HB_E2E_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= 8 && B >= 64 * v && ctx->sqp_version == 2) nchunk = v; }
+  const int nchunk = (B >= 256) ? 2 : 1;
   int rc = HB_OK;
   for (int c = 0; c < nchunk && rc == HB_OK; ++c) {
     const size_t lo = (size_t)B * c / nchunk, hi = (size_t)B * (c + 1) / nchunk, n = hi - lo;
@@ -1302,7 +1348,7 @@ int hb_resident_plan_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_re
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (!cold_start && ctx->res_valid < B) return HB_EINVAL;
   if (set_device(ctx)) return HB_ECUDA;
-  const int nchunk = (B >= 256 && ctx->sqp_version == 2) ? 2 : 1;
+  const int nchunk = (B >= 256) ? 2 : 1;
   int rc = HB_OK;
   for (int c = 0; c < nchunk && rc == HB_OK; ++c) {
     const size_t lo = (size_t)B * c / nchunk, hi = (size_t)B * (c + 1) / nchunk, n = hi - lo;
@@ -1407,6 +1453,7 @@ int hb_reference_expand_batch(hb_ctx* ctx, int B, const double* t0, const hb_ref
   if (!ctx || B < 0 || !t0 || !refs || !x_ref || !swing_ref || !mode) return HB_EINVAL;
   if (B == 0) return HB_OK;
   if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (!references_valid(B, refs)) return HB_EINVAL;
   if (set_device(ctx)) return HB_ECUDA;
   const size_t N = ctx->cfg.horizon_N;
   H2D(ctx->s_t0, t0, sizeof(double) * B); H2D(ctx->s_refs, refs, sizeof(hb_reference) * B);

@@ -62,6 +62,7 @@ typedef struct {
 #define HB_MAX_EVENTS 32
 #define HB_MAX_TARGETS 16
 #define HB_MAX_SEGMENTS 24
+#define HB_MAX_HORIZON 512   /* hb_create rejects longer horizons (shared-memory staging of one instance's trajectories) */
 typedef struct {
   int32_t n_events;                       /* mode schedule: modes[i] holds on (event_times[i-1], event_times[i]] */
   double event_times[HB_MAX_EVENTS];
@@ -145,6 +146,16 @@ int hb_wbc_qp_batch_dev(hb_ctx* ctx, int B, int n, int m, const double* H, const
                         const double* ubA, double* x, int32_t* status, int32_t* iters);
 int hb_wbc_solve_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
                            const uint8_t* stance_mode, double* sol, int32_t* status);
+/* WbcBase::formulate*Task + WeightedWbc::formulateConstraints / formulateWeightedTasks (legged_wbc/src/WbcBase.cpp:138-338,
+ * WeightedWbc.cpp:68-94) in the layout WeightedWbc::update hands to qpOASES (WeightedWbc.cpp:24-42): H = A_w' A_w (38 x 38), g = -A_w' b_w,
+ * A (60 rows allocated, m_rows[i] used, row-major 60 x 38), lbA / ubA (60, -1e20 = qpOASES -INFTY). Feeds the raw QP sweep
+ * (BASELINE configs[4]) and the assembly parity test; the product path (hb_wbc_solve_batch) never materialises these matrices. */
+int hb_wbc_assemble_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                              const uint8_t* stance_mode /*nullable*/, double* H, double* g, double* A, double* lbA, double* ubA,
+                              int32_t* m_rows);
+/* hb_wbc_qp_batch_dev with a per-problem row count: A / lbA / ubA are allocated with m_alloc rows, problem i uses its first m_rows[i] */
+int hb_wbc_qp_rows_batch_dev(hb_ctx* ctx, int B, int n, int m_alloc, const int32_t* m_rows, const double* H, const double* g,
+                             const double* A, const double* lbA, const double* ubA, double* x, int32_t* status, int32_t* iters);
 int hb_mpc_cold_start_batch_dev(hb_ctx* ctx, int B, const double* x0, const int32_t* mode, double* x_traj, double* u_traj);
 int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
                            double* x_traj, double* u_traj, hb_solve_info* info);
@@ -187,7 +198,8 @@ int hb_reference_expand_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb
 /* world positions of the four contact frames at the configuration of x (InverseKinematics::computeFootPos,
  * legged_interface/src/foot_planner/InverseKinematics.cpp:253-267) */
 int hb_contact_positions_batch_dev(hb_ctx* ctx, int B, const double* x, double* pos /*B x 12*/);
-/* probes used by the parity tests: rigid-body quantities and the node LQ model computed by the device code */
+/* probe used by the parity tests: the shipping node linearisation (lin_half of K0) expanded to full tiles: f (22), A = df/dx and
+ * Bm = df/du (22 x 22), ee = [pos(12), vel(12), dpos/dx (12 x 22), dvel/dx (12 x 22), dvel/du (12 x 22)] */
 int hb_probe_flow_map_dev(hb_ctx* ctx, int B, const double* x, const double* u, double* f, double* A, double* Bm, double* ee);
 
 /* ---- host-pointer (synchronous) entry points: H2D copy, device call, D2H copy ---- */
@@ -195,6 +207,8 @@ int hb_wbc_qp_batch(hb_ctx* ctx, int B, int n, int m, const double* H, const dou
                     const double* ubA, double* x, int32_t* status, int32_t* iters);
 int hb_wbc_solve_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
                        const uint8_t* stance_mode, double* sol, int32_t* status);
+int hb_wbc_assemble_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                          const uint8_t* stance_mode /*nullable*/, double* H, double* g, double* A, double* lbA, double* ubA, int32_t* m_rows);
 int hb_mpc_cold_start_batch(hb_ctx* ctx, int B, const double* x0, const int32_t* mode, double* x_traj, double* u_traj);
 int hb_mpc_solve_batch(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
                        double* x_traj, double* u_traj, hb_solve_info* info);
@@ -230,7 +244,8 @@ int hb_contact_positions_batch(hb_ctx* ctx, int B, const double* x, double* pos 
  * (legged_controllers/src/TargetTrajectoriesPublisher.cpp:102-130) and calculateJointRef + InverseKinematics::computeIK
  * (src/SwitchedModelReferenceManager.cpp:251-300, src/foot_planner/InverseKinematics.cpp:20-231). latest_stance (B x 12) is the planner's state, in/out.
  * Returns 0, or -1 on misuse, or -5 when a schedule does not define the take-off / touch-down of a swing phase (the reference
- * throws there, SwingTrajectoryPlanner.cpp:421-458) or exceeds the capacity of hb_reference. */
+ * throws there, SwingTrajectoryPlanner.cpp:421-458) or exceeds the capacity of hb_reference.
+ * Instances are spread over std::thread::hardware_concurrency() host threads (environment variable HB_PLAN_THREADS overrides the count). */
 int hb_plan_references(int B, const hb_plan_input* in, double* latest_stance, hb_reference* out);
 /* speed-based gait selection (calculateVelAbs + walkGait / trotGait, src/SwitchedModelReferenceManager.cpp:185-249): updates the
  * 50-sample moving average of 0.5*(command + target) speed of every instance and applies the thresholds stance <= 0.02 < (no change)

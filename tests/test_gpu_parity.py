@@ -83,6 +83,21 @@ def test_wbc_solve_vs_oracle(gpu_ctx, oracle):
         assert rel(sol[i], so[i]) < 1e-4
 
 
+def test_wbc_device_assembly_vs_oracle(gpu_ctx, oracle):
+    """hb_wbc_assemble_batch (W1-W3 in the qpOASES layout of WeightedWbc.cpp:24-42) against the oracle's assembly, entry by entry."""
+    x, u, rbd, mode, stance = _wbc_cases(40, 23)
+    H, g, A, lb, ub, m = gpu_ctx.wbc_assemble(x, u, rbd, mode, stance)
+    for i in range(len(mode)):
+        Hi, gi, Ai, lbi, ubi = oracle.wbc_assemble(x[i], u[i], rbd[i], int(mode[i]), bool(stance[i]))
+        assert m[i] == Ai.shape[0]
+        sc_ = max(1.0, np.abs(Hi).max())
+        assert np.abs(H[i] - Hi).max() < 1e-9 * sc_ and np.abs(g[i] - gi).max() < 1e-9 * max(1.0, np.abs(gi).max())
+        assert np.abs(A[i, :m[i]] - Ai).max() < 1e-9 * max(1.0, np.abs(Ai).max())
+        fin = np.abs(lbi) < 1e19
+        assert np.abs(lb[i, :m[i]][fin] - lbi[fin]).max() < 1e-8 * max(1.0, np.abs(lbi[fin]).max()) and (lb[i, :m[i]][~fin] <= -1e19).all()
+        assert np.abs(ub[i, :m[i]] - ubi).max() < 1e-8 * max(1.0, np.abs(ubi).max())
+
+
 def test_wbc_assembly_and_raw_qp_vs_oracle(gpu_ctx, oracle):
     """Config 5 path: raw (H, g, A, lbA, ubA) problems in qpOASES layout, mixed 56/58/60-row problems padded to 60 rows."""
     x, u, rbd, mode, stance = _wbc_cases(48, 22)
