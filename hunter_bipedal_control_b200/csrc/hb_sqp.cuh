@@ -297,83 +297,82 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
 
-// Shared memory of the node LQ kernel. `rec` first holds the linearisation record (brought in with cp.async); once the
-// discretisation, cost and constraint rows are built it is dead and re-used for the projection workspace and the projected model.
-struct LqShared {
-  double rec[LIN_STRIDE];
-  double Ad[9 * NX];                   // rows 3..11 of the discrete A, then of At (the other rows are identity / identity + dt Pxv and are formed on the way out)
-  double BdF[9 * 12], Bdv[9 * NJ];     // rows 3..11 of Bd
-  double Cv[12 * NX], Dv[12 * NJ], ev[12];
-  double Nv[NJ * NVMAX], pev[NJ];
-  double Rvv[NJ * NJ], Pv[NJ * NX], RFF[12 * 12];
-  double gx[8 * NX], gv[8 * NJ], gh[8];
-  double x[NX], u[NU], xn[NX], xref[NX], swing[24], b[NX], Qd[NX], q[NX], r[NU], bt[NX], rRpe[NJ];
-  int rowc[12], rowa[12], rowt[12], piv[NJ], freev[NJ], stidx[12];
-};
-// aliases inside `rec` after it is dead
-constexpr int LQ_G = 0, LQ_GL = 34, LQ_T1 = 340, LQ_BT = 560, LQ_PXV = 912;   // G 10x34, T1 10x22, Bt 22x16, Pxv 10x22 (ends at 1132)
-static_assert(LQ_PXV + NJ * NX <= LIN_STRIDE, "aliased area overflow");
-
-template <int MR>
-__device__ __forceinline__ void lq_build_tableau(const LqShared& sh, double* __restrict__ G, int lane) {
-  constexpr int GL = LQ_GL;
-  double xr[MR];
-#pragma unroll
-  for (int r = 0; r < MR; ++r) xr[r] = (lane < NJ) ? sh.Dv[r * NJ + lane] : -sh.Cv[r * NX + lane - NJ];
-#pragma unroll
-  for (int i = 0; i < NJ; ++i) {
-    double s = 0.0;
-#pragma unroll
-    for (int r = 0; r < MR; ++r) s = fma(sh.Dv[r * NJ + i], xr[r], s);
-    G[i * GL + lane] = s;
-  }
-  if (lane < NJ) {
-    double s = 0.0;
-#pragma unroll
-    for (int r = 0; r < MR; ++r) s = fma(-sh.Dv[r * NJ + lane], sh.ev[r], s);
-    G[lane * GL + NJ + NX] = s;
-  }
+// TMA bulk copies (1-D, cp.async.bulk) completing on an mbarrier: one elected lane arms the barrier with the byte count and issues the
+// copies, every lane waits on the phase bit. Addresses and sizes must be multiples of 16 bytes (the node records are).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
 }
 
-__global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  LqShared& sh = *reinterpret_cast<LqShared*>(smem_raw);
-  const int lane = threadIdx.x;
+// Shared memory of the node LQ kernel (14.2 KB -> 14 CTAs per SM by shared memory). `rec` receives the linearisation record by one TMA bulk
+// copy; its regions are re-used as soon as they are dead:
+//   A1 (9x22)            -> Ad  : rows 3..11 of the discrete A                     (after the RK2 sensitivities)
+//   A2 (9x22)            -> BdF (9x12), Bdv (9x10): rows 3..11 of the discrete B
+//   EPOS .. DVX (632..)  -> T = [Pxv | Nv | pev | 0] (10 x 32): the joint-velocity part of the input as an affine map of (dx, w, 1)
+// `G` holds the 10 x 33 tableau of the least-squares projection, then YZ (8 x 32: reduced gradients of the soft swing rows) + gv (8 x 10).
+struct LqShared {
+  double rec[LIN_STRIDE];
+  double G[NJ * 34];
+  double x[NX], u[NU], swing[24];
+  double q[NX], Qd[NX], r[NU], b[NX];
+  double ev[12], rowg[12], dvd[NJ], RFF[36];
+  unsigned long long bar;
+  int rowi[12], rowa[12], piv[NJ], freev[NJ];
+};
+constexpr int LQ_AD = LIN_A1, LQ_BDF = LIN_A2, LQ_BDV = LIN_A2 + 108, LQ_T = LIN_EPOS, LQ_TL = 32, LQ_GL = 34, LQ_YZ = 0, LQ_GV = 256;
+static_assert(LQ_BDV + 9 * NJ <= LIN_BF1, "discrete B must fit in the A2 region");
+static_assert(LQ_T + NJ * LQ_TL <= LIN_STRIDE && LQ_GV + 8 * NJ <= NJ * LQ_GL, "aliased areas overflow");
+static_assert((LQ_T % 2) == 0 && (sizeof(double) * LIN_STRIDE) % 16 == 0, "T is read with 128-bit loads");
+
+// One node of the LQ approximation. NSW = number of swing contacts (0 stance, 2 single support, 4 flight): 3 (4 - NSW) stance-force inputs,
+// 12 - 2 NSW contact-velocity rows, 2 NSW soft swing rows.
+//
+// Every quadratic term in the joint velocities v is reduced through the affine map v = T (dx, w, 1) of the projection:
+//   stage cost  1/2 v' Rb v + r_v' v        ->  T' Rb T  (blocks: Qt, Pt, Rt_nn and the vectors qt, rt_n)
+//   soft swing  1/2 w_s (h + gx' dx + gv' v)^2  ->  rank one in YZ_p = [gx_p | 0 | h_p] + gv_p' T
+// so the projected model is M = T' Rb T + w_s YZ' YZ evaluated once, lane = column, rows streamed from shared memory.
+template <int NSW>
+__device__ __forceinline__ void lq_node(LqShared& sh, const SqpArgs& a, int inst, int k, int lane, int mode, double xn_l, double xref_l) {
+  constexpr int MR = 12 - 2 * NSW, NP = 2 * NSW, NF = 3 * (4 - NSW), GL = LQ_GL, TL = LQ_TL;
   const int N = a.N;
-  const long long w = blockIdx.x;
-  const int inst = (int)(w / N), k = (int)(w - (long long)inst * N);
   const double dt = a.dt;
   const Model& md = c_model;
-  const double* grec = a.lin + ((size_t)inst * N + k) * LIN_STRIDE;
+  const double im = 1.0 / md.total_mass;
   double* out = a.proj + ((size_t)inst * N + k) * PJ_STRIDE;
-  const double* xk = (k == 0) ? a.x0 + (size_t)inst * NX : a.xt + ((size_t)inst * (N + 1) + k) * NX;
-  // ---- asynchronous loads: record + node vectors
-  for (int i = 2 * lane; i < LIN_DVV + 12 * NJ; i += 64) cp_async16(sh.rec + i, grec + i);
-  if (lane < 11) {
-    cp_async16(sh.x + 2 * lane, xk + 2 * lane);
-    cp_async16(sh.u + 2 * lane, a.ut + ((size_t)inst * N + k) * NU + 2 * lane);
-    cp_async16(sh.xn + 2 * lane, a.xt + ((size_t)inst * (N + 1) + k + 1) * NX + 2 * lane);
-    cp_async16(sh.xref + 2 * lane, a.x_ref + ((size_t)inst * (N + 1) + k) * NX + 2 * lane);
-  } else if (lane >= 16 && lane < 28) {
-    cp_async16(sh.swing + 2 * (lane - 16), a.swing + ((size_t)inst * (N + 1) + k) * 24 + 2 * (lane - 16));
-  }
-  cp_async_commit();
-  const int mode = a.mode[(size_t)inst * (N + 1) + k];
-  bool fl[4]; int ns = 0;
-  for (int c = 0; c < 4; ++c) { fl[c] = contact_flag(mode, c); ns += fl[c]; }
-  // constant parts that do not need the record
-  for (int idx = lane; idx < NJ * NJ; idx += 32) { const int i = idx / NJ, j = idx - i * NJ; sh.Rvv[idx] = md.R[(12 + i) * NU + 12 + j]; }
-  for (int idx = lane; idx < 144; idx += 32) { const int i = idx / 12, j = idx - i * 12; sh.RFF[idx] = (i == j) ? md.R[i * NU + i] : 0.0; }
-  for (int idx = lane; idx < NJ * NX; idx += 32) sh.Pv[idx] = 0.0;
-  cp_async_wait<0>();
-  __syncwarp();
+  const unsigned flm = (contact_flag(mode, 0) ? 1u : 0u) | (contact_flag(mode, 1) ? 2u : 0u) | (contact_flag(mode, 2) ? 4u : 0u) | (contact_flag(mode, 3) ? 8u : 0u);
   const double* A1c = sh.rec + LIN_A1; const double* A2c = sh.rec + LIN_A2;
   const double* Bf1 = sh.rec + LIN_BF1; const double* Bf2 = sh.rec + LIN_BF2;
   const double* Bv1 = sh.rec + LIN_BV1; const double* Bv2 = sh.rec + LIN_BV2;
   const double* f1 = sh.rec + LIN_F1; const double* f2 = sh.rec + LIN_F2;
   const double* epos = sh.rec + LIN_EPOS; const double* evel = sh.rec + LIN_EVEL;
   const double* dpq = sh.rec + LIN_DPQ; const double* dvx = sh.rec + LIN_DVX; const double* dvv = sh.rec + LIN_DVV;
-  // ---- RK2 sensitivities (S2) on the non-trivial rows 3..11
+  double* Ad = sh.rec + LQ_AD; double* BdF = sh.rec + LQ_BDF; double* Bdv = sh.rec + LQ_BDV; double* T = sh.rec + LQ_T;
+  double* G = sh.G; double* YZ = sh.G + LQ_YZ; double* GV = sh.G + LQ_GV;
+  // ---- RK2 sensitivities (S2) on the non-trivial rows 3..11, lane = column; results stay in registers until every lane has read A2
+  double ad[9], bd[9];
+  double d2 = 0.0;
   if (lane < NX) {
     const int j = lane;
     double c1[9];
@@ -384,16 +383,17 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
       double s = 0.0;
 #pragma unroll
       for (int kk = 0; kk < 9; ++kk) s = fma(A2c[i * NX + 3 + kk], c1[kk], s);
-      sh.Ad[i * NX + j] = 0.5 * dt * (c1[i] + A2c[i * NX + j] + dt * s) + ((3 + i == j) ? 1.0 : 0.0);
+      ad[i] = 0.5 * dt * (c1[i] + A2c[i * NX + j] + dt * s) + ((3 + i == j) ? 1.0 : 0.0);
     }
     if (j < 12) {
       // B1 force column j = [e_a / m ; Bf1[:, j] ; 0]: (A2 B1)[i][j] = A2c[i][a] / m + A2c[i][3:6] Bf1[:, j]
       const double b0 = Bf1[j], b1 = Bf1[12 + j], b2 = Bf1[24 + j];
+      const int ja = j % 3;
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
-        const double s = A2c[i * NX + 3] * b0 + A2c[i * NX + 4] * b1 + A2c[i * NX + 5] * b2 + A2c[i * NX + (j % 3)] / md.total_mass;
+        const double s = A2c[i * NX + 3] * b0 + A2c[i * NX + 4] * b1 + A2c[i * NX + 5] * b2 + A2c[i * NX + ja] * im;
         const double base = (i < 3) ? (Bf1[i * 12 + j] + Bf2[i * 12 + j]) : 0.0;
-        sh.BdF[i * 12 + j] = 0.5 * dt * (base + dt * s);
+        bd[i] = 0.5 * dt * (base + dt * s);
       }
     } else {
       const int jj = j - 12;
@@ -406,27 +406,49 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
 #pragma unroll
         for (int kk = 0; kk < 6; ++kk) s = fma(A2c[i * NX + 6 + kk], cb[kk], s);
         const double base = (i >= 3) ? (Bv1[(i - 3) * NJ + jj] + Bv2[(i - 3) * NJ + jj]) : 0.0;
-        sh.Bdv[i * NJ + jj] = 0.5 * dt * (base + dt * s);
+        bd[i] = 0.5 * dt * (base + dt * s);
       }
     }
+    const double bb = sh.x[lane] + 0.5 * dt * (f1[lane] + f2[lane]) - xn_l;
+    sh.b[lane] = bb; d2 = bb * bb;
   }
-  double d2 = 0.0;
-  if (lane < NX) { const double bb = sh.x[lane] + 0.5 * dt * (f1[lane] + f2[lane]) - sh.xn[lane]; sh.b[lane] = bb; d2 = bb * bb; }
   d2 = warp_sum(d2);
-  // ---- cost (M2, M6, M7, M8), scaled by dt at the end
-  const double fz = ns > 0 ? md.total_mass * HB_GRAVITY / ns : 0.0;
+  __syncwarp();          // every lane has read A1 / A2: their storage takes the discrete model
+  if (lane < NX) {
+    const int j = lane;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Ad[i * NX + j] = ad[i];
+    if (j < 12) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) BdF[i * 12 + j] = bd[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Bdv[i * NJ + j - 12] = bd[i];
+    }
+  }
+  // ---- cost (M2, M6, M8), scaled by dt at the end
+  const double fz = (NSW < 4) ? md.total_mass * HB_GRAVITY / (4 - NSW) : 0.0;
   double cost = 0.0;
   if (lane < NX) {
-    const double d = sh.x[lane] - sh.xref[lane];
+    const double d = sh.x[lane] - xref_l;
     sh.q[lane] = md.Q[lane] * d;
     sh.Qd[lane] = md.Q[lane];
     cost += 0.5 * md.Q[lane] * d * d;
     double s = 0.0;
-    if (lane < 12) { double dul = sh.u[lane]; if ((lane % 3) == 2 && fl[lane / 3]) dul -= fz; s = md.R[lane * NU + lane] * dul; cost += 0.5 * dul * s; }
-    else { for (int j = 12; j < NU; ++j) s += md.R[lane * NU + j] * sh.u[j]; cost += 0.5 * sh.u[lane] * s; }
+    if (lane < 12) { double dul = sh.u[lane]; if ((lane % 3) == 2 && ((flm >> (lane / 3)) & 1u)) dul -= fz; s = md.R[lane * NU + lane] * dul; cost += 0.5 * dul * s; }
+    else {
+#pragma unroll
+      for (int j = 12; j < NU; ++j) s = fma(md.R[lane * NU + j], sh.u[j], s);
+      cost += 0.5 * sh.u[lane] * s;
+    }
     sh.r[lane] = s;
   }
+  if (lane < 12) {      // RFF: one 3x3 block per contact (the friction-cone Hessian couples the axes of one contact only)
+    const int c = lane / 3, ax = lane - 3 * c;
+    sh.RFF[c * 9 + ax * 3] = 0.0; sh.RFF[c * 9 + ax * 3 + 1] = 0.0; sh.RFF[c * 9 + ax * 3 + 2] = 0.0;
+  }
   __syncwarp();
+  if (lane < 12) { const int c = lane / 3, ax = lane - 3 * c; sh.RFF[c * 9 + ax * 4] = md.R[lane * NU + lane]; }
   // all scalar penalties in ONE pass: lanes 0-9 joint position limits, 10-19 joint velocity limits, 20-23 normal-force limits
   // (double sided), 24-27 friction cones of stance contacts (one sided)
   double shiftsum = 0.0;
@@ -439,7 +461,7 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     else if (lane < 24) { const int c = lane - 20; h = sh.u[3 * c + 2]; lo = 0.0; hi = HB_LIMIT_FORCE_MAX; pmu = HB_LIMIT_FORCE_MU; pdl = HB_LIMIT_FORCE_DELTA; on = true; }
     else if (lane < 28) {
       const int c = lane - 24;
-      if (fl[c]) {
+      if ((flm >> c) & 1u) {
         Fx = sh.u[3 * c]; Fy = sh.u[3 * c + 1];
         t2 = Fx * Fx + Fy * Fy + HB_FRICTION_REGULARIZATION; tn = sqrt(t2);
         h = HB_FRICTION_MU * sh.u[3 * c + 2] - tn; lo = 0.0; pmu = HB_FRICTION_BARRIER_MU; pdl = HB_FRICTION_BARRIER_DELTA; two = false; on = true;
@@ -452,130 +474,87 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     if (on) {
       cost += pv;
       if (lane < 10) { sh.q[12 + lane] += p1; sh.Qd[12 + lane] += p2; }
-      else if (lane < 20) { const int j = lane - 10; sh.r[12 + j] += p1; sh.Rvv[j * NJ + j] += p2; }
-      else if (lane < 24) { const int c = lane - 20; sh.r[3 * c + 2] += p1; sh.RFF[(3 * c + 2) * 12 + 3 * c + 2] += p2; }
+      else if (lane < 20) { const int j = lane - 10; sh.r[12 + j] += p1; sh.dvd[j] = p2; }
+      else if (lane < 24) { const int c = lane - 20; sh.r[3 * c + 2] += p1; sh.RFF[c * 9 + 8] += p2; }
     }
     __syncwarp();
     if (on && lane >= 24) {
       const int c = lane - 24;
-      const double t32 = tn * t2;
-      const double gr[3] = {-Fx / tn, -Fy / tn, HB_FRICTION_MU};
-      const double Hh[9] = {-(Fy * Fy + HB_FRICTION_REGULARIZATION) / t32, Fx * Fy / t32, 0.0, Fx * Fy / t32,
-                            -(Fx * Fx + HB_FRICTION_REGULARIZATION) / t32, 0.0, 0.0, 0.0, 0.0};
-      for (int i = 0; i < 3; ++i) {
-        sh.r[3 * c + i] += p1 * gr[i];
-        for (int j = 0; j < 3; ++j) sh.RFF[(3 * c + i) * 12 + 3 * c + j] += p2 * gr[i] * gr[j] + p1 * Hh[3 * i + j];
-      }
+      const double it = 1.0 / tn, it32 = 1.0 / (tn * t2);
+      const double g0 = -Fx * it, g1 = -Fy * it, g2 = HB_FRICTION_MU;
+      const double h00 = -(Fy * Fy + HB_FRICTION_REGULARIZATION) * it32, h01 = Fx * Fy * it32, h11 = -(Fx * Fx + HB_FRICTION_REGULARIZATION) * it32;
+      double* Rc = sh.RFF + c * 9;
+      sh.r[3 * c] += p1 * g0; sh.r[3 * c + 1] += p1 * g1; sh.r[3 * c + 2] += p1 * g2;
+      Rc[0] += p2 * g0 * g0 + p1 * h00; Rc[1] += p2 * g0 * g1 + p1 * h01; Rc[2] += p2 * g0 * g2;
+      Rc[3] += p2 * g1 * g0 + p1 * h01; Rc[4] += p2 * g1 * g1 + p1 * h11; Rc[5] += p2 * g1 * g2;
+      Rc[6] += p2 * g2 * g0;            Rc[7] += p2 * g2 * g1;            Rc[8] += p2 * g2 * g2;
       shiftsum = -p1 * HB_FRICTION_HESSIAN_SHIFT;
     }
   }
   shiftsum = warp_sum(shiftsum);
   __syncwarp();
   if (lane < NX) sh.Qd[lane] += shiftsum;
-  if (lane < 12) sh.RFF[lane * 12 + lane] += shiftsum;
-  else if (lane >= 16 && lane < 16 + NJ) sh.Rvv[(lane - 16) * NJ + lane - 16] += shiftsum;
-  // xy swing soft constraint: gradients gx (22) / gv (10, vj columns only)
-  int npair = 0;
-  for (int c = 0; c < 4; ++c) {
-    if (fl[c]) continue;
-    for (int ax = 0; ax < 2; ++ax) {
-      const int row = 3 * c + ax;
-      if (lane < NX) {
-        double px = 0.0;
-        if (lane >= 6 && lane < 9) px = (lane - 6 == ax) ? 1.0 : 0.0;
-        else if (lane >= 9) px = dpq[row * NDIR + lane - 9];
-        sh.gx[npair * NX + lane] = dvx[row * NX + lane] + HB_XY_POSITION_GAIN * px;
-        if (lane < NJ) sh.gv[npair * NJ + lane] = dvv[row * NJ + lane];
-      }
-      if (lane == 0) sh.gh[npair] = evel[row] - sh.swing[6 * c + 3 + ax] + HB_XY_POSITION_GAIN * (epos[row] - sh.swing[6 * c + ax]);
-      ++npair;
+  if (lane < 12) sh.RFF[(lane / 3) * 9 + (lane % 3) * 4] += shiftsum;
+  else if (lane >= 16 && lane < 16 + NJ) sh.dvd[lane - 16] += shiftsum;
+  // ---- contact-velocity equality rows (M4, M5); swing forces handled separately (M3). Row r -> contact-kinematics row rowi[r] = 3c + axis.
+  if (lane == 0) {
+    int mr = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if ((flm >> c) & 1u) {
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) { sh.rowi[mr] = 3 * c + ax; sh.rowa[mr] = ax; sh.rowg[mr] = (ax == 2) ? (double)HB_ZEROVEL_Z_GAIN : 0.0; ++mr; }
+      } else { sh.rowi[mr] = 3 * c + 2; sh.rowa[mr] = 2; sh.rowg[mr] = (double)HB_POSITION_ERROR_GAIN; ++mr; }
     }
-  }
-  for (int idx = npair * NX + lane; idx < 8 * NX; idx += 32) sh.gx[idx] = 0.0;   // unused pairs must be exact zeros (they enter Qt with weight 0)
-  __syncwarp();
-  if (npair > 0) {
-    const double w = HB_SOFT_SWING_WEIGHT;
-    if (lane < NX) {
-      double qa = 0.0;
-      double pvc[NJ];
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) pvc[i] = 0.0;
-      for (int p = 0; p < npair; ++p) {
-        const double h = sh.gh[p], gxj = sh.gx[p * NX + lane];
-        qa += w * h * gxj;
-#pragma unroll
-        for (int i = 0; i < NJ; ++i) pvc[i] = fma(w * sh.gv[p * NJ + i], gxj, pvc[i]);
-      }
-      sh.q[lane] += qa;
-#pragma unroll
-      for (int i = 0; i < NJ; ++i) sh.Pv[i * NX + lane] = pvc[i];
-      if (lane < NJ) {
-        double ra = 0.0;
-        for (int p = 0; p < npair; ++p) {
-          const double gvj = sh.gv[p * NJ + lane];
-          ra += w * sh.gh[p] * gvj;
-#pragma unroll
-          for (int i = 0; i < NJ; ++i) sh.Rvv[i * NJ + lane] += w * sh.gv[p * NJ + i] * gvj;
-        }
-        sh.r[12 + lane] += ra;
-      }
-    }
-    if (lane < npair) cost += 0.5 * w * sh.gh[lane] * sh.gh[lane];
-  }
-  cost = warp_sum(cost);
-  // ---- contact-velocity equality rows (M4, M5); swing forces handled separately (M3)
-  int mr = 0;
-  for (int c = 0; c < 4; ++c) {
-    if (fl[c]) { for (int ax = 0; ax < 3; ++ax) { if (lane == 0) { sh.rowc[mr] = c; sh.rowa[mr] = ax; sh.rowt[mr] = 0; } ++mr; } }
-    else { if (lane == 0) { sh.rowc[mr] = c; sh.rowa[mr] = 2; sh.rowt[mr] = 2; } ++mr; }
   }
   __syncwarp();
   double e2 = 0.0;
-  if (lane < NX) {
-    for (int rr = 0; rr < mr; ++rr) {
-      const int ra = sh.rowa[rr], row = 3 * sh.rowc[rr] + ra, t = sh.rowt[rr];
-      const double gain = (t == 0) ? ((ra == 2) ? HB_ZEROVEL_Z_GAIN : 0.0) : HB_POSITION_ERROR_GAIN;
-      double px = 0.0;
-      if (lane >= 6 && lane < 9) px = (lane - 6 == ra) ? 1.0 : 0.0;
-      else if (lane >= 9) px = dpq[row * NDIR + lane - 9];
-      sh.Cv[rr * NX + lane] = dvx[row * NX + lane] + gain * px;
-      if (lane < NJ) sh.Dv[rr * NJ + lane] = dvv[row * NJ + lane];
-    }
-  }
-  if (lane < mr) {
-    const int c = sh.rowc[lane], ax = sh.rowa[lane], row = 3 * c + ax;
+  if (lane < MR) {
+    const int row = sh.rowi[lane], c = row / 3, ax = row - 3 * c;
     double evv;
-    if (sh.rowt[lane] == 0) evv = evel[row] + (ax == 2 ? HB_ZEROVEL_Z_GAIN * epos[row] + HB_ZEROVEL_Z_OFFSET : 0.0);
+    if ((flm >> c) & 1u) evv = evel[row] + (ax == 2 ? HB_ZEROVEL_Z_GAIN * epos[row] + HB_ZEROVEL_Z_OFFSET : 0.0);
     else evv = evel[row] - sh.swing[6 * c + 5] + HB_POSITION_ERROR_GAIN * (epos[row] - sh.swing[6 * c + 2]);
     sh.ev[lane] = evv;
     e2 = evv * evv;
   }
-  if (lane >= 16 && lane < 28) { const int j = lane - 16; if (!fl[j / 3]) e2 += sh.u[j] * sh.u[j]; }
+  if (lane >= 16 && lane < 28) { const int j = lane - 16; if (!((flm >> (j / 3)) & 1u)) e2 += sh.u[j] * sh.u[j]; }
   e2 = warp_sum(e2);
-  __syncwarp();
-  // ================= the record is dead from here on: its storage holds G, T1, Bt, Pxv =================
-  double* G = sh.rec + LQ_G; double* T1 = sh.rec + LQ_T1; double* Bt = sh.rec + LQ_BT; double* Pxv = sh.rec + LQ_PXV;
-  // ---- least-squares projection on vj: G = Dv'Dv, rhs = -Dv'[Cv | ev]  (10 x 33, ld 34), entries spread over all lanes
-  constexpr int GW = NJ + NX + 1, GL = LQ_GL;
-  // lane j owns column j of the tableau: its right operand X[r][j] (Dv, -Cv) stays in registers, Dv[r][i] is a broadcast load.
-  // mr is 4 (flight), 8 (single support) or 12 (stance) for the contact pairs of this robot.
-  if (mr == 4) lq_build_tableau<4>(sh, G, lane);
-  else if (mr == 8) lq_build_tableau<8>(sh, G, lane);
-  else if (mr == 12) lq_build_tableau<12>(sh, G, lane);
-  else {
-    for (int idx = lane; idx < NJ * GW; idx += 32) {
-      const int i = idx / GW, j = idx - i * GW;
+  // ---- least-squares projection on vj: tableau G = Dv' [Dv | -Cv | -ev] (10 x 33, ld 34) built straight from the record. Lane j owns column
+  // j: its right operand X[r][j] (Dv for j < 10, -Cv for the 22 state columns) stays in registers, Dv[r][i] is a broadcast load.
+  {
+    double xr[MR];
+#pragma unroll
+    for (int r = 0; r < MR; ++r) {
+      const int row = sh.rowi[r];
+      double v;
+      if (lane < NJ) v = dvv[row * NJ + lane];
+      else {
+        const int jj = lane - NJ;
+        double px = 0.0;
+        if (jj >= 6 && jj < 9) px = (jj - 6 == sh.rowa[r]) ? 1.0 : 0.0;
+        else if (jj >= 9) px = dpq[row * NDIR + jj - 9];
+        v = -(dvx[row * NX + jj] + sh.rowg[r] * px);
+      }
+      xr[r] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
       double s = 0.0;
-      if (j < NJ) { for (int r = 0; r < mr; ++r) s = fma(sh.Dv[r * NJ + i], sh.Dv[r * NJ + j], s); }
-      else if (j < NJ + NX) { for (int r = 0; r < mr; ++r) s = fma(-sh.Dv[r * NJ + i], sh.Cv[r * NX + j - NJ], s); }
-      else { for (int r = 0; r < mr; ++r) s = fma(-sh.Dv[r * NJ + i], sh.ev[r], s); }
-      G[i * GL + j] = s;
+#pragma unroll
+      for (int r = 0; r < MR; ++r) s = fma(dvv[sh.rowi[r] * NJ + i], xr[r], s);
+      G[i * GL + lane] = s;
+    }
+    if (lane < NJ) {
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < MR; ++r) s = fma(-xr[r], sh.ev[r], s);
+      G[lane * GL + NJ + NX] = s;
+      sh.piv[lane] = 0;
     }
   }
-  if (lane < NJ) sh.piv[lane] = 0;
   __syncwarp();
   double dmax = lane < NJ ? G[lane * GL + lane] : 0.0;
-  if (ns < 4) dmax = fmax(dmax, 1.0);     // the swing-force selector rows of D have unit diagonal in D'D
+  if (NSW > 0) dmax = fmax(dmax, 1.0);     // the swing-force selector rows of D have unit diagonal in D'D
   dmax = warp_max(dmax);
   const double tol = 1e-9 * fmax(dmax, 1e-300);
   for (int step = 0; step < NJ; ++step) {
@@ -592,7 +571,6 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     const int p = pi;
     const double inv = 1.0 / dv;
     // lane j owns column j (j < 32) of the 10 x 33 tableau; the last column (index 32) is updated by lane i for row i
-    static_assert(GW == 33, "column ownership below assumes 33 columns");
     const double pj = G[p * GL + lane] * inv;                   // scaled pivot-row entry of this lane's column
     const double p32 = G[p * GL + 32] * inv;
     const double colv = (lane < NJ) ? G[lane * GL + p] : 0.0;   // column p before elimination, one entry per lane
@@ -608,154 +586,246 @@ __global__ void __launch_bounds__(32) lq_kernel(SqpArgs a) {
     __syncwarp();
   }
   int nv = 0;
+#pragma unroll
   for (int i = 0; i < NJ; ++i) if (!sh.piv[i]) { if (lane == 0) sh.freev[nv] = i; ++nv; }
-  int nf = 0;
-  for (int j = 0; j < 12; ++j) if (fl[j / 3]) { if (lane == 0) sh.stidx[nf] = j; ++nf; }
   bool overflow = false;
   if (nv > NVMAX) { nv = NVMAX; overflow = true; }       // degenerate pose (velocity rows lost rank): flagged, instance reported as failed
-  if (nf + nv > NTMAX) { nv = NTMAX - nf; overflow = true; }
-  const int nt = nf + nv;
-  const int ntp = ntp_of(nt);
+  if (NF + nv > NTMAX) { nv = NTMAX - NF; overflow = true; }
+  const int nt = NF + nv;
   __syncwarp();
-  if (lane < NX) {
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) Pxv[i * NX + lane] = sh.piv[i] ? G[i * GL + NJ + lane] : 0.0;
-    if (lane < NJ) sh.pev[lane] = sh.piv[lane] ? G[lane * GL + NJ + NX] : 0.0;
-    if (lane < nv) { const int fc = sh.freev[lane]; for (int i = 0; i < NJ; ++i) sh.Nv[i * NVMAX + lane] = sh.piv[i] ? -G[i * GL + fc] : ((i == fc) ? 1.0 : 0.0); }
-  }
-  for (int idx = lane; idx < NX * NTMAX; idx += 32) Bt[idx] = 0.0;
-  __syncwarp();
-  // ---- projected model (cost scaled by dt)
-  if (lane < NX) {
-    const int j = lane;
-    double pc[NJ];
-#pragma unroll
-    for (int kk = 0; kk < NJ; ++kk) pc[kk] = Pxv[kk * NX + j];
-    // At = Ad + Bd_v Pxv : rows 3..11 += Bdv Pxv ; rows 12..21 += dt Pxv
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      double s = sh.Ad[i * NX + j];
-#pragma unroll
-      for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Bdv[i * NJ + kk], pc[kk], s);
-      sh.Ad[i * NX + j] = s;
-    }
-    // PRPx_v = Pv + Rvv Pxv (10 x 22)
+  // ---- column `lane` of T = [Pxv (22) | Nv (8) | pev | 0] in registers
+  const int cc = lane - NX;                               // null-space column of lanes 22..29
+  const bool nlane = cc >= 0 && cc < nv;                  // lane owns an active null-space column
+  double tc[NJ];
+  {
+    const int fc = (cc >= 0 && cc < NVMAX && cc < nv) ? sh.freev[cc] : -1;
 #pragma unroll
     for (int i = 0; i < NJ; ++i) {
-      double s = sh.Pv[i * NX + j];
-#pragma unroll
-      for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Rvv[i * NJ + kk], pc[kk], s);
-      T1[i * NX + j] = s;
+      const bool pv = sh.piv[i] != 0;
+      double v = 0.0;
+      if (lane < NX) v = pv ? G[i * GL + NJ + lane] : 0.0;
+      else if (fc >= 0) v = pv ? -G[i * GL + fc] : ((i == fc) ? 1.0 : 0.0);
+      else if (lane == 30) v = pv ? G[i * GL + NJ + NX] : 0.0;
+      tc[i] = v;
     }
   }
-  if (lane < NJ) {
-    double s = sh.r[12 + lane];
+  __syncwarp();       // the tableau is dead: its storage takes YZ and gv
+  // ---- xy swing soft constraint (M7): row p = [gx_p (22) | 0 (8) | h_p | 0], gv_p (10)
+  if (NP > 0) {
+    int p = 0;
 #pragma unroll
-    for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Rvv[lane * NJ + kk], sh.pev[kk], s);
-    sh.rRpe[lane] = s;
+    for (int c = 0; c < 4; ++c) {
+      if ((flm >> c) & 1u) continue;
+#pragma unroll
+      for (int ax = 0; ax < 2; ++ax) {
+        const int row = 3 * c + ax;
+        double v = 0.0;
+        if (lane < NX) {
+          double px = 0.0;
+          if (lane >= 6 && lane < 9) px = (lane - 6 == ax) ? 1.0 : 0.0;
+          else if (lane >= 9) px = dpq[row * NDIR + lane - 9];
+          v = dvx[row * NX + lane] + HB_XY_POSITION_GAIN * px;
+        } else if (lane == 30) v = evel[row] - sh.swing[6 * c + 3 + ax] + HB_XY_POSITION_GAIN * (epos[row] - sh.swing[6 * c + ax]);
+        if (p < NP) {
+          YZ[p * TL + lane] = v;
+          if (lane < NJ) GV[p * NJ + lane] = dvv[row * NJ + lane];
+        }
+        ++p;
+      }
+    }
+  }
+  __syncwarp();       // every read of the contact-kinematics part of the record is done: T takes its place
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) T[i * TL + lane] = tc[i];
+  double wyz[NP > 0 ? NP : 1];
+  if (NP > 0) {
+    if (lane < NP) { const double g = YZ[lane * TL + 30]; cost += 0.5 * HB_SOFT_SWING_WEIGHT * g * g; }
+    __syncwarp();       // the unreduced h_p are read before lane 30 replaces them
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      double s = YZ[p * TL + lane];
+#pragma unroll
+      for (int kk = 0; kk < NJ; ++kk) s = fma(GV[p * NJ + kk], tc[kk], s);
+      wyz[p] = HB_SOFT_SWING_WEIGHT * s;
+      YZ[p * TL + lane] = s;
+    }
+  }
+  cost = warp_sum(cost);
+  // ---- Rb T (column `lane`): Rb = R_vv (constant) + diag(velocity-limit curvature + shift); linear term r_v' T
+  double rb[NJ];
+  double lin = 0.0;
+#pragma unroll
+  for (int i = 0; i < NJ; ++i) {
+    double s = sh.dvd[i] * tc[i];
+#pragma unroll
+    for (int kk = 0; kk < NJ; ++kk) s = fma(md.R[(12 + i) * NU + 12 + kk], tc[kk], s);
+    rb[i] = s;
+    lin = fma(sh.r[12 + i], tc[i], lin);
   }
   __syncwarp();
-  // Qt = diag(Qd) + sum_p w gx_p gx_p' + Pxv' PRPx_v + Pv' Pxv ; qt = q + Pxv' rRpe + Pv' pev   (column j by lane j)
-  if (lane < NX) {
-    const int j = lane;
-    double tc[NJ], pc[NJ], gj[8];
-#pragma unroll
-    for (int kk = 0; kk < NJ; ++kk) { tc[kk] = T1[kk * NX + j]; pc[kk] = Pxv[kk * NX + j]; }
-#pragma unroll
-    for (int p = 0; p < 8; ++p) gj[p] = (p < npair) ? HB_SOFT_SWING_WEIGHT * sh.gx[p * NX + j] : 0.0;
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      double s = (i == j) ? sh.Qd[i] : 0.0;
-#pragma unroll
-      for (int kk = 0; kk < NJ; ++kk) { s = fma(Pxv[kk * NX + i], tc[kk], s); s = fma(sh.Pv[kk * NX + i], pc[kk], s); }
-      if (npair > 0) {
-#pragma unroll
-        for (int p = 0; p < 8; ++p) s = fma(sh.gx[p * NX + i], gj[p], s);
-      }
-      out[PJ_QT + i * NX + j] = dt * s;
-    }
-    double s = sh.q[j];
-#pragma unroll
-    for (int kk = 0; kk < NJ; ++kk) s += pc[kk] * sh.rRpe[kk] + sh.Pv[kk * NX + j] * sh.pev[kk];
-    out[PJ_QV + j] = dt * s;
-  }
-  // Bt (22 x nt, ld NTMAX): stance-force columns then null-space columns; padded columns stay zero
-  if (lane < nt) {
-    const int c = lane;
-    if (c < nf) {
-      const int j = sh.stidx[c];
-      Bt[(j % 3) * NTMAX + c] = dt / md.total_mass;
-#pragma unroll
-      for (int i = 0; i < 9; ++i) Bt[(3 + i) * NTMAX + c] = sh.BdF[i * 12 + j];
+  // ---- M = T' Rb T + YZ' (w YZ), row by row (rows come in pairs with 128-bit broadcast loads); lane = column:
+  //   lanes 0..21 : rows 0..21 -> Qt, row 30 -> qt          lanes 22..29 : rows 0..21 -> Pt^T, rows 22..29 -> Rt (null block), row 30 -> rt
+  const double Qd_l = (lane < NX) ? sh.Qd[lane] : 0.0;
+  auto m_store = [&](int i, double s) {
+    if (i < NX) {
+      if (lane < NX) out[PJ_QT + i * NX + lane] = dt * (s + ((i == lane) ? Qd_l : 0.0));
+      else if (nlane) out[PJ_PT + i * NTMAX + NF + cc] = dt * s;
+    } else if (i < NX + NVMAX) {
+      if (nlane && i - NX < nv) out[PJ_RT + (NF + i - NX) * NTMAX + NF + cc] = dt * s;
     } else {
-      const int cc = c - nf;
+      if (lane < NX) out[PJ_QV + lane] = dt * (sh.q[lane] + s + lin);
+      else if (nlane) out[PJ_RV + NF + cc] = dt * (s + lin);
+    }
+  };
 #pragma unroll
-      for (int i = 0; i < 9; ++i) { double s = 0.0; for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Bdv[i * NJ + kk], sh.Nv[kk * NVMAX + cc], s); Bt[(3 + i) * NTMAX + c] = s; }
-      for (int kk = 0; kk < NJ; ++kk) Bt[(12 + kk) * NTMAX + c] = dt * sh.Nv[kk * NVMAX + cc];
+  for (int i = 0; i < 30; i += 2) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < NJ; ++kk) {
+      const double2 t = *reinterpret_cast<const double2*>(T + kk * TL + i);
+      s0 = fma(t.x, rb[kk], s0); s1 = fma(t.y, rb[kk], s1);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const double2 y = *reinterpret_cast<const double2*>(YZ + p * TL + i);
+      s0 = fma(y.x, wyz[p], s0); s1 = fma(y.y, wyz[p], s1);
+    }
+    m_store(i, s0); m_store(i + 1, s1);
+  }
+  {
+    double s = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < NJ; ++kk) s = fma(T[kk * TL + 30], rb[kk], s);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) s = fma(YZ[p * TL + 30], wyz[p], s);
+    m_store(30, s);
+  }
+  // ---- dynamics through T: Bdv T (rows 3..11) -> At (lanes 0..21, + Ad), Bt null columns (lanes 22..29), bt (lane 30); rows 12..21 are dt T
+  double at9[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    double s = (lane < NX) ? Ad[i * NX + lane] : 0.0;
+#pragma unroll
+    for (int kk = 0; kk < NJ; ++kk) s = fma(Bdv[i * NJ + kk], tc[kk], s);
+    at9[i] = s;
+  }
+  if (lane == 30) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sh.b[3 + i] += at9[i];
+#pragma unroll
+    for (int kk = 0; kk < NJ; ++kk) sh.b[12 + kk] += dt * tc[kk];
+  }
+  // role of the lane in the input-column writes: lanes 0..15 own the stance-force columns c < NF and the padded columns c >= nt,
+  // lanes 22..29 own the null-space columns NF + cc
+  const bool fcol = lane < NF, pcol = lane >= nt && lane < NTMAX;
+  const bool wcol = fcol || pcol || nlane;
+  const int col = nlane ? NF + cc : lane;
+  int sj = 0;           // input index of stance-force column `lane`
+  if (fcol) {
+    int cnt = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if ((flm >> c) & 1u) { if (lane >= cnt && lane < cnt + 3) sj = 3 * c + lane - cnt; cnt += 3; }
+  }
+  if (lane < NX) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[PJ_AT + i * NX + lane] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) out[PJ_AT + (3 + i) * NX + lane] = at9[i];
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) out[PJ_AT + (12 + i) * NX + lane] = ((12 + i == lane) ? 1.0 : 0.0) + dt * tc[i];
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) out[PJ_PXV + i * NX + lane] = tc[i];
+  } else if (cc >= 0 && cc < NVMAX) {
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) out[PJ_NV + i * NVMAX + cc] = nlane ? tc[i] : 0.0;
+  } else if (lane == 30) {
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) out[PJ_PEV + i] = tc[i];
+  }
+  if (wcol) {
+    const int sa = sj % 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[PJ_BT + i * NTMAX + col] = (fcol && i == sa) ? dt * im : 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) out[PJ_BT + (3 + i) * NTMAX + col] = fcol ? BdF[i * 12 + sj] : (nlane ? at9[i] : 0.0);
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) out[PJ_BT + (12 + i) * NTMAX + col] = nlane ? dt * tc[i] : 0.0;
+    if (!nlane) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) out[PJ_PT + i * NTMAX + col] = 0.0;
+      out[PJ_RV + col] = fcol ? dt * sh.r[sj] : 0.0;
+    }
+    // Rt column: stance-force block (3x3 per contact), identity on the padded diagonal, zeros between the blocks
+    int cnt = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (!((flm >> c) & 1u)) continue;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        double v = 0.0;
+        if (fcol && sj / 3 == c) v = dt * sh.RFF[c * 9 + ax * 3 + sa];
+        if (cnt < NF) out[PJ_RT + cnt * NTMAX + col] = v;
+        ++cnt;
+      }
+    }
+#pragma unroll
+    for (int i = NF; i < NTMAX; ++i) {
+      if (nlane) { if (i >= nt) out[PJ_RT + i * NTMAX + col] = 0.0; }
+      else out[PJ_RT + i * NTMAX + col] = (pcol && i == col) ? 1.0 : 0.0;
     }
   }
-  // bt = b + Bd_v pev - Bd_F[:, swing] F_swing
+  // a null lane's Rt rows NF..nt-1 with cc2 >= nv do not exist (nv rows); rows of inactive null columns are padded columns (lanes >= nt)
+  __syncwarp();
+  // bt = b + Bd_v pev + dt pev - Bd_F[:, swing] F_swing
   if (lane < NX) {
     const int i = lane;
     double s = sh.b[i];
-    if (i >= 3 && i < 12) {
-      for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Bdv[(i - 3) * NJ + kk], sh.pev[kk], s);
-      for (int j = 0; j < 12; ++j) if (!fl[j / 3]) s -= sh.BdF[(i - 3) * 12 + j] * sh.u[j];
-    } else if (i >= 12) s += dt * sh.pev[i - 12];
-    else { for (int c = 0; c < 4; ++c) if (!fl[c]) s -= dt / md.total_mass * sh.u[3 * c + i]; }
-    sh.bt[i] = s;
+    if (NSW > 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if ((flm >> c) & 1u) continue;
+        if (i < 3) s -= dt * im * sh.u[3 * c + i];
+        else if (i < 12) s -= BdF[(i - 3) * 12 + 3 * c] * sh.u[3 * c] + BdF[(i - 3) * 12 + 3 * c + 1] * sh.u[3 * c + 1] + BdF[(i - 3) * 12 + 3 * c + 2] * sh.u[3 * c + 2];
+      }
+    }
+    out[PJ_BTV + lane] = s;
+  }
+  if (lane == 0) { out[PJ_META] = nt; out[PJ_META + 1] = NF; out[PJ_META + 2] = nv; out[PJ_META + 3] = cost; out[PJ_META + 4] = d2; out[PJ_META + 5] = e2; out[PJ_META + 6] = overflow ? 1.0 : 0.0; }
+}
+
+#ifndef HB_LQ_MINB
+#define HB_LQ_MINB 12
+#endif
+__global__ void __launch_bounds__(32, HB_LQ_MINB) lq_kernel(SqpArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LqShared& sh = *reinterpret_cast<LqShared*>(smem_raw);
+  const int lane = threadIdx.x;
+  const int N = a.N;
+  const long long w = blockIdx.x;
+  const int inst = (int)(w / N), k = (int)(w - (long long)inst * N);
+  const double* grec = a.lin + ((size_t)inst * N + k) * LIN_STRIDE;
+  const double* xk = (k == 0) ? a.x0 + (size_t)inst * NX : a.xt + ((size_t)inst * (N + 1) + k) * NX;
+  // ---- one TMA bulk copy for the record (9568 B) and one each for x, u, the swing references; a single mbarrier collects the bytes
+  if (lane == 0) {
+    constexpr unsigned REC_BYTES = (LIN_DVV + 12 * NJ) * sizeof(double), V_BYTES = NX * sizeof(double), SW_BYTES = 24 * sizeof(double);
+    mbar_init(&sh.bar, 1);
+    mbar_expect_tx(&sh.bar, REC_BYTES + 2 * V_BYTES + SW_BYTES);
+    bulk_g2s(sh.rec, grec, REC_BYTES, &sh.bar);
+    bulk_g2s(sh.x, xk, V_BYTES, &sh.bar);
+    bulk_g2s(sh.u, a.ut + ((size_t)inst * N + k) * NU, V_BYTES, &sh.bar);
+    bulk_g2s(sh.swing, a.swing + ((size_t)inst * (N + 1) + k) * 24, SW_BYTES, &sh.bar);
   }
   __syncwarp();
-  // Rt (ntp x ntp), Pt (ntp x 22), rt (ntp); RN = Rvv Nv (10 x nv) goes into the dead constraint-row storage first
-  double* RN = sh.Cv;
-  for (int idx = lane; idx < NJ * NVMAX; idx += 32) {
-    const int p = idx / NVMAX, cj = idx - p * NVMAX;
-    double t = 0.0;
-    if (cj < nv) { for (int qq = 0; qq < NJ; ++qq) t = fma(sh.Rvv[p * NJ + qq], sh.Nv[qq * NVMAX + cj], t); }
-    RN[idx] = t;
-  }
-  __syncwarp();
-  for (int idx = lane; idx < NTMAX * NTMAX; idx += 32) {
-    const int i = idx / NTMAX, j = idx - i * NTMAX;
-    double s = 0.0;
-    if (i >= nt || j >= nt) s = (i == j) ? 1.0 / dt : 0.0;       // identity on the padded diagonal
-    else if (i < nf && j < nf) s = sh.RFF[sh.stidx[i] * 12 + sh.stidx[j]];
-    else if (i >= nf && j >= nf) {
-      const int ci = i - nf, cj = j - nf;
-      for (int p = 0; p < NJ; ++p) s = fma(sh.Nv[p * NVMAX + ci], RN[p * NVMAX + cj], s);
-    }
-    out[PJ_RT + i * NTMAX + j] = dt * s;
-  }
-  if (lane < NX) {
-    // Pt is stored transposed (22 x NTMAX) so that the Riccati kernel can stage it with 16-byte async copies
-    for (int c = 0; c < NTMAX; ++c) {
-      double s = 0.0;
-      if (c >= nf && c < nt) { const int cc = c - nf; for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Nv[kk * NVMAX + cc], T1[kk * NX + lane], s); }
-      out[PJ_PT + lane * NTMAX + c] = dt * s;
-    }
-  }
-  if (lane < ntp) {
-    double s;
-    if (lane >= nt) s = 0.0;
-    else if (lane < nf) s = sh.r[sh.stidx[lane]];
-    else { s = 0.0; const int cc = lane - nf; for (int kk = 0; kk < NJ; ++kk) s = fma(sh.Nv[kk * NVMAX + cc], sh.rRpe[kk], s); }
-    out[PJ_RV + lane] = dt * s;
-  }
-  // ---- write the rest of the record
-  for (int idx = lane; idx < TS; idx += 32) {
-    const int i = idx / NX, j = idx - i * NX;
-    double v;
-    if (i < 3) v = (i == j) ? 1.0 : 0.0;                                   // momentum rows: identity
-    else if (i < 12) v = sh.Ad[idx - 3 * NX];
-    else v = ((i == j) ? 1.0 : 0.0) + dt * Pxv[(i - 12) * NX + j];         // joint rows: I + dt Pxv
-    out[PJ_AT + idx] = v;
-  }
-  for (int idx = lane; idx < NX * NTMAX; idx += 32) out[PJ_BT + idx] = Bt[idx];
-  if (lane < NX) out[PJ_BTV + lane] = sh.bt[lane];
-  for (int idx = lane; idx < NJ * NX; idx += 32) out[PJ_PXV + idx] = Pxv[idx];
-  for (int idx = lane; idx < NJ * NVMAX; idx += 32) { const int c = idx % NVMAX; out[PJ_NV + idx] = (c < nv) ? sh.Nv[idx] : 0.0; }
-  if (lane < NJ) out[PJ_PEV + lane] = sh.pev[lane];
-  if (lane == 0) { out[PJ_META] = nt; out[PJ_META + 1] = nf; out[PJ_META + 2] = nv; out[PJ_META + 3] = cost; out[PJ_META + 4] = d2; out[PJ_META + 5] = e2; out[PJ_META + 6] = overflow ? 1.0 : 0.0; }
+  const int mode = a.mode[(size_t)inst * (N + 1) + k];
+  double xn_l = 0.0, xref_l = 0.0;
+  if (lane < NX) { xn_l = a.xt[((size_t)inst * (N + 1) + k + 1) * NX + lane]; xref_l = a.x_ref[((size_t)inst * (N + 1) + k) * NX + lane]; }
+  int nsw = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) nsw += contact_flag(mode, c) ? 0 : 1;
+  mbar_wait(&sh.bar, 0);
+  if (nsw == 2) lq_node<2>(sh, a, inst, k, lane, mode, xn_l, xref_l);
+  else if (nsw == 0) lq_node<0>(sh, a, inst, k, lane, mode, xn_l, xref_l);
+  else lq_node<4>(sh, a, inst, k, lane, mode, xn_l, xref_l);
 }
 
 // ---------------------------------------------------------------- K2: value-function recursion
