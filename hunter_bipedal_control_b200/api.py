@@ -28,12 +28,14 @@ EXPORTED_SYMBOLS = [
     "hb_estimator_update_batch", "hb_default_pd_gains", "hb_joint_command_batch_dev", "hb_joint_command_batch",
     "hb_wbc_qp_batch", "hb_wbc_solve_batch", "hb_mpc_cold_start_batch", "hb_mpc_solve_batch", "hb_control_step_batch",
     "hb_rbd_to_centroidal_batch", "hb_reference_expand_batch", "hb_probe_flow_map",
+    "hb_time_grid_batch_dev", "hb_reference_expand_grid_batch_dev", "hb_mpc_solve_grid_batch_dev", "hb_policy_eval_grid_batch_dev",
+    "hb_time_grid_batch", "hb_reference_expand_grid_batch", "hb_mpc_solve_grid_batch", "hb_resident_read_grid_batch",
 ]
 
 
 class HbConfig(C.Structure):
     _fields_ = [("horizon_N", C.c_int32), ("dt", C.c_double), ("max_batch", C.c_int32), ("wbc_rho", C.c_double),
-                ("qp_max_iter", C.c_int32), ("line_search_max_trials", C.c_int32)]
+                ("qp_max_iter", C.c_int32), ("line_search_max_trials", C.c_int32), ("time_horizon", C.c_double), ("event_nodes", C.c_int32)]
 
 
 class HbSolveInfo(C.Structure):
@@ -206,12 +208,14 @@ def _f64(a):
 class Context:
     """Owner of one hb_ctx (one GPU, one stream). Single-owner: use it from one thread at a time."""
 
-    def __init__(self, horizon_N=100, dt=0.01, max_batch=1024, device=0, wbc_rho=1e-8, qp_max_iter=40, line_search_max_trials=14):
+    def __init__(self, horizon_N=100, dt=0.01, max_batch=1024, device=0, wbc_rho=1e-8, qp_max_iter=40, line_search_max_trials=14, time_horizon=0.0,
+                 event_nodes=False):
         lib = load_library()
         cfg = HbConfig()
         _check(lib.hb_default_config(C.byref(cfg)), "hb_default_config")
         cfg.horizon_N, cfg.dt, cfg.max_batch, cfg.wbc_rho = horizon_N, dt, max_batch, wbc_rho
         cfg.qp_max_iter, cfg.line_search_max_trials = qp_max_iter, line_search_max_trials
+        cfg.time_horizon, cfg.event_nodes = float(time_horizon), 1 if event_nodes else 0
         self.cfg = cfg
         self.N, self.dt, self.max_batch, self.device = horizon_N, dt, max_batch, device
         self._h = C.c_void_p()
@@ -294,6 +298,35 @@ class Context:
         info = np.zeros(B, dtype=INFO_DTYPE)
         _check(self._lib.hb_mpc_solve_batch(self._h, B, _ptr(x0), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(xt), _ptr(ut), _ptr(info)), "hb_mpc_solve_batch", self._h)
         return xt, ut, info
+
+    def time_grid(self, t0, refs):
+        """Event-node time discretisation (row S1): returns (node_times [B, N+1], n_intervals [B], status [B])."""
+        t0 = _f64(t0); B = t0.shape[0]
+        tk = np.zeros((B, self.N + 1)); nn = np.zeros(B, dtype=np.int32); st = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_time_grid_batch(self._h, B, _ptr(t0), C.cast(refs, C.c_void_p), _ptr(tk), _ptr(nn), _ptr(st)), "hb_time_grid_batch", self._h)
+        return tk, nn, st
+
+    def reference_expand_grid(self, node_times, refs):
+        tk = _f64(node_times); B = tk.shape[0]
+        x_ref = np.zeros((B, self.N + 1, NX)); swing = np.zeros((B, self.N + 1, 24)); mode = np.zeros((B, self.N + 1), dtype=np.int32)
+        _check(self._lib.hb_reference_expand_grid_batch(self._h, B, _ptr(tk), C.cast(refs, C.c_void_p), _ptr(x_ref), _ptr(swing), _ptr(mode)),
+               "hb_reference_expand_grid_batch", self._h)
+        return x_ref, swing, mode
+
+    def mpc_solve_grid(self, x0, node_times, n_intervals, x_ref, swing, mode, xt, ut):
+        x0, tk, x_ref, swing = map(_f64, (x0, node_times, x_ref, swing))
+        B = x0.shape[0]
+        nn = np.ascontiguousarray(n_intervals, dtype=np.int32); mode = np.ascontiguousarray(mode, dtype=np.int32)
+        xt = _f64(xt).copy(); ut = _f64(ut).copy()
+        info = np.zeros(B, dtype=INFO_DTYPE)
+        _check(self._lib.hb_mpc_solve_grid_batch(self._h, B, _ptr(x0), _ptr(tk), _ptr(nn), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(xt), _ptr(ut), _ptr(info)),
+               "hb_mpc_solve_grid_batch", self._h)
+        return xt, ut, info
+
+    def resident_read_grid(self, B):
+        tk = np.zeros((B, self.N + 1)); nn = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_resident_read_grid_batch(self._h, B, _ptr(tk), _ptr(nn)), "hb_resident_read_grid_batch", self._h)
+        return tk, nn
 
     def control_step(self, t_rel, x0, x_ref, swing, mode, rbd, xt, ut):
         x0, x_ref, swing, rbd = map(_f64, (x0, x_ref, swing, rbd))

@@ -150,47 +150,66 @@ __global__ void cold_start_kernel(int B, int N, const double* x0, const int32_t*
   }
 }
 
+// index k of the interval [tk[k], tk[k+1]) of a grid with n intervals that holds t (clamped to 0 .. n-1), and the interpolation weight
+__device__ __forceinline__ int grid_interval(const double* tk, int n, double t, double& al) {
+  int lo = 0, hi = n;                     // invariant: tk[lo] <= t (or lo == 0), tk[hi] > t (or hi == n)
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tk[mid] <= t) lo = mid; else hi = mid; }
+  const double d = tk[lo + 1] - tk[lo];
+  double a = d > 0.0 ? (t - tk[lo]) / d : 0.0;
+  al = a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a);
+  return lo;
+}
+
 // Warm start of the next solve from the resident primal solution (ocs2::SqpSolver::initializeStateInputTrajectories; mpc.coldStart
 // false, task.info:146): x[0] = measured state; interval i takes u[i] = previous input at t_i and x[i+1] = previous state at t_{i+1}
 // while t_{i+1} lies inside the previous horizon, otherwise the initializer (weight-compensating input, state kept,
 // LeggedRobotInitializer.cpp:67-77). One block per instance; the previous trajectories are staged in shared memory so that the
-// update can be done in place.
+// update can be done in place. With event-node grids (tk_new != null) both the previous and the new node times are arbitrary:
+// tk_res / nn_res hold the previous grid and are replaced by the new one at the end.
 __global__ void __launch_bounds__(128) warm_shift_kernel(int B, int N, double dt, const double* t0_new, double* t0_res, const double* x0,
-                                                          const int32_t* mode, double* xt, double* ut) {
+                                                          const int32_t* mode, double* xt, double* ut, const double* tk_new, const int32_t* nn_new,
+                                                          double* tk_res, int32_t* nn_res) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* px = reinterpret_cast<double*>(smem_raw);
   double* pu = px + (size_t)(N + 1) * NX;
+  __shared__ double ptk[HB_MAX_HORIZON + 1];
   const int inst = blockIdx.x;
+  const bool grid = tk_new != nullptr;
   double* x = xt + (size_t)inst * (N + 1) * NX; double* u = ut + (size_t)inst * N * NU;
   for (int i = threadIdx.x; i < (N + 1) * NX; i += blockDim.x) px[i] = x[i];
   for (int i = threadIdx.x; i < N * NU; i += blockDim.x) pu[i] = u[i];
+  const int np = grid ? nn_res[inst] : N;                        // intervals of the previous grid
+  const int nw = grid ? nn_new[inst] : N;                        // intervals of the new grid
+  const double* tn_ = grid ? tk_new + (size_t)inst * (N + 1) : nullptr;
+  if (grid) for (int i = threadIdx.x; i <= N; i += blockDim.x) ptk[i] = tk_res[(size_t)inst * (N + 1) + i];
   __syncthreads();
-  const double tp = t0_res[inst], tn = t0_new[inst], t_end = tp + N * dt;
-  auto prev_state = [&](double t, int j) {
+  const double tp = grid ? ptk[0] : t0_res[inst], tn = t0_new[inst], t_end = grid ? ptk[np] : tp + N * dt;
+  auto new_time = [&](int k) { return grid ? tn_[k < nw ? k : nw] : tn + k * dt; };
+  auto locate = [&](double t, double& al) {
+    if (grid) return grid_interval(ptk, np, t, al);
     double s = (t - tp) / dt; s = s < 0.0 ? 0.0 : (s > (double)N ? (double)N : s);
     int k = (int)floor(s); if (k >= N) k = N - 1;
-    const double al = s - k;
-    return (1.0 - al) * px[k * NX + j] + al * px[(k + 1) * NX + j];
+    al = s - k;
+    return k;
   };
+  auto prev_state = [&](double t, int j) { double al; const int k = locate(t, al); return (1.0 - al) * px[k * NX + j] + al * px[(k + 1) * NX + j]; };
   auto prev_input = [&](double t, int j) {
-    double s = (t - tp) / dt; s = s < 0.0 ? 0.0 : (s > (double)N ? (double)N : s);
-    int k = (int)floor(s); if (k >= N) k = N - 1;
-    const double al = s - k;
-    const int k1 = (k + 1 < N) ? k + 1 : N - 1;
+    double al; const int k = locate(t, al);
+    const int k1 = (k + 1 < np) ? k + 1 : np - 1;
     return (1.0 - al) * pu[k * NU + j] + al * pu[k1 * NU + j];
   };
   // first interval that falls back to the initializer: smallest i with t_{i+1} > t_end (1e-9 guards the grid-aligned case)
-  int istar = N;
-  for (int i = 0; i < N; ++i) if (tn + (i + 1) * dt > t_end + 1e-9) { istar = i; break; }
+  int istar = nw;
+  for (int i = 0; i < nw; ++i) if (new_time(i + 1) > t_end + 1e-9) { istar = i; break; }
   for (int idx = threadIdx.x; idx < (N + 1) * NX; idx += blockDim.x) {
     const int k = idx / NX, j = idx - k * NX;
     const int ks = k <= istar ? k : istar;                 // the initializer keeps the state of node istar
-    x[idx] = (ks == 0) ? x0[(size_t)inst * NX + j] : prev_state(tn + ks * dt, j);
+    x[idx] = (ks == 0) ? x0[(size_t)inst * NX + j] : prev_state(new_time(ks), j);
   }
   for (int idx = threadIdx.x; idx < N * NU; idx += blockDim.x) {
     const int k = idx / NU, j = idx - k * NU;
     double v;
-    if (k < istar) v = prev_input(tn + k * dt, j);
+    if (k < istar) v = prev_input(new_time(k), j);
     else {
       const int md = mode[(size_t)inst * (N + 1) + k];
       int ns = 0;
@@ -199,27 +218,37 @@ __global__ void __launch_bounds__(128) warm_shift_kernel(int B, int N, double dt
     }
     u[idx] = v;
   }
-  if (threadIdx.x == 0) t0_res[inst] = tn;
+  __syncthreads();
+  if (threadIdx.x == 0) { t0_res[inst] = tn; if (grid) nn_res[inst] = nw; }
+  if (grid) for (int i = threadIdx.x; i <= N; i += blockDim.x) tk_res[(size_t)inst * (N + 1) + i] = tn_[i];
 }
 
 // MPC_MRT_Interface::evaluatePolicy with the feed-forward policy (LeggedController.cpp:154-156, task.info:93):
 // linear interpolation of the state / input trajectories at t0 + t_rel; mode = mode in force at that time.
 __global__ void policy_eval_kernel(int B, int N, double dt, double t_rel, const double* xt, const double* ut, const int32_t* mode, double* x_des,
-                                   double* u_des, int32_t* mode_out) {
+                                   double* u_des, int32_t* mode_out, const double* tk, const int32_t* nn) {
   const int inst = blockIdx.x * blockDim.x / 32 + (threadIdx.x >> 5);
   if (inst >= B) return;
   const int lane = threadIdx.x & 31;
-  double s = t_rel / dt;
-  if (s < 0.0) s = 0.0;
-  if (s > (double)N) s = (double)N;
-  int k = (int)floor(s);
-  if (k >= N) k = N - 1;
-  const double al = s - k;
+  int k, na = N;
+  double al;
+  if (tk) {      // event-node grid: node times of this instance
+    const double* t = tk + (size_t)inst * (N + 1);
+    na = nn[inst];
+    k = grid_interval(t, na, t[0] + t_rel, al);
+  } else {
+    double s = t_rel / dt;
+    if (s < 0.0) s = 0.0;
+    if (s > (double)N) s = (double)N;
+    k = (int)floor(s);
+    if (k >= N) k = N - 1;
+    al = s - k;
+  }
   const double* x = xt + (size_t)inst * (N + 1) * NX;
   const double* u = ut + (size_t)inst * N * NU;
   if (lane < NX) {
     x_des[(size_t)inst * NX + lane] = (1.0 - al) * x[k * NX + lane] + al * x[(k + 1) * NX + lane];
-    const int k1 = (k + 1 < N) ? k + 1 : N - 1;   // the input trajectory repeats its last sample at the final node
+    const int k1 = (k + 1 < na) ? k + 1 : na - 1;   // the input trajectory repeats its last sample at the final node
     u_des[(size_t)inst * NU + lane] = (1.0 - al) * u[k * NU + lane] + al * u[k1 * NU + lane];
   }
   if (lane == 0 && mode_out) mode_out[inst] = mode[(size_t)inst * (N + 1) + k];
@@ -428,15 +457,48 @@ __global__ void rbd_to_centroidal_kernel(int B, const double* rbd, double* x) {
 // Expansion of the compact reference description onto the node grid (SwitchedModelReferenceManager::modifyReferences
 // products evaluated where the solver needs them: TargetTrajectories::getDesiredState, ModeSchedule::modeAtTime,
 // SwingTrajectoryPlanner::get{X,Y,Z}{position,velocity}Constraint; CubicSpline.cpp:46-124).
+// Time discretisation with event nodes (row S1; ocs2::timeDiscretizationWithEvents as SqpSolver::run calls it): nodes step by dt from the
+// initial time; a step that would pass a mode-switch time lands on it instead (the pre-event interval is shortened) and the grid
+// re-anchors there; the last node is the final time; nodes closer than dt_min to their predecessor replace it. OCS2's duplicated
+// pre- / post-event node pair (identity jump map, no cost, no constraint on it) is collapsed into one node that carries the post-event
+// mode. One thread per instance; nn[inst] = number of intervals (<= N, the capacity); status 1 = capacity exhausted (last interval stretched).
+__global__ void time_grid_kernel(int B, int N, double dt, double T, const double* t0, const hb_reference* refs, double* tk, int32_t* nn, int32_t* status) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= B) return;
+  const hb_reference& rf = refs[inst];
+  const int nev = min(max(rf.n_events, 0), HB_MAX_EVENTS);
+  double* t = tk + (size_t)inst * (N + 1);
+  const double ti = t0[inst], tf = ti + T, dt_min = 1e-9;
+  int ei = 0;
+  while (ei < nev && rf.event_times[ei] <= ti + 1e-9) ++ei;      // switches at (or before) the initial time are in force already
+  int n = 0, st = 0;
+  double cur = ti;
+  t[0] = ti;
+  while (cur < tf) {
+    double nx = cur + dt;
+    if (ei < nev && nx >= rf.event_times[ei]) { nx = rf.event_times[ei]; ++ei; }
+    if (nx >= tf) nx = tf;
+    if (nx > cur + dt_min || n == 0) {
+      if (n == N) { t[N] = tf; st = 1; break; }
+      ++n;
+    }
+    t[n] = nx;
+    cur = nx;
+  }
+  for (int k = n + 1; k <= N; ++k) t[k] = t[n];
+  nn[inst] = n;
+  if (status) status[inst] = st;
+}
+
 __global__ void reference_expand_kernel(int B, int N, double dt, const double* t0, const hb_reference* refs, double* x_ref, double* swing,
-                                        int32_t* mode) {
+                                        int32_t* mode, const double* tk) {
   const int inst = blockIdx.x;
   const hb_reference& rf = refs[inst];
   // counts are clamped to the capacities of hb_reference: a malformed struct cannot index out of bounds (the host-pointer entry
   // points reject it with HB_EINVAL before it gets here; device-pointer callers own their data)
   const int n_events = min(max(rf.n_events, 0), HB_MAX_EVENTS), n_targets = min(max(rf.n_targets, 1), HB_MAX_TARGETS);
   for (int k = threadIdx.x; k <= N; k += blockDim.x) {
-    const double t = t0[inst] + k * dt;
+    const double t = tk ? tk[(size_t)inst * (N + 1) + k] : t0[inst] + k * dt;
     // mode in force on the interval starting at t (post-event mode when t coincides with an event)
     int idx = 0;
     while (idx < n_events && rf.event_times[idx] <= t + 1e-9) ++idx;
@@ -616,6 +678,7 @@ struct hb_ctx {
   // staging for host-pointer calls
   double *s_x0, *s_xref, *s_swing, *s_xt, *s_ut, *s_rbd, *s_xd, *s_ud, *s_sol, *s_tau, *s_t0, *s_misc;
   double *res_xt = nullptr, *res_ut = nullptr, *res_t0 = nullptr;   // resident primal solution (hb_resident_cycle_batch)
+  double *s_tk = nullptr, *res_tk = nullptr; int32_t *s_nn = nullptr, *res_nn = nullptr;   // node times / interval counts (event-node grids)
   int res_valid = 0;                                                // number of instances holding a previous solution
   hb_plan_input* s_plan = nullptr; double* res_stance = nullptr; int32_t* s_pstatus = nullptr;   // device planner (row N1)
   double* res_sol = nullptr; int res_sol_valid = 0;   // last good WBC solution per instance (WeightedWbc fallback, W5)
@@ -690,6 +753,8 @@ int hb_default_config(hb_config* cfg) {
   cfg->wbc_rho = 1e-8;
   cfg->qp_max_iter = 40;
   cfg->line_search_max_trials = 14;
+  cfg->time_horizon = 0.0;
+  cfg->event_nodes = 0;
   return HB_OK;
 }
 
@@ -707,7 +772,7 @@ const char* hb_strerror(int code) {
 
 int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   // horizon cap: the warm shift stages one instance's previous trajectories in shared memory ((2N+1) x 22 doubles <= 227 KB)
-  if (!cfg || !out || cfg->horizon_N < 1 || cfg->horizon_N > HB_MAX_HORIZON || cfg->max_batch < 1 || !(cfg->dt > 0.0)) return HB_EINVAL;
+  if (!cfg || !out || cfg->horizon_N < 1 || cfg->horizon_N > HB_MAX_HORIZON || cfg->max_batch < 1 || !(cfg->dt > 0.0) || cfg->time_horizon < 0.0) return HB_EINVAL;
   hb_ctx* ctx = new (std::nothrow) hb_ctx();
   if (!ctx) return HB_ENOMEM;
   memset(ctx, 0, sizeof(*ctx));
@@ -749,7 +814,8 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   if (e != cudaSuccess) { ctx->last_cuda = (int)e; hb_destroy(ctx); return HB_ECUDA; }
   const size_t B = cfg->max_batch, N = cfg->horizon_N;
   bool ok = true;
-  ok = ok && dalloc(&ctx->lin, B * N * LIN_STRIDE) == cudaSuccess && dalloc(&ctx->proj, B * N * PJ_STRIDE) == cudaSuccess && dalloc(&ctx->rk, B * N * RK_STRIDE) == cudaSuccess;
+  // the node records of the SQP pipeline (31 KB per instance and interval) are allocated by the first MPC solve: contexts that only run the
+  // WBC / QP / planner / estimator entry points never pay for them
   ok = ok && dalloc(&ctx->dxt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->dut, B * N * NU) == cudaSuccess;
   ok = ok && dalloc(&ctx->perf, B * 4) == cudaSuccess && dalloc(&ctx->flags, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->xdes, B * NX) == cudaSuccess && dalloc(&ctx->udes, B * NU) == cudaSuccess && dalloc(&ctx->wsol, B * NWBC) == cudaSuccess;
@@ -758,6 +824,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   ok = ok && dalloc(&ctx->s_kf, B) == cudaSuccess && dalloc(&ctx->res_sol, B * NWBC) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_plan, B) == cudaSuccess && dalloc(&ctx->res_stance, B * 12) == cudaSuccess && dalloc(&ctx->s_pstatus, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->res_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->res_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->res_t0, B) == cudaSuccess;
+  ok = ok && dalloc(&ctx->s_tk, B * (N + 1)) == cudaSuccess && dalloc(&ctx->res_tk, B * (N + 1)) == cudaSuccess && dalloc(&ctx->s_nn, B) == cudaSuccess && dalloc(&ctx->res_nn, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->s_rbd, B * 32) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_xd, B * NX) == cudaSuccess && dalloc(&ctx->s_ud, B * NU) == cudaSuccess && dalloc(&ctx->s_sol, B * NWBC) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_tau, B * NJ) == cudaSuccess && dalloc(&ctx->s_t0, B) == cudaSuccess && dalloc(&ctx->s_misc, B * (size_t)(NX + 2 * TS + 24 + 36 * NX)) == cudaSuccess;
@@ -787,7 +854,7 @@ int hb_destroy(hb_ctx* ctx) {
   void* ptrs[] = {ctx->lin, ctx->proj, ctx->rk, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->xdes, ctx->udes,
                   ctx->wsol, ctx->wstatus, ctx->witers, ctx->wmode, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_xt, ctx->s_ut, ctx->s_rbd, ctx->s_xd,
                   ctx->s_ud, ctx->s_sol, ctx->s_tau, ctx->s_t0, ctx->s_misc, ctx->s_mode, ctx->s_imode, ctx->s_status, ctx->s_iters, ctx->s_stance,
-                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf, ctx->res_sol};
+                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf, ctx->res_sol, ctx->s_tk, ctx->res_tk, ctx->s_nn, ctx->res_nn};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
   if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
@@ -910,13 +977,24 @@ int hb_mpc_cold_start_batch_dev(hb_ctx* ctx, int B, const double* x0, const int3
   return HB_OK;
 }
 
-int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
-                           double* x_traj, double* u_traj, hb_solve_info* info) {
-  if (!ctx || B < 0 || !x0 || !x_ref || !swing_ref || !mode || !x_traj || !u_traj) return HB_EINVAL;
+static int mpc_solve_impl(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
+                          double* x_traj, double* u_traj, hb_solve_info* info, const double* tk, const int32_t* nn) {
+  if (!ctx || B < 0 || !x0 || !x_ref || !swing_ref || !mode || !x_traj || !u_traj || ((tk == nullptr) != (nn == nullptr))) return HB_EINVAL;
   if (B == 0) return HB_OK;
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (set_device(ctx)) return HB_ECUDA;
+  if (!ctx->lin) {
+    const size_t Bc = ctx->cfg.max_batch, Nc = ctx->cfg.horizon_N;
+    if (dalloc(&ctx->lin, Bc * Nc * LIN_STRIDE) != cudaSuccess || dalloc(&ctx->proj, Bc * Nc * PJ_STRIDE) != cudaSuccess || dalloc(&ctx->rk, Bc * Nc * RK_STRIDE) != cudaSuccess) {
+      cudaGetLastError();
+      if (ctx->lin) cudaFree(ctx->lin);
+      if (ctx->proj) cudaFree(ctx->proj);
+      ctx->lin = ctx->proj = ctx->rk = nullptr;
+      return HB_ENOMEM;
+    }
+  }
   SqpArgs a;
+  a.tk = tk; a.nn = nn;
   a.B = B; a.N = ctx->cfg.horizon_N; a.dt = ctx->cfg.dt; a.x_ref = x_ref; a.swing = swing_ref; a.mode = mode; a.xt = x_traj; a.ut = u_traj;
   {
     const size_t o = (size_t)ctx->base, Nn = (size_t)ctx->cfg.horizon_N;
@@ -948,27 +1026,61 @@ int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x
   return HB_OK;
 }
 
-int hb_policy_eval_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x_traj, const double* u_traj, const int32_t* mode, double* x_des,
-                             double* u_des, int32_t* mode_out) {
-  if (!ctx || B < 0 || !x_traj || !u_traj || !mode || !x_des || !u_des) return HB_EINVAL;
+int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
+                           double* x_traj, double* u_traj, hb_solve_info* info) {
+  return mpc_solve_impl(ctx, B, x0, x_ref, swing_ref, mode, x_traj, u_traj, info, nullptr, nullptr);
+}
+
+int hb_mpc_solve_grid_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* node_times, const int32_t* n_intervals, const double* x_ref,
+                                const double* swing_ref, const int32_t* mode, double* x_traj, double* u_traj, hb_solve_info* info) {
+  if (!node_times || !n_intervals) return HB_EINVAL;
+  return mpc_solve_impl(ctx, B, x0, x_ref, swing_ref, mode, x_traj, u_traj, info, node_times, n_intervals);
+}
+
+static int policy_eval_impl(hb_ctx* ctx, int B, double t_rel, const double* x_traj, const double* u_traj, const int32_t* mode, double* x_des,
+                            double* u_des, int32_t* mode_out, const double* tk, const int32_t* nn) {
+  if (!ctx || B < 0 || !x_traj || !u_traj || !mode || !x_des || !u_des || ((tk == nullptr) != (nn == nullptr))) return HB_EINVAL;
   if (B == 0) return HB_OK;
   if (set_device(ctx)) return HB_ECUDA;
   const int wpb = 4;
-  policy_eval_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, 0, ctx->stream>>>(B, ctx->cfg.horizon_N, ctx->cfg.dt, t_rel, x_traj, u_traj, mode, x_des, u_des, mode_out);
+  policy_eval_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, 0, ctx->stream>>>(B, ctx->cfg.horizon_N, ctx->cfg.dt, t_rel, x_traj, u_traj, mode, x_des, u_des, mode_out,
+                                                                         tk, nn);
   ctx->launches++;
   CK(cudaGetLastError());
   return HB_OK;
 }
 
-int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
-                              const double* rbd, double* x_traj, double* u_traj, hb_solve_info* info, double* wbc_sol, double* torque,
-                              int32_t* wbc_status) {
+int hb_policy_eval_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x_traj, const double* u_traj, const int32_t* mode, double* x_des,
+                             double* u_des, int32_t* mode_out) {
+  return policy_eval_impl(ctx, B, t_rel, x_traj, u_traj, mode, x_des, u_des, mode_out, nullptr, nullptr);
+}
+
+int hb_policy_eval_grid_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* node_times, const int32_t* n_intervals, const double* x_traj,
+                                  const double* u_traj, const int32_t* mode, double* x_des, double* u_des, int32_t* mode_out) {
+  if (!node_times || !n_intervals) return HB_EINVAL;
+  return policy_eval_impl(ctx, B, t_rel, x_traj, u_traj, mode, x_des, u_des, mode_out, node_times, n_intervals);
+}
+
+int hb_time_grid_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* node_times, int32_t* n_intervals, int32_t* status) {
+  if (!ctx || B < 0 || !t0 || !refs || !node_times || !n_intervals) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  const double T = ctx->cfg.time_horizon > 0.0 ? ctx->cfg.time_horizon : ctx->cfg.horizon_N * ctx->cfg.dt;
+  time_grid_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, ctx->cfg.horizon_N, ctx->cfg.dt, T, t0, refs, node_times, n_intervals, status);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+static int control_step_impl(hb_ctx* ctx, int B, double t_rel, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
+                             const double* rbd, double* x_traj, double* u_traj, hb_solve_info* info, double* wbc_sol, double* torque,
+                             int32_t* wbc_status, const double* tk, const int32_t* nn) {
   if (!ctx || !rbd || !wbc_sol) return HB_EINVAL;
-  int rc = hb_mpc_solve_batch_dev(ctx, B, x0, x_ref, swing_ref, mode, x_traj, u_traj, info);
+  int rc = mpc_solve_impl(ctx, B, x0, x_ref, swing_ref, mode, x_traj, u_traj, info, tk, nn);
   if (rc) return rc;
   if (B == 0) return HB_OK;
   double* xdes = ctx->xdes + (size_t)ctx->base * NX; double* udes = ctx->udes + (size_t)ctx->base * NU; int32_t* wmode = ctx->wmode + ctx->base;
-  rc = hb_policy_eval_batch_dev(ctx, B, t_rel, x_traj, u_traj, mode, xdes, udes, wmode);
+  rc = policy_eval_impl(ctx, B, t_rel, x_traj, u_traj, mode, xdes, udes, wmode, tk, nn);
   if (rc) return rc;
   rc = hb_wbc_solve_batch_dev(ctx, B, xdes, udes, rbd, wmode, nullptr, wbc_sol, wbc_status);
   if (rc) return rc;
@@ -978,6 +1090,12 @@ int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0
     CK(cudaGetLastError());
   }
   return HB_OK;
+}
+
+int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
+                              const double* rbd, double* x_traj, double* u_traj, hb_solve_info* info, double* wbc_sol, double* torque,
+                              int32_t* wbc_status) {
+  return control_step_impl(ctx, B, t_rel, x0, x_ref, swing_ref, mode, rbd, x_traj, u_traj, info, wbc_sol, torque, wbc_status, nullptr, nullptr);
 }
 
 // WeightedWbc::update fallback (WeightedWbc.cpp:57-64): a QP that did not solve returns the previous solution of that instance; a solved
@@ -996,9 +1114,15 @@ __global__ void wbc_fallback_kernel(int B, int have_prev, const int32_t* status,
 }
 
 // store the solve time of a cold-started resident solution
-__global__ void set_times_kernel(int B, const double* t0_new, double* t0_res) {
+__global__ void set_times_kernel(int B, int N, const double* t0_new, double* t0_res, const double* tk_new, const int32_t* nn_new, double* tk_res,
+                                 int32_t* nn_res) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B) t0_res[i] = t0_new[i];
+  if (i >= B) return;
+  t0_res[i] = t0_new[i];
+  if (tk_new) {
+    nn_res[i] = nn_new[i];
+    for (int k = 0; k <= N; ++k) tk_res[(size_t)i * (N + 1) + k] = tk_new[(size_t)i * (N + 1) + k];
+  }
 }
 
 int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0, const hb_reference* refs,
@@ -1011,20 +1135,31 @@ int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel
   const size_t N = ctx->cfg.horizon_N, o = (size_t)ctx->base;
   double* xref = ctx->s_xref + o * (N + 1) * NX; double* swing = ctx->s_swing + o * (N + 1) * 24; int32_t* mode = ctx->s_mode + o * (N + 1);
   double* xt = ctx->res_xt + o * (N + 1) * NX; double* ut = ctx->res_ut + o * N * NU; double* tres = ctx->res_t0 + o;
-  int rc = hb_reference_expand_batch_dev(ctx, B, t0, refs, xref, swing, mode);
+  // event-node grids (cfg.event_nodes): per-instance node times, kept resident beside the primal solution
+  const bool grid = ctx->cfg.event_nodes != 0;
+  double* tk = grid ? ctx->s_tk + o * (N + 1) : nullptr; int32_t* nn = grid ? ctx->s_nn + o : nullptr;
+  double* tkres = grid ? ctx->res_tk + o * (N + 1) : nullptr; int32_t* nnres = grid ? ctx->res_nn + o : nullptr;
+  int rc = HB_OK;
+  if (grid) {
+    rc = hb_time_grid_batch_dev(ctx, B, t0, refs, tk, nn, nullptr);
+    if (rc) return rc;
+    rc = hb_reference_expand_grid_batch_dev(ctx, B, tk, refs, xref, swing, mode);
+  } else {
+    rc = hb_reference_expand_batch_dev(ctx, B, t0, refs, xref, swing, mode);
+  }
   if (rc) return rc;
   if (cold_start) {
     rc = hb_mpc_cold_start_batch_dev(ctx, B, x0, mode, xt, ut);
     if (rc) return rc;
-    set_times_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, t0, tres);
+    set_times_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(B, (int)N, t0, tres, tk, nn, tkres, nnres);
   } else {
     const size_t smem = sizeof(double) * ((N + 1) * NX + N * NU);     // opted in at hb_create
-    warm_shift_kernel<<<B, 128, smem, ctx->stream>>>(B, (int)N, ctx->cfg.dt, t0, tres, x0, mode, xt, ut);
+    warm_shift_kernel<<<B, 128, smem, ctx->stream>>>(B, (int)N, ctx->cfg.dt, t0, tres, x0, mode, xt, ut, tk, nn, tkres, nnres);
   }
   ctx->launches++;
   CK(cudaGetLastError());
   if (ctx->res_valid < ctx->base + B) ctx->res_valid = ctx->base + B;
-  rc = hb_control_step_batch_dev(ctx, B, t_rel, x0, xref, swing, mode, rbd, xt, ut, info, wbc_sol, torque, wbc_status);
+  rc = control_step_impl(ctx, B, t_rel, x0, xref, swing, mode, rbd, xt, ut, info, wbc_sol, torque, wbc_status, tk, nn);
   if (rc) return rc;
   if (wbc_status) {
     const int have_prev = (!cold_start && ctx->res_sol_valid >= ctx->base + B) ? 1 : 0;
@@ -1113,7 +1248,18 @@ int hb_reference_expand_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb
   if (!ctx || B < 0 || !t0 || !refs || !x_ref || !swing_ref || !mode) return HB_EINVAL;
   if (B == 0) return HB_OK;
   if (set_device(ctx)) return HB_ECUDA;
-  reference_expand_kernel<<<B, 128, 0, ctx->stream>>>(B, ctx->cfg.horizon_N, ctx->cfg.dt, t0, refs, x_ref, swing_ref, mode);
+  reference_expand_kernel<<<B, 128, 0, ctx->stream>>>(B, ctx->cfg.horizon_N, ctx->cfg.dt, t0, refs, x_ref, swing_ref, mode, nullptr);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_reference_expand_grid_batch_dev(hb_ctx* ctx, int B, const double* node_times, const hb_reference* refs, double* x_ref, double* swing_ref,
+                                       int32_t* mode) {
+  if (!ctx || B < 0 || !node_times || !refs || !x_ref || !swing_ref || !mode) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  reference_expand_kernel<<<B, 128, 0, ctx->stream>>>(B, ctx->cfg.horizon_N, ctx->cfg.dt, nullptr, refs, x_ref, swing_ref, mode, node_times);
   ctx->launches++;
   CK(cudaGetLastError());
   return HB_OK;
@@ -1237,6 +1383,69 @@ int hb_mpc_solve_batch(hb_ctx* ctx, int B, const double* x0, const double* x_ref
   if (rc) return rc;
   D2H(x_traj, ctx->s_xt, sizeof(double) * B * (N + 1) * NX); D2H(u_traj, ctx->s_ut, sizeof(double) * B * N * NU);
   if (info) D2H(info, ctx->s_info, sizeof(hb_solve_info) * B);
+  return hb_sync(ctx);
+}
+
+int hb_mpc_solve_grid_batch(hb_ctx* ctx, int B, const double* x0, const double* node_times, const int32_t* n_intervals, const double* x_ref,
+                            const double* swing_ref, const int32_t* mode, double* x_traj, double* u_traj, hb_solve_info* info) {
+  if (!ctx || B < 0 || !x0 || !node_times || !n_intervals || !x_ref || !swing_ref || !mode || !x_traj || !u_traj) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  const size_t N = ctx->cfg.horizon_N;
+  for (int i = 0; i < B; ++i) {      // a grid the kernels can walk: 1 <= n <= N intervals of positive length
+    if (n_intervals[i] < 1 || n_intervals[i] > (int)N) return HB_EINVAL;
+    for (int k = 0; k < n_intervals[i]; ++k) if (!(node_times[(size_t)i * (N + 1) + k + 1] > node_times[(size_t)i * (N + 1) + k])) return HB_EINVAL;
+  }
+  if (set_device(ctx)) return HB_ECUDA;
+  H2D(ctx->s_x0, x0, sizeof(double) * B * NX); H2D(ctx->s_xref, x_ref, sizeof(double) * B * (N + 1) * NX);
+  H2D(ctx->s_swing, swing_ref, sizeof(double) * B * (N + 1) * 24); H2D(ctx->s_mode, mode, sizeof(int32_t) * B * (N + 1));
+  H2D(ctx->s_xt, x_traj, sizeof(double) * B * (N + 1) * NX); H2D(ctx->s_ut, u_traj, sizeof(double) * B * N * NU);
+  H2D(ctx->s_tk, node_times, sizeof(double) * B * (N + 1)); H2D(ctx->s_nn, n_intervals, sizeof(int32_t) * B);
+  int rc = hb_mpc_solve_grid_batch_dev(ctx, B, ctx->s_x0, ctx->s_tk, ctx->s_nn, ctx->s_xref, ctx->s_swing, ctx->s_mode, ctx->s_xt, ctx->s_ut, ctx->s_info);
+  if (rc) return rc;
+  D2H(x_traj, ctx->s_xt, sizeof(double) * B * (N + 1) * NX); D2H(u_traj, ctx->s_ut, sizeof(double) * B * N * NU);
+  if (info) D2H(info, ctx->s_info, sizeof(hb_solve_info) * B);
+  return hb_sync(ctx);
+}
+
+int hb_time_grid_batch(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* node_times, int32_t* n_intervals, int32_t* status) {
+  if (!ctx || B < 0 || !t0 || !refs || !node_times || !n_intervals) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (!references_valid(B, refs)) return HB_EINVAL;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t N = ctx->cfg.horizon_N;
+  H2D(ctx->s_t0, t0, sizeof(double) * B); H2D(ctx->s_refs, refs, sizeof(hb_reference) * B);
+  int rc = hb_time_grid_batch_dev(ctx, B, ctx->s_t0, ctx->s_refs, ctx->s_tk, ctx->s_nn, ctx->s_pstatus);
+  if (rc) return rc;
+  D2H(node_times, ctx->s_tk, sizeof(double) * B * (N + 1)); D2H(n_intervals, ctx->s_nn, sizeof(int32_t) * B);
+  if (status) D2H(status, ctx->s_pstatus, sizeof(int32_t) * B);
+  return hb_sync(ctx);
+}
+
+int hb_reference_expand_grid_batch(hb_ctx* ctx, int B, const double* node_times, const hb_reference* refs, double* x_ref, double* swing_ref,
+                                   int32_t* mode) {
+  if (!ctx || B < 0 || !node_times || !refs || !x_ref || !swing_ref || !mode) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (!references_valid(B, refs)) return HB_EINVAL;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t N = ctx->cfg.horizon_N;
+  H2D(ctx->s_tk, node_times, sizeof(double) * B * (N + 1)); H2D(ctx->s_refs, refs, sizeof(hb_reference) * B);
+  int rc = hb_reference_expand_grid_batch_dev(ctx, B, ctx->s_tk, ctx->s_refs, ctx->s_xref, ctx->s_swing, ctx->s_mode);
+  if (rc) return rc;
+  D2H(x_ref, ctx->s_xref, sizeof(double) * B * (N + 1) * NX); D2H(swing_ref, ctx->s_swing, sizeof(double) * B * (N + 1) * 24);
+  D2H(mode, ctx->s_mode, sizeof(int32_t) * B * (N + 1));
+  return hb_sync(ctx);
+}
+
+int hb_resident_read_grid_batch(hb_ctx* ctx, int B, double* node_times, int32_t* n_intervals) {
+  if (!ctx || B < 0 || !node_times || !n_intervals) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->res_valid || !ctx->cfg.event_nodes) return HB_EINVAL;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t N = ctx->cfg.horizon_N;
+  D2H(node_times, ctx->res_tk, sizeof(double) * B * (N + 1)); D2H(n_intervals, ctx->res_nn, sizeof(int32_t) * B);
   return hb_sync(ctx);
 }
 

@@ -29,7 +29,7 @@ constexpr int NTMAX = 16;   // free inputs after projection: 3 n_stance + (10 - 
 constexpr int NVMAX = 8;    // null-space columns kept for the velocity rows
 constexpr int PJ_AT = 0, PJ_BT = 484, PJ_BTV = 836, PJ_QT = 858, PJ_PT = 1342, PJ_RT = 1694, PJ_QV = 1950, PJ_RV = 1972,
               PJ_PXV = 1988, PJ_NV = 2208, PJ_PEV = 2288, PJ_META = 2298, PJ_STRIDE = 2320;
-// META: [0] nt, [1] n_stance_force_dims, [2] nv, [3] cost, [4] defect^2, [5] eq^2, [6] overflow flag
+// META: [0] nt, [1] n_stance_force_dims, [2] nv, [3] dt cost, [4] dt defect^2, [5] dt eq^2, [6] overflow flag
 constexpr int RK_STRIDE = NTMAX * NX + NTMAX;  // K (nt x 22, ld 22) + kff
 __host__ __device__ inline int ntp_of(int nt) { return nt <= 6 ? 6 : (nt <= 10 ? 10 : (nt <= 12 ? 12 : 16)); }
 
@@ -261,7 +261,16 @@ struct SqpArgs {
   double* rk;      // B x N x RK_STRIDE
   double* dxt; double* dut; double* perf; int32_t* flags;
   const double* x0;
+  // time discretisation (row S1): node times tk (B x (N+1)) and active interval counts nn (B) of a grid with event nodes; both null =
+  // uniform grid of N intervals of length dt. N stays the capacity (stride) of every per-node array.
+  const double* tk; const int32_t* nn;
 };
+__device__ __forceinline__ int sqp_nn(const SqpArgs& a, int inst) { return a.nn ? a.nn[inst] : a.N; }
+__device__ __forceinline__ double sqp_dt(const SqpArgs& a, int inst, int k) {
+  if (!a.tk) return a.dt;
+  const double* t = a.tk + (size_t)inst * (a.N + 1) + k;
+  return t[1] - t[0];
+}
 
 __global__ void __launch_bounds__(64) lin_kernel(SqpArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -275,16 +284,19 @@ __global__ void __launch_bounds__(64) lin_kernel(SqpArgs a) {
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
   if (w >= (long long)a.B * NP) return;
   const int inst = (int)(w / NP), pr = (int)(w - (long long)inst * NP);
+  const int nn = sqp_nn(a, inst);
+  if (2 * pr >= nn) return;              // both nodes of the pair lie beyond this instance's grid (warp-uniform)
   const int k = 2 * pr + half;
-  const bool act = k < N;
-  const int kk = act ? k : N - 1;
+  const bool act = k < nn;
+  const int kk = act ? k : nn - 1;
   const double* xk = (kk == 0) ? a.x0 + (size_t)inst * NX : a.xt + ((size_t)inst * (N + 1) + kk) * NX;   // node 0 is pinned to the measured state
   const double* uk = a.ut + ((size_t)inst * N + kk) * NU;
   for (int i = hl; i < NX; i += 16) { sh.x[i] = xk[i]; sh.u[i] = uk[i]; }
   __syncwarp();
   double* rec = a.lin + ((size_t)inst * N + kk) * LIN_STRIDE;
   lin_half(sh, cm, sh.x, hl, act, rec + LIN_F1, rec + LIN_A1, rec + LIN_BF1, rec + LIN_BV1, true, rec);
-  for (int i = hl; i < NX; i += 16) sh.x2[i] = sh.x[i] + a.dt * sh.f[i];
+  const double dtk = sqp_dt(a, inst, kk);
+  for (int i = hl; i < NX; i += 16) sh.x2[i] = sh.x[i] + dtk * sh.f[i];
   __syncwarp();
   lin_half(sh, cm, sh.x2, hl, act, rec + LIN_F2, rec + LIN_A2, rec + LIN_BF2, rec + LIN_BV2, false, rec);
 }
@@ -357,7 +369,7 @@ template <int NSW>
 __device__ __forceinline__ void lq_node(LqShared& sh, const SqpArgs& a, int inst, int k, int lane, int mode, double xn_l, double xref_l) {
   constexpr int MR = 12 - 2 * NSW, NP = 2 * NSW, NF = 3 * (4 - NSW), GL = LQ_GL, TL = LQ_TL;
   const int N = a.N;
-  const double dt = a.dt;
+  const double dt = sqp_dt(a, inst, k);
   const Model& md = c_model;
   const double im = 1.0 / md.total_mass;
   double* out = a.proj + ((size_t)inst * N + k) * PJ_STRIDE;
@@ -790,7 +802,7 @@ __device__ __forceinline__ void lq_node(LqShared& sh, const SqpArgs& a, int inst
     }
     out[PJ_BTV + lane] = s;
   }
-  if (lane == 0) { out[PJ_META] = nt; out[PJ_META + 1] = NF; out[PJ_META + 2] = nv; out[PJ_META + 3] = cost; out[PJ_META + 4] = d2; out[PJ_META + 5] = e2; out[PJ_META + 6] = overflow ? 1.0 : 0.0; }
+  if (lane == 0) { out[PJ_META] = nt; out[PJ_META + 1] = NF; out[PJ_META + 2] = nv; out[PJ_META + 3] = dt * cost; out[PJ_META + 4] = dt * d2; out[PJ_META + 5] = dt * e2; out[PJ_META + 6] = overflow ? 1.0 : 0.0; }
 }
 
 #ifndef HB_LQ_MINB
@@ -803,6 +815,7 @@ __global__ void __launch_bounds__(32, HB_LQ_MINB) lq_kernel(SqpArgs a) {
   const int N = a.N;
   const long long w = blockIdx.x;
   const int inst = (int)(w / N), k = (int)(w - (long long)inst * N);
+  if (k >= sqp_nn(a, inst)) return;      // node beyond this instance's grid (event-node grids have per-instance interval counts)
   const double* grec = a.lin + ((size_t)inst * N + k) * LIN_STRIDE;
   const double* xk = (k == 0) ? a.x0 + (size_t)inst * NX : a.xt + ((size_t)inst * (N + 1) + k) * NX;
   // ---- one TMA bulk copy for the record (9568 B) and one each for x, u, the swing references; a single mbarrier collects the bytes
@@ -988,8 +1001,9 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
 __global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RicShared& sh = *reinterpret_cast<RicShared*>(smem_raw);
-  const int inst = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, N = a.N;
-  const double* proj = a.proj + (size_t)inst * N * PJ_STRIDE;
+  const int inst = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* proj = a.proj + (size_t)inst * a.N * PJ_STRIDE;
+  const int N = sqp_nn(a, inst);         // active intervals of this instance; a.N is the stride
   // warp 1 owns the node-input prefetch (and the Qt staging), warp 0 the Pt^T / Rt staging; each waits for its own groups
   if (warp == 1) ric_prefetch(sh.in[(N - 1) & 1], proj + (size_t)(N - 1) * PJ_STRIDE, lane);
   for (int idx = threadIdx.x; idx < TS; idx += 64) sh.S[idx] = 0.0;   // no terminal cost
@@ -998,7 +1012,7 @@ __global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
   double merit = 0.0, dyn = 0.0, eqs = 0.0;
   for (int k = N - 1; k >= 0; --k) {
     const double* rec = proj + (size_t)k * PJ_STRIDE;
-    double* rk = a.rk + ((size_t)inst * N + k) * RK_STRIDE;
+    double* rk = a.rk + ((size_t)inst * a.N + k) * RK_STRIDE;
     if (warp == 1) cp_async_wait<0>();        // inputs of node k (prefetched one node ahead)
     __syncthreads();
     if (warp == 0) {
@@ -1011,7 +1025,7 @@ __global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
     }
     const RicNodeIn& in = sh.in[k & 1];
     const int nt = (int)in.meta[0];
-    merit += a.dt * in.meta[3]; dyn += a.dt * in.meta[4]; eqs += a.dt * in.meta[5];
+    merit += in.meta[3]; dyn += in.meta[4]; eqs += in.meta[5];
     if (in.meta[6] != 0.0) fail = true;
     const int ntp = ntp_of(nt);
     if (ntp == 12) riccati_node<12>(sh, in, rec, rk, fail, warp);
@@ -1057,17 +1071,17 @@ __device__ __forceinline__ void fw_prefetch(FwNode& n, const double* __restrict_
 __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int max_trials, void* info_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Fw2Shared& sh = *reinterpret_cast<Fw2Shared*>(smem_raw);
-  const int inst = blockIdx.x, lane = threadIdx.x, N = a.N;
-  const double dt = a.dt;
-  double* xt = a.xt + (size_t)inst * (N + 1) * NX;
-  double* ut = a.ut + (size_t)inst * N * NU;
-  double* dxt = a.dxt + (size_t)inst * (N + 1) * NX;
-  double* dut = a.dut + (size_t)inst * N * NU;
-  const double* xref = a.x_ref + (size_t)inst * (N + 1) * NX;
-  const double* swing = a.swing + (size_t)inst * (N + 1) * 24;
-  const int32_t* mode = a.mode + (size_t)inst * (N + 1);
-  const double* proj = a.proj + (size_t)inst * N * PJ_STRIDE;
-  const double* rkb = a.rk + (size_t)inst * N * RK_STRIDE;
+  const int inst = blockIdx.x, lane = threadIdx.x, NS = a.N;     // NS: stride (capacity); N: active intervals of this instance
+  const int N = sqp_nn(a, inst);
+  double* xt = a.xt + (size_t)inst * (NS + 1) * NX;
+  double* ut = a.ut + (size_t)inst * NS * NU;
+  double* dxt = a.dxt + (size_t)inst * (NS + 1) * NX;
+  double* dut = a.dut + (size_t)inst * NS * NU;
+  const double* xref = a.x_ref + (size_t)inst * (NS + 1) * NX;
+  const double* swing = a.swing + (size_t)inst * (NS + 1) * 24;
+  const int32_t* mode = a.mode + (size_t)inst * (NS + 1);
+  const double* proj = a.proj + (size_t)inst * NS * PJ_STRIDE;
+  const double* rkb = a.rk + (size_t)inst * NS * RK_STRIDE;
   fw_prefetch(sh.nd[0], proj, rkb, ut, lane);
   if (lane < NX) { xt[lane] = a.x0[(size_t)inst * NX + lane]; sh.dx[lane] = 0.0; dxt[lane] = 0.0; }
   double armijo = 0.0;
@@ -1128,6 +1142,7 @@ __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int 
     while (alpha >= alpha_min && trials < max_trials) {
       double ms = 0.0, ds = 0.0, es = 0.0;
       for (int k = lane; k < N; k += 32) {
+        const double dt = sqp_dt(a, inst, k);
         double x[NX], u[NU], xn[NX], f1[NX], f2[NX], x2[NX], ep[12], ev[12], xr[NX], sw[24];
         for (int i = 0; i < NX; ++i) { x[i] = xt[k * NX + i] + alpha * dxt[k * NX + i]; xn[i] = xt[(k + 1) * NX + i] + alpha * dxt[(k + 1) * NX + i]; xr[i] = xref[k * NX + i]; }
         for (int i = 0; i < NU; ++i) u[i] = ut[k * NU + i] + alpha * dut[k * NU + i];

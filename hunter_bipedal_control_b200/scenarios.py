@@ -155,6 +155,63 @@ def make_reference(x0, cmd_vel, gait, N, dt, t0=0.0, phase=0.0):
     return x_ref, swing.reshape(N + 1, 24), mode, compact
 
 
+def sample_reference(compact, times):
+    """Evaluate a compact reference description (make_reference's 4th value) at arbitrary node times, the way the device expansion does:
+    mode in force on the interval starting at t, clamped linear target interpolation, cubic-Hermite swing segments."""
+    times = np.asarray(times, dtype=np.float64)
+    ev, md = compact["events"], compact["modes"]
+    tt, ts = compact["target_times"], compact["target_states"]
+    n = len(times)
+    mode = np.array([mode_at(ev, md, t) for t in times], dtype=np.int32)
+    x_ref = np.zeros((n, 22))
+    for k, t in enumerate(times):
+        if len(tt) <= 1 or t <= tt[0]:
+            x_ref[k] = ts[0]
+        elif t >= tt[-1]:
+            x_ref[k] = ts[-1]
+        else:
+            s = 0
+            while s + 2 < len(tt) and tt[s + 1] <= t:
+                s += 1
+            al = (t - tt[s]) / (tt[s + 1] - tt[s])
+            x_ref[k] = (1 - al) * ts[s] + al * ts[s + 1]
+    swing = np.zeros((n, 4, 6))
+    for c in range(4):
+        for a in range(3):
+            segs = compact["segments"][c][a]
+            for k, t in enumerate(times):
+                s = 0
+                while s + 1 < len(segs) and t >= segs[s][1]:
+                    s += 1
+                pv = hermite(t, *segs[s])
+                swing[k, c, a] = pv[0]; swing[k, c, 3 + a] = pv[1]
+    return x_ref, swing.reshape(n, 24), mode
+
+
+def event_time_grid(t0, T, dt, events, capacity, dt_min=1e-9):
+    """Time discretisation with event nodes (SURVEY 8a row S1, ocs2::timeDiscretizationWithEvents with the pre-/post-event node pair collapsed):
+    steps of dt, a node on every mode switch inside the horizon (the grid re-anchors there), last node = t0 + T."""
+    tf = t0 + T
+    ev = [e for e in events if e > t0 + 1e-9]
+    nodes = [t0]
+    cur, ei = t0, 0
+    while cur < tf:
+        nx = cur + dt
+        if ei < len(ev) and nx >= ev[ei]:
+            nx = ev[ei]; ei += 1
+        if nx >= tf:
+            nx = tf
+        if nx > cur + dt_min or len(nodes) == 1:
+            if len(nodes) - 1 == capacity:
+                nodes[-1] = tf
+                break
+            nodes.append(nx)
+        else:
+            nodes[-1] = nx
+        cur = nx
+    return np.array(nodes)
+
+
 def make_batch(B, N=100, dt=0.01, gait="trot", cmd_vel=(0.2, 0.0, 0.0, 0.0), seed=20240901, gaits=None, cmd_vels=None, return_compact=False):
     x0 = random_initial_states(B, seed)
     x_ref = np.zeros((B, N + 1, 22)); swing = np.zeros((B, N + 1, 24)); mode = np.zeros((B, N + 1), dtype=np.int32)

@@ -47,6 +47,10 @@ typedef struct {
   double wbc_rho;        /* Tikhonov weight that defines the least-norm WBC optimum (qpOASES setToMPC regularisation) */
   int32_t qp_max_iter;   /* interior-point iteration cap                                          */
   int32_t line_search_max_trials; /* alpha = 1, 1/2, ... >= 1e-4 -> 14                            */
+  double time_horizon;   /* mpc.timeHorizon [s] (task.info:144 0.8); 0 = horizon_N * dt. Used by the event-node grid */
+  int32_t event_nodes;   /* 1: the resident cycle discretises [t0, t0 + time_horizon] like ocs2::timeDiscretizationWithEvents
+                            (steps of dt, a node on every mode switch, grid re-anchored there, last node = final time); horizon_N is
+                            then the node capacity. 0: uniform grid t0 + k dt (BASELINE configs)                          */
 } hb_config;
 
 typedef struct {
@@ -159,6 +163,19 @@ int hb_wbc_qp_rows_batch_dev(hb_ctx* ctx, int B, int n, int m_alloc, const int32
 int hb_mpc_cold_start_batch_dev(hb_ctx* ctx, int B, const double* x0, const int32_t* mode, double* x_traj, double* u_traj);
 int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
                            double* x_traj, double* u_traj, hb_solve_info* info);
+/* ---- time discretisation with event nodes ----
+ * hb_time_grid_batch: node times (B x (horizon_N + 1)) and interval counts (B) of every instance from its mode-switch times
+ * (hb_reference.event_times); status[i] = 1 when the capacity horizon_N was exhausted (last interval stretched to the final time).
+ * The *_grid_* entry points are the grid-aware forms of their uniform counterparts: interval k of instance i has length
+ * node_times[i][k+1] - node_times[i][k]; nodes beyond n_intervals[i] are ignored. */
+int hb_time_grid_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* node_times, int32_t* n_intervals,
+                           int32_t* status /*nullable*/);
+int hb_reference_expand_grid_batch_dev(hb_ctx* ctx, int B, const double* node_times, const hb_reference* refs, double* x_ref, double* swing_ref,
+                                       int32_t* mode);
+int hb_mpc_solve_grid_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* node_times, const int32_t* n_intervals, const double* x_ref,
+                                const double* swing_ref, const int32_t* mode, double* x_traj, double* u_traj, hb_solve_info* info);
+int hb_policy_eval_grid_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* node_times, const int32_t* n_intervals, const double* x_traj,
+                                  const double* u_traj, const int32_t* mode, double* x_des, double* u_des, int32_t* mode_out);
 int hb_policy_eval_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x_traj, const double* u_traj, const int32_t* mode,
                              double* x_des, double* u_des, int32_t* mode_out);
 int hb_control_step_batch_dev(hb_ctx* ctx, int B, double t_rel, const double* x0, const double* x_ref, const double* swing_ref,
@@ -221,6 +238,12 @@ int hb_joint_command_batch(hb_ctx* ctx, int B, const hb_pd_gains* gains, double 
 int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0, const hb_reference* refs,
                             const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque, int32_t* wbc_status);
 int hb_resident_read_batch(hb_ctx* ctx, int B, double* t0 /*nullable*/, double* x_traj /*nullable*/, double* u_traj /*nullable*/);
+/* node times / interval counts of the resident solution (contexts created with event_nodes = 1) */
+int hb_resident_read_grid_batch(hb_ctx* ctx, int B, double* node_times, int32_t* n_intervals);
+int hb_time_grid_batch(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* node_times, int32_t* n_intervals, int32_t* status /*nullable*/);
+int hb_reference_expand_grid_batch(hb_ctx* ctx, int B, const double* node_times, const hb_reference* refs, double* x_ref, double* swing_ref, int32_t* mode);
+int hb_mpc_solve_grid_batch(hb_ctx* ctx, int B, const double* x0, const double* node_times, const int32_t* n_intervals, const double* x_ref,
+                            const double* swing_ref, const int32_t* mode, double* x_traj, double* u_traj, hb_solve_info* info);
 /* hb_plan_references on the device, host pointers in and out (parity checks of the device planner against the host planner) */
 int hb_plan_references_gpu(hb_ctx* ctx, int B, const hb_plan_input* in, double* latest_stance, hb_reference* out, int32_t* status /*nullable*/);
 /* The whole cycle from the plan inputs: computeFootPos at x0 + planner (P1, P3, P4, P5) + hb_resident_cycle_batch, all on the device.
