@@ -28,6 +28,9 @@ EXPORTED_SYMBOLS = [
     "hb_estimator_update_batch", "hb_default_pd_gains", "hb_joint_command_batch_dev", "hb_joint_command_batch",
     "hb_wbc_qp_batch", "hb_wbc_solve_batch", "hb_mpc_cold_start_batch", "hb_mpc_solve_batch", "hb_control_step_batch",
     "hb_rbd_to_centroidal_batch", "hb_reference_expand_batch", "hb_probe_flow_map",
+    "hb_observer_reset", "hb_contact_force_estimate_batch_dev", "hb_contact_force_estimate_batch",
+    "hb_default_sim_params", "hb_actuation_reset", "hb_actuation_batch_dev", "hb_actuation_batch", "hb_sim_step_batch_dev", "hb_sim_step_batch",
+    "hb_resident_wbc_batch_dev", "hb_resident_wbc_batch",
     "hb_time_grid_batch_dev", "hb_reference_expand_grid_batch_dev", "hb_mpc_solve_grid_batch_dev", "hb_policy_eval_grid_batch_dev",
     "hb_time_grid_batch", "hb_reference_expand_grid_batch", "hb_mpc_solve_grid_batch", "hb_resident_read_grid_batch",
 ]
@@ -72,6 +75,41 @@ class HbKfState(C.Structure):
 class HbKfParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("foot_radius", "imu_process_noise_position", "imu_process_noise_velocity", "foot_process_noise_position",
                                           "foot_sensor_noise_position", "foot_sensor_noise_velocity", "foot_height_sensor_noise")]
+
+
+HB_ACT_CAPACITY = 16
+
+
+class HbActuationState(C.Structure):
+    _fields_ = [("count", C.c_int32), ("head", C.c_int32), ("stamp", C.c_double * HB_ACT_CAPACITY), ("cmd", (C.c_double * 50) * HB_ACT_CAPACITY)]
+
+
+class HbSimParams(C.Structure):
+    _fields_ = [("dt", C.c_double), ("substeps", C.c_int32), ("ground_height", C.c_double), ("ground_stiffness", C.c_double), ("ground_damping", C.c_double),
+                ("tangential_damping", C.c_double), ("friction_mu", C.c_double), ("joint_armature", C.c_double), ("joint_damping", C.c_double)]
+
+
+def default_sim_params():
+    p = HbSimParams()
+    _check(load_library().hb_default_sim_params(C.byref(p)), "hb_default_sim_params")
+    return p
+
+
+def actuation_states(B):
+    st = (HbActuationState * B)()
+    _check(load_library().hb_actuation_reset(B, st), "hb_actuation_reset")
+    return st
+
+
+class HbObserverState(C.Structure):
+    _fields_ = [("p_filtered", C.c_double * 16)]
+
+
+def observer_states(B):
+    """Freshly reset momentum-observer states (pSCgZinvlast_ = 0)."""
+    st = (HbObserverState * B)()
+    _check(load_library().hb_observer_reset(B, st), "hb_observer_reset")
+    return st
 
 
 def default_kf_params():
@@ -378,6 +416,41 @@ class Context:
         _check(self._lib.hb_estimator_update_batch(self._h, B, C.byref(params), C.c_double(dt), state, _ptr(quat), _ptr(ang_vel_local), _ptr(lin_acc_local),
                                                    _ptr(joint_pos), _ptr(joint_vel), _ptr(flags), _ptr(rbd)), "hb_estimator_update_batch", self._h)
         return rbd
+
+    def actuation(self, time, state, command, rbd, delay=0.009):
+        """LeggedHWSim::writeSim: delayed hybrid joint command -> applied joint torques [B,10]; `state` (ctypes array of HbActuationState) in place."""
+        command, rbd = _f64(command), _f64(rbd); B = rbd.shape[0]
+        time = _f64(np.broadcast_to(_f64(time), (B,)))
+        tau = np.zeros((B, NJ))
+        _check(self._lib.hb_actuation_batch(self._h, B, C.c_double(delay), _ptr(time), state, _ptr(command), _ptr(rbd), _ptr(tau)), "hb_actuation_batch", self._h)
+        return tau
+
+    def sim_step(self, rbd, tau, params=None):
+        """One control period of the batched rigid-body plant: returns (rbd_next [B,32], contact_force [B,12], contact_flag [B,4])."""
+        rbd = _f64(rbd).copy(); tau = _f64(tau); B = rbd.shape[0]
+        params = params or default_sim_params()
+        cf = np.zeros((B, 12)); fl = np.zeros((B, 4), dtype=np.uint8)
+        _check(self._lib.hb_sim_step_batch(self._h, B, C.byref(params), _ptr(rbd), _ptr(tau), _ptr(cf), _ptr(fl)), "hb_sim_step_batch", self._h)
+        return rbd, cf, fl
+
+    def resident_wbc(self, t_now, rbd, stance_mode=None):
+        """Policy of the resident solution at absolute time t_now + WeightedWbc: returns (x_des, u_des, mode, sol, torque, status)."""
+        rbd = _f64(rbd); B = rbd.shape[0]
+        t_now = _f64(np.broadcast_to(_f64(t_now), (B,)))
+        sm = None if stance_mode is None else np.ascontiguousarray(stance_mode, dtype=np.uint8)
+        xd = np.zeros((B, NX)); ud = np.zeros((B, NU)); md = np.zeros(B, dtype=np.int32); sol = np.zeros((B, NWBC)); tau = np.zeros((B, NJ)); st = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_resident_wbc_batch(self._h, B, _ptr(t_now), _ptr(rbd), _ptr(sm), _ptr(xd), _ptr(ud), _ptr(md), _ptr(sol), _ptr(tau), _ptr(st)),
+               "hb_resident_wbc_batch", self._h)
+        return xd, ud, md, sol, tau, st
+
+    def contact_force_estimate(self, dt, state, rbd, tau_cmd, cutoff_frequency=250.0):
+        """StateEstimateBase::estContactForce for a batch; `state` (ctypes array of HbObserverState) is updated in place.
+        Returns (est_contact_force [B,16], disturbance_torque [B,16])."""
+        rbd, tau_cmd = _f64(rbd), _f64(tau_cmd); B = rbd.shape[0]
+        est = np.zeros((B, 16)); dist = np.zeros((B, 16))
+        _check(self._lib.hb_contact_force_estimate_batch(self._h, B, C.c_double(cutoff_frequency), C.c_double(dt), state, _ptr(rbd), _ptr(tau_cmd), _ptr(est),
+                                                         _ptr(dist)), "hb_contact_force_estimate_batch", self._h)
+        return est, dist
 
     def joint_command(self, period, x_des, u_des, wbc_sol, mode_cmd, rbd, loaded=None, estop=None, gains=None):
         """Joint command law (LeggedController.cpp:186-257): returns (command [B,10,5], output_torque [B,10], estop [B])."""

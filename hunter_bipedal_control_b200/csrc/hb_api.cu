@@ -226,10 +226,11 @@ __global__ void __launch_bounds__(128) warm_shift_kernel(int B, int N, double dt
 // MPC_MRT_Interface::evaluatePolicy with the feed-forward policy (LeggedController.cpp:154-156, task.info:93):
 // linear interpolation of the state / input trajectories at t0 + t_rel; mode = mode in force at that time.
 __global__ void policy_eval_kernel(int B, int N, double dt, double t_rel, const double* xt, const double* ut, const int32_t* mode, double* x_des,
-                                   double* u_des, int32_t* mode_out, const double* tk, const int32_t* nn) {
+                                   double* u_des, int32_t* mode_out, const double* tk, const int32_t* nn, const double* t_abs, const double* t0res) {
   const int inst = blockIdx.x * blockDim.x / 32 + (threadIdx.x >> 5);
   if (inst >= B) return;
   const int lane = threadIdx.x & 31;
+  if (t_abs) t_rel = t_abs[inst] - t0res[inst];        // evaluation at an absolute time per instance (500 Hz WBC ticks between MPC updates)
   int k, na = N;
   double al;
   if (tk) {      // event-node grid: node times of this instance
@@ -434,6 +435,211 @@ __global__ void __launch_bounds__(32) kf_update_kernel(int B, hb_kf_params prm, 
   double* rb = rbd_out + (size_t)inst * 32;
   if (lane < 3) { rb[lane] = zyx[lane]; rb[3 + lane] = sh.x[lane]; rb[16 + lane] = wg[lane]; rb[19 + lane] = sh.x[3 + lane]; }
   if (lane < NJ) { rb[6 + lane] = q[6 + lane]; rb[22 + lane] = v[6 + lane]; }
+}
+
+// ---------------------------------------------------------------------------------------------- contact-force estimate (row N3, second half)
+// StateEstimateBase::estContactForce (legged_estimation/src/StateEstimateBase.cpp:130-206): generalised-momentum observer
+//   p = M v,  pSCg = beta p + S' tau_cmd + C' v - g,  low-pass (gamma = exp(-lambda dt), beta = (1 - gamma) / (gamma dt)),  tau_d = beta p - filtered,
+// then per foot the least-norm 6-D wrench w with (S_leg J_foot') w = S_leg tau_d (5 joint rows of the leg, toe frame Jacobian in world axes).
+// One warp per instance; the terms Pinocchio provides are obtained as
+//   M v  = inverse dynamics with acceleration v at zero velocity, no gravity;   g = inverse dynamics at rest with gravity;
+//   C' v = d/dq (1/2 v' M(q) v) at fixed v (lane i = dual sweep seeded on q_i; valid for any C with dM/dt = C + C', as Pinocchio's).
+struct ObsShared { double p[NQ], g[NQ], ctv[NQ], taud[NQ], Jf[2 * 5 * 6]; };
+__global__ void __launch_bounds__(32) contact_force_kernel(int B, double lambda, double dt_in, hb_observer_state* state, const double* rbd, const double* tau_cmd,
+                                                           double* est, double* disturbance) {
+  __shared__ ObsShared sh;
+  const int inst = blockIdx.x, lane = threadIdx.x;
+  const double dt = dt_in > 1.0 ? 0.002 : dt_in;
+  const double gama = exp(-lambda * dt), beta = (1.0 - gama) / (gama * dt);
+  const double* r = rbd + (size_t)inst * 32;
+  double q[NQ], v[NQ];
+  for (int i = 0; i < 3; ++i) { q[i] = r[3 + i]; q[3 + i] = r[i]; v[i] = r[NQ + 3 + i]; }
+  for (int j = 0; j < NJ; ++j) { q[6 + j] = r[6 + j]; v[6 + j] = r[NQ + 6 + j]; }
+  {
+    double sz, cz, sy, cy;
+    sincos(q[3], &sz, &cz); sincos(q[4], &sy, &cy);
+    const double dxr = (cz * r[NQ] + sz * r[NQ + 1]) / cy;      // getEulerAnglesZyxDerivativesFromGlobalAngularVelocity
+    v[5] = dxr; v[4] = -sz * r[NQ] + cz * r[NQ + 1]; v[3] = r[NQ + 2] + sy * dxr;
+  }
+  if (lane < 3) sh.ctv[lane] = 0.0;                 // the kinetic energy does not depend on the base position
+  else if (lane < NQ) {
+    D1 qd[NQ], vd[NQ];
+    for (int i = 0; i < NQ; ++i) { qd[i] = D1(q[i], i == lane ? 1.0 : 0.0); vd[i] = D1(v[i], 0.0); }
+    KinOut<D1> o;
+    kin_pass<D1>(qd, vd, o);
+    sh.ctv[lane] = o.ke.d;
+  } else if (lane == 16) {
+    double zero[NQ], tau[NQ];
+    for (int i = 0; i < NQ; ++i) zero[i] = 0.0;
+    rnea_pass(q, zero, v, false, tau, nullptr);
+    for (int i = 0; i < NQ; ++i) sh.p[i] = tau[i];
+  } else if (lane == 17) {
+    double zero[NQ], tau[NQ];
+    for (int i = 0; i < NQ; ++i) zero[i] = 0.0;
+    rnea_pass(q, zero, zero, true, tau, nullptr);
+    for (int i = 0; i < NQ; ++i) sh.g[i] = tau[i];
+  } else if (lane < 20) {
+    // toe-frame Jacobian of leg `leg` with respect to its five joints, world axes: column j = [a_j x (p_toe - o_j) ; a_j]
+    const int leg = lane - 18;
+    double R[9], ax0[9], pj[3], o[5][3], a[5][3];
+    base_frame(q, R, ax0);
+    for (int i = 0; i < 3; ++i) pj[i] = q[i];
+    for (int j = 0; j < 5; ++j) {
+      const int b = 1 + 5 * leg + j;
+      double d[3];
+      rot_const(R, &c_model.joint_xyz[3 * b], d);
+      for (int i = 0; i < 3; ++i) { pj[i] += d[i]; o[j][i] = pj[i]; }
+      joint_rotate(R, c_model.joint_axis[b], q[5 + b], a[j]);
+    }
+    double off[3], toe[3];
+    rot_const(R, &c_model.contact_offset[3 * leg], off);
+    for (int i = 0; i < 3; ++i) toe[i] = pj[i] + off[i];
+    for (int j = 0; j < 5; ++j) {
+      double rr[3], lin[3];
+      for (int i = 0; i < 3; ++i) rr[i] = toe[i] - o[j][i];
+      cross(a[j], rr, lin);
+      for (int i = 0; i < 3; ++i) { sh.Jf[(leg * 5 + j) * 6 + i] = lin[i]; sh.Jf[(leg * 5 + j) * 6 + 3 + i] = a[j][i]; }
+    }
+  }
+  __syncwarp();
+  hb_observer_state& st = state[inst];
+  if (lane < NQ) {
+    const double p = sh.p[lane];
+    const double pscg = beta * p + (lane >= 6 ? tau_cmd[(size_t)inst * NJ + lane - 6] : 0.0) + sh.ctv[lane] - sh.g[lane];
+    const double filt = (1.0 - gama) * pscg + gama * st.p_filtered[lane];
+    st.p_filtered[lane] = filt;
+    const double td = beta * p - filt;
+    sh.taud[lane] = td;
+    if (disturbance) disturbance[(size_t)inst * NQ + lane] = td;
+  }
+  __syncwarp();
+  double* e = est + (size_t)inst * 16;
+  if (lane < 2) {
+    // least-norm solution of A w = b, A = S J' (5 x 6): w = A' (A A')^-1 b (the reference takes the SVD solve; same result at full row rank)
+    const double* A = sh.Jf + lane * 30;          // row j = joint j of the leg, 6 columns
+    double Gm[5][6];
+    for (int i = 0; i < 5; ++i) {
+      for (int j = 0; j < 5; ++j) { double s = 0.0; for (int c = 0; c < 6; ++c) s += A[i * 6 + c] * A[j * 6 + c]; Gm[i][j] = s; }
+      Gm[i][5] = sh.taud[6 + 5 * lane + i];
+    }
+    for (int c = 0; c < 5; ++c) {
+      int pv = c; double best = fabs(Gm[c][c]);
+      for (int rr = c + 1; rr < 5; ++rr) if (fabs(Gm[rr][c]) > best) { best = fabs(Gm[rr][c]); pv = rr; }
+      if (pv != c) for (int j = 0; j < 6; ++j) { const double t = Gm[c][j]; Gm[c][j] = Gm[pv][j]; Gm[pv][j] = t; }
+      const double inv = 1.0 / Gm[c][c];
+      for (int rr = c + 1; rr < 5; ++rr) { const double f = Gm[rr][c] * inv; for (int j = c; j < 6; ++j) Gm[rr][j] -= f * Gm[c][j]; }
+    }
+    double y[5];
+    for (int rr = 4; rr >= 0; --rr) { double s = Gm[rr][5]; for (int j = rr + 1; j < 5; ++j) s -= Gm[rr][j] * y[j]; y[rr] = s / Gm[rr][rr]; }
+    double w[6], n3 = 0.0, n6 = 0.0;
+    for (int c = 0; c < 6; ++c) { double s = 0.0; for (int j = 0; j < 5; ++j) s += A[j * 6 + c] * y[j]; w[c] = s; n6 += s * s; if (c < 3) n3 += s * s; }
+    for (int c = 0; c < 6; ++c) e[6 * lane + c] = w[c];
+    e[12 + lane] = sqrt(n3);
+    e[14 + lane] = sqrt(n6);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- closed-loop rollout pieces (row N2)
+// Actuation model of the simulated hardware (legged_gazebo/src/LeggedHWSim.cpp:166-192): every write pushes the hybrid joint command
+// (posDes, velDes, kp, kd, ff) with its time stamp on a buffer, drops the entries older than `delay` from the far end, and applies the
+// OLDEST remaining one: tau = kp (posDes - q) + kd (velDes - qd) + ff with the CURRENT joint state. One thread per instance; the deque is a
+// ring of HB_ACT_CAPACITY entries (a full ring drops its oldest entry first).
+__global__ void actuation_kernel(int B, double delay, const double* time, hb_actuation_state* state, const double* command, const double* rbd, double* tau) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= B) return;
+  hb_actuation_state& st = state[inst];
+  const double t = time[inst];
+  int cnt = st.count, head = st.head;             // head = newest entry; entries head, head+1, ... (mod capacity) are older and older
+  while (cnt > 0 && st.stamp[(head + cnt - 1) % HB_ACT_CAPACITY] + delay < t) --cnt;
+  if (cnt == HB_ACT_CAPACITY) --cnt;
+  head = (head + HB_ACT_CAPACITY - 1) % HB_ACT_CAPACITY;
+  st.stamp[head] = t;
+  for (int k = 0; k < NJ * 5; ++k) st.cmd[head][k] = command[(size_t)inst * NJ * 5 + k];
+  ++cnt;
+  st.count = cnt; st.head = head;
+  const double* c = st.cmd[(head + cnt - 1) % HB_ACT_CAPACITY];
+  const double* r = rbd + (size_t)inst * 32;
+  for (int j = 0; j < NJ; ++j) tau[(size_t)inst * NJ + j] = c[5 * j + 2] * (c[5 * j] - r[6 + j]) + c[5 * j + 3] * (c[5 * j + 1] - r[NQ + 6 + j]) + c[5 * j + 4];
+}
+
+// One step of a batched rigid-body simulation of the robot on flat ground (stands in for the Gazebo / MuJoCo plant of the reference's
+// closed loop, legged_gazebo / legged_mujoco): forward dynamics M(q) qdd = S' tau + J_c' F_c - nle with compliant point contacts at the four
+// contact frames (normal spring-damper, viscous tangential friction clipped to the cone), semi-implicit Euler over `substeps` substeps.
+// Same rigid-body passes as the WBC assembly: lanes 0-15 unit-velocity sweeps -> J_c columns, lanes 0-15 RNEA with unit accelerations ->
+// M columns, lane 16 -> nle; 16 x 16 Cholesky in shared memory. One warp per instance.
+struct SimShared { double q[NQ], v[NQ], J[12 * NQ], M[NQ * 17], nle[NQ], rhs[NQ], t1[NQ], t2[NQ], kdi[NQ], F[12], cpos[12], cvel[12]; };
+__global__ void __launch_bounds__(32) sim_step_kernel(int B, hb_sim_params prm, double* rbd_io, const double* tau, double* contact_force, uint8_t* contact_flag) {
+  __shared__ SimShared sh;
+  const int inst = blockIdx.x, lane = threadIdx.x;
+  double* r = rbd_io + (size_t)inst * 32;
+  if (lane == 0) {
+    for (int i = 0; i < 3; ++i) { sh.q[i] = r[3 + i]; sh.q[3 + i] = r[i]; sh.v[i] = r[NQ + 3 + i]; }
+    for (int j = 0; j < NJ; ++j) { sh.q[6 + j] = r[6 + j]; sh.v[6 + j] = r[NQ + 6 + j]; }
+    double sz, cz, sy, cy;
+    sincos(sh.q[3], &sz, &cz); sincos(sh.q[4], &sy, &cy);
+    const double dxr = (cz * r[NQ] + sz * r[NQ + 1]) / cy;
+    sh.v[5] = dxr; sh.v[4] = -sz * r[NQ] + cz * r[NQ + 1]; sh.v[3] = r[NQ + 2] + sy * dxr;
+  }
+  __syncwarp();
+  const double h = prm.dt / (prm.substeps > 0 ? prm.substeps : 1);
+  for (int sub = 0; sub < (prm.substeps > 0 ? prm.substeps : 1); ++sub) {
+    if (lane < NQ) {
+      double q[NQ], e[NQ];
+      for (int i = 0; i < NQ; ++i) { q[i] = sh.q[i]; e[i] = (i == lane) ? 1.0 : 0.0; }
+      KinOut<double> o;
+      kin_pass<double>(q, e, o);
+      for (int rr = 0; rr < 12; ++rr) sh.J[rr * NQ + lane] = o.cvel[rr];
+      if (lane == 0) for (int rr = 0; rr < 12; ++rr) sh.cpos[rr] = o.cpos[rr];
+    }
+    __syncwarp();
+    if (lane < 12) { double s = 0.0; for (int i = 0; i < NQ; ++i) s += sh.J[lane * NQ + i] * sh.v[i]; sh.cvel[lane] = s; }
+    __syncwarp();
+    if (lane < 4) {
+      const double depth = prm.ground_height - sh.cpos[3 * lane + 2];
+      double fz = 0.0, fx = 0.0, fy = 0.0;
+      if (depth > 0.0) {
+        fz = prm.ground_stiffness * depth - prm.ground_damping * sh.cvel[3 * lane + 2];
+        if (fz < 0.0) fz = 0.0;
+        fx = -prm.tangential_damping * sh.cvel[3 * lane]; fy = -prm.tangential_damping * sh.cvel[3 * lane + 1];
+        const double ft = sqrt(fx * fx + fy * fy), fmax_ = prm.friction_mu * fz;
+        if (ft > fmax_) { const double sc = ft > 0.0 ? fmax_ / ft : 0.0; fx *= sc; fy *= sc; }
+      }
+      sh.F[3 * lane] = fx; sh.F[3 * lane + 1] = fy; sh.F[3 * lane + 2] = fz;
+    }
+    if (lane < 17) {
+      double q[NQ], v[NQ], a[NQ], tq[NQ];
+      for (int i = 0; i < NQ; ++i) { q[i] = sh.q[i]; v[i] = lane == 16 ? sh.v[i] : 0.0; a[i] = (i == lane) ? 1.0 : 0.0; }
+      rnea_pass(q, v, a, lane == 16, tq, nullptr);
+      if (lane < 16) { for (int rr = 0; rr < NQ; ++rr) sh.M[rr * 17 + lane] = tq[rr]; }
+      else { for (int rr = 0; rr < NQ; ++rr) sh.nle[rr] = tq[rr]; }
+    }
+    __syncwarp();
+    if (lane < NQ) {
+      // joint side of the plant as in the reference's MuJoCo model (mujoco/model/hunter/hunter.xml:6): rotor armature on the diagonal of M,
+      // viscous joint damping
+      double s = -sh.nle[lane] + (lane >= 6 ? tau[(size_t)inst * NJ + lane - 6] - prm.joint_damping * sh.v[lane] : 0.0);
+      for (int rr = 0; rr < 12; ++rr) s += sh.J[rr * NQ + lane] * sh.F[rr];
+      sh.rhs[lane] = s;
+      if (lane >= 6) sh.M[lane * 17 + lane] += prm.joint_armature;
+      for (int j = lane + 1; j < NQ; ++j) { const double a = 0.5 * (sh.M[lane * 17 + j] + sh.M[j * 17 + lane]); sh.M[j * 17 + lane] = a; }   // lower triangle, symmetrised
+    }
+    __syncwarp();
+    warp_chol_inv(sh.M, NQ, 17, sh.kdi, lane);
+    warp_li_mv(sh.M, NQ, 17, sh.kdi, sh.rhs, sh.t1, lane);
+    warp_lit_mv(sh.M, NQ, 17, sh.kdi, sh.t1, sh.t2, lane);      // t2 = qdd
+    if (lane < NQ) { const double vn = sh.v[lane] + h * sh.t2[lane]; sh.v[lane] = vn; sh.q[lane] += h * vn; }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    for (int i = 0; i < 3; ++i) { r[3 + i] = sh.q[i]; r[i] = sh.q[3 + i]; r[NQ + 3 + i] = sh.v[i]; }
+    for (int j = 0; j < NJ; ++j) { r[6 + j] = sh.q[6 + j]; r[NQ + 6 + j] = sh.v[6 + j]; }
+    double sz, cz, sy, cy;
+    sincos(sh.q[3], &sz, &cz); sincos(sh.q[4], &sy, &cy);
+    const double d0 = sh.v[3], d1 = sh.v[4], d2 = sh.v[5];      // yaw, pitch, roll rates -> world angular velocity
+    r[NQ] = -sz * d1 + cz * cy * d2; r[NQ + 1] = cz * d1 + sz * cy * d2; r[NQ + 2] = d0 - sy * d2;
+  }
+  if (lane < 12 && contact_force) contact_force[(size_t)inst * 12 + lane] = sh.F[lane];
+  if (lane < 4 && contact_flag) contact_flag[(size_t)inst * 4 + lane] = sh.F[3 * lane + 2] > 0.0 ? 1 : 0;
 }
 
 // computeCentroidalStateFromRbdModel (LeggedController.cpp:336)
@@ -679,6 +885,7 @@ struct hb_ctx {
   double *s_x0, *s_xref, *s_swing, *s_xt, *s_ut, *s_rbd, *s_xd, *s_ud, *s_sol, *s_tau, *s_t0, *s_misc;
   double *res_xt = nullptr, *res_ut = nullptr, *res_t0 = nullptr;   // resident primal solution (hb_resident_cycle_batch)
   double *s_tk = nullptr, *res_tk = nullptr; int32_t *s_nn = nullptr, *res_nn = nullptr;   // node times / interval counts (event-node grids)
+  int32_t* res_mode = nullptr;                                      // node modes of the resident solution (policy evaluation between MPC solves)
   int res_valid = 0;                                                // number of instances holding a previous solution
   hb_plan_input* s_plan = nullptr; double* res_stance = nullptr; int32_t* s_pstatus = nullptr;   // device planner (row N1)
   double* res_sol = nullptr; int res_sol_valid = 0;   // last good WBC solution per instance (WeightedWbc fallback, W5)
@@ -824,6 +1031,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   ok = ok && dalloc(&ctx->s_kf, B) == cudaSuccess && dalloc(&ctx->res_sol, B * NWBC) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_plan, B) == cudaSuccess && dalloc(&ctx->res_stance, B * 12) == cudaSuccess && dalloc(&ctx->s_pstatus, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->res_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->res_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->res_t0, B) == cudaSuccess;
+  ok = ok && dalloc(&ctx->res_mode, B * (N + 1)) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_tk, B * (N + 1)) == cudaSuccess && dalloc(&ctx->res_tk, B * (N + 1)) == cudaSuccess && dalloc(&ctx->s_nn, B) == cudaSuccess && dalloc(&ctx->res_nn, B) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_xt, B * (N + 1) * NX) == cudaSuccess && dalloc(&ctx->s_ut, B * N * NU) == cudaSuccess && dalloc(&ctx->s_rbd, B * 32) == cudaSuccess;
   ok = ok && dalloc(&ctx->s_xd, B * NX) == cudaSuccess && dalloc(&ctx->s_ud, B * NU) == cudaSuccess && dalloc(&ctx->s_sol, B * NWBC) == cudaSuccess;
@@ -854,7 +1062,7 @@ int hb_destroy(hb_ctx* ctx) {
   void* ptrs[] = {ctx->lin, ctx->proj, ctx->rk, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->xdes, ctx->udes,
                   ctx->wsol, ctx->wstatus, ctx->witers, ctx->wmode, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_xt, ctx->s_ut, ctx->s_rbd, ctx->s_xd,
                   ctx->s_ud, ctx->s_sol, ctx->s_tau, ctx->s_t0, ctx->s_misc, ctx->s_mode, ctx->s_imode, ctx->s_status, ctx->s_iters, ctx->s_stance,
-                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf, ctx->res_sol, ctx->s_tk, ctx->res_tk, ctx->s_nn, ctx->res_nn};
+                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf, ctx->res_sol, ctx->s_tk, ctx->res_tk, ctx->s_nn, ctx->res_nn, ctx->res_mode};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
   if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
@@ -1044,7 +1252,7 @@ static int policy_eval_impl(hb_ctx* ctx, int B, double t_rel, const double* x_tr
   if (set_device(ctx)) return HB_ECUDA;
   const int wpb = 4;
   policy_eval_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, 0, ctx->stream>>>(B, ctx->cfg.horizon_N, ctx->cfg.dt, t_rel, x_traj, u_traj, mode, x_des, u_des, mode_out,
-                                                                         tk, nn);
+                                                                         tk, nn, nullptr, nullptr);
   ctx->launches++;
   CK(cudaGetLastError());
   return HB_OK;
@@ -1158,6 +1366,7 @@ int hb_resident_cycle_batch_dev(hb_ctx* ctx, int B, int cold_start, double t_rel
   }
   ctx->launches++;
   CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->res_mode + o * (N + 1), mode, sizeof(int32_t) * B * (N + 1), cudaMemcpyDeviceToDevice, ctx->stream));
   if (ctx->res_valid < ctx->base + B) ctx->res_valid = ctx->base + B;
   rc = control_step_impl(ctx, B, t_rel, x0, xref, swing, mode, rbd, xt, ut, info, wbc_sol, torque, wbc_status, tk, nn);
   if (rc) return rc;
@@ -1207,6 +1416,88 @@ int hb_estimator_update_batch_dev(hb_ctx* ctx, int B, const hb_kf_params* params
   if (set_device(ctx)) return HB_ECUDA;
   kf_update_kernel<<<B, 32, sizeof(KfShared), ctx->stream>>>(B, *params, dt, state, quat, ang_vel_local, lin_acc_local, joint_pos, joint_vel, contact_flag,
                                                             rbd_out);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_default_sim_params(hb_sim_params* p) {
+  if (!p) return HB_EINVAL;
+  p->dt = 0.002; p->substeps = 4; p->ground_height = 0.0; p->ground_stiffness = 3.0e4; p->ground_damping = 3.0e2; p->tangential_damping = 3.0e2; p->friction_mu = 0.7;
+  p->joint_armature = 0.1; p->joint_damping = 1.0;       // mujoco/model/hunter/hunter.xml:6 (default joint armature / damping of the reference's plant)
+  return HB_OK;
+}
+
+int hb_actuation_reset(int B, hb_actuation_state* state) {
+  if (B < 0 || !state) return HB_EINVAL;
+  memset(state, 0, sizeof(hb_actuation_state) * (size_t)B);       // cmdBuffer_ cleared (LeggedHWSim.cpp:171-174)
+  return HB_OK;
+}
+
+int hb_actuation_batch_dev(hb_ctx* ctx, int B, double delay, const double* time, hb_actuation_state* state, const double* command, const double* rbd,
+                           double* tau) {
+  if (!ctx || B < 0 || !time || !state || !command || !rbd || !tau || delay < 0.0) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  actuation_kernel<<<(B + 63) / 64, 64, 0, ctx->stream>>>(B, delay, time, state, command, rbd, tau);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_sim_step_batch_dev(hb_ctx* ctx, int B, const hb_sim_params* params, double* rbd, const double* tau, double* contact_force, uint8_t* contact_flag) {
+  if (!ctx || B < 0 || !params || !rbd || !tau || !(params->dt > 0.0) || params->substeps < 1 || params->substeps > 1000) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  sim_step_kernel<<<B, 32, 0, ctx->stream>>>(B, *params, rbd, tau, contact_force, contact_flag);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_resident_wbc_batch_dev(hb_ctx* ctx, int B, const double* t_now, const double* rbd, const uint8_t* stance_mode, double* x_des, double* u_des,
+                              int32_t* mode_out, double* wbc_sol, double* torque, int32_t* wbc_status) {
+  if (!ctx || B < 0 || !t_now || !rbd || !x_des || !u_des || !mode_out || !wbc_sol) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (ctx->base + B > ctx->res_valid) return HB_EINVAL;             // no resident solution to evaluate
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t N = ctx->cfg.horizon_N, o = (size_t)ctx->base;
+  const bool grid = ctx->cfg.event_nodes != 0;
+  const int wpb = 4;
+  policy_eval_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, 0, ctx->stream>>>(B, (int)N, ctx->cfg.dt, 0.0, ctx->res_xt + o * (N + 1) * NX, ctx->res_ut + o * N * NU,
+                                                                         ctx->res_mode + o * (N + 1), x_des, u_des, mode_out, grid ? ctx->res_tk + o * (N + 1) : nullptr,
+                                                                         grid ? ctx->res_nn + o : nullptr, t_now, ctx->res_t0 + o);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  int rc = hb_wbc_solve_batch_dev(ctx, B, x_des, u_des, rbd, mode_out, stance_mode, wbc_sol, wbc_status);
+  if (rc) return rc;
+  if (torque) {
+    torque_kernel<<<(B * NJ + 127) / 128, 128, 0, ctx->stream>>>(B, wbc_sol, torque);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  if (wbc_status) {
+    const int have_prev = (ctx->res_sol_valid >= ctx->base + B) ? 1 : 0;
+    wbc_fallback_kernel<<<(B * NWBC + 127) / 128, 128, 0, ctx->stream>>>(B, have_prev, wbc_status, wbc_sol, ctx->res_sol + o * NWBC, torque);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (ctx->res_sol_valid < ctx->base + B) ctx->res_sol_valid = ctx->base + B;
+  }
+  return HB_OK;
+}
+
+int hb_observer_reset(int B, hb_observer_state* state) {
+  if (B < 0 || !state) return HB_EINVAL;
+  memset(state, 0, sizeof(hb_observer_state) * (size_t)B);      // pSCgZinvlast_ starts at zero (StateEstimateBase.cpp:58-59)
+  return HB_OK;
+}
+
+int hb_contact_force_estimate_batch_dev(hb_ctx* ctx, int B, double cutoff_frequency, double dt, hb_observer_state* state, const double* rbd,
+                                        const double* tau_cmd, double* est_contact_force, double* disturbance_torque) {
+  if (!ctx || B < 0 || !state || !rbd || !tau_cmd || !est_contact_force || !(cutoff_frequency > 0.0) || !(dt > 0.0)) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (set_device(ctx)) return HB_ECUDA;
+  contact_force_kernel<<<B, 32, 0, ctx->stream>>>(B, cutoff_frequency, dt, state, rbd, tau_cmd, est_contact_force, disturbance_torque);
   ctx->launches++;
   CK(cudaGetLastError());
   return HB_OK;
@@ -1643,6 +1934,75 @@ int hb_estimator_update_batch(hb_ctx* ctx, int B, const hb_kf_params* params, do
   if (rc) return rc;
   D2H(state, ctx->s_kf, sizeof(hb_kf_state) * B);
   D2H(rbd_out, ctx->s_rbd, sizeof(double) * B * 32);
+  return hb_sync(ctx);
+}
+
+int hb_actuation_batch(hb_ctx* ctx, int B, double delay, const double* time, hb_actuation_state* state, const double* command, const double* rbd,
+                       double* tau) {
+  if (!ctx || B < 0 || !time || !state || !command || !rbd || !tau) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  const size_t need = ((size_t)B * sizeof(hb_actuation_state) + 7) / 8;
+  int rc = qp_staging_reserve(ctx, need);
+  if (rc) return rc;
+  hb_actuation_state* d_state = reinterpret_cast<hb_actuation_state*>(ctx->s_qpH);
+  H2D(d_state, state, sizeof(hb_actuation_state) * B); H2D(ctx->s_t0, time, sizeof(double) * B);
+  H2D(ctx->s_misc, command, sizeof(double) * B * NJ * 5); H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32);
+  rc = hb_actuation_batch_dev(ctx, B, delay, ctx->s_t0, d_state, ctx->s_misc, ctx->s_rbd, ctx->s_tau);
+  if (rc) return rc;
+  D2H(state, d_state, sizeof(hb_actuation_state) * B); D2H(tau, ctx->s_tau, sizeof(double) * B * NJ);
+  return hb_sync(ctx);
+}
+
+int hb_sim_step_batch(hb_ctx* ctx, int B, const hb_sim_params* params, double* rbd, const double* tau, double* contact_force, uint8_t* contact_flag) {
+  if (!ctx || B < 0 || !params || !rbd || !tau) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  uint8_t* d_flag = (uint8_t*)ctx->s_status;      // B int32 words hold B x 4 flags
+  H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32); H2D(ctx->s_tau, tau, sizeof(double) * B * NJ);
+  int rc = hb_sim_step_batch_dev(ctx, B, params, ctx->s_rbd, ctx->s_tau, ctx->s_misc, d_flag);
+  if (rc) return rc;
+  D2H(rbd, ctx->s_rbd, sizeof(double) * B * 32);
+  if (contact_force) D2H(contact_force, ctx->s_misc, sizeof(double) * B * 12);
+  if (contact_flag) D2H(contact_flag, d_flag, (size_t)B * 4);
+  return hb_sync(ctx);
+}
+
+int hb_resident_wbc_batch(hb_ctx* ctx, int B, const double* t_now, const double* rbd, const uint8_t* stance_mode, double* x_des, double* u_des,
+                          int32_t* mode_out, double* wbc_sol, double* torque, int32_t* wbc_status) {
+  if (!ctx || B < 0 || !t_now || !rbd || !x_des || !u_des || !mode_out || !wbc_sol) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (B > ctx->res_valid) return HB_EINVAL;
+  if (set_device(ctx)) return HB_ECUDA;
+  H2D(ctx->s_t0, t_now, sizeof(double) * B); H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32);
+  if (stance_mode) H2D(ctx->s_stance, stance_mode, B);
+  int rc = hb_resident_wbc_batch_dev(ctx, B, ctx->s_t0, ctx->s_rbd, stance_mode ? ctx->s_stance : nullptr, ctx->s_xd, ctx->s_ud, ctx->s_imode, ctx->s_sol, ctx->s_tau,
+                                     ctx->s_status);
+  if (rc) return rc;
+  D2H(x_des, ctx->s_xd, sizeof(double) * B * NX); D2H(u_des, ctx->s_ud, sizeof(double) * B * NU); D2H(mode_out, ctx->s_imode, sizeof(int32_t) * B);
+  D2H(wbc_sol, ctx->s_sol, sizeof(double) * B * NWBC);
+  if (torque) D2H(torque, ctx->s_tau, sizeof(double) * B * NJ);
+  if (wbc_status) D2H(wbc_status, ctx->s_status, sizeof(int32_t) * B);
+  return hb_sync(ctx);
+}
+
+int hb_contact_force_estimate_batch(hb_ctx* ctx, int B, double cutoff_frequency, double dt, hb_observer_state* state, const double* rbd,
+                                    const double* tau_cmd, double* est_contact_force, double* disturbance_torque) {
+  if (!ctx || B < 0 || !state || !rbd || !tau_cmd || !est_contact_force) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  // staging: s_misc holds the observer states (16 doubles), the estimates (16) and the disturbance torques (16) of the batch
+  hb_observer_state* d_state = reinterpret_cast<hb_observer_state*>(ctx->s_misc);
+  double* d_est = ctx->s_misc + (size_t)B * 16; double* d_dist = d_est + (size_t)B * 16;
+  H2D(d_state, state, sizeof(hb_observer_state) * B); H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32); H2D(ctx->s_tau, tau_cmd, sizeof(double) * B * NJ);
+  int rc = hb_contact_force_estimate_batch_dev(ctx, B, cutoff_frequency, dt, d_state, ctx->s_rbd, ctx->s_tau, d_est, d_dist);
+  if (rc) return rc;
+  D2H(state, d_state, sizeof(hb_observer_state) * B); D2H(est_contact_force, d_est, sizeof(double) * B * 16);
+  if (disturbance_torque) D2H(disturbance_torque, d_dist, sizeof(double) * B * NQ);
   return hb_sync(ctx);
 }
 

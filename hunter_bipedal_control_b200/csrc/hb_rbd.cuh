@@ -112,6 +112,7 @@ struct KinOut {
   T com[3];    // centre of mass
   T cpos[12];  // contact positions
   T cvel[12];  // contact velocities J_c(q) v
+  T ke;        // kinetic energy 1/2 v' M(q) v
 };
 
 // R <- R * Rot(axis) given the sine / cosine of the joint angle; returns the world joint axis in a[].
@@ -162,6 +163,7 @@ __device__ __forceinline__ void kin_pass_f(QF qf, VF vf, SCF scf, OF of) {
     ax0[6] = cz * cy; ax0[7] = sz * cy; ax0[8] = -sy;
   }
   T w0[3], P[3], Lo[3], mc[3];
+  T ke = T(0.0);
   {
     const T v3 = vf(3), v4 = vf(4), v5 = vf(5);
 #pragma unroll
@@ -184,6 +186,8 @@ __device__ __forceinline__ void kin_pass_f(QF qf, VF vf, SCF scf, OF of) {
     rot(R, Iwl, Iw);
 #pragma unroll
     for (int i = 0; i < 3; ++i) { P[i] = P[i] + vc[i]; Lo[i] = Lo[i] + l[i] + Iw[i]; mc[i] = mc[i] + cw[i] * mb; }
+    // kinetic energy of the body (dead code for sinks that ignore it)
+    ke = ke + ((vl[0] + wxr[0]) * vc[0] + (vl[1] + wxr[1]) * vc[1] + (vl[2] + wxr[2]) * vc[2] + wl[0] * Iwl[0] + wl[1] * Iwl[1] + wl[2] * Iwl[2]) * 0.5;
   };
   T p0[3] = {qf(0), qf(1), qf(2)}, v0[3] = {vf(0), vf(1), vf(2)};
   add_body(0, R0, p0, w0, v0);
@@ -224,6 +228,7 @@ __device__ __forceinline__ void kin_pass_f(QF qf, VF vf, SCF scf, OF of) {
   cross(com, P, cxP);
 #pragma unroll
   for (int i = 0; i < 3; ++i) { of.h(i, P[i]); of.h(3 + i, Lo[i] - cxP[i]); }
+  of.ke(ke);
 }
 
 // ---- chain-split sweep (used by the node linearisation): a lane evaluates the base frame and ONE leg chain only.
@@ -319,6 +324,7 @@ template <class T> struct KinOutSink {
   __device__ __forceinline__ void com(int i, const T& x) { o.com[i] = x; }
   __device__ __forceinline__ void cpos(int i, const T& x) { o.cpos[i] = x; }
   __device__ __forceinline__ void cvel(int i, const T& x) { o.cvel[i] = x; }
+  __device__ __forceinline__ void ke(const T& x) { o.ke = x; }
 };
 
 // Array form (used where the lane-private copy of q, v is needed anyway)

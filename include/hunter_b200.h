@@ -14,6 +14,7 @@
  *   hb_resident_cycle_batch <-> SqpSolver::run with its resident primalSolution_ (warm start) + the rest of LeggedController::update
  *   hb_resident_plan_cycle_batch <-> ReferenceManager::preSolverRun (planner on the device) + hb_resident_cycle_batch
  *   hb_estimator_update_batch <-> KalmanFilterEstimate::update        legged_estimation/src/LinearKalmanFilter.cpp:72-185
+ *   hb_contact_force_estimate_batch <-> StateEstimateBase::estContactForce   legged_estimation/src/StateEstimateBase.cpp:130-206
  *   hb_joint_command_batch  <-> joint command / torque law            LeggedController.cpp:186-257
  *   hb_plan_references      <-> GaitSchedule tiling + SwingTrajectoryPlanner::update + cmdVelToTargetTrajectories + calculateJointRef
  *   hb_gait_select          <-> SwitchedModelReferenceManager::calculateVelAbs + walkGait/trotGait   :185-249
@@ -124,6 +125,30 @@ typedef struct {           /* task.info:336-345 */
   double foot_sensor_noise_position, foot_sensor_noise_velocity, foot_height_sensor_noise;
 } hb_kf_params;
 
+/* state of the generalised-momentum observer behind the contact-force estimate (pSCgZinvlast_, StateEstimateBase.h:125) */
+typedef struct { double p_filtered[16]; } hb_observer_state;
+int hb_observer_reset(int B, hb_observer_state* state);   /* host only: zeros (StateEstimateBase.cpp:58-59) */
+
+/* ---- closed-loop rollout: actuation model of the simulated hardware and a batched rigid-body plant ---- */
+#define HB_ACT_CAPACITY 16
+typedef struct {           /* command buffer of one robot (LeggedHWSim::cmdBuffer_, legged_gazebo/src/LeggedHWSim.cpp:166-186) */
+  int32_t count, head;     /* entries in the ring; index of the newest one                                  */
+  double stamp[HB_ACT_CAPACITY];
+  double cmd[HB_ACT_CAPACITY][50];   /* per joint: posDes, velDes, kp, kd, ff                               */
+} hb_actuation_state;
+typedef struct {
+  double dt;                /* control period covered by one call [s] (500 Hz loop: 0.002)                  */
+  int32_t substeps;         /* semi-implicit Euler substeps per call                                        */
+  double ground_height;     /* flat ground z                                                                */
+  double ground_stiffness, ground_damping;   /* normal spring-damper per contact point [N/m], [N s/m]       */
+  double tangential_damping;                 /* viscous tangential friction [N s/m], clipped to mu * F_z    */
+  double friction_mu;
+  double joint_armature;    /* rotor inertia added to the joint diagonal of M [kg m^2] (mujoco/model/hunter/hunter.xml:6: 0.1) */
+  double joint_damping;     /* viscous joint damping [N m s/rad] (hunter.xml:6: 1)                           */
+} hb_sim_params;
+int hb_default_sim_params(hb_sim_params* p);
+int hb_actuation_reset(int B, hb_actuation_state* state);   /* host only */
+
 int hb_default_kf_params(hb_kf_params* p);
 /* x_hat = 0, P = 100 I, heights = 0 (KalmanFilterEstimate constructor, LinearKalmanFilter.cpp:24-63); host only */
 int hb_kf_reset(int B, hb_kf_state* state);
@@ -209,6 +234,25 @@ int hb_plan_references_batch_dev(hb_ctx* ctx, int B, const hb_plan_input* in, co
 int hb_estimator_update_batch_dev(hb_ctx* ctx, int B, const hb_kf_params* params, double dt, hb_kf_state* state, const double* quat,
                                   const double* ang_vel_local, const double* lin_acc_local, const double* joint_pos,
                                   const double* joint_vel, const uint8_t* contact_flag, double* rbd_out);
+/* StateEstimateBase::estContactForce (legged_estimation/src/StateEstimateBase.cpp:130-206): momentum-observer disturbance torque and the
+ * least-norm 6-D wrench at the toe frame of each foot. cutoff_frequency = contactForceEsimation.cutoffFrequency (task.info:349, 250);
+ * dt > 1 is replaced by 0.002 as in the reference. rbd: measured state (B x 32), tau_cmd: last commanded joint torques (B x 10).
+ * est_contact_force (B x 16) = [wrench_left(6), wrench_right(6), |F_l|, |F_r|, |W_l|, |W_r|]; disturbance_torque (B x 16, nullable). */
+int hb_contact_force_estimate_batch_dev(hb_ctx* ctx, int B, double cutoff_frequency, double dt, hb_observer_state* state, const double* rbd,
+                                        const double* tau_cmd, double* est_contact_force, double* disturbance_torque /*nullable*/);
+/* LeggedHWSim::writeSim (legged_gazebo/src/LeggedHWSim.cpp:166-192): command (B x 10 x 5 as written by hb_joint_command_batch) delayed by up to
+ * `delay` seconds (legged_gazebo/config/default.yaml:2, 0.009), PD + feed-forward evaluated with the current joint state -> tau (B x 10) */
+int hb_actuation_batch_dev(hb_ctx* ctx, int B, double delay, const double* time /*B*/, hb_actuation_state* state, const double* command,
+                           const double* rbd, double* tau);
+/* one control period of the batched plant: rbd (B x 32, [zyx, p, q_j, omega_world, v, qd_j]) advanced in place under the joint torques tau
+ * (B x 10); contact_force (B x 12) and contact_flag (B x 4) of the last substep are optional outputs */
+int hb_sim_step_batch_dev(hb_ctx* ctx, int B, const hb_sim_params* params, double* rbd, const double* tau, double* contact_force /*nullable*/,
+                          uint8_t* contact_flag /*nullable*/);
+/* The 500 Hz half of LeggedController::update between two MPC solves (LeggedController.cpp:154-184): evaluatePolicy of the RESIDENT solution at
+ * the absolute time t_now[i], WeightedWbc (with the previous-solution fallback), torque law. Outputs the desired state / input / mode too
+ * (inputs of hb_joint_command_batch). */
+int hb_resident_wbc_batch_dev(hb_ctx* ctx, int B, const double* t_now, const double* rbd, const uint8_t* stance_mode /*nullable*/, double* x_des,
+                              double* u_des, int32_t* mode_out, double* wbc_sol, double* torque /*nullable*/, int32_t* wbc_status /*nullable*/);
 int hb_rbd_to_centroidal_batch_dev(hb_ctx* ctx, int B, const double* rbd, double* x);
 int hb_reference_expand_batch_dev(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                                   int32_t* mode);
@@ -255,6 +299,14 @@ int hb_resident_plan_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_re
 int hb_estimator_update_batch(hb_ctx* ctx, int B, const hb_kf_params* params, double dt, hb_kf_state* state, const double* quat,
                               const double* ang_vel_local, const double* lin_acc_local, const double* joint_pos, const double* joint_vel,
                               const uint8_t* contact_flag, double* rbd_out);
+int hb_contact_force_estimate_batch(hb_ctx* ctx, int B, double cutoff_frequency, double dt, hb_observer_state* state, const double* rbd,
+                                    const double* tau_cmd, double* est_contact_force, double* disturbance_torque /*nullable*/);
+int hb_actuation_batch(hb_ctx* ctx, int B, double delay, const double* time, hb_actuation_state* state, const double* command, const double* rbd,
+                       double* tau);
+int hb_sim_step_batch(hb_ctx* ctx, int B, const hb_sim_params* params, double* rbd, const double* tau, double* contact_force /*nullable*/,
+                      uint8_t* contact_flag /*nullable*/);
+int hb_resident_wbc_batch(hb_ctx* ctx, int B, const double* t_now, const double* rbd, const uint8_t* stance_mode /*nullable*/, double* x_des, double* u_des,
+                          int32_t* mode_out, double* wbc_sol, double* torque /*nullable*/, int32_t* wbc_status /*nullable*/);
 int hb_rbd_to_centroidal_batch(hb_ctx* ctx, int B, const double* rbd, double* x);
 int hb_reference_expand_batch(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* x_ref, double* swing_ref,
                               int32_t* mode);

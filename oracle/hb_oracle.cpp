@@ -901,6 +901,32 @@ void hbo_rbd(const double* q, const double* v, double* M, double* nle, double* J
   for (int i = 0; i < NC; ++i) { D1 vc[3]; contact_velocity(kd, ud, i, vc); for (int a = 0; a < 3; ++a) dJv[3 * i + a] = vc[a].d[0]; }
 }
 
+// Terms of the momentum observer (StateEstimateBase.cpp:130-206, Pinocchio calls :157-166 restated): p = M v, generalised gravity g,
+// C' v = (dM/dt - C) v with dM/dt v from a dual number seeded ALONG v and C v from inverse dynamics (a different route than the device
+// code, which differentiates the kinetic energy per coordinate), and the 6-D toe-frame Jacobians (LOCAL_WORLD_ALIGNED) of both feet.
+void hbo_observer_terms(const double* q, const double* v, double* p, double* g, double* ctv, double* Jfoot /*2 x 6 x 16*/) {
+  double zero[NQ] = {0};
+  Kin<double> kin; forward_kinematics(q, kin);
+  rnea(q, zero, v, false, p, &kin);
+  rnea(q, zero, zero, true, g, &kin);
+  double cv[NQ];
+  rnea(q, v, zero, false, cv, &kin);
+  using D1 = Dual<1>;
+  D1 qd[NQ], zd[NQ], vd[NQ], pd[NQ];
+  for (int i = 0; i < NQ; ++i) { qd[i].v = q[i]; qd[i].d[0] = v[i]; zd[i] = D1(0.0); vd[i] = D1(v[i]); }
+  rnea<D1>(qd, zd, vd, false, pd);
+  for (int i = 0; i < NQ; ++i) ctv[i] = pd[i].d[0] - cv[i];
+  for (int f = 0; f < 2; ++f) {
+    for (int c = 0; c < NQ; ++c) {
+      double e[NQ] = {0}; e[c] = 1.0;
+      Vel<double> ve; velocities(kin, e, ve);
+      double vc[3]; contact_velocity(kin, ve, f, vc);
+      const int b = HB_CONTACT_BODY[f];
+      for (int a = 0; a < 3; ++a) { Jfoot[(f * 6 + a) * NQ + c] = vc[a]; Jfoot[(f * 6 + 3 + a) * NQ + c] = ve.w[b][a]; }
+    }
+  }
+}
+
 // computeCentroidalStateFromRbdModel (LeggedController.cpp:336; App. C.2)
 void hbo_rbd_to_centroidal(const double* rbd, double* x) {
   double q[NQ], v[NQ];

@@ -39,6 +39,7 @@ void hbo_init(void);
 void hbo_rbd(const double* q, const double* v, double* M /*16x16*/, double* nle /*16*/, double* J /*12x16*/,
              double* dJv /*12*/, double* A /*6x16*/, double* com /*3*/, double* h /*6*/, double* cpos /*12*/);
 void hbo_rbd_to_centroidal(const double* rbd /*32*/, double* x /*22*/);
+void hbo_observer_terms(const double* q, const double* v, double* p /*16*/, double* g /*16*/, double* ctv /*16*/, double* Jfoot /*2x6x16*/);
 void hbo_flow_map(const double* x, const double* u, double* f /*22*/, double* A /*22x22*/, double* B /*22x22*/);
 void hbo_ee_kinematics(const double* x, const double* u, double* pos /*12*/, double* vel /*12*/, double* dpos_dx /*12x22*/,
                        double* dvel_dx /*12x22*/, double* dvel_du /*12x22*/);

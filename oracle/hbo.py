@@ -63,6 +63,14 @@ def rbd(q, v):
     return dict(M=M, nle=nle, J=J, dJv=dJv, A=A, com=com, h=h, cpos=cpos)
 
 
+def observer_terms(q, v):
+    """p = M v, generalised gravity, C' v and the 6-D toe-frame Jacobians of both feet (momentum observer, StateEstimateBase.cpp:157-190)."""
+    q, v = _d(q), _d(v)
+    p = np.zeros(16); g = np.zeros(16); ctv = np.zeros(16); J = np.zeros((2, 6, 16))
+    lib().hbo_observer_terms(_p(q), _p(v), _p(p), _p(g), _p(ctv), _p(J))
+    return p, g, ctv, J
+
+
 def rbd_to_centroidal(rbd_state):
     r = _d(rbd_state); x = np.zeros(22)
     lib().hbo_rbd_to_centroidal(_p(r), _p(x))

@@ -595,6 +595,38 @@ def euler_rates_from_global(zyx, w):
     return np.array([w[2] + sy * r, -sz * w[0] + cz * w[1], r])
 
 
+class ContactForceObserverRef:
+    """StateEstimateBase::estContactForce (legged_estimation/src/StateEstimateBase.cpp:130-206) restated: generalised-momentum observer and
+    the SVD (least-norm) solve of the per-foot wrench, on the rigid-body terms of oracle/hb_oracle.cpp."""
+
+    def __init__(self, cutoff_frequency=250.0):
+        self.lam = cutoff_frequency
+        self.last = np.zeros(16)                       # pSCgZinvlast_
+        self.est = np.full(16, 50.0)                   # estContactforce_ (:60-61)
+        self.disturbance = np.zeros(16)
+
+    def update(self, rbd, tau_cmd, dt):
+        from . import hbo
+        if dt > 1:
+            dt = 0.002
+        gama = np.exp(-self.lam * dt); beta = (1 - gama) / (gama * dt)
+        q = np.concatenate([rbd[3:6], rbd[0:3], rbd[6:16]])
+        v = np.concatenate([rbd[19:22], euler_rates_from_global(rbd[0:3], rbd[16:19]), rbd[22:32]])
+        p, g, ctv, J = hbo.observer_terms(q, v)
+        pscg = beta * p + np.concatenate([np.zeros(6), tau_cmd]) + ctv - g
+        filt = (1 - gama) * pscg + gama * self.last
+        self.last = filt
+        self.disturbance = beta * p - filt
+        for i in range(2):
+            S_JT = J[i][:, 6 + 5 * i:11 + 5 * i].T                       # S_li * Jac_i^T  (5 x 6)
+            S_tau = self.disturbance[6 + 5 * i:11 + 5 * i]
+            self.est[6 * i:6 * i + 6] = np.linalg.pinv(S_JT) @ S_tau    # bdcSvd(...).solve: least-norm least-squares solution
+        for i in range(2):
+            self.est[12 + i] = np.linalg.norm(self.est[6 * i:6 * i + 3])
+            self.est[14 + i] = np.linalg.norm(self.est[6 * i:6 * i + 6])
+        return self.est.copy()
+
+
 class KalmanFilterRef:
     def __init__(self):
         self.x = np.zeros(18); self.P = 100.0 * np.eye(18); self.heights = np.zeros(4)
