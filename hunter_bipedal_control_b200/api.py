@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "hb_wbc_qp_batch", "hb_wbc_solve_batch", "hb_mpc_cold_start_batch", "hb_mpc_solve_batch", "hb_control_step_batch",
     "hb_rbd_to_centroidal_batch", "hb_reference_expand_batch", "hb_probe_flow_map",
     "hb_observer_reset", "hb_contact_force_estimate_batch_dev", "hb_contact_force_estimate_batch",
+    "hb_hoqp_solve_batch_dev", "hb_hierarchical_wbc_solve_batch_dev", "hb_hoqp_solve_batch", "hb_hierarchical_wbc_solve_batch", "hb_hierarchical_wbc_tasks_batch",
     "hb_default_sim_params", "hb_actuation_reset", "hb_actuation_batch_dev", "hb_actuation_batch", "hb_sim_step_batch_dev", "hb_sim_step_batch",
     "hb_resident_wbc_batch_dev", "hb_resident_wbc_batch",
     "hb_time_grid_batch_dev", "hb_reference_expand_grid_batch_dev", "hb_mpc_solve_grid_batch_dev", "hb_policy_eval_grid_batch_dev",
@@ -78,6 +79,45 @@ class HbKfParams(C.Structure):
 
 
 HB_ACT_CAPACITY = 16
+HB_HOQP_MAX_LEVELS, HB_HOQP_N, HB_HOQP_MAX_EQ, HB_HOQP_MAX_IN, HB_HOQP_MAX_STACKED = 3, 38, 32, 40, 80
+
+
+class HbHoqpProblem(C.Structure):
+    _fields_ = [("n", C.c_int32), ("levels", C.c_int32), ("ma", C.c_int32 * HB_HOQP_MAX_LEVELS), ("md", C.c_int32 * HB_HOQP_MAX_LEVELS),
+                ("a", ((C.c_double * HB_HOQP_N) * HB_HOQP_MAX_EQ) * HB_HOQP_MAX_LEVELS), ("b", (C.c_double * HB_HOQP_MAX_EQ) * HB_HOQP_MAX_LEVELS),
+                ("d", ((C.c_double * HB_HOQP_N) * HB_HOQP_MAX_IN) * HB_HOQP_MAX_LEVELS), ("f", (C.c_double * HB_HOQP_MAX_IN) * HB_HOQP_MAX_LEVELS)]
+
+
+def make_hoqp_problems(hierarchies):
+    """hierarchies: list (one per instance) of lists of tasks (a, b, d, f) by decreasing priority -> ctypes array of HbHoqpProblem."""
+    pbs = (HbHoqpProblem * len(hierarchies))()
+    for pb, levels in zip(pbs, hierarchies):
+        pb.levels = len(levels)
+        n = 0
+        for l, (a, b, d, f) in enumerate(levels):
+            a = np.zeros((0, 0)) if a is None else np.atleast_2d(np.asarray(a, dtype=float)); d = np.zeros((0, 0)) if d is None else np.atleast_2d(np.asarray(d, dtype=float))
+            n = max(n, a.shape[1] if a.size else 0, d.shape[1] if d.size else 0)
+            pb.ma[l] = a.shape[0] if a.size else 0; pb.md[l] = d.shape[0] if d.size else 0
+            for i in range(pb.ma[l]):
+                pb.b[l][i] = float(b[i])
+                for j in range(a.shape[1]):
+                    pb.a[l][i][j] = a[i, j]
+            for i in range(pb.md[l]):
+                pb.f[l][i] = float(f[i])
+                for j in range(d.shape[1]):
+                    pb.d[l][i][j] = d[i, j]
+        pb.n = n
+    return pbs
+
+
+def hoqp_tasks(pb):
+    """HbHoqpProblem -> list of (a, b, d, f) numpy tasks."""
+    out = []
+    for l in range(pb.levels):
+        a = np.array([[pb.a[l][i][j] for j in range(pb.n)] for i in range(pb.ma[l])]).reshape(pb.ma[l], pb.n)
+        d = np.array([[pb.d[l][i][j] for j in range(pb.n)] for i in range(pb.md[l])]).reshape(pb.md[l], pb.n)
+        out.append((a, np.array([pb.b[l][i] for i in range(pb.ma[l])]), d, np.array([pb.f[l][i] for i in range(pb.md[l])])))
+    return out
 
 
 class HbActuationState(C.Structure):
@@ -321,6 +361,29 @@ class Context:
                                                _ptr(ub), _ptr(m)), "hb_wbc_assemble_batch", self._h)
         return H, g, A, lb, ub, m
 
+    def hoqp_solve(self, problems):
+        """legged::HoQp cascade for a batch (ctypes array of HbHoqpProblem): returns (x [B,38], stacked slack [B,80], status [B])."""
+        B = len(problems)
+        x = np.zeros((B, HB_HOQP_N)); sl = np.zeros((B, HB_HOQP_MAX_STACKED)); st = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_hoqp_solve_batch(self._h, B, problems, _ptr(x), _ptr(sl), _ptr(st)), "hb_hoqp_solve_batch", self._h)
+        return x, sl, st
+
+    def hierarchical_wbc_tasks(self, x_des, u_des, rbd, mode):
+        x_des, u_des, rbd = map(_f64, (x_des, u_des, rbd)); B = x_des.shape[0]
+        mode = np.ascontiguousarray(mode, dtype=np.int32)
+        pbs = (HbHoqpProblem * B)()
+        _check(self._lib.hb_hierarchical_wbc_tasks_batch(self._h, B, _ptr(x_des), _ptr(u_des), _ptr(rbd), _ptr(mode), pbs), "hb_hierarchical_wbc_tasks_batch", self._h)
+        return pbs
+
+    def hierarchical_wbc_solve(self, x_des, u_des, rbd, mode):
+        """legged::HierarchicalWbc::update for a batch: returns (sol [B,38] = [qdd, F, tau], status [B])."""
+        x_des, u_des, rbd = map(_f64, (x_des, u_des, rbd)); B = x_des.shape[0]
+        mode = np.ascontiguousarray(mode, dtype=np.int32)
+        sol = np.zeros((B, NWBC)); st = np.zeros(B, dtype=np.int32)
+        _check(self._lib.hb_hierarchical_wbc_solve_batch(self._h, B, _ptr(x_des), _ptr(u_des), _ptr(rbd), _ptr(mode), _ptr(sol), _ptr(st)),
+               "hb_hierarchical_wbc_solve_batch", self._h)
+        return sol, st
+
     def mpc_cold_start(self, x0, mode):
         x0 = _f64(x0); B = x0.shape[0]
         mode = np.ascontiguousarray(mode, dtype=np.int32)
@@ -519,6 +582,19 @@ class Context:
 
 # ---------------------------------------------------------------------------------------------------------------------
 # Host-side mirrors of the reference operators (single-robot use, B = 1), for drop-in style tests.
+class HierarchicalWbc:
+    """Mirror of legged::HierarchicalWbc (legged_wbc/include/legged_wbc/HierarchicalWbc.h, src/HierarchicalWbc.cpp:18-31)."""
+
+    def __init__(self, ctx=None):
+        self._ctx = ctx or Context(max_batch=1)
+
+    def update(self, stateDesired, inputDesired, rbdStateMeasured, mode, period):
+        sol, st = self._ctx.hierarchical_wbc_solve(np.asarray(stateDesired)[None], np.asarray(inputDesired)[None], np.asarray(rbdStateMeasured)[None], [int(mode)])
+        if st[0] != 0:
+            raise HunterB200Error("[HierarchicalWbc] a level of the hierarchy did not solve (status %d)" % st[0])
+        return sol[0]
+
+
 class WeightedWbc:
     """Mirror of legged::WeightedWbc (legged_wbc/include/legged_wbc/WeightedWbc.h, WbcBase.h:41-76)."""
 

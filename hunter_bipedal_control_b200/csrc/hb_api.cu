@@ -18,6 +18,7 @@
 #include "hb_rbd.cuh"
 #include "hb_sqp.cuh"
 #include "hb_wbc.cuh"
+#include "hb_hoqp.cuh"
 
 using namespace hb;
 
@@ -132,6 +133,71 @@ __global__ void wbc_fused_kernel(int B, const double* x_des, const double* u_des
     out[NQ + 12 + lane] = t;
   }
   if (lane == 0) { if (status) status[inst] = r.status; if (iters) iters[inst] = r.iters; }
+}
+
+// ---------------------------------------------------------------------------------------------- hierarchical WBC (row N4)
+__global__ void __launch_bounds__(32) hoqp_kernel(int B, const hb_hoqp_problem* problems, double* scratch, int max_iter, double* x, double* slack, int32_t* status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int inst = blockIdx.x;
+  if (inst >= B) return;
+  HoqpShared& sh = *reinterpret_cast<HoqpShared*>(smem_raw);
+  QpWorkspace w;
+  qp_carve(reinterpret_cast<double*>(smem_raw + sizeof(HoqpShared)), HQ_NQ, w, 1, HQ_ROWS);
+  const int st = hoqp_solve_warp(problems[inst], sh, w, scratch + (size_t)inst * HQ_SCRATCH, max_iter, x + (size_t)inst * HQ_N, slack ? slack + (size_t)inst * HQ_STK : nullptr);
+  if (status && threadIdx.x == 0) status[inst] = st;
+}
+
+// The three tasks of HierarchicalWbc::update from the WBC terms of one instance (decision vector [qdd(16), F(12), tau(10)]):
+//   task0 = formulateFloatingBaseEomTask + formulateTorqueLimitsTask + formulateFrictionConeTask + formulateNoContactMotionTask
+//   task1 = formulateBaseAccelTask          task2 = formulateContactForceTask * 0.1 + formulateSwingLegTask * 1     (WbcBase.cpp:138-338)
+__global__ void __launch_bounds__(32) hwbc_tasks_kernel(int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, hb_hoqp_problem* problems) {
+  __shared__ WbcShared sh;
+  const int inst = blockIdx.x, lane = threadIdx.x;
+  if (inst >= B) return;
+  const int md_ = mode[inst];
+  int nw = 0;
+  wbc_assemble_warp(x_des + (size_t)inst * NX, u_des + (size_t)inst * NU, rbd + (size_t)inst * 32, md_, false, sh, nullptr, nullptr, nullptr, nullptr, nullptr, &nw);
+  hb_hoqp_problem& pb = problems[inst];
+  bool fl[4]; int nc = 0;
+  for (int c = 0; c < 4; ++c) { fl[c] = contact_flag(md_, c); nc += fl[c]; }
+  const int nsw = 4 - nc;
+  const int ma0 = 16 + 3 * nsw + 3 * nc, md0 = 20 + 5 * nc, ma1 = 6, ma2 = 12 + 3 * nsw;
+  if (lane == 0) { pb.n = NWBC; pb.levels = 3; pb.ma[0] = ma0; pb.md[0] = md0; pb.ma[1] = ma1; pb.md[1] = 0; pb.ma[2] = ma2; pb.md[2] = 0; }
+  for (int idx = lane; idx < HB_HOQP_MAX_EQ * NWBC; idx += 32) { (&pb.a[0][0][0])[idx] = 0.0; (&pb.a[1][0][0])[idx] = 0.0; (&pb.a[2][0][0])[idx] = 0.0; }
+  for (int idx = lane; idx < HB_HOQP_MAX_IN * NWBC; idx += 32) (&pb.d[0][0][0])[idx] = 0.0;
+  __syncwarp();
+  // task0 equalities: EoM rows [M | -J' | -S'] x = -nle
+  for (int idx = lane; idx < 16 * NWBC; idx += 32) {
+    const int i = idx / NWBC, j = idx - i * NWBC;
+    double a;
+    if (j < NQ) a = sh.M[i * 16 + j];
+    else if (j < NQ + 12) a = -sh.J[(j - NQ) * 16 + i];
+    else a = (i >= 6 && j - NQ - 12 == i - 6) ? -1.0 : 0.0;
+    pb.a[0][i][j] = a;
+  }
+  if (lane < 16) pb.b[0][lane] = -sh.nle[lane];
+  if (lane == 0) {
+    int r = 16;
+    for (int c = 0; c < 4; ++c) if (!fl[c]) for (int a = 0; a < 3; ++a) { pb.a[0][r][NQ + 3 * c + a] = 1.0; pb.b[0][r] = 0.0; ++r; }      // zero swing force
+    for (int c = 0; c < 4; ++c) if (fl[c]) for (int a = 0; a < 3; ++a) {                                                                  // no contact motion
+      for (int j = 0; j < NQ; ++j) pb.a[0][r][j] = sh.J[(3 * c + a) * 16 + j];
+      pb.b[0][r] = -sh.dJv[3 * c + a]; ++r;
+    }
+    // task0 inequalities: torque limits, friction pyramid
+    int q = 0;
+    for (int sgn = 0; sgn < 2; ++sgn) for (int j = 0; j < NJ; ++j) { pb.d[0][q][NQ + 12 + j] = sgn == 0 ? 1.0 : -1.0; pb.f[0][q] = c_model.torque_limit[j]; ++q; }
+    const double mu = HB_WBC_FRICTION_MU;
+    const double pyr[5][3] = {{0, 0, -1}, {1, 0, -mu}, {-1, 0, -mu}, {0, 1, -mu}, {0, -1, -mu}};
+    for (int c = 0; c < 4; ++c) if (fl[c]) for (int k = 0; k < 5; ++k) { for (int a = 0; a < 3; ++a) pb.d[0][q][NQ + 3 * c + a] = pyr[k][a]; pb.f[0][q] = 0.0; ++q; }
+    // task2 first part: 0.1 * (F = F_des)
+    for (int j = 0; j < 12; ++j) { pb.a[2][j][NQ + j] = 0.1; pb.b[2][j] = 0.1 * u_des[(size_t)inst * NU + j]; }
+  }
+  // task1: base acceleration rows (the weighted formulation's base rows with the weight divided out); task2 second part: swing rows
+  const int nswr = 3 * nsw;
+  for (int idx = lane; idx < 6 * NQ; idx += 32) { const int i = idx / NQ, j = idx - i * NQ; pb.a[1][i][j] = sh.Aw[(nswr + i) * 16 + j] / HB_WBC_WEIGHT_BASE; }
+  if (lane < 6) pb.b[1][lane] = sh.bw[nswr + lane] / HB_WBC_WEIGHT_BASE;
+  for (int idx = lane; idx < nswr * NQ; idx += 32) { const int i = idx / NQ, j = idx - i * NQ; pb.a[2][12 + i][j] = sh.Aw[i * 16 + j] / HB_WBC_WEIGHT_SWING; }
+  if (lane < nswr) pb.b[2][12 + lane] = sh.bw[lane] / HB_WBC_WEIGHT_SWING;
 }
 
 // LeggedRobotInitializer::compute (initialization/LeggedRobotInitializer.cpp:67-77)
@@ -885,6 +951,7 @@ struct hb_ctx {
   double *s_x0, *s_xref, *s_swing, *s_xt, *s_ut, *s_rbd, *s_xd, *s_ud, *s_sol, *s_tau, *s_t0, *s_misc;
   double *res_xt = nullptr, *res_ut = nullptr, *res_t0 = nullptr;   // resident primal solution (hb_resident_cycle_batch)
   double *s_tk = nullptr, *res_tk = nullptr; int32_t *s_nn = nullptr, *res_nn = nullptr;   // node times / interval counts (event-node grids)
+  double* hoqp_scratch = nullptr; hb_hoqp_problem* hoqp_prob = nullptr;   // hierarchical WBC (allocated by its first call)
   int32_t* res_mode = nullptr;                                      // node modes of the resident solution (policy evaluation between MPC solves)
   int res_valid = 0;                                                // number of instances holding a previous solution
   hb_plan_input* s_plan = nullptr; double* res_stance = nullptr; int32_t* s_pstatus = nullptr;   // device planner (row N1)
@@ -1045,6 +1112,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
     attr((const void*)probe_flow_map_kernel, sizeof(ProbeShared));
     attr((const void*)qp_batch_kernel, 200 * 1024);
     attr((const void*)wbc_fused_kernel, wbc_fused_doubles() * sizeof(double));
+    attr((const void*)hoqp_kernel, hoqp_smem_bytes());
     attr((const void*)lin_kernel, 4 * sizeof(LinHalf) + sizeof(ChainModel));
     attr((const void*)lq_kernel, sizeof(LqShared));
     attr((const void*)riccati_kernel, sizeof(RicShared));
@@ -1062,7 +1130,7 @@ int hb_destroy(hb_ctx* ctx) {
   void* ptrs[] = {ctx->lin, ctx->proj, ctx->rk, ctx->dxt, ctx->dut, ctx->perf, ctx->flags, ctx->xdes, ctx->udes,
                   ctx->wsol, ctx->wstatus, ctx->witers, ctx->wmode, ctx->s_x0, ctx->s_xref, ctx->s_swing, ctx->s_xt, ctx->s_ut, ctx->s_rbd, ctx->s_xd,
                   ctx->s_ud, ctx->s_sol, ctx->s_tau, ctx->s_t0, ctx->s_misc, ctx->s_mode, ctx->s_imode, ctx->s_status, ctx->s_iters, ctx->s_stance,
-                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf, ctx->res_sol, ctx->s_tk, ctx->res_tk, ctx->s_nn, ctx->res_nn, ctx->res_mode};
+                  ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf, ctx->res_sol, ctx->s_tk, ctx->res_tk, ctx->s_nn, ctx->res_nn, ctx->res_mode, ctx->hoqp_scratch, ctx->hoqp_prob};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
   if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
@@ -1173,6 +1241,55 @@ int hb_wbc_qp_rows_batch_dev(hb_ctx* ctx, int B, int n, int m_alloc, const int32
   if (B == 0) return HB_OK;
   if (set_device(ctx)) return HB_ECUDA;
   return launch_qp(ctx, B, n, m_alloc, H, g, A, lbA, ubA, (size_t)n * n, (size_t)m_alloc * n, (size_t)m_alloc, m_rows, x, status, iters);
+}
+
+static int hoqp_reserve(hb_ctx* ctx) {
+  if (ctx->hoqp_scratch) return HB_OK;
+  const size_t Bc = ctx->cfg.max_batch;
+  if (dalloc(&ctx->hoqp_scratch, Bc * HQ_SCRATCH) != cudaSuccess || dalloc(&ctx->hoqp_prob, Bc) != cudaSuccess) {
+    cudaGetLastError();
+    if (ctx->hoqp_scratch) cudaFree(ctx->hoqp_scratch);
+    ctx->hoqp_scratch = nullptr; ctx->hoqp_prob = nullptr;
+    return HB_ENOMEM;
+  }
+  return HB_OK;
+}
+
+int hb_hoqp_solve_batch_dev(hb_ctx* ctx, int B, const hb_hoqp_problem* problems, double* x, double* slack, int32_t* status) {
+  if (!ctx || B < 0 || !problems || !x) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  int rc = hoqp_reserve(ctx);
+  if (rc) return rc;
+  prof_begin(ctx, K_QP);
+  hoqp_kernel<<<B, 32, hoqp_smem_bytes(), ctx->stream>>>(B, problems, ctx->hoqp_scratch, 2 * ctx->cfg.qp_max_iter, x, slack, status);
+  prof_end(ctx);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+static int hwbc_tasks_dev(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, hb_hoqp_problem* problems) {
+  prof_begin(ctx, K_WBC_ASSEMBLE);
+  hwbc_tasks_kernel<<<B, 32, 0, ctx->stream>>>(B, x_des, u_des, rbd, mode, problems);
+  prof_end(ctx);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return HB_OK;
+}
+
+int hb_hierarchical_wbc_solve_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, double* sol,
+                                        int32_t* status) {
+  if (!ctx || B < 0 || !x_des || !u_des || !rbd || !mode || !sol) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  int rc = hoqp_reserve(ctx);
+  if (rc) return rc;
+  rc = hwbc_tasks_dev(ctx, B, x_des, u_des, rbd, mode, ctx->hoqp_prob);
+  if (rc) return rc;
+  return hb_hoqp_solve_batch_dev(ctx, B, ctx->hoqp_prob, sol, nullptr, status);
 }
 
 int hb_mpc_cold_start_batch_dev(hb_ctx* ctx, int B, const double* x0, const int32_t* mode, double* x_traj, double* u_traj) {
@@ -1641,6 +1758,63 @@ int hb_wbc_solve_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_
   H2D(ctx->s_imode, mode, sizeof(int32_t) * B);
   if (stance_mode) H2D(ctx->s_stance, stance_mode, B);
   int rc = hb_wbc_solve_batch_dev(ctx, B, ctx->s_xd, ctx->s_ud, ctx->s_rbd, ctx->s_imode, stance_mode ? ctx->s_stance : nullptr, ctx->s_sol, ctx->s_status);
+  if (rc) return rc;
+  D2H(sol, ctx->s_sol, sizeof(double) * B * NWBC);
+  if (status) D2H(status, ctx->s_status, sizeof(int32_t) * B);
+  return hb_sync(ctx);
+}
+
+int hb_hoqp_solve_batch(hb_ctx* ctx, int B, const hb_hoqp_problem* problems, double* x, double* slack, int32_t* status) {
+  if (!ctx || B < 0 || !problems || !x) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  for (int i = 0; i < B; ++i) {
+    const hb_hoqp_problem& p = problems[i];
+    if (p.n < 1 || p.n > HB_HOQP_N || p.levels < 1 || p.levels > HB_HOQP_MAX_LEVELS) return HB_EINVAL;
+    int stk = 0;
+    for (int l = 0; l < p.levels; ++l) { if (p.ma[l] < 0 || p.ma[l] > HB_HOQP_MAX_EQ || p.md[l] < 0 || p.md[l] > HB_HOQP_MAX_IN) return HB_EINVAL; stk += p.md[l]; }
+    if (stk > HB_HOQP_MAX_STACKED) return HB_EINVAL;
+  }
+  if (set_device(ctx)) return HB_ECUDA;
+  int rc = hoqp_reserve(ctx);
+  if (rc) return rc;
+  rc = qp_staging_reserve(ctx, (size_t)B * (HQ_N + HQ_STK + 1));
+  if (rc) return rc;
+  double* dx = ctx->s_qpH; double* dsl = dx + (size_t)B * HQ_N; int32_t* dst = reinterpret_cast<int32_t*>(dsl + (size_t)B * HQ_STK);
+  H2D(ctx->hoqp_prob, problems, sizeof(hb_hoqp_problem) * B);
+  rc = hb_hoqp_solve_batch_dev(ctx, B, ctx->hoqp_prob, dx, dsl, dst);
+  if (rc) return rc;
+  D2H(x, dx, sizeof(double) * B * HQ_N);
+  if (slack) D2H(slack, dsl, sizeof(double) * B * HQ_STK);
+  if (status) D2H(status, dst, sizeof(int32_t) * B);
+  return hb_sync(ctx);
+}
+
+int hb_hierarchical_wbc_tasks_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                                    hb_hoqp_problem* problems) {
+  if (!ctx || B < 0 || !x_des || !u_des || !rbd || !mode || !problems) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  int rc = hoqp_reserve(ctx);
+  if (rc) return rc;
+  H2D(ctx->s_xd, x_des, sizeof(double) * B * NX); H2D(ctx->s_ud, u_des, sizeof(double) * B * NU); H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32);
+  H2D(ctx->s_imode, mode, sizeof(int32_t) * B);
+  rc = hwbc_tasks_dev(ctx, B, ctx->s_xd, ctx->s_ud, ctx->s_rbd, ctx->s_imode, ctx->hoqp_prob);
+  if (rc) return rc;
+  D2H(problems, ctx->hoqp_prob, sizeof(hb_hoqp_problem) * B);
+  return hb_sync(ctx);
+}
+
+int hb_hierarchical_wbc_solve_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, double* sol,
+                                    int32_t* status) {
+  if (!ctx || B < 0 || !x_des || !u_des || !rbd || !mode || !sol) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  if (set_device(ctx)) return HB_ECUDA;
+  H2D(ctx->s_xd, x_des, sizeof(double) * B * NX); H2D(ctx->s_ud, u_des, sizeof(double) * B * NU); H2D(ctx->s_rbd, rbd, sizeof(double) * B * 32);
+  H2D(ctx->s_imode, mode, sizeof(int32_t) * B);
+  int rc = hb_hierarchical_wbc_solve_batch_dev(ctx, B, ctx->s_xd, ctx->s_ud, ctx->s_rbd, ctx->s_imode, ctx->s_sol, ctx->s_status);
   if (rc) return rc;
   D2H(sol, ctx->s_sol, sizeof(double) * B * NWBC);
   if (status) D2H(status, ctx->s_status, sizeof(int32_t) * B);

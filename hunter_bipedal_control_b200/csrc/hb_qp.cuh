@@ -14,10 +14,10 @@
 
 namespace hb {
 
-constexpr int QP_MAX_N = 40;    // variables
+constexpr int QP_MAX_N = 80;    // variables (38 for the WBC; 78 for a lifted HoQP level: 38 decision + 40 slack variables)
 constexpr int QP_MAX_EQ = 32;   // equality rows
 constexpr int QP_MAX_IN = 96;   // one-sided inequality entries (two-sided rows count twice)
-constexpr int QP_MAX_M = 64;    // rows of A
+constexpr int QP_MAX_M = 160;   // rows of A
 
 struct QpWorkspace {
   double *H, *Aeq, *K, *V, *S;

@@ -6,6 +6,8 @@
  *   hb_wbc_solve_batch      <-> legged::WeightedWbc::update            legged_wbc/src/WeightedWbc.cpp:18-66,
  *                               legged::WbcBase::update               legged_wbc/include/legged_wbc/WbcBase.h:43-44
  *   hb_wbc_qp_batch         <-> qpOASES::QProblem::init + getPrimalSolution   legged_wbc/src/WeightedWbc.cpp:44-55
+ *   hb_hierarchical_wbc_solve_batch <-> legged::HierarchicalWbc::update   legged_wbc/src/HierarchicalWbc.cpp:18-31
+ *   hb_hoqp_solve_batch     <-> legged::HoQp (null-space cascade)          legged_wbc/src/HoQp.cpp:21-198
  *   hb_mpc_solve_batch      <-> ocs2::MPC_MRT_Interface::advanceMpc -> SqpMpc/SqpSolver::run (one SQP iteration)
  *                               legged_controllers/src/LeggedController.cpp:378-379,406
  *   hb_mpc_cold_start_batch <-> LeggedRobotInitializer::compute       legged_interface/src/initialization/LeggedRobotInitializer.cpp:67-77
@@ -129,6 +131,19 @@ typedef struct {           /* task.info:336-345 */
 typedef struct { double p_filtered[16]; } hb_observer_state;
 int hb_observer_reset(int B, hb_observer_state* state);   /* host only: zeros (StateEstimateBase.cpp:58-59) */
 
+/* ---- hierarchical QP: legged::HoQp / legged::HierarchicalWbc ---- */
+#define HB_HOQP_MAX_LEVELS 3
+#define HB_HOQP_N 38            /* decision variables (the WBC's [qdd, F, tau])                             */
+#define HB_HOQP_MAX_EQ 32       /* rows of a (equality task) per level                                      */
+#define HB_HOQP_MAX_IN 40       /* rows of d (inequality task) per level                                    */
+#define HB_HOQP_MAX_STACKED 80  /* inequality rows of all levels together                                   */
+typedef struct {                /* one hierarchy: level 0 has the highest priority (Task a x = b, d x <= f; legged_wbc/include/legged_wbc/Task.h) */
+  int32_t n, levels;
+  int32_t ma[HB_HOQP_MAX_LEVELS], md[HB_HOQP_MAX_LEVELS];
+  double a[HB_HOQP_MAX_LEVELS][HB_HOQP_MAX_EQ][HB_HOQP_N], b[HB_HOQP_MAX_LEVELS][HB_HOQP_MAX_EQ];
+  double d[HB_HOQP_MAX_LEVELS][HB_HOQP_MAX_IN][HB_HOQP_N], f[HB_HOQP_MAX_LEVELS][HB_HOQP_MAX_IN];
+} hb_hoqp_problem;
+
 /* ---- closed-loop rollout: actuation model of the simulated hardware and a batched rigid-body plant ---- */
 #define HB_ACT_CAPACITY 16
 typedef struct {           /* command buffer of one robot (LeggedHWSim::cmdBuffer_, legged_gazebo/src/LeggedHWSim.cpp:166-186) */
@@ -185,6 +200,13 @@ int hb_wbc_assemble_batch_dev(hb_ctx* ctx, int B, const double* x_des, const dou
 /* hb_wbc_qp_batch_dev with a per-problem row count: A / lbA / ubA are allocated with m_alloc rows, problem i uses its first m_rows[i] */
 int hb_wbc_qp_rows_batch_dev(hb_ctx* ctx, int B, int n, int m_alloc, const int32_t* m_rows, const double* H, const double* g,
                              const double* A, const double* lbA, const double* ubA, double* x, int32_t* status, int32_t* iters);
+/* HoQp cascade (legged_wbc/src/HoQp.cpp:21-198): x (B x 38, first n entries used) = solution of the lowest level (HoQp::getSolutions),
+ * slack (B x 80, nullable) = stacked slack solutions in level order, status[i] = 0 or 10 * (QP status) + level of the first failing level */
+int hb_hoqp_solve_batch_dev(hb_ctx* ctx, int B, const hb_hoqp_problem* problems, double* x, double* slack /*nullable*/, int32_t* status /*nullable*/);
+/* legged::HierarchicalWbc::update (legged_wbc/src/HierarchicalWbc.cpp:18-31): task0 = floating-base EoM + torque limits + friction cone +
+ * no contact motion, task1 = base acceleration, task2 = 0.1 * contact force + swing leg; sol (B x 38) = [qdd, F, tau] */
+int hb_hierarchical_wbc_solve_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                                        double* sol, int32_t* status /*nullable*/);
 int hb_mpc_cold_start_batch_dev(hb_ctx* ctx, int B, const double* x0, const int32_t* mode, double* x_traj, double* u_traj);
 int hb_mpc_solve_batch_dev(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
                            double* x_traj, double* u_traj, hb_solve_info* info);
@@ -270,6 +292,12 @@ int hb_wbc_solve_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_
                        const uint8_t* stance_mode, double* sol, int32_t* status);
 int hb_wbc_assemble_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
                           const uint8_t* stance_mode /*nullable*/, double* H, double* g, double* A, double* lbA, double* ubA, int32_t* m_rows);
+int hb_hoqp_solve_batch(hb_ctx* ctx, int B, const hb_hoqp_problem* problems, double* x, double* slack /*nullable*/, int32_t* status /*nullable*/);
+int hb_hierarchical_wbc_solve_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, double* sol,
+                                    int32_t* status /*nullable*/);
+/* the three tasks HierarchicalWbc::update builds, one hb_hoqp_problem per instance; for inspection / parity tests */
+int hb_hierarchical_wbc_tasks_batch(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                                    hb_hoqp_problem* problems);
 int hb_mpc_cold_start_batch(hb_ctx* ctx, int B, const double* x0, const int32_t* mode, double* x_traj, double* u_traj);
 int hb_mpc_solve_batch(hb_ctx* ctx, int B, const double* x0, const double* x_ref, const double* swing_ref, const int32_t* mode,
                        double* x_traj, double* u_traj, hb_solve_info* info);
