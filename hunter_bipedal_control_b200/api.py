@@ -29,11 +29,12 @@ EXPORTED_SYMBOLS = [
     "hb_wbc_qp_batch", "hb_wbc_solve_batch", "hb_mpc_cold_start_batch", "hb_mpc_solve_batch", "hb_control_step_batch",
     "hb_rbd_to_centroidal_batch", "hb_reference_expand_batch", "hb_probe_flow_map",
     "hb_observer_reset", "hb_contact_force_estimate_batch_dev", "hb_contact_force_estimate_batch",
+    "hb_default_wbc_settings", "hb_parse_task_info", "hb_wbc_get_settings", "hb_wbc_set_settings", "hb_wbc_set_kp_kd", "hb_load_task_info",
     "hb_hoqp_solve_batch_dev", "hb_hierarchical_wbc_solve_batch_dev", "hb_hoqp_solve_batch", "hb_hierarchical_wbc_solve_batch", "hb_hierarchical_wbc_tasks_batch",
     "hb_default_sim_params", "hb_actuation_reset", "hb_actuation_batch_dev", "hb_actuation_batch", "hb_sim_step_batch_dev", "hb_sim_step_batch",
     "hb_resident_wbc_batch_dev", "hb_resident_wbc_batch",
     "hb_time_grid_batch_dev", "hb_reference_expand_grid_batch_dev", "hb_mpc_solve_grid_batch_dev", "hb_policy_eval_grid_batch_dev",
-    "hb_time_grid_batch", "hb_reference_expand_grid_batch", "hb_mpc_solve_grid_batch", "hb_resident_read_grid_batch",
+    "hb_time_grid_batch", "hb_reference_expand_grid_batch", "hb_mpc_solve_grid_batch", "hb_resident_read_grid_batch", "hb_resident_write_batch",
 ]
 
 
@@ -76,6 +77,27 @@ class HbKfState(C.Structure):
 class HbKfParams(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("foot_radius", "imu_process_noise_position", "imu_process_noise_velocity", "foot_process_noise_position",
                                           "foot_sensor_noise_position", "foot_sensor_noise_velocity", "foot_height_sensor_noise")]
+
+
+class HbWbcSettings(C.Structure):
+    _fields_ = [("torque_limits", C.c_double * 5)] + [(k, C.c_double) for k in (
+        "friction_coefficient", "swing_kp", "swing_kd", "base_accel_kp", "base_accel_kd", "base_height_kp", "base_height_kd", "base_angular_kp",
+        "base_angular_kd", "weight_swing_leg", "weight_base_accel", "weight_contact_force")]
+
+    def as_array(self):
+        return np.frombuffer(bytes(self), dtype=np.float64).copy()
+
+
+class HbTaskInfo(C.Structure):
+    _fields_ = [("wbc", HbWbcSettings), ("kalman", C.c_double * 7), ("contact_force_cutoff_frequency", C.c_double), ("contact_threshold", C.c_double),
+                ("sqp_dt", C.c_double), ("sqp_iteration", C.c_int32), ("mpc_time_horizon", C.c_double), ("mpc_cold_start", C.c_int32), ("found", C.c_int32)]
+
+
+def parse_task_info(path):
+    """hb_parse_task_info: the WBC / estimator / discretisation settings of a task.info file (host only)."""
+    ti = HbTaskInfo()
+    _check(load_library().hb_parse_task_info(str(path).encode(), C.byref(ti)), "hb_parse_task_info")
+    return ti
 
 
 HB_ACT_CAPACITY = 16
@@ -314,6 +336,21 @@ class Context:
     def sync(self):
         _check(self._lib.hb_sync(self._h), "hb_sync")
 
+    # ------------------------------------------------------------------ run-time WBC settings (WbcBase::loadTasksSetting / setKpKd)
+    def wbc_settings(self):
+        s = HbWbcSettings()
+        _check(self._lib.hb_wbc_get_settings(self._h, C.byref(s)), "hb_wbc_get_settings")
+        return s
+
+    def set_wbc_settings(self, s):
+        _check(self._lib.hb_wbc_set_settings(self._h, C.byref(s)), "hb_wbc_set_settings")
+
+    def set_kp_kd(self, swing_kp, swing_kd):
+        _check(self._lib.hb_wbc_set_kp_kd(self._h, C.c_double(swing_kp), C.c_double(swing_kd)), "hb_wbc_set_kp_kd")
+
+    def load_task_info(self, path):
+        _check(self._lib.hb_load_task_info(self._h, str(path).encode()), "hb_load_task_info")
+
     @property
     def launch_count(self):
         return int(self._lib.hb_launch_count(self._h))
@@ -423,6 +460,13 @@ class Context:
         _check(self._lib.hb_mpc_solve_grid_batch(self._h, B, _ptr(x0), _ptr(tk), _ptr(nn), _ptr(x_ref), _ptr(swing), _ptr(mode), _ptr(xt), _ptr(ut), _ptr(info)),
                "hb_mpc_solve_grid_batch", self._h)
         return xt, ut, info
+
+    def resident_write(self, t0, xt, ut, mode=None, node_times=None, n_intervals=None):
+        """Restore a resident-solution snapshot (hb_resident_write_batch)."""
+        t0, xt, ut = _f64(t0), _f64(xt), _f64(ut); B = t0.shape[0]
+        md = None if mode is None else np.ascontiguousarray(mode, dtype=np.int32)
+        tk = None if node_times is None else _f64(node_times); nn = None if n_intervals is None else np.ascontiguousarray(n_intervals, dtype=np.int32)
+        _check(self._lib.hb_resident_write_batch(self._h, B, _ptr(t0), _ptr(xt), _ptr(ut), _ptr(md), _ptr(tk), _ptr(nn)), "hb_resident_write_batch", self._h)
 
     def resident_read_grid(self, B):
         tk = np.zeros((B, self.N + 1)); nn = np.zeros(B, dtype=np.int32)
@@ -604,8 +648,16 @@ class WeightedWbc:
         self._last = None
 
     def loadTasksSetting(self, taskFile=None, verbose=False):
-        """Gains are compiled in from task.info through include/hunter_model_constants.h (WbcBase.cpp:352-411)."""
-        return None
+        """WbcBase::loadTasksSetting + WeightedWbc::loadTasksSetting (WbcBase.cpp:352-411, WeightedWbc.cpp:96-111): torque limits, friction
+        coefficient, task gains and weights from the task file; without a file the shipped values stay in force."""
+        if taskFile is not None:
+            self._ctx.load_task_info(taskFile)
+        if verbose:
+            s = self._ctx.wbc_settings()
+            print(" #### WBC settings:", {k: (list(getattr(s, k)) if k == "torque_limits" else getattr(s, k)) for k, _ in s._fields_})
+
+    def setKpKd(self, swingKp, swingKd):
+        self._ctx.set_kp_kd(swingKp, swingKd)
 
     def setStanceMode(self, flag):
         self._stance_mode = bool(flag)

@@ -12,6 +12,8 @@
 #include "hb_mpc.cuh"
 #include "hb_planner.h"
 #include <algorithm>
+#include <string>
+#include <utility>
 #include <thread>
 #include <vector>
 #include "hb_qp.cuh"
@@ -71,7 +73,7 @@ __global__ void qp_batch_kernel(int B, int n, int m, const double* H, const doub
   if (lane_id() == 0) { if (status) status[inst] = r.status; if (iters) iters[inst] = r.iters; }
 }
 
-__global__ void wbc_assemble_kernel(int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+__global__ void wbc_assemble_kernel(int B, hb_wbc_settings ws, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
                                     const uint8_t* stance_mode, double* H, double* g, double* A, double* lbA, double* ubA, int32_t* m_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -79,7 +81,7 @@ __global__ void wbc_assemble_kernel(int B, const double* x_des, const double* u_
   if (inst >= B) return;
   WbcShared& sh = reinterpret_cast<WbcShared*>(smem_raw)[warp];
   const int m = wbc_assemble_warp(x_des + (size_t)inst * NX, u_des + (size_t)inst * NU, rbd + (size_t)inst * 32, mode[inst],
-                                  stance_mode ? stance_mode[inst] != 0 : false, sh, H + (size_t)inst * QP_STRIDE_H, g + (size_t)inst * NWBC,
+                                  stance_mode ? stance_mode[inst] != 0 : false, ws, sh, H + (size_t)inst * QP_STRIDE_H, g + (size_t)inst * NWBC,
                                   A + (size_t)inst * QP_STRIDE_A, lbA + (size_t)inst * WBC_ROWS, ubA + (size_t)inst * WBC_ROWS);
   if (lane_id() == 0) m_out[inst] = m;
 }
@@ -90,7 +92,7 @@ __global__ void wbc_assemble_kernel(int B, const double* x_des, const double* u_
 constexpr int WZ_N = 28, WZ_ME = 6, WZ_MI = 40, WZ_ROWS = 36;
 __host__ __device__ inline size_t wbc_fused_doubles() { return qp_workspace_doubles(WZ_N, WZ_ME, WZ_MI) + WZ_ROWS * WZ_N + 2 * WZ_ROWS + 3 * WZ_N + 16 + 8; }
 
-__global__ void wbc_fused_kernel(int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const uint8_t* stance_mode,
+__global__ void wbc_fused_kernel(int B, hb_wbc_settings ws, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, const uint8_t* stance_mode,
                                  double rho, int max_iter, double* sol, int32_t* status, int32_t* iters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
@@ -111,10 +113,10 @@ __global__ void wbc_fused_kernel(int B, const double* x_des, const double* u_des
   WbcShared& sh = *reinterpret_cast<WbcShared*>(w.K);   // K, V, S, vectors: dead until the QP starts
   const int md = mode[inst];
   int nw = 0;
-  wbc_assemble_warp(x_des + (size_t)inst * NX, u_des + (size_t)inst * NU, rbd + (size_t)inst * 32, md, stance_mode ? stance_mode[inst] != 0 : false, sh,
+  wbc_assemble_warp(x_des + (size_t)inst * NX, u_des + (size_t)inst * NU, rbd + (size_t)inst * 32, md, stance_mode ? stance_mode[inst] != 0 : false, ws, sh,
                     nullptr, nullptr, nullptr, nullptr, nullptr, &nw);
   int m = 0;
-  const int nz = wbc_reduced_build(sh, md, nw, rho, w.H, qp_ld(WZ_N), gz, Az, lbz, ubz, stcol, m);
+  const int nz = wbc_reduced_build(sh, md, nw, stance_mode ? stance_mode[inst] != 0 : false, rho, ws, u_des + (size_t)inst * NU, w.H, qp_ld(WZ_N), gz, Az, lbz, ubz, stcol, m);
   if (lane < NJ) nlej[lane] = sh.nle[6 + lane];
   __syncwarp();
   // the workspace is carved for n = 28 (leading dimension 29); smaller problems (nz = 22, 16) use the same leading dimension
@@ -150,13 +152,14 @@ __global__ void __launch_bounds__(32) hoqp_kernel(int B, const hb_hoqp_problem* 
 // The three tasks of HierarchicalWbc::update from the WBC terms of one instance (decision vector [qdd(16), F(12), tau(10)]):
 //   task0 = formulateFloatingBaseEomTask + formulateTorqueLimitsTask + formulateFrictionConeTask + formulateNoContactMotionTask
 //   task1 = formulateBaseAccelTask          task2 = formulateContactForceTask * 0.1 + formulateSwingLegTask * 1     (WbcBase.cpp:138-338)
-__global__ void __launch_bounds__(32) hwbc_tasks_kernel(int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, hb_hoqp_problem* problems) {
+__global__ void __launch_bounds__(32) hwbc_tasks_kernel(int B, hb_wbc_settings ws, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                                                        hb_hoqp_problem* problems) {
   __shared__ WbcShared sh;
   const int inst = blockIdx.x, lane = threadIdx.x;
   if (inst >= B) return;
   const int md_ = mode[inst];
   int nw = 0;
-  wbc_assemble_warp(x_des + (size_t)inst * NX, u_des + (size_t)inst * NU, rbd + (size_t)inst * 32, md_, false, sh, nullptr, nullptr, nullptr, nullptr, nullptr, &nw);
+  wbc_assemble_warp(x_des + (size_t)inst * NX, u_des + (size_t)inst * NU, rbd + (size_t)inst * 32, md_, false, ws, sh, nullptr, nullptr, nullptr, nullptr, nullptr, &nw);
   hb_hoqp_problem& pb = problems[inst];
   bool fl[4]; int nc = 0;
   for (int c = 0; c < 4; ++c) { fl[c] = contact_flag(md_, c); nc += fl[c]; }
@@ -185,8 +188,8 @@ __global__ void __launch_bounds__(32) hwbc_tasks_kernel(int B, const double* x_d
     }
     // task0 inequalities: torque limits, friction pyramid
     int q = 0;
-    for (int sgn = 0; sgn < 2; ++sgn) for (int j = 0; j < NJ; ++j) { pb.d[0][q][NQ + 12 + j] = sgn == 0 ? 1.0 : -1.0; pb.f[0][q] = c_model.torque_limit[j]; ++q; }
-    const double mu = HB_WBC_FRICTION_MU;
+    for (int sgn = 0; sgn < 2; ++sgn) for (int j = 0; j < NJ; ++j) { pb.d[0][q][NQ + 12 + j] = sgn == 0 ? 1.0 : -1.0; pb.f[0][q] = ws.torque_limits[j % 5]; ++q; }
+    const double mu = ws.friction_coefficient;
     const double pyr[5][3] = {{0, 0, -1}, {1, 0, -mu}, {-1, 0, -mu}, {0, 1, -mu}, {0, -1, -mu}};
     for (int c = 0; c < 4; ++c) if (fl[c]) for (int k = 0; k < 5; ++k) { for (int a = 0; a < 3; ++a) pb.d[0][q][NQ + 3 * c + a] = pyr[k][a]; pb.f[0][q] = 0.0; ++q; }
     // task2 first part: 0.1 * (F = F_des)
@@ -194,10 +197,10 @@ __global__ void __launch_bounds__(32) hwbc_tasks_kernel(int B, const double* x_d
   }
   // task1: base acceleration rows (the weighted formulation's base rows with the weight divided out); task2 second part: swing rows
   const int nswr = 3 * nsw;
-  for (int idx = lane; idx < 6 * NQ; idx += 32) { const int i = idx / NQ, j = idx - i * NQ; pb.a[1][i][j] = sh.Aw[(nswr + i) * 16 + j] / HB_WBC_WEIGHT_BASE; }
-  if (lane < 6) pb.b[1][lane] = sh.bw[nswr + lane] / HB_WBC_WEIGHT_BASE;
-  for (int idx = lane; idx < nswr * NQ; idx += 32) { const int i = idx / NQ, j = idx - i * NQ; pb.a[2][12 + i][j] = sh.Aw[i * 16 + j] / HB_WBC_WEIGHT_SWING; }
-  if (lane < nswr) pb.b[2][12 + lane] = sh.bw[lane] / HB_WBC_WEIGHT_SWING;
+  for (int idx = lane; idx < 6 * NQ; idx += 32) { const int i = idx / NQ, j = idx - i * NQ; pb.a[1][i][j] = sh.Aw[(nswr + i) * 16 + j] / ws.weight_base_accel; }
+  if (lane < 6) pb.b[1][lane] = sh.bw[nswr + lane] / ws.weight_base_accel;
+  for (int idx = lane; idx < nswr * NQ; idx += 32) { const int i = idx / NQ, j = idx - i * NQ; pb.a[2][12 + i][j] = sh.Aw[i * 16 + j] / ws.weight_swing_leg; }
+  if (lane < nswr) pb.b[2][12 + lane] = sh.bw[lane] / ws.weight_swing_leg;
 }
 
 // LeggedRobotInitializer::compute (initialization/LeggedRobotInitializer.cpp:67-77)
@@ -935,6 +938,7 @@ __global__ void __launch_bounds__(32) probe_flow_map_kernel(int B, const double*
 // ---------------------------------------------------------------------------------------------- context
 struct hb_ctx {
   hb_config cfg;
+  hb_wbc_settings wbc;       // WBC gains / limits / weights in force (task.info values by default; hb_wbc_set_settings, hb_load_task_info)
   int device;
   cudaStream_t stream;
   cudaStream_t stream_main, stream_aux;   // the host-pointer control step pipelines two half-batches over these
@@ -1052,6 +1056,7 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
   memset(ctx, 0, sizeof(*ctx));
   ctx->cfg = *cfg;
   ctx->device = device;
+  hb_default_wbc_settings(&ctx->wbc);
   // every failure below goes through hb_destroy (streams and partial allocations are released there)
   if (cudaSetDevice(device) != cudaSuccess) { hb_destroy(ctx); return HB_ECUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->stream = nullptr; hb_destroy(ctx); return HB_ECUDA; }
@@ -1213,7 +1218,7 @@ int hb_wbc_solve_batch_dev(hb_ctx* ctx, int B, const double* x_des, const double
   if (set_device(ctx)) return HB_ECUDA;
   const size_t per_warp = wbc_fused_doubles() * sizeof(double);
   prof_begin(ctx, K_QP);
-  wbc_fused_kernel<<<B, 32, per_warp, ctx->stream>>>(B, x_des, u_des, rbd, mode, stance_mode, ctx->cfg.wbc_rho, ctx->cfg.qp_max_iter, sol,
+  wbc_fused_kernel<<<B, 32, per_warp, ctx->stream>>>(B, ctx->wbc, x_des, u_des, rbd, mode, stance_mode, ctx->cfg.wbc_rho, ctx->cfg.qp_max_iter, sol,
                                                       status ? status : ctx->wstatus + ctx->base, ctx->witers + ctx->base);
   prof_end(ctx);
   ctx->launches++;
@@ -1228,7 +1233,7 @@ int hb_wbc_assemble_batch_dev(hb_ctx* ctx, int B, const double* x_des, const dou
   if (set_device(ctx)) return HB_ECUDA;
   const int wpb = 4;
   prof_begin(ctx, K_WBC_ASSEMBLE);
-  wbc_assemble_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, sizeof(WbcShared) * wpb, ctx->stream>>>(B, x_des, u_des, rbd, mode, stance_mode, H, g, A, lbA, ubA, m_rows);
+  wbc_assemble_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, sizeof(WbcShared) * wpb, ctx->stream>>>(B, ctx->wbc, x_des, u_des, rbd, mode, stance_mode, H, g, A, lbA, ubA, m_rows);
   prof_end(ctx);
   ctx->launches++;
   CK(cudaGetLastError());
@@ -1272,7 +1277,7 @@ int hb_hoqp_solve_batch_dev(hb_ctx* ctx, int B, const hb_hoqp_problem* problems,
 
 static int hwbc_tasks_dev(hb_ctx* ctx, int B, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode, hb_hoqp_problem* problems) {
   prof_begin(ctx, K_WBC_ASSEMBLE);
-  hwbc_tasks_kernel<<<B, 32, 0, ctx->stream>>>(B, x_des, u_des, rbd, mode, problems);
+  hwbc_tasks_kernel<<<B, 32, 0, ctx->stream>>>(B, ctx->wbc, x_des, u_des, rbd, mode, problems);
   prof_end(ctx);
   ctx->launches++;
   CK(cudaGetLastError());
@@ -1536,6 +1541,136 @@ int hb_estimator_update_batch_dev(hb_ctx* ctx, int B, const hb_kf_params* params
   ctx->launches++;
   CK(cudaGetLastError());
   return HB_OK;
+}
+
+int hb_default_wbc_settings(hb_wbc_settings* s) {
+  if (!s) return HB_EINVAL;
+  for (int j = 0; j < 5; ++j) s->torque_limits[j] = HB_WBC_TORQUE_LIMITS[j];
+  s->friction_coefficient = HB_WBC_FRICTION_MU;
+  s->swing_kp = HB_WBC_SWING_KP; s->swing_kd = HB_WBC_SWING_KD;
+  s->base_accel_kp = 40.0; s->base_accel_kd = 4.0;            // task.info:310-314; loaded (WbcBase.cpp:386-393) but used by no task
+  s->base_height_kp = HB_WBC_BASE_HEIGHT_KP; s->base_height_kd = HB_WBC_BASE_HEIGHT_KD;
+  s->base_angular_kp = HB_WBC_BASE_ANGULAR_KP; s->base_angular_kd = HB_WBC_BASE_ANGULAR_KD;
+  s->weight_swing_leg = HB_WBC_WEIGHT_SWING; s->weight_base_accel = HB_WBC_WEIGHT_BASE; s->weight_contact_force = HB_WBC_WEIGHT_FORCE;
+  return HB_OK;
+}
+
+int hb_wbc_get_settings(const hb_ctx* ctx, hb_wbc_settings* s) {
+  if (!ctx || !s) return HB_EINVAL;
+  *s = ctx->wbc;
+  return HB_OK;
+}
+
+int hb_wbc_set_settings(hb_ctx* ctx, const hb_wbc_settings* s) {
+  if (!ctx || !s) return HB_EINVAL;
+  for (int j = 0; j < 5; ++j) if (!(s->torque_limits[j] > 0.0)) return HB_EINVAL;
+  if (!(s->friction_coefficient > 0.0) || !(s->weight_swing_leg > 0.0) || !(s->weight_base_accel > 0.0) || s->weight_contact_force < 0.0) return HB_EINVAL;
+  ctx->wbc = *s;      // passed by value with the next launch: nothing in flight is affected
+  return HB_OK;
+}
+
+int hb_wbc_set_kp_kd(hb_ctx* ctx, double swing_kp, double swing_kd) {
+  if (!ctx) return HB_EINVAL;
+  ctx->wbc.swing_kp = swing_kp; ctx->wbc.swing_kd = swing_kd;
+  return HB_OK;
+}
+
+namespace {
+// Minimal reader of the boost property-tree INFO subset the reference's task.info uses: `key value`, `key { ... }`, `(i,j) value`,
+// `;` comments. Values are collected under dotted paths ("swingLegTask.kp", "torqueLimitsTask.(0,0)").
+struct InfoMap {
+  std::vector<std::pair<std::string, std::string>> kv;
+  const std::string* find(const std::string& k) const { for (const auto& e : kv) if (e.first == k) return &e.second; return nullptr; }
+  bool number(const std::string& k, double* out) const {
+    const std::string* v = find(k);
+    if (!v) return false;
+    char* end = nullptr;
+    const double d = strtod(v->c_str(), &end);
+    if (end == v->c_str()) { if (*v == "true") { *out = 1.0; return true; } if (*v == "false") { *out = 0.0; return true; } return false; }
+    *out = d;
+    return true;
+  }
+};
+bool info_parse(const char* path, InfoMap& out) {
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  std::vector<std::string> tok;
+  std::string cur;
+  int ch;
+  bool comment = false;
+  auto flush = [&]() { if (!cur.empty()) { tok.push_back(cur); cur.clear(); } };
+  while ((ch = fgetc(f)) != EOF) {
+    if (comment) { if (ch == '\n') comment = false; continue; }
+    if (ch == ';') { flush(); comment = true; continue; }
+    if (ch == '{' || ch == '}') { flush(); tok.push_back(std::string(1, (char)ch)); continue; }
+    if (ch == ' ' || ch == '\t' || ch == '\n' || ch == '\r') { flush(); continue; }
+    cur.push_back((char)ch);
+  }
+  flush();
+  fclose(f);
+  std::vector<std::string> path_stack;
+  size_t i = 0;
+  while (i < tok.size()) {
+    const std::string& t = tok[i];
+    if (t == "}") { if (path_stack.empty()) return false; path_stack.pop_back(); ++i; continue; }
+    if (t == "{") return false;
+    if (i + 1 < tok.size() && tok[i + 1] == "{") { path_stack.push_back(t); i += 2; continue; }
+    if (i + 1 >= tok.size() || tok[i + 1] == "}") { ++i; continue; }      // key without a value
+    std::string key;
+    for (const auto& p : path_stack) { key += p; key += '.'; }
+    key += t;
+    out.kv.emplace_back(key, tok[i + 1]);
+    i += 2;
+  }
+  return path_stack.empty();
+}
+}  // namespace
+
+int hb_parse_task_info(const char* path, hb_task_info* out) {
+  if (!path || !out) return HB_EINVAL;
+  InfoMap m;
+  if (!info_parse(path, m)) return HB_EINVAL;
+  memset(out, 0, sizeof(*out));
+  hb_default_wbc_settings(&out->wbc);
+  hb_kf_params kf; hb_default_kf_params(&kf);
+  memcpy(out->kalman, &kf, sizeof(kf));
+  out->contact_force_cutoff_frequency = 250.0; out->contact_threshold = 75.0;
+  out->sqp_dt = 0.015; out->sqp_iteration = 1; out->mpc_time_horizon = 0.8; out->mpc_cold_start = 0;
+  double v;
+  int found = 0;
+  hb_wbc_settings& w = out->wbc;
+  for (int j = 0; j < 5; ++j) { char k[64]; snprintf(k, sizeof(k), "torqueLimitsTask.(%d,0)", j); if (m.number(k, &v)) { w.torque_limits[j] = v; found |= 1; } }
+  if (m.number("frictionConeTask.frictionCoefficient", &v)) { w.friction_coefficient = v; found |= 1; }
+  if (m.number("swingLegTask.kp", &v)) { w.swing_kp = v; found |= 1; }
+  if (m.number("swingLegTask.kd", &v)) { w.swing_kd = v; found |= 1; }
+  if (m.number("baseAccelTask.kp", &v)) { w.base_accel_kp = v; found |= 1; }
+  if (m.number("baseAccelTask.kd", &v)) { w.base_accel_kd = v; found |= 1; }
+  if (m.number("baseHeightTask.kp", &v)) { w.base_height_kp = v; found |= 1; }
+  if (m.number("baseHeightTask.kd", &v)) { w.base_height_kd = v; found |= 1; }
+  if (m.number("baseAngularTask.kp", &v)) { w.base_angular_kp = v; found |= 1; }
+  if (m.number("baseAngularTask.kd", &v)) { w.base_angular_kd = v; found |= 1; }
+  if (m.number("weight.swingLeg", &v)) { w.weight_swing_leg = v; found |= 1; }
+  if (m.number("weight.baseAccel", &v)) { w.weight_base_accel = v; found |= 1; }
+  if (m.number("weight.contactForce", &v)) { w.weight_contact_force = v; found |= 1; }
+  const char* kfk[7] = {"footRadius", "imuProcessNoisePosition", "imuProcessNoiseVelocity", "footProcessNoisePosition", "footSensorNoisePosition",
+                        "footSensorNoiseVelocity", "footHeightSensorNoise"};
+  for (int j = 0; j < 7; ++j) if (m.number(std::string("kalmanFilter.") + kfk[j], &v)) { out->kalman[j] = v; found |= 2; }
+  if (m.number("contactForceEsimation.cutoffFrequency", &v)) { out->contact_force_cutoff_frequency = v; found |= 4; }
+  if (m.number("contactForceEsimation.contactThreshold", &v)) { out->contact_threshold = v; found |= 4; }
+  if (m.number("sqp.dt", &v)) { out->sqp_dt = v; found |= 8; }
+  if (m.number("sqp.sqpIteration", &v)) { out->sqp_iteration = (int32_t)v; found |= 8; }
+  if (m.number("mpc.timeHorizon", &v)) { out->mpc_time_horizon = v; found |= 16; }
+  if (m.number("mpc.coldStart", &v)) { out->mpc_cold_start = v != 0.0; found |= 16; }
+  out->found = found;
+  return HB_OK;
+}
+
+int hb_load_task_info(hb_ctx* ctx, const char* path) {
+  if (!ctx || !path) return HB_EINVAL;
+  hb_task_info ti;
+  int rc = hb_parse_task_info(path, &ti);
+  if (rc) return rc;
+  return hb_wbc_set_settings(ctx, &ti.wbc);
 }
 
 int hb_default_sim_params(hb_sim_params* p) {
@@ -1902,6 +2037,25 @@ int hb_reference_expand_grid_batch(hb_ctx* ctx, int B, const double* node_times,
   D2H(x_ref, ctx->s_xref, sizeof(double) * B * (N + 1) * NX); D2H(swing_ref, ctx->s_swing, sizeof(double) * B * (N + 1) * 24);
   D2H(mode, ctx->s_mode, sizeof(int32_t) * B * (N + 1));
   return hb_sync(ctx);
+}
+
+int hb_resident_write_batch(hb_ctx* ctx, int B, const double* t0, const double* x_traj, const double* u_traj, const int32_t* mode, const double* node_times,
+                            const int32_t* n_intervals) {
+  if (!ctx || B < 0 || !t0 || !x_traj || !u_traj) return HB_EINVAL;
+  if (B == 0) return HB_OK;
+  if (B > ctx->cfg.max_batch) return HB_ECAP;
+  const bool grid = ctx->cfg.event_nodes != 0;
+  if (grid && (!node_times || !n_intervals)) return HB_EINVAL;      // an event-node context shifts between grids: the snapshot needs its grid
+  const size_t N = ctx->cfg.horizon_N;
+  if (grid) for (int i = 0; i < B; ++i) if (n_intervals[i] < 1 || n_intervals[i] > (int)N) return HB_EINVAL;
+  if (set_device(ctx)) return HB_ECUDA;
+  H2D(ctx->res_t0, t0, sizeof(double) * B); H2D(ctx->res_xt, x_traj, sizeof(double) * B * (N + 1) * NX); H2D(ctx->res_ut, u_traj, sizeof(double) * B * N * NU);
+  if (mode) H2D(ctx->res_mode, mode, sizeof(int32_t) * B * (N + 1));
+  if (grid) { H2D(ctx->res_tk, node_times, sizeof(double) * B * (N + 1)); H2D(ctx->res_nn, n_intervals, sizeof(int32_t) * B); }
+  int rc = hb_sync(ctx);
+  if (rc) return rc;
+  if (ctx->res_valid < B) ctx->res_valid = B;
+  return HB_OK;
 }
 
 int hb_resident_read_grid_batch(hb_ctx* ctx, int B, double* node_times, int32_t* n_intervals) {

@@ -9,6 +9,7 @@
 #pragma once
 #include "hb_common.cuh"
 #include "hb_rbd.cuh"
+#include "../../include/hunter_b200.h"
 
 namespace hb {
 
@@ -45,7 +46,7 @@ __device__ inline void rotation_error_world(const double* Rref, const double* Rm
 
 // Assemble one instance. Outputs may be global or shared. Returns the number of constraint rows m.
 __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const double* __restrict__ u_des,
-                                        const double* __restrict__ rbd, int mode, bool stance_mode, WbcShared& sh,
+                                        const double* __restrict__ rbd, int mode, bool stance_mode, const hb_wbc_settings& ws, WbcShared& sh,
                                         double* H, double* g, double* A, double* lbA, double* ubA, int* nw_out = nullptr) {
   const int lane = lane_id();
   const Model& md = c_model;
@@ -130,7 +131,7 @@ __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const 
   if (lane == 0) {
     for (int i = 0; i < 18 * 16; ++i) sh.Aw[i] = 0.0;
     if (stance_mode) {
-      for (int i = 0; i < 6; ++i) { sh.Aw[i * 16 + i] = HB_WBC_WEIGHT_BASE; sh.bw[i] = 0.0; }
+      for (int i = 0; i < 6; ++i) { sh.Aw[i * 16 + i] = ws.weight_base_accel; sh.bw[i] = 0.0; }
     } else {
       // normalised centroidal momentum rate at the plan (getNormalizedCentroidalMomentumRate)
       double hd[6] = {0, 0, 0, 0, 0, 0};
@@ -169,23 +170,23 @@ __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const 
       int r = 0;
       // swing leg task (WbcBase.cpp:297-323), weight 100
       for (int c = 0; c < 4; ++c) if (!fl[c]) for (int a = 0; a < 3; ++a) {
-        const double acc = HB_WBC_SWING_KP * (sh.pos_d[3 * c + a] - sh.pos_m[3 * c + a]) + HB_WBC_SWING_KD * (sh.vel_d[3 * c + a] - sh.vel_m[3 * c + a]);
-        for (int j = 0; j < NQ; ++j) sh.Aw[r * 16 + j] = HB_WBC_WEIGHT_SWING * sh.J[(3 * c + a) * 16 + j];
-        sh.bw[r] = HB_WBC_WEIGHT_SWING * (acc - sh.dJv[3 * c + a]);
+        const double acc = ws.swing_kp * (sh.pos_d[3 * c + a] - sh.pos_m[3 * c + a]) + ws.swing_kd * (sh.vel_d[3 * c + a] - sh.vel_m[3 * c + a]);
+        for (int j = 0; j < NQ; ++j) sh.Aw[r * 16 + j] = ws.weight_swing_leg * sh.J[(3 * c + a) * 16 + j];
+        sh.bw[r] = ws.weight_swing_leg * (acc - sh.dJv[3 * c + a]);
         ++r;
       }
       // base xy acceleration (WbcBase.cpp:228-240)
-      for (int a = 0; a < 2; ++a) { sh.Aw[r * 16 + a] = HB_WBC_WEIGHT_BASE; sh.bw[r] = HB_WBC_WEIGHT_BASE * qbdd[a]; ++r; }
+      for (int a = 0; a < 2; ++a) { sh.Aw[r * 16 + a] = ws.weight_base_accel; sh.bw[r] = ws.weight_base_accel * qbdd[a]; ++r; }
       // base height (WbcBase.cpp:243-256)
-      sh.Aw[r * 16 + 2] = HB_WBC_WEIGHT_BASE;
-      sh.bw[r] = HB_WBC_WEIGHT_BASE * (qbdd[2] + HB_WBC_BASE_HEIGHT_KP * (sh.qd[2] - sh.q[2]) + HB_WBC_BASE_HEIGHT_KD * (sh.vd[2] - sh.v[2]));
+      sh.Aw[r * 16 + 2] = ws.weight_base_accel;
+      sh.bw[r] = ws.weight_base_accel * (qbdd[2] + ws.base_height_kp * (sh.qd[2] - sh.q[2]) + ws.base_height_kd * (sh.vd[2] - sh.v[2]));
       ++r;
       // base angular motion (WbcBase.cpp:259-290)
       double err[3];
       rotation_error_world(Rd, Rm, err);
       for (int a = 0; a < 3; ++a) {
-        for (int i = 0; i < 3; ++i) sh.Aw[r * 16 + 3 + i] = HB_WBC_WEIGHT_BASE * axm[3 * i + a];
-        sh.bw[r] = HB_WBC_WEIGHT_BASE * (baseAccW[a] + HB_WBC_BASE_ANGULAR_KP * err[a] + HB_WBC_BASE_ANGULAR_KD * (baseVelW[a] - wm[a]) - dJw_v[a]);
+        for (int i = 0; i < 3; ++i) sh.Aw[r * 16 + 3 + i] = ws.weight_base_accel * axm[3 * i + a];
+        sh.bw[r] = ws.weight_base_accel * (baseAccW[a] + ws.base_angular_kp * err[a] + ws.base_angular_kd * (baseVelW[a] - wm[a]) - dJw_v[a]);
         ++r;
       }
     }
@@ -194,15 +195,19 @@ __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const 
   if (nw_out) *nw_out = nw;
   if (H == nullptr) return 16 + 3 * (4 - nc) + 20 + 5 * nc + 3 * (4 - nc);   // terms only (fused path builds the reduced QP from sh)
   // ---- H = Aw'Aw, g = -Aw'bw (WeightedWbc.cpp:38-41); only the qdd block is non-zero
+  // formulateContactForceTask * weightContactForce (WbcBase.cpp:325-338, WeightedWbc.cpp:87-91; not in stance mode): rows w_f [0 | I_12 | 0] x = w_f F_des
+  const double wf2 = stance_mode ? 0.0 : ws.weight_contact_force * ws.weight_contact_force;
   for (int idx = lane; idx < NWBC * NWBC; idx += 32) {
     const int i = idx / NWBC, j = idx - i * NWBC;
     double s = 0.0;
     if (i < NQ && j < NQ) for (int r = 0; r < nw; ++r) s += sh.Aw[r * 16 + i] * sh.Aw[r * 16 + j];
+    if (i == j && i >= NQ && i < NQ + 12) s += wf2;
     H[idx] = s;
   }
   for (int i = lane; i < NWBC; i += 32) {
     double s = 0.0;
     if (i < NQ) for (int r = 0; r < nw; ++r) s += sh.Aw[r * 16 + i] * sh.bw[r];
+    else if (i < NQ + 12) s = wf2 * u_des[i - NQ];
     g[i] = -s;
   }
   // ---- constraints (WeightedWbc.cpp:68-71): EoM (16 eq) + swing force = 0 (3 per swing contact) + torque limits (20)
@@ -224,9 +229,9 @@ __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const 
     int r = r_sw;
     for (int c = 0; c < 4; ++c) if (!fl[c]) for (int a = 0; a < 3; ++a) { A[r * NWBC + NQ + 3 * c + a] = 1.0; lbA[r] = 0.0; ubA[r] = 0.0; ++r; }
     for (int sgn = 0; sgn < 2; ++sgn) for (int j = 0; j < NJ; ++j) {
-      A[r * NWBC + NQ + 12 + j] = sgn == 0 ? 1.0 : -1.0; lbA[r] = -QP_INFTY; ubA[r] = md.torque_limit[j]; ++r;
+      A[r * NWBC + NQ + 12 + j] = sgn == 0 ? 1.0 : -1.0; lbA[r] = -QP_INFTY; ubA[r] = ws.torque_limits[j % 5]; ++r;
     }
-    const double mu = HB_WBC_FRICTION_MU;
+    const double mu = ws.friction_coefficient;
     const double pyr[5][3] = {{0, 0, -1}, {1, 0, -mu}, {-1, 0, -mu}, {0, 1, -mu}, {0, -1, -mu}};
     for (int c = 0; c < 4; ++c) if (fl[c]) for (int k = 0; k < 5; ++k) {
       for (int a = 0; a < 3; ++a) A[r * NWBC + NQ + 3 * c + a] = pyr[k][a];
@@ -242,8 +247,8 @@ __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const 
 //   z = [qdd(16), F_stance(3 n_st)],  6 equalities (base rows of the EoM), 10 two-sided torque rows, 5 friction rows per
 // stance contact. The Tikhonov term rho ||[qdd, F, tau]||^2 of the full problem is carried over exactly (rho I + rho T'T).
 // Hz is written into `Hw` (leading dimension ldh), rows of Az have stride nz. Returns nz; m_out = number of rows.
-__device__ inline int wbc_reduced_build(const WbcShared& sh, int mode, int nw, double rho, double* Hw, int ldh, double* gz, double* Az,
-                                        double* lbz, double* ubz, int* stcol /*12*/, int& m_out) {
+__device__ inline int wbc_reduced_build(const WbcShared& sh, int mode, int nw, bool stance_mode, double rho, const hb_wbc_settings& ws, const double* __restrict__ u_des,
+                                        double* Hw, int ldh, double* gz, double* Az, double* lbz, double* ubz, int* stcol /*12*/, int& m_out) {
   const int lane = lane_id();
   const Model& md = c_model;
   int nst = 0;
@@ -261,7 +266,7 @@ __device__ inline int wbc_reduced_build(const WbcShared& sh, int mode, int nw, d
       const int fr = r - 6 - NJ, ci = fr / 5, k = fr - 5 * ci;     // stance contact ci occupies columns NQ+3ci .. NQ+3ci+2
       const int cc = c - NQ - 3 * ci;
       if (cc >= 0 && cc < 3) {
-        const double mu = HB_WBC_FRICTION_MU;
+        const double mu = ws.friction_coefficient;
         const double pyr[5][3] = {{0, 0, -1}, {1, 0, -mu}, {-1, 0, -mu}, {0, 1, -mu}, {0, -1, -mu}};
         v = pyr[k][cc];
       }
@@ -270,14 +275,16 @@ __device__ inline int wbc_reduced_build(const WbcShared& sh, int mode, int nw, d
   }
   for (int r = lane; r < m; r += 32) {
     if (r < 6) { lbz[r] = -sh.nle[r]; ubz[r] = -sh.nle[r]; }
-    else if (r < 6 + NJ) { const int j = r - 6; lbz[r] = -md.torque_limit[j] - sh.nle[6 + j]; ubz[r] = md.torque_limit[j] - sh.nle[6 + j]; }
+    else if (r < 6 + NJ) { const int j = r - 6; lbz[r] = -ws.torque_limits[j % 5] - sh.nle[6 + j]; ubz[r] = ws.torque_limits[j % 5] - sh.nle[6 + j]; }
     else { lbz[r] = -QP_INFTY; ubz[r] = 0.0; }
   }
   __syncwarp();
   const double* Tm = Az + 6 * nz;   // torque rows double as the map tau = T z + nle_j
+  const double wf2 = stance_mode ? 0.0 : ws.weight_contact_force * ws.weight_contact_force;
   for (int idx = lane; idx < nz * nz; idx += 32) {
     const int i = idx / nz, j = idx - i * nz;
     double s = (i == j) ? rho : 0.0;
+    if (i == j && i >= NQ) s += wf2;                      // contact-force task on the stance forces (swing forces are eliminated at zero)
     if (i < NQ && j < NQ) for (int r = 0; r < nw; ++r) s += sh.Aw[r * 16 + i] * sh.Aw[r * 16 + j];
     double t = 0.0;
     for (int r = 0; r < NJ; ++r) t += Tm[r * nz + i] * Tm[r * nz + j];
@@ -286,6 +293,7 @@ __device__ inline int wbc_reduced_build(const WbcShared& sh, int mode, int nw, d
   for (int i = lane; i < nz; i += 32) {
     double s = 0.0;
     if (i < NQ) for (int r = 0; r < nw; ++r) s -= sh.Aw[r * 16 + i] * sh.bw[r];
+    else s = -wf2 * u_des[stcol[i - NQ]];
     double t = 0.0;
     for (int r = 0; r < NJ; ++r) t += Tm[r * nz + i] * sh.nle[6 + r];
     gz[i] = s + rho * t;

@@ -131,6 +131,40 @@ typedef struct {           /* task.info:336-345 */
 typedef struct { double p_filtered[16]; } hb_observer_state;
 int hb_observer_reset(int B, hb_observer_state* state);   /* host only: zeros (StateEstimateBase.cpp:58-59) */
 
+/* ---- run-time WBC settings: what WbcBase::loadTasksSetting / WeightedWbc::loadTasksSetting read from task.info
+ * (legged_wbc/src/WbcBase.cpp:352-411, WeightedWbc.cpp:96-111) and WbcBase::setKpKd changes (WbcBase.h:65-69) ---- */
+typedef struct {
+  double torque_limits[5];            /* torqueLimitsTask (motor 1..5 of a leg)                    task.info:290-297 */
+  double friction_coefficient;        /* frictionConeTask.frictionCoefficient                      :299-302          */
+  double swing_kp, swing_kd;          /* swingLegTask                                              :304-308          */
+  double base_accel_kp, base_accel_kd;   /* baseAccelTask (loaded by the reference, used by no task) :310-314        */
+  double base_height_kp, base_height_kd; /* baseHeightTask                                          :316-320         */
+  double base_angular_kp, base_angular_kd; /* baseAngularTask                                       :322-326         */
+  double weight_swing_leg, weight_base_accel, weight_contact_force;   /* weight                     :328-333         */
+} hb_wbc_settings;
+
+/* what hb_parse_task_info extracts from a task.info file (boost property-tree INFO format): the WBC block above, the estimator
+ * parameters and the solver discretisation. `found` has one bit per section that was present (1 WBC, 2 kalmanFilter,
+ * 4 contactForceEsimation, 8 sqp, 16 mpc); absent sections keep the defaults. */
+typedef struct {
+  hb_wbc_settings wbc;
+  double kalman[7];                   /* hb_kf_params in declaration order (kalmanFilter, task.info:336-345)                */
+  double contact_force_cutoff_frequency, contact_threshold;   /* contactForceEsimation                   :347-351          */
+  double sqp_dt;                      /* sqp.dt                                                            :82               */
+  int32_t sqp_iteration;              /* sqp.sqpIteration                                                  :83               */
+  double mpc_time_horizon;            /* mpc.timeHorizon                                                   :144              */
+  int32_t mpc_cold_start;             /* mpc.coldStart                                                     :146              */
+  int32_t found;
+} hb_task_info;
+
+int hb_default_wbc_settings(hb_wbc_settings* s);
+int hb_parse_task_info(const char* path, hb_task_info* out);          /* host only; -1: file missing or malformed */
+/* the WBC settings in force for this context (defaults: the shipped task.info values compiled into include/hunter_model_constants.h) */
+int hb_wbc_get_settings(const hb_ctx* ctx, hb_wbc_settings* s);
+int hb_wbc_set_settings(hb_ctx* ctx, const hb_wbc_settings* s);
+int hb_wbc_set_kp_kd(hb_ctx* ctx, double swing_kp, double swing_kd);   /* WbcBase::setKpKd */
+int hb_load_task_info(hb_ctx* ctx, const char* path);                  /* hb_parse_task_info + hb_wbc_set_settings */
+
 /* ---- hierarchical QP: legged::HoQp / legged::HierarchicalWbc ---- */
 #define HB_HOQP_MAX_LEVELS 3
 #define HB_HOQP_N 38            /* decision variables (the WBC's [qdd, F, tau])                             */
@@ -310,6 +344,11 @@ int hb_joint_command_batch(hb_ctx* ctx, int B, const hb_pd_gains* gains, double 
 int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0, const hb_reference* refs,
                             const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque, int32_t* wbc_status);
 int hb_resident_read_batch(hb_ctx* ctx, int B, double* t0 /*nullable*/, double* x_traj /*nullable*/, double* u_traj /*nullable*/);
+/* Restores a snapshot taken with hb_resident_read_batch (+ hb_resident_read_grid_batch): the next warm cycle shifts it exactly as if this
+ * context had produced it (checkpoint / resume, migration of instances between contexts or GPUs). mode (B x (N+1), nullable) = node modes of
+ * the solution, needed by hb_resident_wbc_batch until the next cycle; node_times / n_intervals are required by event_nodes contexts only. */
+int hb_resident_write_batch(hb_ctx* ctx, int B, const double* t0, const double* x_traj, const double* u_traj, const int32_t* mode /*nullable*/,
+                            const double* node_times /*nullable*/, const int32_t* n_intervals /*nullable*/);
 /* node times / interval counts of the resident solution (contexts created with event_nodes = 1) */
 int hb_resident_read_grid_batch(hb_ctx* ctx, int B, double* node_times, int32_t* n_intervals);
 int hb_time_grid_batch(hb_ctx* ctx, int B, const double* t0, const hb_reference* refs, double* node_times, int32_t* n_intervals, int32_t* status /*nullable*/);

@@ -19,6 +19,12 @@ using D44 = Dual<ND>;
 
 double g_R[NU * NU];
 bool g_init = false;
+// WBC gains / limits / weights: the shipped task.info values unless a test overrides them (hbo_set_wbc_settings), mirroring what
+// WbcBase::loadTasksSetting / WeightedWbc::loadTasksSetting / setKpKd make configurable at run time
+struct WbcSettings { double torque[5], mu, swing_kp, swing_kd, accel_kp, accel_kd, height_kp, height_kd, angular_kp, angular_kd, weight_swing, weight_base, weight_force; };
+WbcSettings g_wbc = {{HB_WBC_TORQUE_LIMITS[0], HB_WBC_TORQUE_LIMITS[1], HB_WBC_TORQUE_LIMITS[2], HB_WBC_TORQUE_LIMITS[3], HB_WBC_TORQUE_LIMITS[4]},
+                     HB_WBC_FRICTION_MU, HB_WBC_SWING_KP, HB_WBC_SWING_KD, 40.0, 4.0, HB_WBC_BASE_HEIGHT_KP, HB_WBC_BASE_HEIGHT_KD, HB_WBC_BASE_ANGULAR_KP,
+                     HB_WBC_BASE_ANGULAR_KD, HB_WBC_WEIGHT_SWING, HB_WBC_WEIGHT_BASE, HB_WBC_WEIGHT_FORCE};
 
 // MotionPhaseDefinition.h:55-87
 inline void mode_to_flags(int mode, bool* f) {
@@ -666,10 +672,10 @@ void wbc_assemble(const double* x_des, const double* u_des, const double* rbd, i
   for (int c = 0; c < NC; ++c) if (!fl[c]) for (int a = 0; a < 3; ++a) { qp.A[row * NV + NQ + 3 * c + a] = 1.0; qp.lbA[row] = qp.ubA[row] = 0.0; ++row; }
   // formulateTorqueLimitsTask (WbcBase.cpp:151-167)
   for (int sgn = 0; sgn < 2; ++sgn) for (int j = 0; j < NJ; ++j) {
-    qp.A[row * NV + NQ + 12 + j] = sgn == 0 ? 1.0 : -1.0; qp.lbA[row] = -QP_INF; qp.ubA[row] = HB_WBC_TORQUE_LIMITS[j % 5]; ++row;
+    qp.A[row * NV + NQ + 12 + j] = sgn == 0 ? 1.0 : -1.0; qp.lbA[row] = -QP_INF; qp.ubA[row] = g_wbc.torque[j % 5]; ++row;
   }
   // friction pyramid on stance contacts, then 3*(4-nc) all-zero rows (WbcBase.cpp:205-221)
-  const double mu = HB_WBC_FRICTION_MU;
+  const double mu = g_wbc.mu;
   const double pyr[5][3] = {{0, 0, -1}, {1, 0, -mu}, {-1, 0, -mu}, {0, 1, -mu}, {0, -1, -mu}};
   for (int c = 0; c < NC; ++c) if (fl[c]) for (int r = 0; r < 5; ++r) {
     for (int a = 0; a < 3; ++a) qp.A[row * NV + NQ + 3 * c + a] = pyr[r][a];
@@ -678,22 +684,22 @@ void wbc_assemble(const double* x_des, const double* u_des, const double* rbd, i
   for (int r = 0; r < 3 * (NC - nc); ++r) { qp.lbA[row] = -QP_INF; qp.ubA[row] = 0.0; ++row; }
   qp.m = row;
   // ---- weighted tasks (WeightedWbc.cpp:73-94)
-  double Aw[24 * 38]; double bw[24]; int rw = 0;
-  std::fill(Aw, Aw + 24 * NV, 0.0);
+  double Aw[36 * 38]; double bw[36]; int rw = 0;
+  std::fill(Aw, Aw + 36 * NV, 0.0);
   if (stance_mode) {
-    for (int i = 0; i < 6; ++i) { Aw[rw * NV + i] = HB_WBC_WEIGHT_BASE; bw[rw] = 0.0; ++rw; }
+    for (int i = 0; i < 6; ++i) { Aw[rw * NV + i] = g_wbc.weight_base; bw[rw] = 0.0; ++rw; }
   } else {
     // swing leg task (WbcBase.cpp:297-323)
     for (int c = 0; c < NC; ++c) if (!fl[c]) for (int a = 0; a < 3; ++a) {
-      const double acc = HB_WBC_SWING_KP * (pos_d[3 * c + a] - pos_m[3 * c + a]) + HB_WBC_SWING_KD * (vel_d[3 * c + a] - vel_m[3 * c + a]);
-      for (int j = 0; j < NQ; ++j) Aw[rw * NV + j] = HB_WBC_WEIGHT_SWING * J[(3 * c + a) * NQ + j];
-      bw[rw] = HB_WBC_WEIGHT_SWING * (acc - dJv[3 * c + a]); ++rw;
+      const double acc = g_wbc.swing_kp * (pos_d[3 * c + a] - pos_m[3 * c + a]) + g_wbc.swing_kd * (vel_d[3 * c + a] - vel_m[3 * c + a]);
+      for (int j = 0; j < NQ; ++j) Aw[rw * NV + j] = g_wbc.weight_swing * J[(3 * c + a) * NQ + j];
+      bw[rw] = g_wbc.weight_swing * (acc - dJv[3 * c + a]); ++rw;
     }
     // base xy acceleration (WbcBase.cpp:228-240)
-    for (int a = 0; a < 2; ++a) { Aw[rw * NV + a] = HB_WBC_WEIGHT_BASE; bw[rw] = HB_WBC_WEIGHT_BASE * baseAcc[a]; ++rw; }
+    for (int a = 0; a < 2; ++a) { Aw[rw * NV + a] = g_wbc.weight_base; bw[rw] = g_wbc.weight_base * baseAcc[a]; ++rw; }
     // base height (WbcBase.cpp:243-256)
-    Aw[rw * NV + 2] = HB_WBC_WEIGHT_BASE;
-    bw[rw] = HB_WBC_WEIGHT_BASE * (baseAcc[2] + HB_WBC_BASE_HEIGHT_KP * (basePose[2] - q[2]) + HB_WBC_BASE_HEIGHT_KD * (baseVel[2] - v[2]));
+    Aw[rw * NV + 2] = g_wbc.weight_base;
+    bw[rw] = g_wbc.weight_base * (baseAcc[2] + g_wbc.height_kp * (basePose[2] - q[2]) + g_wbc.height_kd * (baseVel[2] - v[2]));
     ++rw;
     // base angular motion (WbcBase.cpp:259-290)
     double Rm[9], Rr[9], err[3], wm[3];
@@ -701,14 +707,16 @@ void wbc_assemble(const double* x_des, const double* u_des, const double* rbd, i
     rotation_error_world(Rr, Rm, err);
     for (int i = 0; i < 3; ++i) wm[i] = kin.ax[3][i] * v[3] + kin.ax[4][i] * v[4] + kin.ax[5][i] * v[5];
     for (int a = 0; a < 3; ++a) {
-      for (int j = 0; j < NQ; ++j) Aw[rw * NV + j] = HB_WBC_WEIGHT_BASE * Jw[a * NQ + j];
-      bw[rw] = HB_WBC_WEIGHT_BASE * (baseAcc[3 + a] + HB_WBC_BASE_ANGULAR_KP * err[a] + HB_WBC_BASE_ANGULAR_KD * (baseVel[3 + a] - wm[a]) - dJw_v[a]);
+      for (int j = 0; j < NQ; ++j) Aw[rw * NV + j] = g_wbc.weight_base * Jw[a * NQ + j];
+      bw[rw] = g_wbc.weight_base * (baseAcc[3 + a] + g_wbc.angular_kp * err[a] + g_wbc.angular_kd * (baseVel[3 + a] - wm[a]) - dJw_v[a]);
       ++rw;
     }
-    // contact force task has weight 0 (task.info:328-333): rows vanish from H and g
+    // contact force task (WbcBase.cpp:325-338) * weightContactForce (0 in the shipped task.info:328-333)
+    if (g_wbc.weight_force != 0.0) for (int j = 0; j < 12; ++j) { Aw[rw * NV + NQ + j] = g_wbc.weight_force; bw[rw] = g_wbc.weight_force * u_des[j]; ++rw; }
   }
   if (terms) {
-    std::memcpy(terms->Aw, Aw, sizeof(Aw)); std::memcpy(terms->bw, bw, sizeof(bw)); terms->rw = rw;
+    const int rt = rw < 24 ? rw : 24;      // the swing / base rows (the hierarchical formulation builds its own contact-force task)
+    std::memcpy(terms->Aw, Aw, sizeof(double) * 24 * NV); std::memcpy(terms->bw, bw, sizeof(double) * 24); terms->rw = rt;
     std::memcpy(terms->J, J, sizeof(J)); std::memcpy(terms->dJv, dJv, sizeof(dJv));
   }
   for (int i = 0; i < NV; ++i) {
@@ -872,6 +880,13 @@ void hbo_init(void) {
     g_R[(12 + i) * NU + 12 + j] = s;
   }
   g_init = true;
+}
+
+// 17 doubles in the order of hb_wbc_settings (include/hunter_b200.h); NULL restores the shipped values
+void hbo_set_wbc_settings(const double* s) {
+  static const WbcSettings defaults = g_wbc;
+  if (!s) { g_wbc = defaults; return; }
+  std::memcpy(&g_wbc, s, sizeof(WbcSettings));
 }
 
 void hbo_input_cost_R(double* R) { hbo_init(); std::memcpy(R, g_R, sizeof(g_R)); }

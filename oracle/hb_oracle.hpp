@@ -44,6 +44,7 @@ void hbo_flow_map(const double* x, const double* u, double* f /*22*/, double* A 
 void hbo_ee_kinematics(const double* x, const double* u, double* pos /*12*/, double* vel /*12*/, double* dpos_dx /*12x22*/,
                        double* dvel_dx /*12x22*/, double* dvel_du /*12x22*/);
 void hbo_input_cost_R(double* R /*22x22*/);
+void hbo_set_wbc_settings(const double* s /*17 doubles, order of hb_wbc_settings; NULL = shipped task.info values*/);
 // node LQ model (for inspection): returns sizes via pointers
 void hbo_node_lq(double t_dt, const double* x, const double* u, const double* xn, const double* xref, const double* swing,
                  int mode, double* Ad, double* Bd, double* b, double* Q, double* R, double* P, double* q, double* r,

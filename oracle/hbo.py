@@ -63,6 +63,15 @@ def rbd(q, v):
     return dict(M=M, nle=nle, J=J, dJv=dJv, A=A, com=com, h=h, cpos=cpos)
 
 
+def set_wbc_settings(values=None):
+    """Override the WBC gains / limits / weights of the oracle (17 doubles in the order of hb_wbc_settings); None restores the shipped values."""
+    if values is None:
+        lib().hbo_set_wbc_settings(None)
+    else:
+        v = _d(values); assert v.size == 17
+        lib().hbo_set_wbc_settings(_p(v))
+
+
 def observer_terms(q, v):
     """p = M v, generalised gravity, C' v and the 6-D toe-frame Jacobians of both feet (momentum observer, StateEstimateBase.cpp:157-190)."""
     q, v = _d(q), _d(v)

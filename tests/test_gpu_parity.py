@@ -287,7 +287,9 @@ def test_mirror_classes(oracle):
     import hunter_bipedal_control_b200 as hb
     sc = S()
     wbc = hb.WeightedWbc()
-    wbc.loadTasksSetting("task.info", False)
+    with pytest.raises(hb.HunterB200Error):
+        wbc.loadTasksSetting("/nonexistent/task.info", False)      # the reference throws on a missing task file too (boost read_info)
+    wbc.loadTasksSetting(None, False)                              # no file: the shipped values stay in force
     x = sc.INITIAL_STATE; u = np.zeros(22); u[[2, 5, 8, 11]] = sc.TOTAL_MASS * 9.81 / 4
     rbd = np.r_[x[9:12], x[6:9], x[12:], np.zeros(16)]
     s1 = wbc.update(x, u, rbd, 3, 0.002)              # stance mode until setStanceMode(False)
@@ -297,3 +299,38 @@ def test_mirror_classes(oracle):
     s2 = wbc.update(x, u, rbd, 3, 0.002)
     so, _ = oracle.wbc_solve(x, u, rbd, 3, False, 1e-8)
     assert rel(s2[28:], so[28:]) < TAU_RTOL and wbc.getContactForceSize() == 12
+
+
+def test_runtime_wbc_settings_from_task_info(oracle):
+    """WbcBase::loadTasksSetting / WeightedWbc::loadTasksSetting / setKpKd honoured at run time: gains, limits and weights loaded from a
+    task.info variant change the device WBC exactly as they change the restatement (assembly entry by entry, torques to 1e-4)."""
+    import hunter_bipedal_control_b200 as hb
+    ctx = hb.Context(horizon_N=10, dt=0.02, max_batch=64, device=0)
+    x, u, rbd, mode, stance = _wbc_cases(32, 31)
+    base, _ = ctx.wbc_solve(x, u, rbd, mode, stance)
+    try:
+        ctx.load_task_info(os.path.join(HERE, "golden", "task_wbc_variant.info"))
+        s = ctx.wbc_settings()
+        assert s.swing_kp == 140.0 and s.weight_contact_force == 0.02 and list(s.torque_limits) == [25.0, 55.0, 50.0, 58.0, 20.0]
+        for variant in range(2):
+            if variant == 1:
+                ctx.set_kp_kd(90.0, 9.0)                       # WbcBase::setKpKd (WbcBase.h:65-69)
+                s = ctx.wbc_settings()
+                assert (s.swing_kp, s.swing_kd) == (90.0, 9.0)
+            oracle.set_wbc_settings(s.as_array())
+            H, g, A, lb, ub, m = ctx.wbc_assemble(x, u, rbd, mode, stance)
+            sol, st = ctx.wbc_solve(x, u, rbd, mode, stance)
+            assert (st == 0).all()
+            changed = 0
+            for i in range(len(mode)):
+                Hi, gi, Ai, lbi, ubi = oracle.wbc_assemble(x[i], u[i], rbd[i], int(mode[i]), bool(stance[i]))
+                assert np.abs(H[i] - Hi).max() < 1e-9 * max(1.0, np.abs(Hi).max()) and np.abs(g[i] - gi).max() < 1e-9 * max(1.0, np.abs(gi).max())
+                assert np.abs(A[i, :m[i]] - Ai).max() < 1e-9 * max(1.0, np.abs(Ai).max()) and np.abs(ub[i, :m[i]] - ubi).max() < 1e-8 * max(1.0, np.abs(ubi).max())
+                so, sto = oracle.wbc_solve(x[i], u[i], rbd[i], int(mode[i]), bool(stance[i]), 1e-8)
+                assert sto == 0 and rel(sol[i, 28:], so[28:]) < TAU_RTOL, (variant, i)
+                assert (np.abs(sol[i, 28:]) <= np.tile(list(s.torque_limits), 2) + 1e-6).all()
+                changed += rel(sol[i, 28:], base[i, 28:]) > 1e-3
+            assert changed > len(mode) // 2                    # the new settings do change the answer
+    finally:
+        oracle.set_wbc_settings(None)
+        ctx.close()

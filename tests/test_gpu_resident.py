@@ -130,3 +130,35 @@ def test_wbc_fallback_returns_previous_solution():
     for i in (0, 1, 3, 5):
         assert not np.array_equal(sol1[i], sol0[i])
     ctx.close()
+
+
+def test_snapshot_write_back_resumes_bit_identically():
+    """Checkpoint / resume: a resident solution read out and written into a FRESH context continues exactly like the original one --
+    uniform grid and event-node grid."""
+    for event_nodes in (False, True):
+        kw = dict(horizon_N=N, dt=DT, max_batch=32, device=0)
+        if event_nodes:
+            kw.update(time_horizon=0.7, event_nodes=True)
+        a = hb.Context(**kw); b = hb.Context(**kw)
+        B = 10
+        x0, refs, rbd = _setup(B, seed=47)
+        a.resident_cycle(True, 0.002, np.zeros(B), x0, refs, rbd)
+        a.resident_cycle(False, 0.002, np.full(B, 0.01), x0 + 1e-3, refs, rbd)
+        t_s, x_s, u_s = a.resident_read(B)
+        grid = a.resident_read_grid(B) if event_nodes else (None, None)
+        xr, sw, md = (a.reference_expand_grid(grid[0], refs) if event_nodes else a.reference_expand(t_s, refs))
+        ra = a.resident_cycle(False, 0.002, np.full(B, 0.02), x0 + 2e-3, refs, rbd)
+        b.resident_write(t_s, x_s, u_s, md, *grid)
+        rb = b.resident_cycle(False, 0.002, np.full(B, 0.02), x0 + 2e-3, refs, rbd)
+        assert ra[0].tobytes() == rb[0].tobytes() and np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2])
+        xa, xb = a.resident_read(B), b.resident_read(B)
+        assert np.array_equal(xa[1], xb[1]) and np.array_equal(xa[2], xb[2])
+        # the 500 Hz tick works on the restored snapshot too (needs the node modes)
+        c = hb.Context(**kw)
+        c.resident_write(t_s, x_s, u_s, md, *grid)
+        ta = a.resident_wbc(np.full(B, 0.024), rbd); tb = b.resident_wbc(np.full(B, 0.024), rbd)
+        assert np.array_equal(ta[3], tb[3])
+        with pytest.raises(hb.HunterB200Error):
+            hb.Context(**kw).resident_cycle(False, 0.002, np.zeros(B), x0, refs, rbd)      # nothing to shift in a fresh context
+        for cx in (a, b, c):
+            cx.close()

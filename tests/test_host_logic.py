@@ -151,3 +151,39 @@ def test_host_only_entry_points_reject_misuse():
     g = hb.default_pd_gains(); k = hb.default_kf_params()
     assert (g.kp_big_stance, g.kd_feet) == (40.0, 0.01) and (k.foot_radius, k.foot_sensor_noise_velocity) == (0.02, 0.1)
     assert b"capacity" in lib.hb_strerror(-5) or b"planner" in lib.hb_strerror(-5)
+
+
+def test_task_info_parser_reads_the_wbc_estimator_and_solver_blocks():
+    """hb_parse_task_info on a fixture in the layout of the reference's task.info (values changed on purpose): nested blocks, `(i,j) value`
+    matrix entries, `;` comments, booleans; absent keys keep the shipped defaults."""
+    import hunter_bipedal_control_b200 as hb
+    ti = hb.parse_task_info(os.path.join(ROOT, "tests", "golden", "task_wbc_variant.info"))
+    w = ti.wbc
+    assert list(w.torque_limits) == [25.0, 55.0, 50.0, 58.0, 20.0]
+    assert (w.friction_coefficient, w.swing_kp, w.swing_kd) == (0.55, 140.0, 15.0)
+    assert (w.base_height_kp, w.base_height_kd, w.base_angular_kp, w.base_angular_kd) == (25.0, 3.5, 18.0, 2.5)
+    assert (w.weight_swing_leg, w.weight_base_accel, w.weight_contact_force) == (80.0, 1.5, 0.02)
+    assert list(ti.kalman) == [0.021, 0.03, 0.02, 0.5, 0.5, 0.1, 0.02]          # three keys present, four defaults (task.info:336-345)
+    assert (ti.contact_force_cutoff_frequency, ti.contact_threshold) == (200.0, 70.0)
+    assert (ti.sqp_dt, ti.sqp_iteration, ti.mpc_time_horizon, ti.mpc_cold_start) == (0.0125, 1, 0.75, 0)
+    assert ti.found == 1 | 2 | 4 | 8 | 16
+    lib = hb.load_library()
+    import ctypes as C
+    assert lib.hb_parse_task_info(b"/nonexistent/task.info", C.byref(hb.HbTaskInfo())) != 0
+    d = hb.HbWbcSettings(); assert lib.hb_default_wbc_settings(C.byref(d)) == 0
+    assert list(d.torque_limits) == [28.0, 60.0, 60.0, 60.0, 28.0] and (d.swing_kp, d.swing_kd, d.weight_swing_leg, d.weight_contact_force) == (160.0, 18.0, 100.0, 0.0)
+
+
+def test_task_info_parser_on_the_reference_file_when_present():
+    """The shipped task.info itself (only in the build container; the GPU box has no reference tree): the values equal the compiled-in defaults."""
+    import pytest
+    import hunter_bipedal_control_b200 as hb
+    path = "/root/reference/legged_controllers/config/hunter/task.info"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    ti = hb.parse_task_info(path)
+    import ctypes as C
+    d = hb.HbWbcSettings(); hb.load_library().hb_default_wbc_settings(C.byref(d))
+    assert np.array_equal(ti.wbc.as_array(), d.as_array())
+    assert ti.found == 31 and (ti.sqp_dt, ti.mpc_time_horizon, ti.contact_force_cutoff_frequency) == (0.015, 0.8, 250.0)
+    assert list(ti.kalman) == [0.02, 0.02, 0.02, 0.5, 0.5, 0.1, 0.01]
