@@ -375,6 +375,7 @@ def main():
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4], help="BASELINE.json configs[k]")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks of the host-pointer cycle (0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -410,7 +411,7 @@ def main():
         for k in range(B):
             C.memmove(C.addressof(sorted_refs[k]), C.addressof(refs[int(perm[k])]), C.sizeof(hb.HbReference))
         refs = sorted_refs
-    ctx = hb.Context(horizon_N=HORIZON_N, dt=DT, max_batch=B, device=local)
+    ctx = hb.Context(horizon_N=HORIZON_N, dt=DT, max_batch=B, device=local, e2e_chunks=args.e2e_chunks)
     stream = torch.cuda.ExternalStream(ctx.stream_handle, device=dev)
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     to = lambda a, dt_=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt_)
@@ -506,7 +507,8 @@ def main():
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
-    h2d = (h_t0.numel() + h_x0.numel() + h_rbd.numel()) * 8 + ref_bytes
+    ref_up = ctx.last_reference_upload_bytes            # only the used entries of the fixed-capacity hb_reference structs cross PCIe
+    h2d = (h_t0.numel() + h_x0.numel() + h_rbd.numel()) * 8 + ref_up
     d2h = (h_info.numel() + h_sol.numel() + h_tau.numel()) * 8 + h_st.numel() * 4
     extra = {}
     plan_s = full_s = 0.0
@@ -595,7 +597,7 @@ def main():
                            "parallelism": "instances sharded in contiguous blocks, NCCL gather of torques on a side stream" if world > 1 else "single GPU",
                            "l2": "per-step working set (node records %.0f MB + references/trajectories %.0f MB) exceeds the 126 MB L2" % (B * HORIZON_N * (1200 + 2320 + 368) * 8 / 1e6, full_h2d / 1e6)},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
-                        "call": "hb_resident_cycle_batch(cold_start=1): t0, x0, compact references, rbd in; info, WBC solution, torques, status out",
+                        "call": "hb_resident_cycle_batch(cold_start=1): t0, x0, compact references (packed: %d of %d bytes), rbd in; info, WBC solution, torques, status out" % (ref_up, ref_bytes),
                         "torque_max_rel_diff_vs_device_path": e2e_tau_diff},
                 "gpu_launches": int(launches),
                 "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},

@@ -20,7 +20,7 @@ NX, NU, NQ, NJ, NWBC = 22, 22, 16, 10, 38
 HB_MAX_EVENTS, HB_MAX_TARGETS, HB_MAX_SEGMENTS = 32, 16, 24
 
 EXPORTED_SYMBOLS = [
-    "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_last_cuda_error", "hb_launch_count", "hb_stream", "hb_profile_enable", "hb_profile_read",
+    "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_last_cuda_error", "hb_launch_count", "hb_last_reference_upload_bytes", "hb_stream", "hb_profile_enable", "hb_profile_read",
     "hb_wbc_qp_batch_dev", "hb_wbc_qp_rows_batch_dev", "hb_wbc_assemble_batch_dev", "hb_wbc_assemble_batch", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
     "hb_policy_eval_batch_dev", "hb_control_step_batch_dev", "hb_rbd_to_centroidal_batch_dev", "hb_reference_expand_batch_dev",
     "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references", "hb_gait_select", "hb_resident_cycle_batch_dev", "hb_resident_cycle_batch", "hb_resident_read_batch", "hb_plan_references_batch_dev",
@@ -40,7 +40,7 @@ EXPORTED_SYMBOLS = [
 
 class HbConfig(C.Structure):
     _fields_ = [("horizon_N", C.c_int32), ("dt", C.c_double), ("max_batch", C.c_int32), ("wbc_rho", C.c_double),
-                ("qp_max_iter", C.c_int32), ("line_search_max_trials", C.c_int32), ("time_horizon", C.c_double), ("event_nodes", C.c_int32)]
+                ("qp_max_iter", C.c_int32), ("line_search_max_trials", C.c_int32), ("time_horizon", C.c_double), ("event_nodes", C.c_int32), ("e2e_chunks", C.c_int32)]
 
 
 class HbSolveInfo(C.Structure):
@@ -280,6 +280,7 @@ def load_library():
         _lib.hb_strerror.restype = C.c_char_p
         _lib.hb_last_cuda_error.restype = C.c_char_p
         _lib.hb_launch_count.restype = C.c_int64
+        _lib.hb_last_reference_upload_bytes.restype = C.c_int64
         _lib.hb_stream.restype = C.c_void_p
     return _lib
 
@@ -309,13 +310,13 @@ class Context:
     """Owner of one hb_ctx (one GPU, one stream). Single-owner: use it from one thread at a time."""
 
     def __init__(self, horizon_N=100, dt=0.01, max_batch=1024, device=0, wbc_rho=1e-8, qp_max_iter=40, line_search_max_trials=14, time_horizon=0.0,
-                 event_nodes=False):
+                 event_nodes=False, e2e_chunks=0):
         lib = load_library()
         cfg = HbConfig()
         _check(lib.hb_default_config(C.byref(cfg)), "hb_default_config")
         cfg.horizon_N, cfg.dt, cfg.max_batch, cfg.wbc_rho = horizon_N, dt, max_batch, wbc_rho
         cfg.qp_max_iter, cfg.line_search_max_trials = qp_max_iter, line_search_max_trials
-        cfg.time_horizon, cfg.event_nodes = float(time_horizon), 1 if event_nodes else 0
+        cfg.time_horizon, cfg.event_nodes, cfg.e2e_chunks = float(time_horizon), 1 if event_nodes else 0, int(e2e_chunks)
         self.cfg = cfg
         self.N, self.dt, self.max_batch, self.device = horizon_N, dt, max_batch, device
         self._h = C.c_void_p()
@@ -363,6 +364,10 @@ class Context:
         _check(self._lib.hb_profile_read(self._h, _ptr(ms), _ptr(cnt)), "hb_profile_read", self._h)
         names = ["mpc_riccati", "mpc_forward_linesearch", "wbc_assemble", "qp_ipm", "other", "mpc_linearise", "mpc_lq_project"]
         return {n: dict(ms=float(m), launches=int(c)) for n, m, c in zip(names, ms, cnt)}
+
+    @property
+    def last_reference_upload_bytes(self):
+        return int(self._lib.hb_last_reference_upload_bytes(self._h))
 
     @property
     def stream_handle(self):

@@ -732,6 +732,37 @@ __global__ void rbd_to_centroidal_kernel(int B, const double* rbd, double* x) {
 // Expansion of the compact reference description onto the node grid (SwitchedModelReferenceManager::modifyReferences
 // products evaluated where the solver needs them: TargetTrajectories::getDesiredState, ModeSchedule::modeAtTime,
 // SwingTrajectoryPlanner::get{X,Y,Z}{position,velocity}Constraint; CubicSpline.cpp:46-124).
+// Packed upload of hb_reference (host-pointer cycle): only the used entries of the fixed-capacity struct cross PCIe (about 3 KB instead of
+// 17.7 KB per instance). Stream layout per instance, 8-byte words: header {n_events, n_targets, n_segments[12], 2 pad} (8 words),
+// event_times, modes (as int32 pairs, padded), target_times, target_states, segments. `offs` (B + 1 words offsets) leads the stream.
+struct RefPackHeader { int32_t n_events, n_targets, nseg[12], pad[2]; };
+static_assert(sizeof(RefPackHeader) == 64, "header is 8 words");
+__global__ void reference_unpack_kernel(int B, const long long* offs, const double* stream, hb_reference* refs) {
+  const int inst = blockIdx.x;
+  if (inst >= B) return;
+  const double* p = stream + offs[inst];
+  const RefPackHeader hd = *reinterpret_cast<const RefPackHeader*>(p);
+  hb_reference& r = refs[inst];
+  const int ne = min(max(hd.n_events, 0), HB_MAX_EVENTS), nt = min(max(hd.n_targets, 0), HB_MAX_TARGETS);
+  p += 8;
+  if (threadIdx.x == 0) { r.n_events = ne; r.n_targets = nt; for (int q = 0; q < 12; ++q) r.n_segments[q / 3][q % 3] = min(max(hd.nseg[q], 0), HB_MAX_SEGMENTS); }
+  for (int i = threadIdx.x; i < ne; i += blockDim.x) r.event_times[i] = p[i];
+  p += ne;
+  const int32_t* pm = reinterpret_cast<const int32_t*>(p);
+  for (int i = threadIdx.x; i <= ne; i += blockDim.x) r.modes[i] = pm[i];
+  p += (ne + 2) / 2;
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) r.target_times[i] = p[i];
+  p += nt;
+  for (int i = threadIdx.x; i < nt * 22; i += blockDim.x) r.target_states[i / 22][i % 22] = p[i];
+  p += nt * 22;
+  for (int q = 0; q < 12; ++q) {
+    const int ns = min(max(hd.nseg[q], 0), HB_MAX_SEGMENTS);
+    double* dst = &r.segments[q / 3][q % 3][0][0];
+    for (int i = threadIdx.x; i < ns * 6; i += blockDim.x) dst[i] = p[i];
+    p += ns * 6;
+  }
+}
+
 // Time discretisation with event nodes (row S1; ocs2::timeDiscretizationWithEvents as SqpSolver::run calls it): nodes step by dt from the
 // initial time; a step that would pass a mode-switch time lands on it instead (the pre-event interval is shortened) and the grid
 // re-anchors there; the last node is the final time; nodes closer than dt_min to their predecessor replace it. OCS2's duplicated
@@ -955,6 +986,7 @@ struct hb_ctx {
   double *s_x0, *s_xref, *s_swing, *s_xt, *s_ut, *s_rbd, *s_xd, *s_ud, *s_sol, *s_tau, *s_t0, *s_misc;
   double *res_xt = nullptr, *res_ut = nullptr, *res_t0 = nullptr;   // resident primal solution (hb_resident_cycle_batch)
   double *s_tk = nullptr, *res_tk = nullptr; int32_t *s_nn = nullptr, *res_nn = nullptr;   // node times / interval counts (event-node grids)
+  double* h_pack = nullptr; double* d_pack = nullptr; size_t pack_cap = 0;   // packed reference stream: pinned host staging + device copy (words)
   double* hoqp_scratch = nullptr; hb_hoqp_problem* hoqp_prob = nullptr;   // hierarchical WBC (allocated by its first call)
   int32_t* res_mode = nullptr;                                      // node modes of the resident solution (policy evaluation between MPC solves)
   int res_valid = 0;                                                // number of instances holding a previous solution
@@ -968,6 +1000,7 @@ struct hb_ctx {
   double *s_qpH, *s_qpA;   // generic QP staging (sized on demand)
   size_t s_qp_cap;
   int last_cuda;
+  size_t last_h2d_bytes;     // bytes of packed references uploaded by the last hb_resident_cycle_batch
   // optional per-kernel event timing (hb_profile_enable / hb_profile_read)
   int prof_on, prof_n;
   cudaEvent_t* prof_ev;   // 2 * PROF_MAX events
@@ -1033,6 +1066,7 @@ int hb_default_config(hb_config* cfg) {
   cfg->line_search_max_trials = 14;
   cfg->time_horizon = 0.0;
   cfg->event_nodes = 0;
+  cfg->e2e_chunks = 0;
   return HB_OK;
 }
 
@@ -1138,6 +1172,8 @@ int hb_destroy(hb_ctx* ctx) {
                   ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf, ctx->res_sol, ctx->s_tk, ctx->res_tk, ctx->s_nn, ctx->res_nn, ctx->res_mode, ctx->hoqp_scratch, ctx->hoqp_prob};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
+  if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
+  if (ctx->d_pack) cudaFree(ctx->d_pack);
   if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
   if (ctx->stream_main) cudaStreamDestroy(ctx->stream_main);
   else if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1182,6 +1218,7 @@ int hb_profile_read(hb_ctx* ctx, double* ms_per_kind, int64_t* count_per_kind) {
 const char* hb_last_cuda_error(const hb_ctx* ctx) { return ctx ? cudaGetErrorString((cudaError_t)ctx->last_cuda) : "no context"; }
 
 int64_t hb_launch_count(const hb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t hb_last_reference_upload_bytes(const hb_ctx* ctx) { return ctx ? (int64_t)ctx->last_h2d_bytes : 0; }
 void* hb_stream(hb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 // ------------------------------------------------------------------------------------------ device-pointer entry points
@@ -2114,6 +2151,37 @@ int hb_control_step_batch(hb_ctx* ctx, int B, double t_rel, const double* x0, co
   return HB_OK;
 }
 
+// words (8 bytes) one packed instance needs
+static inline size_t ref_pack_words(const hb_reference& r) {
+  size_t w = 8 + (size_t)r.n_events + ((size_t)r.n_events + 2) / 2 + (size_t)r.n_targets * 23;
+  for (int c = 0; c < 4; ++c) for (int a = 0; a < 3; ++a) w += (size_t)r.n_segments[c][a] * 6;
+  return w;
+}
+// pack refs[lo, hi) into the pinned staging area at word offset `base` (offsets first, then the per-instance streams); returns the words used
+static size_t ref_pack(const hb_reference* refs, size_t lo, size_t hi, double* dst) {
+  const size_t n = hi - lo;
+  long long* offs = reinterpret_cast<long long*>(dst);
+  size_t w = n + 1;
+  for (size_t i = 0; i < n; ++i) {
+    const hb_reference& r = refs[lo + i];
+    offs[i] = (long long)w;
+    double* p = dst + w;
+    RefPackHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    hd.n_events = r.n_events; hd.n_targets = r.n_targets;
+    for (int q = 0; q < 12; ++q) hd.nseg[q] = r.n_segments[q / 3][q % 3];
+    memcpy(p, &hd, sizeof(hd)); p += 8;
+    memcpy(p, r.event_times, sizeof(double) * r.n_events); p += r.n_events;
+    memcpy(p, r.modes, sizeof(int32_t) * (r.n_events + 1)); p += (r.n_events + 2) / 2;
+    memcpy(p, r.target_times, sizeof(double) * r.n_targets); p += r.n_targets;
+    memcpy(p, r.target_states, sizeof(double) * 22 * r.n_targets); p += 22 * r.n_targets;
+    for (int q = 0; q < 12; ++q) { const int ns = r.n_segments[q / 3][q % 3]; memcpy(p, &r.segments[q / 3][q % 3][0][0], sizeof(double) * 6 * ns); p += 6 * ns; }
+    w = (size_t)(p - dst);
+  }
+  offs[n] = (long long)w;
+  return w;
+}
+
 int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0, const hb_reference* refs,
                             const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque, int32_t* wbc_status) {
   if (!ctx || B < 0 || !t0 || !x0 || !refs || !rbd) return HB_EINVAL;
@@ -2122,8 +2190,27 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
   if (!cold_start && ctx->res_valid < B) return HB_EINVAL;
   if (!references_valid(B, refs)) return HB_EINVAL;
   if (set_device(ctx)) return HB_ECUDA;
-  // Two half-batches on two streams, as in hb_control_step_batch; only the small per-instance inputs and results cross PCIe.
-  const int nchunk = (B >= 256) ? 2 : 1;
+  // Half-batches on two streams, as in hb_control_step_batch; only the small per-instance inputs and results cross PCIe.
+  const int nchunk = ctx->cfg.e2e_chunks > 0 ? ((B >= 64 * ctx->cfg.e2e_chunks) ? ctx->cfg.e2e_chunks : 1) : ((B >= 256) ? 2 : 1);
+  {
+    size_t need = 0;
+    for (int i = 0; i < B; ++i) need += ref_pack_words(refs[i]);
+    need += (size_t)B + 2 * (size_t)nchunk + 8;
+    if (need > ctx->pack_cap) {
+      if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
+      if (ctx->d_pack) cudaFree(ctx->d_pack);
+      ctx->h_pack = nullptr; ctx->d_pack = nullptr; ctx->pack_cap = 0;
+      const size_t cap = need + need / 4;
+      if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_pack), cap * sizeof(double), cudaHostAllocDefault) != cudaSuccess || dalloc(&ctx->d_pack, cap) != cudaSuccess) {
+        cudaGetLastError();
+        if (ctx->h_pack) { cudaFreeHost(ctx->h_pack); ctx->h_pack = nullptr; }
+        return HB_ENOMEM;
+      }
+      ctx->pack_cap = cap;
+    }
+  }
+  size_t pack_base = 0;
+  ctx->last_h2d_bytes = 0;
   int rc = HB_OK;
   for (int c = 0; c < nchunk && rc == HB_OK; ++c) {
     const size_t lo = (size_t)B * c / nchunk, hi = (size_t)B * (c + 1) / nchunk, n = hi - lo;
@@ -2134,7 +2221,19 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
     auto d2h = [&](void* h, const void* d, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream); };
     h2d(ctx->s_t0 + lo, t0 + lo, sizeof(double) * n);
     h2d(ctx->s_x0 + lo * NX, x0 + lo * NX, sizeof(double) * n * NX);
-    h2d(ctx->s_refs + lo, refs + lo, sizeof(hb_reference) * n);
+    {
+      // references: only the used entries cross PCIe (packed into the context's pinned staging area, unpacked into s_refs on the device)
+      const size_t words = ref_pack(refs, lo, hi, ctx->h_pack + pack_base);
+      h2d(ctx->d_pack + pack_base, ctx->h_pack + pack_base, sizeof(double) * words);
+      if (e == cudaSuccess) {
+        reference_unpack_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((int)n, reinterpret_cast<const long long*>(ctx->d_pack + pack_base), ctx->d_pack + pack_base,
+                                                                        ctx->s_refs + lo);
+        ctx->launches++;
+        e = cudaGetLastError();
+      }
+      pack_base += words;
+      ctx->last_h2d_bytes += sizeof(double) * words;
+    }
     h2d(ctx->s_rbd + lo * 32, rbd + lo * 32, sizeof(double) * n * 32);
     if (e != cudaSuccess) { ctx->last_cuda = (int)e; rc = HB_ECUDA; break; }
     rc = hb_resident_cycle_batch_dev(ctx, (int)n, cold_start, t_rel, ctx->s_t0 + lo, ctx->s_x0 + lo * NX, ctx->s_refs + lo, ctx->s_rbd + lo * 32,

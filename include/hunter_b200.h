@@ -54,6 +54,8 @@ typedef struct {
   int32_t event_nodes;   /* 1: the resident cycle discretises [t0, t0 + time_horizon] like ocs2::timeDiscretizationWithEvents
                             (steps of dt, a node on every mode switch, grid re-anchored there, last node = final time); horizon_N is
                             then the node capacity. 0: uniform grid t0 + k dt (BASELINE configs)                          */
+  int32_t e2e_chunks;    /* host-pointer cycle calls split the batch into this many chunks pipelined over two streams (copies of one
+                            chunk overlap kernels of the other); 0 = automatic                                            */
 } hb_config;
 
 typedef struct {
@@ -211,6 +213,8 @@ const char* hb_strerror(int code);
 const char* hb_last_cuda_error(const hb_ctx* ctx);
 /* number of kernel launches issued through this context since creation (bench.py reports it as gpu_launches) */
 int64_t hb_launch_count(const hb_ctx* ctx);
+/* bytes of reference data the last hb_resident_cycle_batch moved host -> device (only the used entries of hb_reference are uploaded) */
+int64_t hb_last_reference_upload_bytes(const hb_ctx* ctx);
 /* per-kernel device timing with CUDA events on the context's stream (used by bench.py for the roofline line):
  * kinds 0 = Riccati sweep, 1 = forward pass + line search, 2 = WBC assembly, 3 = interior-point QP, 4 = other,
  *       5 = node linearisation (kinematics), 6 = node LQ model + projection */
