@@ -1061,7 +1061,7 @@ int hb_default_config(hb_config* cfg) {
   cfg->horizon_N = 100;
   cfg->dt = 0.01;
   cfg->max_batch = 1024;
-  cfg->wbc_rho = 1e-8;
+  cfg->wbc_rho = 1e-8;      // torques within 1.3e-4 (worst; median 4e-6) of the exact least-norm optimum, 6.7e-5 at 1e-9 (profiles/r02_wbc_rho.txt)
   cfg->qp_max_iter = 40;
   cfg->line_search_max_trials = 14;
   cfg->time_horizon = 0.0;
@@ -2191,7 +2191,10 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
   if (!references_valid(B, refs)) return HB_EINVAL;
   if (set_device(ctx)) return HB_ECUDA;
   // Half-batches on two streams, as in hb_control_step_batch; only the small per-instance inputs and results cross PCIe.
-  const int nchunk = ctx->cfg.e2e_chunks > 0 ? ((B >= 64 * ctx->cfg.e2e_chunks) ? ctx->cfg.e2e_chunks : 1) : ((B >= 256) ? 2 : 1);
+  // Automatic choice (measured, profiles/r02_e2e_chunks.txt): below ~4096 instances the half-batch kernels of the sequential stages (Riccati,
+  // forward pass, WBC: one wave each) run no faster than the full batch, so one chunk wins (124 k vs 113 k solves/s at 1024); from 4096 on
+  // two chunks hide the copies behind the other chunk's kernels (133 k vs 121 k at 8192).
+  const int nchunk = ctx->cfg.e2e_chunks > 0 ? ((B >= 64 * ctx->cfg.e2e_chunks) ? ctx->cfg.e2e_chunks : 1) : ((B >= 4096) ? 2 : 1);
   {
     size_t need = 0;
     for (int i = 0; i < B; ++i) need += ref_pack_words(refs[i]);
@@ -2275,7 +2278,7 @@ int hb_resident_plan_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_re
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (!cold_start && ctx->res_valid < B) return HB_EINVAL;
   if (set_device(ctx)) return HB_ECUDA;
-  const int nchunk = (B >= 256) ? 2 : 1;
+  const int nchunk = ctx->cfg.e2e_chunks > 0 ? ((B >= 64 * ctx->cfg.e2e_chunks) ? ctx->cfg.e2e_chunks : 1) : ((B >= 4096) ? 2 : 1);
   int rc = HB_OK;
   for (int c = 0; c < nchunk && rc == HB_OK; ++c) {
     const size_t lo = (size_t)B * c / nchunk, hi = (size_t)B * (c + 1) / nchunk, n = hi - lo;

@@ -26,8 +26,8 @@ def _setup(B, seed=41):
 
 
 def test_cold_cycle_equals_control_step():
-    ctx = hb.Context(horizon_N=N, dt=DT, max_batch=512, device=0)
-    for B in (7, 300):                      # single chunk and two pipelined half-batches
+    ctx = hb.Context(horizon_N=N, dt=DT, max_batch=512, device=0, e2e_chunks=2)
+    for B in (7, 300):                      # single chunk and two pipelined half-batches (packed reference upload per chunk)
         x0, refs, rbd = _setup(B)
         t0 = np.zeros(B)
         info, sol, tau, st = ctx.resident_cycle(True, 0.002, t0, x0, refs, rbd)
