@@ -36,18 +36,22 @@ __host__ __device__ inline int ntp_of(int nt) { return nt <= 6 ? 6 : (nt <= 10 ?
 // ---------------------------------------------------------------- K0
 struct LinHalf {
   double x[NX], u[NU], x2[NX], f[NX];
-  double Acm[6 * 16], Jc[12 * 16], dh[6 * NDIR], dcom[3 * NDIR], dp[12 * NDIR], dv[12 * NDIR];
-  double Abinv[36], AbinvAj[6 * NJ], dvb[6 * NDIR], vgen[16], epos[12], evel[12], com[3];
+  double Acm[6 * 16], Jc[12 * 16], dp[12 * NDIR], dv[12 * NDIR];
+  double Abinv[36], AbinvAj[6 * NJ], vgen[16], epos[12], evel[12], com[3];
   double sn[NDIR], cs[NDIR];   // sines / cosines of yaw, pitch, roll and the ten joint angles, shared by all sweeps of a stage
-  double part[16 * 9];         // per-lane partial sums of a chain-split sweep: P(3), Lo(3), mc(3)
+  // dh (6 x 13), dcom (3 x 13), dvb (6 x 13) are contiguous: the per-lane partial sums of a chain-split sweep (`part`: 16 lanes x {P(3), Lo(3),
+  // mc(3)}) live in the same storage -- they are consumed (into registers) before dh / dcom / dvb are written
+  double dh[6 * NDIR], dcom[3 * NDIR], dvb[6 * NDIR];
   double vals[2 * 6];          // values from the two base-seeded lanes 0 (base + left chain) and 3 (right chain): P(3), mc(3)
 };
+static_assert(16 * 9 <= 6 * NDIR + 3 * NDIR + 6 * NDIR, "partial sums must fit in the dh | dcom | dvb storage");
 
 // Linearise the flow map of one node at state xs (half-warp cooperative; `hl` = lane within the half, `act` = node exists).
 // Writes f, compact A rows 3..11 (9x22), Bf rows 3..5 (3x12), Bv rows 6..11 (6x10); with want_ee the contact kinematics record.
 __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const double* xs, int hl, bool act, double* rec_f, double* rec_A, double* rec_Bf,
                                       double* rec_Bv, bool want_ee, double* rec) {
   const double m = c_model.total_mass;
+  double* part = sh.dh;       // aliased storage, see LinHalf
   if (hl < NDIR) { double s, c; sincos(xs[9 + hl], &s, &c); sh.sn[hl] = s; sh.cs[hl] = c; }
   __syncwarp();
   // Lane tasks of the two chain-split sweeps (16 lanes, all busy):
@@ -66,7 +70,7 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const d
     kin_chain_f<double>(cm, leg, with_base, [&](int i) { return xs[6 + i]; }, [&](int i) { return (i == gen) ? 1.0 : 0.0; },
                         [&](int k, double& s, double& c) { s = sh.sn[k]; c = sh.cs[k]; }, co);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { sh.part[hl * 9 + i] = co.P[i]; sh.part[hl * 9 + 3 + i] = co.Lo[i]; }
+    for (int i = 0; i < 3; ++i) { part[hl * 9 + i] = co.P[i]; part[hl * 9 + 3 + i] = co.Lo[i]; }
     if (vlane) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) sh.vals[(hl / 3) * 6 + 3 + i] = co.mc[i];
@@ -95,8 +99,8 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const d
     double P[3], Lo[3], com[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      P[i] = sh.part[la * 9 + i]; Lo[i] = sh.part[la * 9 + 3 + i];
-      if (hl < 3) { P[i] += sh.part[(3 + hl) * 9 + i]; Lo[i] += sh.part[(3 + hl) * 9 + 3 + i]; }
+      P[i] = part[la * 9 + i]; Lo[i] = part[la * 9 + 3 + i];
+      if (hl < 3) { P[i] += part[(3 + hl) * 9 + i]; Lo[i] += part[(3 + hl) * 9 + 3 + i]; }
       com[i] = (sh.vals[3 + i] + sh.vals[9 + i]) / m;
     }
     sh.Acm[0 * 16 + g] = P[0]; sh.Acm[1 * 16 + g] = P[1]; sh.Acm[2 * 16 + g] = P[2];
@@ -142,7 +146,7 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const d
                     [&](int k, D1& s, D1& c) { const double sv = sh.sn[k], cv = sh.cs[k]; const double on = (k == dir) ? 1.0 : 0.0; s = D1(sv, cv * on); c = D1(cv, -sv * on); },
                     co);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { sh.part[hl * 9 + i] = co.P[i].d; sh.part[hl * 9 + 3 + i] = co.Lo[i].d; sh.part[hl * 9 + 6 + i] = co.mc[i].d; }
+    for (int i = 0; i < 3; ++i) { part[hl * 9 + i] = co.P[i].d; part[hl * 9 + 3 + i] = co.Lo[i].d; part[hl * 9 + 6 + i] = co.mc[i].d; }
     if (vlane) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) { sh.vals[(hl / 3) * 6 + i] = co.P[i].v; sh.vals[(hl / 3) * 6 + 3 + i] = co.mc[i].v; }
@@ -161,17 +165,20 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const d
     }
   }
   __syncwarp();
+  double Pd[3], Ld[3], dc[3], Pv[3], cv[3];
   if (hl < NDIR) {
     const int la = (hl < 3) ? hl : 3 + hl;
-    double Pd[3], Ld[3], dc[3], Pv[3], cv[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      Pd[i] = sh.part[la * 9 + i]; Ld[i] = sh.part[la * 9 + 3 + i]; dc[i] = sh.part[la * 9 + 6 + i];
-      if (hl < 3) { Pd[i] += sh.part[(3 + hl) * 9 + i]; Ld[i] += sh.part[(3 + hl) * 9 + 3 + i]; dc[i] += sh.part[(3 + hl) * 9 + 6 + i]; }
+      Pd[i] = part[la * 9 + i]; Ld[i] = part[la * 9 + 3 + i]; dc[i] = part[la * 9 + 6 + i];
+      if (hl < 3) { Pd[i] += part[(3 + hl) * 9 + i]; Ld[i] += part[(3 + hl) * 9 + 3 + i]; dc[i] += part[(3 + hl) * 9 + 6 + i]; }
       dc[i] /= m;
       Pv[i] = sh.vals[i] + sh.vals[6 + i];
       cv[i] = (sh.vals[3 + i] + sh.vals[9 + i]) / m;
     }
+  }
+  __syncwarp();     // every partial sum is in registers before dh / dcom overwrite the storage they share
+  if (hl < NDIR) {
     // d/dq of h = [P ; Lo - com x P]
     sh.dh[0 * NDIR + hl] = Pd[0]; sh.dh[1 * NDIR + hl] = Pd[1]; sh.dh[2 * NDIR + hl] = Pd[2];
     sh.dh[3 * NDIR + hl] = Ld[0] - ((dc[1] * Pv[2] - dc[2] * Pv[1]) + (cv[1] * Pd[2] - cv[2] * Pd[1]));
@@ -272,7 +279,10 @@ __device__ __forceinline__ double sqp_dt(const SqpArgs& a, int inst, int k) {
   return t[1] - t[0];
 }
 
-__global__ void __launch_bounds__(64) lin_kernel(SqpArgs a) {
+#ifndef HB_LIN_MINB
+#define HB_LIN_MINB 6
+#endif
+__global__ void __launch_bounds__(64, HB_LIN_MINB) lin_kernel(SqpArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp_in_block = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
@@ -324,6 +334,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }   // generic-proxy accesses before, async-proxy (TMA) writes after
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
   asm volatile(
       "{\n"
@@ -879,7 +890,24 @@ struct RicShared {
   double SBK[NX * NTMAX];                            // SB (22 x NTMAX), later K (NTMAX x 22)
   double HuxT[NX * NTMAX], Huu[NTMAX * 18];
   double sv[NX], sb[NX], hu[NTMAX], kff[NTMAX], idg[NTMAX];
+  unsigned long long bar[4];                         // mbarriers of the TMA staging: node inputs (two buffers), Pt^T / Rt, Qt
 };
+#ifndef HB_RIC_TMA
+#define HB_RIC_TMA 1     // 1: node records staged with TMA bulk copies + mbarriers; 0: the cp.async (LDGSTS) staging of round 1 (A/B measurements)
+#endif
+static_assert(sizeof(RicNodeIn) % 16 == 0 && (TS * sizeof(double)) % 16 == 0 && (NX * NTMAX * sizeof(double)) % 16 == 0, "bulk copies need 16-byte multiples");
+
+// node inputs by TMA: one elected lane arms the buffer's mbarrier with the byte count and issues six bulk copies (At, Bt, bt, qt, rt, meta)
+__device__ __forceinline__ void ric_prefetch_tma(RicNodeIn& n, const double* __restrict__ rec, unsigned long long* bar) {
+  fence_proxy_async();
+  mbar_expect_tx(bar, (unsigned)sizeof(RicNodeIn));
+  bulk_g2s(n.At, rec + PJ_AT, TS * sizeof(double), bar);
+  bulk_g2s(n.Bt, rec + PJ_BT, NX * NTMAX * sizeof(double), bar);
+  bulk_g2s(n.bt, rec + PJ_BTV, NX * sizeof(double), bar);
+  bulk_g2s(n.qt, rec + PJ_QV, NX * sizeof(double), bar);
+  bulk_g2s(n.rt, rec + PJ_RV, NTMAX * sizeof(double), bar);
+  bulk_g2s(n.meta, rec + PJ_META, 8 * sizeof(double), bar);
+}
 
 __device__ __forceinline__ void ric_prefetch(RicNodeIn& n, const double* __restrict__ rec, int lane) {
   for (int i = 2 * lane; i < TS; i += 64) cp_async16(n.At + i, rec + PJ_AT + i);
@@ -895,13 +923,17 @@ __device__ __forceinline__ void ric_prefetch(RicNodeIn& n, const double* __restr
 // the gain solve (one warp, latency bound) overlap with the largest product At' S At of the other warp.
 template <int NTP>
 __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, const double* __restrict__ rec, double* __restrict__ rk, bool& fail,
-                                          int warp) {
+                                          int warp, unsigned ph) {
   const int lane = lane_id();
   double* SB = sh.SBK; double* K = sh.SBK;
   // ---- phase A: [SA | SB | sb] = S [At | Bt | bt] (+ s): 22 + NTP + 1 result columns, split 16 / rest
   if (warp == 0) {
     rowmm<16, false, 0>(sh.SA, NX, sh.S, NX, in.At, NX, NX, NX);
+#if HB_RIC_TMA
+    mbar_wait(&sh.bar[2], ph);                // Pt^T / Rt staged by this warp at the top of the node
+#else
     cp_async_wait<0>();                       // Pt^T / Rt staged by this warp at the top of the node
+#endif
   } else {
     rowmm<6, false, 0>(sh.SA + 16, NX, sh.S, NX, in.At + 16, NX, NX, NX);
     rowmm<NTP, false, 0>(SB, NTMAX, sh.S, NX, in.Bt, NTMAX, NX, NX);
@@ -918,8 +950,12 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
     rowmm<NTP, true, 1>(sh.HuxT, NTMAX, sh.SA, NX, in.Bt, NTMAX, NX, NX);
   } else {
     // S is dead until phase D: stage Qt into it now (arrives while Huu is formed)
+#if HB_RIC_TMA
+    if (lane == 0) { fence_proxy_async(); mbar_expect_tx(&sh.bar[3], TS * sizeof(double)); bulk_g2s(sh.S, rec + PJ_QT, TS * sizeof(double), &sh.bar[3]); }
+#else
     for (int i = 2 * lane; i < TS; i += 64) cp_async16(sh.S + i, rec + PJ_QT + i);
     cp_async_commit();
+#endif
     rowmm<NTP, true, 1>(sh.Huu, 18, in.Bt, NTMAX, SB, NTMAX, NTP, NX);
     if (lane < NTP) {
       double s0 = in.rt[lane];
@@ -985,7 +1021,11 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
       sh.sv[lane] = s0 + s1;
     }
   } else {
+#if HB_RIC_TMA
+    mbar_wait(&sh.bar[3], ph);   // Qt has landed in S
+#else
     cp_async_wait<0>();   // Qt has landed in S (and the next node's inputs, issued by this warp at the top of the node)
+#endif
     __syncwarp();
     rowmm<NX, true, 1>(sh.S, NX, in.At, NX, sh.SA, NX, NX, NX);
   }
@@ -1004,15 +1044,40 @@ __global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
   const int inst = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double* proj = a.proj + (size_t)inst * a.N * PJ_STRIDE;
   const int N = sqp_nn(a, inst);         // active intervals of this instance; a.N is the stride
-  // warp 1 owns the node-input prefetch (and the Qt staging), warp 0 the Pt^T / Rt staging; each waits for its own groups
+  // warp 1 owns the node-input prefetch (and the Qt staging), warp 0 the Pt^T / Rt staging
+#if HB_RIC_TMA
+  if (threadIdx.x == 0) { for (int b = 0; b < 4; ++b) mbar_init(&sh.bar[b], 1); }
+  __syncthreads();
+  if (warp == 1 && lane == 0) ric_prefetch_tma(sh.in[(N - 1) & 1], proj + (size_t)(N - 1) * PJ_STRIDE, &sh.bar[(N - 1) & 1]);
+  unsigned ph_in0 = 0u, ph_in1 = 0u;
+#else
   if (warp == 1) ric_prefetch(sh.in[(N - 1) & 1], proj + (size_t)(N - 1) * PJ_STRIDE, lane);
+#endif
   for (int idx = threadIdx.x; idx < TS; idx += 64) sh.S[idx] = 0.0;   // no terminal cost
   if (threadIdx.x < NX) sh.sv[threadIdx.x] = 0.0;
   bool fail = false;
   double merit = 0.0, dyn = 0.0, eqs = 0.0;
+  __syncthreads();
   for (int k = N - 1; k >= 0; --k) {
     const double* rec = proj + (size_t)k * PJ_STRIDE;
     double* rk = a.rk + ((size_t)inst * a.N + k) * RK_STRIDE;
+    const unsigned ph = (unsigned)(N - 1 - k) & 1u;      // phase of the once-per-node barriers
+#if HB_RIC_TMA
+    // every thread waits for the inputs of node k (prefetched one node ahead); the two block barriers that end the previous node already
+    // order the re-use of HuxT / Huu / the other input buffer, so no barrier is needed here
+    if (k & 1) { mbar_wait(&sh.bar[1], ph_in1); ph_in1 ^= 1u; } else { mbar_wait(&sh.bar[0], ph_in0); ph_in0 ^= 1u; }
+    if (warp == 0) {
+      if (lane == 0) {
+        // Pt^T -> HuxT (22 x 16, contiguous) and Rt -> Huu (16 rows of 16 doubles, leading dimension 18): 1 + 16 bulk copies on one mbarrier
+        fence_proxy_async();
+        mbar_expect_tx(&sh.bar[2], (unsigned)((NX * NTMAX + NTMAX * NTMAX) * sizeof(double)));
+        bulk_g2s(sh.HuxT, rec + PJ_PT, NX * NTMAX * sizeof(double), &sh.bar[2]);
+        for (int r = 0; r < NTMAX; ++r) bulk_g2s(sh.Huu + r * 18, rec + PJ_RT + r * NTMAX, NTMAX * sizeof(double), &sh.bar[2]);
+      }
+    } else if (k > 0 && lane == 0) {
+      ric_prefetch_tma(sh.in[(k - 1) & 1], proj + (size_t)(k - 1) * PJ_STRIDE, &sh.bar[(k - 1) & 1]);
+    }
+#else
     if (warp == 1) cp_async_wait<0>();        // inputs of node k (prefetched one node ahead)
     __syncthreads();
     if (warp == 0) {
@@ -1023,15 +1088,16 @@ __global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
     } else if (k > 0) {
       ric_prefetch(sh.in[(k - 1) & 1], proj + (size_t)(k - 1) * PJ_STRIDE, lane);
     }
+#endif
     const RicNodeIn& in = sh.in[k & 1];
     const int nt = (int)in.meta[0];
     merit += in.meta[3]; dyn += in.meta[4]; eqs += in.meta[5];
     if (in.meta[6] != 0.0) fail = true;
     const int ntp = ntp_of(nt);
-    if (ntp == 12) riccati_node<12>(sh, in, rec, rk, fail, warp);
-    else if (ntp == 10) riccati_node<10>(sh, in, rec, rk, fail, warp);
-    else if (ntp == 6) riccati_node<6>(sh, in, rec, rk, fail, warp);
-    else riccati_node<16>(sh, in, rec, rk, fail, warp);
+    if (ntp == 12) riccati_node<12>(sh, in, rec, rk, fail, warp, ph);
+    else if (ntp == 10) riccati_node<10>(sh, in, rec, rk, fail, warp, ph);
+    else if (ntp == 6) riccati_node<6>(sh, in, rec, rk, fail, warp, ph);
+    else riccati_node<16>(sh, in, rec, rk, fail, warp, ph);
   }
   if (threadIdx.x == 0) {
     double* pf = a.perf + (size_t)inst * 4;
@@ -1049,7 +1115,30 @@ struct FwNode {
 struct Fw2Shared {
   FwNode nd[2];
   double dx[NX], dxn[NX], w[NTMAX];
+  unsigned long long bar[2];
 };
+#ifndef HB_FW_TMA
+#define HB_FW_TMA 1      // 1: node data staged with TMA bulk copies + mbarriers; 0: cp.async (LDGSTS) staging of round 1
+#endif
+static_assert(sizeof(FwNode) % 16 == 0 && (NJ * sizeof(double)) % 16 == 0 && (NJ * NX * sizeof(double)) % 16 == 0, "bulk copies need 16-byte multiples");
+
+__device__ __forceinline__ void fw_prefetch_tma(FwNode& n, const double* __restrict__ rec, const double* __restrict__ rk, const double* __restrict__ uk,
+                                                unsigned long long* bar) {
+  fence_proxy_async();
+  mbar_expect_tx(bar, (unsigned)sizeof(FwNode));
+  bulk_g2s(n.At, rec + PJ_AT, sizeof(n.At), bar);
+  bulk_g2s(n.Bt, rec + PJ_BT, sizeof(n.Bt), bar);
+  bulk_g2s(n.K, rk, sizeof(n.K), bar);
+  bulk_g2s(n.Pxv, rec + PJ_PXV, sizeof(n.Pxv), bar);
+  bulk_g2s(n.Nv, rec + PJ_NV, sizeof(n.Nv), bar);
+  bulk_g2s(n.bt, rec + PJ_BTV, sizeof(n.bt), bar);
+  bulk_g2s(n.qt, rec + PJ_QV, sizeof(n.qt), bar);
+  bulk_g2s(n.kff, rk + NTMAX * NX, sizeof(n.kff), bar);
+  bulk_g2s(n.rt, rec + PJ_RV, sizeof(n.rt), bar);
+  bulk_g2s(n.pev, rec + PJ_PEV, sizeof(n.pev), bar);
+  bulk_g2s(n.meta, rec + PJ_META, sizeof(n.meta), bar);
+  bulk_g2s(n.u, uk, sizeof(n.u), bar);
+}
 
 __device__ __forceinline__ void fw_prefetch(FwNode& n, const double* __restrict__ rec, const double* __restrict__ rk, const double* __restrict__ uk, int lane) {
   auto copy = [&](double* dst, const double* src, int ndbl) { for (int i = 2 * lane; i < ndbl; i += 64) cp_async16(dst + i, src + i); };
@@ -1082,14 +1171,27 @@ __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int 
   const int32_t* mode = a.mode + (size_t)inst * (NS + 1);
   const double* proj = a.proj + (size_t)inst * NS * PJ_STRIDE;
   const double* rkb = a.rk + (size_t)inst * NS * RK_STRIDE;
+#if HB_FW_TMA
+  if (lane == 0) { mbar_init(&sh.bar[0], 1); mbar_init(&sh.bar[1], 1); }
+  __syncwarp();
+  if (lane == 0) fw_prefetch_tma(sh.nd[0], proj, rkb, ut, &sh.bar[0]);
+  unsigned fph0 = 0u, fph1 = 0u;
+#else
   fw_prefetch(sh.nd[0], proj, rkb, ut, lane);
+#endif
   if (lane < NX) { xt[lane] = a.x0[(size_t)inst * NX + lane]; sh.dx[lane] = 0.0; dxt[lane] = 0.0; }
   double armijo = 0.0;
   bool finite = (a.flags[inst] == 0);
   for (int k = 0; k < N; ++k) {
+#if HB_FW_TMA
+    // the other buffer was last read at node k - 1 (the __syncwarp that ends every node orders those reads before the new copies)
+    if (k + 1 < N && lane == 0) fw_prefetch_tma(sh.nd[(k + 1) & 1], proj + (size_t)(k + 1) * PJ_STRIDE, rkb + (size_t)(k + 1) * RK_STRIDE, ut + (k + 1) * NU, &sh.bar[(k + 1) & 1]);
+    if (k & 1) { mbar_wait(&sh.bar[1], fph1); fph1 ^= 1u; } else { mbar_wait(&sh.bar[0], fph0); fph0 ^= 1u; }
+#else
     if (k + 1 < N) { fw_prefetch(sh.nd[(k + 1) & 1], proj + (size_t)(k + 1) * PJ_STRIDE, rkb + (size_t)(k + 1) * RK_STRIDE, ut + (k + 1) * NU, lane); cp_async_wait<1>(); }
     else cp_async_wait<0>();
     __syncwarp();
+#endif
     const FwNode& nd = sh.nd[k & 1];
     const int nt = (int)nd.meta[0], nf = (int)nd.meta[1], nv = (int)nd.meta[2];
     const int md_k = mode[k];

@@ -250,7 +250,6 @@ __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const 
 __device__ inline int wbc_reduced_build(const WbcShared& sh, int mode, int nw, bool stance_mode, double rho, const hb_wbc_settings& ws, const double* __restrict__ u_des,
                                         double* Hw, int ldh, double* gz, double* Az, double* lbz, double* ubz, int* stcol /*12*/, int& m_out) {
   const int lane = lane_id();
-  const Model& md = c_model;
   int nst = 0;
   for (int j = 0; j < 12; ++j) if (contact_flag(mode, j / 3)) { if (lane == 0) stcol[nst] = j; ++nst; }
   const int nz = NQ + nst;

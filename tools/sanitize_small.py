@@ -32,3 +32,24 @@ st = hb.kf_states(B)
 quat = np.tile([0.0, 0.0, 0.0, 1.0], (B, 1))
 rb = ctx.estimator_update(0.002, st, quat, np.zeros((B, 3)), np.tile([0, 0, 9.81], (B, 1)), x0[:, 12:22], np.zeros((B, 10)), np.ones((B, 4), dtype=np.uint8))
 print("estimator rbd finite", np.isfinite(rb).all(), "height", rb[0, 5])
+# round-2 kernels: event-node grid cycle, momentum observer, plant step, actuation model, 500 Hz tick, HoQP / hierarchical WBC, WBC assembly
+ev = hb.Context(horizon_N=40, dt=0.015, max_batch=8, time_horizon=0.45, event_nodes=True)
+comps = [sc.make_reference(x0[i], (0.3, 0.0, 0.0, 0.1), gaits[i], 30, 0.015, phase=0.011 * (i + 1))[3] for i in range(B)]
+erefs = sc.pack_references(comps, 2.0)
+for cyc, t_now in enumerate((0.0, 0.01)):
+    info, sol, tau, st = ev.resident_cycle(cyc == 0, 0.002, np.full(B, t_now), x0, erefs, rbd)
+xd, ud, md, sol2, tau2, st2 = ev.resident_wbc(np.full(B, 0.014), rbd)
+tk, nn = ev.resident_read_grid(B)
+print("event-node cycle: status", info["status"], st, "intervals", nn, "tick status", st2)
+obs = hb.observer_states(B)
+est, dist = ctx.contact_force_estimate(0.002, obs, rbd, tau)
+act = hb.actuation_states(B)
+cmd, out_tau, es = ctx.joint_command(0.002, xd, ud, sol2, md, rbd)
+tau_a = ctx.actuation(0.002, act, cmd, rbd)
+nxt, cf, fl = ctx.sim_step(rbd, tau_a)
+print("observer finite", np.isfinite(est).all(), "plant finite", np.isfinite(nxt).all(), "contacts", fl.sum(axis=1))
+hs, hst = ctx.hierarchical_wbc_solve(xd, ud, rbd, md)
+H, gq, A, lb, ub, m = ctx.wbc_assemble(xd, ud, rbd, md)
+print("hierarchical WBC status", hst, "rows", m)
+ev.close(); ctx.close()
+print("contexts closed")
