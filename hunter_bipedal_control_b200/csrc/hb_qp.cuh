@@ -117,6 +117,79 @@ __device__ inline bool warp_chol_inv(double* M, int n, int ld, double* invdiag, 
   return ok;
 }
 
+// Row-in-registers form of warp_chol_inv for n <= WMAX <= 32 and a compile-time leading dimension. 43 % of the fused WBC kernel's
+// instructions were spent in the shared-memory version (profiles/r02_wbc_breakdown.txt): two shared loads per multiply-add plus the
+// index arithmetic of a triangular loop nest. Here lane i keeps row i of the trailing matrix in registers as a SLIDING window: a[0] is
+// always the pivot column, and the rank-1 update writes a[k] from a[k+1], so the window advances without a move and the loop over the
+// pivots stays ROLLED (register arrays only ever see compile-time indices). The pivot column goes through shared memory once (it is
+// L, which the inverse needs anyway) and comes back as warp-uniform loads at immediate offsets: one LDS + one DFMA per term.
+// The window narrows in stages of seven columns (28 -> 21 -> 14 -> 7), so the code is four short loops rather than one unrolled
+// triangle -- a fully unrolled variant (~2.6k straight-line instructions per call) was faster for one in-phase wave of warps and 25-40 %
+// SLOWER once several waves ran out of phase and every warp streamed that code through the instruction cache on its own.
+// The inverse uses the same window on the residual of L y = e_c (lane c owns column c of Li).
+// A stage reads up to 6 + (W - rem) rows past row n-1 of M; those values only ever reach window slots of columns >= n, which are never
+// pivots, and the bytes lie inside the warp's workspace (K is followed by V, S by the vectors).
+template <int LD, int W, int WMAX>
+__device__ __forceinline__ void chol_window_factor(double (&a)[WMAX], double* M, int& j, int jend, int n, double* invdiag, int lane,
+                                                   double piv_floor, bool& ok) {
+  for (; j < jend; ++j) {
+    double d = __shfl_sync(HB_FULL_MASK, a[0], j);
+    if (!(d > piv_floor)) { if (piv_floor > 0.0 && d == d) d = piv_floor; else { ok = false; d = 1.0; } }
+    const double r = rsqrt(d);
+    const double l = a[0] * r;                       // L[i][j] on lane i > j
+    if (lane < n) M[lane * LD + j] = l;              // rows above the diagonal hold scratch; the inverse overwrites them
+    if (lane == j) invdiag[j] = r;
+    __syncwarp();
+    const double* col = M + (j + 1) * LD + j;        // L[j+1+k][j]
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k) a[k] = fma(-l, col[k * LD], a[k + 1]);
+  }
+}
+
+template <int LD, int W, int WMAX>
+__device__ __forceinline__ void chol_window_inverse(double (&res)[WMAX], double* M, int& j, int jend, const double* invdiag, int lane) {
+  for (; j < jend; ++j) {
+    const double y = res[0] * invdiag[j];            // Li[j][lane]; zero while j < lane
+    if (lane < j) M[lane * LD + j] = y;
+    const double* col = M + (j + 1) * LD + j;
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k) res[k] = fma(-col[k * LD], y, res[k + 1]);
+  }
+}
+
+template <int LD, int WMAX>
+__device__ __noinline__ bool warp_chol_inv_window(double* M, int n, double* invdiag, int lane, double piv_floor) {
+  static_assert(WMAX <= 32 && WMAX % 7 == 0, "one lane per row, stages of seven columns");
+  bool ok = true;
+  double a[WMAX];
+#pragma unroll
+  for (int c = 0; c < WMAX; ++c) a[c] = (lane < n && c <= lane) ? M[lane * LD + c] : 0.0;
+  __syncwarp();
+  int j = 0;
+  if constexpr (WMAX >= 28) chol_window_factor<LD, 28, WMAX>(a, M, j, n - 21, n, invdiag, lane, piv_floor, ok);
+  if constexpr (WMAX >= 21) chol_window_factor<LD, 21, WMAX>(a, M, j, n - 14, n, invdiag, lane, piv_floor, ok);
+  if constexpr (WMAX >= 14) chol_window_factor<LD, 14, WMAX>(a, M, j, n - 7, n, invdiag, lane, piv_floor, ok);
+  chol_window_factor<LD, 7, WMAX>(a, M, j, n, n, invdiag, lane, piv_floor, ok);
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < WMAX; ++c) a[c] = (c == lane) ? 1.0 : 0.0;
+  j = 0;
+  if constexpr (WMAX >= 28) chol_window_inverse<LD, 28, WMAX>(a, M, j, n - 21, invdiag, lane);
+  if constexpr (WMAX >= 21) chol_window_inverse<LD, 21, WMAX>(a, M, j, n - 14, invdiag, lane);
+  if constexpr (WMAX >= 14) chol_window_inverse<LD, 14, WMAX>(a, M, j, n - 7, invdiag, lane);
+  chol_window_inverse<LD, 7, WMAX>(a, M, j, n, invdiag, lane);
+  __syncwarp();
+  return ok;
+}
+
+// dispatch on the layout: the window form for the fused WBC problem (16 + 3 n_stance <= 28 variables at ld 29, <= 6 equalities at ld 7),
+// the shared-memory form for everything else
+__device__ inline bool warp_chol_inv_any(double* M, int n, int ld, double* invdiag, int lane, double piv_floor) {
+  if (ld == 29 && n <= 28) return warp_chol_inv_window<29, 28>(M, n, invdiag, lane, piv_floor);
+  if (ld == 7 && n <= 7) return warp_chol_inv_window<7, 7>(M, n, invdiag, lane, piv_floor);
+  return warp_chol_inv(M, n, ld, invdiag, lane, piv_floor);
+}
+
 // y = Li v  (lower-triangular inverse stored as described above); lanes over rows
 __device__ inline void warp_li_mv(const double* M, int n, int ld, const double* invdiag, const double* v, double* y, int lane) {
   for (int i = lane; i < n; i += 32) {
@@ -322,7 +395,7 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
     }
     // directions that only the Tikhonov term rho controls have pivots ~1e-8 next to barrier weights ~1e10 late in the solve:
     // floor the pivots instead of failing
-    bool ok = warp_chol_inv(w.K, n, ldn, w.kdi, lane, 1e-10);
+    bool ok = warp_chol_inv_any(w.K, n, ldn, w.kdi, lane, 1e-10);
     // ---------------- V = Li Aeq'  (n x me), lane per equality row
     if (me > 0) {
       // entries (i, e) spread over all lanes (a lane per equality row would leave most of the warp idle: me is 6 for the WBC)
@@ -348,7 +421,7 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
         }
       }
       __syncwarp();
-      ok = warp_chol_inv(w.S, me, lds, w.sdi, lane, 1e-14) && ok;
+      ok = warp_chol_inv_any(w.S, me, lds, w.sdi, lane, 1e-14) && ok;
     }
     if (!ok) { res.status = 2; break; }
 
