@@ -308,6 +308,9 @@ def run_qp_sweep(args, rank, world, local):
             if name == "raw":
                 it = d_it[:B].to(torch.float64)
                 res[name]["mean_iters"] = float(it.mean().item()); res[name]["max_iters"] = int(it.max().item())
+                # interior-point iterations per QP: {iterations: QPs}; the kernel's latency is (slowest warp per SM) x (per-iteration chain)
+                hist = torch.bincount(d_it[:B].to(torch.int64))
+                res[name]["iters_hist"] = {str(i): int(c) for i, c in enumerate(hist.tolist()) if c}
         sweep.append(res)
     # parity of the two device paths on the largest batch (same optimum: torques to 1e-4 relative)
     raw_tau = None

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "hb_default_config", "hb_create", "hb_destroy", "hb_sync", "hb_strerror", "hb_last_cuda_error", "hb_launch_count", "hb_last_reference_upload_bytes", "hb_stream", "hb_profile_enable", "hb_profile_read",
     "hb_wbc_qp_batch_dev", "hb_wbc_qp_rows_batch_dev", "hb_wbc_assemble_batch_dev", "hb_wbc_assemble_batch", "hb_wbc_solve_batch_dev", "hb_mpc_cold_start_batch_dev", "hb_mpc_solve_batch_dev",
     "hb_policy_eval_batch_dev", "hb_control_step_batch_dev", "hb_rbd_to_centroidal_batch_dev", "hb_reference_expand_batch_dev",
-    "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references", "hb_gait_select", "hb_resident_cycle_batch_dev", "hb_resident_cycle_batch", "hb_resident_read_batch", "hb_plan_references_batch_dev",
+    "hb_probe_flow_map_dev", "hb_contact_positions_batch_dev", "hb_contact_positions_batch", "hb_plan_references", "hb_plan_set_threads", "hb_gait_select", "hb_resident_cycle_batch_dev", "hb_resident_cycle_batch", "hb_resident_read_batch", "hb_plan_references_batch_dev",
     "hb_plan_references_gpu", "hb_resident_plan_cycle_batch", "hb_default_kf_params", "hb_kf_reset", "hb_estimator_update_batch_dev",
     "hb_estimator_update_batch", "hb_default_pd_gains", "hb_joint_command_batch_dev", "hb_joint_command_batch",
     "hb_wbc_qp_batch", "hb_wbc_solve_batch", "hb_mpc_cold_start_batch", "hb_mpc_solve_batch", "hb_control_step_batch",
@@ -247,6 +247,11 @@ def make_plan_inputs(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_
         for j in range(4): p.cmd_vel[j] = cmd_vel[i, j]
         for j in range(12): p.feet_pos[j] = feet_pos[i, j]
     return ins
+
+
+def plan_set_threads(n):
+    """Host threads of plan_references (0 = all); hb_plan_set_threads."""
+    _check(load_library().hb_plan_set_threads(int(n)), "hb_plan_set_threads")
 
 
 def plan_references(t0, horizon, x0, cmd_vel, feet_pos, gait, gait_start, prev_event=None, time_to_target=None, latest_stance=None, joint_ik=True):

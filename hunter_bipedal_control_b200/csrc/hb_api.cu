@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <string>
 #include <utility>
+#include <atomic>
 #include <thread>
 #include <vector>
 #include "hb_qp.cuh"
@@ -2475,6 +2476,7 @@ int hb_contact_positions_batch(hb_ctx* ctx, int B, const double* x, double* pos)
   return hb_sync(ctx);
 }
 
+static std::atomic<int> g_plan_threads{0};   // 0 = hardware_concurrency (hb_plan_set_threads)
 static int plan_range(int lo, int hi, const hb_plan_input* in, double* latest_stance, hb_reference* out) {
   static const hbplan::PlanConsts pc = hbplan::make_consts();
   for (int i = lo; i < hi; ++i) {
@@ -2484,11 +2486,17 @@ static int plan_range(int lo, int hi, const hb_plan_input* in, double* latest_st
   return HB_OK;
 }
 
+int hb_plan_set_threads(int n_threads) {
+  if (n_threads < 0) return HB_EINVAL;
+  g_plan_threads.store(n_threads);
+  return HB_OK;
+}
+
 int hb_plan_references(int B, const hb_plan_input* in, double* latest_stance, hb_reference* out) {
   if (B < 0 || !in || !latest_stance || !out) return HB_EINVAL;
   // instances are independent: spread them over the host cores (the planner feeds ~1e5 solves/s per GPU; one core plans ~2e4/s)
   unsigned hw = std::thread::hardware_concurrency();
-  if (const char* e = getenv("HB_PLAN_THREADS")) hw = (unsigned)atoi(e);
+  if (const int forced = g_plan_threads.load()) hw = (unsigned)forced;
   int nt = (int)std::min<unsigned>(hw ? hw : 1u, (unsigned)((B + 63) / 64));
   if (nt <= 1) return plan_range(0, B, in, latest_stance, out);
   std::vector<std::thread> pool;

@@ -391,8 +391,10 @@ int hb_contact_positions_batch(hb_ctx* ctx, int B, const double* x, double* pos 
  * (src/SwitchedModelReferenceManager.cpp:251-300, src/foot_planner/InverseKinematics.cpp:20-231). latest_stance (B x 12) is the planner's state, in/out.
  * Returns 0, or -1 on misuse, or -5 when a schedule does not define the take-off / touch-down of a swing phase (the reference
  * throws there, SwingTrajectoryPlanner.cpp:421-458) or exceeds the capacity of hb_reference.
- * Instances are spread over std::thread::hardware_concurrency() host threads (environment variable HB_PLAN_THREADS overrides the count). */
+ * Instances are spread over std::thread::hardware_concurrency() host threads (hb_plan_set_threads overrides the count). */
 int hb_plan_references(int B, const hb_plan_input* in, double* latest_stance, hb_reference* out);
+/* Host threads used by hb_plan_references (process-wide); 0 = hardware_concurrency. The result does not depend on the count. */
+int hb_plan_set_threads(int n_threads);
 /* speed-based gait selection (calculateVelAbs + walkGait / trotGait, src/SwitchedModelReferenceManager.cpp:185-249): updates the
  * 50-sample moving average of 0.5*(command + target) speed of every instance and applies the thresholds stance <= 0.02 < (no change)
  * <= 0.03 < trot < 0.4 <= level 3. gait_type: 0 walk (automatic), 2 trot (forced). level[i] = gait level in force after the call,

@@ -157,13 +157,14 @@ def test_gait_selector_matches_restatement():
     assert seen >= {0, 1, 3}
 
 
-def test_planner_threads_give_identical_bytes(monkeypatch):
+def test_planner_threads_give_identical_bytes():
     n = 200
     x0, gaits, cmd, t0, start, feet, latest = _cases(n, seed=31)
-    monkeypatch.setenv("HB_PLAN_THREADS", "1")
+    hb.plan_set_threads(1)
     r1, l1 = hb.plan_references(t0, T, x0, cmd, feet, gaits, start, latest_stance=latest)
-    monkeypatch.setenv("HB_PLAN_THREADS", "3")
+    hb.plan_set_threads(3)
     r3, l3 = hb.plan_references(t0, T, x0, cmd, feet, gaits, start, latest_stance=latest)
+    hb.plan_set_threads(0)
     assert bytes(r1) == bytes(r3) and np.array_equal(l1, l3)
 
 
