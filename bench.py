@@ -378,6 +378,7 @@ def main():
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4], help="BASELINE.json configs[k]")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-gather", action="store_true", help="multi-GPU: gather with torch.distributed instead of hb_shard_gather_dev")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks of the host-pointer cycle (0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -417,10 +418,21 @@ def main():
     ctx = hb.Context(horizon_N=HORIZON_N, dt=DT, max_batch=B, device=local, e2e_chunks=args.e2e_chunks)
     stream = torch.cuda.ExternalStream(ctx.stream_handle, device=dev)
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    # the gather behind the C ABI (hb_shard_*: un-permute + NCCL all-gather on the shard's own stream); torch.distributed only carries the
+    # 128-byte communicator id and the barriers. `--torch-gather` keeps the round-1 path (dist.all_gather issued from Python).
+    shard = None
+    if world > 1 and not args.torch_gather:
+        uid_t = torch.zeros(sharding.SHARD_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid_t.copy_(torch.frombuffer(bytearray(sharding.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid_t, 0)
+        shard = sharding.Shard(ctx, bytes(uid_t.cpu().numpy().tobytes()), world, rank, total_B, max_row_doubles=10)
+        assert (shard.lo, shard.hi) == (lo, hi)
     to = lambda a, dt_=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt_)
     d_x0, d_xref, d_swing, d_rbd = to(x0), to(x_ref), to(swing), to(rbd)
     d_mode = to(mode, torch.int32)
     d_inv = to(inv, torch.int64) if inv is not None else None
+    d_inv32 = to(inv, torch.int32) if inv is not None else None
     d_xt0 = torch.zeros((B, HORIZON_N + 1, 22), dtype=torch.float64, device=dev); d_ut0 = torch.zeros((B, HORIZON_N, 22), dtype=torch.float64, device=dev)
     ctx.mpc_cold_start_dev(d_x0, d_mode, d_xt0, d_ut0)
     ctx.sync()
@@ -436,7 +448,9 @@ def main():
         with torch.cuda.stream(stream):
             d_xt.copy_(d_xt0, non_blocking=True); d_ut.copy_(d_ut0, non_blocking=True)   # every step starts from the initializer's cold start
         ctx.control_step_dev(T_POLICY, d_x0, d_xref, d_swing, d_mode, d_rbd, d_xt, d_ut, d_info, d_sol, d_tau, d_st)
-        if world > 1:
+        if shard is not None:
+            gathered[0] = shard.gather(d_tau, d_inv32)      # asynchronous: pack on the compute stream, all-gather + compaction on the shard's stream
+        elif world > 1:
             buf = d_out[step_no[0] & 1]
             step_no[0] += 1
             with torch.cuda.stream(stream):
@@ -452,6 +466,8 @@ def main():
 
     def barrier():
         if world > 1:
+            if shard is not None:
+                shard.wait(block_host=True)
             comm_stream.synchronize()
             dist.barrier()
         ctx.sync(); torch.cuda.synchronize(dev)
@@ -470,8 +486,10 @@ def main():
     ev0.record(stream)
     for _ in range(args.steps):
         step_device()
-    if world > 1:
-        stream.wait_stream(comm_stream)      # the timed region ends when the last gather has landed
+    if shard is not None:
+        shard.wait()                         # the compute stream waits for the last gather: the timed region ends when it has landed
+    elif world > 1:
+        stream.wait_stream(comm_stream)
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -480,7 +498,12 @@ def main():
     ctx.profile_enable(False)
     gather_ok = None
     if world > 1 and rank == 0:
-        gather_ok = bool(gathered[0] is not None and gathered[0].shape[0] == total_B and torch.isfinite(gathered[0]).all().item())
+        if shard is not None:
+            g_all = shard.to_host(gathered[0], 10)
+            mine = d_tau.cpu().numpy() if inv is None else d_tau.cpu().numpy()[inv]
+            gather_ok = bool(g_all.shape[0] == total_B and np.isfinite(g_all).all() and np.array_equal(g_all[lo:hi], mine))
+        else:
+            gather_ok = bool(gathered[0] is not None and gathered[0].shape[0] == total_B and torch.isfinite(gathered[0]).all().item())
     # ---------------- end-to-end through the host-pointer C ABI, pinned host buffers, copies inside the timed region.
     # e2e      : hb_resident_cycle_batch -- the closed-loop call: t0 / x0 / compact references / rbd in, info / WBC solution / torques out;
     #            reference expansion and the initializer cold start run on the device, the primal solution stays resident.
@@ -597,7 +620,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_desc(cfg, B) + ", one SQP iteration from the initializer cold start + policy eval at 2 ms + WeightedWbc QP",
                            "instances_total": total_B,
-                           "parallelism": "instances sharded in contiguous blocks, NCCL gather of torques on a side stream" if world > 1 else "single GPU",
+                           "parallelism": ("instances sharded in contiguous blocks, NCCL all-gather of torques on a side stream (%s)" % ("hb_shard_gather_dev, C ABI" if shard is not None else "torch.distributed")) if world > 1 else "single GPU",
                            "l2": "per-step working set (node records %.0f MB + references/trajectories %.0f MB) exceeds the 126 MB L2" % (B * HORIZON_N * (1200 + 2320 + 368) * 8 / 1e6, full_h2d / 1e6)},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
                         "call": "hb_resident_cycle_batch(cold_start=1): t0, x0, compact references (packed: %d of %d bytes), rbd in; info, WBC solution, torques, status out" % (ref_up, ref_bytes),
@@ -633,6 +656,8 @@ def main():
                                     "sample": "%d control steps of the same workload, all host threads; single-thread %.2f solves/s" % (n, 2 / t_one),
                                     "single_thread_value": 2 / t_one, "torque_rel_err_vs_gpu": err}
         print(json.dumps(line))
+    if shard is not None:
+        shard.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -15,6 +15,8 @@
 #include <string>
 #include <utility>
 #include <atomic>
+#include <mutex>
+#include <cstring>
 #include <thread>
 #include <vector>
 #include "hb_qp.cuh"
@@ -1010,7 +1012,7 @@ struct hb_ctx {
 
 namespace {
 
-enum { HB_OK = 0, HB_EINVAL = -1, HB_ECUDA = -2, HB_ENOMEM = -3, HB_ECAP = -4, HB_EPLAN = -5 };
+enum { HB_OK = 0, HB_EINVAL = -1, HB_ECUDA = -2, HB_ENOMEM = -3, HB_ECAP = -4, HB_EPLAN = -5, HB_ECOMM = -6 };
 
 #define CK(call)                                   \
   do {                                             \
@@ -1079,6 +1081,7 @@ const char* hb_strerror(int code) {
     case HB_ENOMEM: return "out of memory";
     case HB_ECAP: return "batch exceeds context capacity";
     case HB_EPLAN: return "reference planner: swing phase without take-off / touch-down time, or reference capacity exceeded";
+    case HB_ECOMM: return "NCCL not available or a collective failed (hb_shard_last_error)";
     default: return "unknown error";
   }
 }
@@ -2539,3 +2542,5 @@ int hb_probe_flow_map(hb_ctx* ctx, int B, const double* x, const double* u, doub
 }
 
 }  // extern "C"
+
+#include "hb_shard.cuh"

@@ -402,6 +402,32 @@ int hb_plan_set_threads(int n_threads);
 int hb_gait_select(int B, hb_gait_selector* state, const int32_t* gait_type, const double* cmd_vel /*B x 4*/,
                    const double* target_state0 /*B x 22*/, int32_t* level, int32_t* insert);
 
+/* ---- (e) multi-GPU shards (replaces nothing in the reference, which runs one robot per process): one process + one hb_ctx
+ * per GPU, instances split in contiguous blocks, no collective on the data path. The only exchange is the gather of per-instance
+ * output rows (the 80-byte torque rows of the control step), by NCCL all-gather on the shard's own stream behind an event on the
+ * context's stream, so it overlaps the next step's kernels. NCCL is resolved at run time (the libnccl.so.2 already in the process, else
+ * the system one); a single-GPU caller never loads it. Return code -6: NCCL missing or a collective failed (hb_shard_last_error). */
+#define HB_SHARD_ID_BYTES 128
+typedef struct hb_shard hb_shard;
+/* contiguous block [begin, begin + count) of `rank`; block sizes differ by at most one */
+int hb_shard_partition(int total, int world, int rank, int* begin, int* count);
+/* stable permutation that groups instances with the same mode sequence (mode: B x nodes), so that the warps of a wave run the same
+ * swing-contact specialisation: sorted[i] = original[perm[i]]; inverse (nullable): inverse[perm[i]] = i */
+int hb_shard_sort_by_schedule(int B, int nodes, const int32_t* mode, int32_t* perm, int32_t* inverse);
+/* rank 0 draws the communicator id (HB_SHARD_ID_BYTES bytes); the caller hands the bytes to the other ranks out of band (MPI, a file, a socket) */
+int hb_shard_unique_id(void* id);
+/* collective over all ranks; total_instances = instances of the whole job, max_row_doubles = widest row ever gathered. world == 1: id may be NULL */
+int hb_shard_create(hb_ctx* ctx, const void* id, int world, int rank, int total_instances, int max_row_doubles, hb_shard** out);
+int hb_shard_destroy(hb_shard* shard);
+int hb_shard_block(const hb_shard* shard, int* begin, int* count);
+/* rows_dev: count x row_doubles of this rank's block (device). inverse_dev (nullable, device): undo a schedule sort first
+ * (row i of the block = rows_dev[inverse_dev[i]]). *gathered_dev: total_instances x row_doubles in instance order on EVERY rank, complete
+ * after hb_shard_wait; double buffered, valid until the second next call. Asynchronous: ordered behind the context's stream. */
+int hb_shard_gather_dev(hb_shard* shard, int row_doubles, const double* rows_dev, const int32_t* inverse_dev, const double** gathered_dev);
+/* the context's stream waits for the last gather; block_host != 0 also blocks the calling thread until it has landed */
+int hb_shard_wait(hb_shard* shard, int block_host);
+const char* hb_shard_last_error(const hb_shard* shard);
+
 #ifdef __cplusplus
 }
 #endif

@@ -187,3 +187,20 @@ def test_task_info_parser_on_the_reference_file_when_present():
     assert np.array_equal(ti.wbc.as_array(), d.as_array())
     assert ti.found == 31 and (ti.sqp_dt, ti.mpc_time_horizon, ti.contact_force_cutoff_frequency) == (0.015, 0.8, 250.0)
     assert list(ti.kalman) == [0.02, 0.02, 0.02, 0.5, 0.5, 0.1, 0.01]
+
+
+def test_native_shard_helpers_match_python_mirror():
+    """hb_shard_partition / hb_shard_sort_by_schedule (C ABI, host only) against sharding.partition / sort_by_schedule."""
+    from hunter_bipedal_control_b200 import sharding
+    for total in (0, 1, 7, 10, 1024, 65536):
+        for w in (1, 2, 3, 8):
+            blocks = [sharding.native_partition(total, w, r) for r in range(w)]
+            assert blocks == [sharding.partition(total, w, r) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == total and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+    rng = np.random.default_rng(0)
+    mode = rng.integers(0, 4, (300, 6)).astype(np.int32)
+    p, i = sharding.native_sort_by_schedule(mode)
+    p2, i2 = sharding.sort_by_schedule(mode)
+    assert np.array_equal(p, p2) and np.array_equal(i, i2)
+    srt = mode[p]
+    assert all(tuple(srt[k]) <= tuple(srt[k + 1]) for k in range(len(srt) - 1))
