@@ -32,24 +32,122 @@ __device__ __forceinline__ Pen double_sided(double h, double lo, double hi, doub
 
 // ------------------------------------------------------------------ centroidal flow map, one lane = one evaluation
 // (used by the line search: lane-per-node). x = [hbar(6), q(16)], u = [F(12), qj_dot(10)]   
-// Uses the block structure of the centroidal momentum matrix: A[:, 0:3] = [m I; 0] (computeFloatingBaseCentroidalMomentumMatrixInverse).
+// ONE sweep over the kinematic tree per evaluation. The base twist solves A_b v_b = m hbar - A_j qj_dot; instead of probing the columns of
+// the centroidal momentum matrix with unit velocities (five sweeps in round 1: joint momentum, three Euler-rate columns, contact
+// velocities) the sweep runs with the base at rest and accumulates, next to the joint momentum A_j qj_dot, the rotational inertia of the
+// whole robot about the origin. For a rigid motion (v0, w) of the base the momentum is [m (v0 + w x (com - p0)); I_C w] with
+// I_C = I_O - m (|com|^2 1 - com com'), so A[:, 0:3] = [m I; 0] (computeFloatingBaseCentroidalMomentumMatrixInverse) and the Euler-rate
+// columns are [m w_c x (com - p0); I_C w_c] with w_c the world axis of Euler rate c. Velocities are linear in v, so the contact
+// velocities are the base-at-rest ones plus v0 + W x (cpos - p0).
 __device__ inline void flow_map_lane(const double* x, const double* u, double* f, double* epos, double* evel) {
-  const double m = c_model.total_mass;
-  double q[NQ], v[NQ];
-  for (int i = 0; i < NQ; ++i) q[i] = x[6 + i];
-  KinOut<double> o;
-  for (int i = 0; i < 6; ++i) v[i] = 0.0;
-  for (int j = 0; j < NJ; ++j) v[6 + j] = u[12 + j];
-  kin_pass<double>(q, v, o);
-  double hj[6], com[3], cp[12];
-  for (int i = 0; i < 6; ++i) hj[i] = o.h[i];
-  for (int i = 0; i < 3; ++i) com[i] = o.com[i];
-  for (int i = 0; i < 12; ++i) cp[i] = o.cpos[i];
-  double Ae[6][3];  // euler columns of A
+  const Model& md = c_model;
+  const double m = md.total_mass;
+  double R0[9], ax0[9];
+  {
+    double sz, cz, sy, cy, sx, cx;
+    sincos_t(x[9], sz, cz); sincos_t(x[10], sy, cy); sincos_t(x[11], sx, cx);
+    R0[0] = cz * cy; R0[1] = cz * sy * sx - sz * cx; R0[2] = cz * sy * cx + sz * sx;
+    R0[3] = sz * cy; R0[4] = sz * sy * sx + cz * cx; R0[5] = sz * sy * cx - cz * sx;
+    R0[6] = -sy;     R0[7] = cy * sx;                R0[8] = cy * cx;
+    ax0[0] = 0.0; ax0[1] = 0.0; ax0[2] = 1.0;
+    ax0[3] = -sz; ax0[4] = cz; ax0[5] = 0.0;
+    ax0[6] = cz * cy; ax0[7] = sz * cy; ax0[8] = -sy;
+  }
+  const double p0[3] = {x[6], x[7], x[8]};
+  double P[3] = {0, 0, 0}, Lo[3] = {0, 0, 0}, mc[3] = {0, 0, 0};
+  double IO[6] = {0, 0, 0, 0, 0, 0};    // xx xy xz yy yz zz about the origin
+  double cp[12], cvj[12];
+  // mass, first moment and rotational inertia of body b (world frame, about the origin)
+  auto add_inertia = [&](int b, const double* R, const double* cw) {
+    const double mb = md.mass[b];
+    const double* I = &md.inertia[9 * b];
+    double T[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) T[3 * i + k] = R[3 * i] * I[k] + R[3 * i + 1] * I[3 + k] + R[3 * i + 2] * I[6 + k];
+    const double c2 = cw[0] * cw[0] + cw[1] * cw[1] + cw[2] * cw[2];
+    IO[0] += T[0] * R[0] + T[1] * R[1] + T[2] * R[2] + mb * (c2 - cw[0] * cw[0]);
+    IO[1] += T[0] * R[3] + T[1] * R[4] + T[2] * R[5] - mb * cw[0] * cw[1];
+    IO[2] += T[0] * R[6] + T[1] * R[7] + T[2] * R[8] - mb * cw[0] * cw[2];
+    IO[3] += T[3] * R[3] + T[4] * R[4] + T[5] * R[5] + mb * (c2 - cw[1] * cw[1]);
+    IO[4] += T[3] * R[6] + T[4] * R[7] + T[5] * R[8] - mb * cw[1] * cw[2];
+    IO[5] += T[6] * R[6] + T[7] * R[7] + T[8] * R[8] + mb * (c2 - cw[2] * cw[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) mc[i] += cw[i] * mb;
+  };
+  {
+    double r[3], cw[3];
+    rot_const(R0, &md.com[0], r);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cw[i] = p0[i] + r[i];
+    add_inertia(0, R0, cw);                       // the base is at rest: no momentum
+  }
+  for (int leg = 0; leg < 2; ++leg) {
+    double R[9], p[3], w[3] = {0, 0, 0}, vl[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = R0[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p[i] = p0[i];
+    for (int j = 0; j < 5; ++j) {
+      const int b = 1 + 5 * leg + j;
+      double d[3], wxd[3], a[3], sj, cj;
+      rot_const(R, &md.joint_xyz[3 * b], d);
+      cross(w, d, wxd);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { p[i] += d[i]; vl[i] += wxd[i]; }
+      sincos_t(x[11 + b], sj, cj);
+      joint_rotate_sc(R, md.joint_axis[b], sj, cj, a);
+      const double vb = u[11 + b];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) w[i] += a[i] * vb;
+      double r[3], wxr[3], vc[3], cw[3], l[3], wl[3], Iwl[3], Iw[3];
+      rot_const(R, &md.com[3 * b], r);
+      cross(w, r, wxr);
+      const double mb = md.mass[b];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { vc[i] = (vl[i] + wxr[i]) * mb; cw[i] = p[i] + r[i]; }
+      cross(cw, vc, l);
+      rotT(R, w, wl);
+      const double* I = &md.inertia[9 * b];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Iwl[i] = wl[0] * I[3 * i] + wl[1] * I[3 * i + 1] + wl[2] * I[3 * i + 2];
+      rot(R, Iwl, Iw);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { P[i] += vc[i]; Lo[i] += l[i] + Iw[i]; }
+      add_inertia(b, R, cw);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {  // toe (contact leg), heel (contact 2+leg)
+      const int c = leg + 2 * t;
+      double off[3], wxo[3];
+      rot_const(R, &md.contact_offset[3 * c], off);
+      cross(w, off, wxo);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { cp[3 * c + i] = p[i] + off[i]; cvj[3 * c + i] = vl[i] + wxo[i]; }
+    }
+  }
+  const double im = 1.0 / m;
+  double com[3], cxP[3], hj[6];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) com[i] = mc[i] * im;
+  cross(com, P, cxP);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { hj[i] = P[i]; hj[3 + i] = Lo[i] - cxP[i]; }
+  // inertia about the centre of mass
+  const double cc = com[0] * com[0] + com[1] * com[1] + com[2] * com[2];
+  const double Ic[9] = {IO[0] - m * (cc - com[0] * com[0]), IO[1] + m * com[0] * com[1], IO[2] + m * com[0] * com[2],
+                        IO[1] + m * com[0] * com[1], IO[3] - m * (cc - com[1] * com[1]), IO[4] + m * com[1] * com[2],
+                        IO[2] + m * com[0] * com[2], IO[4] + m * com[1] * com[2], IO[5] - m * (cc - com[2] * com[2])};
+  const double rb[3] = {com[0] - p0[0], com[1] - p0[1], com[2] - p0[2]};
+  double Ae[6][3];  // Euler-rate columns of A
+#pragma unroll
   for (int c = 0; c < 3; ++c) {
-    for (int i = 0; i < NQ; ++i) v[i] = (i == 3 + c) ? 1.0 : 0.0;
-    kin_pass<double>(q, v, o);
-    for (int r = 0; r < 6; ++r) Ae[r][c] = o.h[r];
+    const double* wc = &ax0[3 * c];
+    double wxr[3];
+    cross(wc, rb, wxr);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { Ae[i][c] = m * wxr[i]; Ae[3 + i][c] = Ic[3 * i] * wc[0] + Ic[3 * i + 1] * wc[1] + Ic[3 * i + 2] * wc[2]; }
   }
   double rl[3], ra[3];
   for (int i = 0; i < 3; ++i) { rl[i] = m * x[i] - hj[i]; ra[i] = m * x[3 + i] - hj[3 + i]; }
@@ -64,17 +162,23 @@ __device__ inline void flow_map_lane(const double* x, const double* u, double* f
   double vb[6];
   for (int i = 0; i < 3; ++i) { vb[i] = (rl[i] - Ae[i][0] * th[0] - Ae[i][1] * th[1] - Ae[i][2] * th[2]) / m; vb[3 + i] = th[i]; }
   if (evel) {
-    for (int i = 0; i < 6; ++i) v[i] = vb[i];
-    for (int j = 0; j < NJ; ++j) v[6 + j] = u[12 + j];
-    kin_pass<double>(q, v, o);
-    for (int i = 0; i < 12; ++i) evel[i] = o.cvel[i];
+    double W[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) W[i] = ax0[i] * th[0] + ax0[3 + i] * th[1] + ax0[6 + i] * th[2];
+#pragma unroll
+    for (int cc2 = 0; cc2 < NC; ++cc2) {
+      const double rr[3] = {cp[3 * cc2] - p0[0], cp[3 * cc2 + 1] - p0[1], cp[3 * cc2 + 2] - p0[2]};
+      double wxr[3];
+      cross(W, rr, wxr);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) evel[3 * cc2 + i] = cvj[3 * cc2 + i] + vb[i] + wxr[i];
+    }
   }
   if (epos) for (int i = 0; i < 12; ++i) epos[i] = cp[i];
-  const double im = 1.0 / m;
   double fl[3] = {0, 0, 0}, fa[3] = {0, 0, 0};
-  for (int cc = 0; cc < NC; ++cc) {
-    const double* F = u + 3 * cc;
-    const double r0 = cp[3 * cc] - com[0], r1 = cp[3 * cc + 1] - com[1], r2 = cp[3 * cc + 2] - com[2];
+  for (int cc2 = 0; cc2 < NC; ++cc2) {
+    const double* F = u + 3 * cc2;
+    const double r0 = cp[3 * cc2] - com[0], r1 = cp[3 * cc2 + 1] - com[1], r2 = cp[3 * cc2 + 2] - com[2];
     fl[0] += F[0]; fl[1] += F[1]; fl[2] += F[2];
     fa[0] += r1 * F[2] - r2 * F[1]; fa[1] += r2 * F[0] - r0 * F[2]; fa[2] += r0 * F[1] - r1 * F[0];
   }
