@@ -766,6 +766,32 @@ __global__ void reference_unpack_kernel(int B, const long long* offs, const doub
   }
 }
 
+// The same copy without the host pass: when the caller's hb_reference array is pinned (cudaHostAlloc / cudaHostRegister) the block reads the
+// USED entries straight out of host memory through the mapped alias (zero-copy), so no host core packs and only the used bytes cross PCIe.
+__global__ void reference_gather_pinned_kernel(int B, const hb_reference* __restrict__ src, hb_reference* refs) {
+  const int inst = blockIdx.x;
+  if (inst >= B) return;
+  const hb_reference& h = src[inst];
+  hb_reference& r = refs[inst];
+  __shared__ int cnt[14];
+  if (threadIdx.x == 0) cnt[0] = min(max(h.n_events, 0), HB_MAX_EVENTS);
+  if (threadIdx.x == 1) cnt[1] = min(max(h.n_targets, 0), HB_MAX_TARGETS);
+  if (threadIdx.x >= 2 && threadIdx.x < 14) { const int q = threadIdx.x - 2; cnt[threadIdx.x] = min(max(h.n_segments[q / 3][q % 3], 0), HB_MAX_SEGMENTS); }
+  __syncthreads();
+  const int ne = cnt[0], nt = cnt[1];
+  if (threadIdx.x == 0) { r.n_events = ne; r.n_targets = nt; }
+  if (threadIdx.x >= 2 && threadIdx.x < 14) { const int q = threadIdx.x - 2; r.n_segments[q / 3][q % 3] = cnt[threadIdx.x]; }
+  for (int i = threadIdx.x; i < ne; i += blockDim.x) r.event_times[i] = h.event_times[i];
+  for (int i = threadIdx.x; i <= ne; i += blockDim.x) r.modes[i] = h.modes[i];
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) r.target_times[i] = h.target_times[i];
+  for (int i = threadIdx.x; i < nt * 22; i += blockDim.x) r.target_states[i / 22][i % 22] = h.target_states[i / 22][i % 22];
+  // the twelve (foot, axis) segment lists in one flattened loop: all loads of the block are in flight together (PCIe round trips overlap)
+  for (int i = threadIdx.x; i < 12 * HB_MAX_SEGMENTS * 6; i += blockDim.x) {
+    const int q = i / (HB_MAX_SEGMENTS * 6), e = i - q * (HB_MAX_SEGMENTS * 6);
+    if (e < cnt[2 + q] * 6) (&r.segments[q / 3][q % 3][0][0])[e] = (&h.segments[q / 3][q % 3][0][0])[e];
+  }
+}
+
 // Time discretisation with event nodes (row S1; ocs2::timeDiscretizationWithEvents as SqpSolver::run calls it): nodes step by dt from the
 // initial time; a step that would pass a mode-switch time lands on it instead (the pre-event interval is shortened) and the grid
 // re-anchors there; the last node is the final time; nodes closer than dt_min to their predecessor replace it. OCS2's duplicated
@@ -2204,7 +2230,14 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
   // forward pass, WBC: one wave each) run no faster than the full batch, so one chunk wins (124 k vs 113 k solves/s at 1024); from 4096 on
   // two chunks hide the copies behind the other chunk's kernels (133 k vs 121 k at 8192).
   const int nchunk = ctx->cfg.e2e_chunks > 0 ? ((B >= 64 * ctx->cfg.e2e_chunks) ? ctx->cfg.e2e_chunks : 1) : ((B >= 4096) ? 2 : 1);
+  // a pinned (page-locked, mapped) reference array is read by the device directly
+  const hb_reference* refs_dev = nullptr;
   {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, refs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) refs_dev = static_cast<const hb_reference*>(at.devicePointer);
+    else cudaGetLastError();
+  }
+  if (!refs_dev) {
     size_t need = 0;
     for (int i = 0; i < B; ++i) need += ref_pack_words(refs[i]);
     need += (size_t)B + 2 * (size_t)nchunk + 8;
@@ -2233,7 +2266,17 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
     auto d2h = [&](void* h, const void* d, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream); };
     h2d(ctx->s_t0 + lo, t0 + lo, sizeof(double) * n);
     h2d(ctx->s_x0 + lo * NX, x0 + lo * NX, sizeof(double) * n * NX);
-    {
+    if (refs_dev) {
+      // pinned caller array: the device gathers the used entries itself (no host pass, no staging copy)
+      if (e == cudaSuccess) {
+        reference_gather_pinned_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((int)n, refs_dev + lo, ctx->s_refs + lo);
+        ctx->launches++;
+        e = cudaGetLastError();
+      }
+      size_t words = 0;
+      for (size_t i = lo; i < hi; ++i) words += ref_pack_words(refs[i]) - 8 + 7;     // counts (14 x int32) + used entries
+      ctx->last_h2d_bytes += sizeof(double) * words;
+    } else {
       // references: only the used entries cross PCIe (packed into the context's pinned staging area, unpacked into s_refs on the device)
       const size_t words = ref_pack(refs, lo, hi, ctx->h_pack + pack_base);
       h2d(ctx->d_pack + pack_base, ctx->h_pack + pack_base, sizeof(double) * words);

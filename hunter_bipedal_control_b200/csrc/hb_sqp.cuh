@@ -978,7 +978,7 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
       for (int j = 0; j < NTP; ++j) {
         double d = __shfl_sync(HB_FULL_MASK, a[j], j);
         if (!(d > 0.0)) { fail = true; d = 1.0; }
-        const double r = 1.0 / sqrt(d);
+        const double r = rsqrt(d);
         rinv[j] = r;
         const double l = a[j] * r;              // L[i][j] on lane i >= j
         a[j] = l;

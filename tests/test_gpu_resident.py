@@ -162,3 +162,28 @@ def test_snapshot_write_back_resumes_bit_identically():
             hb.Context(**kw).resident_cycle(False, 0.002, np.zeros(B), x0, refs, rbd)      # nothing to shift in a fresh context
         for cx in (a, b, c):
             cx.close()
+
+
+def test_pinned_reference_array_is_gathered_by_the_device():
+    """A page-locked hb_reference array is read by the device directly (zero-copy gather of the used entries, no host packing pass);
+    a pageable one goes through the packed staging upload. Same results bit for bit, one chunk and two chunks."""
+    import ctypes as C
+    import torch
+    ctx = hb.Context(horizon_N=N, dt=DT, max_batch=512, device=0, e2e_chunks=2)
+    for B in (9, 300):
+        x0, refs, rbd = _setup(B, seed=77)
+        t0 = np.full(B, 0.004)
+        a = ctx.resident_cycle(True, 0.002, t0, x0, refs, rbd)                        # ctypes array: pageable
+        up_pageable = ctx.last_reference_upload_bytes
+        _, xa, ua = ctx.resident_read(B)
+        nbytes = C.sizeof(refs)
+        pinned = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        C.memmove(pinned.data_ptr(), C.addressof(refs), nbytes)
+        b = ctx.resident_cycle(True, 0.002, t0, x0, C.cast(C.c_void_p(pinned.data_ptr()), C.POINTER(hb.HbReference)), rbd)
+        up_pinned = ctx.last_reference_upload_bytes
+        _, xb, ub = ctx.resident_read(B)
+        assert np.array_equal(xa, xb) and np.array_equal(ua, ub)
+        for p, q in zip(a, b):
+            assert np.array_equal(p, q)
+        assert 0 < up_pinned <= up_pageable < nbytes                                   # only used entries cross PCIe either way
+    ctx.close()
