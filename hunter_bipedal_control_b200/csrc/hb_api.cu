@@ -768,27 +768,56 @@ __global__ void reference_unpack_kernel(int B, const long long* offs, const doub
 
 // The same copy without the host pass: when the caller's hb_reference array is pinned (cudaHostAlloc / cudaHostRegister) the block reads the
 // USED entries straight out of host memory through the mapped alias (zero-copy), so no host core packs and only the used bytes cross PCIe.
-__global__ void reference_gather_pinned_kernel(int B, const hb_reference* __restrict__ src, hb_reference* refs) {
+__global__ void reference_gather_pinned_kernel(int B, const hb_reference* __restrict__ src, hb_reference* refs, unsigned long long* stat) {
   const int inst = blockIdx.x;
   if (inst >= B) return;
   const hb_reference& h = src[inst];
   hb_reference& r = refs[inst];
   __shared__ int cnt[14];
-  if (threadIdx.x == 0) cnt[0] = min(max(h.n_events, 0), HB_MAX_EVENTS);
-  if (threadIdx.x == 1) cnt[1] = min(max(h.n_targets, 0), HB_MAX_TARGETS);
-  if (threadIdx.x >= 2 && threadIdx.x < 14) { const int q = threadIdx.x - 2; cnt[threadIdx.x] = min(max(h.n_segments[q / 3][q % 3], 0), HB_MAX_SEGMENTS); }
+  __shared__ int bad;
+  if (threadIdx.x == 0) { bad = 0; cnt[0] = min(max(h.n_events, 0), HB_MAX_EVENTS); if (cnt[0] != h.n_events) bad = 1; }
+  __syncthreads();
+  if (threadIdx.x == 1) { const int nt = h.n_targets; cnt[1] = min(max(nt, 0), HB_MAX_TARGETS); if (nt < 1 || nt > HB_MAX_TARGETS) bad = 1; }
+  if (threadIdx.x >= 2 && threadIdx.x < 14) {
+    const int q = threadIdx.x - 2, ns = h.n_segments[q / 3][q % 3];
+    cnt[threadIdx.x] = min(max(ns, 0), HB_MAX_SEGMENTS);
+    if (ns < 0 || ns > HB_MAX_SEGMENTS) bad = 1;
+  }
   __syncthreads();
   const int ne = cnt[0], nt = cnt[1];
   if (threadIdx.x == 0) { r.n_events = ne; r.n_targets = nt; }
   if (threadIdx.x >= 2 && threadIdx.x < 14) { const int q = threadIdx.x - 2; r.n_segments[q / 3][q % 3] = cnt[threadIdx.x]; }
-  for (int i = threadIdx.x; i < ne; i += blockDim.x) r.event_times[i] = h.event_times[i];
-  for (int i = threadIdx.x; i <= ne; i += blockDim.x) r.modes[i] = h.modes[i];
-  for (int i = threadIdx.x; i < nt; i += blockDim.x) r.target_times[i] = h.target_times[i];
+  // the checks of references_valid() ride on the copy: the values are in registers anyway
+  bool ok = true;
+  for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+    const double t = h.event_times[i];
+    r.event_times[i] = t;
+    if (!(t == t) || (i > 0 && t < h.event_times[i - 1])) ok = false;
+  }
+  for (int i = threadIdx.x; i <= ne; i += blockDim.x) { const int32_t m = h.modes[i]; r.modes[i] = m; if (m < 0 || m > 3) ok = false; }
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+    const double t = h.target_times[i];
+    r.target_times[i] = t;
+    if (!(t == t) || (i > 0 && !(t > h.target_times[i - 1]))) ok = false;
+  }
   for (int i = threadIdx.x; i < nt * 22; i += blockDim.x) r.target_states[i / 22][i % 22] = h.target_states[i / 22][i % 22];
   // the twelve (foot, axis) segment lists in one flattened loop: all loads of the block are in flight together (PCIe round trips overlap)
   for (int i = threadIdx.x; i < 12 * HB_MAX_SEGMENTS * 6; i += blockDim.x) {
     const int q = i / (HB_MAX_SEGMENTS * 6), e = i - q * (HB_MAX_SEGMENTS * 6);
-    if (e < cnt[2 + q] * 6) (&r.segments[q / 3][q % 3][0][0])[e] = (&h.segments[q / 3][q % 3][0][0])[e];
+    if (e < cnt[2 + q] * 6) {
+      const double* sp = &h.segments[q / 3][q % 3][0][0];
+      const double v = sp[e];
+      (&r.segments[q / 3][q % 3][0][0])[e] = v;
+      if (e % 6 == 1 && !(v > sp[e - 1])) ok = false;       // segment end time after its start time
+    }
+  }
+  if (!ok) bad = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (bad) atomicAdd(stat, 1ull);
+    int words = 7 + ne + (ne + 2) / 2 + 23 * nt;
+    for (int q = 0; q < 12; ++q) words += 6 * cnt[2 + q];
+    atomicAdd(stat + 1, (unsigned long long)words);
   }
 }
 
@@ -1015,6 +1044,7 @@ struct hb_ctx {
   double *s_x0, *s_xref, *s_swing, *s_xt, *s_ut, *s_rbd, *s_xd, *s_ud, *s_sol, *s_tau, *s_t0, *s_misc;
   double *res_xt = nullptr, *res_ut = nullptr, *res_t0 = nullptr;   // resident primal solution (hb_resident_cycle_batch)
   double *s_tk = nullptr, *res_tk = nullptr; int32_t *s_nn = nullptr, *res_nn = nullptr;   // node times / interval counts (event-node grids)
+  unsigned long long* h_refstat = nullptr; unsigned long long* d_refstat = nullptr; int refstat_cap = 0;   // per chunk: {invalid structs, words read} of the pinned gather
   double* h_pack = nullptr; double* d_pack = nullptr; size_t pack_cap = 0;   // packed reference stream: pinned host staging + device copy (words)
   double* hoqp_scratch = nullptr; hb_hoqp_problem* hoqp_prob = nullptr;   // hierarchical WBC (allocated by its first call)
   int32_t* res_mode = nullptr;                                      // node modes of the resident solution (policy evaluation between MPC solves)
@@ -1202,6 +1232,8 @@ int hb_destroy(hb_ctx* ctx) {
                   ctx->s_info, ctx->s_refs, ctx->s_qpH, ctx->s_qpA, ctx->res_xt, ctx->res_ut, ctx->res_t0, ctx->s_plan, ctx->res_stance, ctx->s_pstatus, ctx->s_kf, ctx->res_sol, ctx->s_tk, ctx->res_tk, ctx->s_nn, ctx->res_nn, ctx->res_mode, ctx->hoqp_scratch, ctx->hoqp_prob};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->prof_ev) { for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(ctx->prof_ev[i]); delete[] ctx->prof_ev; delete[] ctx->prof_kind; }
+  if (ctx->h_refstat) cudaFreeHost(ctx->h_refstat);
+  if (ctx->d_refstat) cudaFree(ctx->d_refstat);
   if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
   if (ctx->d_pack) cudaFree(ctx->d_pack);
   if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
@@ -2223,7 +2255,6 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
   if (B == 0) return HB_OK;
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (!cold_start && ctx->res_valid < B) return HB_EINVAL;
-  if (!references_valid(B, refs)) return HB_EINVAL;
   if (set_device(ctx)) return HB_ECUDA;
   // Half-batches on two streams, as in hb_control_step_batch; only the small per-instance inputs and results cross PCIe.
   // Automatic choice (measured, profiles/r02_e2e_chunks.txt): below ~4096 instances the half-batch kernels of the sequential stages (Riccati,
@@ -2237,7 +2268,22 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
     if (cudaPointerGetAttributes(&at, refs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) refs_dev = static_cast<const hb_reference*>(at.devicePointer);
     else cudaGetLastError();
   }
-  if (!refs_dev) {
+  if (refs_dev) {
+    // validation and byte count happen on the device while it copies (no per-instance host work at all); the verdict comes back with the results
+    if (ctx->refstat_cap < 2 * nchunk) {
+      if (ctx->h_refstat) cudaFreeHost(ctx->h_refstat);
+      if (ctx->d_refstat) cudaFree(ctx->d_refstat);
+      ctx->h_refstat = nullptr; ctx->d_refstat = nullptr; ctx->refstat_cap = 0;
+      if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_refstat), sizeof(unsigned long long) * 2 * nchunk, cudaHostAllocDefault) != cudaSuccess ||
+          cudaMalloc(reinterpret_cast<void**>(&ctx->d_refstat), sizeof(unsigned long long) * 2 * nchunk) != cudaSuccess) {
+        cudaGetLastError();
+        if (ctx->h_refstat) { cudaFreeHost(ctx->h_refstat); ctx->h_refstat = nullptr; }
+        return HB_ENOMEM;
+      }
+      ctx->refstat_cap = 2 * nchunk;
+    }
+  } else {
+    if (!references_valid(B, refs)) return HB_EINVAL;
     size_t need = 0;
     for (int i = 0; i < B; ++i) need += ref_pack_words(refs[i]);
     need += (size_t)B + 2 * (size_t)nchunk + 8;
@@ -2268,14 +2314,13 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
     h2d(ctx->s_x0 + lo * NX, x0 + lo * NX, sizeof(double) * n * NX);
     if (refs_dev) {
       // pinned caller array: the device gathers the used entries itself (no host pass, no staging copy)
+      if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_refstat + 2 * c, 0, 2 * sizeof(unsigned long long), ctx->stream);
       if (e == cudaSuccess) {
-        reference_gather_pinned_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((int)n, refs_dev + lo, ctx->s_refs + lo);
+        reference_gather_pinned_kernel<<<(unsigned)n, 128, 0, ctx->stream>>>((int)n, refs_dev + lo, ctx->s_refs + lo, ctx->d_refstat + 2 * c);
         ctx->launches++;
         e = cudaGetLastError();
       }
-      size_t words = 0;
-      for (size_t i = lo; i < hi; ++i) words += ref_pack_words(refs[i]) - 8 + 7;     // counts (14 x int32) + used entries
-      ctx->last_h2d_bytes += sizeof(double) * words;
+      d2h(ctx->h_refstat + 2 * c, ctx->d_refstat + 2 * c, 2 * sizeof(unsigned long long));
     } else {
       // references: only the used entries cross PCIe (packed into the context's pinned staging area, unpacked into s_refs on the device)
       const size_t words = ref_pack(refs, lo, hi, ctx->h_pack + pack_base);
@@ -2305,6 +2350,12 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
   cudaError_t e1 = cudaStreamSynchronize(ctx->stream_aux), e0 = cudaStreamSynchronize(ctx->stream_main);
   if (rc) return rc;
   if (e0 != cudaSuccess || e1 != cudaSuccess) { ctx->last_cuda = (int)(e0 != cudaSuccess ? e0 : e1); return HB_ECUDA; }
+  if (refs_dev) {
+    unsigned long long invalid = 0, words = 0;
+    for (int c = 0; c < nchunk; ++c) { invalid += ctx->h_refstat[2 * c]; words += ctx->h_refstat[2 * c + 1]; }
+    ctx->last_h2d_bytes = sizeof(double) * (size_t)words;
+    if (invalid) { ctx->res_valid = 0; return HB_EINVAL; }      // malformed structs: counts were clamped on the device, the outputs are not meaningful
+  }
   return HB_OK;
 }
 

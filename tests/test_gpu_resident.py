@@ -187,3 +187,42 @@ def test_pinned_reference_array_is_gathered_by_the_device():
             assert np.array_equal(p, q)
         assert 0 < up_pinned <= up_pageable < nbytes                                   # only used entries cross PCIe either way
     ctx.close()
+
+
+def test_malformed_references_are_rejected_on_both_upload_paths():
+    """hb_reference structs with counts beyond their capacity, unordered times or an empty target list are refused (-1) whether the host
+    validates them (pageable array) or the device does while it gathers them (pinned array); nothing is indexed out of bounds."""
+    import ctypes as C
+    import torch
+    B = 12
+    ctx = hb.Context(horizon_N=N, dt=DT, max_batch=64, device=0)
+    x0, refs, rbd = _setup(B, seed=5)
+    t0 = np.zeros(B)
+
+    def corrupt(kind):
+        bad = (hb.HbReference * B)()
+        C.memmove(C.addressof(bad), C.addressof(refs), C.sizeof(refs))
+        if kind == "events":
+            bad[3].n_events = 4000
+        elif kind == "targets":
+            bad[7].n_targets = 0
+        elif kind == "segments":
+            bad[5].n_segments[1][2] = -3
+        elif kind == "order":
+            bad[2].target_times[1] = bad[2].target_times[0] - 1.0
+        elif kind == "mode":
+            bad[9].modes[0] = 7
+        return bad
+
+    for kind in ("events", "targets", "segments", "order", "mode"):
+        bad = corrupt(kind)
+        with pytest.raises(hb.HunterB200Error, match="invalid argument"):
+            ctx.resident_cycle(True, 0.002, t0, x0, bad, rbd)
+        pinned = torch.empty(C.sizeof(bad), dtype=torch.uint8).pin_memory()
+        C.memmove(pinned.data_ptr(), C.addressof(bad), C.sizeof(bad))
+        with pytest.raises(hb.HunterB200Error, match="invalid argument"):
+            ctx.resident_cycle(True, 0.002, t0, x0, C.cast(C.c_void_p(pinned.data_ptr()), C.POINTER(hb.HbReference)), rbd)
+    # the context is still usable afterwards
+    info, sol, tau, st = ctx.resident_cycle(True, 0.002, t0, x0, refs, rbd)
+    assert (info["status"] == 0).all() and np.isfinite(tau).all()
+    ctx.close()
