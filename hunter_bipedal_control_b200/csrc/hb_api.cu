@@ -2256,11 +2256,6 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
   if (B > ctx->cfg.max_batch) return HB_ECAP;
   if (!cold_start && ctx->res_valid < B) return HB_EINVAL;
   if (set_device(ctx)) return HB_ECUDA;
-  // Half-batches on two streams, as in hb_control_step_batch; only the small per-instance inputs and results cross PCIe.
-  // Automatic choice (measured, profiles/r02_e2e_chunks.txt): below ~4096 instances the half-batch kernels of the sequential stages (Riccati,
-  // forward pass, WBC: one wave each) run no faster than the full batch, so one chunk wins (124 k vs 113 k solves/s at 1024); from 4096 on
-  // two chunks hide the copies behind the other chunk's kernels (133 k vs 121 k at 8192).
-  const int nchunk = ctx->cfg.e2e_chunks > 0 ? ((B >= 64 * ctx->cfg.e2e_chunks) ? ctx->cfg.e2e_chunks : 1) : ((B >= 4096) ? 2 : 1);
   // a pinned (page-locked, mapped) reference array is read by the device directly
   const hb_reference* refs_dev = nullptr;
   {
@@ -2268,6 +2263,12 @@ int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, co
     if (cudaPointerGetAttributes(&at, refs) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) refs_dev = static_cast<const hb_reference*>(at.devicePointer);
     else cudaGetLastError();
   }
+  // Chunks on two streams, as in hb_control_step_batch; only the small per-instance inputs and results cross PCIe.
+  // Automatic choice (measured, profiles/r02_e2e_chunks.txt): with a pageable reference array the host packs the used entries (0.5 ms per 1024
+  // instances), and from 4096 instances on two chunks hide that pass and the copies behind the other chunk's kernels (133 k vs 121 k solves/s
+  // at 8192; below, the half-batch kernels of the sequential stages run no faster than the full batch: 124 k vs 113 k at 1024). With a pinned
+  // array there is no host pass to hide and one chunk wins at every size (158.7 k vs 150.6 k at 8192).
+  const int nchunk = ctx->cfg.e2e_chunks > 0 ? ((B >= 64 * ctx->cfg.e2e_chunks) ? ctx->cfg.e2e_chunks : 1) : ((!refs_dev && B >= 4096) ? 2 : 1);
   if (refs_dev) {
     // validation and byte count happen on the device while it copies (no per-instance host work at all); the verdict comes back with the results
     if (ctx->refstat_cap < 2 * nchunk) {
