@@ -416,36 +416,18 @@ __device__ void rnea_pass(const double* q, const double* v, const double* a, boo
   }
 }
 
-// Solve the 6x6 system M y = r (M row-major, ld 6) by Gaussian elimination with partial pivoting, per lane in registers.
-__device__ inline void solve6(const double* Min, const double* rin, double* y) {
-  double M[6][7];
-  for (int i = 0; i < 6; ++i) { for (int j = 0; j < 6; ++j) M[i][j] = Min[6 * i + j]; M[i][6] = rin[i]; }
+// Solve A_b y = r for the base block of the centroidal momentum matrix (row-major, ld 6). A_b = [m I, A12; 0, A22]
+// (computeFloatingBaseCentroidalMomentumMatrixInverse uses the same structure): one 3x3 adjugate and one division instead of a pivoted
+// 6x6 elimination with twelve divisions on the dependent chain (15.8 % of lin_kernel's stall samples in round 1's form).
+__device__ __forceinline__ void solve6_cmm(const double* A, const double* r, double* y) {
+  const double a = A[21], b = A[22], c = A[23], d = A[27], e = A[28], g = A[29], h = A[33], k = A[34], l = A[35];
+  const double c00 = e * l - g * k, c01 = d * l - g * h, c02 = d * k - e * h;
+  const double id = 1.0 / (a * c00 - b * c01 + c * c02);
+  y[3] = (c00 * r[3] - (b * l - c * k) * r[4] + (b * g - c * e) * r[5]) * id;
+  y[4] = (-c01 * r[3] + (a * l - c * h) * r[4] - (a * g - c * d) * r[5]) * id;
+  y[5] = (c02 * r[3] - (a * k - b * h) * r[4] + (a * e - b * d) * r[5]) * id;
 #pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    int p = c; double best = fabs(M[c][c]);
-#pragma unroll
-    for (int r = c + 1; r < 6; ++r) { const double a = fabs(M[r][c]); if (a > best) { best = a; p = r; } }
-#pragma unroll
-    for (int r = c + 1; r < 6; ++r)
-      if (r == p) {
-#pragma unroll
-        for (int j = 0; j < 7; ++j) { const double t = M[c][j]; M[c][j] = M[r][j]; M[r][j] = t; }
-      }
-    const double inv = 1.0 / M[c][c];
-#pragma unroll
-    for (int r = c + 1; r < 6; ++r) {
-      const double f = M[r][c] * inv;
-#pragma unroll
-      for (int j = c; j < 7; ++j) M[r][j] -= f * M[c][j];
-    }
-  }
-#pragma unroll
-  for (int r = 5; r >= 0; --r) {
-    double s = M[r][6];
-#pragma unroll
-    for (int j = r + 1; j < 6; ++j) s -= M[r][j] * y[j];
-    y[r] = s / M[r][r];
-  }
+  for (int i = 0; i < 3; ++i) y[i] = (r[i] - A[6 * i + 3] * y[3] - A[6 * i + 4] * y[4] - A[6 * i + 5] * y[5]) / A[7 * i];
 }
 
 }  // namespace hb

@@ -123,7 +123,7 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const d
 #pragma unroll
       for (int r = 0; r < 6; ++r) { double s = m * xs[r]; for (int j = 0; j < NJ; ++j) s -= sh.Acm[r * 16 + 6 + j] * sh.u[12 + j]; rhs[r] = s; }
     }
-    solve6(Ab, rhs, y);
+    solve6_cmm(Ab, rhs, y);
     if (hl < 6) {
 #pragma unroll
       for (int r = 0; r < 6; ++r) sh.Abinv[6 * r + hl] = y[r];
@@ -246,15 +246,33 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const d
   }
   if (want_ee) {
     if (hl < 12) { rec[LIN_EPOS + hl] = sh.epos[hl]; rec[LIN_EVEL + hl] = sh.evel[hl]; }
-    for (int j = hl; j < NX; j += 16) {
-      for (int r = 0; r < 12; ++r) {
-        double vx = 0.0;
-        if (j < 6) { for (int c = 0; c < 6; ++c) vx += sh.Jc[r * 16 + c] * sh.Abinv[6 * c + j]; vx *= m; }
-        else if (j >= 9) { const int k = j - 9; vx = sh.dv[r * NDIR + k]; for (int c = 0; c < 6; ++c) vx += sh.Jc[r * 16 + c] * sh.dvb[c * NDIR + k]; rec[LIN_DPQ + r * NDIR + k] = sh.dp[r * NDIR + k]; }
-        rec[LIN_DVX + r * NX + j] = vx;
-        if (j >= 12) { const int jj = j - 12; double vu = sh.Jc[r * 16 + 6 + jj]; for (int c = 0; c < 6; ++c) vu -= sh.Jc[r * 16 + c] * sh.AbinvAj[c * NJ + jj]; rec[LIN_DVV + r * NJ + jj] = vu; }
+    // 29 equal work items (12 rows x one 6-term product each) over the 16 lanes of the node: state columns 0..5 (momentum), 9..21
+    // (orientation + joints; the position columns 6..8 are zero) and the ten joint-velocity columns; two rounds, every lane busy in both
+    for (int t = hl; t < 29; t += 16) {
+      if (t < 6) {
+        for (int r = 0; r < 12; ++r) {
+          double vx = 0.0;
+          for (int c = 0; c < 6; ++c) vx += sh.Jc[r * 16 + c] * sh.Abinv[6 * c + t];
+          rec[LIN_DVX + r * NX + t] = vx * m;
+        }
+      } else if (t < 19) {
+        const int k = t - 6, j = 9 + k;
+        for (int r = 0; r < 12; ++r) {
+          double vx = sh.dv[r * NDIR + k];
+          for (int c = 0; c < 6; ++c) vx += sh.Jc[r * 16 + c] * sh.dvb[c * NDIR + k];
+          rec[LIN_DPQ + r * NDIR + k] = sh.dp[r * NDIR + k];
+          rec[LIN_DVX + r * NX + j] = vx;
+        }
+      } else {
+        const int jj = t - 19;
+        for (int r = 0; r < 12; ++r) {
+          double vu = sh.Jc[r * 16 + 6 + jj];
+          for (int c = 0; c < 6; ++c) vu -= sh.Jc[r * 16 + c] * sh.AbinvAj[c * NJ + jj];
+          rec[LIN_DVV + r * NJ + jj] = vu;
+        }
       }
     }
+    if (hl < 12) { rec[LIN_DVX + hl * NX + 6] = 0.0; rec[LIN_DVX + hl * NX + 7] = 0.0; rec[LIN_DVX + hl * NX + 8] = 0.0; }
   }
 }
 

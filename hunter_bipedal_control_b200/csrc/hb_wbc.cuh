@@ -83,7 +83,7 @@ __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const 
       for (int j = 0; j < NJ; ++j) s -= sh.Ad[r * 16 + 6 + j] * u_des[12 + j];
       rhs[r] = s;
     }
-    solve6(Ab, rhs, vb);
+    solve6_cmm(Ab, rhs, vb);
     for (int i = 0; i < 6; ++i) sh.vd[i] = vb[i];
     for (int j = 0; j < NJ; ++j) sh.vd[6 + j] = u_des[12 + j];
   }
@@ -144,7 +144,7 @@ __device__ inline int wbc_assemble_warp(const double* __restrict__ x_des, const 
       hd[2] -= md.total_mass * HB_GRAVITY;
       double Ab[36], rhs[6], qbdd[6];
       for (int r = 0; r < 6; ++r) { for (int c = 0; c < 6; ++c) Ab[6 * r + c] = sh.Ad[r * 16 + c]; rhs[r] = hd[r] - sh.Adv[r]; }
-      solve6(Ab, rhs, qbdd);
+      solve6_cmm(Ab, rhs, qbdd);
       // euler axes at the plan and at the measurement
       double Rd[9], axd[9], Rm[9], axm[9];
       base_frame<double>(sh.qd, Rd, axd);
