@@ -1183,6 +1183,18 @@ int hb_create(const hb_config* cfg, int device, hb_ctx** out) {
       cudaFree(dR);
     }
   }
+  if (e == cudaSuccess) {
+    double tab[32 * LQ_LANE_TAB] = {};
+    for (int l = 0; l < 32; ++l) {
+      double* t = tab + l * LQ_LANE_TAB;
+      if (l < NX) t[0] = m->Q[l];
+      if (l < 12) t[1] = m->R[l * NU + l];
+      if (l >= 12 && l < NU) for (int j = 0; j < NJ; ++j) t[2 + j] = m->R[l * NU + 12 + j];
+      if (l < 10) { t[12] = m->joint_lower[l]; t[13] = m->joint_upper[l]; }
+      else if (l < 20) { t[12] = -m->joint_vel_limit[l - 10]; t[13] = m->joint_vel_limit[l - 10]; }
+    }
+    e = cudaMemcpyToSymbol(g_lq_lane, tab, sizeof(tab));
+  }
   delete m;
   if (e != cudaSuccess) { ctx->last_cuda = (int)e; hb_destroy(ctx); return HB_ECUDA; }
   const size_t B = cfg->max_batch, N = cfg->horizon_N;

@@ -28,6 +28,11 @@ struct Model {
 };
 
 __constant__ Model c_model;  // single translation unit (hb_api.cu)
+// Per-lane constants of lq_kernel in GLOBAL memory (16 doubles per lane): a constant-memory operand indexed by the lane serialises into one
+// fetch per distinct address (22 for Q[lane], 10 x 10 for the velocity block of R), a global load of the same table is one L1 hit.
+// [0] Q[l]; [1] R[l][l] (l < 12); [2..11] R[l][12..21] (12 <= l < 22); [12], [13] bounds of the lane's limit penalty (l < 20).
+constexpr int LQ_LANE_TAB = 16;
+__device__ double g_lq_lane[32 * LQ_LANE_TAB];
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ double warp_sum(double v) {

@@ -468,18 +468,20 @@ __device__ __forceinline__ void lq_node(LqShared& sh, const SqpArgs& a, int inst
     }
   }
   // ---- cost (M2, M6, M8), scaled by dt at the end
+  const double* __restrict__ ltab = g_lq_lane + lane * LQ_LANE_TAB;     // this lane's constants (global memory: see hb_common.cuh)
   const double fz = (NSW < 4) ? md.total_mass * HB_GRAVITY / (4 - NSW) : 0.0;
   double cost = 0.0;
   if (lane < NX) {
     const double d = sh.x[lane] - xref_l;
-    sh.q[lane] = md.Q[lane] * d;
-    sh.Qd[lane] = md.Q[lane];
-    cost += 0.5 * md.Q[lane] * d * d;
+    const double Ql = ltab[0];
+    sh.q[lane] = Ql * d;
+    sh.Qd[lane] = Ql;
+    cost += 0.5 * Ql * d * d;
     double s = 0.0;
-    if (lane < 12) { double dul = sh.u[lane]; if ((lane % 3) == 2 && ((flm >> (lane / 3)) & 1u)) dul -= fz; s = md.R[lane * NU + lane] * dul; cost += 0.5 * dul * s; }
+    if (lane < 12) { double dul = sh.u[lane]; if ((lane % 3) == 2 && ((flm >> (lane / 3)) & 1u)) dul -= fz; s = ltab[1] * dul; cost += 0.5 * dul * s; }
     else {
 #pragma unroll
-      for (int j = 12; j < NU; ++j) s = fma(md.R[lane * NU + j], sh.u[j], s);
+      for (int j = 0; j < NJ; ++j) s = fma(ltab[2 + j], sh.u[12 + j], s);
       cost += 0.5 * sh.u[lane] * s;
     }
     sh.r[lane] = s;
@@ -489,7 +491,7 @@ __device__ __forceinline__ void lq_node(LqShared& sh, const SqpArgs& a, int inst
     sh.RFF[c * 9 + ax * 3] = 0.0; sh.RFF[c * 9 + ax * 3 + 1] = 0.0; sh.RFF[c * 9 + ax * 3 + 2] = 0.0;
   }
   __syncwarp();
-  if (lane < 12) { const int c = lane / 3, ax = lane - 3 * c; sh.RFF[c * 9 + ax * 4] = md.R[lane * NU + lane]; }
+  if (lane < 12) { const int c = lane / 3, ax = lane - 3 * c; sh.RFF[c * 9 + ax * 4] = ltab[1]; }
   // all scalar penalties in ONE pass: lanes 0-9 joint position limits, 10-19 joint velocity limits, 20-23 normal-force limits
   // (double sided), 24-27 friction cones of stance contacts (one sided)
   double shiftsum = 0.0;
@@ -497,8 +499,8 @@ __device__ __forceinline__ void lq_node(LqShared& sh, const SqpArgs& a, int inst
     double h = 1.0, lo = 0.0, hi = 2.0, pmu = 0.0, pdl = 1.0;
     bool two = true, on = false;
     double Fx = 0.0, Fy = 0.0, tn = 1.0, t2 = 1.0;
-    if (lane < 10) { h = sh.x[12 + lane]; lo = md.joint_lower[lane]; hi = md.joint_upper[lane]; pmu = HB_LIMIT_POS_MU; pdl = HB_LIMIT_POS_DELTA; on = true; }
-    else if (lane < 20) { const int j = lane - 10; h = sh.u[12 + j]; lo = -md.joint_vel_limit[j]; hi = md.joint_vel_limit[j]; pmu = HB_LIMIT_VEL_MU; pdl = HB_LIMIT_VEL_DELTA; on = true; }
+    if (lane < 10) { h = sh.x[12 + lane]; lo = ltab[12]; hi = ltab[13]; pmu = HB_LIMIT_POS_MU; pdl = HB_LIMIT_POS_DELTA; on = true; }
+    else if (lane < 20) { const int j = lane - 10; h = sh.u[12 + j]; lo = ltab[12]; hi = ltab[13]; pmu = HB_LIMIT_VEL_MU; pdl = HB_LIMIT_VEL_DELTA; on = true; }
     else if (lane < 24) { const int c = lane - 20; h = sh.u[3 * c + 2]; lo = 0.0; hi = HB_LIMIT_FORCE_MAX; pmu = HB_LIMIT_FORCE_MU; pdl = HB_LIMIT_FORCE_DELTA; on = true; }
     else if (lane < 28) {
       const int c = lane - 24;
