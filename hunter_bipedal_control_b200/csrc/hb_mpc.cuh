@@ -188,6 +188,18 @@ __device__ inline void flow_map_lane(const double* x, const double* u, double* f
   for (int j = 0; j < NJ; ++j) f[12 + j] = u[12 + j];
 }
 
+// Value of a sum of relaxed log barriers that share (mu, delta): -mu sum log(h_i) over the arguments above delta is -mu log(prod h_i) -- ONE
+// logarithm per group instead of one per constraint (52 per node in the line search); arguments at or below delta take the quadratic
+// extension term by term. The products stay far inside the double range (<= 20 factors of at most a few hundred each).
+struct BarrierSum {
+  double prod = 1.0, quad = 0.0;
+  __device__ __forceinline__ void add(double h, double delta) {
+    if (h > delta) prod *= h;
+    else { const double z = (h - 2.0 * delta) / delta; quad += -log(delta) + 0.5 * z * z - 0.5; }
+  }
+  __device__ __forceinline__ double value(double mu) const { return mu * (quad - log(prod)); }
+};
+
 // Stage cost (unscaled) and equality-constraint values of one node, one lane = one node (values only).
 __device__ inline void node_values_lane(const double* x, const double* u, const double* xref, const double* swing, int mode,
                                         const double* epos, const double* evel, double& cost, double& eq_sq) {
@@ -202,11 +214,12 @@ __device__ inline void node_values_lane(const double* x, const double* u, const 
   for (int c = 0; c < 4; ++c) if (fl[c]) du[3 * c + 2] -= fz;
   for (int i = 0; i < NU; ++i) { double s = 0.0; for (int j = 0; j < NU; ++j) s += md.R[i * NU + j] * du[j]; cst += 0.5 * du[i] * s; }
   double e2 = 0.0;
+  BarrierSum fric, lpos, lvel, lforce;
   for (int c = 0; c < 4; ++c) {
     if (fl[c]) {
       const double Fx = u[3 * c], Fy = u[3 * c + 1], Fz = u[3 * c + 2];
       const double h = HB_FRICTION_MU * Fz - sqrt(Fx * Fx + Fy * Fy + HB_FRICTION_REGULARIZATION);
-      cst += relaxed_barrier(h, HB_FRICTION_BARRIER_MU, HB_FRICTION_BARRIER_DELTA).v;
+      fric.add(h, HB_FRICTION_BARRIER_DELTA);
       const double e0 = evel[3 * c], e1 = evel[3 * c + 1], e2z = evel[3 * c + 2] + HB_ZEROVEL_Z_GAIN * epos[3 * c + 2] + HB_ZEROVEL_Z_OFFSET;
       e2 += e0 * e0 + e1 * e1 + e2z * e2z;
     } else {
@@ -219,10 +232,11 @@ __device__ inline void node_values_lane(const double* x, const double* u, const 
     }
   }
   for (int j = 0; j < NJ; ++j) {
-    cst += double_sided(x[12 + j], md.joint_lower[j], md.joint_upper[j], HB_LIMIT_POS_MU, HB_LIMIT_POS_DELTA).v;
-    cst += double_sided(u[12 + j], -md.joint_vel_limit[j], md.joint_vel_limit[j], HB_LIMIT_VEL_MU, HB_LIMIT_VEL_DELTA).v;
+    lpos.add(x[12 + j] - md.joint_lower[j], HB_LIMIT_POS_DELTA); lpos.add(md.joint_upper[j] - x[12 + j], HB_LIMIT_POS_DELTA);
+    lvel.add(u[12 + j] + md.joint_vel_limit[j], HB_LIMIT_VEL_DELTA); lvel.add(md.joint_vel_limit[j] - u[12 + j], HB_LIMIT_VEL_DELTA);
   }
-  for (int c = 0; c < 4; ++c) cst += double_sided(u[3 * c + 2], 0.0, HB_LIMIT_FORCE_MAX, HB_LIMIT_FORCE_MU, HB_LIMIT_FORCE_DELTA).v;
+  for (int c = 0; c < 4; ++c) { lforce.add(u[3 * c + 2], HB_LIMIT_FORCE_DELTA); lforce.add(HB_LIMIT_FORCE_MAX - u[3 * c + 2], HB_LIMIT_FORCE_DELTA); }
+  cst += fric.value(HB_FRICTION_BARRIER_MU) + lpos.value(HB_LIMIT_POS_MU) + lvel.value(HB_LIMIT_VEL_MU) + lforce.value(HB_LIMIT_FORCE_MU);
   cost = cst; eq_sq = e2;
 }
 

@@ -276,9 +276,19 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
     if (pass == 0) nwide = nact;
   }
   __syncwarp();
+  // n <= 32: lane = column. Which narrow entries touch this lane's column is fixed for the whole solve: one bit per narrow entry (in
+  // processing order), so the loops below visit the 5 friction rows of a force column instead of testing the span of all 20.
+  const bool colmask = n <= 32 && nact - nwide <= 32;
+  unsigned nmask = 0u;
+  if (colmask && lane < n)
+    for (int q = nwide; q < nact; ++q) { const int j = w.ord[q]; if (lane >= w.in_c0[j] && lane < w.in_c1[j]) nmask |= 1u << (q - nwide); }
   // a = base + sum_j wt[j] A[row_j][i] over the ordered entries (A' times the merged coefficient vector), lane i
   auto at_mul = [&](int i, double a) {
     for (int q = 0; q < nwide; ++q) { const int j = w.ord[q]; a = fma(w.wt[j], A[(size_t)w.in_row[j] * n + i], a); }
+    if (colmask) {          // i == lane; same entries in the same order as the span test below
+      for (unsigned mk = nmask; mk; mk &= mk - 1u) { const int j = w.ord[nwide + __ffs(mk) - 1]; a = fma(w.wt[j], A[(size_t)w.in_row[j] * n + i], a); }
+      return a;
+    }
     for (int q = nwide; q < nact; ++q) {
       const int j = w.ord[q];
       if (i >= w.in_c0[j] && i < w.in_c1[j]) a = fma(w.wt[j], A[(size_t)w.in_row[j] * n + i], a);
@@ -381,7 +391,19 @@ __device__ inline QpResult qp_solve_warp(int n, int m, const double* __restrict_
       }
     }
     __syncwarp();
-    // narrow rows: rank-1 update inside the span, lanes own the columns c <= i
+    // narrow rows: rank-1 update inside the span. n <= 32: lane c owns column c of the lower triangle and walks only the entries that
+    // touch it (no two lanes write the same element, no barrier between entries); otherwise entry by entry, lanes over the columns c <= i
+    if (colmask) {
+      for (unsigned mk = nmask; mk; mk &= mk - 1u) {
+        const int j = w.ord[nwide + __ffs(mk) - 1];
+        const int c1 = w.in_c1[j];
+        const double wj = w.wt[j];
+        const double* a = A + (size_t)w.in_row[j] * n;
+        const double ac = a[lane];
+        for (int i = lane; i < c1; ++i) w.K[i * ldn + lane] += (wj * a[i]) * ac;
+      }
+      __syncwarp();
+    } else
     for (int q = nwide; q < nact; ++q) {
       const int j = w.ord[q];
       const int c0 = w.in_c0[j], c1 = w.in_c1[j];

@@ -50,7 +50,7 @@ static_assert(16 * 9 <= 6 * NDIR + 3 * NDIR + 6 * NDIR, "partial sums must fit i
 // Writes f, compact A rows 3..11 (9x22), Bf rows 3..5 (3x12), Bv rows 6..11 (6x10); with want_ee the contact kinematics record.
 __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const double* xs, int hl, bool act, double* rec_f, double* rec_A, double* rec_Bf,
                                       double* rec_Bv, bool want_ee, double* rec) {
-  const double m = c_model.total_mass;
+  const double m = c_model.total_mass, im = 1.0 / m;   // products with im instead of divisions on the dependent chains
   double* part = sh.dh;       // aliased storage, see LinHalf
   if (hl < NDIR) { double s, c; sincos(xs[9 + hl], &s, &c); sh.sn[hl] = s; sh.cs[hl] = c; }
   __syncwarp();
@@ -101,7 +101,7 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const d
     for (int i = 0; i < 3; ++i) {
       P[i] = part[la * 9 + i]; Lo[i] = part[la * 9 + 3 + i];
       if (hl < 3) { P[i] += part[(3 + hl) * 9 + i]; Lo[i] += part[(3 + hl) * 9 + 3 + i]; }
-      com[i] = (sh.vals[3 + i] + sh.vals[9 + i]) / m;
+      com[i] = (sh.vals[3 + i] + sh.vals[9 + i]) * im;
     }
     sh.Acm[0 * 16 + g] = P[0]; sh.Acm[1 * 16 + g] = P[1]; sh.Acm[2 * 16 + g] = P[2];
     sh.Acm[3 * 16 + g] = Lo[0] - (com[1] * P[2] - com[2] * P[1]);
@@ -172,9 +172,9 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const d
     for (int i = 0; i < 3; ++i) {
       Pd[i] = part[la * 9 + i]; Ld[i] = part[la * 9 + 3 + i]; dc[i] = part[la * 9 + 6 + i];
       if (hl < 3) { Pd[i] += part[(3 + hl) * 9 + i]; Ld[i] += part[(3 + hl) * 9 + 3 + i]; dc[i] += part[(3 + hl) * 9 + 6 + i]; }
-      dc[i] /= m;
+      dc[i] *= im;
       Pv[i] = sh.vals[i] + sh.vals[6 + i];
-      cv[i] = (sh.vals[3 + i] + sh.vals[9 + i]) / m;
+      cv[i] = (sh.vals[3 + i] + sh.vals[9 + i]) * im;
     }
   }
   __syncwarp();     // every partial sum is in registers before dh / dcom overwrite the storage they share
@@ -197,12 +197,12 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const d
     if (i < 3) {
       double s = 0.0;
       for (int c = 0; c < NC; ++c) s += sh.u[3 * c + i];
-      val = s / m - (i == 2 ? HB_GRAVITY : 0.0);
+      val = s * im - (i == 2 ? HB_GRAVITY : 0.0);
     } else if (i < 6) {
       const int a = i - 3, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
       double s = 0.0;
       for (int c = 0; c < NC; ++c) s += (sh.epos[3 * c + a1] - sh.com[a1]) * sh.u[3 * c + a2] - (sh.epos[3 * c + a2] - sh.com[a2]) * sh.u[3 * c + a1];
-      val = s / m;
+      val = s * im;
     } else if (i < 12) val = sh.vgen[i - 6];
     else val = sh.u[i];
     sh.f[i] = val;
@@ -226,7 +226,7 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const d
         const double* F = sh.u + 3 * c;
         t0 += d1 * F[2] - d2 * F[1]; t1 += d2 * F[0] - d0 * F[2]; t2 += d0 * F[1] - d1 * F[0];
       }
-      ca[0] = t0 / m; ca[1] = t1 / m; ca[2] = t2 / m;
+      ca[0] = t0 * im; ca[1] = t1 * im; ca[2] = t2 * im;
 #pragma unroll
       for (int r = 0; r < 6; ++r) ca[3 + r] = sh.dvb[r * NDIR + k];
     }
@@ -235,7 +235,7 @@ __device__ __noinline__ void lin_half(LinHalf& sh, const ChainModel& cm, const d
   }
   if (hl < 12) {
     const int c = hl / 3, a = hl - 3 * c;
-    const double r0 = (sh.epos[3 * c] - sh.com[0]) / m, r1 = (sh.epos[3 * c + 1] - sh.com[1]) / m, r2 = (sh.epos[3 * c + 2] - sh.com[2]) / m;
+    const double r0 = (sh.epos[3 * c] - sh.com[0]) * im, r1 = (sh.epos[3 * c + 1] - sh.com[1]) * im, r2 = (sh.epos[3 * c + 2] - sh.com[2]) * im;
     double b0 = 0.0, b1 = 0.0, b2 = 0.0;   // (r - com) x e_a / m
     if (a == 0) { b1 = r2; b2 = -r1; } else if (a == 1) { b0 = -r2; b2 = r0; } else { b0 = r1; b1 = -r0; }
     rec_Bf[0 * 12 + hl] = b0; rec_Bf[1 * 12 + hl] = b1; rec_Bf[2 * 12 + hl] = b2;
@@ -330,13 +330,6 @@ __global__ void __launch_bounds__(64, HB_LIN_MINB) lin_kernel(SqpArgs a) {
 }
 
 // ---------------------------------------------------------------- K1
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int NKEEP> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
-
 // TMA bulk copies (1-D, cp.async.bulk) completing on an mbarrier: one elected lane arms the barrier with the byte count and issues the
 // copies, every lane waits on the phase bit. Addresses and sizes must be multiples of 16 bytes (the node records are).
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -911,10 +904,8 @@ struct RicShared {
   double HuxT[NX * NTMAX], Huu[NTMAX * 18];
   double sv[NX], sb[NX], hu[NTMAX], kff[NTMAX], idg[NTMAX];
   unsigned long long bar[4];                         // mbarriers of the TMA staging: node inputs (two buffers), Pt^T / Rt, Qt
+  unsigned short pair[NX * (NX - 1) / 2];            // (i << 8 | j), j > i: the strict upper triangle of S, one entry per symmetrisation task
 };
-#ifndef HB_RIC_TMA
-#define HB_RIC_TMA 1     // 1: node records staged with TMA bulk copies + mbarriers; 0: the cp.async (LDGSTS) staging of round 1 (A/B measurements)
-#endif
 static_assert(sizeof(RicNodeIn) % 16 == 0 && (TS * sizeof(double)) % 16 == 0 && (NX * NTMAX * sizeof(double)) % 16 == 0, "bulk copies need 16-byte multiples");
 
 // node inputs by TMA: one elected lane arms the buffer's mbarrier with the byte count and issues six bulk copies (At, Bt, bt, qt, rt, meta)
@@ -929,15 +920,6 @@ __device__ __forceinline__ void ric_prefetch_tma(RicNodeIn& n, const double* __r
   bulk_g2s(n.meta, rec + PJ_META, 8 * sizeof(double), bar);
 }
 
-__device__ __forceinline__ void ric_prefetch(RicNodeIn& n, const double* __restrict__ rec, int lane) {
-  for (int i = 2 * lane; i < TS; i += 64) cp_async16(n.At + i, rec + PJ_AT + i);
-  for (int i = 2 * lane; i < NX * NTMAX; i += 64) cp_async16(n.Bt + i, rec + PJ_BT + i);
-  if (lane < 11) { cp_async16(n.bt + 2 * lane, rec + PJ_BTV + 2 * lane); cp_async16(n.qt + 2 * lane, rec + PJ_QV + 2 * lane); }
-  else if (lane < 19) cp_async16(n.rt + 2 * (lane - 11), rec + PJ_RV + 2 * (lane - 11));
-  else if (lane < 23) cp_async16(n.meta + 2 * (lane - 19), rec + PJ_META + 2 * (lane - 19));
-  cp_async_commit();
-}
-
 // One node of the recursion, executed by the TWO warps of the block. The products that do not depend on each other are split
 // between the warps (by result columns, so that every row-owner product keeps its full lane utilisation); the Cholesky of Huu and
 // the gain solve (one warp, latency bound) overlap with the largest product At' S At of the other warp.
@@ -949,11 +931,7 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
   // ---- phase A: [SA | SB | sb] = S [At | Bt | bt] (+ s): 22 + NTP + 1 result columns, split 16 / rest
   if (warp == 0) {
     rowmm<16, false, 0>(sh.SA, NX, sh.S, NX, in.At, NX, NX, NX);
-#if HB_RIC_TMA
     mbar_wait(&sh.bar[2], ph);                // Pt^T / Rt staged by this warp at the top of the node
-#else
-    cp_async_wait<0>();                       // Pt^T / Rt staged by this warp at the top of the node
-#endif
   } else {
     rowmm<6, false, 0>(sh.SA + 16, NX, sh.S, NX, in.At + 16, NX, NX, NX);
     rowmm<NTP, false, 0>(SB, NTMAX, sh.S, NX, in.Bt, NTMAX, NX, NX);
@@ -969,13 +947,8 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
   if (warp == 0) {
     rowmm<NTP, true, 1>(sh.HuxT, NTMAX, sh.SA, NX, in.Bt, NTMAX, NX, NX);
   } else {
-    // S is dead until phase D: stage Qt into it now (arrives while Huu is formed)
-#if HB_RIC_TMA
+    // S is dead until phase C: stage Qt into it now (arrives while Huu is formed)
     if (lane == 0) { fence_proxy_async(); mbar_expect_tx(&sh.bar[3], TS * sizeof(double)); bulk_g2s(sh.S, rec + PJ_QT, TS * sizeof(double), &sh.bar[3]); }
-#else
-    for (int i = 2 * lane; i < TS; i += 64) cp_async16(sh.S + i, rec + PJ_QT + i);
-    cp_async_commit();
-#endif
     rowmm<NTP, true, 1>(sh.Huu, 18, in.Bt, NTMAX, SB, NTMAX, NTP, NX);
     if (lane < NTP) {
       double s0 = in.rt[lane];
@@ -986,6 +959,8 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
   }
   __syncthreads();
   // ---- phase C: gains (warp 0) || S = Qt + At' SA (warp 1)
+  // (Measured and rejected: factorising Huu in warp 1's phase-B slack and keeping the factor in registers across the barrier -- the
+  // kernel needs 255 registers then, and capped at 7 blocks/SM the factor lives in local memory: 1.72 instead of 1.63 ms.)
   if (warp == 0) {
     // Cholesky of the symmetrised Huu entirely in registers: lane i owns row i (right-looking, column by column, the pivot column is
     // broadcast with shuffles), then forward / backward substitution of the 22 + 1 right-hand sides, one per lane, with the factor
@@ -1041,11 +1016,7 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
       sh.sv[lane] = s0 + s1;
     }
   } else {
-#if HB_RIC_TMA
     mbar_wait(&sh.bar[3], ph);   // Qt has landed in S
-#else
-    cp_async_wait<0>();   // Qt has landed in S (and the next node's inputs, issued by this warp at the top of the node)
-#endif
     __syncwarp();
     rowmm<NX, true, 1>(sh.S, NX, in.At, NX, sh.SA, NX, NX, NX);
   }
@@ -1054,7 +1025,12 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
   if (warp == 0) rowmm<12, false, 1>(sh.S, NX, sh.HuxT, NTMAX, K, NX, NX, NTP);
   else rowmm<10, false, 1>(sh.S + 12, NX, sh.HuxT, NTMAX, K + 12, NX, NX, NTP);
   __syncthreads();
-  for (int idx = threadIdx.x; idx < TS; idx += 64) { const int i = idx / NX, j = idx - i * NX; if (j > i) { const double v = 0.5 * (sh.S[idx] + sh.S[j * NX + i]); sh.S[idx] = v; sh.S[j * NX + i] = v; } }
+  // S <- (S + S') / 2: one (i, j) pair per thread and round, 231 pairs = 4 rounds of 64 threads
+  for (int t = threadIdx.x; t < NX * (NX - 1) / 2; t += 64) {
+    const int pr = sh.pair[t], i = pr >> 8, j = pr & 255;
+    const double v = 0.5 * (sh.S[i * NX + j] + sh.S[j * NX + i]);
+    sh.S[i * NX + j] = v; sh.S[j * NX + i] = v;
+  }
   __syncthreads();
 }
 
@@ -1065,15 +1041,15 @@ __global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
   const double* proj = a.proj + (size_t)inst * a.N * PJ_STRIDE;
   const int N = sqp_nn(a, inst);         // active intervals of this instance; a.N is the stride
   // warp 1 owns the node-input prefetch (and the Qt staging), warp 0 the Pt^T / Rt staging
-#if HB_RIC_TMA
   if (threadIdx.x == 0) { for (int b = 0; b < 4; ++b) mbar_init(&sh.bar[b], 1); }
   __syncthreads();
   if (warp == 1 && lane == 0) ric_prefetch_tma(sh.in[(N - 1) & 1], proj + (size_t)(N - 1) * PJ_STRIDE, &sh.bar[(N - 1) & 1]);
   unsigned ph_in0 = 0u, ph_in1 = 0u;
-#else
-  if (warp == 1) ric_prefetch(sh.in[(N - 1) & 1], proj + (size_t)(N - 1) * PJ_STRIDE, lane);
-#endif
   for (int idx = threadIdx.x; idx < TS; idx += 64) sh.S[idx] = 0.0;   // no terminal cost
+  for (int idx = threadIdx.x; idx < TS; idx += 64) {
+    const int i = idx / NX, j = idx - i * NX;
+    if (j > i) sh.pair[i * NX - i * (i + 1) / 2 + (j - i - 1)] = (unsigned short)((i << 8) | j);
+  }
   if (threadIdx.x < NX) sh.sv[threadIdx.x] = 0.0;
   bool fail = false;
   double merit = 0.0, dyn = 0.0, eqs = 0.0;
@@ -1082,7 +1058,6 @@ __global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
     const double* rec = proj + (size_t)k * PJ_STRIDE;
     double* rk = a.rk + ((size_t)inst * a.N + k) * RK_STRIDE;
     const unsigned ph = (unsigned)(N - 1 - k) & 1u;      // phase of the once-per-node barriers
-#if HB_RIC_TMA
     // every thread waits for the inputs of node k (prefetched one node ahead); the two block barriers that end the previous node already
     // order the re-use of HuxT / Huu / the other input buffer, so no barrier is needed here
     if (k & 1) { mbar_wait(&sh.bar[1], ph_in1); ph_in1 ^= 1u; } else { mbar_wait(&sh.bar[0], ph_in0); ph_in0 ^= 1u; }
@@ -1097,18 +1072,6 @@ __global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
     } else if (k > 0 && lane == 0) {
       ric_prefetch_tma(sh.in[(k - 1) & 1], proj + (size_t)(k - 1) * PJ_STRIDE, &sh.bar[(k - 1) & 1]);
     }
-#else
-    if (warp == 1) cp_async_wait<0>();        // inputs of node k (prefetched one node ahead)
-    __syncthreads();
-    if (warp == 0) {
-      // stage Pt^T -> HuxT (22 x 16) and Rt -> Huu (16 rows of 16, leading dimension 18) for this node
-      for (int i = 2 * lane; i < NX * NTMAX; i += 64) cp_async16(sh.HuxT + i, rec + PJ_PT + i);
-      for (int c = lane; c < NTMAX * 8; c += 32) { const int r = c >> 3, q = c & 7; cp_async16(sh.Huu + r * 18 + 2 * q, rec + PJ_RT + r * NTMAX + 2 * q); }
-      cp_async_commit();
-    } else if (k > 0) {
-      ric_prefetch(sh.in[(k - 1) & 1], proj + (size_t)(k - 1) * PJ_STRIDE, lane);
-    }
-#endif
     const RicNodeIn& in = sh.in[k & 1];
     const int nt = (int)in.meta[0];
     merit += in.meta[3]; dyn += in.meta[4]; eqs += in.meta[5];
@@ -1137,9 +1100,6 @@ struct Fw2Shared {
   double dx[NX], dxn[NX], w[NTMAX];
   unsigned long long bar[2];
 };
-#ifndef HB_FW_TMA
-#define HB_FW_TMA 1      // 1: node data staged with TMA bulk copies + mbarriers; 0: cp.async (LDGSTS) staging of round 1
-#endif
 static_assert(sizeof(FwNode) % 16 == 0 && (NJ * sizeof(double)) % 16 == 0 && (NJ * NX * sizeof(double)) % 16 == 0, "bulk copies need 16-byte multiples");
 
 __device__ __forceinline__ void fw_prefetch_tma(FwNode& n, const double* __restrict__ rec, const double* __restrict__ rk, const double* __restrict__ uk,
@@ -1160,23 +1120,6 @@ __device__ __forceinline__ void fw_prefetch_tma(FwNode& n, const double* __restr
   bulk_g2s(n.u, uk, sizeof(n.u), bar);
 }
 
-__device__ __forceinline__ void fw_prefetch(FwNode& n, const double* __restrict__ rec, const double* __restrict__ rk, const double* __restrict__ uk, int lane) {
-  auto copy = [&](double* dst, const double* src, int ndbl) { for (int i = 2 * lane; i < ndbl; i += 64) cp_async16(dst + i, src + i); };
-  copy(n.At, rec + PJ_AT, TS);
-  copy(n.Bt, rec + PJ_BT, NX * NTMAX);
-  copy(n.K, rk, NTMAX * NX);
-  copy(n.Pxv, rec + PJ_PXV, NJ * NX);
-  copy(n.Nv, rec + PJ_NV, NJ * NVMAX);
-  copy(n.bt, rec + PJ_BTV, NX);
-  copy(n.qt, rec + PJ_QV, NX);
-  copy(n.kff, rk + NTMAX * NX, NTMAX);
-  copy(n.rt, rec + PJ_RV, NTMAX);
-  copy(n.pev, rec + PJ_PEV, NJ);
-  copy(n.meta, rec + PJ_META, 8);
-  copy(n.u, uk, NU);
-  cp_async_commit();
-}
-
 __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int max_trials, void* info_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Fw2Shared& sh = *reinterpret_cast<Fw2Shared*>(smem_raw);
@@ -1191,30 +1134,23 @@ __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int 
   const int32_t* mode = a.mode + (size_t)inst * (NS + 1);
   const double* proj = a.proj + (size_t)inst * NS * PJ_STRIDE;
   const double* rkb = a.rk + (size_t)inst * NS * RK_STRIDE;
-#if HB_FW_TMA
   if (lane == 0) { mbar_init(&sh.bar[0], 1); mbar_init(&sh.bar[1], 1); }
   __syncwarp();
   if (lane == 0) fw_prefetch_tma(sh.nd[0], proj, rkb, ut, &sh.bar[0]);
   unsigned fph0 = 0u, fph1 = 0u;
-#else
-  fw_prefetch(sh.nd[0], proj, rkb, ut, lane);
-#endif
   if (lane < NX) { xt[lane] = a.x0[(size_t)inst * NX + lane]; sh.dx[lane] = 0.0; dxt[lane] = 0.0; }
   double armijo = 0.0;
   bool finite = (a.flags[inst] == 0);
   for (int k = 0; k < N; ++k) {
-#if HB_FW_TMA
     // the other buffer was last read at node k - 1 (the __syncwarp that ends every node orders those reads before the new copies)
     if (k + 1 < N && lane == 0) fw_prefetch_tma(sh.nd[(k + 1) & 1], proj + (size_t)(k + 1) * PJ_STRIDE, rkb + (size_t)(k + 1) * RK_STRIDE, ut + (k + 1) * NU, &sh.bar[(k + 1) & 1]);
     if (k & 1) { mbar_wait(&sh.bar[1], fph1); fph1 ^= 1u; } else { mbar_wait(&sh.bar[0], fph0); fph0 ^= 1u; }
-#else
-    if (k + 1 < N) { fw_prefetch(sh.nd[(k + 1) & 1], proj + (size_t)(k + 1) * PJ_STRIDE, rkb + (size_t)(k + 1) * RK_STRIDE, ut + (k + 1) * NU, lane); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
-    __syncwarp();
-#endif
     const FwNode& nd = sh.nd[k & 1];
     const int nt = (int)nd.meta[0], nf = (int)nd.meta[1], nv = (int)nd.meta[2];
     const int md_k = mode[k];
+    unsigned fmask = 0u;      // stance force coordinates of the node (three bits per stance contact)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if (contact_flag(md_k, c)) fmask |= 7u << (3 * c);
     double arm = 0.0;
     if (lane < nt) {
       double s = nd.kff[lane];
@@ -1236,7 +1172,7 @@ __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int 
       // du: stance forces are free variables, swing forces go to zero, vj from the projection
       double du;
       if (lane < 12) {
-        if (contact_flag(md_k, lane / 3)) { int c = 0; for (int j = 0; j < lane; ++j) c += contact_flag(md_k, j / 3); du = sh.w[c]; }
+        if (contact_flag(md_k, lane / 3)) du = sh.w[__popc(fmask & ((1u << lane) - 1u))];      // index among the stance force coordinates
         else du = -nd.u[lane];
       } else {
         const int i = lane - 12;
