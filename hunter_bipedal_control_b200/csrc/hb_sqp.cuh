@@ -700,12 +700,12 @@ __device__ __forceinline__ void lq_node(LqShared& sh, const SqpArgs& a, int inst
   }
   __syncwarp();
   // ---- M = T' Rb T + YZ' (w YZ), row by row (rows come in pairs with 128-bit broadcast loads); lane = column:
-  //   lanes 0..21 : rows 0..21 -> Qt, row 30 -> qt          lanes 22..29 : rows 0..21 -> Pt^T, rows 22..29 -> Rt (null block), row 30 -> rt
+  //   lanes 0..21 : rows 0..21 -> Qt, row 30 -> qt          lanes 22..29 : rows 0..21 -> Pt (stored input-major, NTMAX x 22), rows 22..29 -> Rt (null block), row 30 -> rt
   const double Qd_l = (lane < NX) ? sh.Qd[lane] : 0.0;
   auto m_store = [&](int i, double s) {
     if (i < NX) {
       if (lane < NX) out[PJ_QT + i * NX + lane] = dt * (s + ((i == lane) ? Qd_l : 0.0));
-      else if (nlane) out[PJ_PT + i * NTMAX + NF + cc] = dt * s;
+      else if (nlane) out[PJ_PT + (NF + cc) * NX + i] = dt * s;
     } else if (i < NX + NVMAX) {
       if (nlane && i - NX < nv) out[PJ_RT + (NF + i - NX) * NTMAX + NF + cc] = dt * s;
     } else {
@@ -788,7 +788,7 @@ __device__ __forceinline__ void lq_node(LqShared& sh, const SqpArgs& a, int inst
     for (int i = 0; i < NJ; ++i) out[PJ_BT + (12 + i) * NTMAX + col] = nlane ? dt * tc[i] : 0.0;
     if (!nlane) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) out[PJ_PT + i * NTMAX + col] = 0.0;
+      for (int i = 0; i < NX; ++i) out[PJ_PT + col * NX + i] = 0.0;
       out[PJ_RV + col] = fcol ? dt * sh.r[sj] : 0.0;
     }
     // Rt column: stance-force block (3x3 per contact), identity on the padded diagonal, zeros between the blocks
@@ -870,14 +870,16 @@ __global__ void __launch_bounds__(32, HB_LQ_MINB) lq_kernel(SqpArgs a) {
 // broadcast loads (two doubles per load), N accumulators stay in registers. NTP = number of free inputs padded to an even
 // compile-time size (6 flight, 10 single support, 12 stance, 16 degenerate); the padded rows/columns of the projected model
 // are zero (identity on the diagonal of R~), so the padded gains are zero.
-template <int N, bool TA, int MODE>
+// TC: the result is stored transposed (C[j * ldc + i]): lanes then touch consecutive addresses -- the layout of choice whenever the
+// row-major leading dimension would be a multiple of 16 doubles (every lane in the same bank).
+template <int N, bool TA, int MODE, bool TC = false>
 __device__ __forceinline__ void rowmm(double* __restrict__ C, int ldc, const double* __restrict__ A, int lda,
                                       const double* __restrict__ B, int ldb, int m, int kdim) {
   const int i = lane_id();
   if (i < m) {
     double c[N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) c[j] = (MODE == 1) ? C[i * ldc + j] : 0.0;
+    for (int j = 0; j < N; ++j) c[j] = (MODE == 1) ? (TC ? C[j * ldc + i] : C[i * ldc + j]) : 0.0;
 #pragma unroll 2
     for (int k = 0; k < kdim; ++k) {
       const double a = TA ? A[k * lda + i] : A[i * lda + k];
@@ -890,20 +892,21 @@ __device__ __forceinline__ void rowmm(double* __restrict__ C, int ldc, const dou
       }
     }
 #pragma unroll
-    for (int j = 0; j < N; ++j) C[i * ldc + j] = c[j];
+    for (int j = 0; j < N; ++j) { if (TC) C[j * ldc + i] = c[j]; else C[i * ldc + j] = c[j]; }
   }
   __syncwarp();
 }
 
 
+constexpr int SB_LD = 18;
 struct RicNodeIn { double At[TS], Bt[NX * NTMAX], bt[NX], qt[NX], rt[NTMAX], meta[8]; };
 struct RicShared {
   double S[TS], SA[TS];
   RicNodeIn in[2];                                   // node data, staged one node ahead with cp.async
-  double SBK[NX * NTMAX];                            // SB (22 x NTMAX), later K (NTMAX x 22)
-  double HuxT[NX * NTMAX], Huu[NTMAX * 18];
+  double SBK[NX * SB_LD];                            // SB (22 x NTP, leading dimension 18: 2-way instead of 16-way bank conflicts on the row-owner stores), later K (NTMAX x 22)
+  double Hux[NTMAX * NX], Huu[NTMAX * 18];           // Hux input-major (NTMAX x 22): lanes = state index touch consecutive addresses
   double sv[NX], sb[NX], hu[NTMAX], kff[NTMAX], idg[NTMAX];
-  unsigned long long bar[4];                         // mbarriers of the TMA staging: node inputs (two buffers), Pt^T / Rt, Qt
+  unsigned long long bar[4];                         // mbarriers of the TMA staging: node inputs (two buffers), Pt / Rt, Qt
   unsigned short pair[NX * (NX - 1) / 2];            // (i << 8 | j), j > i: the strict upper triangle of S, one entry per symmetrisation task
 };
 static_assert(sizeof(RicNodeIn) % 16 == 0 && (TS * sizeof(double)) % 16 == 0 && (NX * NTMAX * sizeof(double)) % 16 == 0, "bulk copies need 16-byte multiples");
@@ -931,10 +934,10 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
   // ---- phase A: [SA | SB | sb] = S [At | Bt | bt] (+ s): 22 + NTP + 1 result columns, split 16 / rest
   if (warp == 0) {
     rowmm<16, false, 0>(sh.SA, NX, sh.S, NX, in.At, NX, NX, NX);
-    mbar_wait(&sh.bar[2], ph);                // Pt^T / Rt staged by this warp at the top of the node
+    mbar_wait(&sh.bar[2], ph);                // Pt / Rt staged by this warp at the top of the node
   } else {
     rowmm<6, false, 0>(sh.SA + 16, NX, sh.S, NX, in.At + 16, NX, NX, NX);
-    rowmm<NTP, false, 0>(SB, NTMAX, sh.S, NX, in.Bt, NTMAX, NX, NX);
+    rowmm<NTP, false, 0>(SB, SB_LD, sh.S, NX, in.Bt, NTMAX, NX, NX);
     if (lane < NX) {
       double s0 = sh.sv[lane], s1 = 0.0;
 #pragma unroll
@@ -943,13 +946,13 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
     }
   }
   __syncthreads();
-  // ---- phase B: Hux^T (22 x NTP) = Pt^T + SA^T Bt (warp 0) ; Huu = Rt + Bt^T SB, hu = rt + Bt^T sb (warp 1)
+  // ---- phase B: Hux (NTP x 22, stored input-major) = Pt + Bt^T SA (warp 0: row-owner over the state index, transposed store) ; Huu = Rt + Bt^T SB, hu = rt + Bt^T sb (warp 1)
   if (warp == 0) {
-    rowmm<NTP, true, 1>(sh.HuxT, NTMAX, sh.SA, NX, in.Bt, NTMAX, NX, NX);
+    rowmm<NTP, true, 1, true>(sh.Hux, NX, sh.SA, NX, in.Bt, NTMAX, NX, NX);
   } else {
     // S is dead until phase C: stage Qt into it now (arrives while Huu is formed)
     if (lane == 0) { fence_proxy_async(); mbar_expect_tx(&sh.bar[3], TS * sizeof(double)); bulk_g2s(sh.S, rec + PJ_QT, TS * sizeof(double), &sh.bar[3]); }
-    rowmm<NTP, true, 1>(sh.Huu, 18, in.Bt, NTMAX, SB, NTMAX, NTP, NX);
+    rowmm<NTP, true, 1>(sh.Huu, 18, in.Bt, NTMAX, SB, SB_LD, NTP, NX);
     if (lane < NTP) {
       double s0 = in.rt[lane];
 #pragma unroll
@@ -982,7 +985,7 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
       }
       double col[NTP], y[NTP];
 #pragma unroll
-      for (int c = 0; c < NTP; ++c) col[c] = (lane < NX) ? sh.HuxT[lane * NTMAX + c] : ((lane == NX) ? sh.hu[c] : 0.0);
+      for (int c = 0; c < NTP; ++c) col[c] = (lane < NX) ? sh.Hux[c * NX + lane] : ((lane == NX) ? sh.hu[c] : 0.0);
 #pragma unroll
       for (int c = 0; c < NTP; ++c) {
         double sacc = col[c];
@@ -1012,7 +1015,7 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
 #pragma unroll
       for (int k = 0; k < NX; k += 2) { s0 = fma(in.At[k * NX + lane], sh.sb[k], s0); s1 = fma(in.At[(k + 1) * NX + lane], sh.sb[k + 1], s1); }
 #pragma unroll
-      for (int c = 0; c < NTP; ++c) s0 = fma(sh.HuxT[lane * NTMAX + c], sh.kff[c], s0);
+      for (int c = 0; c < NTP; ++c) s0 = fma(sh.Hux[c * NX + lane], sh.kff[c], s0);
       sh.sv[lane] = s0 + s1;
     }
   } else {
@@ -1022,8 +1025,8 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
   }
   __syncthreads();
   // ---- phase D: S += Hux' K, result columns split 12 / 10
-  if (warp == 0) rowmm<12, false, 1>(sh.S, NX, sh.HuxT, NTMAX, K, NX, NX, NTP);
-  else rowmm<10, false, 1>(sh.S + 12, NX, sh.HuxT, NTMAX, K + 12, NX, NX, NTP);
+  if (warp == 0) rowmm<12, true, 1>(sh.S, NX, sh.Hux, NX, K, NX, NX, NTP);
+  else rowmm<10, true, 1>(sh.S + 12, NX, sh.Hux, NX, K + 12, NX, NX, NTP);
   __syncthreads();
   // S <- (S + S') / 2: one (i, j) pair per thread and round, 231 pairs = 4 rounds of 64 threads
   for (int t = threadIdx.x; t < NX * (NX - 1) / 2; t += 64) {
@@ -1040,7 +1043,7 @@ __global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
   const int inst = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double* proj = a.proj + (size_t)inst * a.N * PJ_STRIDE;
   const int N = sqp_nn(a, inst);         // active intervals of this instance; a.N is the stride
-  // warp 1 owns the node-input prefetch (and the Qt staging), warp 0 the Pt^T / Rt staging
+  // warp 1 owns the node-input prefetch (and the Qt staging), warp 0 the Pt / Rt staging
   if (threadIdx.x == 0) { for (int b = 0; b < 4; ++b) mbar_init(&sh.bar[b], 1); }
   __syncthreads();
   if (warp == 1 && lane == 0) ric_prefetch_tma(sh.in[(N - 1) & 1], proj + (size_t)(N - 1) * PJ_STRIDE, &sh.bar[(N - 1) & 1]);
@@ -1059,14 +1062,14 @@ __global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
     double* rk = a.rk + ((size_t)inst * a.N + k) * RK_STRIDE;
     const unsigned ph = (unsigned)(N - 1 - k) & 1u;      // phase of the once-per-node barriers
     // every thread waits for the inputs of node k (prefetched one node ahead); the two block barriers that end the previous node already
-    // order the re-use of HuxT / Huu / the other input buffer, so no barrier is needed here
+    // order the re-use of Hux / Huu / the other input buffer, so no barrier is needed here
     if (k & 1) { mbar_wait(&sh.bar[1], ph_in1); ph_in1 ^= 1u; } else { mbar_wait(&sh.bar[0], ph_in0); ph_in0 ^= 1u; }
     if (warp == 0) {
       if (lane == 0) {
-        // Pt^T -> HuxT (22 x 16, contiguous) and Rt -> Huu (16 rows of 16 doubles, leading dimension 18): 1 + 16 bulk copies on one mbarrier
+        // Pt -> Hux (16 x 22, contiguous) and Rt -> Huu (16 rows of 16 doubles, leading dimension 18): 1 + 16 bulk copies on one mbarrier
         fence_proxy_async();
         mbar_expect_tx(&sh.bar[2], (unsigned)((NX * NTMAX + NTMAX * NTMAX) * sizeof(double)));
-        bulk_g2s(sh.HuxT, rec + PJ_PT, NX * NTMAX * sizeof(double), &sh.bar[2]);
+        bulk_g2s(sh.Hux, rec + PJ_PT, NX * NTMAX * sizeof(double), &sh.bar[2]);
         for (int r = 0; r < NTMAX; ++r) bulk_g2s(sh.Huu + r * 18, rec + PJ_RT + r * NTMAX, NTMAX * sizeof(double), &sh.bar[2]);
       }
     } else if (k > 0 && lane == 0) {
