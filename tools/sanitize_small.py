@@ -51,5 +51,23 @@ print("observer finite", np.isfinite(est).all(), "plant finite", np.isfinite(nxt
 hs, hst = ctx.hierarchical_wbc_solve(xd, ud, rbd, md)
 H, gq, A, lb, ub, m = ctx.wbc_assemble(xd, ud, rbd, md)
 print("hierarchical WBC status", hst, "rows", m)
+# pinned reference array: zero-copy gather + validation on the device; shard gather (world 1: pack + compaction kernels).
+# Buffers come straight from the CUDA runtime and are released again (torch's caching allocators would show up as leaks in the memcheck log).
+import ctypes as C
+from cuda.bindings import runtime as cudart
+from hunter_bipedal_control_b200 import sharding
+nbytes = C.sizeof(refs)
+err, hptr = cudart.cudaHostAlloc(nbytes, 0); assert int(err) == 0
+C.memmove(hptr, C.addressof(refs), nbytes)
+info, sol, tau, st = ctx.resident_cycle(True, 0.002, np.zeros(B), x0, C.cast(C.c_void_p(hptr), C.POINTER(hb.HbReference)), rbd)
+shard = sharding.Shard(ctx, None, 1, 0, B, max_row_doubles=10)
+err, dptr = cudart.cudaMalloc(tau.nbytes); assert int(err) == 0
+err, = cudart.cudaMemcpy(dptr, tau.ctypes.data, tau.nbytes, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice); assert int(err) == 0
+out = C.c_void_p()
+hb.api._check(ctx._lib.hb_shard_gather_dev(shard._h, 10, C.c_void_p(dptr), None, C.byref(out)), "hb_shard_gather_dev", ctx._h)
+shard.wait(block_host=True)
+print("pinned cycle status", st, "gather equal", np.array_equal(shard.to_host(out.value, 10), tau))
+shard.close()
+cudart.cudaFree(dptr); cudart.cudaFreeHost(hptr)
 ev.close(); ctx.close()
 print("contexts closed")
