@@ -1094,8 +1094,10 @@ __global__ void __launch_bounds__(64) riccati_kernel(SqpArgs a) {
 
 // ---------------------------------------------------------------- K3: forward pass + filter line search
 // per-node data of the forward pass, double-buffered and filled with cp.async (16-byte LDGSTS) one node ahead
+// Of A~ and B~ the forward pass loads rows 3..11 only: rows 0..2 are the identity plus dt/m on the stance-force coordinates, rows 12..21 are
+// I + dt P_xv and dt N_v, and P_xv / N_v are loaded anyway for the input step (8.9 KB per node instead of 12.8 KB; this kernel runs at half of HBM).
 struct FwNode {
-  double At[TS], Bt[NX * NTMAX], K[NTMAX * NX], Pxv[NJ * NX], Nv[NJ * NVMAX];
+  double At9[9 * NX], Bt9[9 * NTMAX], K[NTMAX * NX], Pxv[NJ * NX], Nv[NJ * NVMAX];
   double bt[NX], qt[NX], kff[NTMAX], rt[NTMAX], pev[NJ], meta[8], u[NU];
 };
 struct Fw2Shared {
@@ -1109,8 +1111,8 @@ __device__ __forceinline__ void fw_prefetch_tma(FwNode& n, const double* __restr
                                                 unsigned long long* bar) {
   fence_proxy_async();
   mbar_expect_tx(bar, (unsigned)sizeof(FwNode));
-  bulk_g2s(n.At, rec + PJ_AT, sizeof(n.At), bar);
-  bulk_g2s(n.Bt, rec + PJ_BT, sizeof(n.Bt), bar);
+  bulk_g2s(n.At9, rec + PJ_AT + 3 * NX, sizeof(n.At9), bar);
+  bulk_g2s(n.Bt9, rec + PJ_BT + 3 * NTMAX, sizeof(n.Bt9), bar);
   bulk_g2s(n.K, rk, sizeof(n.K), bar);
   bulk_g2s(n.Pxv, rec + PJ_PXV, sizeof(n.Pxv), bar);
   bulk_g2s(n.Nv, rec + PJ_NV, sizeof(n.Nv), bar);
@@ -1144,6 +1146,7 @@ __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int 
   if (lane < NX) { xt[lane] = a.x0[(size_t)inst * NX + lane]; sh.dx[lane] = 0.0; dxt[lane] = 0.0; }
   double armijo = 0.0;
   bool finite = (a.flags[inst] == 0);
+  const double im_mass = 1.0 / c_model.total_mass;
   for (int k = 0; k < N; ++k) {
     // the other buffer was last read at node k - 1 (the __syncwarp that ends every node orders those reads before the new copies)
     if (k + 1 < N && lane == 0) fw_prefetch_tma(sh.nd[(k + 1) & 1], proj + (size_t)(k + 1) * PJ_STRIDE, rkb + (size_t)(k + 1) * RK_STRIDE, ut + (k + 1) * NU, &sh.bar[(k + 1) & 1]);
@@ -1151,6 +1154,7 @@ __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int 
     const FwNode& nd = sh.nd[k & 1];
     const int nt = (int)nd.meta[0], nf = (int)nd.meta[1], nv = (int)nd.meta[2];
     const int md_k = mode[k];
+    const double dtk = sqp_dt(a, inst, k);
     unsigned fmask = 0u;      // stance force coordinates of the node (three bits per stance contact)
 #pragma unroll
     for (int c = 0; c < 4; ++c) if (contact_flag(md_k, c)) fmask |= 7u << (3 * c);
@@ -1164,14 +1168,6 @@ __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int 
     }
     __syncwarp();
     if (lane < NX) {
-      double s = nd.bt[lane], s1 = 0.0;
-#pragma unroll
-      for (int j = 0; j < NX; j += 2) { s = fma(nd.At[lane * NX + j], sh.dx[j], s); s1 = fma(nd.At[lane * NX + j + 1], sh.dx[j + 1], s1); }
-      s += s1;
-      for (int c = 0; c < nt; ++c) s = fma(nd.Bt[lane * NTMAX + c], sh.w[c], s);
-      sh.dxn[lane] = s;
-      dxt[(k + 1) * NX + lane] = s;
-      arm += nd.qt[lane] * sh.dx[lane];
       // du: stance forces are free variables, swing forces go to zero, vj from the projection
       double du;
       if (lane < 12) {
@@ -1184,6 +1180,27 @@ __global__ void __launch_bounds__(32) forward_linesearch2_kernel(SqpArgs a, int 
         for (int j = 0; j < NX; ++j) du = fma(nd.Pxv[i * NX + j], sh.dx[j], du);
         for (int c = 0; c < nv; ++c) du = fma(nd.Nv[i * NVMAX + c], sh.w[nf + c], du);
       }
+      // dx' = A~ dx + B~ w + b~ by row class
+      double s = nd.bt[lane];
+      if (lane >= 3 && lane < 12) {
+        const double* ar = nd.At9 + (lane - 3) * NX;
+        const double* br = nd.Bt9 + (lane - 3) * NTMAX;
+        double s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; j += 2) { s = fma(ar[j], sh.dx[j], s); s1 = fma(ar[j + 1], sh.dx[j + 1], s1); }
+        s += s1;
+        for (int c = 0; c < nt; ++c) s = fma(br[c], sh.w[c], s);
+      } else if (lane < 3) {
+        double fsum = 0.0;      // linear momentum rate: sum of the stance-force steps along this axis
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (contact_flag(md_k, c)) fsum += sh.w[__popc(fmask & ((1u << (3 * c + lane)) - 1u))];
+        s += sh.dx[lane] + (dtk * im_mass) * fsum;
+      } else {
+        s += sh.dx[lane] + dtk * (du - nd.pev[lane - 12]);      // rows I + dt P_xv | dt N_v: dt times the joint-velocity step without its affine part
+      }
+      sh.dxn[lane] = s;
+      dxt[(k + 1) * NX + lane] = s;
+      arm += nd.qt[lane] * sh.dx[lane];
       dut[k * NU + lane] = du;
       if (!isfinite(s) || !isfinite(du)) finite = false;
     }
