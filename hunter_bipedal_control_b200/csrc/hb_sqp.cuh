@@ -931,17 +931,18 @@ __device__ __noinline__ void riccati_node(RicShared& sh, const RicNodeIn& in, co
                                           int warp, unsigned ph) {
   const int lane = lane_id();
   double* SB = sh.SBK; double* K = sh.SBK;
-  // ---- phase A: [SA | SB | sb] = S [At | Bt | bt] (+ s): 22 + NTP + 1 result columns, split 16 / rest
+  // ---- phase A: [SA | SB | sb] = S [At | Bt | bt] (+ s): 22 + NTP + 1 result columns, split 16 / rest. S is exactly symmetric (both halves
+  // are written with the same value at the end of every node), so lane i reads its row as column i: consecutive addresses, no bank conflicts
   if (warp == 0) {
-    rowmm<16, false, 0>(sh.SA, NX, sh.S, NX, in.At, NX, NX, NX);
+    rowmm<16, true, 0>(sh.SA, NX, sh.S, NX, in.At, NX, NX, NX);
     mbar_wait(&sh.bar[2], ph);                // Pt / Rt staged by this warp at the top of the node
   } else {
-    rowmm<6, false, 0>(sh.SA + 16, NX, sh.S, NX, in.At + 16, NX, NX, NX);
-    rowmm<NTP, false, 0>(SB, SB_LD, sh.S, NX, in.Bt, NTMAX, NX, NX);
+    rowmm<6, true, 0>(sh.SA + 16, NX, sh.S, NX, in.At + 16, NX, NX, NX);
+    rowmm<NTP, true, 0>(SB, SB_LD, sh.S, NX, in.Bt, NTMAX, NX, NX);
     if (lane < NX) {
       double s0 = sh.sv[lane], s1 = 0.0;
 #pragma unroll
-      for (int k = 0; k < NX; k += 2) { s0 = fma(sh.S[lane * NX + k], in.bt[k], s0); s1 = fma(sh.S[lane * NX + k + 1], in.bt[k + 1], s1); }
+      for (int k = 0; k < NX; k += 2) { s0 = fma(sh.S[k * NX + lane], in.bt[k], s0); s1 = fma(sh.S[(k + 1) * NX + lane], in.bt[k + 1], s1); }
       sh.sb[lane] = s0 + s1;
     }
   }
