@@ -345,6 +345,10 @@ int hb_control_step_batch(hb_ctx* ctx, int B, double t_rel, const double* x0, co
 int hb_joint_command_batch(hb_ctx* ctx, int B, const hb_pd_gains* gains, double period, const double* x_des, const double* u_des,
                            const double* wbc_sol, const int32_t* mode_cmd, const double* rbd, const uint8_t* loaded, uint8_t* estop,
                            double* command, double* output_torque);
+/* Host-pointer resident cycle. Only the USED entries of the fixed-capacity hb_reference structs cross PCIe. If `refs` points into page-locked
+ * memory (cudaHostAlloc / cudaHostRegister; the whole array refs[0..B) must lie inside that allocation) the device gathers and validates the
+ * entries itself and the call does no per-instance host work; a pageable array is validated and packed on the host first. Malformed structs
+ * (counts beyond the capacities, unordered times, an empty target list, modes outside 0..3) return -1 on both paths. */
 int hb_resident_cycle_batch(hb_ctx* ctx, int B, int cold_start, double t_rel, const double* t0, const double* x0, const hb_reference* refs,
                             const double* rbd, hb_solve_info* info, double* wbc_sol, double* torque, int32_t* wbc_status);
 int hb_resident_read_batch(hb_ctx* ctx, int B, double* t0 /*nullable*/, double* x_traj /*nullable*/, double* u_traj /*nullable*/);

@@ -204,3 +204,16 @@ def test_native_shard_helpers_match_python_mirror():
     assert np.array_equal(p, p2) and np.array_equal(i, i2)
     srt = mode[p]
     assert all(tuple(srt[k]) <= tuple(srt[k + 1]) for k in range(len(srt) - 1))
+
+
+def test_model_constants_header_regenerates_from_the_reference_files_when_present(tmp_path):
+    """include/hunter_model_constants.h (inertias, joint tree and limits from hunter.urdf; MPC / WBC weights and gains from task.info; default
+    joint state and gait templates from reference.info) is generated, not written by hand: regenerating it from the reference tree gives the
+    committed bytes (build container only; the GPU box has no reference tree)."""
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "legged_controllers/config/hunter/task.info")):
+        pytest.skip("reference tree not present")
+    out = tmp_path / "hunter_model_constants.h"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_model.py"), ref, str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert out.read_bytes() == open(os.path.join(ROOT, "include", "hunter_model_constants.h"), "rb").read()

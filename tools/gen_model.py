@@ -20,7 +20,7 @@ REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 URDF = os.path.join(REF, "legged_examples/legged_hunter/legged_hunter_description/urdf/hunter.urdf")
 TASK = os.path.join(REF, "legged_controllers/config/hunter/task.info")
 REFI = os.path.join(REF, "legged_controllers/config/hunter/reference.info")
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "hunter_model_constants.h")
+OUT = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "hunter_model_constants.h")
 
 JOINTS = ["leg_l1_joint", "leg_l2_joint", "leg_l3_joint", "leg_l4_joint", "leg_l5_joint",
           "leg_r1_joint", "leg_r2_joint", "leg_r3_joint", "leg_r4_joint", "leg_r5_joint"]  # ModelSettings.h:59-60
