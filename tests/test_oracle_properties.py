@@ -50,3 +50,32 @@ def test_wbc_solution_satisfies_reference_constraints(oracle, seed, mode):
     for c in range(4):
         if not fl[c]:
             assert np.abs(sol[16 + 3 * c:19 + 3 * c]).max() < 1e-8
+
+
+def test_event_time_grid_restatement_properties():
+    """scenarios.event_time_grid is the numpy side of row S1's parity test (ocs2::timeDiscretizationWithEvents with the event node pair collapsed):
+    first node t0, last node t0 + T, strictly increasing, no step longer than dt, every mode switch strictly inside the horizon is a node, the grid
+    re-anchors at a switch (the step after it is a full dt again), the uniform case is reproduced, and the capacity is respected."""
+    from hunter_bipedal_control_b200 import scenarios as sc
+    rng = np.random.default_rng(12)
+    dt, T = 0.015, 0.8
+    for trial in range(200):
+        t0 = float(rng.uniform(0.0, 1.0))
+        ev = np.sort(rng.uniform(t0 - 0.2, t0 + T + 0.2, rng.integers(0, 9)))
+        g = sc.event_time_grid(t0, T, dt, list(ev), 96)
+        assert g[0] == t0 and abs(g[-1] - (t0 + T)) < 1e-12
+        d = np.diff(g)
+        assert (d > 1e-9).all() and (d < dt + 1e-12).all()
+        inside = [e for e in ev if t0 + 1e-9 < e < t0 + T - 1e-9]
+        for e in inside:
+            k = int(np.argmin(np.abs(g - e)))
+            assert abs(g[k] - e) < 1e-12
+            if k + 1 < len(g) - 1 and not any(abs(g[k + 1] - f) < 1e-12 for f in inside):
+                assert abs(g[k + 1] - g[k] - dt) < 1e-12            # re-anchored: a full step follows the event node
+        assert len(g) - 1 <= int(np.ceil(T / dt)) + len(inside) + 1
+    # no events: the uniform grid (0.8 / 0.015 is not an integer: the last interval is the remainder)
+    g = sc.event_time_grid(0.0, T, dt, [], 96)
+    assert len(g) == 55 and np.allclose(np.diff(g)[:-1], dt) and abs(g[-1] - T) < 1e-12
+    # capacity exhausted: the last interval is stretched to the final time, the node count stays within the capacity
+    g = sc.event_time_grid(0.0, T, dt, [0.1003, 0.2007, 0.3001], 40)
+    assert len(g) - 1 == 40 and abs(g[-1] - T) < 1e-12 and (np.diff(g) > 0).all()
