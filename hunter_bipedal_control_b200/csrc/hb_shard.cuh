@@ -73,6 +73,7 @@ __global__ void shard_compact_kernel(int total, int world, int nmax, int row, co
 
 struct hb_shard {
   hb_ctx* ctx = nullptr;
+  int device = 0;                          // kept separately: hb_shard_destroy must not touch a context that was destroyed first
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0, total = 0, lo = 0, n = 0, nmax = 0, max_row = 0;
   cudaStream_t stream = nullptr;           // the gather runs here
@@ -115,7 +116,7 @@ int hb_shard_unique_id(void* id) {
 
 int hb_shard_destroy(hb_shard* s) {
   if (!s) return HB_OK;
-  if (s->ctx) cudaSetDevice(s->ctx->device);
+  cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->comm) nccl_api().CommDestroy(s->comm);
   for (int i = 0; i < 2; ++i) { if (s->send[i]) cudaFree(s->send[i]); if (s->out[i]) cudaFree(s->out[i]); }
@@ -132,7 +133,7 @@ int hb_shard_create(hb_ctx* ctx, const void* id, int world, int rank, int total_
   if (set_device(ctx)) return HB_ECUDA;
   hb_shard* s = new (std::nothrow) hb_shard();
   if (!s) return HB_ENOMEM;
-  s->ctx = ctx; s->world = world; s->rank = rank; s->total = total_instances; s->max_row = max_row_doubles;
+  s->ctx = ctx; s->device = ctx->device; s->world = world; s->rank = rank; s->total = total_instances; s->max_row = max_row_doubles;
   shard_block(total_instances, world, rank, &s->lo, &s->n);
   s->nmax = (total_instances + world - 1) / world;
   bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess &&
